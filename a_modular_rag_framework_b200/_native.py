@@ -1,0 +1,91 @@
+"""ctypes binding of libb200r.so -- the only way the package reaches the GPU.
+
+There is no CPU fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+
+from . import build as _build
+
+BF16, F16, F32, I8 = 0, 1, 2, 3
+IP, COS = 0, 1
+PATH_AUTO, PATH_GEMM, PATH_SCAN = 0, 1, 2
+MAX_K = 2048
+EOVERFLOW = -4
+
+#: every symbol include/b200r.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "b200r_version", "b200r_last_error", "b200r_launch_count",
+    "b200r_index_create", "b200r_index_destroy", "b200r_index_info",
+    "b200r_search_workspace_bytes", "b200r_search", "b200r_search_host",
+    "b200r_merge_topk",
+    "b200r_graph_create", "b200r_graph_destroy",
+    "b200r_expand_max_candidates", "b200r_expand_rescore",
+]
+
+
+class B200RError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libb200r error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) the in-tree shared library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise B200RError(-2, f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             f"(needs nvcc); there is no CPU fallback")
+    lib = ctypes.CDLL(path)
+    lib.b200r_version.restype = c_int
+    lib.b200r_last_error.argtypes = [c_char_p, c_size_t]
+    lib.b200r_last_error.restype = c_int
+    lib.b200r_launch_count.restype = c_int64
+    lib.b200r_index_create.argtypes = [c_int, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p, POINTER(c_uint64)]
+    lib.b200r_index_destroy.argtypes = [c_uint64]
+    lib.b200r_index_info.argtypes = [c_uint64, POINTER(c_int64), POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int64)]
+    lib.b200r_search_workspace_bytes.argtypes = [c_uint64, c_int32, c_int32, c_int32]
+    lib.b200r_search_workspace_bytes.restype = c_size_t
+    lib.b200r_search.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.b200r_search_host.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.b200r_merge_topk.argtypes = [c_int, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.b200r_graph_create.argtypes = [c_int, c_void_p, c_void_p, c_int64, c_int64, POINTER(c_uint64)]
+    lib.b200r_graph_destroy.argtypes = [c_uint64]
+    lib.b200r_expand_max_candidates.restype = c_int32
+    lib.b200r_expand_rescore.argtypes = [c_uint64, c_uint64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_int32,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is c_int and name not in ("b200r_version", "b200r_last_error"):
+            fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    buf = ctypes.create_string_buffer(512)
+    load().b200r_last_error(buf, 512)
+    return buf.value.decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise B200RError(rc, last_error())
+
+
+def launch_count() -> int:
+    return int(load().b200r_launch_count())

@@ -1,0 +1,350 @@
+// api.cu -- the C ABI of libb200r.so (declared in include/b200r.h): handles, planning, dispatch.
+#include "internal.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <new>
+
+namespace b200r {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int gemm_tile_rows();
+int gemm_tile_queries();
+int32_t expand_max_candidates();
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda dependency
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_tmap_2d(CUtensorMap* tm, int dtype, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) {
+      set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+      return B200R_ECUDA;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {inner * 2};  // bytes; bf16/f16 only
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = (dtype == B200R_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (base=%p inner=%llu outer=%llu)", (int)r, base,
+              (unsigned long long)inner, (unsigned long long)outer);
+    return B200R_ECUDA;
+  }
+  return B200R_OK;
+}
+
+static Index* get_index(uint64_t h) {
+  Index* ix = reinterpret_cast<Index*>(h);
+  if (!ix || ix->magic != kIndexMagic) { set_error("bad index handle"); return nullptr; }
+  return ix;
+}
+static Graph* get_graph(uint64_t h) {
+  Graph* g = reinterpret_cast<Graph*>(h);
+  if (!g || g->magic != kGraphMagic) { set_error("bad graph handle"); return nullptr; }
+  return g;
+}
+
+int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
+  if (B <= 0) { set_error("B must be > 0 (got %d)", B); return B200R_EINVAL; }
+  if (k <= 0 || k > B200R_MAX_K) { set_error("k must be in [1, %d] (got %d)", B200R_MAX_K, k); return B200R_EINVAL; }
+  const bool gemm_ok = ix->has_tmap;
+  if (path == B200R_PATH_AUTO) path = (gemm_ok && B > 4) ? B200R_PATH_GEMM : B200R_PATH_SCAN;
+  if (path == B200R_PATH_GEMM && !gemm_ok) {
+    set_error("gemm path needs a bf16/f16 corpus with D %% 8 == 0 (dtype=%d D=%d)", ix->dtype, ix->D);
+    return B200R_EINVAL;
+  }
+  if (path != B200R_PATH_GEMM && path != B200R_PATH_SCAN) { set_error("bad path %d", path); return B200R_EINVAL; }
+  memset(pl, 0, sizeof(*pl));
+  pl->path = path; pl->B = B; pl->k = k;
+  pl->cap_soft = list_cap_soft(k); pl->cap = list_cap(k);
+  if (path == B200R_PATH_GEMM) {
+    const int BMq = gemm_tile_queries(), BNr = gemm_tile_rows();
+    pl->num_q_tiles = (B + BMq - 1) / BMq;
+    pl->num_row_tiles = (int)((ix->N + BNr - 1) / BNr);
+    pl->Bpad = pl->num_q_tiles * BMq;
+    // units = (query tile, chunk of row tiles).  More units per CTA = better balance, fewer = less list
+    // traffic; pick the chunk count (near a target) that wastes the fewest CTA slots in the last wave.
+    const int grid_max = kPlanSMs;
+    const int m = pl->num_q_tiles >= 16 ? 8 : (pl->num_q_tiles >= 4 ? 4 : (pl->num_q_tiles >= 2 ? 2 : 1));
+    long long target = ((long long)grid_max * m + pl->num_q_tiles - 1) / pl->num_q_tiles;
+    if (target < 1) target = 1;
+    if (target > pl->num_row_tiles) target = pl->num_row_tiles;
+    int best = (int)target; double best_waste = 1e30;
+    for (long long c = target; c <= target + 40 && c <= pl->num_row_tiles; ++c) {
+      const int tpc = (int)((pl->num_row_tiles + c - 1) / c);
+      const long long cc = (pl->num_row_tiles + tpc - 1) / tpc;
+      const long long units = cc * pl->num_q_tiles;
+      const long long waves = (units + grid_max - 1) / grid_max;
+      const double waste = (double)(waves * grid_max) / (double)units * (double)(tpc * cc) / (double)pl->num_row_tiles;
+      if (waste < best_waste - 1e-9) { best_waste = waste; best = (int)cc; }
+    }
+    pl->tiles_per_chunk = (pl->num_row_tiles + best - 1) / best;
+    pl->num_chunks = (pl->num_row_tiles + pl->tiles_per_chunk - 1) / pl->tiles_per_chunk;
+    pl->num_units = pl->num_chunks * pl->num_q_tiles;
+    pl->grid = pl->num_units < grid_max ? pl->num_units : grid_max;
+    pl->num_segments = pl->num_chunks;
+  } else {
+    pl->Bpad = B;
+    const int R = 4;
+    const int warps_per_block = 8;
+    long long blocks = (long long)kPlanSMs * 4;
+    const long long groups = (ix->N + R - 1) / R;
+    const long long need = (groups + warps_per_block - 1) / warps_per_block;
+    if (blocks > need) blocks = need < 1 ? 1 : need;
+    pl->scan_blocks = (int)blocks;
+    pl->scan_warps = (int)blocks * warps_per_block;
+    pl->num_segments = pl->scan_warps;
+  }
+  size_t off = 0;
+  pl->off_lists = off; off += align_up((size_t)pl->num_segments * pl->Bpad * pl->cap * 8, 256);
+  pl->off_counts = off; off += align_up((size_t)pl->num_segments * pl->Bpad * 4, 256);
+  pl->off_gthr = off; off += align_up((size_t)pl->Bpad * 4, 256);
+  pl->off_qinv = off; off += align_up((size_t)pl->Bpad * 4, 256);
+  pl->off_end = off;
+  return B200R_OK;
+}
+
+static int query_dtype(const Index* ix) { return ix->dtype == B200R_I8 ? B200R_F32 : ix->dtype; }
+
+static int do_search(Index* ix, const void* Q, int B, int k, int path, float* out_scores, int64_t* out_ids, void* ws,
+                     size_t ws_bytes, cudaStream_t st) {
+  SearchPlan pl;
+  int rc = make_plan(ix, B, k, path, &pl);
+  if (rc) return rc;
+  if (!Q || !out_scores || !out_ids) { set_error("null Q / output pointer"); return B200R_EINVAL; }
+  if (!ws || ws_bytes < pl.off_end) {
+    set_error("workspace too small: need %zu bytes, got %zu", pl.off_end, ws_bytes);
+    return B200R_ENOMEM;
+  }
+  if ((reinterpret_cast<uintptr_t>(Q) & 15) || (reinterpret_cast<uintptr_t>(ws) & 255)) {
+    set_error("Q must be 16-byte aligned and the workspace 256-byte aligned");
+    return B200R_EINVAL;
+  }
+  if ((rc = launch_init_search(pl, ws, st))) return rc;
+  if (ix->metric == B200R_COS) {
+    float* qinv = reinterpret_cast<float*>((char*)ws + pl.off_qinv);
+    if ((rc = launch_query_inv_norm(Q, B, ix->D, query_dtype(ix), qinv, st))) return rc;
+  }
+  if (pl.path == B200R_PATH_GEMM) rc = launch_gemm_topk(ix, Q, pl, ws, st);
+  else rc = launch_scan_topk(ix, Q, pl, ws, st);
+  if (rc) return rc;
+  return launch_select_lists(ix, pl, ws, out_scores, out_ids, st);
+}
+
+}  // namespace b200r
+
+using namespace b200r;
+
+extern "C" {
+
+int b200r_version(void) { return B200R_VERSION; }
+
+int b200r_last_error(char* buf, size_t n) {
+  const size_t len = strlen(g_err);
+  if (buf && n) { strncpy(buf, g_err, n - 1); buf[n - 1] = 0; }
+  return (int)len;
+}
+
+int64_t b200r_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int b200r_index_create(int device, const void* X, int64_t N, int32_t D, int32_t dtype, int32_t metric, int64_t id_base,
+                       const float* row_scale, void* stream, uint64_t* out_index) {
+  if (!out_index) { set_error("out_index is null"); return B200R_EINVAL; }
+  *out_index = 0;
+  if (!X || N <= 0 || D <= 0) { set_error("X must be non-null and N, D > 0 (N=%lld D=%d)", (long long)N, D); return B200R_EINVAL; }
+  if (N > 0xffffffffll) { set_error("N=%lld exceeds the 2^32-1 rows one shard can hold", (long long)N); return B200R_EINVAL; }
+  if (dtype < B200R_BF16 || dtype > B200R_I8) { set_error("bad dtype %d", dtype); return B200R_EINVAL; }
+  if (metric != B200R_IP && metric != B200R_COS) { set_error("bad metric %d", metric); return B200R_EINVAL; }
+  if (((size_t)D * elem_size(dtype)) % 16 != 0 || (reinterpret_cast<uintptr_t>(X) & 15)) {
+    set_error("rows must be 16-byte aligned: D*sizeof(elem) %% 16 == 0 and X 16-byte aligned (D=%d dtype=%d)", D, dtype);
+    return B200R_EINVAL;
+  }
+  B200R_CUDA_CHECK(cudaSetDevice(device));
+  Index* ix = new (std::nothrow) Index();
+  if (!ix) { set_error("out of host memory"); return B200R_ENOMEM; }
+  memset(ix, 0, sizeof(*ix));
+  ix->magic = kIndexMagic; ix->device = device; ix->X = X; ix->N = N; ix->D = D; ix->dtype = dtype; ix->metric = metric;
+  ix->id_base = id_base;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool need_mult = (metric == B200R_COS) || (dtype == B200R_I8 && row_scale);
+  if (need_mult) {
+    cudaError_t e = cudaMalloc(&ix->row_mult, (size_t)N * sizeof(float));
+    if (e != cudaSuccess) { set_error("cudaMalloc(row_mult) failed: %s", cudaGetErrorString(e)); delete ix; return B200R_ENOMEM; }
+    int rc = launch_row_mult(ix, row_scale, st);
+    if (rc) { cudaFree(ix->row_mult); delete ix; return rc; }
+  }
+  if ((dtype == B200R_BF16 || dtype == B200R_F16) && D % 8 == 0) {
+    int rc = encode_tmap_2d(&ix->tmap_x, dtype, X, (uint64_t)D, (uint64_t)N, 64, (uint32_t)gemm_tile_rows());
+    if (rc) { if (ix->row_mult) cudaFree(ix->row_mult); delete ix; return rc; }
+    ix->has_tmap = true;
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    set_error("index build failed: %s", cudaGetErrorString(e));
+    if (ix->row_mult) cudaFree(ix->row_mult);
+    delete ix;
+    return B200R_ECUDA;
+  }
+  *out_index = reinterpret_cast<uint64_t>(ix);
+  return B200R_OK;
+}
+
+int b200r_index_destroy(uint64_t index) {
+  Index* ix = get_index(index);
+  if (!ix) return B200R_ESTATE;
+  cudaSetDevice(ix->device);
+  if (ix->row_mult) cudaFree(ix->row_mult);
+  if (ix->h_q_dev) cudaFree(ix->h_q_dev);
+  if (ix->h_s_dev) cudaFree(ix->h_s_dev);
+  if (ix->h_i_dev) cudaFree(ix->h_i_dev);
+  if (ix->h_ws) cudaFree(ix->h_ws);
+  ix->magic = 0;
+  delete ix;
+  return B200R_OK;
+}
+
+int b200r_index_info(uint64_t index, int64_t* N, int32_t* D, int32_t* dtype, int32_t* metric, int64_t* id_base) {
+  Index* ix = get_index(index);
+  if (!ix) return B200R_ESTATE;
+  if (N) *N = ix->N;
+  if (D) *D = ix->D;
+  if (dtype) *dtype = ix->dtype;
+  if (metric) *metric = ix->metric;
+  if (id_base) *id_base = ix->id_base;
+  return B200R_OK;
+}
+
+size_t b200r_search_workspace_bytes(uint64_t index, int32_t B, int32_t k, int32_t path) {
+  Index* ix = get_index(index);
+  if (!ix) return 0;
+  SearchPlan pl;
+  if (make_plan(ix, B, k, path, &pl)) return 0;
+  return pl.off_end;
+}
+
+int b200r_search(uint64_t index, const void* Q, int32_t B, int32_t k, int32_t path, float* out_scores, int64_t* out_ids,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+  Index* ix = get_index(index);
+  if (!ix) return B200R_ESTATE;
+  B200R_CUDA_CHECK(cudaSetDevice(ix->device));
+  return do_search(ix, Q, B, k, path, out_scores, out_ids, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200r_search_host(uint64_t index, const void* Q_host, int32_t B, int32_t k, int32_t path, float* out_scores_host,
+                      int64_t* out_ids_host, void* stream) {
+  Index* ix = get_index(index);
+  if (!ix) return B200R_ESTATE;
+  if (!Q_host || !out_scores_host || !out_ids_host) { set_error("null host pointer"); return B200R_EINVAL; }
+  B200R_CUDA_CHECK(cudaSetDevice(ix->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SearchPlan pl;
+  int rc = make_plan(ix, B, k, path, &pl);
+  if (rc) return rc;
+  const size_t qbytes = (size_t)B * ix->D * elem_size(query_dtype(ix));
+  const size_t oelems = (size_t)B * k;
+  if (ix->q_dev_bytes < qbytes) {
+    if (ix->h_q_dev) cudaFree(ix->h_q_dev);
+    ix->h_q_dev = nullptr; ix->q_dev_bytes = 0;
+    B200R_CUDA_CHECK(cudaMalloc(&ix->h_q_dev, qbytes));
+    ix->q_dev_bytes = qbytes;
+  }
+  if (ix->out_dev_elems < oelems) {
+    if (ix->h_s_dev) cudaFree(ix->h_s_dev);
+    if (ix->h_i_dev) cudaFree(ix->h_i_dev);
+    ix->h_s_dev = nullptr; ix->h_i_dev = nullptr; ix->out_dev_elems = 0;
+    B200R_CUDA_CHECK(cudaMalloc(&ix->h_s_dev, oelems * sizeof(float)));
+    B200R_CUDA_CHECK(cudaMalloc(&ix->h_i_dev, oelems * sizeof(int64_t)));
+    ix->out_dev_elems = oelems;
+  }
+  if (ix->ws_bytes < pl.off_end) {
+    if (ix->h_ws) cudaFree(ix->h_ws);
+    ix->h_ws = nullptr; ix->ws_bytes = 0;
+    B200R_CUDA_CHECK(cudaMalloc(&ix->h_ws, pl.off_end));
+    ix->ws_bytes = pl.off_end;
+  }
+  B200R_CUDA_CHECK(cudaMemcpyAsync(ix->h_q_dev, Q_host, qbytes, cudaMemcpyHostToDevice, st));
+  rc = do_search(ix, ix->h_q_dev, B, k, path, ix->h_s_dev, ix->h_i_dev, ix->h_ws, ix->ws_bytes, st);
+  if (rc) return rc;
+  B200R_CUDA_CHECK(cudaMemcpyAsync(out_scores_host, ix->h_s_dev, oelems * sizeof(float), cudaMemcpyDeviceToHost, st));
+  B200R_CUDA_CHECK(cudaMemcpyAsync(out_ids_host, ix->h_i_dev, oelems * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  B200R_CUDA_CHECK(cudaStreamSynchronize(st));
+  return B200R_OK;
+}
+
+int b200r_merge_topk(int device, const float* cand_scores, const int64_t* cand_ids, int32_t G, int32_t B, int32_t kin,
+                     int32_t k, float* out_scores, int64_t* out_ids, void* stream) {
+  if (!cand_scores || !cand_ids || !out_scores || !out_ids) { set_error("null pointer"); return B200R_EINVAL; }
+  if (G <= 0 || B <= 0 || kin <= 0 || k <= 0) { set_error("G, B, kin, k must be > 0"); return B200R_EINVAL; }
+  B200R_CUDA_CHECK(cudaSetDevice(device));
+  return launch_merge_topk(cand_scores, cand_ids, G, B, kin, k, out_scores, out_ids, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200r_graph_create(int device, const int64_t* row_ptr, const int32_t* col_idx, int64_t V, int64_t E, uint64_t* out_graph) {
+  if (!out_graph) { set_error("out_graph is null"); return B200R_EINVAL; }
+  *out_graph = 0;
+  if (!row_ptr || V <= 0 || E < 0 || (E > 0 && !col_idx)) { set_error("bad graph arguments"); return B200R_EINVAL; }
+  if (V > 0xfffffffell) { set_error("V too large"); return B200R_EINVAL; }
+  Graph* g = new (std::nothrow) Graph();
+  if (!g) { set_error("out of host memory"); return B200R_ENOMEM; }
+  g->magic = kGraphMagic; g->device = device; g->row_ptr = row_ptr; g->col_idx = col_idx; g->V = V; g->E = E;
+  *out_graph = reinterpret_cast<uint64_t>(g);
+  return B200R_OK;
+}
+
+int b200r_graph_destroy(uint64_t graph) {
+  Graph* g = get_graph(graph);
+  if (!g) return B200R_ESTATE;
+  g->magic = 0;
+  delete g;
+  return B200R_OK;
+}
+
+int32_t b200r_expand_max_candidates(void) { return expand_max_candidates(); }
+
+int b200r_expand_rescore(uint64_t index, uint64_t graph, const void* Q, const int64_t* seeds, int32_t B, int32_t S,
+                         int32_t window, float alpha_dense, float alpha_graph, int32_t k, float* out_scores, int64_t* out_ids,
+                         int32_t* out_hops, float* out_graph_norm, float* out_dense_norm, float* out_cos, int32_t* out_ncand,
+                         int32_t* out_status, void* stream) {
+  Index* ix = get_index(index);
+  Graph* g = get_graph(graph);
+  if (!ix || !g) return B200R_ESTATE;
+  if (ix->device != g->device) { set_error("index and graph live on different devices"); return B200R_EINVAL; }
+  if (!Q || !seeds || !out_scores || !out_ids || !out_hops || !out_graph_norm || !out_dense_norm || !out_cos || !out_ncand || !out_status) {
+    set_error("null pointer");
+    return B200R_EINVAL;
+  }
+  if (B <= 0 || S <= 0 || k <= 0 || k > B200R_MAX_K || window < 0 || window > 255) {
+    set_error("bad B/S/k/window (%d/%d/%d/%d)", B, S, k, window);
+    return B200R_EINVAL;
+  }
+  B200R_CUDA_CHECK(cudaSetDevice(ix->device));
+  return launch_expand_rescore(ix, g, Q, seeds, B, S, window, alpha_dense, alpha_graph, k, out_scores, out_ids, out_hops,
+                               out_graph_norm, out_dense_norm, out_cos, out_ncand, out_status,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,348 @@
+// gemm_topk.cu -- K1: Q x X^T on tcgen05/TMEM tiles fed by TMA, with the per-tile score epilogue
+// fused into a running exact top-k, so the [B, N] score matrix never exists in HBM.
+//
+// Replaces DenseReranker._cosine over the candidate pool + sort/slice
+// (reference app/modules/retrieval/retrieval_backend.py:192-197, 245, 371-372) for a whole batch
+// against the whole corpus.
+//
+// Tile: 128 queries (TMEM lanes) x 256 corpus rows (TMEM columns), K streamed in 64-element
+// (128-byte, SWIZZLE_128B) slices through a 4-stage TMA->smem ring.  Two 256-column accumulators
+// alternate so that the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Warp roles (192 threads, 1 CTA/SM): warp 0 = TMA producer (1 thread), warp 1 = TMEM allocator and
+// tcgen05.mma issuer (1 thread), warps 2..5 = epilogue; epilogue thread t owns TMEM lane
+// (warp%4)*32+lane == one query of the tile and therefore sees that query's scores for consecutive
+// corpus rows.  It keeps the query's current k-th best score in a register; a score passes only if it
+// beats it (>=), which after warm-up almost never happens.  Survivors are appended to that query's
+// list (global memory, L2 resident); when a list reaches cap_soft the warp cooperatively reduces it
+// to its exact top-k (radix select, common.cuh) and tightens the threshold.  A global per-query
+// threshold (gthr) lets later units start from the best threshold any earlier unit has published.
+//
+// Work unit = (query tile, chunk of consecutive row tiles); units are numbered chunk-major so the
+// CTAs that share a chunk stream the same X tiles at the same time and hit them in L2.
+#include "common.cuh"
+#include "internal.h"
+
+namespace b200r {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_BYTES = BN * BK * 2;   // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GEMM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int GEMM_SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 * BN * 4 /*row mult*/ +
+                                4 * 256 * 4 /*hist*/ + 16 * 8 /*barriers*/ + 16;
+
+struct GemmTopkParams {
+  int B, k, D;
+  long long N;
+  int num_q_tiles, num_row_tiles, tiles_per_chunk, num_chunks, num_units;
+  int cap, cap_soft, Bpad;
+  const float* row_mult;
+  u64* lists;
+  int* counts;
+  u32* gthr;
+  u32 idesc;
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(u64* bar, u32 parity) {
+  u32 ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+constexpr u64 kEvictNormal = 0x1000000000000000ull;
+constexpr u64 kEvictLast = 0x14F0000000000000ull;
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, u64* bar, int c0, int c1, u64 hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"((u64)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((u64)tmap) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start>>4 [0,14),
+// LBO>>4 [16,30) (unused for swizzled K-major), SBO>>4 [32,46) = 1024 B between 8-row groups,
+// version=1 [46,48), layout=SWIZZLE_128B(2) [61,64).
+__device__ __forceinline__ u64 make_smem_desc(u32 smem_addr) {
+  return (u64)((smem_addr >> 4) & 0x3fffu) | ((u64)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void umma_f16(u32 tmem_d, u64 desc_a, u64 desc_b, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(u64* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(u32 taddr, u32* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
+                 const GemmTopkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const u32 raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  uint8_t* smem_a = smem;                               // STAGES x 16 KB
+  uint8_t* smem_b = smem + STAGES * A_BYTES;            // STAGES x 32 KB
+  float* smem_mult = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // [2][BN]
+  u32* smem_hist = reinterpret_cast<u32*>(smem_mult + 2 * BN);               // [4][256]
+  u64* bars = reinterpret_cast<u64*>(smem_hist + 4 * 256);
+  u64* full_bar = bars;                  // [STAGES]
+  u64* empty_bar = bars + STAGES;        // [STAGES]
+  u64* tmem_full_bar = bars + 2 * STAGES;       // [2]
+  u64* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
+  u32* tmem_ptr_smem = reinterpret_cast<u32*>(bars + 2 * STAGES + 4);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_x);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const u32 tmem_base = *tmem_ptr_smem;
+
+  const int num_kb = (p.D + BK - 1) / BK;
+
+  if (warp_idx == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0; u32 phase = 0;
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+        const int q_tile = u % p.num_q_tiles;
+        const int chunk = u / p.num_q_tiles;
+        const int t0 = chunk * p.tiles_per_chunk;
+        const int t1 = min(p.num_row_tiles, t0 + p.tiles_per_chunk);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tma_load_2d(smem_a + stage * A_BYTES, &tmap_q, &full_bar[stage], kb * BK, q_tile * BM, kEvictLast);
+            tma_load_2d(smem_b + stage * B_BYTES, &tmap_x, &full_bar[stage], kb * BK, t * BN, kEvictNormal);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      int stage = 0; u32 phase = 0;
+      u32 tile_iter = 0;
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+        const int chunk = u / p.num_q_tiles;
+        const int t0 = chunk * p.tiles_per_chunk;
+        const int t1 = min(p.num_row_tiles, t0 + p.tiles_per_chunk);
+        for (int t = t0; t < t1; ++t, ++tile_iter) {
+          const u32 acc = tile_iter & 1;
+          mbar_wait(&tmem_empty_bar[acc], ((tile_iter >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const u32 tmem_d = tmem_base + acc * BN;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const u64 desc_a = make_smem_desc(smem_u32(smem_a + stage * A_BYTES));
+            const u64 desc_b = make_smem_desc(smem_u32(smem_b + stage * B_BYTES));
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              // advance 16 elements = 32 bytes inside the 128-byte swizzle span: +2 in the >>4 address field
+              umma_f16(tmem_d, desc_a + (u64)(kk * 2), desc_b + (u64)(kk * 2), p.idesc, (kb | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
+            if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int quarter = warp_idx & 3;             // TMEM lane quarter this warp may access
+    const int q_lane = quarter * 32 + lane;       // query within the tile
+    const int epi_tid = (warp_idx - 2) * 32 + lane;  // 0..127
+    u32* hist = smem_hist + (warp_idx - 2) * 256;
+    u32 tile_iter = 0;
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      const int q_tile = u % p.num_q_tiles;
+      const int chunk = u / p.num_q_tiles;
+      const int t0 = chunk * p.tiles_per_chunk;
+      const int t1 = min(p.num_row_tiles, t0 + p.tiles_per_chunk);
+      const int q = q_tile * BM + q_lane;
+      const bool valid = q < p.B;
+      const size_t slot = (size_t)chunk * p.Bpad + (size_t)q_tile * BM + q_lane;
+      u64* my_list = p.lists + slot * (size_t)p.cap;
+      int cnt = 0;
+      u64 kth_key = 0;
+      float thr = valid ? ordered_to_f32(__ldcg(p.gthr + q)) : __int_as_float(0x7f800000);
+
+      for (int t = t0; t < t1; ++t, ++tile_iter) {
+        const u32 acc = tile_iter & 1;
+        float* mult = smem_mult + (tile_iter & 1) * BN;
+        // per-row multipliers of this tile (1/|x| for cosine); NaN marks rows beyond N so they never pass
+        {
+          const long long r = (long long)t * BN + epi_tid * 2;
+          float m0 = __int_as_float(0x7fc00000), m1 = __int_as_float(0x7fc00000);
+          if (r < p.N) m0 = p.row_mult ? __ldg(p.row_mult + r) : 1.0f;
+          if (r + 1 < p.N) m1 = p.row_mult ? __ldg(p.row_mult + r + 1) : 1.0f;
+          mult[epi_tid * 2] = m0;
+          mult[epi_tid * 2 + 1] = m1;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
+        tc_fence_after();
+        const u32 row0 = (u32)t * BN;
+        const u32 taddr = tmem_base + ((u32)(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          u32 v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (c == BN / 32 - 1) {
+            // the whole accumulator is in registers: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          float s[32];
+          bool any = false;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 m4 = *reinterpret_cast<const float4*>(mult + c * 32 + j);
+            s[j] = __uint_as_float(v[j]) * m4.x;
+            s[j + 1] = __uint_as_float(v[j + 1]) * m4.y;
+            s[j + 2] = __uint_as_float(v[j + 2]) * m4.z;
+            s[j + 3] = __uint_as_float(v[j + 3]) * m4.w;
+            any |= (s[j] >= thr) | (s[j + 1] >= thr) | (s[j + 2] >= thr) | (s[j + 3] >= thr);
+          }
+          if (__any_sync(kFullMask, any)) {
+            if (any) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (s[j] >= thr) {
+                  const u64 key = make_key(s[j], row0 + c * 32 + j);
+                  if (key > kth_key) { __stcg(my_list + cnt, key); ++cnt; }
+                }
+              }
+            }
+            u32 full = __ballot_sync(kFullMask, cnt >= p.cap_soft);
+            while (full) {
+              const int l = __ffs(full) - 1;
+              full &= full - 1;
+              u64* lp = reinterpret_cast<u64*>(__shfl_sync(kFullMask, (u64)my_list, l));
+              const int n = __shfl_sync(kFullMask, cnt, l);
+              const u64 kth = warp_compact(lp, n, p.k, hist);
+              if (lane == l) {
+                kth_key = kth;
+                thr = fmaxf(thr, key_score(kth));
+                cnt = p.k;
+                atomicMax(p.gthr + q, (u32)(kth >> 32));
+              }
+            }
+          }
+        }
+        // pick up thresholds published by other CTAs working on the same queries
+        if (valid) thr = fmaxf(thr, ordered_to_f32(__ldcg(p.gthr + q)));
+      }
+      p.counts[slot] = valid ? cnt : 0;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+int launch_gemm_topk(const Index* ix, const void* Q, const SearchPlan& pl, void* ws, cudaStream_t st) {
+  if (!ix->has_tmap) { set_error("gemm path needs a bf16/f16 corpus with D %% 8 == 0"); return B200R_EINVAL; }
+  CUtensorMap tmap_q;
+  int rc = encode_tmap_2d(&tmap_q, ix->dtype, Q, (uint64_t)ix->D, (uint64_t)pl.B, BK, BM);
+  if (rc) return rc;
+  GemmTopkParams p;
+  p.B = pl.B; p.k = pl.k; p.D = ix->D; p.N = ix->N;
+  p.num_q_tiles = pl.num_q_tiles; p.num_row_tiles = pl.num_row_tiles; p.tiles_per_chunk = pl.tiles_per_chunk;
+  p.num_chunks = pl.num_chunks; p.num_units = pl.num_units;
+  p.cap = pl.cap; p.cap_soft = pl.cap_soft; p.Bpad = pl.Bpad;
+  p.row_mult = ix->row_mult;
+  p.lists = reinterpret_cast<u64*>((char*)ws + pl.off_lists);
+  p.counts = reinterpret_cast<int*>((char*)ws + pl.off_counts);
+  p.gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
+  // instruction descriptor: D=f32 (1<<4), A/B format (bf16=1, f16=0) at [7,10)/[10,13), K-major A and B,
+  // N>>3 at [17,23), M>>4 at [24,29)
+  const u32 fmt = (ix->dtype == B200R_BF16) ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((u32)(BN >> 3) << 17) | ((u32)(BM >> 4) << 24);
+  B200R_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  gemm_topk_kernel<<<pl.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(tmap_q, ix->tmap_x, p);
+  count_launch();
+  B200R_CUDA_CHECK(cudaGetLastError());
+  return B200R_OK;
+}
+
+int gemm_tile_rows() { return BN; }
+int gemm_tile_queries() { return BM; }
+
+}  // namespace b200r

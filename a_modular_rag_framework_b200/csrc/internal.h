@@ -1,0 +1,89 @@
+// internal.h -- host-side declarations shared by the translation units of libb200r.so
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+
+#include "../../include/b200r.h"
+
+namespace b200r {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define B200R_CUDA_CHECK(expr)                                                            \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::b200r::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return B200R_ECUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+struct Index {
+  uint32_t magic;
+  int device;
+  const void* X;
+  int64_t N;
+  int32_t D;
+  int32_t dtype;
+  int32_t metric;
+  int64_t id_base;
+  float* row_mult;      // [N] or nullptr: cos -> 1/|x_n| (0 when |x_n| == 0); ip+i8 -> row_scale; ip -> nullptr
+  bool has_tmap;        // X tensor map valid (bf16/f16, D % 8 == 0)
+  CUtensorMap tmap_x;
+  // staging for b200r_search_host
+  void* h_q_dev; size_t q_dev_bytes;
+  float* h_s_dev; int64_t* h_i_dev; size_t out_dev_elems;
+  void* h_ws; size_t ws_bytes;
+};
+
+struct Graph {
+  uint32_t magic;
+  int device;
+  const int64_t* row_ptr;
+  const int32_t* col_idx;
+  int64_t V, E;
+};
+
+constexpr int kPlanSMs = 148;  // B200
+constexpr uint32_t kIndexMagic = 0xB200A001u;
+constexpr uint32_t kGraphMagic = 0xB200A002u;
+
+inline size_t elem_size(int dtype) { return dtype == B200R_F32 ? 4 : (dtype == B200R_I8 ? 1 : 2); }
+inline int list_cap_soft(int k) { return k <= 256 ? 512 : 2 * k; }
+inline int list_cap(int k) { return list_cap_soft(k) + 32; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- plan of one search: how the corpus is cut into units and where the partial lists live -------
+struct SearchPlan {
+  int path;             // B200R_PATH_GEMM / B200R_PATH_SCAN
+  int B, k, cap, cap_soft;
+  int Bpad;             // list slots per segment (>= B)
+  int num_segments;     // lists per query
+  // gemm
+  int num_q_tiles, num_row_tiles, tiles_per_chunk, num_chunks, num_units, grid;
+  // scan
+  int scan_bq, scan_warps, scan_blocks;
+  // workspace layout (byte offsets)
+  size_t off_lists, off_counts, off_gthr, off_qinv, off_end;
+};
+
+int make_plan(const Index* ix, int B, int k, int path, SearchPlan* plan);
+
+// kernels (each returns a B200R_* code and records the launch)
+int launch_row_mult(const Index* ix, const float* row_scale, cudaStream_t st);
+int launch_query_inv_norm(const void* Q, int B, int D, int qdtype, float* qinv, cudaStream_t st);
+int launch_init_search(const SearchPlan& p, void* ws, cudaStream_t st);
+int launch_gemm_topk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
+int launch_scan_topk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
+int launch_select_lists(const Index* ix, const SearchPlan& p, void* ws, float* out_scores, int64_t* out_ids, cudaStream_t st);
+int launch_merge_topk(const float* cs, const int64_t* ci, int G, int B, int kin, int k, float* os, int64_t* oi, cudaStream_t st);
+int launch_expand_rescore(const Index* ix, const Graph* g, const void* Q, const int64_t* seeds, int B, int S, int window,
+                          float alpha_dense, float alpha_graph, int k, float* out_scores, int64_t* out_ids, int32_t* out_hops,
+                          float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand, int32_t* out_status, cudaStream_t st);
+int encode_tmap_2d(CUtensorMap* tm, int dtype, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer);
+
+}  // namespace b200r

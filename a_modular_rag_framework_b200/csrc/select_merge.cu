@@ -1,0 +1,213 @@
+// select_merge.cu -- K4: exact top-k of candidate lists, ordered by (score desc, id asc).
+//
+//  * select_lists_kernel: final reduction of the per-unit candidate lists K1/K2 leave in the
+//    workspace -> out_scores/out_ids [B, k].
+//  * merge_topk_kernel: public merge of G per-shard top-k lists (after the NCCL all-gather).
+// Both implement the reference's ranking rule -- python stable sort, descending, slice
+// (app/modules/retrieval/retrieval_backend.py:371-372, retrieval_adapter.py:129-131) -- over
+// candidates enumerated in id order, i.e. ties go to the lower id.
+#include "common.cuh"
+#include "internal.h"
+#include <math_constants.h>
+
+namespace b200r {
+
+constexpr int SEL_THREADS = 512;
+
+struct SelectParams {
+  const u64* lists;
+  const int* counts;
+  int S, Bpad, cap, scan_len;  // scan_len: entries per list that can be valid (<= cap)
+  int B, k, kp2;
+  const float* qinv;           // nullable
+  long long id_base;
+  float* out_scores;
+  long long* out_ids;
+};
+
+__global__ void __launch_bounds__(SEL_THREADS) select_lists_kernel(const SelectParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  u64* sk = reinterpret_cast<u64*>(smem_raw);               // [kp2]
+  u32* hist = reinterpret_cast<u32*>(sk + p.kp2);           // [256]
+  __shared__ u64 s_prefix;
+  __shared__ int s_remaining, s_total, s_nout;
+
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const long long vtotal = (long long)p.S * p.scan_len;
+
+  if (tid == 0) { s_total = 0; s_nout = 0; s_prefix = 0; }
+  __syncthreads();
+  {
+    int local = 0;
+    for (int s = tid; s < p.S; s += SEL_THREADS) local += p.counts[(size_t)s * p.Bpad + q];
+    if (local) atomicAdd(&s_total, local);
+  }
+  __syncthreads();
+  const int total = s_total;
+  const int want = total < p.k ? total : p.k;
+
+  u64 kth = 0;
+  if (total > p.k) {
+    if (tid == 0) s_remaining = p.k;
+    for (int pass = 7; pass >= 0; --pass) {
+      const int shift = pass * 8;
+      for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
+      __syncthreads();
+      const u64 prefix = s_prefix;
+      const u64 hi_mask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
+      for (long long v = tid; v < vtotal; v += SEL_THREADS) {
+        const int seg = (int)(v / p.scan_len), i = (int)(v % p.scan_len);
+        const size_t slot = (size_t)seg * p.Bpad + q;
+        if (i < p.counts[slot]) {
+          const u64 key = p.lists[slot * (size_t)p.cap + i];
+          if ((key & hi_mask) == prefix) atomicAdd(&hist[(u32)(key >> shift) & 255u], 1u);
+        }
+      }
+      __syncthreads();
+      if (tid < 32) {
+        const int lane = tid;
+        const int remaining = s_remaining;
+        u32 c[8]; u32 lane_sum = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { c[b] = hist[lane * 8 + b]; lane_sum += c[b]; }
+        u32 suffix = lane_sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 t = __shfl_down_sync(kFullMask, suffix, o);
+          if (lane + o < 32) suffix += t;
+        }
+        const u32 above = suffix - lane_sum;
+        if (above < (u32)remaining && (u32)remaining <= suffix) {
+          u32 run = above;
+#pragma unroll
+          for (int b = 7; b >= 0; --b) {
+            if (run + c[b] >= (u32)remaining) {
+              s_prefix = prefix | ((u64)(u32)(lane * 8 + b) << shift);
+              s_remaining = remaining - (int)run;
+              break;
+            }
+            run += c[b];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    kth = s_prefix;
+  }
+
+  for (int i = tid; i < p.kp2; i += SEL_THREADS) sk[i] = 0;
+  __syncthreads();
+  for (long long v = tid; v < vtotal; v += SEL_THREADS) {
+    const int seg = (int)(v / p.scan_len), i = (int)(v % p.scan_len);
+    const size_t slot = (size_t)seg * p.Bpad + q;
+    if (i < p.counts[slot]) {
+      const u64 key = p.lists[slot * (size_t)p.cap + i];
+      if (key >= kth) {
+        const int pos = atomicAdd(&s_nout, 1);
+        if (pos < p.kp2) sk[pos] = key;
+      }
+    }
+  }
+  __syncthreads();
+  block_bitonic_desc(sk, p.kp2);
+  const float qi = p.qinv ? p.qinv[q] : 1.0f;
+  for (int i = tid; i < p.k; i += SEL_THREADS) {
+    const u64 key = sk[i];
+    const bool ok = (i < want) && key != 0;
+    p.out_scores[(size_t)q * p.k + i] = ok ? key_score(key) * qi : -CUDART_INF_F;
+    p.out_ids[(size_t)q * p.k + i] = ok ? (p.id_base + (long long)key_id(key)) : -1ll;
+  }
+}
+
+static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+int launch_select_lists(const Index* ix, const SearchPlan& pl, void* ws, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+  SelectParams p;
+  p.lists = reinterpret_cast<const u64*>((char*)ws + pl.off_lists);
+  p.counts = reinterpret_cast<const int*>((char*)ws + pl.off_counts);
+  p.S = pl.num_segments; p.Bpad = pl.Bpad; p.cap = pl.cap;
+  p.scan_len = (pl.path == B200R_PATH_SCAN) ? pl.k : pl.cap;  // K2 compacts every list to <= k before exiting
+  p.B = pl.B; p.k = pl.k; p.kp2 = next_pow2(pl.k);
+  p.qinv = (ix->metric == B200R_COS) ? reinterpret_cast<const float*>((char*)ws + pl.off_qinv) : nullptr;
+  p.id_base = ix->id_base;
+  p.out_scores = out_scores;
+  p.out_ids = reinterpret_cast<long long*>(out_ids);
+  const size_t smem = (size_t)p.kp2 * 8 + 256 * 4;
+  select_lists_kernel<<<pl.B, SEL_THREADS, smem, st>>>(p);
+  count_launch();
+  B200R_CUDA_CHECK(cudaGetLastError());
+  return B200R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// public merge: candidates [G, B, kin] (f32 score, i64 id) -> [B, k]
+// ------------------------------------------------------------------------------------------------
+constexpr int MERGE_THREADS = 256;
+
+struct MergeParams {
+  const float* cs;
+  const long long* ci;
+  int G, B, kin, k, np2;
+  float* os;
+  long long* oi;
+};
+
+__device__ __forceinline__ bool cand_better(u32 sa, long long ia, u32 sb, long long ib) {
+  return sa > sb || (sa == sb && ia < ib);
+}
+
+__global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const MergeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  long long* ids = reinterpret_cast<long long*>(smem_raw);  // [np2]
+  u32* sc = reinterpret_cast<u32*>(ids + p.np2);            // [np2] ordered scores
+  const int q = blockIdx.x;
+  const int n = p.G * p.kin;
+  for (int i = threadIdx.x; i < p.np2; i += MERGE_THREADS) {
+    u32 s = 0; long long id = 0x7fffffffffffffffll;
+    if (i < n) {
+      const int g = i / p.kin, j = i % p.kin;
+      const size_t off = ((size_t)g * p.B + q) * p.kin + j;
+      const long long cid = p.ci[off];
+      if (cid >= 0) { id = cid; s = f32_to_ordered(p.cs[off] + 0.0f); }
+    }
+    sc[i] = s; ids[i] = id;
+  }
+  for (int size = 2; size <= p.np2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < p.np2 / 2; t += MERGE_THREADS) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const u32 sa = sc[lo], sb = sc[hi];
+        const long long ia = ids[lo], ib = ids[hi];
+        const bool lo_better = cand_better(sa, ia, sb, ib);
+        if (lo_better != desc) { sc[lo] = sb; sc[hi] = sa; ids[lo] = ib; ids[hi] = ia; }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.k; i += MERGE_THREADS) {
+    const bool ok = i < p.np2 && ids[i] != 0x7fffffffffffffffll;
+    p.os[(size_t)q * p.k + i] = ok ? ordered_to_f32(sc[i]) : -CUDART_INF_F;
+    p.oi[(size_t)q * p.k + i] = ok ? ids[i] : -1ll;
+  }
+}
+
+int launch_merge_topk(const float* cs, const int64_t* ci, int G, int B, int kin, int k, float* os, int64_t* oi, cudaStream_t st) {
+  const long long n = (long long)G * kin;
+  if (n > 16384) { set_error("merge_topk: G*kin = %lld exceeds 16384", n); return B200R_EINVAL; }
+  MergeParams p;
+  p.cs = cs; p.ci = reinterpret_cast<const long long*>(ci); p.G = G; p.B = B; p.kin = kin; p.k = k;
+  p.np2 = next_pow2((int)n < 2 ? 2 : (int)n);
+  p.os = os; p.oi = reinterpret_cast<long long*>(oi);
+  const size_t smem = (size_t)p.np2 * 12;
+  B200R_CUDA_CHECK(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_topk_kernel<<<B, MERGE_THREADS, smem, st>>>(p);
+  count_launch();
+  B200R_CUDA_CHECK(cudaGetLastError());
+  return B200R_OK;
+}
+
+}  // namespace b200r

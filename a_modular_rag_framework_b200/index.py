@@ -1,0 +1,216 @@
+"""Host-side mirrors of the C ABI objects: DenseIndex (corpus), PassageGraph (CSR) and the calls on them.
+
+PyTorch is used for device memory, streams and dtype plumbing only; every computation is a kernel of
+libb200r.so reached through ctypes (``_native``).  Nothing here falls back to the CPU.
+
+Reference behaviour replaced (paths relative to the reference root):
+  DenseIndex.search        DenseReranker.score + sort/slice   app/modules/retrieval/retrieval_backend.py:215-247, 371-372
+  PassageGraph             load_graph_json + build_index      app/modules/retrieval/graph_utils.py:13-55
+  expand_rescore           expand_qmatch_neighbors + fusion   graph_utils.py:58-129, retrieval_backend.py:296-301, 353-372
+  merge_topk               the same stable-sort rule over per-shard lists
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+_DTYPES = {torch.bfloat16: N.BF16, torch.float16: N.F16, torch.float32: N.F32, torch.int8: N.I8}
+_METRICS = {"ip": N.IP, "cos": N.COS, "cosine": N.COS}
+_PATHS = {"auto": N.PATH_AUTO, "gemm": N.PATH_GEMM, "scan": N.PATH_SCAN}
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+class DenseIndex:
+    """Exact cosine / inner-product top-k over a resident [N, D] passage-embedding matrix."""
+
+    def __init__(self, X: torch.Tensor, metric: str = "cos", id_base: int = 0, row_scale: Optional[torch.Tensor] = None):
+        _require_cuda(X, "X")
+        if X.dim() != 2:
+            raise ValueError("X must be [N, D]")
+        if X.dtype not in _DTYPES:
+            raise ValueError(f"unsupported corpus dtype {X.dtype}")
+        if metric not in _METRICS:
+            raise ValueError(f"unknown metric {metric!r}")
+        if row_scale is not None:
+            _require_cuda(row_scale, "row_scale")
+            if row_scale.dtype != torch.float32 or row_scale.numel() != X.shape[0]:
+                raise ValueError("row_scale must be float32 [N]")
+        self._lib = N.load()
+        self.X = X                      # borrowed by the library for the index lifetime
+        self.row_scale = row_scale
+        self.metric = metric
+        self.id_base = int(id_base)
+        self.device = X.device
+        self.N, self.D = int(X.shape[0]), int(X.shape[1])
+        self.query_dtype = torch.float32 if X.dtype == torch.int8 else X.dtype
+        self._ws: Optional[torch.Tensor] = None
+        self._handle = ctypes.c_uint64(0)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.b200r_index_create(
+                self.device.index or 0, X.data_ptr(), self.N, self.D, _DTYPES[X.dtype], _METRICS[metric], self.id_base,
+                row_scale.data_ptr() if row_scale is not None else None, _stream_ptr(self.device), ctypes.byref(self._handle)))
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.b200r_index_destroy(self._handle)
+            self._handle = ctypes.c_uint64(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self) -> int:
+        if not self._handle.value:
+            raise RuntimeError("index is closed")
+        return self._handle.value
+
+    # -- search -----------------------------------------------------------------------------------
+    def _workspace(self, B: int, k: int, path: int) -> torch.Tensor:
+        need = int(self._lib.b200r_search_workspace_bytes(self._handle, B, k, path))
+        if need == 0:
+            raise N.B200RError(-1, N.last_error())
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def search(self, Q: torch.Tensor, k: int, path: str = "auto",
+               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Q [B, D] on the device in ``query_dtype`` -> (scores f32 [B, k], ids i64 [B, k]), stream-ordered, no sync."""
+        _require_cuda(Q, "Q")
+        if Q.dim() != 2 or Q.shape[1] != self.D:
+            raise ValueError(f"Q must be [B, {self.D}]")
+        if Q.dtype != self.query_dtype:
+            raise ValueError(f"Q must be {self.query_dtype} for a {self.X.dtype} corpus")
+        B = int(Q.shape[0])
+        p = _PATHS[path]
+        ws = self._workspace(B, k, p)
+        if out is None:
+            scores = torch.empty((B, k), dtype=torch.float32, device=self.device)
+            ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
+        else:
+            scores, ids = out
+        with torch.cuda.device(self.device):
+            N.check(self._lib.b200r_search(self._handle, Q.data_ptr(), B, k, p, scores.data_ptr(), ids.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+        return scores, ids
+
+    def search_host(self, Q_host: torch.Tensor, k: int, path: str = "auto",
+                    out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Host buffers in, host buffers out (H2D + search + D2H + stream sync inside the C call)."""
+        if Q_host.is_cuda or not Q_host.is_contiguous() or Q_host.dtype != self.query_dtype or Q_host.shape[1] != self.D:
+            raise ValueError("Q_host must be a contiguous CPU tensor [B, D] in the index's query dtype")
+        B = int(Q_host.shape[0])
+        if out is None:
+            scores = torch.empty((B, k), dtype=torch.float32).pin_memory()
+            ids = torch.empty((B, k), dtype=torch.int64).pin_memory()
+        else:
+            scores, ids = out
+        with torch.cuda.device(self.device):
+            N.check(self._lib.b200r_search_host(self._handle, Q_host.data_ptr(), B, k, _PATHS[path], scores.data_ptr(),
+                                                ids.data_ptr(), _stream_ptr(self.device)))
+        return scores, ids
+
+
+def merge_topk(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[G, B, kin] per-shard lists -> [B, k] by (score desc, id asc); ids < 0 are padding."""
+    _require_cuda(cand_scores, "cand_scores")
+    _require_cuda(cand_ids, "cand_ids")
+    if cand_scores.dtype != torch.float32 or cand_ids.dtype != torch.int64 or cand_scores.shape != cand_ids.shape or cand_scores.dim() != 3:
+        raise ValueError("cand_scores f32 / cand_ids i64 must both be [G, B, kin]")
+    G, B, kin = (int(x) for x in cand_scores.shape)
+    dev = cand_scores.device
+    scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((B, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.load().b200r_merge_topk(dev.index or 0, cand_scores.data_ptr(), cand_ids.data_ptr(), G, B, kin, k,
+                                          scores.data_ptr(), ids.data_ptr(), _stream_ptr(dev)))
+    return scores, ids
+
+
+class PassageGraph:
+    """CSR of the undirected next_in_doc adjacency; node id == corpus row id."""
+
+    def __init__(self, row_ptr: torch.Tensor, col_idx: torch.Tensor):
+        _require_cuda(row_ptr, "row_ptr")
+        _require_cuda(col_idx, "col_idx")
+        if row_ptr.dtype != torch.int64 or col_idx.dtype != torch.int32:
+            raise ValueError("row_ptr must be int64 and col_idx int32")
+        self._lib = N.load()
+        self.row_ptr, self.col_idx = row_ptr, col_idx
+        self.device = row_ptr.device
+        self.V = int(row_ptr.numel()) - 1
+        self.E = int(col_idx.numel())
+        self._handle = ctypes.c_uint64(0)
+        N.check(self._lib.b200r_graph_create(self.device.index or 0, row_ptr.data_ptr(),
+                                             col_idx.data_ptr() if self.E else None, self.V, self.E, ctypes.byref(self._handle)))
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.b200r_graph_destroy(self._handle)
+            self._handle = ctypes.c_uint64(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self) -> int:
+        if not self._handle.value:
+            raise RuntimeError("graph is closed")
+        return self._handle.value
+
+
+def expand_rescore(index: DenseIndex, graph: PassageGraph, Q: torch.Tensor, seeds: torch.Tensor, window: int,
+                   alpha_dense: float, alpha_graph: float, k: int, check_status: bool = True) -> Dict[str, torch.Tensor]:
+    """Graph second stage for B queries: BFS (<= window hops) from ``seeds`` [B, S] (i64, <0 = padding),
+    cosine re-score, min-max fusion, top-k.  Returns device tensors keyed like the reference's meta keys."""
+    _require_cuda(Q, "Q")
+    _require_cuda(seeds, "seeds")
+    if Q.dtype != index.query_dtype or Q.dim() != 2 or Q.shape[1] != index.D:
+        raise ValueError("Q must be [B, D] in the index's query dtype")
+    if seeds.dtype != torch.int64 or seeds.dim() != 2 or seeds.shape[0] != Q.shape[0]:
+        raise ValueError("seeds must be int64 [B, S]")
+    B, S = int(seeds.shape[0]), int(seeds.shape[1])
+    dev = index.device
+    out = {
+        "score": torch.empty((B, k), dtype=torch.float32, device=dev),
+        "id": torch.empty((B, k), dtype=torch.int64, device=dev),
+        "hop": torch.empty((B, k), dtype=torch.int32, device=dev),
+        "score_graph_norm": torch.empty((B, k), dtype=torch.float32, device=dev),
+        "score_dense_norm": torch.empty((B, k), dtype=torch.float32, device=dev),
+        "cos": torch.empty((B, k), dtype=torch.float32, device=dev),
+        "ncand": torch.empty((B,), dtype=torch.int32, device=dev),
+        "status": torch.empty((B,), dtype=torch.int32, device=dev),
+    }
+    with torch.cuda.device(dev):
+        N.check(N.load().b200r_expand_rescore(
+            index.handle, graph.handle, Q.data_ptr(), seeds.data_ptr(), B, S, int(window), float(alpha_dense), float(alpha_graph), int(k),
+            out["score"].data_ptr(), out["id"].data_ptr(), out["hop"].data_ptr(), out["score_graph_norm"].data_ptr(),
+            out["score_dense_norm"].data_ptr(), out["cos"].data_ptr(), out["ncand"].data_ptr(), out["status"].data_ptr(),
+            _stream_ptr(dev)))
+    if check_status:
+        bad = int((out["status"] != 0).sum().item())
+        if bad:
+            raise N.B200RError(N.EOVERFLOW, f"{bad} queries reached more than {N.load().b200r_expand_max_candidates()} graph nodes")
+    return out

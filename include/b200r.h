@@ -1,0 +1,124 @@
+/* b200r.h -- C ABI of the B200-native retrieval hot path (libb200r.so).
+ *
+ * The reference (AndyUkJ/A-Modular-RAG-Framework) is pure Python; nothing in it is C.  Each entry
+ * point below therefore cites the PYTHON interface it replaces (paths relative to the reference
+ * root) -- this is what a maintainer binds with ctypes/cffi from
+ * app/modules/retrieval (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative B200R_E* code on failure;
+ *     b200r_last_error() returns the message of the calling thread's last failure;
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - the caller owns every buffer it passes in; the library borrows corpus / graph pointers for
+ *     the lifetime of the handle and allocates only its own small derived state (row norms, tensor maps);
+ *   - `stream` is a cudaStream_t passed as void*; no call synchronises the device except the
+ *     *_host convenience calls and b200r_index_create (which returns with the norms computed);
+ *   - handles are not thread-safe; distinct handles are independent;
+ *   - there is NO CPU fallback: without a CUDA device every call fails with B200R_ECUDA.
+ */
+#ifndef B200R_H_
+#define B200R_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200R_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define B200R_OK 0
+#define B200R_EINVAL -1   /* bad argument (message says which) */
+#define B200R_ECUDA -2    /* CUDA runtime/driver error */
+#define B200R_ENOMEM -3   /* workspace too small / allocation failed */
+#define B200R_EOVERFLOW -4 /* a bounded on-chip structure overflowed (graph frontier) */
+#define B200R_ESTATE -5   /* bad handle */
+
+/* element types of the corpus matrix (queries use the same type, except I8 -> F32 queries) */
+#define B200R_BF16 0
+#define B200R_F16 1
+#define B200R_F32 2
+#define B200R_I8 3
+
+/* metric.  COS == DenseReranker._cosine (retrieval_backend.py:192-197): dot/(|q||x|), 0.0 when a norm is 0 */
+#define B200R_IP 0
+#define B200R_COS 1
+
+/* search path */
+#define B200R_PATH_AUTO 0
+#define B200R_PATH_GEMM 1 /* tcgen05/TMEM/TMA tiles with the top-k fused into the epilogue (bf16/f16) */
+#define B200R_PATH_SCAN 2 /* CUDA-core streaming scan, 128-bit loads (all types; meant for B <= 4) */
+
+#define B200R_MAX_K 2048
+
+int b200r_version(void);
+/* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
+int b200r_last_error(char* buf, size_t n);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t b200r_launch_count(void);
+
+/* ---- corpus index ------------------------------------------------------------------------
+ * Replaces the per-query embedding fetch + candidate list of DenseReranker.score
+ * (retrieval_backend.py:215-247): X[N, D] row-major is the passage-embedding matrix, row n being
+ * line n of docs.jsonl (BM25LiteIndex._build, text_index.py:35-53).  Reported ids are id_base + n.
+ * row_scale (I8 only, may be NULL = 1.0): x[n, d] = row_scale[n] * X[n, d].
+ */
+int b200r_index_create(int device, const void* X, int64_t N, int32_t D, int32_t dtype, int32_t metric,
+                       int64_t id_base, const float* row_scale, void* stream, uint64_t* out_index);
+int b200r_index_destroy(uint64_t index);
+int b200r_index_info(uint64_t index, int64_t* N, int32_t* D, int32_t* dtype, int32_t* metric, int64_t* id_base);
+
+/* ---- exact top-k search --------------------------------------------------------------------
+ * Replaces `{id: _cosine(qv, v)}` + `sort(key=score, reverse=True)[:k]`
+ * (retrieval_backend.py:245, 371-372; retrieval_adapter.py:129-131) for a batch of B queries over
+ * the WHOLE corpus.  Q[B, D] row-major in the corpus dtype (F32 for an I8 corpus).
+ * out_scores[B, k] f32, out_ids[B, k] i64, ordered by (score desc, id asc); when N < k the tail is
+ * (-inf, -1).  workspace: device scratch of at least b200r_search_workspace_bytes().
+ */
+size_t b200r_search_workspace_bytes(uint64_t index, int32_t B, int32_t k, int32_t path);
+int b200r_search(uint64_t index, const void* Q, int32_t B, int32_t k, int32_t path, float* out_scores,
+                 int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream);
+/* Same call with HOST query / result buffers (what the Python plug-in hands over): copies Q to the
+ * device, searches, copies the results back and synchronises `stream`.  Uses library-owned staging
+ * buffers that grow on demand. */
+int b200r_search_host(uint64_t index, const void* Q_host, int32_t B, int32_t k, int32_t path,
+                      float* out_scores_host, int64_t* out_ids_host, void* stream);
+
+/* ---- merge of per-shard top-k lists ----------------------------------------------------------
+ * The same stable-sort rule applied to the union of G lists (one per GPU after the NCCL all-gather):
+ * cand_scores/cand_ids [G, B, kin] -> out [B, k], (score desc, id asc); ids < 0 are padding.
+ */
+int b200r_merge_topk(int device, const float* cand_scores, const int64_t* cand_ids, int32_t G, int32_t B,
+                     int32_t kin, int32_t k, float* out_scores, int64_t* out_ids, void* stream);
+
+/* ---- passage/entity graph --------------------------------------------------------------------
+ * Replaces load_graph_json + build_index (graph_utils.py:13-55), done once instead of per query:
+ * CSR of the UNDIRECTED next_in_doc adjacency (neighbours(s) = next_forward[s] + next_backward[s],
+ * graph_utils.py:123).  row_ptr[V+1] i64, col_idx[E] i32, node id == corpus row id.
+ */
+int b200r_graph_create(int device, const int64_t* row_ptr, const int32_t* col_idx, int64_t V, int64_t E,
+                       uint64_t* out_graph);
+int b200r_graph_destroy(uint64_t graph);
+
+/* Replaces expand_qmatch_neighbors (graph_utils.py:58-129) + _cosine re-score + _minmax_norm and the
+ * weighted fusion / sort / slice of HybridRetrievalBackend.run (retrieval_backend.py:296-301, 353-372)
+ * for B queries at once.  seeds[B, S] i64 are q_match targets (< 0 = padding); BFS depth <= window;
+ * graph score = decay(hop) (graph_utils.py:87-94); fused = alpha_graph*minmax(graph) + alpha_dense*minmax(cos).
+ * Outputs [B, k]: fused score, id, hop distance, the two normalised channel scores (the
+ * score_graph_norm / score_dense_norm meta keys, retrieval_backend.py:368) and the raw cosine; tail
+ * entries beyond the candidate count are (-inf, -1, -1, 0, 0, 0).  out_ncand[B] = candidates found.
+ * Fails with B200R_EOVERFLOW if a query reaches more than b200r_expand_max_candidates() nodes.
+ */
+int32_t b200r_expand_max_candidates(void);
+int b200r_expand_rescore(uint64_t index, uint64_t graph, const void* Q, const int64_t* seeds, int32_t B,
+                         int32_t S, int32_t window, float alpha_dense, float alpha_graph, int32_t k,
+                         float* out_scores, int64_t* out_ids, int32_t* out_hops, float* out_graph_norm,
+                         float* out_dense_norm, float* out_cos, int32_t* out_ncand, int32_t* out_status,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200R_H_ */

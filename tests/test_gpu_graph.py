@@ -1,0 +1,118 @@
+"""Parity of the CSR expand + re-score kernel against the golden fixtures and the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import retrieval_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _run(X_f32, q_f32, row_ptr, col_idx, seeds, window, a_d, a_g, k, dtype=torch.bfloat16):
+    from a_modular_rag_framework_b200 import DenseIndex, PassageGraph, expand_rescore
+    X = torch.from_numpy(np.ascontiguousarray(X_f32, dtype=np.float32)).to(_dev()).to(dtype)
+    Q = torch.from_numpy(np.ascontiguousarray(q_f32, dtype=np.float32)).to(_dev()).to(dtype)
+    ix = DenseIndex(X)
+    g = PassageGraph(torch.from_numpy(row_ptr.astype(np.int64)).to(_dev()), torch.from_numpy(col_idx.astype(np.int32)).to(_dev()))
+    return expand_rescore(ix, g, Q, torch.from_numpy(np.asarray(seeds, dtype=np.int64)).to(_dev()), window, a_d, a_g, k)
+
+
+def _check_query(out, b, top, dist, k, tol=2e-3):
+    ids = out["id"][b].cpu().numpy()
+    sc = out["score"][b].cpu().numpy().astype(np.float64)
+    hop = out["hop"][b].cpu().numpy()
+    n = len(top)
+    assert int(out["ncand"][b]) == len(dist)
+    assert np.all(ids[n:] == -1)
+    ref_ids = [t[0] for t in top]
+    ref_sc = np.array([t[1] for t in top])
+    # hop distances are integers: exact
+    for i in range(n):
+        assert hop[i] == dist[int(ids[i])]
+    assert np.allclose(sc[:n], ref_sc, atol=tol)
+    if list(ids[:n]) != ref_ids:
+        # only near-ties (within tol) may be permuted / swapped at the boundary
+        full = {t[0]: t[1] for t in top}
+        for i, nid in enumerate(ids[:n]):
+            assert abs(sc[i] - ref_sc[i]) <= tol
+            if int(nid) in full:
+                assert abs(full[int(nid)] - sc[i]) <= tol
+
+
+def test_golden_expand_rescore(golden_dir):
+    with open(os.path.join(golden_dir, "expand_rescore_cases.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        X = O.bf16_bits_to_f32(np.array(c["X_bf16"], dtype=np.uint16))
+        q = O.bf16_bits_to_f32(np.array(c["q_bf16"], dtype=np.uint16))
+        row_ptr, col_idx = O.csr_from_edges(c["V"], np.array(c["src"], dtype=np.int64), np.array(c["dst"], dtype=np.int64))
+        out = _run(X, q[None, :], row_ptr, col_idx, [c["seeds"]], c["window"], c["alpha_dense"], c["alpha_graph"], c["k"])
+        ids = out["id"][0].cpu().numpy()
+        n = len(c["top_ids"])
+        dist = dict(zip(c["cand"], c["dist"]))
+        assert int(out["ncand"][0]) == len(c["cand"])
+        assert np.allclose(out["score"][0].cpu().numpy()[:n], c["top_scores"], atol=2e-3)
+        got = list(ids[:n])
+        if got != c["top_ids"]:
+            # near-ties only
+            ref = dict(zip(c["top_ids"], c["top_scores"]))
+            for i, nid in enumerate(got):
+                assert abs(out["score"][0, i].item() - c["top_scores"][i]) <= 2e-3
+        for i in range(n):
+            assert int(out["hop"][0, i]) == dist[int(ids[i])]
+        assert np.allclose(out["score_graph_norm"][0].cpu().numpy()[:n][np.array(got) == np.array(c["top_ids"])],
+                           np.array(c["top_g"])[np.array(got) == np.array(c["top_ids"])], atol=1e-5)
+
+
+def test_bfs_golden_distances(golden_dir):
+    """window sweep incl. 0 (seeds only) and deep windows; distances are integer-exact."""
+    with open(os.path.join(golden_dir, "bfs_cases.json")) as f:
+        cases = json.load(f)
+    rng = np.random.default_rng(0)
+    for c in cases:
+        V = c["V"]
+        X = rng.standard_normal((V, 32)).astype(np.float32)
+        q = rng.standard_normal((1, 32)).astype(np.float32)
+        row_ptr, col_idx = O.csr_from_edges(V, np.array(c["src"], dtype=np.int64), np.array(c["dst"], dtype=np.int64))
+        k = min(max(len(c["nodes"]), 1), 2048)
+        out = _run(X, q, row_ptr, col_idx, [c["seeds"]], c["window"], 0.4, 0.2, k)
+        assert int(out["ncand"][0]) == len(c["nodes"])
+        ids = out["id"][0].cpu().numpy()[:len(c["nodes"])]
+        assert sorted(ids.tolist()) == c["nodes"]
+        dist = dict(zip(c["nodes"], c["dist"]))
+        for i, nid in enumerate(ids):
+            assert int(out["hop"][0, i]) == dist[int(nid)]
+
+
+def test_random_graph_batch_vs_oracle():
+    rng = np.random.default_rng(42)
+    V, E, D, B, S, k = 20000, 100000, 128, 64, 20, 10
+    src, dst = rng.integers(0, V, size=E), rng.integers(0, V, size=E)
+    row_ptr, col_idx = O.csr_from_edges(V, src, dst)
+    X = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((V, D)).astype(np.float32)))
+    Q = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((B, D)).astype(np.float32)))
+    seeds = rng.integers(0, V, size=(B, S))
+    seeds[:, -2:] = -1          # padding
+    seeds[:, 1] = seeds[:, 0]   # duplicate seed
+    out = _run(X, Q, row_ptr, col_idx, seeds, 2, 0.4, 0.2, k)
+    for b in range(0, B, 7):
+        top, dist = O.expand_rescore(Q[b], X, row_ptr, col_idx, seeds[b], 2, 0.4, 0.2, k)
+        _check_query(out, b, top, dist, k)
+
+
+def test_frontier_overflow_is_reported():
+    from a_modular_rag_framework_b200 import B200RError
+    V = 20000
+    src = np.zeros(V - 1, dtype=np.int64)
+    dst = np.arange(1, V, dtype=np.int64)   # a star: node 0 reaches everything in one hop
+    row_ptr, col_idx = O.csr_from_edges(V, src, dst)
+    X = np.ones((V, 8), dtype=np.float32)
+    with pytest.raises(B200RError):
+        _run(X, np.ones((1, 8), dtype=np.float32), row_ptr, col_idx, [[0]], 1, 0.4, 0.2, 10)

@@ -1,0 +1,194 @@
+"""Parity of the CUDA search paths (through the C ABI) against the oracle and the golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import retrieval_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.bfloat16: 1e-3, torch.float16: 1e-3, torch.float32: 1e-5, torch.int8: 1e-5}
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _to_dev(x_f32: np.ndarray, dtype):
+    return torch.from_numpy(np.ascontiguousarray(x_f32, dtype=np.float32)).to(_dev()).to(dtype).contiguous()
+
+
+def _as_f32(t: torch.Tensor) -> np.ndarray:
+    return t.float().cpu().numpy()
+
+
+def _check_against_scores(scores, ids, S_ref, k, tol, id_base=0):
+    scores, ids = scores.cpu().numpy(), ids.cpu().numpy()
+    B, N = S_ref.shape
+    for b in range(B):
+        kk = min(k, N)
+        O.check_topk(scores[b], ids[b], S_ref[b], k, rel_tol=tol, id_base=id_base)
+        if kk < k:
+            assert np.all(ids[b, kk:] == -1) and np.all(np.isneginf(scores[b, kk:]))
+        # bit-equal returned scores must come in ascending id order (ties -> lower id)
+        s = scores[b, :kk]
+        same = s[1:] == s[:-1]
+        assert np.all(ids[b, 1:kk][same] > ids[b, :kk - 1][same])
+
+
+def _index(X, metric="cos", **kw):
+    from a_modular_rag_framework_b200 import DenseIndex
+    return DenseIndex(X, metric=metric, **kw)
+
+
+@pytest.mark.parametrize("name,dtype,paths", [
+    ("topk_bf16_n600_d64.npz", torch.bfloat16, ("scan", "gemm")),
+    ("topk_f16_n300_d384.npz", torch.float16, ("scan", "gemm")),
+    ("topk_f32_n400_d48.npz", torch.float32, ("scan",)),
+])
+def test_golden_fixtures(golden_dir, name, dtype, paths):
+    z = np.load(os.path.join(golden_dir, name))
+    X, Q, S = _to_dev(z["X"], dtype), _to_dev(z["Q"], dtype), z["S"]
+    assert np.array_equal(_as_f32(X), z["X"]) and np.array_equal(_as_f32(Q), z["Q"])  # fixtures are exactly representable
+    ix = _index(X)
+    for key in z.files:
+        if not key.startswith("ids_k"):
+            continue
+        k = int(key[5:])
+        for path in paths:
+            scores, ids = ix.search(Q, k, path=path)
+            _check_against_scores(scores, ids, S, k, TOL[dtype])
+            # the reference's exact-tie groups (duplicated rows 3, 7, N/2, N-1) must appear lowest id first,
+            # and the all-zero query must return ids 0..k-1 with score 0.0
+            ids_np = ids.cpu().numpy()
+            kk = min(k, X.shape[0])
+            assert np.array_equal(ids_np[-1, :kk], np.arange(kk)), (path, k)
+            assert np.all(scores.cpu().numpy()[-1, :kk] == 0.0)
+            ref_ids = z[key]
+            b = Q.shape[0] - 2  # query == row 3: its duplicates lead the list in id order
+            assert np.array_equal(ids_np[b, :min(4, kk)], ref_ids[b, :min(4, kk)])
+
+
+@pytest.mark.parametrize("N,D,B,k,path,dtype,metric", [
+    (20000, 128, 37, 100, "gemm", torch.bfloat16, "cos"),
+    (20000, 128, 3, 100, "scan", torch.bfloat16, "cos"),
+    (5000, 72, 129, 10, "gemm", torch.bfloat16, "cos"),      # D % 64 != 0, two query tiles
+    (70000, 64, 300, 10, "gemm", torch.float16, "ip"),
+    (9000, 768, 16, 100, "gemm", torch.bfloat16, "cos"),
+    (9000, 768, 16, 100, "auto", torch.bfloat16, "cos"),
+    (9000, 768, 1, 100, "auto", torch.bfloat16, "cos"),
+    (3001, 96, 7, 1000, "gemm", torch.bfloat16, "cos"),
+    (3001, 96, 2, 1000, "scan", torch.float16, "cos"),
+    (4000, 100, 5, 50, "scan", torch.float32, "cos"),
+    (4000, 100, 9, 50, "scan", torch.float32, "ip"),
+    (50, 64, 6, 100, "gemm", torch.bfloat16, "cos"),         # N < k
+    (50, 64, 2, 100, "scan", torch.bfloat16, "cos"),
+    (1, 8, 1, 1, "scan", torch.bfloat16, "cos"),
+    (257, 8, 5, 3, "gemm", torch.bfloat16, "cos"),
+])
+def test_random_vs_oracle(N, D, B, k, path, dtype, metric):
+    rng = np.random.default_rng(N * 31 + D + B)
+    X = _to_dev(rng.standard_normal((N, D)), dtype)
+    Q = _to_dev(rng.standard_normal((B, D)), dtype)
+    S = O.score_matrix(_as_f32(Q), _as_f32(X), metric)
+    ix = _index(X, metric=metric, id_base=1000)
+    scores, ids = ix.search(Q, k, path=path)
+    _check_against_scores(scores, ids, S, k, TOL[dtype], id_base=1000)
+
+
+@pytest.mark.parametrize("path,B", [("gemm", 40), ("scan", 4)])
+def test_exact_integer_data_bit_exact_ids(path, B):
+    """Small-integer vectors make every product and sum exact in fp32, so ids (ties included) must
+    equal the oracle's stable-sort order exactly."""
+    rng = np.random.default_rng(7)
+    N, D, k = 6000, 64, 100
+    X = rng.integers(-2, 3, size=(N, D)).astype(np.float32)
+    Qn = rng.integers(-2, 3, size=(B, D)).astype(np.float32)
+    Xd, Qd = _to_dev(X, torch.bfloat16), _to_dev(Qn, torch.bfloat16)
+    ref_s, ref_i = O.topk(Qn, X, k, metric="ip")
+    ix = _index(Xd, metric="ip")
+    scores, ids = ix.search(Qd, k, path=path)
+    assert np.array_equal(ids.cpu().numpy(), ref_i)
+    assert np.array_equal(scores.cpu().numpy().astype(np.float64), ref_s)
+
+
+def test_constant_vectors_all_tie():
+    """The Ollama mock provider returns constant vectors (reference ollama_provider.py:26-28): every
+    cosine ties, so the result is ids 0..k-1."""
+    X = torch.full((3000, 64), 0.1, device=_dev(), dtype=torch.bfloat16)
+    Q = torch.full((5, 64), 0.1, device=_dev(), dtype=torch.bfloat16)
+    ix = _index(X)
+    for path in ("gemm", "scan"):
+        scores, ids = ix.search(Q, 20, path=path)
+        assert np.array_equal(ids.cpu().numpy(), np.tile(np.arange(20), (5, 1))), path
+        assert np.allclose(scores.cpu().numpy(), 1.0, atol=1e-3)
+
+
+def test_int8_corpus_scan():
+    rng = np.random.default_rng(11)
+    N, D, B, k = 5000, 128, 3, 20
+    Xf = rng.standard_normal((N, D)).astype(np.float32)
+    q8, scale = O.quantize_int8_rows(Xf)
+    Qn = rng.standard_normal((B, D)).astype(np.float32)
+    X = torch.from_numpy(q8).to(_dev())
+    Q = torch.from_numpy(Qn).to(_dev())
+    deq = q8.astype(np.float32) * scale[:, None]
+    for metric in ("cos", "ip"):
+        ix = _index(X, metric=metric, row_scale=torch.from_numpy(scale).to(_dev()))
+        scores, ids = ix.search(Q, k)
+        _check_against_scores(scores, ids, O.score_matrix(Qn, deq, metric), k, 1e-5)
+
+
+def test_multi_chunk_large():
+    """Several units per CTA and per query (chunked rows, published thresholds)."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    N, D, B, k = 300000, 64, 200, 100
+    X = torch.randn((N, D), generator=g, device=_dev()).to(torch.bfloat16)
+    Q = torch.randn((B, D), generator=g, device=_dev()).to(torch.bfloat16)
+    ix = _index(X)
+    scores, ids = ix.search(Q, k, path="gemm")
+    sub = [0, 1, 99, 127, 128, 199]
+    S = O.score_matrix(_as_f32(Q[sub]), _as_f32(X))
+    _check_against_scores(scores[sub], ids[sub], S, k, 1e-3)
+    s2, i2 = ix.search(Q[:3].contiguous(), k, path="scan")
+    _check_against_scores(s2, i2, O.score_matrix(_as_f32(Q[:3]), _as_f32(X)), k, 1e-3)
+
+
+def test_search_host_matches_device():
+    g = torch.Generator(device="cuda").manual_seed(9)
+    X = torch.randn((10000, 64), generator=g, device=_dev()).to(torch.bfloat16)
+    Q = torch.randn((33, 64), generator=g, device=_dev()).to(torch.bfloat16)
+    ix = _index(X)
+    s_dev, i_dev = ix.search(Q, 10)
+    s_h, i_h = ix.search_host(Q.cpu().pin_memory(), 10)
+    assert torch.equal(i_dev.cpu(), i_h) and torch.equal(s_dev.cpu(), s_h)
+
+
+def test_merge_topk_vs_oracle():
+    from a_modular_rag_framework_b200 import merge_topk
+    rng = np.random.default_rng(2)
+    G, B, kin, k = 8, 9, 100, 100
+    sc = rng.standard_normal((G, B, kin)).astype(np.float32)
+    sc[:, :, 5] = 0.25  # cross-shard exact ties
+    ids = np.stack([np.stack([rng.permutation(1000)[:kin] + g * 1000 for _ in range(B)]) for g in range(G)]).astype(np.int64)
+    ids[3, :, 90:] = -1  # padding
+    ms, mi = merge_topk(torch.from_numpy(sc).to(_dev()), torch.from_numpy(ids).to(_dev()), k)
+    rs, ri = O.merge_topk(sc.transpose(1, 0, 2), ids.transpose(1, 0, 2), k)
+    assert np.array_equal(mi.cpu().numpy(), ri)
+    assert np.array_equal(ms.cpu().numpy(), rs)
+
+
+def test_bad_arguments_raise():
+    from a_modular_rag_framework_b200 import B200RError, DenseIndex
+    X = torch.zeros((16, 8), device=_dev(), dtype=torch.bfloat16)
+    ix = DenseIndex(X)
+    with pytest.raises(B200RError):
+        ix.search(torch.zeros((1, 8), device=_dev(), dtype=torch.bfloat16), 5000)
+    with pytest.raises(ValueError):
+        ix.search(torch.zeros((1, 8), device=_dev(), dtype=torch.float32), 5)
+    with pytest.raises(ValueError):
+        DenseIndex(torch.zeros((16, 8), dtype=torch.bfloat16))
+    with pytest.raises(B200RError):
+        DenseIndex(torch.zeros((16, 4), device=_dev(), dtype=torch.bfloat16))  # rows not 16-byte aligned
