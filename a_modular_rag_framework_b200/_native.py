@@ -21,7 +21,7 @@ EXPORTS = [
     "b200r_version", "b200r_last_error", "b200r_launch_count",
     "b200r_index_create", "b200r_index_destroy", "b200r_index_info",
     "b200r_search_workspace_bytes", "b200r_search", "b200r_search_host",
-    "b200r_merge_topk",
+    "b200r_merge_topk", "b200r_merge_topk_packed", "b200r_profile_enable", "b200r_profile_read",
     "b200r_graph_create", "b200r_graph_destroy",
     "b200r_expand_max_candidates", "b200r_expand_rescore",
 ]
@@ -63,6 +63,9 @@ def load() -> ctypes.CDLL:
     lib.b200r_search.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.b200r_search_host.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
     lib.b200r_merge_topk.argtypes = [c_int, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.b200r_merge_topk_packed.argtypes = [c_int, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.b200r_profile_enable.argtypes = [c_int]
+    lib.b200r_profile_read.argtypes = [POINTER(ctypes.c_double), POINTER(c_int64)]
     lib.b200r_graph_create.argtypes = [c_int, c_void_p, c_void_p, c_int64, c_int64, POINTER(c_uint64)]
     lib.b200r_graph_destroy.argtypes = [c_uint64]
     lib.b200r_expand_max_candidates.restype = c_int32
@@ -89,3 +92,14 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(load().b200r_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    check(load().b200r_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """-> (summed device ms of the dominant search kernel since the last read, number of launches)"""
+    ms, n = ctypes.c_double(0.0), c_int64(0)
+    check(load().b200r_profile_read(ctypes.byref(ms), ctypes.byref(n)))
+    return float(ms.value), int(n.value)

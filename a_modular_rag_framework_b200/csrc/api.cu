@@ -7,6 +7,7 @@
 #include <cstring>
 #include <cmath>
 #include <new>
+#include <vector>
 
 namespace b200r {
 
@@ -20,6 +21,21 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- optional event bracketing of the dominant kernel (b200r_profile_*) ----
+static bool g_prof_on = false;
+static std::vector<cudaEvent_t> g_prof_events;  // start0, stop0, start1, stop1, ...
+void profile_begin(cudaStream_t st) {
+  if (!g_prof_on) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); g_prof_events.push_back(e); }
+}
+void profile_end(cudaStream_t st) {
+  if (!g_prof_on || (g_prof_events.size() & 1) == 0) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); g_prof_events.push_back(e); }
+  else { cudaEventDestroy(g_prof_events.back()); g_prof_events.pop_back(); }
+}
 
 int gemm_tile_rows();
 int gemm_tile_queries();
@@ -149,8 +165,10 @@ static int do_search(Index* ix, const void* Q, int B, int k, int path, float* ou
     float* qinv = reinterpret_cast<float*>((char*)ws + pl.off_qinv);
     if ((rc = launch_query_inv_norm(Q, B, ix->D, query_dtype(ix), qinv, st))) return rc;
   }
+  profile_begin(st);
   if (pl.path == B200R_PATH_GEMM) rc = launch_gemm_topk(ix, Q, pl, ws, st);
   else rc = launch_scan_topk(ix, Q, pl, ws, st);
+  profile_end(st);
   if (rc) return rc;
   return launch_select_lists(ix, pl, ws, out_scores, out_ids, st);
 }
@@ -300,7 +318,47 @@ int b200r_merge_topk(int device, const float* cand_scores, const int64_t* cand_i
   if (!cand_scores || !cand_ids || !out_scores || !out_ids) { set_error("null pointer"); return B200R_EINVAL; }
   if (G <= 0 || B <= 0 || kin <= 0 || k <= 0) { set_error("G, B, kin, k must be > 0"); return B200R_EINVAL; }
   B200R_CUDA_CHECK(cudaSetDevice(device));
-  return launch_merge_topk(cand_scores, cand_ids, G, B, kin, k, out_scores, out_ids, reinterpret_cast<cudaStream_t>(stream));
+  return launch_merge_topk(cand_scores, cand_ids, (size_t)B * kin, (size_t)B * kin, G, B, kin, k, out_scores, out_ids,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200r_merge_topk_packed(int device, const void* packed, int32_t G, int32_t B, int32_t kin, int32_t k, float* out_scores,
+                            int64_t* out_ids, void* stream) {
+  if (!packed || !out_scores || !out_ids) { set_error("null pointer"); return B200R_EINVAL; }
+  if (G <= 0 || B <= 0 || kin <= 0 || k <= 0) { set_error("G, B, kin, k must be > 0"); return B200R_EINVAL; }
+  B200R_CUDA_CHECK(cudaSetDevice(device));
+  const size_t n = (size_t)B * kin;
+  const int64_t* ids = reinterpret_cast<const int64_t*>(packed);
+  const float* scores = reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + n * 8);
+  // one record = n*8 + n*4 bytes: 1.5*n int64 elements, 3*n float elements
+  if (n % 2) { set_error("merge_topk_packed needs B*kin even (record stride must be a whole number of int64)"); return B200R_EINVAL; }
+  return launch_merge_topk(scores, ids, 3 * n, n + n / 2, G, B, kin, k, out_scores, out_ids, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200r_profile_enable(int on) {
+  g_prof_on = on != 0;
+  if (!g_prof_on) {
+    for (cudaEvent_t e : g_prof_events) cudaEventDestroy(e);
+    g_prof_events.clear();
+  }
+  return B200R_OK;
+}
+
+int b200r_profile_read(double* kernel_ms, int64_t* launches) {
+  double total = 0.0;
+  int64_t n = 0;
+  for (size_t i = 0; i + 1 < g_prof_events.size(); i += 2) {
+    float ms = 0.f;
+    B200R_CUDA_CHECK(cudaEventSynchronize(g_prof_events[i + 1]));
+    B200R_CUDA_CHECK(cudaEventElapsedTime(&ms, g_prof_events[i], g_prof_events[i + 1]));
+    total += ms;
+    ++n;
+  }
+  for (cudaEvent_t e : g_prof_events) cudaEventDestroy(e);
+  g_prof_events.clear();
+  if (kernel_ms) *kernel_ms = total;
+  if (launches) *launches = n;
+  return B200R_OK;
 }
 
 int b200r_graph_create(int device, const int64_t* row_ptr, const int32_t* col_idx, int64_t V, int64_t E, uint64_t* out_graph) {

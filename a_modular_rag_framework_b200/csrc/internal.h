@@ -80,7 +80,10 @@ int launch_init_search(const SearchPlan& p, void* ws, cudaStream_t st);
 int launch_gemm_topk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
 int launch_scan_topk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
 int launch_select_lists(const Index* ix, const SearchPlan& p, void* ws, float* out_scores, int64_t* out_ids, cudaStream_t st);
-int launch_merge_topk(const float* cs, const int64_t* ci, int G, int B, int kin, int k, float* os, int64_t* oi, cudaStream_t st);
+int launch_merge_topk(const float* cs, const int64_t* ci, size_t shard_stride_s, size_t shard_stride_i, int G, int B, int kin, int k,
+                      float* os, int64_t* oi, cudaStream_t st);
+void profile_begin(cudaStream_t st);
+void profile_end(cudaStream_t st);
 int launch_expand_rescore(const Index* ix, const Graph* g, const void* Q, const int64_t* seeds, int B, int S, int window,
                           float alpha_dense, float alpha_graph, int k, float* out_scores, int64_t* out_ids, int32_t* out_hops,
                           float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand, int32_t* out_status, cudaStream_t st);

@@ -148,6 +148,7 @@ constexpr int MERGE_THREADS = 256;
 struct MergeParams {
   const float* cs;
   const long long* ci;
+  size_t stride_s, stride_i;   // elements between consecutive shards
   int G, B, kin, k, np2;
   float* os;
   long long* oi;
@@ -167,9 +168,9 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const MergePa
     u32 s = 0; long long id = 0x7fffffffffffffffll;
     if (i < n) {
       const int g = i / p.kin, j = i % p.kin;
-      const size_t off = ((size_t)g * p.B + q) * p.kin + j;
-      const long long cid = p.ci[off];
-      if (cid >= 0) { id = cid; s = f32_to_ordered(p.cs[off] + 0.0f); }
+      const size_t off = (size_t)q * p.kin + j;
+      const long long cid = p.ci[(size_t)g * p.stride_i + off];
+      if (cid >= 0) { id = cid; s = f32_to_ordered(p.cs[(size_t)g * p.stride_s + off] + 0.0f); }
     }
     sc[i] = s; ids[i] = id;
   }
@@ -195,11 +196,12 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const MergePa
   }
 }
 
-int launch_merge_topk(const float* cs, const int64_t* ci, int G, int B, int kin, int k, float* os, int64_t* oi, cudaStream_t st) {
+int launch_merge_topk(const float* cs, const int64_t* ci, size_t shard_stride_s, size_t shard_stride_i, int G, int B, int kin, int k,
+                      float* os, int64_t* oi, cudaStream_t st) {
   const long long n = (long long)G * kin;
   if (n > 16384) { set_error("merge_topk: G*kin = %lld exceeds 16384", n); return B200R_EINVAL; }
   MergeParams p;
-  p.cs = cs; p.ci = reinterpret_cast<const long long*>(ci); p.G = G; p.B = B; p.kin = kin; p.k = k;
+  p.cs = cs; p.ci = reinterpret_cast<const long long*>(ci); p.stride_s = shard_stride_s; p.stride_i = shard_stride_i; p.G = G; p.B = B; p.kin = kin; p.k = k;
   p.np2 = next_pow2((int)n < 2 ? 2 : (int)n);
   p.os = os; p.oi = reinterpret_cast<long long*>(oi);
   const size_t smem = (size_t)p.np2 * 12;

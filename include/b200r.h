@@ -93,6 +93,18 @@ int b200r_search_host(uint64_t index, const void* Q_host, int32_t B, int32_t k, 
 int b200r_merge_topk(int device, const float* cand_scores, const int64_t* cand_ids, int32_t G, int32_t B,
                      int32_t kin, int32_t k, float* out_scores, int64_t* out_ids, void* stream);
 
+/* Same merge over the layout the all-gather of one packed buffer per rank produces:
+ * packed = G records, each [ids i64 [B, kin] | scores f32 [B, kin]] (12*B*kin bytes). */
+int b200r_merge_topk_packed(int device, const void* packed, int32_t G, int32_t B, int32_t kin, int32_t k,
+                            float* out_scores, int64_t* out_ids, void* stream);
+
+/* ---- kernel timing (bench.py's roofline leg) --------------------------------------------------
+ * When enabled, the library brackets every launch of its DOMINANT search kernel (gemm_topk or
+ * scan_topk) with CUDA events on the caller's stream.  b200r_profile_read synchronises those events and
+ * returns the summed device time in ms and the number of bracketed launches (and clears them). */
+int b200r_profile_enable(int on);
+int b200r_profile_read(double* kernel_ms, int64_t* launches);
+
 /* ---- passage/entity graph --------------------------------------------------------------------
  * Replaces load_graph_json + build_index (graph_utils.py:13-55), done once instead of per query:
  * CSR of the UNDIRECTED next_in_doc adjacency (neighbours(s) = next_forward[s] + next_backward[s],
