@@ -118,10 +118,39 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
       const double waste = (double)(waves * grid_max) / (double)units * (double)(tpc * cc) / (double)pl->num_row_tiles;
       if (waste < best_waste - 1e-9) { best_waste = waste; best = (int)cc; }
     }
-    pl->tiles_per_chunk = (pl->num_row_tiles + best - 1) / best;
-    pl->num_chunks = (pl->num_row_tiles + pl->tiles_per_chunk - 1) / pl->tiles_per_chunk;
-    pl->num_units = pl->num_chunks * pl->num_q_tiles;
-    pl->grid = pl->num_units < grid_max ? pl->num_units : grid_max;
+    {
+      const int tpc = (pl->num_row_tiles + best - 1) / best;
+      pl->num_chunks = (pl->num_row_tiles + tpc - 1) / tpc;
+    }
+    // Phase schedule.  Phase 0 starts with no threshold, so every score is a candidate: keep it tiny and
+    // spread it over enough lists that none overflows (rows per list <= cap_soft - 32).  Each later phase
+    // covers ~8x the rows seen so far, which bounds the survivors per query per phase by ~7k.
+    const int T = pl->num_row_tiles;
+    const int C = pl->num_chunks;
+    int seen = 0, np = 0;
+    int want0 = (10 * k + BNr - 1) / BNr;
+    if (want0 < 4) want0 = 4;
+    int tpc0 = (pl->cap_soft - 32) / BNr;
+    if (tpc0 < 1) tpc0 = 1;
+    if (want0 > C * tpc0) want0 = C * tpc0;
+    while (seen < T && np < kMaxPhases) {
+      int end;
+      if (np == 0) end = want0 < T ? want0 : T;
+      else {
+        long long e = (long long)seen * 8;
+        end = e < T ? (int)e : T;
+        if (T - end < end / 2 || np == kMaxPhases - 1) end = T;   // fold a short tail into this phase
+      }
+      GemmPhase& ph = pl->phases[np];
+      ph.tile_begin = seen; ph.tile_end = end;
+      const int tiles = end - seen;
+      int chunks = tiles < C ? tiles : C;
+      if (np == 0) { const int need = (tiles + tpc0 - 1) / tpc0; chunks = need < C ? need : C; }
+      ph.tiles_per_chunk = (tiles + chunks - 1) / chunks;
+      ph.num_chunks = (tiles + ph.tiles_per_chunk - 1) / ph.tiles_per_chunk;
+      seen = end; ++np;
+    }
+    pl->num_phases = np;
     pl->num_segments = pl->num_chunks;
   } else {
     pl->Bpad = B;
@@ -165,11 +194,22 @@ static int do_search(Index* ix, const void* Q, int B, int k, int path, float* ou
     float* qinv = reinterpret_cast<float*>((char*)ws + pl.off_qinv);
     if ((rc = launch_query_inv_norm(Q, B, ix->D, query_dtype(ix), qinv, st))) return rc;
   }
-  profile_begin(st);
-  if (pl.path == B200R_PATH_GEMM) rc = launch_gemm_topk(ix, Q, pl, ws, st);
-  else rc = launch_scan_topk(ix, Q, pl, ws, st);
-  profile_end(st);
-  if (rc) return rc;
+  if (pl.path == B200R_PATH_GEMM) {
+    CUtensorMap tmap_q;
+    if ((rc = encode_query_tmap(ix, Q, B, &tmap_q))) return rc;
+    for (int i = 0; i < pl.num_phases; ++i) {
+      profile_begin(st);
+      rc = launch_gemm_topk(ix, &tmap_q, pl, pl.phases[i], ws, st);
+      profile_end(st);
+      if (rc) return rc;
+      if (i + 1 < pl.num_phases && (rc = launch_select_lists(ix, pl, ws, nullptr, nullptr, st))) return rc;
+    }
+  } else {
+    profile_begin(st);
+    rc = launch_scan_topk(ix, Q, pl, ws, st);
+    profile_end(st);
+    if (rc) return rc;
+  }
   return launch_select_lists(ix, pl, ws, out_scores, out_ids, st);
 }
 

@@ -22,6 +22,7 @@
 // CTAs that share a chunk stream the same X tiles at the same time and hit them in L2.
 #include "common.cuh"
 #include "internal.h"
+#include <math_constants.h>
 
 namespace b200r {
 
@@ -40,7 +41,8 @@ constexpr int GEMM_SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 
 struct GemmTopkParams {
   int B, k, D;
   long long N;
-  int num_q_tiles, num_row_tiles, tiles_per_chunk, num_chunks, num_units;
+  int num_q_tiles, num_row_tiles;
+  int tile_begin, tile_end, tiles_per_chunk, num_units;   // this phase: row tiles [tile_begin, tile_end) cut into chunks
   int cap, cap_soft, Bpad;
   const float* row_mult;
   u64* lists;
@@ -171,8 +173,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
         const int q_tile = u % p.num_q_tiles;
         const int chunk = u / p.num_q_tiles;
-        const int t0 = chunk * p.tiles_per_chunk;
-        const int t1 = min(p.num_row_tiles, t0 + p.tiles_per_chunk);
+        const int t0 = p.tile_begin + chunk * p.tiles_per_chunk;
+        const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -191,8 +193,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       u32 tile_iter = 0;
       for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
         const int chunk = u / p.num_q_tiles;
-        const int t0 = chunk * p.tiles_per_chunk;
-        const int t1 = min(p.num_row_tiles, t0 + p.tiles_per_chunk);
+        const int t0 = p.tile_begin + chunk * p.tiles_per_chunk;
+        const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
         for (int t = t0; t < t1; ++t, ++tile_iter) {
           const u32 acc = tile_iter & 1;
           mbar_wait(&tmem_empty_bar[acc], ((tile_iter >> 1) & 1) ^ 1);
@@ -225,13 +227,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
       const int q_tile = u % p.num_q_tiles;
       const int chunk = u / p.num_q_tiles;
-      const int t0 = chunk * p.tiles_per_chunk;
-      const int t1 = min(p.num_row_tiles, t0 + p.tiles_per_chunk);
+      const int t0 = p.tile_begin + chunk * p.tiles_per_chunk;
+      const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
+      if (t0 >= t1) continue;                 // empty chunk in a short phase (uniform across roles)
       const int q = q_tile * BM + q_lane;
       const bool valid = q < p.B;
       const size_t slot = (size_t)chunk * p.Bpad + (size_t)q_tile * BM + q_lane;
       u64* my_list = p.lists + slot * (size_t)p.cap;
-      int cnt = 0;
+      int cnt = valid ? __ldcg(p.counts + slot) : 0;   // lists persist across phases (ids keep increasing)
       u64 kth_key = 0;
       float thr = valid ? ordered_to_f32(__ldcg(p.gthr + q)) : __int_as_float(0x7f800000);
 
@@ -264,7 +267,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
           }
           float s[32];
-          bool any = false;
+          float cmax = -CUDART_INF_F;          // fmaxf drops NaN (rows beyond N), so they never pass
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 m4 = *reinterpret_cast<const float4*>(mult + c * 32 + j);
@@ -272,13 +275,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             s[j + 1] = __uint_as_float(v[j + 1]) * m4.y;
             s[j + 2] = __uint_as_float(v[j + 2]) * m4.z;
             s[j + 3] = __uint_as_float(v[j + 3]) * m4.w;
-            any |= (s[j] >= thr) | (s[j + 1] >= thr) | (s[j + 2] >= thr) | (s[j + 3] >= thr);
+            cmax = fmaxf(cmax, fmaxf(fmaxf(s[j], s[j + 1]), fmaxf(s[j + 2], s[j + 3])));
           }
-          if (__any_sync(kFullMask, any)) {
-            if (any) {
+          if (__any_sync(kFullMask, cmax >= thr)) {
+            // rare path, kept warp-uniform: one vote per column, only lanes that pass do work
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (s[j] >= thr) {
+            for (int j = 0; j < 32; ++j) {
+              const bool pj = s[j] >= thr;
+              if (__any_sync(kFullMask, pj)) {
+                if (pj) {
                   const u64 key = make_key(s[j], row0 + c * 32 + j);
                   if (key > kth_key) { __stcg(my_list + cnt, key); ++cnt; }
                 }
@@ -317,15 +322,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------ host
-int launch_gemm_topk(const Index* ix, const void* Q, const SearchPlan& pl, void* ws, cudaStream_t st) {
+int encode_query_tmap(const Index* ix, const void* Q, int B, CUtensorMap* tmap_q) {
   if (!ix->has_tmap) { set_error("gemm path needs a bf16/f16 corpus with D %% 8 == 0"); return B200R_EINVAL; }
-  CUtensorMap tmap_q;
-  int rc = encode_tmap_2d(&tmap_q, ix->dtype, Q, (uint64_t)ix->D, (uint64_t)pl.B, BK, BM);
-  if (rc) return rc;
+  return encode_tmap_2d(tmap_q, ix->dtype, Q, (uint64_t)ix->D, (uint64_t)B, BK, BM);
+}
+
+int launch_gemm_topk(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& pl, const GemmPhase& ph, void* ws, cudaStream_t st) {
   GemmTopkParams p;
   p.B = pl.B; p.k = pl.k; p.D = ix->D; p.N = ix->N;
-  p.num_q_tiles = pl.num_q_tiles; p.num_row_tiles = pl.num_row_tiles; p.tiles_per_chunk = pl.tiles_per_chunk;
-  p.num_chunks = pl.num_chunks; p.num_units = pl.num_units;
+  p.num_q_tiles = pl.num_q_tiles; p.num_row_tiles = pl.num_row_tiles;
+  p.tile_begin = ph.tile_begin; p.tile_end = ph.tile_end; p.tiles_per_chunk = ph.tiles_per_chunk;
+  p.num_units = ph.num_chunks * pl.num_q_tiles;
   p.cap = pl.cap; p.cap_soft = pl.cap_soft; p.Bpad = pl.Bpad;
   p.row_mult = ix->row_mult;
   p.lists = reinterpret_cast<u64*>((char*)ws + pl.off_lists);
@@ -336,7 +343,8 @@ int launch_gemm_topk(const Index* ix, const void* Q, const SearchPlan& pl, void*
   const u32 fmt = (ix->dtype == B200R_BF16) ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((u32)(BN >> 3) << 17) | ((u32)(BM >> 4) << 24);
   B200R_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  gemm_topk_kernel<<<pl.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(tmap_q, ix->tmap_x, p);
+  const int grid = p.num_units < kNumSMs ? p.num_units : kNumSMs;
+  gemm_topk_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(*tmap_q, ix->tmap_x, p);
   count_launch();
   B200R_CUDA_CHECK(cudaGetLastError());
   return B200R_OK;

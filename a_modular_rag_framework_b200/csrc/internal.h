@@ -57,14 +57,20 @@ inline int list_cap_soft(int k) { return k <= 256 ? 512 : 2 * k; }
 inline int list_cap(int k) { return list_cap_soft(k) + 32; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+constexpr int kMaxPhases = 16;
+struct GemmPhase { int tile_begin, tile_end, num_chunks, tiles_per_chunk; };
+
 // ---- plan of one search: how the corpus is cut into units and where the partial lists live -------
 struct SearchPlan {
   int path;             // B200R_PATH_GEMM / B200R_PATH_SCAN
   int B, k, cap, cap_soft;
   int Bpad;             // list slots per segment (>= B)
   int num_segments;     // lists per query
-  // gemm
-  int num_q_tiles, num_row_tiles, tiles_per_chunk, num_chunks, num_units, grid;
+  // gemm: row tiles are processed in phases [tile_begin, tile_end) of geometrically growing size; after each
+  // phase the exact k-th best so far becomes every query's filter threshold for the next one
+  int num_q_tiles, num_row_tiles, num_chunks;
+  int num_phases;
+  GemmPhase phases[kMaxPhases];
   // scan
   int scan_bq, scan_warps, scan_blocks;
   // workspace layout (byte offsets)
@@ -77,8 +83,10 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* plan);
 int launch_row_mult(const Index* ix, const float* row_scale, cudaStream_t st);
 int launch_query_inv_norm(const void* Q, int B, int D, int qdtype, float* qinv, cudaStream_t st);
 int launch_init_search(const SearchPlan& p, void* ws, cudaStream_t st);
-int launch_gemm_topk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
+int encode_query_tmap(const Index* ix, const void* Q, int B, CUtensorMap* tmap_q);
+int launch_gemm_topk(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& p, const GemmPhase& ph, void* ws, cudaStream_t st);
 int launch_scan_topk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
+// out_scores == nullptr: threshold mode (publish the exact k-th best so far into gthr); else final output
 int launch_select_lists(const Index* ix, const SearchPlan& p, void* ws, float* out_scores, int64_t* out_ids, cudaStream_t st);
 int launch_merge_topk(const float* cs, const int64_t* ci, size_t shard_stride_s, size_t shard_stride_i, int G, int B, int kin, int k,
                       float* os, int64_t* oi, cudaStream_t st);

@@ -13,28 +13,49 @@
 namespace b200r {
 
 constexpr int SEL_THREADS = 512;
+constexpr int SEL_WARPS = SEL_THREADS / 32;
+constexpr int SEL_STAGE_MAX = 6144;   // keys staged in shared memory (48 KB) -> 4 CTAs/SM
 
 struct SelectParams {
   const u64* lists;
   const int* counts;
-  int S, Bpad, cap, scan_len;  // scan_len: entries per list that can be valid (<= cap)
-  int B, k, kp2;
+  int S, Bpad, cap;
+  int B, k, kp2, stage_cap;
   const float* qinv;           // nullable
+  u32* gthr;
   long long id_base;
-  float* out_scores;
+  float* out_scores;           // nullptr => threshold mode
   long long* out_ids;
 };
 
+// Visit every valid key of query q: from the shared-memory stage if the keys were staged, else from
+// the per-segment lists in global memory (one warp per segment, lanes stride the list).
+template <typename F>
+__device__ __forceinline__ void for_each_key(const SelectParams& p, int q, bool staged, const u64* stage, int total, F f) {
+  if (staged) {
+    for (int i = threadIdx.x; i < total; i += SEL_THREADS) f(stage[i]);
+  } else {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int s = warp; s < p.S; s += SEL_WARPS) {
+      const size_t slot = (size_t)s * p.Bpad + q;
+      const int c = p.counts[slot];
+      const u64* lp = p.lists + slot * (size_t)p.cap;
+      for (int i = lane; i < c; i += 32) f(lp[i]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(SEL_THREADS) select_lists_kernel(const SelectParams p) {
   extern __shared__ uint8_t smem_raw[];
-  u64* sk = reinterpret_cast<u64*>(smem_raw);               // [kp2]
-  u32* hist = reinterpret_cast<u32*>(sk + p.kp2);           // [256]
+  u64* stage = reinterpret_cast<u64*>(smem_raw);            // [stage_cap]
+  u64* sk = stage + p.stage_cap;                            // [kp2] (output mode)
+  __shared__ u32 hist[256];
   __shared__ u64 s_prefix;
   __shared__ int s_remaining, s_total, s_nout;
 
   const int q = blockIdx.x;
-  const int tid = threadIdx.x;
-  const long long vtotal = (long long)p.S * p.scan_len;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool output = p.out_scores != nullptr;
 
   if (tid == 0) { s_total = 0; s_nout = 0; s_prefix = 0; }
   __syncthreads();
@@ -45,10 +66,26 @@ __global__ void __launch_bounds__(SEL_THREADS) select_lists_kernel(const SelectP
   }
   __syncthreads();
   const int total = s_total;
-  const int want = total < p.k ? total : p.k;
+  if (!output && total < p.k) return;   // not enough candidates yet for a threshold
+  const bool staged = total <= p.stage_cap;
+  if (staged) {
+    // gather the valid keys: one warp per segment, coalesced
+    for (int s = warp; s < p.S; s += SEL_WARPS) {
+      const size_t slot = (size_t)s * p.Bpad + q;
+      const int c = p.counts[slot];
+      if (c == 0) continue;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_nout, c);
+      base = __shfl_sync(kFullMask, base, 0);
+      const u64* lp = p.lists + slot * (size_t)p.cap;
+      for (int i = lane; i < c; i += 32) stage[base + i] = lp[i];
+    }
+    __syncthreads();
+    if (tid == 0) s_nout = 0;
+  }
 
   u64 kth = 0;
-  if (total > p.k) {
+  if (total > p.k || !output) {   // threshold mode always has total >= k here (k-th largest of exactly k = the minimum)
     if (tid == 0) s_remaining = p.k;
     for (int pass = 7; pass >= 0; --pass) {
       const int shift = pass * 8;
@@ -56,17 +93,11 @@ __global__ void __launch_bounds__(SEL_THREADS) select_lists_kernel(const SelectP
       __syncthreads();
       const u64 prefix = s_prefix;
       const u64 hi_mask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
-      for (long long v = tid; v < vtotal; v += SEL_THREADS) {
-        const int seg = (int)(v / p.scan_len), i = (int)(v % p.scan_len);
-        const size_t slot = (size_t)seg * p.Bpad + q;
-        if (i < p.counts[slot]) {
-          const u64 key = p.lists[slot * (size_t)p.cap + i];
-          if ((key & hi_mask) == prefix) atomicAdd(&hist[(u32)(key >> shift) & 255u], 1u);
-        }
-      }
+      for_each_key(p, q, staged, stage, total, [&](u64 key) {
+        if ((key & hi_mask) == prefix) atomicAdd(&hist[(u32)(key >> shift) & 255u], 1u);
+      });
       __syncthreads();
       if (tid < 32) {
-        const int lane = tid;
         const int remaining = s_remaining;
         u32 c[8]; u32 lane_sum = 0;
 #pragma unroll
@@ -96,19 +127,21 @@ __global__ void __launch_bounds__(SEL_THREADS) select_lists_kernel(const SelectP
     kth = s_prefix;
   }
 
+  if (!output) {
+    __syncthreads();
+    if (tid == 0) atomicMax(p.gthr + q, (u32)(kth >> 32));
+    return;
+  }
+
+  const int want = total < p.k ? total : p.k;
   for (int i = tid; i < p.kp2; i += SEL_THREADS) sk[i] = 0;
   __syncthreads();
-  for (long long v = tid; v < vtotal; v += SEL_THREADS) {
-    const int seg = (int)(v / p.scan_len), i = (int)(v % p.scan_len);
-    const size_t slot = (size_t)seg * p.Bpad + q;
-    if (i < p.counts[slot]) {
-      const u64 key = p.lists[slot * (size_t)p.cap + i];
-      if (key >= kth) {
-        const int pos = atomicAdd(&s_nout, 1);
-        if (pos < p.kp2) sk[pos] = key;
-      }
+  for_each_key(p, q, staged, stage, total, [&](u64 key) {
+    if (key >= kth) {
+      const int pos = atomicAdd(&s_nout, 1);
+      if (pos < p.kp2) sk[pos] = key;
     }
-  }
+  });
   __syncthreads();
   block_bitonic_desc(sk, p.kp2);
   const float qi = p.qinv ? p.qinv[q] : 1.0f;
@@ -127,13 +160,16 @@ int launch_select_lists(const Index* ix, const SearchPlan& pl, void* ws, float* 
   p.lists = reinterpret_cast<const u64*>((char*)ws + pl.off_lists);
   p.counts = reinterpret_cast<const int*>((char*)ws + pl.off_counts);
   p.S = pl.num_segments; p.Bpad = pl.Bpad; p.cap = pl.cap;
-  p.scan_len = (pl.path == B200R_PATH_SCAN) ? pl.k : pl.cap;  // K2 compacts every list to <= k before exiting
   p.B = pl.B; p.k = pl.k; p.kp2 = next_pow2(pl.k);
+  const long long all = (long long)pl.num_segments * pl.cap;
+  p.stage_cap = (int)(all < SEL_STAGE_MAX ? all : SEL_STAGE_MAX);
   p.qinv = (ix->metric == B200R_COS) ? reinterpret_cast<const float*>((char*)ws + pl.off_qinv) : nullptr;
+  p.gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
   p.id_base = ix->id_base;
   p.out_scores = out_scores;
   p.out_ids = reinterpret_cast<long long*>(out_ids);
-  const size_t smem = (size_t)p.kp2 * 8 + 256 * 4;
+  const size_t smem = (size_t)p.stage_cap * 8 + (out_scores ? (size_t)p.kp2 * 8 : 0);
+  B200R_CUDA_CHECK(cudaFuncSetAttribute(select_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   select_lists_kernel<<<pl.B, SEL_THREADS, smem, st>>>(p);
   count_launch();
   B200R_CUDA_CHECK(cudaGetLastError());
