@@ -88,7 +88,9 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   if (B <= 0) { set_error("B must be > 0 (got %d)", B); return B200R_EINVAL; }
   if (k <= 0 || k > B200R_MAX_K) { set_error("k must be in [1, %d] (got %d)", B200R_MAX_K, k); return B200R_EINVAL; }
   const bool gemm_ok = ix->has_tmap;
-  if (path == B200R_PATH_AUTO) path = (gemm_ok && B > 4) ? B200R_PATH_GEMM : B200R_PATH_SCAN;
+  // measured on B200: the tensor-core path is HBM-bound (77% of copy bandwidth) already at B=1, so it is the
+  // default whenever the corpus type allows it; the CUDA-core scan serves fp32 / int8 / odd-D corpora
+  if (path == B200R_PATH_AUTO) path = gemm_ok ? B200R_PATH_GEMM : B200R_PATH_SCAN;
   if (path == B200R_PATH_GEMM && !gemm_ok) {
     set_error("gemm path needs a bf16/f16 corpus with D %% 8 == 0 (dtype=%d D=%d)", ix->dtype, ix->D);
     return B200R_EINVAL;

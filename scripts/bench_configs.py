@@ -1,0 +1,135 @@
+"""Secondary measurements (not the driver's contract line): the other BASELINE.json configs on ONE GPU.
+Each line reports queries/s and the roofline fraction of the dominant kernel (CUDA events via the
+library's profiling hooks).  Usage: python scripts/bench_configs.py [names...]"""
+import json, os, sys, time
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from a_modular_rag_framework_b200 import DenseIndex, PassageGraph, expand_rescore, _native
+
+dev = torch.device("cuda:0")
+PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
+
+
+def corpus(N, D, dtype, seed=1):
+    X = torch.empty((N, D), dtype=dtype, device=dev)
+    blk = 1 << 20
+    for r0 in range(0, N, blk):
+        r1 = min(N, r0 + blk)
+        g = torch.Generator(device=dev).manual_seed(seed + r0)
+        t = torch.randn((r1 - r0, D), generator=g, device=dev)
+        t /= t.norm(dim=1, keepdim=True)
+        X[r0:r1] = t.to(dtype)
+    return X
+
+
+def queries(n, B, D, dtype, seed=99):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    Q = torch.randn((n, B, D), generator=g, device=dev)
+    Q /= Q.norm(dim=2, keepdim=True)
+    return Q.to(dtype)
+
+
+def run_search(name, N, D, B, k, dtype, path, steps=10, warmup=3, check=True):
+    X = corpus(N, D, dtype)
+    Q = queries(steps + warmup, B, D, dtype)
+    ix = DenseIndex(X, metric="cos")
+    for i in range(warmup):
+        out = ix.search(Q[i], k, path=path)
+    torch.cuda.synchronize()
+    _native.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        out = ix.search(Q[warmup + i], k, path=path)
+    e1.record()
+    torch.cuda.synchronize()
+    kms, kn = _native.profile_read()
+    _native.profile_enable(False)
+    ms = e0.elapsed_time(e1) / steps
+    kms /= steps
+    esz = X.element_size()
+    used = path if path != "auto" else ("gemm" if dtype in (torch.bfloat16, torch.float16) else "scan")
+    line = {"config": name, "rows": N, "dim": D, "batch": B, "k": k, "dtype": str(dtype).split(".")[-1], "path": used,
+            "ms_per_batch": ms, "queries_per_s": B / (ms * 1e-3), "kernel_ms_per_batch": kms, "kernel_launches_per_batch": kn / steps}
+    passes = 1 if used == "gemm" else (B + 3) // 4
+    gbs = N * D * esz * passes / (kms * 1e-3) / 1e9
+    tfs = 2.0 * B * N * D / (kms * 1e-3) / 1e12
+    line["hbm_GBps"] = gbs
+    line["hbm_frac_of_measured"] = gbs / PEAKS["hbm_gbs"]
+    line["tensor_TFLOPs"] = tfs
+    line["tensor_frac_of_measured_sustained"] = tfs / PEAKS["bf16_tflops_sustained"]
+    if check:
+        from oracle import retrieval_oracle as O
+        s, ids = out
+        nq = min(B, 2)
+        Qn = Q[warmup + steps - 1][:nq].float().cpu().numpy()
+        best_s = np.full((nq, 0), 0.0); best_i = np.zeros((nq, 0), dtype=np.int64)
+        for r0 in range(0, N, 1 << 20):
+            Xn = X[r0:r0 + (1 << 20)].float().cpu().numpy()
+            ss, ii = O.topk(Qn, Xn, k, dtype=np.float32, id_base=r0)
+            best_s = np.concatenate([best_s, ss], 1); best_i = np.concatenate([best_i, ii], 1)
+        ms_, mi_ = O.merge_topk(best_s[:, None, :], best_i[:, None, :], k)
+        got = ids[:nq].cpu().numpy()
+        inter = np.mean([len(set(got[b]) & set(mi_[b])) / k for b in range(nq)])
+        line["recall_vs_oracle_f32"] = float(inter)
+        line["max_abs_score_err"] = float(np.max(np.abs(np.sort(s[:nq].cpu().numpy(), 1) - np.sort(ms_, 1))))
+    print(json.dumps(line), flush=True)
+    del ix, X, Q
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_graph(name, V, E, D, B, S, k, steps=5, warmup=2):
+    X = corpus(V, D, torch.bfloat16)
+    g = torch.Generator(device=dev).manual_seed(5)
+    src = torch.randint(0, V, (E,), generator=g, device=dev)
+    dst = torch.randint(0, V, (E,), generator=g, device=dev)
+    a = torch.cat([src, dst]); b = torch.cat([dst, src])
+    order = torch.argsort(a * V + b)
+    a, b = a[order], b[order]
+    row_ptr = torch.zeros(V + 1, dtype=torch.int64, device=dev)
+    row_ptr[1:] = torch.cumsum(torch.bincount(a, minlength=V), 0)
+    col = b.to(torch.int32).contiguous()
+    del src, dst, a, b, order
+    graph = PassageGraph(row_ptr, col)
+    ix = DenseIndex(X, metric="cos")
+    Q = queries(steps + warmup, B, D, torch.bfloat16)
+    # seeds = the dense top-S of each query (the north-star pipeline)
+    seeds = [ix.search(Q[i], S)[1] for i in range(steps + warmup)]
+    for i in range(warmup):
+        out = expand_rescore(ix, graph, Q[i], seeds[i], 2, 0.4, 0.2, k)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        out = expand_rescore(ix, graph, Q[warmup + i], seeds[warmup + i], 2, 0.4, 0.2, k, check_status=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ncand = out["ncand"].float().mean().item()
+    gather_bytes = ncand * B * D * 2
+    line = {"config": name, "nodes": V, "edges_undirected": 2 * E, "dim": D, "batch": B, "seeds": S, "k": k, "window": 2,
+            "ms_per_batch": ms, "queries_per_s": B / (ms * 1e-3), "avg_candidates": ncand,
+            "gather_GBps": gather_bytes / (ms * 1e-3) / 1e9, "hbm_frac_of_measured": gather_bytes / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"],
+            "overflowed_queries": int((out["status"] != 0).sum().item())}
+    print(json.dumps(line), flush=True)
+
+
+CONFIGS = {
+    "cfg1_1Mx768_B1024": lambda: run_search("cfg1_1Mx768_B1024", 1_000_000, 768, 1024, 100, torch.bfloat16, "auto"),
+    "cfg2_10Mx768_B1_scan": lambda: run_search("cfg2_10Mx768_B1_scan", 10_000_000, 768, 1, 100, torch.bfloat16, "scan", steps=20),
+    "cfg2_10Mx768_B4_scan": lambda: run_search("cfg2_10Mx768_B4_scan", 10_000_000, 768, 4, 100, torch.bfloat16, "scan", steps=20),
+    "cfg2_10Mx768_B16_gemm": lambda: run_search("cfg2_10Mx768_B16_gemm", 10_000_000, 768, 16, 100, torch.bfloat16, "gemm", steps=20),
+    "cfg2_10Mx768_B16_scan": lambda: run_search("cfg2_10Mx768_B16_scan", 10_000_000, 768, 16, 100, torch.bfloat16, "scan", steps=5),
+    "cfg2_10Mx768_B1_gemm": lambda: run_search("cfg2_10Mx768_B1_gemm", 10_000_000, 768, 1, 100, torch.bfloat16, "gemm", steps=20),
+    "cfg3_12p5Mx384_f16_k1000_B16": lambda: run_search("cfg3_12p5Mx384_f16_k1000_B16", 12_500_000, 384, 16, 1000, torch.float16, "gemm", steps=10),
+    "cfg3_12p5Mx384_f16_k1000_B1": lambda: run_search("cfg3_12p5Mx384_f16_k1000_B1", 12_500_000, 384, 1, 1000, torch.float16, "scan", steps=10),
+    "cfg4_graph_5M_50M": lambda: run_graph("cfg4_graph_5M_50M", 5_000_000, 25_000_000, 768, 1024, 20, 10),
+}
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CONFIGS)
+    for n in names:
+        CONFIGS[n]()

@@ -1,0 +1,164 @@
+"""Host logic of B200RetrievalBackend (CPU): boundary shape, ids/meta, fusion, spans, adapter round trip.
+The compute engine is an oracle stand-in here; tests/test_gpu_backend.py runs the same flow on the CUDA engine."""
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from a_modular_rag_framework_b200 import store
+from a_modular_rag_framework_b200.backend import B200RetrievalBackend
+from tests.helpers_backend import FakeRouter, ListSink, OracleEngine, make_corpus, text_vec
+from oracle import retrieval_oracle as O
+
+REFERENCE = "/root/reference"
+
+
+def _req(query, graph_id="g1", top_k=10, trace_id="t1", **kw):
+    return SimpleNamespace(query=query, graph_id=graph_id, top_k=top_k, trace_id=trace_id, **kw)
+
+
+@pytest.fixture()
+def corpus(tmp_path):
+    return make_corpus(str(tmp_path))
+
+
+def _backend(c, **kw):
+    eng = OracleEngine(c.X, c.row_ptr, c.col_idx)
+    return B200RetrievalBackend(router=FakeRouter(c.dim), sink=kw.pop("sink", None), index_path=c.index_path,
+                                emb_path=c.emb_path, graph_path=c.graph_path, engine=eng, **kw)
+
+
+def test_store_roundtrip(corpus):
+    X, meta, scales = store.load_embeddings(corpus.emb_path)
+    assert meta == {"N": 60, "D": 64, "dtype": "bf16", "metric": "cos", "has_scales": False} and scales is None
+    assert np.array_equal(np.asarray(X), O.f32_to_bf16_bits(corpus.X))
+    assert store.load_docs(corpus.index_path) == corpus.docs
+    rp, ci = store.load_csr(corpus.graph_path)
+    assert np.array_equal(rp, corpus.row_ptr) and np.array_equal(ci, corpus.col_idx)
+    # chain inside each 5-sentence document, nothing across documents
+    assert rp[-1] == 2 * 12 * 4 and list(ci[rp[0]:rp[1]]) == [1] and list(ci[rp[2]:rp[3]]) == [1, 3]
+
+
+def test_graph_json_to_csr_follows_build_index():
+    graph = {"nodes": [], "edges": [
+        {"source": "a", "target": "b", "type": "next_in_doc"}, {"source": "b", "target": "c", "type": "next_in_doc"},
+        {"source": "a", "target": "c", "type": "semantic_sim"}, {"source": "q1", "target": "b", "type": "q_match"},
+        {"source": "q2", "target": "a", "type": "q_match"}, {"source": "c", "target": "zz", "type": "next_in_doc"}]}
+    rows = {"a": 0, "b": 1, "c": 2}
+    rp, ci, seeds = store.graph_json_to_csr(graph, rows.get, 3)
+    assert seeds == [1] and list(rp) == [0, 1, 3, 4] and list(ci) == [1, 0, 2, 1]
+
+
+def test_run_shape_ids_meta_and_diagnostics(corpus):
+    sink = ListSink()
+    be = _backend(corpus, sink=sink, seed_k=5)
+    q = corpus.docs[17]["text"]
+    out = be.run(_req(q, top_k=8))
+    hits, diag = out["hits"], out["diagnostics"]
+    assert len(hits) == 8 and all(set(h) == {"id", "score", "meta"} for h in hits)
+    assert [h["score"] for h in hits] == sorted((h["score"] for h in hits), reverse=True)
+    top = hits[0]
+    assert top["meta"]["row"] == 17 and top["meta"]["doc"] == "Title 3" and top["meta"]["sent_id"] == 2
+    assert top["id"] == "sent::Title 3::2" and top["meta"]["text"] == q
+    for key in ("score_text_norm", "score_graph_norm", "score_dense_norm", "kind", "text", "doc", "sent_id", "source"):
+        assert key in top["meta"]
+    # sentence 0 ids mirror the reference's falsy-sent_id behaviour (retrieval_backend.py:287-291)
+    zero = [h for h in hits if h["meta"]["sent_id"] == 0]
+    assert all(h["id"].endswith("::") for h in zero)
+    for key in ("queries", "bm25_candidates", "graph_candidates", "dense_scored", "weights", "pool", "graph_window_used",
+                "embed_batch", "resolved_embed_model"):
+        assert key in diag
+    assert diag["resolved_embed_model"] == "fake-embed" and diag["graph_window_used"] == 2 and diag["queries"] == [q]
+    nodes = [e["node"] for e in sink.events if e["event"] == "node_end"]
+    assert nodes == ["Backend/Expand", "Backend/TextSearch", "Backend/DenseRerank", "Backend/GraphExpand"]
+    assert be.router.calls[0][0] == "fake-embed" and be.router.calls[0][2] == {"trace_id": "t1"}
+
+
+def test_graph_stage_matches_oracle_composition(corpus):
+    be = _backend(corpus, seed_k=4, graph_window=2)
+    q = corpus.docs[31]["text"]
+    out = be.run(_req(q, top_k=10))
+    qv = O.bf16_bits_to_f32(O.f32_to_bf16_bits(text_vec(q, corpus.dim)))
+    Xb = O.bf16_bits_to_f32(O.f32_to_bf16_bits(corpus.X))
+    _, seeds = O.topk(qv[None], Xb, 10)
+    top, dist = O.expand_rescore(qv, Xb, corpus.row_ptr, corpus.col_idx, seeds[0][:4], 2, 0.4, 0.2, 150)
+    assert [h["meta"]["row"] for h in out["hits"]] == [t[0] for t in top[:10]]
+    assert np.allclose([h["score"] for h in out["hits"]], [t[1] for t in top[:10]])
+    assert out["diagnostics"]["graph_candidates"] == len(dist)
+    assert all(h["meta"]["distance"] == dist[h["meta"]["row"]] for h in out["hits"])
+
+
+def test_dense_only_when_no_graph_id_or_window_zero(corpus):
+    be = _backend(corpus)
+    q = corpus.docs[5]["text"]
+    out = be.run(_req(q, graph_id="", top_k=5))
+    qv = O.bf16_bits_to_f32(O.f32_to_bf16_bits(text_vec(q, corpus.dim)))
+    s, i = O.topk(qv[None], O.bf16_bits_to_f32(O.f32_to_bf16_bits(corpus.X)), 20)
+    assert [h["meta"]["row"] for h in out["hits"]] == list(i[0][:5])
+    assert out["hits"][0]["meta"]["score_dense_norm"] == 1.0 and out["hits"][0]["score"] == pytest.approx(0.4)
+    assert out["diagnostics"]["graph_candidates"] == 0
+    out0 = be.run(_req(q, top_k=5, graph_window=0))      # per-request override, like getattr(req, "graph_window") (:318)
+    assert out0["diagnostics"]["graph_window_used"] == 0 and all(h["meta"]["distance"] == 0 for h in out0["hits"])
+
+
+def test_text_channel_fusion(corpus):
+    class Text:
+        def search(self, queries, top_k):
+            return [{"id": "sent::Title 9::3", "score": 7.0, "meta": {"doc": "Title 9", "sent_id": 3, "text": "x", "source": "bm25"}},
+                    {"id": "sent::Title 0::1", "score": 3.0, "meta": {"doc": "Title 0", "sent_id": 1, "text": "y", "source": "bm25"}}]
+    be = _backend(corpus, text_searcher=Text())
+    out = be.run(_req(corpus.docs[1]["text"], top_k=60))
+    by_id = {h["id"]: h for h in out["hits"]}
+    assert by_id["sent::Title 9::3"]["meta"]["score_text_norm"] == 1.0
+    assert by_id["sent::Title 0::1"]["meta"]["score_text_norm"] == 0.0
+    assert out["diagnostics"]["bm25_candidates"] == 2
+    h = by_id["sent::Title 0::1"]   # joined on id with the dense/graph candidate for row 1
+    assert h["meta"]["row"] == 1 and h["score"] == pytest.approx(0.2 * h["meta"]["score_graph_norm"] + 0.4 * h["meta"]["score_dense_norm"])
+
+
+def test_degenerate_embeddings_degrade_like_reference(corpus):
+    be = _backend(corpus)
+    be.router = SimpleNamespace(policy={}, providers={}, embed=lambda **kw: [[0.0, 0.0, 0.0]])   # the router's mock fallback (llm_router.py:116-129)
+    out = be.run(_req("anything"))
+    assert out["hits"] == [] and out["diagnostics"]["dense_scored"] == 0
+
+    def boom(**kw):
+        raise RuntimeError("provider down")
+    be.router = SimpleNamespace(policy={}, providers={}, embed=boom)
+    assert be.run(_req("anything"))["hits"] == []
+
+
+def test_retrieve_returns_retrievalout(corpus):
+    be = _backend(corpus)
+    ro = be.retrieve(_req(corpus.docs[3]["text"], top_k=3))
+    assert len(ro.hits) == 3 and ro.hits[0].meta["row"] == 3 and "weights" in ro.diagnostics
+
+
+def test_rows_docs_mismatch_raises(corpus):
+    with pytest.raises(ValueError):
+        B200RetrievalBackend(router=FakeRouter(corpus.dim), index_path=corpus.index_path, engine=OracleEngine(corpus.X[:10]))
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "app")), reason="reference checkout not present on this box")
+def test_through_the_references_own_adapter_and_flow_conventions(corpus, monkeypatch):
+    """Plug-in convention B (retrieval_adapter.py:31-42, 112-133) drives our class by its import string, and
+    convention A's kwarg filtering (flow.py:97-106) finds `router`/`sink` in our signature."""
+    import inspect
+    monkeypatch.syspath_prepend(REFERENCE)
+    monkeypatch.setattr(sys, "dont_write_bytecode", True)
+    from app.modules.retrieval.retrieval_adapter import RetrievalAdapter
+    from app.core.dto import RetrievalIn, RetrievalOut
+    eng = OracleEngine(corpus.X, corpus.row_ptr, corpus.col_idx)
+    ad = RetrievalAdapter(router=FakeRouter(corpus.dim), sink=None,
+                          backend_impl="a_modular_rag_framework_b200.backend:B200RetrievalBackend",
+                          backend_kwargs={"index_path": corpus.index_path, "emb_path": corpus.emb_path,
+                                          "graph_path": corpus.graph_path, "engine": eng, "seed_k": 5})
+    out = ad.retrieve(RetrievalIn(query=corpus.docs[42]["text"], graph_id="g", top_k=6, trace_id="t"))
+    assert isinstance(out, RetrievalOut) and len(out.hits) == 6 and out.hits[0].meta["row"] == 42
+    assert [h.score for h in out.hits] == sorted((h.score for h in out.hits), reverse=True)
+    params = inspect.signature(B200RetrievalBackend.__init__).parameters
+    for name in ("router", "sink", "index_path", "graph_root", "graph_window", "alpha_text", "alpha_graph", "alpha_dense",
+                 "bm25_pool_k", "default_top_k", "qe_lines", "qe_attr_paraphrase", "embed_batch"):
+        assert name in params
