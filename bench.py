@@ -253,10 +253,14 @@ def main():
     kernel_ms, kernel_n = _native.profile_read()
     _native.profile_enable(False)
     ms = ev0.elapsed_time(ev1)
+    per_rank = [{"rank": rank, "ms_per_step": ms / a.steps, "kernel_ms_per_step": kernel_ms / a.steps}]
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_rank[0])
+        per_rank = gathered
     value = a.steps * a.batch / (ms * 1e-3)
 
     # ---- end-to-end through the host-buffer C-ABI call ---------------------------------------------
@@ -340,7 +344,7 @@ def main():
                        "path": used_path, "sharding": f"rows/{world}",
                        "l2": "corpus shard (>= 1.9 GB) is far larger than the 126 MB L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks,
+            "clocks": clocks, "per_rank": per_rank,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
