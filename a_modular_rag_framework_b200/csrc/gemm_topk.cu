@@ -126,6 +126,19 @@ __device__ __forceinline__ void tmem_ld32(u32 taddr, u32* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// s[j] for a runtime j without spilling s[] to local memory: a balanced tree of 31 selects
+template <int LO, int N>
+__device__ __forceinline__ float mux_tree(const float (&s)[32], int j) {
+  if constexpr (N == 1) {
+    return s[LO];
+  } else {
+    const float a = mux_tree<LO, N / 2>(s, j);
+    const float b = mux_tree<LO + N / 2, N / 2>(s, j);
+    return (j & (N / 2)) ? b : a;
+  }
+}
+__device__ __forceinline__ float mux32(const float (&s)[32], int j) { return mux_tree<0, 32>(s, j); }
+
 // ------------------------------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
@@ -278,16 +291,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             cmax = fmaxf(cmax, fmaxf(fmaxf(s[j], s[j + 1]), fmaxf(s[j + 2], s[j + 3])));
           }
           if (__any_sync(kFullMask, cmax >= thr)) {
-            // rare path, kept warp-uniform: one vote per column, only lanes that pass do work
+            // rare path: survivor bitmask per lane (straight-line), then each lane walks its own bits and
+            // picks the value with a 5-level select tree -- no dependent vote/branch chain
+            u32 mask = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const bool pj = s[j] >= thr;
-              if (__any_sync(kFullMask, pj)) {
-                if (pj) {
-                  const u64 key = make_key(s[j], row0 + c * 32 + j);
-                  if (key > kth_key) { __stcg(my_list + cnt, key); ++cnt; }
-                }
-              }
+            for (int j = 0; j < 32; ++j) mask |= (s[j] >= thr) ? (1u << j) : 0u;
+            while (mask) {
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1;
+              const u64 key = make_key(mux32(s, j), row0 + c * 32 + j);
+              if (key > kth_key) { __stcg(my_list + cnt, key); ++cnt; }
             }
             u32 full = __ballot_sync(kFullMask, cnt >= p.cap_soft);
             while (full) {
