@@ -305,10 +305,11 @@ def main():
     # the dominant kernel is launched once per phase of a step: sum its launches over the step
     kernel_avg_ms = kernel_ms / max(a.steps, 1)
     launches_per_step = kernel_n / max(a.steps, 1)
-    traffic = None
+    traffic, traffic_note = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"{used_path}_bytes_per_launch")
+            tj = json.load(f)
+            traffic, traffic_note = tj.get(f"{used_path}_bytes_per_launch"), tj.get(f"{used_path}_note")
     except Exception:
         pass
     if used_path == "gemm":
@@ -316,7 +317,7 @@ def main():
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         achieved = flops / (kernel_avg_ms * 1e-3) / 1e12 if kernel_avg_ms > 0 else 0.0
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": "gemm_topk_kernel", "kernel_ms_per_step": kernel_avg_ms, "launches_per_step": launches_per_step,
+                    "traffic": traffic, "traffic_note": traffic_note, "kernel": "gemm_topk_kernel", "kernel_ms_per_step": kernel_avg_ms, "launches_per_step": launches_per_step,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
                     "algorithmic": "2*B*N_local*D flop per step, summed over the phase launches of gemm_topk_kernel"}
     else:
