@@ -37,6 +37,7 @@ void profile_end(cudaStream_t st) {
   else { cudaEventDestroy(g_prof_events.back()); g_prof_events.pop_back(); }
 }
 
+int select_group_size();
 int gemm_tile_rows();
 int gemm_tile_queries();
 int32_t expand_max_candidates();
@@ -158,7 +159,7 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
     pl->Bpad = B;
     const int R = 4;
     const int warps_per_block = 8;
-    long long blocks = (long long)kPlanSMs * 4;
+    long long blocks = (long long)kPlanSMs * 3;   // scan kernels are compiled for 3 CTAs/SM: one full wave
     const long long groups = (ix->N + R - 1) / R;
     const long long need = (groups + warps_per_block - 1) / warps_per_block;
     if (blocks > need) blocks = need < 1 ? 1 : need;
@@ -171,6 +172,12 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   pl->off_counts = off; off += align_up((size_t)pl->num_segments * pl->Bpad * 4, 256);
   pl->off_gthr = off; off += align_up((size_t)pl->Bpad * 4, 256);
   pl->off_qinv = off; off += align_up((size_t)pl->Bpad * 4, 256);
+  pl->num_groups = 0;
+  if (pl->num_segments > 2 * select_group_size()) {
+    pl->num_groups = (pl->num_segments + select_group_size() - 1) / select_group_size();
+    pl->off_lists2 = off; off += align_up((size_t)pl->num_groups * pl->Bpad * pl->k * 8, 256);
+    pl->off_counts2 = off; off += align_up((size_t)pl->num_groups * pl->Bpad * 4, 256);
+  }
   pl->off_end = off;
   return B200R_OK;
 }

@@ -1,10 +1,16 @@
-// csr_expand.cu -- K3: graph-enhanced second stage.  One CTA per query:
-//   1. level-synchronous BFS from the seed passages over the CSR adjacency, depth <= window, with a
-//      shared-memory hash set as the `visited` set (first arrival == minimum hop distance) and a
-//      warp-level __match_any_sync pre-dedup so each distinct neighbour issues one atomic per warp;
-//   2. re-score every reached node against the query (one warp per candidate row, 128-bit gathers);
-//   3. per-query min/max of both channels, fused = a_g*minmax(decay(hop)) + a_d*minmax(cos);
-//   4. exact top-k by (fused desc, id asc) with an in-smem bitonic sort.
+// csr_expand.cu -- K3: graph-enhanced second stage.  One CTA (512 threads) per query:
+//   1. level-synchronous BFS from the seed passages over the CSR adjacency, depth <= window.  The
+//      `visited` set is a shared-memory hash set (first arrival == minimum hop distance).  A frontier
+//      level is expanded thread-per-node (all row_ptr / col_idx latencies of a level overlap), with a
+//      warp-level __match_any_sync pre-dedup so each distinct neighbour costs one atomic per warp; nodes
+//      with a long adjacency list are deferred to a warp-per-node pass with lane-strided 128-byte reads.
+//   2. re-score every reached node against the query: one warp per 4 candidate rows, all 128-bit row
+//      loads of the group in flight together (this gather is the HBM-bound part).
+//   3. per-query min/max of both channels, fused = a_g*minmax(decay(hop)) + a_d*minmax(cos).
+//   4. exact top-k by (fused desc, id asc): radix select of the k-th key in smem + bitonic sort of k.
+//
+// Two instantiations share the code: 4096 candidates (71 KB smem, 3 CTAs/SM) runs for every query; the
+// 8192-candidate one re-runs only the queries that overflowed the first; beyond that B200R_EOVERFLOW.
 //
 // Replaces expand_qmatch_neighbors (reference app/modules/retrieval/graph_utils.py:58-129: BFS :109-127,
 // decay :87-94), DenseReranker._cosine (retrieval_backend.py:192-197), _minmax_norm (:296-301) and the
@@ -15,11 +21,14 @@
 
 namespace b200r {
 
-constexpr int EXP_THREADS = 256;
+constexpr int EXP_THREADS = 512;
 constexpr int EXP_WARPS = EXP_THREADS / 32;
-constexpr int EXP_MAXC = 8192;        // candidates per query
-constexpr int EXP_HASH = 16384;       // hash slots (load factor <= 0.5); 64 KB, later reused for the sort keys
+constexpr int EXP_MAXC_BIG = 8192;
+constexpr int EXP_HUB_DEG = 32;       // adjacency lists longer than this are expanded by a whole warp
+constexpr int EXP_MAX_HUBS = 256;
+constexpr int EXP_ROWS = 4;           // candidate rows gathered together by one warp
 constexpr u32 EXP_EMPTY = 0xffffffffu;
+constexpr int kStatusRetry = 1;       // internal: overflowed the small instantiation, big one will redo it
 
 struct ExpandParams {
   const void* X;
@@ -29,7 +38,7 @@ struct ExpandParams {
   const int* col_idx;
   const long long* seeds;
   long long N, V, id_base;
-  int D, B, S, window, k, metric;
+  int D, B, S, window, k, kp2, metric;
   float alpha_dense, alpha_graph;
   float* out_scores; long long* out_ids; int* out_hops; float* out_gn; float* out_dn; float* out_cos;
   int* out_ncand; int* out_status;
@@ -44,36 +53,44 @@ __device__ __forceinline__ float hop_decay(int d) {
 }
 
 // insert `v` into the visited set; returns true if this call inserted it
+template <int HASH>
 __device__ __forceinline__ bool hash_insert(u32* table, u32 v) {
-  u32 h = (v * 2654435761u) & (EXP_HASH - 1);
+  u32 h = (v * 2654435761u) & (HASH - 1);
   while (true) {
     const u32 prev = atomicCAS(&table[h], EXP_EMPTY, v);
     if (prev == EXP_EMPTY) return true;
     if (prev == v) return false;
-    h = (h + 1) & (EXP_HASH - 1);
+    h = (h + 1) & (HASH - 1);
   }
 }
 
-template <typename T>
+template <typename T, int MAXC, bool RETRY_PASS>
 __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const ExpandParams p) {
   typedef typename QueryType<T>::type QT;
   constexpr int VEC = ElemTraits<T>::kVec;
+  constexpr int HASH = 2 * MAXC;
+  const int q = blockIdx.x;
+  if (RETRY_PASS && p.out_status[q] != kStatusRetry) return;
+
   extern __shared__ uint8_t smem_raw[];
-  u64* keys = reinterpret_cast<u64*>(smem_raw);                    // [EXP_MAXC]  (aliases the hash table)
-  u32* table = reinterpret_cast<u32*>(smem_raw);                   // [EXP_HASH] u32 == 64 KB
-  u32* cand = reinterpret_cast<u32*>(smem_raw + EXP_MAXC * 8);     // [EXP_MAXC] node ids
-  float* cosv = reinterpret_cast<float*>(cand + EXP_MAXC);         // [EXP_MAXC]
-  uint8_t* dist = reinterpret_cast<uint8_t*>(cosv + EXP_MAXC);     // [EXP_MAXC]
-  float* qs = reinterpret_cast<float*>(dist + EXP_MAXC);           // [D]
-  __shared__ int s_count, s_overflow;
+  u64* keys = reinterpret_cast<u64*>(smem_raw);                    // [MAXC]  (aliases the hash table, used after the BFS)
+  u32* table = reinterpret_cast<u32*>(smem_raw);                   // [HASH] u32
+  u32* cand = reinterpret_cast<u32*>(smem_raw + MAXC * 8);         // [MAXC] node ids
+  float* cosv = reinterpret_cast<float*>(cand + MAXC);             // [MAXC]
+  uint8_t* dist = reinterpret_cast<uint8_t*>(cosv + MAXC);         // [MAXC]
+  float* qs = reinterpret_cast<float*>(dist + MAXC);               // [D]
+  u64* sk = reinterpret_cast<u64*>(qs + ((p.D + 1) & ~1));         // [kp2]
+  __shared__ int s_count, s_overflow, s_nhubs, s_remaining, s_nout;
+  __shared__ int s_hubs[EXP_MAX_HUBS];
   __shared__ float s_red[4][EXP_WARPS];
   __shared__ double s_qn[EXP_WARPS];
+  __shared__ u32 hist[256];
+  __shared__ u64 s_prefix;
 
-  const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int i = tid; i < EXP_HASH; i += EXP_THREADS) table[i] = EXP_EMPTY;
-  if (tid == 0) { s_count = 0; s_overflow = 0; }
+  for (int i = tid; i < HASH; i += EXP_THREADS) table[i] = EXP_EMPTY;
+  if (tid == 0) { s_count = 0; s_overflow = 0; s_nhubs = 0; }
   // query -> fp32 in smem, and its norm
   const QT* Qp = reinterpret_cast<const QT*>(p.Q) + (size_t)q * p.D;
   double qn = 0.0;
@@ -94,43 +111,76 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
   for (int i = tid; i < p.S; i += EXP_THREADS) {
     const long long s = p.seeds[(size_t)q * p.S + i] - p.id_base;
     if (s >= 0 && s < p.V) {
-      if (hash_insert(table, (u32)s)) {
+      if (hash_insert<HASH>(table, (u32)s)) {
         const int pos = atomicAdd(&s_count, 1);
-        if (pos < EXP_MAXC) { cand[pos] = (u32)s; dist[pos] = 0; } else s_overflow = 1;
+        if (pos < MAXC) { cand[pos] = (u32)s; dist[pos] = 0; } else s_overflow = 1;
       }
     }
   }
   __syncthreads();
 
-  // ---- levels 1..window: one warp per frontier node, lanes stride over its neighbours -------------
+  // ---- levels 1..window ---------------------------------------------------------------------------
   int level_begin = 0;
   for (int d = 1; d <= p.window; ++d) {
-    const int level_end = min(s_count, EXP_MAXC);
+    const int level_end = min(s_count, MAXC);
     __syncthreads();                      // everyone has read s_count before the level appends to it
-    if (level_end == level_begin) break;  // block-uniform
-    for (int f = level_begin + warp; f < level_end; f += EXP_WARPS) {
-      const u32 u = cand[f];
-      const long long e0 = p.row_ptr[u], e1 = p.row_ptr[u + 1];
-      for (long long base = e0; base < e1; base += 32) {
-        const long long e = base + lane;
-        const bool in = e < e1;
-        const u32 v = in ? (u32)__ldg(p.col_idx + e) : EXP_EMPTY;
-        // warp-level pre-dedup: one lane per distinct neighbour id goes to the hash set
+    if (level_end == level_begin || s_overflow) break;  // block-uniform
+    const uint8_t dd = (uint8_t)min(d, 255);
+    // (a) thread per frontier node; the loop bounds are warp-uniform so the match_any below is legal
+    for (int fb = level_begin + warp * 32; fb < level_end; fb += EXP_THREADS) {
+      const int f = fb + lane;
+      long long e0 = 0;
+      int deg = 0;
+      if (f < level_end) {
+        const u32 u = cand[f];
+        e0 = __ldg(p.row_ptr + u);
+        const long long e1 = __ldg(p.row_ptr + u + 1);
+        deg = (int)min(e1 - e0, (long long)0x7fffffff);
+        if (deg > EXP_HUB_DEG) {
+          const int h = atomicAdd(&s_nhubs, 1);
+          if (h < EXP_MAX_HUBS) { s_hubs[h] = f; deg = 0; }   // deferred to the warp-per-node pass
+        }
+      }
+      int maxdeg = deg;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) maxdeg = max(maxdeg, __shfl_xor_sync(kFullMask, maxdeg, o));
+      for (int j = 0; j < maxdeg; ++j) {
+        const bool in = j < deg;
+        const u32 v = in ? (u32)__ldg(p.col_idx + e0 + j) : EXP_EMPTY;
         const u32 peers = __match_any_sync(kFullMask, v);
         const bool leader = in && (lane == __ffs(peers) - 1);
-        if (leader && !*(volatile int*)&s_overflow && hash_insert(table, v)) {
+        if (leader && !*(volatile int*)&s_overflow && hash_insert<HASH>(table, v)) {
           const int pos = atomicAdd(&s_count, 1);
-          if (pos < EXP_MAXC) { cand[pos] = v; dist[pos] = (uint8_t)min(d, 255); } else s_overflow = 1;
+          if (pos < MAXC) { cand[pos] = v; dist[pos] = dd; } else s_overflow = 1;
         }
       }
     }
     __syncthreads();
+    // (b) long adjacency lists: one warp per node, lanes stride the list
+    const int nh = min(s_nhubs, EXP_MAX_HUBS);
+    for (int h = warp; h < nh; h += EXP_WARPS) {
+      const u32 u = cand[s_hubs[h]];
+      const long long e0 = __ldg(p.row_ptr + u), e1 = __ldg(p.row_ptr + u + 1);
+      for (long long base = e0; base < e1; base += 32) {
+        const long long e = base + lane;
+        const bool in = e < e1;
+        const u32 v = in ? (u32)__ldg(p.col_idx + e) : EXP_EMPTY;
+        const u32 peers = __match_any_sync(kFullMask, v);
+        const bool leader = in && (lane == __ffs(peers) - 1);
+        if (leader && !*(volatile int*)&s_overflow && hash_insert<HASH>(table, v)) {
+          const int pos = atomicAdd(&s_count, 1);
+          if (pos < MAXC) { cand[pos] = v; dist[pos] = dd; } else s_overflow = 1;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_nhubs = 0;
     level_begin = level_end;
   }
   __syncthreads();
-  const int ncand = min(s_count, EXP_MAXC);
+  const int ncand = min(s_count, MAXC);
   if (s_overflow) {  // block-uniform
-    if (tid == 0) { p.out_status[q] = B200R_EOVERFLOW; p.out_ncand[q] = s_count; }
+    if (tid == 0) { p.out_status[q] = (MAXC < EXP_MAXC_BIG) ? kStatusRetry : B200R_EOVERFLOW; p.out_ncand[q] = s_count; }
     for (int i = tid; i < p.k; i += EXP_THREADS) {
       const size_t o = (size_t)q * p.k + i;
       p.out_scores[o] = -CUDART_INF_F; p.out_ids[o] = -1; p.out_hops[o] = -1; p.out_gn[o] = 0; p.out_dn[o] = 0; p.out_cos[o] = 0;
@@ -138,28 +188,44 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
     return;
   }
 
-  // ---- re-score: one warp per candidate row -------------------------------------------------------
+  // ---- re-score: one warp per EXP_ROWS candidate rows, their loads in flight together ---------------
   const uint8_t* Xb = reinterpret_cast<const uint8_t*>(p.X);
   const int chunks = p.D / VEC;
-  for (int c = warp; c < ncand; c += EXP_WARPS) {
-    const u32 row = cand[c];
-    const bool have = (long long)row < p.N;
-    float acc = 0.0f;
-    if (have) {
-      const uint8_t* rp = Xb + (size_t)row * p.D * sizeof(T);
-      for (int chunk = lane; chunk < chunks; chunk += 32) {
-        const uint4 xv = ld_stream_16B(rp + (size_t)chunk * 16);
-        float xf[VEC];
-        ElemTraits<T>::unpack(xv, xf);
+  const size_t row_bytes = (size_t)p.D * sizeof(T);
+  for (int c0 = warp * EXP_ROWS; c0 < ncand; c0 += EXP_WARPS * EXP_ROWS) {
+    const uint8_t* rp[EXP_ROWS];
+    bool have[EXP_ROWS];
+    float acc[EXP_ROWS];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) acc = fmaf(xf[e], qs[chunk * VEC + e], acc);
+    for (int r = 0; r < EXP_ROWS; ++r) {
+      const int c = min(c0 + r, ncand - 1);
+      const u32 row = cand[c];
+      have[r] = (c0 + r < ncand) && ((long long)row < p.N);
+      rp[r] = Xb + (size_t)(have[r] ? row : 0) * row_bytes;
+      acc[r] = 0.0f;
+    }
+    for (int chunk = lane; chunk < chunks; chunk += 32) {
+      uint4 xv[EXP_ROWS];
+#pragma unroll
+      for (int r = 0; r < EXP_ROWS; ++r) xv[r] = ld_stream_16B(rp[r] + (size_t)chunk * 16);
+      const float* qc = qs + chunk * VEC;
+#pragma unroll
+      for (int r = 0; r < EXP_ROWS; ++r) {
+        float xf[VEC];
+        ElemTraits<T>::unpack(xv[r], xf);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[r] = fmaf(xf[e], qc[e], acc[r]);
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
-    if (lane == 0) {
-      const float m = have ? (p.row_mult ? p.row_mult[row] : 1.0f) : 0.0f;
-      cosv[c] = (acc * m) * qinv + 0.0f;
+    for (int r = 0; r < EXP_ROWS; ++r) {
+      float a = acc[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFullMask, a, o);
+      if (lane == 0 && c0 + r < ncand) {
+        const float m = have[r] ? (p.row_mult ? p.row_mult[cand[c0 + r]] : 1.0f) : 0.0f;
+        cosv[c0 + r] = (a * m) * qinv + 0.0f;
+      }
     }
   }
   __syncthreads();
@@ -184,27 +250,80 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
   const bool c_flat = !(cmax > cmin), g_flat = !(gmax > gmin);   // "vmax <= vmin -> all 0.0" (:300)
   const float c_den = c_flat ? 1.0f : (cmax - cmin), g_den = g_flat ? 1.0f : (gmax - gmin);
 
-  // ---- fused keys + sort (the hash table is dead now; its memory becomes the key array) -----------
-  int np2 = 2;
-  while (np2 < ncand) np2 <<= 1;
-  __syncthreads();
-  for (int c = tid; c < np2; c += EXP_THREADS) {
-    u64 key = 0;
-    if (c < ncand) {
-      const float dn = c_flat ? 0.0f : (cosv[c] - cmin) / c_den;
-      const float gn = g_flat ? 0.0f : (hop_decay(dist[c]) - gmin) / g_den;
-      const float fused = p.alpha_graph * gn + p.alpha_dense * dn;
-      key = make_key(fused, cand[c]);   // ties on the fused score go to the lower node id
-    }
-    keys[c] = key;
+  // ---- fused keys (the hash table is dead now; its memory becomes the key array) ------------------
+  for (int c = tid; c < ncand; c += EXP_THREADS) {
+    const float dn = c_flat ? 0.0f : (cosv[c] - cmin) / c_den;
+    const float gn = g_flat ? 0.0f : (hop_decay(dist[c]) - gmin) / g_den;
+    keys[c] = make_key(p.alpha_graph * gn + p.alpha_dense * dn, cand[c]);   // ties on the fused score -> lower node id
   }
-  block_bitonic_desc(keys, np2);
+  if (tid == 0) { s_prefix = 0; s_remaining = p.k; s_nout = 0; }
+  for (int i = tid; i < p.kp2; i += EXP_THREADS) sk[i] = 0;
+  __syncthreads();
+
+  // ---- exact k-th key by radix select, then sort the winners ------------------------------------------
+  u64 kth = 0;
+  if (ncand > p.k) {
+    for (int pass = 7; pass >= 0; --pass) {
+      const int shift = pass * 8;
+      for (int i = tid; i < 256; i += EXP_THREADS) hist[i] = 0;
+      __syncthreads();
+      const u64 prefix = s_prefix;
+      const u64 hi_mask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
+      for (int base = warp * 32; base < ncand; base += EXP_THREADS) {
+        const int i = base + lane;
+        const bool active = i < ncand;
+        const u64 key = active ? keys[i] : 0ull;
+        const bool m = active && (key & hi_mask) == prefix;
+        const u32 dgt = m ? ((u32)(key >> shift) & 255u) : 0xffffffffu;
+        const u32 peers = __match_any_sync(kFullMask, dgt);
+        if (m && lane == __ffs(peers) - 1) atomicAdd(&hist[dgt], (u32)__popc(peers));
+      }
+      __syncthreads();
+      if (tid < 32) {
+        const int remaining = s_remaining;
+        u32 c[8]; u32 lane_sum = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { c[b] = hist[lane * 8 + b]; lane_sum += c[b]; }
+        u32 suffix = lane_sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 t = __shfl_down_sync(kFullMask, suffix, o);
+          if (lane + o < 32) suffix += t;
+        }
+        const u32 above = suffix - lane_sum;
+        if (above < (u32)remaining && (u32)remaining <= suffix) {
+          u32 run = above;
+#pragma unroll
+          for (int b = 7; b >= 0; --b) {
+            if (run + c[b] >= (u32)remaining) {
+              s_prefix = prefix | ((u64)(u32)(lane * 8 + b) << shift);
+              s_remaining = remaining - (int)run;
+              break;
+            }
+            run += c[b];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    kth = s_prefix;
+  }
+  for (int i = tid; i < ncand; i += EXP_THREADS) {
+    const u64 key = keys[i];
+    if (key >= kth) {
+      const int pos = atomicAdd(&s_nout, 1);
+      if (pos < p.kp2) sk[pos] = key;
+    }
+  }
+  __syncthreads();
+  block_bitonic_desc(sk, p.kp2);
 
   // ---- emit: winner i is looked up in the candidate list by one warp (k is small) ------------------
+  const int nwin = min(ncand, p.k);
   for (int i = warp; i < p.k; i += EXP_WARPS) {
     const size_t o = (size_t)q * p.k + i;
-    if (i < ncand) {
-      const u64 key = keys[i];
+    if (i < nwin) {
+      const u64 key = sk[i];
       const u32 node = key_id(key);
       int slot = -1;
       for (int base = 0; base < ncand && slot < 0; base += 32) {
@@ -229,38 +348,44 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
   if (tid == 0) { p.out_ncand[q] = ncand; p.out_status[q] = 0; }
 }
 
-int32_t expand_max_candidates() { return EXP_MAXC; }
+int32_t expand_max_candidates() { return EXP_MAXC_BIG; }
+
+template <typename T>
+static int launch_expand_t(const ExpandParams& p, cudaStream_t st) {
+  constexpr int SMALL = 4096;
+  auto smem_of = [&](int maxc) { return (size_t)maxc * 8 + (size_t)maxc * 4 * 2 + maxc + (size_t)((p.D + 1) & ~1) * 4 + (size_t)p.kp2 * 8; };
+  if (smem_of(EXP_MAXC_BIG) > 220 * 1024) { set_error("expand_rescore: D=%d / k=%d too large for shared memory", p.D, p.k); return B200R_EINVAL; }
+  B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(SMALL)));
+  expand_rescore_kernel<T, SMALL, false><<<p.B, EXP_THREADS, smem_of(SMALL), st>>>(p);
+  count_launch();
+  B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, EXP_MAXC_BIG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(EXP_MAXC_BIG)));
+  expand_rescore_kernel<T, EXP_MAXC_BIG, true><<<p.B, EXP_THREADS, smem_of(EXP_MAXC_BIG), st>>>(p);
+  count_launch();
+  B200R_CUDA_CHECK(cudaGetLastError());
+  return B200R_OK;
+}
 
 int launch_expand_rescore(const Index* ix, const Graph* g, const void* Q, const int64_t* seeds, int B, int S, int window,
                           float alpha_dense, float alpha_graph, int k, float* out_scores, int64_t* out_ids, int32_t* out_hops,
                           float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand, int32_t* out_status, cudaStream_t st) {
   ExpandParams p;
-  p.X = ix->X; p.Q = Q; p.row_mult = (ix->metric == B200R_COS || ix->dtype == B200R_I8) ? ix->row_mult : nullptr;
+  p.X = ix->X; p.Q = Q; p.row_mult = ix->row_mult;
   p.row_ptr = reinterpret_cast<const long long*>(g->row_ptr); p.col_idx = g->col_idx;
   p.seeds = reinterpret_cast<const long long*>(seeds);
   p.N = ix->N; p.V = g->V; p.id_base = ix->id_base;
   p.D = ix->D; p.B = B; p.S = S; p.window = window; p.k = k; p.metric = ix->metric;
+  p.kp2 = 2; while (p.kp2 < k) p.kp2 <<= 1;
   p.alpha_dense = alpha_dense; p.alpha_graph = alpha_graph;
   p.out_scores = out_scores; p.out_ids = reinterpret_cast<long long*>(out_ids); p.out_hops = out_hops;
   p.out_gn = out_gn; p.out_dn = out_dn; p.out_cos = out_cos; p.out_ncand = out_ncand; p.out_status = out_status;
-  const size_t smem = (size_t)EXP_MAXC * 8 + EXP_MAXC * 4 + EXP_MAXC * 4 + EXP_MAXC + (size_t)ix->D * 4;
-  if (smem > 220 * 1024) { set_error("expand_rescore: D=%d too large", ix->D); return B200R_EINVAL; }
-#define B200R_LAUNCH_EXP(T)                                                                                        \
-  do {                                                                                                             \
-    B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    expand_rescore_kernel<T><<<B, EXP_THREADS, smem, st>>>(p);                                                     \
-  } while (0)
   switch (ix->dtype) {
-    case B200R_BF16: B200R_LAUNCH_EXP(__nv_bfloat16); break;
-    case B200R_F16: B200R_LAUNCH_EXP(__half); break;
-    case B200R_F32: B200R_LAUNCH_EXP(float); break;
-    case B200R_I8: B200R_LAUNCH_EXP(int8_t); break;
-    default: set_error("bad dtype"); return B200R_EINVAL;
+    case B200R_BF16: return launch_expand_t<__nv_bfloat16>(p, st);
+    case B200R_F16: return launch_expand_t<__half>(p, st);
+    case B200R_F32: return launch_expand_t<float>(p, st);
+    case B200R_I8: return launch_expand_t<int8_t>(p, st);
   }
-#undef B200R_LAUNCH_EXP
-  count_launch();
-  B200R_CUDA_CHECK(cudaGetLastError());
-  return B200R_OK;
+  set_error("bad dtype");
+  return B200R_EINVAL;
 }
 
 }  // namespace b200r

@@ -74,7 +74,8 @@ struct SearchPlan {
   // scan
   int scan_bq, scan_warps, scan_blocks;
   // workspace layout (byte offsets)
-  size_t off_lists, off_counts, off_gthr, off_qinv, off_end;
+  int num_groups;        // > 0: two-level final select (lists2/counts2 hold the first level's output)
+  size_t off_lists, off_counts, off_gthr, off_qinv, off_lists2, off_counts2, off_end;
 };
 
 int make_plan(const Index* ix, int B, int k, int path, SearchPlan* plan);

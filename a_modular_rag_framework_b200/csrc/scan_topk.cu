@@ -30,7 +30,7 @@ struct ScanParams {
 
 // T: corpus element type, BQ: queries per pass, R: rows in flight per warp
 template <typename T, int BQ, int R>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_topk_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(SCAN_THREADS, 3) scan_topk_kernel(const ScanParams p) {
   typedef typename QueryType<T>::type QT;
   constexpr int VEC = ElemTraits<T>::kVec;
   constexpr int PARTS = VEC / 4;
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_topk_kernel(const ScanParam
   }
 }
 
-template <typename T, int R>
+template <typename T, int R1, int R4>
 static int launch_scan_t(const Index* ix, const void* Q, const SearchPlan& pl, void* ws, cudaStream_t st) {
   constexpr int VEC = ElemTraits<T>::kVec;
   ScanParams p;
@@ -176,7 +176,7 @@ static int launch_scan_t(const Index* ix, const void* Q, const SearchPlan& pl, v
   p.gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
   const long long total_warps = (long long)pl.scan_blocks * SCAN_WARPS;
   long long rpw = (ix->N + total_warps - 1) / total_warps;
-  rpw = (rpw + R - 1) / R * R;
+  rpw = (rpw + R1 - 1) / R1 * R1;   // R1 is a multiple of R4
   p.rows_per_warp = rpw;
   const int chunks = ix->D / VEC;
   for (int q0 = 0; q0 < pl.B; q0 += 4) {
@@ -185,14 +185,14 @@ static int launch_scan_t(const Index* ix, const void* Q, const SearchPlan& pl, v
     const int bq = p.nq >= 3 ? 4 : p.nq;
     const size_t smem = (size_t)(VEC / 4) * bq * chunks * sizeof(float4) + SCAN_WARPS * 256 * sizeof(u32);
     if (smem > 200 * 1024) { set_error("scan path: D=%d too large for shared-memory query staging", ix->D); return B200R_EINVAL; }
-#define B200R_LAUNCH_SCAN(BQ)                                                                              \
+#define B200R_LAUNCH_SCAN(BQ, R)                                                                           \
     do {                                                                                                   \
       B200R_CUDA_CHECK(cudaFuncSetAttribute(scan_topk_kernel<T, BQ, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       scan_topk_kernel<T, BQ, R><<<pl.scan_blocks, SCAN_THREADS, smem, st>>>(p);                          \
     } while (0)
-    if (bq == 1) B200R_LAUNCH_SCAN(1);
-    else if (bq == 2) B200R_LAUNCH_SCAN(2);
-    else B200R_LAUNCH_SCAN(4);
+    if (bq == 1) B200R_LAUNCH_SCAN(1, R1);
+    else if (bq == 2) B200R_LAUNCH_SCAN(2, R4);
+    else B200R_LAUNCH_SCAN(4, R4);
 #undef B200R_LAUNCH_SCAN
     count_launch();
     B200R_CUDA_CHECK(cudaGetLastError());
@@ -202,10 +202,10 @@ static int launch_scan_t(const Index* ix, const void* Q, const SearchPlan& pl, v
 
 int launch_scan_topk(const Index* ix, const void* Q, const SearchPlan& pl, void* ws, cudaStream_t st) {
   switch (ix->dtype) {
-    case B200R_BF16: return launch_scan_t<__nv_bfloat16, 4>(ix, Q, pl, ws, st);
-    case B200R_F16: return launch_scan_t<__half, 4>(ix, Q, pl, ws, st);
-    case B200R_F32: return launch_scan_t<float, 4>(ix, Q, pl, ws, st);
-    case B200R_I8: return launch_scan_t<int8_t, 2>(ix, Q, pl, ws, st);
+    case B200R_BF16: return launch_scan_t<__nv_bfloat16, 8, 4>(ix, Q, pl, ws, st);
+    case B200R_F16: return launch_scan_t<__half, 8, 4>(ix, Q, pl, ws, st);
+    case B200R_F32: return launch_scan_t<float, 8, 4>(ix, Q, pl, ws, st);
+    case B200R_I8: return launch_scan_t<int8_t, 4, 2>(ix, Q, pl, ws, st);
   }
   set_error("bad dtype %d", ix->dtype);
   return B200R_EINVAL;

@@ -9,40 +9,63 @@
 #include "common.cuh"
 #include "internal.h"
 #include <math_constants.h>
+#include <cstring>
 
 namespace b200r {
 
 constexpr int SEL_THREADS = 512;
 constexpr int SEL_WARPS = SEL_THREADS / 32;
 constexpr int SEL_STAGE_MAX = 6144;   // keys staged in shared memory (48 KB) -> 4 CTAs/SM
+constexpr int SEL_GROUP = 64;         // segments per CTA in the first level of a two-level select
+
+enum SelectMode { kSelOutput = 0, kSelThreshold = 1, kSelPartial = 2 };
 
 struct SelectParams {
   const u64* lists;
   const int* counts;
-  int S, Bpad, cap;
-  int B, k, kp2, stage_cap;
+  int S, Bpad, cap;            // input segments: lists[(s*Bpad + q)*cap + i], i < counts[s*Bpad + q]
+  int seg_per_cta;             // kSelPartial: CTA (q, g) reduces segments [g*seg_per_cta, ...)
+  int B, k, kp2, stage_cap, mode;
   const float* qinv;           // nullable
   u32* gthr;
   long long id_base;
-  float* out_scores;           // nullptr => threshold mode
+  float* out_scores;
   long long* out_ids;
+  u64* out_lists;              // kSelPartial: out_lists[(g*Bpad + q)*k + i]
+  int* out_counts;
 };
 
-// Visit every valid key of query q: from the shared-memory stage if the keys were staged, else from
-// the per-segment lists in global memory (one warp per segment, lanes stride the list).
+// Visit every valid key of the CTA's segments with a warp-uniform trip count: f(key, active).
 template <typename F>
-__device__ __forceinline__ void for_each_key(const SelectParams& p, int q, bool staged, const u64* stage, int total, F f) {
+__device__ __forceinline__ void for_each_key(const SelectParams& p, int q, int s0, int s1, bool staged, const u64* stage,
+                                             int total, F f) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (staged) {
-    for (int i = threadIdx.x; i < total; i += SEL_THREADS) f(stage[i]);
+    for (int base = warp * 32; base < total; base += SEL_THREADS) {
+      const int i = base + lane;
+      const bool active = i < total;
+      f(active ? stage[i] : 0ull, active);
+    }
   } else {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int s = warp; s < p.S; s += SEL_WARPS) {
+    for (int s = s0 + warp; s < s1; s += SEL_WARPS) {
       const size_t slot = (size_t)s * p.Bpad + q;
       const int c = p.counts[slot];
       const u64* lp = p.lists + slot * (size_t)p.cap;
-      for (int i = lane; i < c; i += 32) f(lp[i]);
+      for (int base = 0; base < c; base += 32) {
+        const int i = base + lane;
+        const bool active = i < c;
+        f(active ? lp[i] : 0ull, active);
+      }
     }
   }
+}
+
+// histogram increment with one shared-memory atomic per distinct digit per warp (candidate keys share
+// their leading bytes, so un-aggregated atomics would serialise on one bin)
+__device__ __forceinline__ void hist_add(u32* hist, bool active, u32 digit) {
+  const u32 d = active ? digit : 0xffffffffu;
+  const u32 peers = __match_any_sync(kFullMask, d);
+  if (active && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[d], (u32)__popc(peers));
 }
 
 __global__ void __launch_bounds__(SEL_THREADS) select_lists_kernel(const SelectParams p) {
@@ -55,22 +78,23 @@ __global__ void __launch_bounds__(SEL_THREADS) select_lists_kernel(const SelectP
 
   const int q = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool output = p.out_scores != nullptr;
+  int s0 = 0, s1 = p.S;
+  if (p.mode == kSelPartial) { s0 = blockIdx.y * p.seg_per_cta; s1 = min(p.S, s0 + p.seg_per_cta); }
 
   if (tid == 0) { s_total = 0; s_nout = 0; s_prefix = 0; }
   __syncthreads();
   {
     int local = 0;
-    for (int s = tid; s < p.S; s += SEL_THREADS) local += p.counts[(size_t)s * p.Bpad + q];
+    for (int s = s0 + tid; s < s1; s += SEL_THREADS) local += p.counts[(size_t)s * p.Bpad + q];
     if (local) atomicAdd(&s_total, local);
   }
   __syncthreads();
   const int total = s_total;
-  if (!output && total < p.k) return;   // not enough candidates yet for a threshold
+  if (p.mode == kSelThreshold && total < p.k) return;   // not enough candidates yet for a threshold
   const bool staged = total <= p.stage_cap;
   if (staged) {
     // gather the valid keys: one warp per segment, coalesced
-    for (int s = warp; s < p.S; s += SEL_WARPS) {
+    for (int s = s0 + warp; s < s1; s += SEL_WARPS) {
       const size_t slot = (size_t)s * p.Bpad + q;
       const int c = p.counts[slot];
       if (c == 0) continue;
@@ -85,16 +109,18 @@ __global__ void __launch_bounds__(SEL_THREADS) select_lists_kernel(const SelectP
   }
 
   u64 kth = 0;
-  if (total > p.k || !output) {   // threshold mode always has total >= k here (k-th largest of exactly k = the minimum)
+  if (total > p.k || p.mode == kSelThreshold) {
+    // threshold mode stops after the top 24 bits: the truncated key is a valid (slightly low) threshold
+    const int last_pass = (p.mode == kSelThreshold) ? 5 : 0;
     if (tid == 0) s_remaining = p.k;
-    for (int pass = 7; pass >= 0; --pass) {
+    for (int pass = 7; pass >= last_pass; --pass) {
       const int shift = pass * 8;
       for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
       __syncthreads();
       const u64 prefix = s_prefix;
       const u64 hi_mask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
-      for_each_key(p, q, staged, stage, total, [&](u64 key) {
-        if ((key & hi_mask) == prefix) atomicAdd(&hist[(u32)(key >> shift) & 255u], 1u);
+      for_each_key(p, q, s0, s1, staged, stage, total, [&](u64 key, bool active) {
+        hist_add(hist, active && (key & hi_mask) == prefix, (u32)(key >> shift) & 255u);
       });
       __syncthreads();
       if (tid < 32) {
@@ -127,17 +153,29 @@ __global__ void __launch_bounds__(SEL_THREADS) select_lists_kernel(const SelectP
     kth = s_prefix;
   }
 
-  if (!output) {
-    __syncthreads();
+  if (p.mode == kSelThreshold) {
     if (tid == 0) atomicMax(p.gthr + q, (u32)(kth >> 32));
     return;
   }
 
   const int want = total < p.k ? total : p.k;
+  if (p.mode == kSelPartial) {
+    const size_t oslot = (size_t)blockIdx.y * p.Bpad + q;
+    u64* ol = p.out_lists + oslot * (size_t)p.k;
+    for_each_key(p, q, s0, s1, staged, stage, total, [&](u64 key, bool active) {
+      if (active && key >= kth) {
+        const int pos = atomicAdd(&s_nout, 1);
+        if (pos < p.k) ol[pos] = key;
+      }
+    });
+    if (tid == 0) p.out_counts[oslot] = want;
+    return;
+  }
+
   for (int i = tid; i < p.kp2; i += SEL_THREADS) sk[i] = 0;
   __syncthreads();
-  for_each_key(p, q, staged, stage, total, [&](u64 key) {
-    if (key >= kth) {
+  for_each_key(p, q, s0, s1, staged, stage, total, [&](u64 key, bool active) {
+    if (active && key >= kth) {
       const int pos = atomicAdd(&s_nout, 1);
       if (pos < p.kp2) sk[pos] = key;
     }
@@ -155,26 +193,45 @@ __global__ void __launch_bounds__(SEL_THREADS) select_lists_kernel(const SelectP
 
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
+static int run_select(SelectParams& p, int grid_y, cudaStream_t st) {
+  const long long all = (long long)(p.mode == kSelPartial ? p.seg_per_cta : p.S) * p.cap;
+  p.stage_cap = (int)(all < SEL_STAGE_MAX ? all : SEL_STAGE_MAX);
+  const size_t smem = (size_t)p.stage_cap * 8 + (p.mode == kSelOutput ? (size_t)p.kp2 * 8 : 0);
+  B200R_CUDA_CHECK(cudaFuncSetAttribute(select_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  select_lists_kernel<<<dim3(p.B, grid_y), SEL_THREADS, smem, st>>>(p);
+  count_launch();
+  B200R_CUDA_CHECK(cudaGetLastError());
+  return B200R_OK;
+}
+
 int launch_select_lists(const Index* ix, const SearchPlan& pl, void* ws, float* out_scores, int64_t* out_ids, cudaStream_t st) {
   SelectParams p;
+  memset(&p, 0, sizeof(p));
   p.lists = reinterpret_cast<const u64*>((char*)ws + pl.off_lists);
   p.counts = reinterpret_cast<const int*>((char*)ws + pl.off_counts);
   p.S = pl.num_segments; p.Bpad = pl.Bpad; p.cap = pl.cap;
   p.B = pl.B; p.k = pl.k; p.kp2 = next_pow2(pl.k);
-  const long long all = (long long)pl.num_segments * pl.cap;
-  p.stage_cap = (int)(all < SEL_STAGE_MAX ? all : SEL_STAGE_MAX);
   p.qinv = (ix->metric == B200R_COS) ? reinterpret_cast<const float*>((char*)ws + pl.off_qinv) : nullptr;
   p.gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
   p.id_base = ix->id_base;
   p.out_scores = out_scores;
   p.out_ids = reinterpret_cast<long long*>(out_ids);
-  const size_t smem = (size_t)p.stage_cap * 8 + (out_scores ? (size_t)p.kp2 * 8 : 0);
-  B200R_CUDA_CHECK(cudaFuncSetAttribute(select_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  select_lists_kernel<<<pl.B, SEL_THREADS, smem, st>>>(p);
-  count_launch();
-  B200R_CUDA_CHECK(cudaGetLastError());
-  return B200R_OK;
+  if (!out_scores) { p.mode = kSelThreshold; return run_select(p, 1, st); }
+  if (pl.num_groups > 0) {
+    // two levels: many short per-warp lists (scan path) are first reduced group-wise to k keys each
+    SelectParams p1 = p;
+    p1.mode = kSelPartial; p1.seg_per_cta = SEL_GROUP;
+    p1.out_lists = reinterpret_cast<u64*>((char*)ws + pl.off_lists2);
+    p1.out_counts = reinterpret_cast<int*>((char*)ws + pl.off_counts2);
+    int rc = run_select(p1, pl.num_groups, st);
+    if (rc) return rc;
+    p.lists = p1.out_lists; p.counts = p1.out_counts; p.S = pl.num_groups; p.cap = pl.k;
+  }
+  p.mode = kSelOutput;
+  return run_select(p, 1, st);
 }
+
+int select_group_size() { return SEL_GROUP; }
 
 // ------------------------------------------------------------------------------------------------
 // public merge: candidates [G, B, kin] (f32 score, i64 id) -> [B, k]

@@ -116,3 +116,22 @@ def test_frontier_overflow_is_reported():
     X = np.ones((V, 8), dtype=np.float32)
     with pytest.raises(B200RError):
         _run(X, np.ones((1, 8), dtype=np.float32), row_ptr, col_idx, [[0]], 1, 0.4, 0.2, 10)
+
+
+def test_hub_node_and_retry_instantiation():
+    """A hub with 6000 neighbours: exercises the warp-per-node hub pass and the 8192-candidate re-run of a
+    query that overflows the 4096-candidate instantiation."""
+    rng = np.random.default_rng(8)
+    V, D, k = 7000, 64, 25
+    src = np.zeros(6000, dtype=np.int64)
+    dst = np.arange(1, 6001, dtype=np.int64)
+    extra_s, extra_d = rng.integers(6001, V, 300), rng.integers(6001, V, 300)
+    row_ptr, col_idx = O.csr_from_edges(V, np.concatenate([src, extra_s]), np.concatenate([dst, extra_d]))
+    X = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((V, D)).astype(np.float32)))
+    Q = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((2, D)).astype(np.float32)))
+    seeds = np.array([[0, 6500, -1], [6100, 6200, 6300]])
+    out = _run(X, Q, row_ptr, col_idx, seeds, 1, 0.4, 0.2, k)
+    for b in range(2):
+        top, dist = O.expand_rescore(Q[b], X, row_ptr, col_idx, seeds[b], 1, 0.4, 0.2, k)
+        _check_query(out, b, top, dist, k)
+    assert int(out["ncand"][0]) > 4096
