@@ -171,6 +171,9 @@ class B200RetrievalBackend:
 
     def _embed_query(self, query: str, trace_id: str) -> Optional[List[float]]:
         """router.embed exactly as DenseReranker.score calls it (retrieval_backend.py:227-231): dict or list result."""
+        cache = getattr(self, "_embed_cache", None)
+        if cache is not None and query in cache:
+            return cache[query]
         try:
             q_emb = self.router.embed(model_hint=self._resolve_embed_model(), texts=[query], require={"trace_id": trace_id})
             qv = (q_emb.get("vectors") if isinstance(q_emb, dict) else q_emb)[0]
@@ -311,7 +314,76 @@ class B200RetrievalBackend:
         }
         return {"hits": hits, "diagnostics": diagnostics}
 
+    def retrieve_many(self, reqs: Sequence[Any]) -> List[RetrievalOut]:
+        """Batching shim: the orchestrator issues one query at a time
+        (app/orchestrator/nodes.py:110-115, my_code/run_system.py:35-39); a batch runner can hand all
+        requests over at once so the dense stage is ONE search launch and the graph stage ONE expand launch.
+        Results are identical to calling retrieve() per request (same engine calls, batched)."""
+        if not reqs:
+            return []
+        self._embed_cache = {}
+        batch = _BatchedEngine(self, reqs)
+        saved = self.engine
+        self.engine = batch
+        try:
+            return [self.retrieve(r) for r in reqs]
+        finally:
+            self.engine = saved
+            self._embed_cache = None
+
     def retrieve(self, req: Any) -> RetrievalOut:
         result = self.run(req)
         hits = [Hit(id=h["id"], score=h["score"], meta=h.get("meta")) for h in result["hits"]]
         return RetrievalOut(hits=hits, diagnostics=result.get("diagnostics", {}))
+
+
+class _BatchedEngine:
+    """Engine proxy used by retrieve_many: pre-computes the dense search (and, when every request takes the
+    graph path with the same window, the expansion) for the whole batch, then serves the per-request calls."""
+
+    def __init__(self, be: "B200RetrievalBackend", reqs: Sequence[Any]):
+        self.inner = be.engine
+        self.N = getattr(self.inner, "N", None)
+        self.D = getattr(self.inner, "D", None)
+        self._dense: Dict[Tuple[float, ...], Tuple[List[float], List[int]]] = {}
+        self._graph: Dict[Tuple[Tuple[float, ...], Tuple[int, ...], int], Dict[str, list]] = {}
+        qvs = []
+        for r in reqs:
+            qv = be._embed_query(r.query, getattr(r, "trace_id", None) or "trace-demo")
+            be._embed_cache[r.query] = qv
+            if qv is not None and (self.D is None or len(qv) == self.D) and any(qv):
+                qvs.append(qv)
+        if not qvs:
+            return
+        pools = {max(be.seed_k, int(getattr(r, "top_k", None) or be.default_top_k)) for r in reqs}
+        pool = max(pools)
+        s, i = self.inner.dense_search(qvs, pool)
+        for qv, ss, ii in zip(qvs, s, i):
+            self._dense[tuple(qv)] = (ss, ii)
+        self._pool = pool
+        windows = {max(0, int(getattr(r, "graph_window", None) if isinstance(getattr(r, "graph_window", None), int) else be.graph_window)) for r in reqs}
+        all_graph = all(bool(getattr(r, "graph_id", "") or "") for r in reqs) and self.inner.has_graph() and be.alpha_graph != 0.0
+        if all_graph and len(windows) == 1 and len(pools) == 1:
+            w = windows.pop()
+            kk = max(pool, be.bm25_pool_k)
+            seeds = [[r for r in self._dense[tuple(qv)][1] if r >= 0][: be.seed_k] for qv in qvs]
+            S = max(len(sd) for sd in seeds)
+            padded = [sd + [-1] * (S - len(sd)) for sd in seeds]
+            out = self.inner.expand_rescore(qvs, padded, w, be.alpha_dense, be.alpha_graph, kk)
+            for j, (qv, sd) in enumerate(zip(qvs, seeds)):
+                self._graph[(tuple(qv), tuple(sd), w)] = {key: [v[j]] for key, v in out.items()}
+
+    def has_graph(self) -> bool:
+        return self.inner.has_graph()
+
+    def dense_search(self, qvecs, k: int):
+        hit = self._dense.get(tuple(qvecs[0])) if len(qvecs) == 1 else None
+        if hit is not None and k <= self._pool:
+            return [hit[0][:k]], [hit[1][:k]]
+        return self.inner.dense_search(qvecs, k)
+
+    def expand_rescore(self, qvecs, seeds, window, alpha_dense, alpha_graph, k):
+        hit = self._graph.get((tuple(qvecs[0]), tuple(seeds[0]), window)) if len(qvecs) == 1 else None
+        if hit is not None and k <= len(hit["id"][0]):
+            return {key: ([v[0][:k]] if isinstance(v[0], list) else v) for key, v in hit.items()}
+        return self.inner.expand_rescore(qvecs, seeds, window, alpha_dense, alpha_graph, k)

@@ -89,9 +89,9 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   if (B <= 0) { set_error("B must be > 0 (got %d)", B); return B200R_EINVAL; }
   if (k <= 0 || k > B200R_MAX_K) { set_error("k must be in [1, %d] (got %d)", B200R_MAX_K, k); return B200R_EINVAL; }
   const bool gemm_ok = ix->has_tmap;
-  // measured on B200: the tensor-core path is HBM-bound (77% of copy bandwidth) already at B=1, so it is the
-  // default whenever the corpus type allows it; the CUDA-core scan serves fp32 / int8 / odd-D corpora
-  if (path == B200R_PATH_AUTO) path = gemm_ok ? B200R_PATH_GEMM : B200R_PATH_SCAN;
+  // measured on B200 (10M x 768 bf16): the CUDA-core scan streams at 100% / 86% of the copy bandwidth for
+  // B = 1 / 2, the tensor-core path at 77-79% for any small B and tensor-bound from B ~ 256 up
+  if (path == B200R_PATH_AUTO) path = (gemm_ok && B > 2) ? B200R_PATH_GEMM : B200R_PATH_SCAN;
   if (path == B200R_PATH_GEMM && !gemm_ok) {
     set_error("gemm path needs a bf16/f16 corpus with D %% 8 == 0 (dtype=%d D=%d)", ix->dtype, ix->D);
     return B200R_EINVAL;

@@ -157,11 +157,14 @@ template <> struct ElemTraits<float> {
 template <> struct ElemTraits<int8_t> {
   static constexpr int kVec = 16;
   __device__ static __forceinline__ void unpack(const uint4& v, float* f) {
-    const u32 w[4] = {v.x, v.y, v.z, v.w};
+    // int8 -> float without I2F: put (b ^ 0x80) into the mantissa of 2^23 and subtract 2^23 + 128
+    const u32 w[4] = {v.x ^ 0x80808080u, v.y ^ 0x80808080u, v.z ^ 0x80808080u, v.w ^ 0x80808080u};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) f[4 * i + j] = (float)(int)(signed char)((w[i] >> (8 * j)) & 0xffu);
+      f[4 * i + 0] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7650)) - 8388736.0f;
+      f[4 * i + 1] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7651)) - 8388736.0f;
+      f[4 * i + 2] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7652)) - 8388736.0f;
+      f[4 * i + 3] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7653)) - 8388736.0f;
     }
   }
 };

@@ -301,7 +301,7 @@ def main():
             peaks = json.load(f)
     except Exception:
         pass
-    used_path = a.path if a.path != "auto" else "gemm"
+    used_path = a.path if a.path != "auto" else ("gemm" if a.batch > 2 else "scan")
     # the dominant kernel is launched once per phase of a step: sum its launches over the step
     kernel_avg_ms = kernel_ms / max(a.steps, 1)
     launches_per_step = kernel_n / max(a.steps, 1)

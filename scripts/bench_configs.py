@@ -50,7 +50,7 @@ def run_search(name, N, D, B, k, dtype, path, steps=10, warmup=3, check=True):
     ms = e0.elapsed_time(e1) / steps
     kms /= steps
     esz = X.element_size()
-    used = path if path != "auto" else ("gemm" if dtype in (torch.bfloat16, torch.float16) else "scan")
+    used = path if path != "auto" else ("gemm" if B > 2 and dtype in (torch.bfloat16, torch.float16) else "scan")
     line = {"config": name, "rows": N, "dim": D, "batch": B, "k": k, "dtype": str(dtype).split(".")[-1], "path": used,
             "ms_per_batch": ms, "queries_per_s": B / (ms * 1e-3), "kernel_ms_per_batch": kms, "kernel_launches_per_batch": kn / steps}
     passes = 1 if used == "gemm" else (B + 3) // 4
@@ -79,6 +79,34 @@ def run_search(name, N, D, B, k, dtype, path, steps=10, warmup=3, check=True):
     del ix, X, Q
     torch.cuda.empty_cache()
     return line
+
+
+def run_search_i8(name, N, D, B, k, steps=10, warmup=3):
+    Xf = corpus(N, D, torch.float16)
+    X = torch.empty((N, D), dtype=torch.int8, device=dev)
+    blk = 1 << 20
+    for r0 in range(0, N, blk):
+        X[r0:r0 + blk] = torch.clamp(torch.round(Xf[r0:r0 + blk].float() * 127.0 / Xf[r0:r0 + blk].float().abs().amax(dim=1, keepdim=True)), -127, 127).to(torch.int8)
+    del Xf
+    Q = queries(steps + warmup, B, D, torch.float32)
+    ix = DenseIndex(X, metric="cos")
+    for i in range(warmup):
+        ix.search(Q[i], k)
+    torch.cuda.synchronize()
+    _native.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        ix.search(Q[warmup + i], k)
+    e1.record()
+    torch.cuda.synchronize()
+    kms, kn = _native.profile_read()
+    _native.profile_enable(False)
+    ms = e0.elapsed_time(e1) / steps
+    kms /= steps
+    gbs = N * D * ((B + 3) // 4) / (kms * 1e-3) / 1e9
+    print(json.dumps({"config": name, "rows": N, "dim": D, "batch": B, "k": k, "dtype": "int8", "path": "scan", "ms_per_batch": ms,
+                      "queries_per_s": B / (ms * 1e-3), "kernel_ms_per_batch": kms, "hbm_GBps": gbs, "hbm_frac_of_measured": gbs / PEAKS["hbm_gbs"]}), flush=True)
 
 
 def run_graph(name, V, E, D, B, S, k, steps=5, warmup=2):
@@ -123,6 +151,11 @@ CONFIGS = {
     "cfg2_10Mx768_B4_scan": lambda: run_search("cfg2_10Mx768_B4_scan", 10_000_000, 768, 4, 100, torch.bfloat16, "scan", steps=20),
     "cfg2_10Mx768_B16_gemm": lambda: run_search("cfg2_10Mx768_B16_gemm", 10_000_000, 768, 16, 100, torch.bfloat16, "gemm", steps=20),
     "cfg2_10Mx768_B16_scan": lambda: run_search("cfg2_10Mx768_B16_scan", 10_000_000, 768, 16, 100, torch.bfloat16, "scan", steps=5),
+    "cfg2_10Mx768_B2_scan": lambda: run_search("cfg2_10Mx768_B2_scan", 10_000_000, 768, 2, 100, torch.bfloat16, "scan", steps=20, check=False),
+    "cfg2_10Mx768_B2_gemm": lambda: run_search("cfg2_10Mx768_B2_gemm", 10_000_000, 768, 2, 100, torch.bfloat16, "gemm", steps=20, check=False),
+    "f32_5Mx768_B1_scan": lambda: run_search("f32_5Mx768_B1_scan", 5_000_000, 768, 1, 100, torch.float32, "scan", steps=20),
+    "f32_5Mx768_B4_scan": lambda: run_search("f32_5Mx768_B4_scan", 5_000_000, 768, 4, 100, torch.float32, "scan", steps=20),
+    "i8_10Mx768_B1_scan": lambda: run_search_i8("i8_10Mx768_B1_scan", 10_000_000, 768, 1, 100, steps=20),
     "cfg2_10Mx768_B1_gemm": lambda: run_search("cfg2_10Mx768_B1_gemm", 10_000_000, 768, 1, 100, torch.bfloat16, "gemm", steps=20),
     "cfg3_12p5Mx384_f16_k1000_B16": lambda: run_search("cfg3_12p5Mx384_f16_k1000_B16", 12_500_000, 384, 16, 1000, torch.float16, "gemm", steps=10),
     "cfg3_12p5Mx384_f16_k1000_B1": lambda: run_search("cfg3_12p5Mx384_f16_k1000_B1", 12_500_000, 384, 1, 1000, torch.float16, "scan", steps=10),

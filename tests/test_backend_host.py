@@ -162,3 +162,18 @@ def test_through_the_references_own_adapter_and_flow_conventions(corpus, monkeyp
     for name in ("router", "sink", "index_path", "graph_root", "graph_window", "alpha_text", "alpha_graph", "alpha_dense",
                  "bm25_pool_k", "default_top_k", "qe_lines", "qe_attr_paraphrase", "embed_batch"):
         assert name in params
+
+
+def test_retrieve_many_equals_retrieve(corpus):
+    be = _backend(corpus, seed_k=4)
+    reqs = [_req(corpus.docs[r]["text"], top_k=7, trace_id=f"t{r}") for r in (3, 14, 15, 42)]
+    single = [be.retrieve(r) for r in reqs]
+    many = be.retrieve_many(reqs)
+    assert len(many) == 4
+    for a, b in zip(single, many):
+        assert [h.id for h in a.hits] == [h.id for h in b.hits]
+        assert np.allclose([h.score for h in a.hits], [h.score for h in b.hits])
+        assert a.diagnostics["graph_candidates"] == b.diagnostics["graph_candidates"]
+    assert type(be.engine).__name__ == "OracleEngine"   # proxy removed afterwards
+    mixed = be.retrieve_many([_req(corpus.docs[5]["text"], graph_id=""), _req(corpus.docs[6]["text"], top_k=3)])
+    assert mixed[0].hits[0].meta["row"] == 5 and len(mixed[1].hits) == 3
