@@ -23,7 +23,7 @@ EXPORTS = [
     "b200r_search_workspace_bytes", "b200r_search", "b200r_search_host",
     "b200r_merge_topk", "b200r_merge_topk_packed", "b200r_profile_enable", "b200r_profile_read",
     "b200r_graph_create", "b200r_graph_destroy",
-    "b200r_expand_max_candidates", "b200r_expand_rescore",
+    "b200r_expand_max_candidates", "b200r_expand_rescore", "b200r_expand_workspace_bytes", "b200r_expand_rescore_sharded",
 ]
 
 
@@ -71,6 +71,11 @@ def load() -> ctypes.CDLL:
     lib.b200r_expand_max_candidates.restype = c_int32
     lib.b200r_expand_rescore.argtypes = [c_uint64, c_uint64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_int32,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.b200r_expand_workspace_bytes.argtypes = [c_int32]
+    lib.b200r_expand_workspace_bytes.restype = c_size_t
+    lib.b200r_expand_rescore_sharded.argtypes = [c_uint64, c_uint64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_int32,
+                                                 c_int32, c_int64, c_int64, c_void_p, c_size_t, c_void_p,
+                                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is c_int and name not in ("b200r_version", "b200r_last_error"):

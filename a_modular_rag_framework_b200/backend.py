@@ -76,7 +76,7 @@ class CudaEngine:
         self.device = torch.device(device)
         X, meta, scales = store.load_embeddings(emb_path)
         tdtype = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32, "i8": torch.int8}[meta["dtype"]]
-        host = torch.from_numpy(np.ascontiguousarray(X))
+        host = torch.from_numpy(np.array(X, copy=True))   # the store is a read-only memmap
         if meta["dtype"] == "bf16":
             host = host.view(torch.bfloat16)
         self.X = host.to(self.device)

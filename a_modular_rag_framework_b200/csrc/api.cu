@@ -7,6 +7,7 @@
 #include <cstring>
 #include <cmath>
 #include <new>
+#include <cstdint>
 #include <vector>
 
 namespace b200r {
@@ -450,8 +451,32 @@ int b200r_expand_rescore(uint64_t index, uint64_t graph, const void* Q, const in
   }
   B200R_CUDA_CHECK(cudaSetDevice(ix->device));
   return launch_expand_rescore(ix, g, Q, seeds, B, S, window, alpha_dense, alpha_graph, k, out_scores, out_ids, out_hops,
-                               out_graph_norm, out_dense_norm, out_cos, out_ncand, out_status,
-                               reinterpret_cast<cudaStream_t>(stream));
+                               out_graph_norm, out_dense_norm, out_cos, out_ncand, out_status, 0, INT64_MIN, INT64_MAX, nullptr,
+                               nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t b200r_expand_workspace_bytes(int32_t B) { return B > 0 ? expand_workspace_bytes(B) : 0; }
+
+int b200r_expand_rescore_sharded(uint64_t index, uint64_t graph, const void* Q, const int64_t* seeds, int32_t B, int32_t S,
+                                 int32_t window, float alpha_dense, float alpha_graph, int32_t k, int32_t pass, int64_t own_lo,
+                                 int64_t own_hi, void* workspace, size_t workspace_bytes, float* minmax, float* out_scores,
+                                 int64_t* out_ids, int32_t* out_hops, float* out_graph_norm, float* out_dense_norm, float* out_cos,
+                                 int32_t* out_ncand, int32_t* out_status, void* stream) {
+  Index* ix = get_index(index);
+  Graph* g = get_graph(graph);
+  if (!ix || !g) return B200R_ESTATE;
+  if (pass != 1 && pass != 2) { set_error("pass must be 1 or 2"); return B200R_EINVAL; }
+  if (!Q || !seeds || !workspace || !minmax || !out_scores || !out_ids || !out_hops || !out_graph_norm || !out_dense_norm ||
+      !out_cos || !out_ncand || !out_status) { set_error("null pointer"); return B200R_EINVAL; }
+  if (B <= 0 || S <= 0 || k <= 0 || k > B200R_MAX_K || window < 0 || window > 255) { set_error("bad B/S/k/window"); return B200R_EINVAL; }
+  if (workspace_bytes < expand_workspace_bytes(B) || (reinterpret_cast<uintptr_t>(workspace) & 255)) {
+    set_error("expand workspace too small or misaligned: need %zu bytes, 256-byte aligned", expand_workspace_bytes(B));
+    return B200R_ENOMEM;
+  }
+  B200R_CUDA_CHECK(cudaSetDevice(ix->device));
+  return launch_expand_rescore(ix, g, Q, seeds, B, S, window, alpha_dense, alpha_graph, k, out_scores, out_ids, out_hops,
+                               out_graph_norm, out_dense_norm, out_cos, out_ncand, out_status, pass, own_lo, own_hi, workspace,
+                               minmax, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

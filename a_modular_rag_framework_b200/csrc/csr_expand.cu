@@ -42,6 +42,11 @@ struct ExpandParams {
   float alpha_dense, alpha_graph;
   float* out_scores; long long* out_ids; int* out_hops; float* out_gn; float* out_dn; float* out_cos;
   int* out_ncand; int* out_status;
+  // row-sharded corpora (one rank per GPU): mode 0 = everything in one launch; 1 = BFS + re-score the candidates this
+  // rank owns + local min/max, parked in the workspace; 2 = fuse with the all-reduced min/max and rank the owned ones
+  int mode;
+  long long own_lo, own_hi;       // global node ids this rank scores: [own_lo, own_hi)
+  u32* ws_cand; float* ws_cos; uint8_t* ws_dist; int* ws_ncand; float* ws_minmax;   // [B][EXP_MAXC_BIG] / [B] / [B][2]
 };
 
 __device__ __forceinline__ float hop_decay(int d) {
@@ -71,6 +76,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
   constexpr int HASH = 2 * MAXC;
   const int q = blockIdx.x;
   if (RETRY_PASS && p.out_status[q] != kStatusRetry) return;
+  if (p.mode == 2 && p.out_status[q] != 0) return;     // pass 1 already reported the overflow
 
   extern __shared__ uint8_t smem_raw[];
   u64* keys = reinterpret_cast<u64*>(smem_raw);                    // [MAXC]  (aliases the hash table, used after the BFS)
@@ -89,6 +95,9 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+  int ncand = 0;
+  float qinv = 1.0f;
+  if (p.mode != 2) {
   for (int i = tid; i < HASH; i += EXP_THREADS) table[i] = EXP_EMPTY;
   if (tid == 0) { s_count = 0; s_overflow = 0; s_nhubs = 0; }
   // query -> fp32 in smem, and its norm
@@ -105,11 +114,11 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
   __syncthreads();
   double qn_tot = 0.0;
   for (int w = 0; w < EXP_WARPS; ++w) qn_tot += s_qn[w];
-  const float qinv = (p.metric == B200R_COS) ? (qn_tot > 0.0 ? (float)(1.0 / sqrt(qn_tot)) : 0.0f) : 1.0f;
+  qinv = (p.metric == B200R_COS) ? (qn_tot > 0.0 ? (float)(1.0 / sqrt(qn_tot)) : 0.0f) : 1.0f;
 
   // ---- level 0: seeds ---------------------------------------------------------------------------
   for (int i = tid; i < p.S; i += EXP_THREADS) {
-    const long long s = p.seeds[(size_t)q * p.S + i] - p.id_base;
+    const long long s = p.seeds[(size_t)q * p.S + i];   // node id == global corpus row id
     if (s >= 0 && s < p.V) {
       if (hash_insert<HASH>(table, (u32)s)) {
         const int pos = atomicAdd(&s_count, 1);
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
     level_begin = level_end;
   }
   __syncthreads();
-  const int ncand = min(s_count, MAXC);
+  ncand = min(s_count, MAXC);
   if (s_overflow) {  // block-uniform
     if (tid == 0) { p.out_status[q] = (MAXC < EXP_MAXC_BIG) ? kStatusRetry : B200R_EOVERFLOW; p.out_ncand[q] = s_count; }
     for (int i = tid; i < p.k; i += EXP_THREADS) {
@@ -199,8 +208,9 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
 #pragma unroll
     for (int r = 0; r < EXP_ROWS; ++r) {
       const int c = min(c0 + r, ncand - 1);
-      const u32 row = cand[c];
-      have[r] = (c0 + r < ncand) && ((long long)row < p.N);
+      const long long node = (long long)cand[c];
+      const long long row = node - p.id_base;
+      have[r] = (c0 + r < ncand) && node >= p.own_lo && node < p.own_hi && row >= 0 && row < p.N;
       rp[r] = Xb + (size_t)(have[r] ? row : 0) * row_bytes;
       acc[r] = 0.0f;
     }
@@ -223,18 +233,30 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFullMask, a, o);
       if (lane == 0 && c0 + r < ncand) {
-        const float m = have[r] ? (p.row_mult ? p.row_mult[cand[c0 + r]] : 1.0f) : 0.0f;
+        const float m = have[r] ? (p.row_mult ? p.row_mult[(long long)cand[c0 + r] - p.id_base] : 1.0f) : 0.0f;
         cosv[c0 + r] = (a * m) * qinv + 0.0f;
       }
     }
   }
   __syncthreads();
+  } else {
+    // pass 2: candidates, hops and cosines were parked by pass 1
+    ncand = p.ws_ncand[q];
+    for (int c = tid; c < ncand; c += EXP_THREADS) {
+      cand[c] = p.ws_cand[(size_t)q * EXP_MAXC_BIG + c];
+      cosv[c] = p.ws_cos[(size_t)q * EXP_MAXC_BIG + c];
+      dist[c] = p.ws_dist[(size_t)q * EXP_MAXC_BIG + c];
+    }
+    __syncthreads();
+  }
 
   // ---- min/max of both channels (retrieval_backend.py:296-301) ----------------------------------
   float cmin = CUDART_INF_F, cmax = -CUDART_INF_F, gmin = CUDART_INF_F, gmax = -CUDART_INF_F;
   for (int c = tid; c < ncand; c += EXP_THREADS) {
     const float cv = cosv[c], gv = hop_decay(dist[c]);
-    cmin = fminf(cmin, cv); cmax = fmaxf(cmax, cv); gmin = fminf(gmin, gv); gmax = fmaxf(gmax, gv);
+    const long long node = (long long)cand[c];
+    if (node >= p.own_lo && node < p.own_hi) { cmin = fminf(cmin, cv); cmax = fmaxf(cmax, cv); }
+    gmin = fminf(gmin, gv); gmax = fmaxf(gmax, gv);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -247,6 +269,17 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
     cmin = fminf(cmin, s_red[0][w]); cmax = fmaxf(cmax, s_red[1][w]);
     gmin = fminf(gmin, s_red[2][w]); gmax = fmaxf(gmax, s_red[3][w]);
   }
+  if (p.mode == 1) {
+    // park this rank's share; the host all-reduces ws_minmax (min, max) across ranks before pass 2
+    for (int c = tid; c < ncand; c += EXP_THREADS) {
+      p.ws_cand[(size_t)q * EXP_MAXC_BIG + c] = cand[c];
+      p.ws_cos[(size_t)q * EXP_MAXC_BIG + c] = cosv[c];
+      p.ws_dist[(size_t)q * EXP_MAXC_BIG + c] = dist[c];
+    }
+    if (tid == 0) { p.ws_ncand[q] = ncand; p.ws_minmax[2 * q] = cmin; p.ws_minmax[2 * q + 1] = cmax; p.out_ncand[q] = ncand; p.out_status[q] = 0; }
+    return;
+  }
+  if (p.mode == 2) { cmin = p.ws_minmax[2 * q]; cmax = p.ws_minmax[2 * q + 1]; }
   const bool c_flat = !(cmax > cmin), g_flat = !(gmax > gmin);   // "vmax <= vmin -> all 0.0" (:300)
   const float c_den = c_flat ? 1.0f : (cmax - cmin), g_den = g_flat ? 1.0f : (gmax - gmin);
 
@@ -254,7 +287,9 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
   for (int c = tid; c < ncand; c += EXP_THREADS) {
     const float dn = c_flat ? 0.0f : (cosv[c] - cmin) / c_den;
     const float gn = g_flat ? 0.0f : (hop_decay(dist[c]) - gmin) / g_den;
-    keys[c] = make_key(p.alpha_graph * gn + p.alpha_dense * dn, cand[c]);   // ties on the fused score -> lower node id
+    const long long node = (long long)cand[c];
+    const bool own = node >= p.own_lo && node < p.own_hi;
+    keys[c] = own ? make_key(p.alpha_graph * gn + p.alpha_dense * dn, cand[c]) : 0ull;   // ties on the fused score -> lower node id
   }
   if (tid == 0) { s_prefix = 0; s_remaining = p.k; s_nout = 0; }
   for (int i = tid; i < p.kp2; i += EXP_THREADS) sk[i] = 0;
@@ -310,7 +345,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
   }
   for (int i = tid; i < ncand; i += EXP_THREADS) {
     const u64 key = keys[i];
-    if (key >= kth) {
+    if (key >= kth && key != 0) {
       const int pos = atomicAdd(&s_nout, 1);
       if (pos < p.kp2) sk[pos] = key;
     }
@@ -319,7 +354,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
   block_bitonic_desc(sk, p.kp2);
 
   // ---- emit: winner i is looked up in the candidate list by one warp (k is small) ------------------
-  const int nwin = min(ncand, p.k);
+  const int nwin = min(min(ncand, p.k), s_nout);
   for (int i = warp; i < p.k; i += EXP_WARPS) {
     const size_t o = (size_t)q * p.k + i;
     if (i < nwin) {
@@ -335,7 +370,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
         const float cv = cosv[slot];
         const int hd = dist[slot];
         p.out_scores[o] = key_score(key);
-        p.out_ids[o] = p.id_base + (long long)node;
+        p.out_ids[o] = (long long)node;
         p.out_hops[o] = hd;
         p.out_gn[o] = g_flat ? 0.0f : (hop_decay(hd) - gmin) / g_den;
         p.out_dn[o] = c_flat ? 0.0f : (cv - cmin) / c_den;
@@ -355,19 +390,30 @@ static int launch_expand_t(const ExpandParams& p, cudaStream_t st) {
   constexpr int SMALL = 4096;
   auto smem_of = [&](int maxc) { return (size_t)maxc * 8 + (size_t)maxc * 4 * 2 + maxc + (size_t)((p.D + 1) & ~1) * 4 + (size_t)p.kp2 * 8; };
   if (smem_of(EXP_MAXC_BIG) > 220 * 1024) { set_error("expand_rescore: D=%d / k=%d too large for shared memory", p.D, p.k); return B200R_EINVAL; }
-  B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(SMALL)));
-  expand_rescore_kernel<T, SMALL, false><<<p.B, EXP_THREADS, smem_of(SMALL), st>>>(p);
-  count_launch();
-  B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, EXP_MAXC_BIG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(EXP_MAXC_BIG)));
-  expand_rescore_kernel<T, EXP_MAXC_BIG, true><<<p.B, EXP_THREADS, smem_of(EXP_MAXC_BIG), st>>>(p);
-  count_launch();
+  if (p.mode != 2) {
+    B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(SMALL)));
+    expand_rescore_kernel<T, SMALL, false><<<p.B, EXP_THREADS, smem_of(SMALL), st>>>(p);
+    count_launch();
+    B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, EXP_MAXC_BIG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(EXP_MAXC_BIG)));
+    expand_rescore_kernel<T, EXP_MAXC_BIG, true><<<p.B, EXP_THREADS, smem_of(EXP_MAXC_BIG), st>>>(p);
+    count_launch();
+  } else {
+    B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, EXP_MAXC_BIG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(EXP_MAXC_BIG)));
+    expand_rescore_kernel<T, EXP_MAXC_BIG, false><<<p.B, EXP_THREADS, smem_of(EXP_MAXC_BIG), st>>>(p);
+    count_launch();
+  }
   B200R_CUDA_CHECK(cudaGetLastError());
   return B200R_OK;
 }
 
+size_t expand_workspace_bytes(int B) {
+  return align_up((size_t)B * EXP_MAXC_BIG * 4, 256) * 2 + align_up((size_t)B * EXP_MAXC_BIG, 256) + align_up((size_t)B * 4, 256);
+}
+
 int launch_expand_rescore(const Index* ix, const Graph* g, const void* Q, const int64_t* seeds, int B, int S, int window,
                           float alpha_dense, float alpha_graph, int k, float* out_scores, int64_t* out_ids, int32_t* out_hops,
-                          float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand, int32_t* out_status, cudaStream_t st) {
+                          float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand, int32_t* out_status, int mode,
+                          int64_t own_lo, int64_t own_hi, void* ws, float* minmax, cudaStream_t st) {
   ExpandParams p;
   p.X = ix->X; p.Q = Q; p.row_mult = ix->row_mult;
   p.row_ptr = reinterpret_cast<const long long*>(g->row_ptr); p.col_idx = g->col_idx;
@@ -378,6 +424,16 @@ int launch_expand_rescore(const Index* ix, const Graph* g, const void* Q, const 
   p.alpha_dense = alpha_dense; p.alpha_graph = alpha_graph;
   p.out_scores = out_scores; p.out_ids = reinterpret_cast<long long*>(out_ids); p.out_hops = out_hops;
   p.out_gn = out_gn; p.out_dn = out_dn; p.out_cos = out_cos; p.out_ncand = out_ncand; p.out_status = out_status;
+  p.mode = mode; p.own_lo = own_lo; p.own_hi = own_hi;
+  p.ws_cand = nullptr; p.ws_cos = nullptr; p.ws_dist = nullptr; p.ws_ncand = nullptr; p.ws_minmax = minmax;
+  if (mode != 0) {
+    char* w = reinterpret_cast<char*>(ws);
+    const size_t a4 = align_up((size_t)B * EXP_MAXC_BIG * 4, 256);
+    p.ws_cand = reinterpret_cast<u32*>(w);
+    p.ws_cos = reinterpret_cast<float*>(w + a4);
+    p.ws_dist = reinterpret_cast<uint8_t*>(w + 2 * a4);
+    p.ws_ncand = reinterpret_cast<int*>(w + 2 * a4 + align_up((size_t)B * EXP_MAXC_BIG, 256));
+  }
   switch (ix->dtype) {
     case B200R_BF16: return launch_expand_t<__nv_bfloat16>(p, st);
     case B200R_F16: return launch_expand_t<__half>(p, st);

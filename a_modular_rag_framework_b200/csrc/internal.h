@@ -95,7 +95,9 @@ void profile_begin(cudaStream_t st);
 void profile_end(cudaStream_t st);
 int launch_expand_rescore(const Index* ix, const Graph* g, const void* Q, const int64_t* seeds, int B, int S, int window,
                           float alpha_dense, float alpha_graph, int k, float* out_scores, int64_t* out_ids, int32_t* out_hops,
-                          float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand, int32_t* out_status, cudaStream_t st);
+                          float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand, int32_t* out_status, int mode,
+                          int64_t own_lo, int64_t own_hi, void* ws, float* minmax, cudaStream_t st);
+size_t expand_workspace_bytes(int B);
 int encode_tmap_2d(CUtensorMap* tm, int dtype, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer);
 
 }  // namespace b200r

@@ -214,3 +214,40 @@ def expand_rescore(index: DenseIndex, graph: PassageGraph, Q: torch.Tensor, seed
         if bad:
             raise N.B200RError(N.EOVERFLOW, f"{bad} queries reached more than {N.load().b200r_expand_max_candidates()} graph nodes")
     return out
+
+
+class ExpandShardState:
+    """Device buffers of one rank's share of a sharded expand_rescore (see sharded.ShardedGraphStage)."""
+
+    def __init__(self, index: DenseIndex, B: int, k: int):
+        dev = index.device
+        lib = N.load()
+        self.ws = torch.empty(int(lib.b200r_expand_workspace_bytes(B)), dtype=torch.uint8, device=dev)
+        self.minmax = torch.empty((B, 2), dtype=torch.float32, device=dev)
+        self.out = {
+            "score": torch.empty((B, k), dtype=torch.float32, device=dev),
+            "id": torch.empty((B, k), dtype=torch.int64, device=dev),
+            "hop": torch.empty((B, k), dtype=torch.int32, device=dev),
+            "score_graph_norm": torch.empty((B, k), dtype=torch.float32, device=dev),
+            "score_dense_norm": torch.empty((B, k), dtype=torch.float32, device=dev),
+            "cos": torch.empty((B, k), dtype=torch.float32, device=dev),
+            "ncand": torch.empty((B,), dtype=torch.int32, device=dev),
+            "status": torch.empty((B,), dtype=torch.int32, device=dev),
+        }
+
+
+def expand_rescore_pass(index: DenseIndex, graph: PassageGraph, Q: torch.Tensor, seeds: torch.Tensor, window: int,
+                        alpha_dense: float, alpha_graph: float, k: int, st: ExpandShardState, which: int,
+                        own_lo: int, own_hi: int) -> None:
+    """One pass (1 or 2) of the owner-computes graph stage on this rank's row shard; seeds/ids are GLOBAL row ids."""
+    _require_cuda(Q, "Q")
+    _require_cuda(seeds, "seeds")
+    B, S = int(seeds.shape[0]), int(seeds.shape[1])
+    o = st.out
+    with torch.cuda.device(index.device):
+        N.check(N.load().b200r_expand_rescore_sharded(
+            index.handle, graph.handle, Q.data_ptr(), seeds.data_ptr(), B, S, int(window), float(alpha_dense), float(alpha_graph), int(k),
+            int(which), int(own_lo), int(own_hi), st.ws.data_ptr(), st.ws.numel(), st.minmax.data_ptr(),
+            o["score"].data_ptr(), o["id"].data_ptr(), o["hop"].data_ptr(), o["score_graph_norm"].data_ptr(),
+            o["score_dense_norm"].data_ptr(), o["cos"].data_ptr(), o["ncand"].data_ptr(), o["status"].data_ptr(),
+            _stream_ptr(index.device)))

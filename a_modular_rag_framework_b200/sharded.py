@@ -72,3 +72,76 @@ class ShardedDenseIndex:
         self.local.search(Q, k, path=path, out=(sc_view, ids_view))
         dist.all_gather_into_tensor(gather, pack, group=self.group)
         return self._merge(gather, self.world, B, k)
+
+
+INT64_MIN, INT64_MAX = -(1 << 63), (1 << 63) - 1
+
+
+def owned_range(N: int, world: int, rank: int) -> Tuple[int, int]:
+    """Global node ids whose candidates `rank` scores: its row block; the first rank also takes ids < 0 (none)
+    and the last rank everything >= its block start (graph nodes that are not corpus rows score 0.0, exactly as
+    on one GPU)."""
+    lo, hi = shard_rows(N, world, rank)
+    return (INT64_MIN if rank == 0 else lo), (INT64_MAX if rank == world - 1 else hi)
+
+
+class ShardedGraphStage:
+    """Graph 2-hop expansion + re-score over a ROW-SHARDED corpus: the CSR is replicated,
+    every rank runs the same (cheap, integer-only) frontier expansion, re-scores only the candidates whose rows it
+    owns, the per-query cosine range is all-reduced (min/max; the reference's per-channel min-max normalisation is a
+    global reduction, retrieval_backend.py:296-301), each rank ranks its own candidates with the global range and the
+    per-rank top-k lists are all-gathered and merged by (fused score desc, id asc)."""
+
+    def __init__(self, local_index, graph, N_total: int, group: Optional[dist.ProcessGroup] = None):
+        self.index, self.graph, self.N_total, self.group = local_index, graph, int(N_total), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._state = None
+
+    def run(self, Q: torch.Tensor, seeds: torch.Tensor, window: int, alpha_dense: float, alpha_graph: float, k: int):
+        from .index import ExpandShardState, expand_rescore_pass, merge_topk
+        B = int(Q.shape[0])
+        if self._state is None or self._state.out["score"].shape != (B, k):
+            self._state = ExpandShardState(self.index, B, k)
+        st = self._state
+        lo, hi = owned_range(self.N_total, self.world, self.rank)
+        expand_rescore_pass(self.index, self.graph, Q, seeds, window, alpha_dense, alpha_graph, k, st, 1, lo, hi)
+        if self.world > 1:
+            mn, mx = st.minmax[:, 0].contiguous(), st.minmax[:, 1].contiguous()
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+            st.minmax[:, 0], st.minmax[:, 1] = mn, mx
+        expand_rescore_pass(self.index, self.graph, Q, seeds, window, alpha_dense, alpha_graph, k, st, 2, lo, hi)
+        if self.world == 1:
+            return dict(st.out)
+        return combine_shard_outputs([self._gather(v) for v in (st.out[key] for key in _AUX_KEYS)], st.out["ncand"], st.out["status"], k)
+
+    def _gather(self, t: torch.Tensor) -> torch.Tensor:
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+
+_AUX_KEYS = ("score", "id", "hop", "score_graph_norm", "score_dense_norm", "cos")
+
+
+def combine_shard_outputs(gathered, ncand: torch.Tensor, status: torch.Tensor, k: int):
+    """gathered: the six [G, B, k] per-rank outputs (order of _AUX_KEYS).  Merge (score, id) on the device with
+    b200r_merge_topk, then pick each winner's other fields from the rank list it came from (plumbing)."""
+    from .index import merge_topk
+    g_score, g_id = gathered[0], gathered[1]
+    G, B, kk = g_score.shape
+    ms, mi = merge_topk(g_score.contiguous(), g_id.contiguous(), k)
+    flat_id = g_id.permute(1, 0, 2).reshape(B, G * kk)
+    # position of every merged id inside its query's gathered candidates (ids are unique per query; -1 pads)
+    match = (flat_id.unsqueeze(1) == mi.unsqueeze(2)) & (mi.unsqueeze(2) >= 0)
+    pos = match.float().argmax(dim=2)
+    valid = mi >= 0
+    out = {"score": ms, "id": mi}
+    fill = {"hop": -1, "score_graph_norm": 0.0, "score_dense_norm": 0.0, "cos": 0.0}
+    for key, g in zip(_AUX_KEYS[2:], gathered[2:]):
+        flat = g.permute(1, 0, 2).reshape(B, G * kk)
+        picked = torch.gather(flat, 1, pos)
+        out[key] = torch.where(valid, picked, torch.full_like(picked, fill[key]))
+    out["ncand"], out["status"] = ncand, status
+    return out

@@ -130,6 +130,20 @@ int b200r_expand_rescore(uint64_t index, uint64_t graph, const void* Q, const in
                          float* out_dense_norm, float* out_cos, int32_t* out_ncand, int32_t* out_status,
                          void* stream);
 
+/* Row-sharded corpora (one rank per GPU, CSR replicated, embeddings sharded by rows; SURVEY 8e "owner
+ * computes").  pass 1: BFS + re-score of the candidates whose global id lies in [own_lo, own_hi), parked in
+ * `workspace` (b200r_expand_workspace_bytes(B)), and minmax[B][2] = this rank's (min, max) cosine.  The caller
+ * all-reduces minmax (MIN on [:,0], MAX on [:,1]) across ranks, then pass 2 fuses with the global range and
+ * returns this rank's top-k among the candidates it owns; the per-rank lists are merged with
+ * b200r_merge_topk.  Seeds and reported ids are GLOBAL row ids (the index's id_base maps them to local rows). */
+size_t b200r_expand_workspace_bytes(int32_t B);
+int b200r_expand_rescore_sharded(uint64_t index, uint64_t graph, const void* Q, const int64_t* seeds, int32_t B,
+                                 int32_t S, int32_t window, float alpha_dense, float alpha_graph, int32_t k,
+                                 int32_t pass, int64_t own_lo, int64_t own_hi, void* workspace,
+                                 size_t workspace_bytes, float* minmax, float* out_scores, int64_t* out_ids,
+                                 int32_t* out_hops, float* out_graph_norm, float* out_dense_norm, float* out_cos,
+                                 int32_t* out_ncand, int32_t* out_status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

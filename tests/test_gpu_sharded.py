@@ -63,6 +63,22 @@ def _nccl_worker(rank, world, port, ret):
         S = O.score_matrix(Qn, Xn)
         for b in range(B):
             O.check_topk(s[b].cpu().numpy(), i[b].cpu().numpy(), S[b], k, rel_tol=1e-3)
+        # graph stage over the same row shards: CSR replicated, owner computes, min/max all-reduced
+        from a_modular_rag_framework_b200 import PassageGraph
+        from a_modular_rag_framework_b200.sharded import ShardedGraphStage
+        row_ptr, col_idx = O.csr_from_edges(N, rng.integers(0, N, 4 * N), rng.integers(0, N, 4 * N))
+        graph = PassageGraph(torch.from_numpy(row_ptr).to(dev), torch.from_numpy(col_idx).to(dev))
+        stage = ShardedGraphStage(sh.local, graph, N)
+        seeds = i[:, :8].contiguous()
+        out = stage.run(torch.from_numpy(Qn).to(dev).to(torch.bfloat16), seeds, 2, 0.4, 0.2, 10)
+        for b in range(0, B, 3):
+            top, dist_ = O.expand_rescore(Qn[b], Xn, row_ptr, col_idx, seeds[b].cpu().numpy(), 2, 0.4, 0.2, 10)
+            assert int(out["ncand"][b]) == len(dist_)
+            assert np.allclose(out["score"][b].cpu().numpy()[:len(top)], [t[1] for t in top], atol=2e-3)
+            got = out["id"][b].cpu().numpy()[:len(top)]
+            assert len(set(got.tolist()) & {t[0] for t in top}) >= len(top) - 1
+            for j, nid in enumerate(got):
+                assert int(out["hop"][b, j]) == dist_[int(nid)]
         ret[rank] = True
     finally:
         dist.destroy_process_group()
@@ -83,3 +99,48 @@ def test_two_rank_nccl_search():
         p.join(300)
         assert p.exitcode == 0
     assert ret.get(0) and ret.get(1)
+
+
+def test_graph_stage_virtual_shards_equal_single_gpu():
+    """Owner-computes graph stage: G virtual ranks on one device (pass 1 per shard, min/max combined like the
+    all-reduce, pass 2 per shard, merge) must reproduce the single-launch result."""
+    from a_modular_rag_framework_b200 import DenseIndex, PassageGraph, expand_rescore
+    from a_modular_rag_framework_b200.index import ExpandShardState, expand_rescore_pass
+    from a_modular_rag_framework_b200.sharded import combine_shard_outputs, owned_range, shard_rows, _AUX_KEYS
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(21)
+    V, E, D, B, S, k, G = 30000, 120000, 64, 16, 20, 10, 4
+    row_ptr, col_idx = O.csr_from_edges(V, rng.integers(0, V, E), rng.integers(0, V, E))
+    Xn = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((V - 500, D)).astype(np.float32)))  # last 500 nodes have no row
+    Qn = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((B, D)).astype(np.float32)))
+    seeds = torch.from_numpy(rng.integers(0, V, size=(B, S))).to(dev)
+    X = torch.from_numpy(Xn).to(dev).to(torch.bfloat16)
+    Q = torch.from_numpy(Qn).to(dev).to(torch.bfloat16)
+    graph = PassageGraph(torch.from_numpy(row_ptr).to(dev), torch.from_numpy(col_idx).to(dev))
+    ref = expand_rescore(DenseIndex(X), graph, Q, seeds, 2, 0.4, 0.2, k)
+    N = X.shape[0]
+    shards, states = [], []
+    for r in range(G):
+        lo, hi = shard_rows(N, G, r)
+        ix = DenseIndex(X[lo:hi], id_base=lo)
+        st = ExpandShardState(ix, B, k)
+        expand_rescore_pass(ix, graph, Q, seeds, 2, 0.4, 0.2, k, st, 1, *owned_range(N, G, r))
+        shards.append(ix); states.append(st)
+    mn = torch.stack([s.minmax[:, 0] for s in states]).min(0).values
+    mx = torch.stack([s.minmax[:, 1] for s in states]).max(0).values
+    for r, (ix, st) in enumerate(zip(shards, states)):
+        st.minmax[:, 0], st.minmax[:, 1] = mn, mx
+        expand_rescore_pass(ix, graph, Q, seeds, 2, 0.4, 0.2, k, st, 2, *owned_range(N, G, r))
+    gathered = [torch.stack([s.out[key] for s in states]) for key in _AUX_KEYS]
+    out = combine_shard_outputs(gathered, states[0].out["ncand"], states[0].out["status"], k)
+    assert torch.equal(out["ncand"], ref["ncand"])
+    assert torch.equal(out["id"], ref["id"])
+    assert torch.allclose(out["score"], ref["score"], atol=1e-6)
+    assert torch.equal(out["hop"], ref["hop"])
+    assert torch.allclose(out["score_dense_norm"], ref["score_dense_norm"], atol=1e-6)
+    assert torch.allclose(out["cos"], ref["cos"], atol=0)
+    # and against the oracle
+    for b in (0, 7, 15):
+        top, dist_ = O.expand_rescore(Qn[b], np.concatenate([Xn, np.zeros((500, D), np.float32)]), row_ptr, col_idx,
+                                      seeds[b].cpu().numpy(), 2, 0.4, 0.2, k)
+        assert np.allclose(out["score"][b].cpu().numpy()[:len(top)], [t[1] for t in top], atol=2e-3)
