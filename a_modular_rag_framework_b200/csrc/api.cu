@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <new>
 #include <cstdint>
@@ -38,6 +39,8 @@ void profile_end(cudaStream_t st) {
   else { cudaEventDestroy(g_prof_events.back()); g_prof_events.pop_back(); }
 }
 
+// B200R_CTA_GROUP=1 forces the single-CTA tile kernel (debug / A-B measurements)
+static int g_cta_group_max = [] { const char* e = getenv("B200R_CTA_GROUP"); return (e && e[0] == '1') ? 1 : 2; }();
 int select_group_size();
 int gemm_tile_rows();
 int gemm_tile_queries();
@@ -102,13 +105,15 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   pl->path = path; pl->B = B; pl->k = k;
   pl->cap_soft = list_cap_soft(k); pl->cap = list_cap(k);
   if (path == B200R_PATH_GEMM) {
-    const int BMq = gemm_tile_queries(), BNr = gemm_tile_rows();
+    // more than one 128-query tile: pair the CTAs (cta_group::2) so each loads half of every corpus tile
+    pl->cta_group = (B > gemm_tile_queries() && g_cta_group_max >= 2) ? 2 : 1;
+    const int BMq = gemm_tile_queries() * pl->cta_group, BNr = gemm_tile_rows();
     pl->num_q_tiles = (B + BMq - 1) / BMq;
     pl->num_row_tiles = (int)((ix->N + BNr - 1) / BNr);
     pl->Bpad = pl->num_q_tiles * BMq;
     // units = (query tile, chunk of row tiles).  More units per CTA = better balance, fewer = less list
     // traffic; pick the chunk count (near a target) that wastes the fewest CTA slots in the last wave.
-    const int grid_max = kPlanSMs;
+    const int grid_max = kPlanSMs / pl->cta_group;
     const int m = pl->num_q_tiles >= 16 ? 8 : (pl->num_q_tiles >= 4 ? 4 : (pl->num_q_tiles >= 2 ? 2 : 1));
     long long target = ((long long)grid_max * m + pl->num_q_tiles - 1) / pl->num_q_tiles;
     if (target < 1) target = 1;
@@ -267,6 +272,7 @@ int b200r_index_create(int device, const void* X, int64_t N, int32_t D, int32_t 
   }
   if ((dtype == B200R_BF16 || dtype == B200R_F16) && D % 8 == 0) {
     int rc = encode_tmap_2d(&ix->tmap_x, dtype, X, (uint64_t)D, (uint64_t)N, 64, (uint32_t)gemm_tile_rows());
+    if (!rc) rc = encode_tmap_2d(&ix->tmap_x_half, dtype, X, (uint64_t)D, (uint64_t)N, 64, (uint32_t)gemm_tile_rows() / 2);
     if (rc) { if (ix->row_mult) cudaFree(ix->row_mult); delete ix; return rc; }
     ix->has_tmap = true;
   }

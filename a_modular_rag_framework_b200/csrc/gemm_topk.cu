@@ -23,20 +23,28 @@
 #include "common.cuh"
 #include "internal.h"
 #include <math_constants.h>
+#include <cstring>
 
 namespace b200r {
 
-constexpr int BM = 128;
-constexpr int BN = 256;
+constexpr int BM = 128;     // queries per CTA (TMEM lanes)
+constexpr int BN = 256;     // corpus rows per tile (TMEM columns)
 constexpr int BK = 64;
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_BYTES = BN * BK * 2;   // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GEMM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr int GEMM_SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 * BN * 4 /*row mult*/ +
-                                4 * 256 * 4 /*hist*/ + 16 * 8 /*barriers*/ + 16;
+
+// CG = 1: one CTA per tile (M=128), it loads all 256 rows of B: 48 KB/stage, 4 stages.
+// CG = 2: a CTA pair per tile (cta_group::2, M=256 = 2 x 128 queries), each CTA loads its own A and HALF of
+//         B (128 rows): 32 KB/stage, 6 stages, half the shared-memory operand traffic per flop.
+template <int CG> struct Geo {
+  static constexpr int kBRows = BN / CG;
+  static constexpr int kBBytes = kBRows * BK * 2;
+  static constexpr int kStageBytes = A_BYTES + kBBytes;
+  static constexpr int kStages = CG == 1 ? 4 : 6;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * BN * 4 /*row mult*/ +
+                                    4 * 256 * 4 /*hist*/ + 24 * 8 /*barriers*/ + 16;
+};
 
 struct GemmTopkParams {
   int B, k, D;
@@ -79,6 +87,19 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+__device__ __forceinline__ u32 cluster_ctarank() { u32 r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(u64* bar, u32 cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+
 constexpr u64 kEvictNormal = 0x1000000000000000ull;
 constexpr u64 kEvictLast = 0x14F0000000000000ull;
 
@@ -87,6 +108,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(smem_u32(smem_dst)), "l"((u64)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+// cta_group::2 flavour: data lands in THIS CTA's shared memory, completion bytes are credited to the barrier at
+// the same offset in the pair's leader CTA (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* tmap, u64* bar, int c0, int c1, u64 hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"((u64)tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
@@ -107,6 +137,19 @@ __device__ __forceinline__ void umma_f16(u32 tmem_d, u64 desc_a, u64 desc_b, u32
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ void umma_f16_cg2(u32 tmem_d, u64 desc_a, u64 desc_b, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_cg2(u64* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
 }
 __device__ __forceinline__ void umma_commit(u64* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -140,15 +183,23 @@ __device__ __forceinline__ float mux_tree(const float (&s)[32], int j) {
 __device__ __forceinline__ float mux32(const float (&s)[32], int j) { return mux_tree<0, 32>(s, j); }
 
 // ------------------------------------------------------------------------------------------ kernel
+template <int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                  const GemmTopkParams p) {
+  constexpr int STAGES = Geo<CG>::kStages;
+  constexpr int B_BYTES = Geo<CG>::kBBytes;
+  constexpr int STAGE_BYTES = Geo<CG>::kStageBytes;
+  const u32 cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int unit0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // first unit of this CTA (pair)
+  const int unit_stride = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const u32 raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
   uint8_t* smem_a = smem;                               // STAGES x 16 KB
-  uint8_t* smem_b = smem + STAGES * A_BYTES;            // STAGES x 32 KB
+  uint8_t* smem_b = smem + STAGES * A_BYTES;            // STAGES x (32 | 16) KB
   float* smem_mult = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // [2][BN]
   u32* smem_hist = reinterpret_cast<u32*>(smem_mult + 2 * BN);               // [4][256]
   u64* bars = reinterpret_cast<u64*>(smem_hist + 4 * 256);
@@ -164,16 +215,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_q);
     prefetch_tmap(&tmap_x);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+    // full: the leader's own arrive(+expect_tx) and, in a pair, the peer producer's remote arrive
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
+    // tmem_empty: one arrive per epilogue warp of every CTA of the group (the peer's arrive remotely)
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4 * CG); }
     fence_barrier_init();
   }
+  if constexpr (CG == 2) cluster_sync_all();      // both CTAs' barriers exist before anything can reach them
   if (warp_idx == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const u32 tmem_base = *tmem_ptr_smem;
 
@@ -183,17 +242,26 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int stage = 0; u32 phase = 0;
-      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-        const int q_tile = u % p.num_q_tiles;
+      for (int u = unit0; u < p.num_units; u += unit_stride) {
+        const int q_tile = (u % p.num_q_tiles) * CG + (int)cta_rank;    // this CTA's 128 queries
         const int chunk = u / p.num_q_tiles;
         const int t0 = p.tile_begin + chunk * p.tiles_per_chunk;
         const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-            tma_load_2d(smem_a + stage * A_BYTES, &tmap_q, &full_bar[stage], kb * BK, q_tile * BM, kEvictLast);
-            tma_load_2d(smem_b + stage * B_BYTES, &tmap_x, &full_bar[stage], kb * BK, t * BN, kEvictNormal);
+            if constexpr (CG == 1) {
+              mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+              tma_load_2d(smem_a + stage * A_BYTES, &tmap_q, &full_bar[stage], kb * BK, q_tile * BM, kEvictLast);
+              tma_load_2d(smem_b + stage * B_BYTES, &tmap_x, &full_bar[stage], kb * BK, t * BN, kEvictNormal);
+            } else {
+              // both CTAs' bytes are credited to the leader's barrier; this CTA loads its A and its half of B
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+              tma_load_2d_cg2(smem_a + stage * A_BYTES, &tmap_q, &full_bar[stage], kb * BK, q_tile * BM, kEvictLast);
+              tma_load_2d_cg2(smem_b + stage * B_BYTES, &tmap_x, &full_bar[stage], kb * BK,
+                              t * BN + (int)cta_rank * (BN / 2), kEvictNormal);
+              if (!leader) mbar_arrive_remote(&full_bar[stage], 0);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -201,10 +269,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
   } else if (warp_idx == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int stage = 0; u32 phase = 0;
       u32 tile_iter = 0;
-      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      for (int u = unit0; u < p.num_units; u += unit_stride) {
         const int chunk = u / p.num_q_tiles;
         const int t0 = p.tile_begin + chunk * p.tiles_per_chunk;
         const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
@@ -221,10 +289,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
               // advance 16 elements = 32 bytes inside the 128-byte swizzle span: +2 in the >>4 address field
-              umma_f16(tmem_d, desc_a + (u64)(kk * 2), desc_b + (u64)(kk * 2), p.idesc, (kb | kk) != 0 ? 1u : 0u);
+              if constexpr (CG == 1) umma_f16(tmem_d, desc_a + (u64)(kk * 2), desc_b + (u64)(kk * 2), p.idesc, (kb | kk) != 0 ? 1u : 0u);
+              else umma_f16_cg2(tmem_d, desc_a + (u64)(kk * 2), desc_b + (u64)(kk * 2), p.idesc, (kb | kk) != 0 ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
-            if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+            if constexpr (CG == 1) {
+              umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
+              if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+            } else {
+              umma_commit_cg2(&empty_bar[stage]);             // ... in both CTAs of the pair
+              if (kb == num_kb - 1) umma_commit_cg2(&tmem_full_bar[acc]);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -237,8 +311,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int epi_tid = (warp_idx - 2) * 32 + lane;  // 0..127
     u32* hist = smem_hist + (warp_idx - 2) * 256;
     u32 tile_iter = 0;
-    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-      const int q_tile = u % p.num_q_tiles;
+    for (int u = unit0; u < p.num_units; u += unit_stride) {
+      const int q_tile = (u % p.num_q_tiles) * CG + (int)cta_rank;
       const int chunk = u / p.num_q_tiles;
       const int t0 = p.tile_begin + chunk * p.tiles_per_chunk;
       const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
@@ -277,7 +351,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             // the whole accumulator is in registers: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) {
+              if (CG == 1 || leader) mbar_arrive(&tmem_empty_bar[acc]);
+              else mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+            }
           }
           float s[32];
           float cmax = -CUDART_INF_F;          // fmaxf drops NaN (rows beyond N), so they never pass
@@ -326,11 +403,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // nobody leaves while the peer can still reach its smem
   if (warp_idx == 1) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -340,10 +418,11 @@ int encode_query_tmap(const Index* ix, const void* Q, int B, CUtensorMap* tmap_q
   return encode_tmap_2d(tmap_q, ix->dtype, Q, (uint64_t)ix->D, (uint64_t)B, BK, BM);
 }
 
-int launch_gemm_topk(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& pl, const GemmPhase& ph, void* ws, cudaStream_t st) {
+template <int CG>
+static int launch_gemm_cg(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& pl, const GemmPhase& ph, void* ws, cudaStream_t st) {
   GemmTopkParams p;
   p.B = pl.B; p.k = pl.k; p.D = ix->D; p.N = ix->N;
-  p.num_q_tiles = pl.num_q_tiles; p.num_row_tiles = pl.num_row_tiles;
+  p.num_q_tiles = pl.num_q_tiles; p.num_row_tiles = pl.num_row_tiles;     // num_q_tiles counts tiles of CG*128 queries
   p.tile_begin = ph.tile_begin; p.tile_end = ph.tile_end; p.tiles_per_chunk = ph.tiles_per_chunk;
   p.num_units = ph.num_chunks * pl.num_q_tiles;
   p.cap = pl.cap; p.cap_soft = pl.cap_soft; p.Bpad = pl.Bpad;
@@ -352,15 +431,29 @@ int launch_gemm_topk(const Index* ix, const CUtensorMap* tmap_q, const SearchPla
   p.counts = reinterpret_cast<int*>((char*)ws + pl.off_counts);
   p.gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
   // instruction descriptor: D=f32 (1<<4), A/B format (bf16=1, f16=0) at [7,10)/[10,13), K-major A and B,
-  // N>>3 at [17,23), M>>4 at [24,29)
+  // N>>3 at [17,23), M>>4 at [24,29) with M = 128 per CTA of the group
   const u32 fmt = (ix->dtype == B200R_BF16) ? 1u : 0u;
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((u32)(BN >> 3) << 17) | ((u32)(BM >> 4) << 24);
-  B200R_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  const int grid = p.num_units < kNumSMs ? p.num_units : kNumSMs;
-  gemm_topk_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(*tmap_q, ix->tmap_x, p);
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((u32)(BN >> 3) << 17) | ((u32)((BM * CG) >> 4) << 24);
+  B200R_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<CG>::kSmemBytes));
+  const int groups = p.num_units < kNumSMs / CG ? p.num_units : kNumSMs / CG;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(groups * CG);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Geo<CG>::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  B200R_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<CG>, *tmap_q, CG == 2 ? ix->tmap_x_half : ix->tmap_x, p));
   count_launch();
   B200R_CUDA_CHECK(cudaGetLastError());
   return B200R_OK;
+}
+
+int launch_gemm_topk(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& pl, const GemmPhase& ph, void* ws, cudaStream_t st) {
+  return pl.cta_group == 2 ? launch_gemm_cg<2>(ix, tmap_q, pl, ph, ws, st) : launch_gemm_cg<1>(ix, tmap_q, pl, ph, ws, st);
 }
 
 int gemm_tile_rows() { return BN; }

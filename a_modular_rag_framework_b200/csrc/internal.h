@@ -33,7 +33,8 @@ struct Index {
   int64_t id_base;
   float* row_mult;      // [N] or nullptr: cos -> 1/|x_n| (0 when |x_n| == 0); ip+i8 -> row_scale; ip -> nullptr
   bool has_tmap;        // X tensor map valid (bf16/f16, D % 8 == 0)
-  CUtensorMap tmap_x;
+  CUtensorMap tmap_x;        // box 64 x 256 rows (one CTA per tile)
+  CUtensorMap tmap_x_half;   // box 64 x 128 rows (CTA pair, each CTA loads half of the tile's rows)
   // staging for b200r_search_host
   void* h_q_dev; size_t q_dev_bytes;
   float* h_s_dev; int64_t* h_i_dev; size_t out_dev_elems;
@@ -68,7 +69,8 @@ struct SearchPlan {
   int num_segments;     // lists per query
   // gemm: row tiles are processed in phases [tile_begin, tile_end) of geometrically growing size; after each
   // phase the exact k-th best so far becomes every query's filter threshold for the next one
-  int num_q_tiles, num_row_tiles, num_chunks;
+  int cta_group;         // 1 or 2 (CTA pair, cta_group::2)
+  int num_q_tiles, num_row_tiles, num_chunks;   // num_q_tiles counts tiles of cta_group*128 queries
   int num_phases;
   GemmPhase phases[kMaxPhases];
   // scan

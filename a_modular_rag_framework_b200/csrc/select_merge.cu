@@ -13,9 +13,10 @@
 
 namespace b200r {
 
-constexpr int SEL_THREADS = 512;
-constexpr int SEL_WARPS = SEL_THREADS / 32;
-constexpr int SEL_STAGE_MAX = 6144;   // keys staged in shared memory (48 KB) -> 4 CTAs/SM
+constexpr int SEL_MAX_THREADS = 1024;  // block size is chosen at launch: the kernel is latency-bound, so many small CTAs
+                                       // when there are thousands of queries, one wide CTA per query when there are few
+constexpr int SEL_STAGE_MAX = 6144;   // keys staged in shared memory for the group-wise first level (48 KB)
+constexpr int SEL_STAGE_LISTS = 2560; // ... and for the per-phase / final select over pruned lists (20 KB -> 11 CTAs/SM)
 constexpr int SEL_GROUP = 64;         // segments per CTA in the first level of a two-level select
 
 enum SelectMode { kSelOutput = 0, kSelThreshold = 1, kSelPartial = 2 };
@@ -40,6 +41,7 @@ template <typename F>
 __device__ __forceinline__ void for_each_key(const SelectParams& p, int q, int s0, int s1, bool staged, const u64* stage,
                                              int total, F f) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int SEL_THREADS = blockDim.x, SEL_WARPS = blockDim.x >> 5;
   if (staged) {
     for (int base = warp * 32; base < total; base += SEL_THREADS) {
       const int i = base + lane;
@@ -68,7 +70,8 @@ __device__ __forceinline__ void hist_add(u32* hist, bool active, u32 digit) {
   if (active && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[d], (u32)__popc(peers));
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) select_lists_kernel(const SelectParams p) {
+__global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const SelectParams p) {
+  const int SEL_THREADS = blockDim.x, SEL_WARPS = blockDim.x >> 5;
   extern __shared__ uint8_t smem_raw[];
   u64* stage = reinterpret_cast<u64*>(smem_raw);            // [stage_cap]
   u64* sk = stage + p.stage_cap;                            // [kp2] (output mode)
@@ -155,6 +158,27 @@ __global__ void __launch_bounds__(SEL_THREADS) select_lists_kernel(const SelectP
 
   if (p.mode == kSelThreshold) {
     if (tid == 0) atomicMax(p.gthr + q, (u32)(kth >> 32));
+    // prune: keys below the (truncated) k-th key can never reach the final top-k, so drop them from the lists.
+    // This keeps every later select (and the final one) at ~k + one phase's survivors per query.
+    u64* wl = const_cast<u64*>(p.lists);
+    int* wc = const_cast<int*>(p.counts);
+    for (int s = s0 + warp; s < s1; s += SEL_WARPS) {
+      const size_t slot = (size_t)s * p.Bpad + q;
+      const int c = wc[slot];
+      if (c == 0) continue;
+      u64* lp = wl + slot * (size_t)p.cap;
+      int out = 0;
+      for (int base = 0; base < c; base += 32) {
+        const int i = base + lane;
+        const u64 key = (i < c) ? lp[i] : 0ull;
+        const bool keep = (i < c) && key >= kth;
+        const u32 m = __ballot_sync(kFullMask, keep);
+        __syncwarp();
+        if (keep) lp[out + __popc(m & ((1u << lane) - 1u))] = key;
+        out += __popc(m);
+      }
+      if (lane == 0) wc[slot] = out;
+    }
     return;
   }
 
@@ -195,10 +219,18 @@ static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 static int run_select(SelectParams& p, int grid_y, cudaStream_t st) {
   const long long all = (long long)(p.mode == kSelPartial ? p.seg_per_cta : p.S) * p.cap;
-  p.stage_cap = (int)(all < SEL_STAGE_MAX ? all : SEL_STAGE_MAX);
+  int limit = SEL_STAGE_MAX;
+  if (p.mode != kSelPartial) {   // pruned lists hold ~k + one phase's survivors
+    limit = 3 * p.k + 2048;
+    if (limit < SEL_STAGE_LISTS) limit = SEL_STAGE_LISTS;
+    if (limit > 24576) limit = 24576;
+  }
+  p.stage_cap = (int)(all < limit ? all : limit);
+  const long long ctas = (long long)p.B * grid_y;
+  const int threads = ctas >= 2048 ? 128 : (ctas >= 512 ? 256 : (ctas >= 128 ? 512 : 1024));
   const size_t smem = (size_t)p.stage_cap * 8 + (p.mode == kSelOutput ? (size_t)p.kp2 * 8 : 0);
   B200R_CUDA_CHECK(cudaFuncSetAttribute(select_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  select_lists_kernel<<<dim3(p.B, grid_y), SEL_THREADS, smem, st>>>(p);
+  select_lists_kernel<<<dim3(p.B, grid_y), threads, smem, st>>>(p);
   count_launch();
   B200R_CUDA_CHECK(cudaGetLastError());
   return B200R_OK;
