@@ -237,11 +237,11 @@ def main():
     # ---- device-resident throughput ------------------------------------------------------------------
     for i in range(a.warmup):
         index.search(Qd[i], a.k, path=a.path)
-    barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank)        # NVML init takes a variable time per process: do it BEFORE the barrier
     _native.profile_enable(True)
     launches0 = _native.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     sampler.start()
     ev0.record()
     for i in range(a.steps):
