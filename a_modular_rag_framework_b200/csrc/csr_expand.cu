@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "internal.h"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace b200r {
 
@@ -26,7 +27,6 @@ constexpr int EXP_WARPS = EXP_THREADS / 32;
 constexpr int EXP_MAXC_BIG = 8192;
 constexpr int EXP_HUB_DEG = 32;       // adjacency lists longer than this are expanded by a whole warp
 constexpr int EXP_MAX_HUBS = 256;
-constexpr int EXP_ROWS = 4;           // candidate rows gathered together by one warp
 constexpr u32 EXP_EMPTY = 0xffffffffu;
 constexpr int kStatusRetry = 1;       // internal: overflowed the small instantiation, big one will redo it
 
@@ -69,7 +69,8 @@ __device__ __forceinline__ bool hash_insert(u32* table, u32 v) {
   }
 }
 
-template <typename T, int MAXC, bool RETRY_PASS>
+// EXP_ROWS: candidate rows gathered together by one warp (all their 128-bit loads in flight at once)
+template <typename T, int MAXC, bool RETRY_PASS, int EXP_ROWS>
 __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const ExpandParams p) {
   typedef typename QueryType<T>::type QT;
   constexpr int VEC = ElemTraits<T>::kVec;
@@ -385,25 +386,33 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
 
 int32_t expand_max_candidates() { return EXP_MAXC_BIG; }
 
-template <typename T>
-static int launch_expand_t(const ExpandParams& p, cudaStream_t st) {
+template <typename T, int ROWS>
+static int launch_expand_r(const ExpandParams& p, cudaStream_t st) {
   constexpr int SMALL = 4096;
   auto smem_of = [&](int maxc) { return (size_t)maxc * 8 + (size_t)maxc * 4 * 2 + maxc + (size_t)((p.D + 1) & ~1) * 4 + (size_t)p.kp2 * 8; };
   if (smem_of(EXP_MAXC_BIG) > 220 * 1024) { set_error("expand_rescore: D=%d / k=%d too large for shared memory", p.D, p.k); return B200R_EINVAL; }
   if (p.mode != 2) {
-    B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(SMALL)));
-    expand_rescore_kernel<T, SMALL, false><<<p.B, EXP_THREADS, smem_of(SMALL), st>>>(p);
+    B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, SMALL, false, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(SMALL)));
+    expand_rescore_kernel<T, SMALL, false, ROWS><<<p.B, EXP_THREADS, smem_of(SMALL), st>>>(p);
     count_launch();
-    B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, EXP_MAXC_BIG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(EXP_MAXC_BIG)));
-    expand_rescore_kernel<T, EXP_MAXC_BIG, true><<<p.B, EXP_THREADS, smem_of(EXP_MAXC_BIG), st>>>(p);
+    B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, EXP_MAXC_BIG, true, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(EXP_MAXC_BIG)));
+    expand_rescore_kernel<T, EXP_MAXC_BIG, true, ROWS><<<p.B, EXP_THREADS, smem_of(EXP_MAXC_BIG), st>>>(p);
     count_launch();
   } else {
-    B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, EXP_MAXC_BIG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(EXP_MAXC_BIG)));
-    expand_rescore_kernel<T, EXP_MAXC_BIG, false><<<p.B, EXP_THREADS, smem_of(EXP_MAXC_BIG), st>>>(p);
+    B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, EXP_MAXC_BIG, false, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(EXP_MAXC_BIG)));
+    expand_rescore_kernel<T, EXP_MAXC_BIG, false, ROWS><<<p.B, EXP_THREADS, smem_of(EXP_MAXC_BIG), st>>>(p);
     count_launch();
   }
   B200R_CUDA_CHECK(cudaGetLastError());
   return B200R_OK;
+}
+
+template <typename T>
+static int launch_expand_t(const ExpandParams& p, cudaStream_t st) {
+  static const int rows = [] { const char* e = getenv("B200R_EXP_ROWS"); return e ? atoi(e) : 4; }();
+  if (rows == 8) return launch_expand_r<T, 8>(p, st);
+  if (rows == 2) return launch_expand_r<T, 2>(p, st);
+  return launch_expand_r<T, 4>(p, st);
 }
 
 size_t expand_workspace_bytes(int B) {

@@ -37,6 +37,20 @@ def _cuda_merge_packed(packed: torch.Tensor, G: int, B: int, k: int) -> Tuple[to
     return scores, ids
 
 
+class PendingResult:
+    """Result of ShardedDenseIndex.search(..., overlap=True): the exchange + merge run on a side stream.
+    get() makes the caller's current stream wait for them and returns (scores, ids)."""
+
+    def __init__(self, scores, ids, event):
+        self._scores, self._ids, self._event = scores, ids, event
+
+    def get(self):
+        if self._event is not None:
+            torch.cuda.current_stream(self._scores.device).wait_event(self._event)
+            self._event = None
+        return self._scores, self._ids
+
+
 class ShardedDenseIndex:
     """`local` searches this rank's rows and reports GLOBAL ids (DenseIndex(X_shard, id_base=lo))."""
 
@@ -47,31 +61,63 @@ class ShardedDenseIndex:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._merge = merge_packed or _cuda_merge_packed
-        self._pack: Optional[torch.Tensor] = None
-        self._gather: Optional[torch.Tensor] = None
+        self._bufs = {}          # (B, k, slot) -> (pack, gather)
+        self._slot = 0
+        self._comm_stream = None
 
-    def _buffers(self, B: int, k: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    def _buffers(self, B: int, k: int, device, slot: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
         n = B * k
         if n % 2:
             raise ValueError("B*k must be even for the packed exchange")
         rec = 12 * n
-        if self._pack is None or self._pack.numel() != rec or self._pack.device != device:
-            self._pack = torch.empty(rec, dtype=torch.uint8, device=device)
-            self._gather = torch.empty(rec * self.world, dtype=torch.uint8, device=device)
-        return self._pack, self._gather
+        key = (B, k, slot, str(device))
+        if key not in self._bufs:
+            self._bufs[key] = (torch.empty(rec, dtype=torch.uint8, device=device),
+                               torch.empty(rec * self.world, dtype=torch.uint8, device=device))
+        return self._bufs[key]
 
-    def search(self, Q: torch.Tensor, k: int, path: str = "auto") -> Tuple[torch.Tensor, torch.Tensor]:
-        """Every rank passes the SAME Q [B, D]; every rank returns the same global (scores, ids) [B, k]."""
+    def search(self, Q: torch.Tensor, k: int, path: str = "auto", overlap: bool = False):
+        """Every rank passes the SAME Q [B, D]; every rank gets the same global (scores, ids) [B, k].
+
+        overlap=True (throughput mode, CUDA only): the all-gather and the merge of this batch are queued on a side
+        stream so the next batch's local search starts right away; returns a PendingResult."""
         if self.world == 1:
-            return self.local.search(Q, k, path=path)
+            res = self.local.search(Q, k, path=path)
+            return PendingResult(res[0], res[1], None) if overlap else res
         B = int(Q.shape[0])
-        pack, gather = self._buffers(B, k, Q.device)
         n = B * k
+        if not overlap:
+            pack, gather = self._buffers(B, k, Q.device)
+            ids_view = pack[: 8 * n].view(torch.int64).view(B, k)
+            sc_view = pack[8 * n:].view(torch.float32).view(B, k)
+            self.local.search(Q, k, path=path, out=(sc_view, ids_view))
+            dist.all_gather_into_tensor(gather, pack, group=self.group)
+            return self._merge(gather, self.world, B, k)
+        # double-buffered exchange on a side stream
+        self._slot ^= 1
+        pack, gather = self._buffers(B, k, Q.device, self._slot)
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=Q.device)
+        cur = torch.cuda.current_stream(Q.device)
+        # the buffers of this slot were last used two batches ago on the side stream
         ids_view = pack[: 8 * n].view(torch.int64).view(B, k)
         sc_view = pack[8 * n:].view(torch.float32).view(B, k)
+        prev = getattr(self, "_slot_events", {}).get(self._slot)
+        if prev is not None:
+            cur.wait_event(prev)          # do not overwrite `pack` before its previous all-gather has read it
         self.local.search(Q, k, path=path, out=(sc_view, ids_view))
-        dist.all_gather_into_tensor(gather, pack, group=self.group)
-        return self._merge(gather, self.world, B, k)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(ready)
+            dist.all_gather_into_tensor(gather, pack, group=self.group)
+            scores, ids = self._merge(gather, self.world, B, k)
+            done = torch.cuda.Event()
+            done.record(self._comm_stream)
+        if not hasattr(self, "_slot_events"):
+            self._slot_events = {}
+        self._slot_events[self._slot] = done
+        return PendingResult(scores, ids, done)
 
 
 INT64_MIN, INT64_MAX = -(1 << 63), (1 << 63) - 1

@@ -160,6 +160,7 @@ CONFIGS = {
     "cfg3_12p5Mx384_f16_k1000_B16": lambda: run_search("cfg3_12p5Mx384_f16_k1000_B16", 12_500_000, 384, 16, 1000, torch.float16, "gemm", steps=10),
     "cfg3_12p5Mx384_f16_k1000_B1": lambda: run_search("cfg3_12p5Mx384_f16_k1000_B1", 12_500_000, 384, 1, 1000, torch.float16, "scan", steps=10),
     "cfg4_graph_5M_50M": lambda: run_graph("cfg4_graph_5M_50M", 5_000_000, 25_000_000, 768, 1024, 20, 10),
+    "cfg4_graph_5M_50M_B4096": lambda: run_graph("cfg4_graph_5M_50M_B4096", 5_000_000, 25_000_000, 768, 4096, 20, 10),
 }
 
 if __name__ == "__main__":

@@ -63,6 +63,12 @@ def _nccl_worker(rank, world, port, ret):
         S = O.score_matrix(Qn, Xn)
         for b in range(B):
             O.check_topk(s[b].cpu().numpy(), i[b].cpu().numpy(), S[b], k, rel_tol=1e-3)
+        # overlapped exchange (side stream, double-buffered): several batches in flight, identical results
+        Qb = torch.from_numpy(Qn).to(dev).to(torch.bfloat16)
+        pend = [sh.search(Qb, k, overlap=True) for _ in range(5)]
+        for pr in pend:
+            s2, i2 = pr.get()
+            assert torch.equal(i2, i) and torch.equal(s2, s)
         # graph stage over the same row shards: CSR replicated, owner computes, min/max all-reduced
         from a_modular_rag_framework_b200 import PassageGraph
         from a_modular_rag_framework_b200.sharded import ShardedGraphStage
