@@ -38,7 +38,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # B200R_LIB points at an alternative build of the same ABI (A/B measurements of kernel variants)
+    return os.environ.get("B200R_LIB") or _build.LIB_PATH
 
 
 def load() -> ctypes.CDLL:

@@ -42,7 +42,7 @@ template <int CG> struct Geo {
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = A_BYTES + kBBytes;
   static constexpr int kStages = CG == 1 ? 4 : 6;
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * BN * 4 /*row mult*/ +
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * BN * 4 /*row mult*/ + 2 * 8 * 4 /*chunk max mult*/ +
                                     4 * 256 * 4 /*hist*/ + 24 * 8 /*barriers*/ + 16;
 };
 
@@ -201,7 +201,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint8_t* smem_a = smem;                               // STAGES x 16 KB
   uint8_t* smem_b = smem + STAGES * A_BYTES;            // STAGES x (32 | 16) KB
   float* smem_mult = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // [2][BN]
-  u32* smem_hist = reinterpret_cast<u32*>(smem_mult + 2 * BN);               // [4][256]
+  float* smem_mmax = smem_mult + 2 * BN;                                     // [2][8] per-32-row-chunk max multiplier
+  u32* smem_hist = reinterpret_cast<u32*>(smem_mmax + 2 * 8);                // [4][256]
   u64* bars = reinterpret_cast<u64*>(smem_hist + 4 * 256);
   u64* full_bar = bars;                  // [STAGES]
   u64* empty_bar = bars + STAGES;        // [STAGES]
@@ -328,7 +329,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int t = t0; t < t1; ++t, ++tile_iter) {
         const u32 acc = tile_iter & 1;
         float* mult = smem_mult + (tile_iter & 1) * BN;
-        // per-row multipliers of this tile (1/|x| for cosine); NaN marks rows beyond N so they never pass
+        float* mmax = smem_mmax + (tile_iter & 1) * 8;
+        // per-row multipliers of this tile (1/|x| for cosine); NaN marks rows beyond N so they never pass.
+        // Also the max multiplier of each 32-row chunk (slightly inflated): acc*mult <= max(0, max_acc * mmax), so a
+        // chunk whose raw accumulator max cannot reach the threshold is rejected without touching the multipliers.
         {
           const long long r = (long long)t * BN + epi_tid * 2;
           float m0 = __int_as_float(0x7fc00000), m1 = __int_as_float(0x7fc00000);
@@ -336,6 +340,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           if (r + 1 < p.N) m1 = p.row_mult ? __ldg(p.row_mult + r + 1) : 1.0f;
           mult[epi_tid * 2] = m0;
           mult[epi_tid * 2 + 1] = m1;
+          float mm = fmaxf(fmaxf(m0, m1), 0.0f);      // fmaxf drops the NaNs
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) mm = fmaxf(mm, __shfl_xor_sync(kFullMask, mm, o));   // 16-lane halves = one chunk
+          if ((lane & 15) == 0) mmax[epi_tid >> 4] = mm * 1.000001f;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         mbar_wait(&tmem_full_bar[acc], (tile_iter >> 1) & 1);
@@ -356,20 +364,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               else mbar_arrive_remote(&tmem_empty_bar[acc], 0);
             }
           }
-          float s[32];
-          float cmax = -CUDART_INF_F;          // fmaxf drops NaN (rows beyond N), so they never pass
+          float rmax = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 m4 = *reinterpret_cast<const float4*>(mult + c * 32 + j);
-            s[j] = __uint_as_float(v[j]) * m4.x;
-            s[j + 1] = __uint_as_float(v[j + 1]) * m4.y;
-            s[j + 2] = __uint_as_float(v[j + 2]) * m4.z;
-            s[j + 3] = __uint_as_float(v[j + 3]) * m4.w;
-            cmax = fmaxf(cmax, fmaxf(fmaxf(s[j], s[j + 1]), fmaxf(s[j + 2], s[j + 3])));
-          }
-          if (__any_sync(kFullMask, cmax >= thr)) {
-            // rare path: survivor bitmask per lane (straight-line), then each lane walks its own bits and
-            // picks the value with a 5-level select tree -- no dependent vote/branch chain
+          for (int j = 2; j < 32; j += 2) rmax = fmaxf(rmax, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+          // conservative test on the raw accumulators (see mmax above); a non-positive threshold always enters
+          const bool maybe = !(rmax * mmax[c] < thr) || !(thr > 0.0f);
+          if (__any_sync(kFullMask, maybe)) {
+            // rare path: exact scores, survivor bitmask per lane (straight-line), then each lane walks its own bits
+            // and picks the value with a 5-level select tree -- no dependent vote/branch chain
+            float s[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 m4 = *reinterpret_cast<const float4*>(mult + c * 32 + j);
+              s[j] = __uint_as_float(v[j]) * m4.x;
+              s[j + 1] = __uint_as_float(v[j + 1]) * m4.y;
+              s[j + 2] = __uint_as_float(v[j + 2]) * m4.z;
+              s[j + 3] = __uint_as_float(v[j + 3]) * m4.w;
+            }
             u32 mask = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) mask |= (s[j] >= thr) ? (1u << j) : 0u;

@@ -87,6 +87,10 @@ def test_golden_fixtures(golden_dir, name, dtype, paths):
     (50, 64, 2, 100, "scan", torch.bfloat16, "cos"),
     (1, 8, 1, 1, "scan", torch.bfloat16, "cos"),
     (257, 8, 5, 3, "gemm", torch.bfloat16, "cos"),
+    (30000, 64, 5, 2048, "gemm", torch.bfloat16, "cos"),     # B200R_MAX_K
+    (30000, 64, 2, 2048, "scan", torch.bfloat16, "cos"),
+    (40000, 128, 700, 64, "gemm", torch.float16, "cos"),     # CTA pairs, partial last query tile
+    (1000, 64, 130, 5, "gemm", torch.bfloat16, "ip"),        # pair whose second CTA has 2 valid queries
 ])
 def test_random_vs_oracle(N, D, B, k, path, dtype, metric):
     rng = np.random.default_rng(N * 31 + D + B)
