@@ -20,7 +20,7 @@ EOVERFLOW = -4
 EXPORTS = [
     "b200r_version", "b200r_last_error", "b200r_launch_count",
     "b200r_index_create", "b200r_index_destroy", "b200r_index_info",
-    "b200r_search_workspace_bytes", "b200r_search", "b200r_search_host",
+    "b200r_search_workspace_bytes", "b200r_search", "b200r_search_host", "b200r_search_scatter",
     "b200r_merge_topk", "b200r_merge_topk_packed", "b200r_profile_enable", "b200r_profile_read",
     "b200r_graph_create", "b200r_graph_destroy",
     "b200r_expand_max_candidates", "b200r_expand_rescore", "b200r_expand_workspace_bytes", "b200r_expand_rescore_sharded",
@@ -63,6 +63,7 @@ def load() -> ctypes.CDLL:
     lib.b200r_search_workspace_bytes.restype = c_size_t
     lib.b200r_search.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.b200r_search_host.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.b200r_search_scatter.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, POINTER(c_uint64), c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.b200r_merge_topk.argtypes = [c_int, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
     lib.b200r_merge_topk_packed.argtypes = [c_int, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
     lib.b200r_profile_enable.argtypes = [c_int]

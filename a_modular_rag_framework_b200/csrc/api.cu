@@ -68,8 +68,11 @@ int encode_tmap_2d(CUtensorMap* tm, int dtype, const void* base, uint64_t inner,
   const cuuint32_t box[2] = {box_inner, box_outer};
   const cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = (dtype == B200R_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  static const int promo = [] { const char* e = getenv("B200R_L2PROMO"); return e ? atoi(e) : 3; }();   // experiment knob
+  const CUtensorMapL2promotion l2p = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                     : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUresult r = fn(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_SWIZZLE_128B, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (base=%p inner=%llu outer=%llu)", (int)r, base,
               (unsigned long long)inner, (unsigned long long)outer);
@@ -191,11 +194,11 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
 static int query_dtype(const Index* ix) { return ix->dtype == B200R_I8 ? B200R_F32 : ix->dtype; }
 
 static int do_search(Index* ix, const void* Q, int B, int k, int path, float* out_scores, int64_t* out_ids, void* ws,
-                     size_t ws_bytes, cudaStream_t st) {
+                     size_t ws_bytes, cudaStream_t st, const PeerScatter* peers = nullptr, cudaEvent_t wait_before_output = nullptr) {
   SearchPlan pl;
   int rc = make_plan(ix, B, k, path, &pl);
   if (rc) return rc;
-  if (!Q || !out_scores || !out_ids) { set_error("null Q / output pointer"); return B200R_EINVAL; }
+  if (!Q || (!peers && (!out_scores || !out_ids))) { set_error("null Q / output pointer"); return B200R_EINVAL; }
   if (!ws || ws_bytes < pl.off_end) {
     set_error("workspace too small: need %zu bytes, got %zu", pl.off_end, ws_bytes);
     return B200R_ENOMEM;
@@ -225,7 +228,9 @@ static int do_search(Index* ix, const void* Q, int B, int k, int path, float* ou
     profile_end(st);
     if (rc) return rc;
   }
-  return launch_select_lists(ix, pl, ws, out_scores, out_ids, st);
+  // the peers' buffers may only be overwritten once every rank has consumed what the previous use of them held
+  if (wait_before_output) B200R_CUDA_CHECK(cudaStreamWaitEvent(st, wait_before_output, 0));
+  return launch_select_lists(ix, pl, ws, out_scores, out_ids, st, peers);
 }
 
 }  // namespace b200r
@@ -326,6 +331,26 @@ int b200r_search(uint64_t index, const void* Q, int32_t B, int32_t k, int32_t pa
   if (!ix) return B200R_ESTATE;
   B200R_CUDA_CHECK(cudaSetDevice(ix->device));
   return do_search(ix, Q, B, k, path, out_scores, out_ids, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200r_search_scatter(uint64_t index, const void* Q, int32_t B, int32_t k, int32_t path, const uint64_t* peer_bases_host,
+                         int32_t n_peers, int32_t rank, void* wait_event, void* workspace, size_t workspace_bytes, void* stream) {
+  Index* ix = get_index(index);
+  if (!ix) return B200R_ESTATE;
+  if (!peer_bases_host || n_peers < 1 || n_peers > B200R_MAX_PEERS || rank < 0 || rank >= n_peers) {
+    set_error("bad peer arguments (n_peers=%d rank=%d)", n_peers, rank);
+    return B200R_EINVAL;
+  }
+  if (((long long)B * k) % 2) { set_error("search_scatter needs B*k even (packed record layout)"); return B200R_EINVAL; }
+  PeerScatter ps;
+  ps.n = n_peers; ps.rank = rank;
+  for (int g = 0; g < n_peers; ++g) {
+    if (!peer_bases_host[g] || (peer_bases_host[g] & 7)) { set_error("peer base %d is null or misaligned", g); return B200R_EINVAL; }
+    ps.base[g] = peer_bases_host[g];
+  }
+  B200R_CUDA_CHECK(cudaSetDevice(ix->device));
+  return do_search(ix, Q, B, k, path, nullptr, nullptr, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream), &ps,
+                   reinterpret_cast<cudaEvent_t>(wait_event));
 }
 
 int b200r_search_host(uint64_t index, const void* Q_host, int32_t B, int32_t k, int32_t path, float* out_scores_host,

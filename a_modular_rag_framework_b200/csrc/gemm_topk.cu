@@ -24,6 +24,7 @@
 #include "internal.h"
 #include <math_constants.h>
 #include <cstring>
+#include <cstdlib>
 
 namespace b200r {
 
@@ -57,6 +58,7 @@ struct GemmTopkParams {
   int* counts;
   u32* gthr;
   u32 idesc;
+  unsigned long long x_hint;   // L2 eviction policy of the corpus tiles
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -102,6 +104,7 @@ __device__ __forceinline__ void mbar_arrive_remote(u64* bar, u32 cta) {
 
 constexpr u64 kEvictNormal = 0x1000000000000000ull;
 constexpr u64 kEvictLast = 0x14F0000000000000ull;
+constexpr u64 kEvictFirst = 0x12F0000000000000ull;
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, u64* bar, int c0, int c1, u64 hint) {
   asm volatile(
@@ -254,13 +257,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if constexpr (CG == 1) {
               mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
               tma_load_2d(smem_a + stage * A_BYTES, &tmap_q, &full_bar[stage], kb * BK, q_tile * BM, kEvictLast);
-              tma_load_2d(smem_b + stage * B_BYTES, &tmap_x, &full_bar[stage], kb * BK, t * BN, kEvictNormal);
+              tma_load_2d(smem_b + stage * B_BYTES, &tmap_x, &full_bar[stage], kb * BK, t * BN, p.x_hint);
             } else {
               // both CTAs' bytes are credited to the leader's barrier; this CTA loads its A and its half of B
               if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
               tma_load_2d_cg2(smem_a + stage * A_BYTES, &tmap_q, &full_bar[stage], kb * BK, q_tile * BM, kEvictLast);
               tma_load_2d_cg2(smem_b + stage * B_BYTES, &tmap_x, &full_bar[stage], kb * BK,
-                              t * BN + (int)cta_rank * (BN / 2), kEvictNormal);
+                              t * BN + (int)cta_rank * (BN / 2), p.x_hint);
               if (!leader) mbar_arrive_remote(&full_bar[stage], 0);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -445,6 +448,10 @@ static int launch_gemm_cg(const Index* ix, const CUtensorMap* tmap_q, const Sear
   // N>>3 at [17,23), M>>4 at [24,29) with M = 128 per CTA of the group
   const u32 fmt = (ix->dtype == B200R_BF16) ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((u32)(BN >> 3) << 17) | ((u32)((BM * CG) >> 4) << 24);
+  // one query tile: every corpus tile is read exactly once -> do not let it displace Q / the lists in L2
+  static const int hint_env = [] { const char* e = getenv("B200R_XHINT"); return e ? atoi(e) : -1; }();
+  const bool stream_once = hint_env >= 0 ? hint_env == 1 : (pl.num_q_tiles == 1);
+  p.x_hint = stream_once ? kEvictFirst : kEvictNormal;
   B200R_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<CG>::kSmemBytes));
   const int groups = p.num_units < kNumSMs / CG ? p.num_units : kNumSMs / CG;
   cudaLaunchConfig_t cfg;

@@ -90,7 +90,9 @@ int encode_query_tmap(const Index* ix, const void* Q, int B, CUtensorMap* tmap_q
 int launch_gemm_topk(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& p, const GemmPhase& ph, void* ws, cudaStream_t st);
 int launch_scan_topk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
 // out_scores == nullptr: threshold mode (publish the exact k-th best so far into gthr); else final output
-int launch_select_lists(const Index* ix, const SearchPlan& p, void* ws, float* out_scores, int64_t* out_ids, cudaStream_t st);
+struct PeerScatter { int n, rank; unsigned long long base[B200R_MAX_PEERS]; };
+int launch_select_lists(const Index* ix, const SearchPlan& p, void* ws, float* out_scores, int64_t* out_ids, cudaStream_t st,
+                        const PeerScatter* peers = nullptr);
 int launch_merge_topk(const float* cs, const int64_t* ci, size_t shard_stride_s, size_t shard_stride_i, int G, int B, int kin, int k,
                       float* os, int64_t* oi, cudaStream_t st);
 void profile_begin(cudaStream_t st);

@@ -34,6 +34,11 @@ struct SelectParams {
   long long* out_ids;
   u64* out_lists;              // kSelPartial: out_lists[(g*Bpad + q)*k + i]
   int* out_counts;
+  // fused exchange (row-sharded corpora): instead of a local result, the final select writes this rank's packed
+  // record [ids i64 [B,k] | scores f32 [B,k]] straight into slot `rank` of EVERY rank's gather buffer (peer
+  // memory over NVLink), so the all-gather needs no separate collective kernel or staging copy
+  unsigned long long peer_base[B200R_MAX_PEERS];
+  int n_peers, rank;
 };
 
 // Visit every valid key of the CTA's segments with a warp-uniform trip count: f(key, active).
@@ -210,8 +215,20 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
   for (int i = tid; i < p.k; i += SEL_THREADS) {
     const u64 key = sk[i];
     const bool ok = (i < want) && key != 0;
-    p.out_scores[(size_t)q * p.k + i] = ok ? key_score(key) * qi : -CUDART_INF_F;
-    p.out_ids[(size_t)q * p.k + i] = ok ? (p.id_base + (long long)key_id(key)) : -1ll;
+    const float sc = ok ? key_score(key) * qi : -CUDART_INF_F;
+    const long long id = ok ? (p.id_base + (long long)key_id(key)) : -1ll;
+    if (p.n_peers == 0) {
+      p.out_scores[(size_t)q * p.k + i] = sc;
+      p.out_ids[(size_t)q * p.k + i] = id;
+    } else {
+      const size_t n = (size_t)p.B * p.k;
+      const size_t rec = 12 * n;
+      for (int g = 0; g < p.n_peers; ++g) {
+        char* base = reinterpret_cast<char*>(p.peer_base[g]) + (size_t)p.rank * rec;
+        reinterpret_cast<long long*>(base)[(size_t)q * p.k + i] = id;
+        reinterpret_cast<float*>(base + 8 * n)[(size_t)q * p.k + i] = sc;
+      }
+    }
   }
 }
 
@@ -236,9 +253,14 @@ static int run_select(SelectParams& p, int grid_y, cudaStream_t st) {
   return B200R_OK;
 }
 
-int launch_select_lists(const Index* ix, const SearchPlan& pl, void* ws, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+int launch_select_lists(const Index* ix, const SearchPlan& pl, void* ws, float* out_scores, int64_t* out_ids, cudaStream_t st,
+                        const PeerScatter* peers) {
   SelectParams p;
   memset(&p, 0, sizeof(p));
+  if (peers) {
+    p.n_peers = peers->n; p.rank = peers->rank;
+    for (int g = 0; g < peers->n; ++g) p.peer_base[g] = peers->base[g];
+  }
   p.lists = reinterpret_cast<const u64*>((char*)ws + pl.off_lists);
   p.counts = reinterpret_cast<const int*>((char*)ws + pl.off_counts);
   p.S = pl.num_segments; p.Bpad = pl.Bpad; p.cap = pl.cap;
@@ -248,7 +270,7 @@ int launch_select_lists(const Index* ix, const SearchPlan& pl, void* ws, float* 
   p.id_base = ix->id_base;
   p.out_scores = out_scores;
   p.out_ids = reinterpret_cast<long long*>(out_ids);
-  if (!out_scores) { p.mode = kSelThreshold; return run_select(p, 1, st); }
+  if (!out_scores && !peers) { p.mode = kSelThreshold; return run_select(p, 1, st); }
   if (pl.num_groups > 0) {
     // two levels: many short per-warp lists (scan path) are first reduced group-wise to k keys each
     SelectParams p1 = p;

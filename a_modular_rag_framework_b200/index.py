@@ -113,6 +113,22 @@ class DenseIndex:
                                            ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
         return scores, ids
 
+    def search_scatter(self, Q: torch.Tensor, k: int, peer_bases, rank: int, path: str = "auto",
+                       wait_event: Optional[torch.cuda.Event] = None) -> None:
+        """Search and let the final select kernel store this rank's packed (ids | scores)[B, k] record into slot
+        `rank` of every rank's gather buffer (`peer_bases`: peer-mapped device addresses).  Stream-ordered, no sync."""
+        _require_cuda(Q, "Q")
+        if Q.dim() != 2 or Q.shape[1] != self.D or Q.dtype != self.query_dtype:
+            raise ValueError(f"Q must be [B, {self.D}] {self.query_dtype}")
+        B = int(Q.shape[0])
+        p = _PATHS[path]
+        ws = self._workspace(B, k, p)
+        arr = (ctypes.c_uint64 * len(peer_bases))(*[int(x) for x in peer_bases])
+        with torch.cuda.device(self.device):
+            N.check(self._lib.b200r_search_scatter(self._handle, Q.data_ptr(), B, k, p, arr, len(peer_bases), int(rank),
+                                                   wait_event.cuda_event if wait_event is not None else None,
+                                                   ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+
     def search_host(self, Q_host: torch.Tensor, k: int, path: str = "auto",
                     out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """Host buffers in, host buffers out (H2D + search + D2H + stream sync inside the C call)."""

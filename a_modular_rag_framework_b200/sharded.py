@@ -55,7 +55,16 @@ class ShardedDenseIndex:
     """`local` searches this rank's rows and reports GLOBAL ids (DenseIndex(X_shard, id_base=lo))."""
 
     def __init__(self, local, group: Optional[dist.ProcessGroup] = None,
-                 merge_packed: Optional[Callable[[torch.Tensor, int, int, int], Tuple[torch.Tensor, torch.Tensor]]] = None):
+                 merge_packed: Optional[Callable[[torch.Tensor, int, int, int], Tuple[torch.Tensor, torch.Tensor]]] = None,
+                 exchange: str = "nccl"):
+        """exchange="nccl": packed all_gather_into_tensor.  exchange="p2p": the final select kernel of the search
+        stores each rank's packed record straight into every rank's gather buffer over NVLink (symmetric memory,
+        b200r_search_scatter), followed by a symmetric-memory barrier -- no collective kernel, no staging copy."""
+        if exchange not in ("nccl", "p2p"):
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        self.exchange = exchange
+        self._p2p = {}           # (B, k) -> per-slot (buffer, handle, peer pointers)
+        self._barrier_events = {}
         self.local = local
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -86,6 +95,8 @@ class ShardedDenseIndex:
             return PendingResult(res[0], res[1], None) if overlap else res
         B = int(Q.shape[0])
         n = B * k
+        if self.exchange == "p2p":
+            return self._search_p2p(Q, k, path, overlap)
         if not overlap:
             pack, gather = self._buffers(B, k, Q.device)
             ids_view = pack[: 8 * n].view(torch.int64).view(B, k)
@@ -117,6 +128,54 @@ class ShardedDenseIndex:
         if not hasattr(self, "_slot_events"):
             self._slot_events = {}
         self._slot_events[self._slot] = done
+        return PendingResult(scores, ids, done)
+
+
+    # ---- fused exchange over peer memory ---------------------------------------------------------------
+    def _p2p_slots(self, B: int, k: int, device):
+        key = (B, k)
+        if key not in self._p2p:
+            import torch.distributed._symmetric_memory as symm_mem
+            n = B * k
+            if n % 2:
+                raise ValueError("B*k must be even for the packed exchange")
+            slots = []
+            for _ in range(2):
+                buf = symm_mem.empty(12 * n * self.world, dtype=torch.uint8, device=device)
+                hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+                slots.append((buf, hdl, [int(p) for p in hdl.buffer_ptrs]))
+            self._p2p[key] = slots
+        return self._p2p[key]
+
+    def _search_p2p(self, Q: torch.Tensor, k: int, path: str, overlap: bool):
+        B = int(Q.shape[0])
+        slots = self._p2p_slots(B, k, Q.device)
+        self._slot ^= 1
+        buf, hdl, ptrs = slots[self._slot]
+        cur = torch.cuda.current_stream(Q.device)
+        # the peers' copies of this slot were last read two batches ago; every rank is past that once the barrier of
+        # the PREVIOUS batch has completed here (its signal is stream-ordered after the peer's merge)
+        prev_barrier = self._barrier_events.get("last")
+        self.local.search_scatter(Q, k, ptrs, self.rank, path=path, wait_event=prev_barrier)
+        if not overlap:
+            hdl.barrier(channel=0)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._barrier_events["last"] = ev
+            return self._merge(buf, self.world, B, k)
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=Q.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(ready)
+            hdl.barrier(channel=0)
+            ev = torch.cuda.Event()
+            ev.record(self._comm_stream)
+            scores, ids = self._merge(buf, self.world, B, k)
+            done = torch.cuda.Event()
+            done.record(self._comm_stream)
+        self._barrier_events["last"] = ev
         return PendingResult(scores, ids, done)
 
 

@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default=os.environ.get("B200R_EXCHANGE", "p2p"), choices=["p2p", "nccl"],
+                    help="N>1: fused select->peer-memory scatter (default) or packed NCCL all-gather")
     return ap.parse_args()
 
 
@@ -227,7 +229,7 @@ def main():
     torch.cuda.synchronize()
 
     local = DenseIndex(X[:max(n_local, 1)] if n_local else X, metric="cos", id_base=lo)
-    index = ShardedDenseIndex(local) if world > 1 else local
+    index = ShardedDenseIndex(local, exchange=a.exchange) if world > 1 else local
 
     def barrier():
         if world > 1:
@@ -352,7 +354,10 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "batch": a.batch, "k": a.k,
                        "path": used_path, "sharding": f"rows/{world}",
-                       "exchange": "none" if world == 1 else "packed NCCL all-gather + device merge on a side stream, overlapped with the next batch's search",
+                       "exchange": "none" if world == 1 else (
+                           "final select kernel stores each rank's packed top-k into every rank's symmetric gather buffer over NVLink, symmetric-memory barrier + device merge on a side stream, overlapped with the next batch's search"
+                           if a.exchange == "p2p" else
+                           "packed NCCL all-gather + device merge on a side stream, overlapped with the next batch's search"),
                        "l2": "corpus shard (>= 1.9 GB) is far larger than the 126 MB L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "per_rank": per_rank,

@@ -52,6 +52,7 @@ extern "C" {
 #define B200R_PATH_SCAN 2 /* CUDA-core streaming scan, 128-bit loads (all types; meant for B <= 4) */
 
 #define B200R_MAX_K 2048
+#define B200R_MAX_PEERS 8
 
 int b200r_version(void);
 /* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
@@ -85,6 +86,18 @@ int b200r_search(uint64_t index, const void* Q, int32_t B, int32_t k, int32_t pa
  * buffers that grow on demand. */
 int b200r_search_host(uint64_t index, const void* Q_host, int32_t B, int32_t k, int32_t path,
                       float* out_scores_host, int64_t* out_ids_host, void* stream);
+
+/* Fused exchange for row-sharded corpora: same search, but the final select kernel writes this rank's packed
+ * record [ids i64 [B,k] | scores f32 [B,k]] directly into slot `rank` of every rank's gather buffer
+ * (peer_bases_host[g] = device address of rank g's buffer, peer-mapped in this process, e.g. from a CUDA IPC /
+ * symmetric-memory rendezvous), i.e. the all-gather is done by the kernel's own stores over NVLink.  The caller
+ * then synchronises the ranks (any cross-GPU barrier ordered after this call) and runs b200r_merge_topk_packed
+ * on its own gather buffer.  n_peers <= B200R_MAX_PEERS.  wait_event (cudaEvent_t as void*, may be NULL): the
+ * stream waits for it right before the kernel that writes to the peers (every rank must have consumed the
+ * buffers' previous contents by then); the tile kernels before it are not delayed. */
+int b200r_search_scatter(uint64_t index, const void* Q, int32_t B, int32_t k, int32_t path,
+                         const uint64_t* peer_bases_host, int32_t n_peers, int32_t rank, void* wait_event,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- merge of per-shard top-k lists ----------------------------------------------------------
  * The same stable-sort rule applied to the union of G lists (one per GPU after the NCCL all-gather):
