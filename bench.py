@@ -230,6 +230,19 @@ def main():
 
     local = DenseIndex(X[:max(n_local, 1)] if n_local else X, metric="cos", id_base=lo)
     index = ShardedDenseIndex(local, exchange=a.exchange) if world > 1 else local
+    if world > 1 and a.exchange == "p2p":
+        # symmetric-memory rendezvous needs CUDA IPC between the ranks; agree on a fallback if any rank cannot do it
+        ok = 1
+        try:
+            index._p2p_slots(a.batch, a.k, dev)
+        except Exception as e:  # noqa: BLE001
+            ok = 0
+            sys.stderr.write(f"[bench] rank {rank}: symmetric-memory exchange unavailable ({e!r}); using the NCCL all-gather\n")
+        flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            a.exchange = "nccl"
+            index = ShardedDenseIndex(local, exchange="nccl")
 
     def barrier():
         if world > 1:
