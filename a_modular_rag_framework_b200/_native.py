@@ -20,7 +20,7 @@ EOVERFLOW = -4
 EXPORTS = [
     "b200r_version", "b200r_last_error", "b200r_launch_count",
     "b200r_index_create", "b200r_index_destroy", "b200r_index_info",
-    "b200r_search_workspace_bytes", "b200r_search", "b200r_search_host", "b200r_search_scatter",
+    "b200r_search_workspace_bytes", "b200r_search", "b200r_search_host", "b200r_search_scatter", "b200r_search_min_score",
     "b200r_merge_topk", "b200r_merge_topk_packed", "b200r_profile_enable", "b200r_profile_read",
     "b200r_graph_create", "b200r_graph_destroy",
     "b200r_expand_max_candidates", "b200r_expand_rescore", "b200r_expand_workspace_bytes", "b200r_expand_rescore_sharded",
@@ -48,9 +48,14 @@ def load() -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     path = lib_path()
+    if not os.path.exists(path) and not os.environ.get("B200R_LIB"):
+        try:
+            _build.build()       # in-tree nvcc build; still no CPU fallback if this fails
+        except Exception as e:  # noqa: BLE001
+            raise B200RError(-2, f"{path} is missing and could not be built ({e}); run "
+                                 f"`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc); there is no CPU fallback")
     if not os.path.exists(path):
-        raise B200RError(-2, f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                             f"(needs nvcc); there is no CPU fallback")
+        raise B200RError(-2, f"{path} is missing; there is no CPU fallback")
     lib = ctypes.CDLL(path)
     lib.b200r_version.restype = c_int
     lib.b200r_last_error.argtypes = [c_char_p, c_size_t]
@@ -63,6 +68,7 @@ def load() -> ctypes.CDLL:
     lib.b200r_search_workspace_bytes.restype = c_size_t
     lib.b200r_search.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.b200r_search_host.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.b200r_search_min_score.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.b200r_search_scatter.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, POINTER(c_uint64), c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.b200r_merge_topk.argtypes = [c_int, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
     lib.b200r_merge_topk_packed.argtypes = [c_int, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]

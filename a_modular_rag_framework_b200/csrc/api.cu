@@ -194,7 +194,8 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
 static int query_dtype(const Index* ix) { return ix->dtype == B200R_I8 ? B200R_F32 : ix->dtype; }
 
 static int do_search(Index* ix, const void* Q, int B, int k, int path, float* out_scores, int64_t* out_ids, void* ws,
-                     size_t ws_bytes, cudaStream_t st, const PeerScatter* peers = nullptr, cudaEvent_t wait_before_output = nullptr) {
+                     size_t ws_bytes, cudaStream_t st, const PeerScatter* peers = nullptr, cudaEvent_t wait_before_output = nullptr,
+                     float min_score = -HUGE_VALF) {
   SearchPlan pl;
   int rc = make_plan(ix, B, k, path, &pl);
   if (rc) return rc;
@@ -212,6 +213,8 @@ static int do_search(Index* ix, const void* Q, int B, int k, int path, float* ou
     float* qinv = reinterpret_cast<float*>((char*)ws + pl.off_qinv);
     if ((rc = launch_query_inv_norm(Q, B, ix->D, query_dtype(ix), qinv, st))) return rc;
   }
+  const bool floor_on = min_score > -HUGE_VALF;
+  if (floor_on && (rc = launch_min_score(pl, ws, ix->metric == B200R_COS, min_score, st))) return rc;
   if (pl.path == B200R_PATH_GEMM) {
     CUtensorMap tmap_q;
     if ((rc = encode_query_tmap(ix, Q, B, &tmap_q))) return rc;
@@ -230,7 +233,7 @@ static int do_search(Index* ix, const void* Q, int B, int k, int path, float* ou
   }
   // the peers' buffers may only be overwritten once every rank has consumed what the previous use of them held
   if (wait_before_output) B200R_CUDA_CHECK(cudaStreamWaitEvent(st, wait_before_output, 0));
-  return launch_select_lists(ix, pl, ws, out_scores, out_ids, st, peers);
+  return launch_select_lists(ix, pl, ws, out_scores, out_ids, st, peers, min_score);
 }
 
 }  // namespace b200r
@@ -331,6 +334,16 @@ int b200r_search(uint64_t index, const void* Q, int32_t B, int32_t k, int32_t pa
   if (!ix) return B200R_ESTATE;
   B200R_CUDA_CHECK(cudaSetDevice(ix->device));
   return do_search(ix, Q, B, k, path, out_scores, out_ids, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200r_search_min_score(uint64_t index, const void* Q, int32_t B, int32_t k, int32_t path, float min_score, float* out_scores,
+                           int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream) {
+  Index* ix = get_index(index);
+  if (!ix) return B200R_ESTATE;
+  if (!(min_score == min_score)) { set_error("min_score is NaN"); return B200R_EINVAL; }
+  B200R_CUDA_CHECK(cudaSetDevice(ix->device));
+  return do_search(ix, Q, B, k, path, out_scores, out_ids, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream),
+                   nullptr, nullptr, min_score);
 }
 
 int b200r_search_scatter(uint64_t index, const void* Q, int32_t B, int32_t k, int32_t path, const uint64_t* peer_bases_host,

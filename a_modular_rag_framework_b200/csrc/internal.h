@@ -86,13 +86,14 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* plan);
 int launch_row_mult(const Index* ix, const float* row_scale, cudaStream_t st);
 int launch_query_inv_norm(const void* Q, int B, int D, int qdtype, float* qinv, cudaStream_t st);
 int launch_init_search(const SearchPlan& p, void* ws, cudaStream_t st);
+int launch_min_score(const SearchPlan& p, void* ws, bool cosine, float min_score, cudaStream_t st);
 int encode_query_tmap(const Index* ix, const void* Q, int B, CUtensorMap* tmap_q);
 int launch_gemm_topk(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& p, const GemmPhase& ph, void* ws, cudaStream_t st);
 int launch_scan_topk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
 // out_scores == nullptr: threshold mode (publish the exact k-th best so far into gthr); else final output
 struct PeerScatter { int n, rank; unsigned long long base[B200R_MAX_PEERS]; };
 int launch_select_lists(const Index* ix, const SearchPlan& p, void* ws, float* out_scores, int64_t* out_ids, cudaStream_t st,
-                        const PeerScatter* peers = nullptr);
+                        const PeerScatter* peers = nullptr, float min_score = -__builtin_huge_valf());
 int launch_merge_topk(const float* cs, const int64_t* ci, size_t shard_stride_s, size_t shard_stride_i, int G, int B, int kin, int k,
                       float* os, int64_t* oi, cudaStream_t st);
 void profile_begin(cudaStream_t st);

@@ -292,6 +292,26 @@ __global__ void init_search_kernel(u32* gthr, int n_gthr, int* counts, long long
   for (long long j = i; j < n_counts; j += stride) counts[j] = 0;
 }
 
+// similarity floor (b200r_search_min_score): start every query's filter at min_score expressed in the key domain
+// (keys carry acc*row_mult; the final score multiplies by 1/|q|), a hair lower so rounding cannot lose a boundary hit
+__global__ void min_score_gthr_kernel(u32* gthr, const float* qinv, int B, float min_score) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= B) return;
+  float t = min_score;
+  if (qinv) t = qinv[q] > 0.0f ? min_score / qinv[q] : (min_score > 0.0f ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000));
+  t = t > 0.0f ? t * (1.0f - 2e-6f) : t * (1.0f + 2e-6f);
+  atomicMax(gthr + q, f32_to_ordered(t));
+}
+
+int launch_min_score(const SearchPlan& pl, void* ws, bool cosine, float min_score, cudaStream_t st) {
+  u32* gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
+  const float* qinv = cosine ? reinterpret_cast<const float*>((char*)ws + pl.off_qinv) : nullptr;
+  min_score_gthr_kernel<<<(pl.B + 255) / 256, 256, 0, st>>>(gthr, qinv, pl.B, min_score);
+  count_launch();
+  B200R_CUDA_CHECK(cudaGetLastError());
+  return B200R_OK;
+}
+
 int launch_init_search(const SearchPlan& pl, void* ws, cudaStream_t st) {
   u32* gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
   int* counts = reinterpret_cast<int*>((char*)ws + pl.off_counts);

@@ -39,6 +39,7 @@ struct SelectParams {
   // memory over NVLink), so the all-gather needs no separate collective kernel or staging copy
   unsigned long long peer_base[B200R_MAX_PEERS];
   int n_peers, rank;
+  float min_score;             // results below it are reported as padding (b200r_search_min_score)
 };
 
 // Visit every valid key of the CTA's segments with a warp-uniform trip count: f(key, active).
@@ -215,8 +216,9 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
   for (int i = tid; i < p.k; i += SEL_THREADS) {
     const u64 key = sk[i];
     const bool ok = (i < want) && key != 0;
-    const float sc = ok ? key_score(key) * qi : -CUDART_INF_F;
-    const long long id = ok ? (p.id_base + (long long)key_id(key)) : -1ll;
+    float sc = ok ? key_score(key) * qi : -CUDART_INF_F;
+    long long id = ok ? (p.id_base + (long long)key_id(key)) : -1ll;
+    if (!(sc >= p.min_score)) { sc = -CUDART_INF_F; id = -1ll; }
     if (p.n_peers == 0) {
       p.out_scores[(size_t)q * p.k + i] = sc;
       p.out_ids[(size_t)q * p.k + i] = id;
@@ -254,9 +256,10 @@ static int run_select(SelectParams& p, int grid_y, cudaStream_t st) {
 }
 
 int launch_select_lists(const Index* ix, const SearchPlan& pl, void* ws, float* out_scores, int64_t* out_ids, cudaStream_t st,
-                        const PeerScatter* peers) {
+                        const PeerScatter* peers, float min_score) {
   SelectParams p;
   memset(&p, 0, sizeof(p));
+  p.min_score = min_score;
   if (peers) {
     p.n_peers = peers->n; p.rank = peers->rank;
     for (int g = 0; g < peers->n; ++g) p.peer_base[g] = peers->base[g];

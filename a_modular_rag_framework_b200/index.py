@@ -93,8 +93,9 @@ class DenseIndex:
         return self._ws
 
     def search(self, Q: torch.Tensor, k: int, path: str = "auto",
-               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Q [B, D] on the device in ``query_dtype`` -> (scores f32 [B, k], ids i64 [B, k]), stream-ordered, no sync."""
+               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, min_score: Optional[float] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Q [B, D] on the device in ``query_dtype`` -> (scores f32 [B, k], ids i64 [B, k]), stream-ordered, no sync.
+        min_score: only results with score >= min_score are reported (the rest of each row is (-inf, -1))."""
         _require_cuda(Q, "Q")
         if Q.dim() != 2 or Q.shape[1] != self.D:
             raise ValueError(f"Q must be [B, {self.D}]")
@@ -109,8 +110,12 @@ class DenseIndex:
         else:
             scores, ids = out
         with torch.cuda.device(self.device):
-            N.check(self._lib.b200r_search(self._handle, Q.data_ptr(), B, k, p, scores.data_ptr(), ids.data_ptr(),
-                                           ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+            if min_score is None:
+                N.check(self._lib.b200r_search(self._handle, Q.data_ptr(), B, k, p, scores.data_ptr(), ids.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+            else:
+                N.check(self._lib.b200r_search_min_score(self._handle, Q.data_ptr(), B, k, p, float(min_score), scores.data_ptr(),
+                                                         ids.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
         return scores, ids
 
     def search_scatter(self, Q: torch.Tensor, k: int, peer_bases, rank: int, path: str = "auto",
@@ -267,3 +272,17 @@ def expand_rescore_pass(index: DenseIndex, graph: PassageGraph, Q: torch.Tensor,
             o["score"].data_ptr(), o["id"].data_ptr(), o["hop"].data_ptr(), o["score_graph_norm"].data_ptr(),
             o["score_dense_norm"].data_ptr(), o["cos"].data_ptr(), o["ncand"].data_ptr(), o["status"].data_ptr(),
             _stream_ptr(index.device)))
+
+
+def semantic_sim_edges(index: DenseIndex, threshold: float, max_per_row: int = 64, batch: int = 4096) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Corpus-scale version of EdgeBuilder.build step 4 (edge_builder.py:146-169): every unordered pair (a, b), a < b,
+    with cosine >= threshold (the reference enumerates itertools.combinations, i.e. each pair once, a before b).
+    Each row keeps at most `max_per_row` best partners.  Returns (src i64, dst i64, sim f32) on the device."""
+    src, dst, sim = [], [], []
+    for r0 in range(0, index.N, batch):
+        Q = index.X[r0:r0 + batch].to(index.query_dtype).contiguous()
+        s, i = index.search(Q, max_per_row + 1, min_score=threshold)
+        rows = torch.arange(r0, r0 + Q.shape[0], device=index.device, dtype=torch.int64).unsqueeze(1).expand_as(i) + index.id_base
+        keep = (i >= 0) & (i > rows)          # drops padding, self matches and the mirrored half
+        src.append(rows[keep]); dst.append(i[keep]); sim.append(s[keep])
+    return torch.cat(src), torch.cat(dst), torch.cat(sim)

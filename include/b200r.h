@@ -87,6 +87,14 @@ int b200r_search(uint64_t index, const void* Q, int32_t B, int32_t k, int32_t pa
 int b200r_search_host(uint64_t index, const void* Q_host, int32_t B, int32_t k, int32_t path,
                       float* out_scores_host, int64_t* out_ids_host, void* stream);
 
+/* Similarity floor: only results with score >= min_score are reported (at most the k best per query, the rest
+ * of the row is (-inf, -1)).  With Q = rows of the corpus itself this is the all-pairs `sim >= semantic_threshold`
+ * test of EdgeBuilder.build step 4 (app/modules/graph_construction/edge_builder.py:146-169) at corpus scale:
+ * the floor seeds every query's filter threshold, so the tile kernels reject almost everything from the start. */
+int b200r_search_min_score(uint64_t index, const void* Q, int32_t B, int32_t k, int32_t path, float min_score,
+                           float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
 /* Fused exchange for row-sharded corpora: same search, but the final select kernel writes this rank's packed
  * record [ids i64 [B,k] | scores f32 [B,k]] directly into slot `rank` of every rank's gather buffer
  * (peer_bases_host[g] = device address of rank g's buffer, peer-mapped in this process, e.g. from a CUDA IPC /

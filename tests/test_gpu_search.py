@@ -199,3 +199,36 @@ def test_bad_arguments_raise():
         DenseIndex(torch.zeros((16, 8), dtype=torch.bfloat16))
     with pytest.raises(B200RError):
         DenseIndex(torch.zeros((16, 4), device=_dev(), dtype=torch.bfloat16))  # rows not 16-byte aligned
+
+
+def test_min_score_floor_and_semantic_sim_edges():
+    """b200r_search_min_score against the oracle, and the corpus-scale semantic_sim edge list against the
+    reference's rule (edge_builder.py:146-169: every pair a<b with sim >= threshold, zero-norm -> 0.0)."""
+    from a_modular_rag_framework_b200.index import semantic_sim_edges
+    rng = np.random.default_rng(17)
+    N, D, tau = 6000, 32, 0.55
+    Xn = rng.standard_normal((N, D)).astype(np.float32)
+    Xn[100:140] = Xn[100] + 0.3 * rng.standard_normal((40, D)).astype(np.float32)   # a cluster of near-duplicates
+    Xn[7] = 0.0
+    Xn = O.bf16_bits_to_f32(O.f32_to_bf16_bits(Xn))
+    X = torch.from_numpy(Xn).to(_dev()).to(torch.bfloat16)
+    ix = _index(X)
+    S = O.score_matrix(Xn, Xn)
+    for path, B in (("gemm", 300), ("scan", 2)):
+        s, i = ix.search(X[:B].contiguous(), 50, path=path, min_score=tau)
+        s, i = s.cpu().numpy(), i.cpu().numpy()
+        for b in range(B):
+            ref = np.nonzero(S[b] >= tau)[0]
+            got = i[b][i[b] >= 0]
+            sure = set(np.nonzero(S[b] >= tau + 1e-3)[0].tolist())
+            maybe = set(np.nonzero(S[b] >= tau - 1e-3)[0].tolist())
+            if len(ref) <= 50:
+                assert sure <= set(got.tolist()) <= maybe, (path, b)
+            assert np.all(s[b][: len(got)] >= tau - 1e-3) and np.all(np.isneginf(s[b][len(got):]))
+    src, dst, sim = semantic_sim_edges(ix, tau, max_per_row=64, batch=1024)
+    got = set(zip(src.cpu().tolist(), dst.cpu().tolist()))
+    iu = np.triu_indices(N, 1)
+    sure = set(zip(*[a[S[iu] >= tau + 1e-3].tolist() for a in iu]))
+    maybe = set(zip(*[a[S[iu] >= tau - 1e-3].tolist() for a in iu]))
+    assert sure <= got <= maybe
+    assert all(a < b for a, b in got) and 7 not in {a for a, _ in got} | {b for _, b in got}
