@@ -63,10 +63,17 @@ def workload_name(a):
 def cpu_reference_qps(rows, dim, batch, k, target_seconds, steps=1, warmup=0, seed=1234):
     """Oracle (reference-semantics numpy restatement, float32 BLAS, all host threads) on a bounded
     sample: Bs queries x Ns rows, timed, then scaled linearly in N to the full corpus."""
+    cores = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[var] = str(cores)
     import numpy as np
     from oracle import retrieval_oracle as O
-
-    cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:  # noqa: BLE001
+        pass
     rng = np.random.default_rng(seed)
     Bs = min(batch, 256)
     # calibrate on a small block, then size the sample for ~target_seconds
