@@ -22,6 +22,7 @@
 // CTAs that share a chunk stream the same X tiles at the same time and hit them in L2.
 #include "common.cuh"
 #include "internal.h"
+#include "tc_ptx.cuh"
 #include <math_constants.h>
 #include <cstring>
 #include <cstdlib>
@@ -60,117 +61,6 @@ struct GemmTopkParams {
   u32 idesc;
   unsigned long long x_hint;   // L2 eviction policy of the corpus tiles
 };
-
-// ------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(u64* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(u64* bar, u32 parity) {
-  u32 ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
-  while (!mbar_try_wait(bar, parity)) {}
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ u32 cluster_ctarank() { u32 r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(u64* bar, u32 cta) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(smem_u32(bar)), "r"(cta) : "memory");
-}
-
-constexpr u64 kEvictNormal = 0x1000000000000000ull;
-constexpr u64 kEvictLast = 0x14F0000000000000ull;
-constexpr u64 kEvictFirst = 0x12F0000000000000ull;
-
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, u64* bar, int c0, int c1, u64 hint) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(smem_dst)), "l"((u64)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
-      : "memory");
-}
-// cta_group::2 flavour: data lands in THIS CTA's shared memory, completion bytes are credited to the barrier at
-// the same offset in the pair's leader CTA (peer bit cleared)
-__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* tmap, u64* bar, int c0, int c1, u64 hint) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(smem_dst)), "l"((u64)tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(hint)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"((u64)tmap) : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start>>4 [0,14),
-// LBO>>4 [16,30) (unused for swizzled K-major), SBO>>4 [32,46) = 1024 B between 8-row groups,
-// version=1 [46,48), layout=SWIZZLE_128B(2) [61,64).
-__device__ __forceinline__ u64 make_smem_desc(u32 smem_addr) {
-  return (u64)((smem_addr >> 4) & 0x3fffu) | ((u64)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-
-__device__ __forceinline__ void umma_f16(u32 tmem_d, u64 desc_a, u64 desc_b, u32 idesc, u32 accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16_cg2(u32 tmem_d, u64 desc_a, u64 desc_b, u32 idesc, u32 accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit_cg2(u64* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
-}
-__device__ __forceinline__ void umma_commit(u64* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(u32 taddr, u32* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // s[j] for a runtime j without spilling s[] to local memory: a balanced tree of 31 selects
 template <int LO, int N>

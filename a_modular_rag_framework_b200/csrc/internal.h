@@ -70,6 +70,7 @@ struct SearchPlan {
   // gemm: row tiles are processed in phases [tile_begin, tile_end) of geometrically growing size; after each
   // phase the exact k-th best so far becomes every query's filter threshold for the next one
   int cta_group;         // 1 or 2 (CTA pair, cta_group::2)
+  int rows_mode;         // 1: small-batch kernel (corpus rows on the MMA's M, queries resident), tiles of 128 rows
   int num_q_tiles, num_row_tiles, num_chunks;   // num_q_tiles counts tiles of cta_group*128 queries
   int num_phases;
   GemmPhase phases[kMaxPhases];
@@ -89,6 +90,11 @@ int launch_init_search(const SearchPlan& p, void* ws, cudaStream_t st);
 int launch_min_score(const SearchPlan& p, void* ws, bool cosine, float min_score, cudaStream_t st);
 int encode_query_tmap(const Index* ix, const void* Q, int B, CUtensorMap* tmap_q);
 int launch_gemm_topk(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& p, const GemmPhase& ph, void* ws, cudaStream_t st);
+int encode_query_tmap_rows(const Index* ix, const void* Q, int B, CUtensorMap* tmap_q);
+int launch_rows_topk(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& p, const GemmPhase& ph, void* ws, cudaStream_t st);
+int rows_mode_stages(int B, int D);
+int rows_mode_nq(int B);
+int rows_tile_rows();
 int launch_scan_topk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
 // out_scores == nullptr: threshold mode (publish the exact k-th best so far into gthr); else final output
 struct PeerScatter { int n, rank; unsigned long long base[B200R_MAX_PEERS]; };

@@ -17,6 +17,7 @@ constexpr int SEL_MAX_THREADS = 1024;  // block size is chosen at launch: the ke
                                        // when there are thousands of queries, one wide CTA per query when there are few
 constexpr int SEL_STAGE_MAX = 6144;   // keys staged in shared memory for the group-wise first level (48 KB)
 constexpr int SEL_STAGE_LISTS = 2560; // ... and for the per-phase / final select over pruned lists (20 KB -> 11 CTAs/SM)
+constexpr int SEL_MAX_SEGS = 1024;     // segments whose counts fit the in-smem prefix (flattened gather)
 constexpr int SEL_GROUP = 64;         // segments per CTA in the first level of a two-level select
 
 enum SelectMode { kSelOutput = 0, kSelThreshold = 1, kSelPartial = 2 };
@@ -90,18 +91,55 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
   int s0 = 0, s1 = p.S;
   if (p.mode == kSelPartial) { s0 = blockIdx.y * p.seg_per_cta; s1 = min(p.S, s0 + p.seg_per_cta); }
 
+  // segment counts -> exclusive prefix in smem (all count loads in flight at once), then every thread fetches keys
+  // of the flattened candidate array by binary search over the prefix: two dependent global loads in total
+  __shared__ int seg_off[SEL_MAX_SEGS + 1];
+  __shared__ int warp_tot[32];
+  const int nseg = s1 - s0;
+  const bool flat = nseg <= SEL_MAX_SEGS;
   if (tid == 0) { s_total = 0; s_nout = 0; s_prefix = 0; }
   __syncthreads();
-  {
+  if (flat) {
+    // blocked scan: thread t owns segments [t*per, t*per+per)
+    const int per = (nseg + SEL_THREADS - 1) / SEL_THREADS;
+    int mine = 0;
+    for (int j = 0; j < per; ++j) {
+      const int sgi = tid * per + j;
+      const int c = sgi < nseg ? p.counts[(size_t)(s0 + sgi) * p.Bpad + q] : 0;
+      if (sgi < nseg) seg_off[sgi] = c;
+      mine += c;
+    }
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFullMask, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
+    int run = wbase + incl - mine;
+    for (int j = 0; j < per; ++j) {
+      const int sgi = tid * per + j;
+      if (sgi < nseg) { const int c = seg_off[sgi]; seg_off[sgi] = run; run += c; }
+    }
+    if (tid == SEL_THREADS - 1) { seg_off[nseg] = run; s_total = run; }
+    __syncthreads();
+  } else {
     int local = 0;
     for (int s = s0 + tid; s < s1; s += SEL_THREADS) local += p.counts[(size_t)s * p.Bpad + q];
     if (local) atomicAdd(&s_total, local);
+    __syncthreads();
   }
-  __syncthreads();
   const int total = s_total;
   if (p.mode == kSelThreshold && total < p.k) return;   // not enough candidates yet for a threshold
   const bool staged = total <= p.stage_cap;
-  if (staged) {
+  if (staged && flat) {
+    for (int i = tid; i < total; i += SEL_THREADS) {
+      int lo = 0, hi = nseg;                       // last segment with seg_off <= i
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_off[mid] <= i) lo = mid; else hi = mid; }
+      stage[i] = p.lists[((size_t)(s0 + lo) * p.Bpad + q) * (size_t)p.cap + (i - seg_off[lo])];
+    }
+    __syncthreads();
+  } else if (staged) {
     // gather the valid keys: one warp per segment, coalesced
     for (int s = s0 + warp; s < s1; s += SEL_WARPS) {
       const size_t slot = (size_t)s * p.Bpad + q;

@@ -150,6 +150,9 @@ CONFIGS = {
     "cfg2_10Mx768_B1_scan": lambda: run_search("cfg2_10Mx768_B1_scan", 10_000_000, 768, 1, 100, torch.bfloat16, "scan", steps=20),
     "cfg2_10Mx768_B4_scan": lambda: run_search("cfg2_10Mx768_B4_scan", 10_000_000, 768, 4, 100, torch.bfloat16, "scan", steps=20),
     "cfg2_10Mx768_B16_gemm": lambda: run_search("cfg2_10Mx768_B16_gemm", 10_000_000, 768, 16, 100, torch.bfloat16, "gemm", steps=20),
+    "cfg2_10Mx768_B4_gemm": lambda: run_search("cfg2_10Mx768_B4_gemm", 10_000_000, 768, 4, 100, torch.bfloat16, "gemm", steps=20),
+    "cfg2_10Mx768_B64_gemm": lambda: run_search("cfg2_10Mx768_B64_gemm", 10_000_000, 768, 64, 100, torch.bfloat16, "gemm", steps=20),
+    "cfg2_10Mx768_B128_gemm": lambda: run_search("cfg2_10Mx768_B128_gemm", 10_000_000, 768, 128, 100, torch.bfloat16, "gemm", steps=20),
     "cfg2_10Mx768_B16_scan": lambda: run_search("cfg2_10Mx768_B16_scan", 10_000_000, 768, 16, 100, torch.bfloat16, "scan", steps=5),
     "cfg2_10Mx768_B2_scan": lambda: run_search("cfg2_10Mx768_B2_scan", 10_000_000, 768, 2, 100, torch.bfloat16, "scan", steps=20, check=False),
     "cfg2_10Mx768_B2_gemm": lambda: run_search("cfg2_10Mx768_B2_gemm", 10_000_000, 768, 2, 100, torch.bfloat16, "gemm", steps=20, check=False),
