@@ -339,9 +339,7 @@ static int launch_gemm_cg(const Index* ix, const CUtensorMap* tmap_q, const Sear
   const u32 fmt = (ix->dtype == B200R_BF16) ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((u32)(BN >> 3) << 17) | ((u32)((BM * CG) >> 4) << 24);
   // one query tile: every corpus tile is read exactly once -> do not let it displace Q / the lists in L2
-  static const int hint_env = [] { const char* e = getenv("B200R_XHINT"); return e ? atoi(e) : -1; }();
-  const bool stream_once = hint_env >= 0 ? hint_env == 1 : (pl.num_q_tiles == 1);
-  p.x_hint = stream_once ? kEvictFirst : kEvictNormal;
+  p.x_hint = (pl.num_q_tiles == 1) ? kEvictFirst : kEvictNormal;
   B200R_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<CG>::kSmemBytes));
   const int groups = p.num_units < kNumSMs / CG ? p.num_units : kNumSMs / CG;
   cudaLaunchConfig_t cfg;
