@@ -302,19 +302,41 @@ def main():
         if world == 1:
             def e2e_step(i):
                 local.search_host(Qh[i], a.k, path=a.path, out=(hs, hi_))
+
+            def e2e_finish():
+                pass
         else:
+            # software-pipelined by one batch: while batch i is searched, batch i-1's exchange/merge finishes on the side
+            # stream and its results are copied to the host; every step still does its own H2D and D2H
+            copy_stream = torch.cuda.Stream(device=dev)
+            inflight = []
+
+            def drain(n_keep):
+                while len(inflight) > n_keep:
+                    pend = inflight.pop(0)
+                    with torch.cuda.stream(copy_stream):
+                        s, ids = pend.get()
+                        hs.copy_(s, non_blocking=True)
+                        hi_.copy_(ids, non_blocking=True)
+                        done = torch.cuda.Event()
+                        done.record(copy_stream)
+                    done.synchronize()          # the host has this batch's results
+
             def e2e_step(i):
                 q = Qh[i].to(dev, non_blocking=True)
-                s, ids = index.search(q, a.k, path=a.path)
-                hs.copy_(s, non_blocking=True)
-                hi_.copy_(ids, non_blocking=True)
-                torch.cuda.synchronize()
+                inflight.append(index.search(q, a.k, path=a.path, overlap=True))
+                drain(1)
+
+            def e2e_finish():
+                drain(0)
         for i in range(min(a.warmup, 2)):
             e2e_step(i)
+        e2e_finish()
         barrier()
         t0 = time.perf_counter()
         for i in range(a.steps):
             e2e_step(a.warmup + i)
+        e2e_finish()
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -323,7 +345,8 @@ def main():
             dt = float(t.item())
         e2e = {"value": a.steps * a.batch / dt, "unit": UNIT, "h2d_bytes_per_step": a.batch * a.dim * 2,
                "d2h_bytes_per_step": a.batch * a.k * 12, "ms_per_step": dt / a.steps * 1e3,
-               "note": "pinned host queries -> H2D -> search -> D2H results, stream sync, per step; corpus index resident"}
+               "note": "pinned host queries -> H2D -> search -> D2H results to pinned host, per step; corpus index resident"
+                       + ("" if world == 1 else "; batches pipelined by one (exchange/merge/D2H of batch i-1 overlap the search of batch i)")}
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------
     peaks = {}
