@@ -39,8 +39,8 @@ void profile_end(cudaStream_t st) {
   else { cudaEventDestroy(g_prof_events.back()); g_prof_events.pop_back(); }
 }
 
-// B200R_ROWS_MODE=0 disables the small-batch kernel, B200R_CTA_GROUP=1 forces the single-CTA tile kernel (A/B measurements)
-static int g_rows_mode_max = [] { const char* e = getenv("B200R_ROWS_MODE"); return (e && e[0] == '0') ? 0 : 1; }();
+// B200R_CTA_GROUP=1 forces the single-CTA tile kernel, B200R_Q_REPLICAS=0 disables the query-tile replication (A/B measurements)
+static int g_q_replicas = [] { const char* e = getenv("B200R_Q_REPLICAS"); return (e && e[0] == '0') ? 0 : 1; }();
 static int g_cta_group_max = [] { const char* e = getenv("B200R_CTA_GROUP"); return (e && e[0] == '1') ? 1 : 2; }();
 int select_group_size();
 int gemm_tile_rows();
@@ -95,9 +95,10 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   if (B <= 0) { set_error("B must be > 0 (got %d)", B); return B200R_EINVAL; }
   if (k <= 0 || k > B200R_MAX_K) { set_error("k must be in [1, %d] (got %d)", B200R_MAX_K, k); return B200R_EINVAL; }
   const bool gemm_ok = ix->has_tmap;
-  // measured on B200 (10M x 768 bf16, % of the measured copy bandwidth): CUDA-core scan 100% / 86% at B = 1 / 2;
-  // tcgen05 small-batch kernel 94% for 3 <= B <= 16; tile kernel 79-106% for 17 <= B <= 128, tensor-bound beyond
-  if (path == B200R_PATH_AUTO) path = (gemm_ok && B > 2) ? B200R_PATH_GEMM : B200R_PATH_SCAN;
+  // measured on B200 (10M x 768 bf16): with the query tile replicated in global memory the tcgen05 tile kernel streams
+  // the corpus at 6.9-7.0 TB/s (105% of the measured copy bandwidth) for every B from 1 to 128 and is tensor-bound
+  // beyond; the CUDA-core scan (6.7 TB/s at B=1, 5.6 at B=2) serves fp32 / int8 / odd-D corpora
+  if (path == B200R_PATH_AUTO) path = gemm_ok ? B200R_PATH_GEMM : B200R_PATH_SCAN;
   if (path == B200R_PATH_GEMM && !gemm_ok) {
     set_error("gemm path needs a bf16/f16 corpus with D %% 8 == 0 (dtype=%d D=%d)", ix->dtype, ix->D);
     return B200R_EINVAL;
@@ -107,14 +108,12 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   pl->path = path; pl->B = B; pl->k = k;
   pl->cap_soft = list_cap_soft(k); pl->cap = list_cap(k);
   if (path == B200R_PATH_GEMM) {
-    // B <= 16: the small-batch kernel (queries resident, corpus rows on M, 128-row tiles, lists per warp);
     // more than one 128-query tile: pair the CTAs (cta_group::2) so each loads half of every corpus tile
-    pl->rows_mode = (g_rows_mode_max && rows_mode_stages(B, ix->D) > 0) ? 1 : 0;
-    pl->cta_group = (!pl->rows_mode && B > gemm_tile_queries() && g_cta_group_max >= 2) ? 2 : 1;
-    const int BMq = pl->rows_mode ? rows_mode_nq(B) : gemm_tile_queries() * pl->cta_group;
-    const int BNr = pl->rows_mode ? rows_tile_rows() : gemm_tile_rows();
-    const int list_rows_per_tile = pl->rows_mode ? 32 : BNr;      // rows one list can receive from one tile
-    pl->num_q_tiles = pl->rows_mode ? 1 : (B + BMq - 1) / BMq;
+    pl->cta_group = (B > gemm_tile_queries() && g_cta_group_max >= 2) ? 2 : 1;
+    const int BMq = gemm_tile_queries() * pl->cta_group;
+    const int BNr = gemm_tile_rows();
+    const int list_rows_per_tile = BNr;      // rows one list can receive from one tile
+    pl->num_q_tiles = (B + BMq - 1) / BMq;
     pl->num_row_tiles = (int)((ix->N + BNr - 1) / BNr);
     pl->Bpad = pl->num_q_tiles * BMq;
     // units = (query tile, chunk of row tiles).  More units per CTA = better balance, fewer = less list
@@ -166,7 +165,7 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
       seen = end; ++np;
     }
     pl->num_phases = np;
-    pl->num_segments = pl->num_chunks * (pl->rows_mode ? 4 : 1);   // rows mode keeps one list per epilogue warp
+    pl->num_segments = pl->num_chunks;
   } else {
     pl->Bpad = B;
     const int R = 4;
@@ -190,6 +189,8 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
     pl->off_lists2 = off; off += align_up((size_t)pl->num_groups * pl->Bpad * pl->k * 8, 256);
     pl->off_counts2 = off; off += align_up((size_t)pl->num_groups * pl->Bpad * 4, 256);
   }
+  pl->q_replicas = (path == B200R_PATH_GEMM && pl->cta_group == 1 && pl->num_q_tiles == 1 && g_q_replicas) ? 1 : 0;
+  if (pl->q_replicas) { pl->off_qrep = off; off += align_up(query_replica_bytes(ix->D), 256); }
   pl->off_end = off;
   return B200R_OK;
 }
@@ -220,10 +221,17 @@ static int do_search(Index* ix, const void* Q, int B, int k, int path, float* ou
   if (floor_on && (rc = launch_min_score(pl, ws, ix->metric == B200R_COS, min_score, st))) return rc;
   if (pl.path == B200R_PATH_GEMM) {
     CUtensorMap tmap_q;
-    if ((rc = pl.rows_mode ? encode_query_tmap_rows(ix, Q, B, &tmap_q) : encode_query_tmap(ix, Q, B, &tmap_q))) return rc;
+    if (pl.q_replicas) {
+      void* rep = (char*)ws + pl.off_qrep;
+      if ((rc = launch_replicate_queries(Q, rep, B, ix->D, st))) return rc;
+      rc = encode_query_tmap_replicated(ix, rep, &tmap_q);
+    } else {
+      rc = encode_query_tmap(ix, Q, B, &tmap_q);
+    }
+    if (rc) return rc;
     for (int i = 0; i < pl.num_phases; ++i) {
       profile_begin(st);
-      rc = pl.rows_mode ? launch_rows_topk(ix, &tmap_q, pl, pl.phases[i], ws, st) : launch_gemm_topk(ix, &tmap_q, pl, pl.phases[i], ws, st);
+      rc = launch_gemm_topk(ix, &tmap_q, pl, pl.phases[i], ws, st);
       profile_end(st);
       if (rc) return rc;
       if (i + 1 < pl.num_phases && (rc = launch_select_lists(ix, pl, ws, nullptr, nullptr, st))) return rc;

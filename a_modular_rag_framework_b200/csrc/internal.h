@@ -70,7 +70,7 @@ struct SearchPlan {
   // gemm: row tiles are processed in phases [tile_begin, tile_end) of geometrically growing size; after each
   // phase the exact k-th best so far becomes every query's filter threshold for the next one
   int cta_group;         // 1 or 2 (CTA pair, cta_group::2)
-  int rows_mode;         // 1: small-batch kernel (corpus rows on the MMA's M, queries resident), tiles of 128 rows
+  int q_replicas;        // 1: single query tile replicated in the workspace (off_qrep) against L2 hot-spotting
   int num_q_tiles, num_row_tiles, num_chunks;   // num_q_tiles counts tiles of cta_group*128 queries
   int num_phases;
   GemmPhase phases[kMaxPhases];
@@ -78,7 +78,7 @@ struct SearchPlan {
   int scan_bq, scan_warps, scan_blocks;
   // workspace layout (byte offsets)
   int num_groups;        // > 0: two-level final select (lists2/counts2 hold the first level's output)
-  size_t off_lists, off_counts, off_gthr, off_qinv, off_lists2, off_counts2, off_end;
+  size_t off_lists, off_counts, off_gthr, off_qinv, off_lists2, off_counts2, off_qrep, off_end;
 };
 
 int make_plan(const Index* ix, int B, int k, int path, SearchPlan* plan);
@@ -90,11 +90,9 @@ int launch_init_search(const SearchPlan& p, void* ws, cudaStream_t st);
 int launch_min_score(const SearchPlan& p, void* ws, bool cosine, float min_score, cudaStream_t st);
 int encode_query_tmap(const Index* ix, const void* Q, int B, CUtensorMap* tmap_q);
 int launch_gemm_topk(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& p, const GemmPhase& ph, void* ws, cudaStream_t st);
-int encode_query_tmap_rows(const Index* ix, const void* Q, int B, CUtensorMap* tmap_q);
-int launch_rows_topk(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& p, const GemmPhase& ph, void* ws, cudaStream_t st);
-int rows_mode_stages(int B, int D);
-int rows_mode_nq(int B);
-int rows_tile_rows();
+size_t query_replica_bytes(int D);
+int launch_replicate_queries(const void* Q, void* rep, int B, int D, cudaStream_t st);
+int encode_query_tmap_replicated(const Index* ix, const void* rep, CUtensorMap* tmap_q);
 int launch_scan_topk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
 // out_scores == nullptr: threshold mode (publish the exact k-th best so far into gthr); else final output
 struct PeerScatter { int n, rank; unsigned long long base[B200R_MAX_PEERS]; };

@@ -355,7 +355,7 @@ def main():
             peaks = json.load(f)
     except Exception:
         pass
-    used_path = a.path if a.path != "auto" else ("gemm" if a.batch > 2 else "scan")
+    used_path = a.path if a.path != "auto" else "gemm"
     # the dominant kernel is launched once per phase of a step: sum its launches over the step
     kernel_avg_ms = kernel_ms / max(a.steps, 1)
     launches_per_step = kernel_n / max(a.steps, 1)
@@ -380,7 +380,7 @@ def main():
         peak = peaks.get("hbm_gbs", 6650.0)
         achieved = nbytes / (kernel_avg_ms * 1e-3) / 1e9 if kernel_avg_ms > 0 else 0.0
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "kernel": "rows_topk_kernel<16>" if a.batch <= 16 else "gemm_topk_kernel<1>",
+                    "kernel": "gemm_topk_kernel<1>",
                     "kernel_ms_per_step": kernel_avg_ms, "launches_per_step": launches_per_step,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
                     "algorithmic": "N_local*D*2 bytes per step (corpus streamed once), summed over the phase launches"}

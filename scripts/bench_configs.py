@@ -50,7 +50,7 @@ def run_search(name, N, D, B, k, dtype, path, steps=10, warmup=3, check=True):
     ms = e0.elapsed_time(e1) / steps
     kms /= steps
     esz = X.element_size()
-    used = path if path != "auto" else ("gemm" if B > 2 and dtype in (torch.bfloat16, torch.float16) else "scan")
+    used = path if path != "auto" else ("gemm" if dtype in (torch.bfloat16, torch.float16) else "scan")
     line = {"config": name, "rows": N, "dim": D, "batch": B, "k": k, "dtype": str(dtype).split(".")[-1], "path": used,
             "ms_per_batch": ms, "queries_per_s": B / (ms * 1e-3), "kernel_ms_per_batch": kms, "kernel_launches_per_batch": kn / steps}
     passes = 1 if used == "gemm" else (B + 3) // 4
@@ -151,6 +151,7 @@ CONFIGS = {
     "cfg2_10Mx768_B4_scan": lambda: run_search("cfg2_10Mx768_B4_scan", 10_000_000, 768, 4, 100, torch.bfloat16, "scan", steps=20),
     "cfg2_10Mx768_B16_gemm": lambda: run_search("cfg2_10Mx768_B16_gemm", 10_000_000, 768, 16, 100, torch.bfloat16, "gemm", steps=20),
     "cfg2_10Mx768_B4_gemm": lambda: run_search("cfg2_10Mx768_B4_gemm", 10_000_000, 768, 4, 100, torch.bfloat16, "gemm", steps=20),
+    "cfg2_10Mx768_B24_gemm": lambda: run_search("cfg2_10Mx768_B24_gemm", 10_000_000, 768, 24, 100, torch.bfloat16, "gemm", steps=20),
     "cfg2_10Mx768_B64_gemm": lambda: run_search("cfg2_10Mx768_B64_gemm", 10_000_000, 768, 64, 100, torch.bfloat16, "gemm", steps=20),
     "cfg2_10Mx768_B128_gemm": lambda: run_search("cfg2_10Mx768_B128_gemm", 10_000_000, 768, 128, 100, torch.bfloat16, "gemm", steps=20),
     "cfg2_10Mx768_B16_scan": lambda: run_search("cfg2_10Mx768_B16_scan", 10_000_000, 768, 16, 100, torch.bfloat16, "scan", steps=5),
