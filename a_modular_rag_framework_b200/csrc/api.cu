@@ -142,6 +142,9 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
     const int T = pl->num_row_tiles;
     const int C = pl->num_chunks;
     int seen = 0, np = 0;
+    // The slow-path work of a phase is ~ B * k * ratio appends, so small batches afford a much coarser schedule
+    // (fewer launches and threshold selects, which is what matters for batch-1 latency on small shards).
+    const int ratio = B <= 16 ? 64 : (B <= 128 ? 16 : 8);
     int want0 = (10 * k + BNr - 1) / BNr;
     if (want0 < 4) want0 = 4;
     int tpc0 = (pl->cap_soft - 32) / list_rows_per_tile;
@@ -151,7 +154,7 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
       int end;
       if (np == 0) end = want0 < T ? want0 : T;
       else {
-        long long e = (long long)seen * 8;
+        long long e = (long long)seen * ratio;
         end = e < T ? (int)e : T;
         if (T - end < end / 2 || np == kMaxPhases - 1) end = T;   // fold a short tail into this phase
       }

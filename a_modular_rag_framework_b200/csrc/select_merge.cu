@@ -282,8 +282,9 @@ static int run_select(SelectParams& p, int grid_y, cudaStream_t st) {
     if (limit < SEL_STAGE_LISTS) limit = SEL_STAGE_LISTS;
     if (limit > 24576) limit = 24576;
   }
-  p.stage_cap = (int)(all < limit ? all : limit);
   const long long ctas = (long long)p.B * grid_y;
+  if (ctas <= 148) limit = 24576;      // a handful of queries: one CTA per SM can afford a 192 KB stage
+  p.stage_cap = (int)(all < limit ? all : limit);
   const int threads = ctas >= 2048 ? 128 : (ctas >= 512 ? 256 : (ctas >= 128 ? 512 : 1024));
   const size_t smem = (size_t)p.stage_cap * 8 + (p.mode == kSelOutput ? (size_t)p.kp2 * 8 : 0);
   B200R_CUDA_CHECK(cudaFuncSetAttribute(select_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
