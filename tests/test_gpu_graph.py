@@ -135,3 +135,17 @@ def test_hub_node_and_retry_instantiation():
         top, dist = O.expand_rescore(Q[b], X, row_ptr, col_idx, seeds[b], 1, 0.4, 0.2, k)
         _check_query(out, b, top, dist, k)
     assert int(out["ncand"][0]) > 4096
+
+
+def test_wide_embeddings_3072():
+    """D = 3072 (text-embedding-3-large, the reference's configured embedding model)."""
+    rng = np.random.default_rng(5)
+    V, E, D, B, k = 3000, 9000, 3072, 3, 10
+    row_ptr, col_idx = O.csr_from_edges(V, rng.integers(0, V, E), rng.integers(0, V, E))
+    X = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((V, D)).astype(np.float32)))
+    Q = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((B, D)).astype(np.float32)))
+    seeds = rng.integers(0, V, size=(B, 8))
+    out = _run(X, Q, row_ptr, col_idx, seeds, 2, 0.4, 0.2, k)
+    for b in range(B):
+        top, dist = O.expand_rescore(Q[b], X, row_ptr, col_idx, seeds[b], 2, 0.4, 0.2, k)
+        _check_query(out, b, top, dist, k)

@@ -94,6 +94,9 @@ def test_golden_fixtures(golden_dir, name, dtype, paths):
     (30000, 64, 2, 2048, "scan", torch.bfloat16, "cos"),
     (40000, 128, 700, 64, "gemm", torch.float16, "cos"),     # CTA pairs, partial last query tile
     (1000, 64, 130, 5, "gemm", torch.bfloat16, "ip"),        # pair whose second CTA has 2 valid queries
+    (6000, 3072, 9, 20, "gemm", torch.bfloat16, "cos"),      # text-embedding-3-large width (reference settings.yaml:8,19)
+    (6000, 3072, 300, 20, "gemm", torch.bfloat16, "cos"),
+    (3000, 3072, 2, 20, "scan", torch.float32, "cos"),
 ])
 def test_random_vs_oracle(N, D, B, k, path, dtype, metric):
     rng = np.random.default_rng(N * 31 + D + B)
