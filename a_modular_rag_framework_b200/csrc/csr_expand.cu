@@ -1,9 +1,10 @@
 // csr_expand.cu -- K3: graph-enhanced second stage.  One CTA (512 threads) per query:
 //   1. level-synchronous BFS from the seed passages over the CSR adjacency, depth <= window.  The
 //      `visited` set is a shared-memory hash set (first arrival == minimum hop distance).  A frontier
-//      level is expanded thread-per-node (all row_ptr / col_idx latencies of a level overlap), with a
-//      warp-level __match_any_sync pre-dedup so each distinct neighbour costs one atomic per warp; nodes
-//      with a long adjacency list are deferred to a warp-per-node pass with lane-strided 128-byte reads.
+//      level is expanded edge-parallel: adjacency ranges of the whole level are read at once, a block scan
+//      turns degrees into edge offsets, and the flattened edge list is spread over all 512 threads (coalesced
+//      col_idx reads, several in flight per thread; hubs need no special case), with a warp-level
+//      __match_any_sync pre-dedup so each distinct neighbour costs one atomic per warp.
 //   2. re-score every reached node against the query: one warp per 4 candidate rows, all 128-bit row
 //      loads of the group in flight together (this gather is the HBM-bound part).
 //   3. per-query min/max of both channels, fused = a_g*minmax(decay(hop)) + a_d*minmax(cos).
@@ -25,8 +26,8 @@ namespace b200r {
 constexpr int EXP_THREADS = 512;
 constexpr int EXP_WARPS = EXP_THREADS / 32;
 constexpr int EXP_MAXC_BIG = 8192;
-constexpr int EXP_HUB_DEG = 32;       // adjacency lists longer than this are expanded by a whole warp
-constexpr int EXP_MAX_HUBS = 256;
+constexpr int EXP_FB = 1024;          // frontier nodes expanded per batch (2 per thread)
+constexpr int EXP_EU = 4;             // col_idx loads in flight per thread
 constexpr u32 EXP_EMPTY = 0xffffffffu;
 constexpr int kStatusRetry = 1;       // internal: overflowed the small instantiation, big one will redo it
 
@@ -71,7 +72,7 @@ __device__ __forceinline__ bool hash_insert(u32* table, u32 v) {
 
 // EXP_ROWS: candidate rows gathered together by one warp (all their 128-bit loads in flight at once)
 template <typename T, int MAXC, bool RETRY_PASS, int EXP_ROWS>
-__global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const ExpandParams p) {
+__global__ void __launch_bounds__(EXP_THREADS, 3) expand_rescore_kernel(const ExpandParams p) {
   typedef typename QueryType<T>::type QT;
   constexpr int VEC = ElemTraits<T>::kVec;
   constexpr int HASH = 2 * MAXC;
@@ -87,8 +88,9 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
   uint8_t* dist = reinterpret_cast<uint8_t*>(cosv + MAXC);         // [MAXC]
   float* qs = reinterpret_cast<float*>(dist + MAXC);               // [D]
   u64* sk = reinterpret_cast<u64*>(qs + ((p.D + 1) & ~1));         // [kp2]
-  __shared__ int s_count, s_overflow, s_nhubs, s_remaining, s_nout;
-  __shared__ int s_hubs[EXP_MAX_HUBS];
+  __shared__ int s_count, s_overflow, s_remaining, s_nout, s_done;
+  __shared__ u32 s_wsum[EXP_WARPS];
+  __shared__ unsigned long long s_wwide[EXP_WARPS];
   __shared__ float s_red[4][EXP_WARPS];
   __shared__ double s_qn[EXP_WARPS];
   __shared__ u32 hist[256];
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
   float qinv = 1.0f;
   if (p.mode != 2) {
   for (int i = tid; i < HASH; i += EXP_THREADS) table[i] = EXP_EMPTY;
-  if (tid == 0) { s_count = 0; s_overflow = 0; s_nhubs = 0; }
+  if (tid == 0) { s_count = 0; s_overflow = 0; }
   // query -> fp32 in smem, and its norm
   const QT* Qp = reinterpret_cast<const QT*>(p.Q) + (size_t)q * p.D;
   double qn = 0.0;
@@ -129,62 +131,93 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
   }
   __syncthreads();
 
-  // ---- levels 1..window ---------------------------------------------------------------------------
+  // ---- levels 1..window: edge-parallel expansion ----------------------------------------------------
+  // A level is expanded in batches of EXP_FB frontier nodes: (1) every node's adjacency range (row_ptr) is read at
+  // once, (2) a block scan turns the degrees into edge offsets, (3) the batch's edges are flattened over all 512
+  // threads (binary search of the offsets), EXP_EU col_idx loads in flight per thread, consecutive threads on
+  // consecutive edges.  A level therefore costs ~2 memory latencies whatever the degree distribution (hubs included).
+  // The scratch lives in the cosine array, which is not written before the re-score.
+  long long* f_e0 = reinterpret_cast<long long*>(cosv);               // [EXP_FB]
+  u32* f_pre = reinterpret_cast<u32*>(cosv) + 2 * EXP_FB;             // [EXP_FB + 1] exclusive edge offsets
   int level_begin = 0;
   for (int d = 1; d <= p.window; ++d) {
     const int level_end = min(s_count, MAXC);
     __syncthreads();                      // everyone has read s_count before the level appends to it
     if (level_end == level_begin || s_overflow) break;  // block-uniform
     const uint8_t dd = (uint8_t)min(d, 255);
-    // (a) thread per frontier node; the loop bounds are warp-uniform so the match_any below is legal
-    for (int fb = level_begin + warp * 32; fb < level_end; fb += EXP_THREADS) {
-      const int f = fb + lane;
-      long long e0 = 0;
-      int deg = 0;
-      if (f < level_end) {
-        const u32 u = cand[f];
-        e0 = __ldg(p.row_ptr + u);
-        const long long e1 = __ldg(p.row_ptr + u + 1);
-        deg = (int)min(e1 - e0, (long long)0x7fffffff);
-        if (deg > EXP_HUB_DEG) {
-          const int h = atomicAdd(&s_nhubs, 1);
-          if (h < EXP_MAX_HUBS) { s_hubs[h] = f; deg = 0; }   // deferred to the warp-per-node pass
-        }
-      }
-      int maxdeg = deg;
+    for (int b0 = level_begin; b0 < level_end; b0 += EXP_FB) {
+      const int nb = min(EXP_FB, level_end - b0);
+      // (1) adjacency ranges, two consecutive frontier nodes per thread
+      u32 deg[2] = {0u, 0u};
+      unsigned long long wide = 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) maxdeg = max(maxdeg, __shfl_xor_sync(kFullMask, maxdeg, o));
-      for (int j = 0; j < maxdeg; ++j) {
-        const bool in = j < deg;
-        const u32 v = in ? (u32)__ldg(p.col_idx + e0 + j) : EXP_EMPTY;
-        const u32 peers = __match_any_sync(kFullMask, v);
-        const bool leader = in && (lane == __ffs(peers) - 1);
-        if (leader && !*(volatile int*)&s_overflow && hash_insert<HASH>(table, v)) {
-          const int pos = atomicAdd(&s_count, 1);
-          if (pos < MAXC) { cand[pos] = v; dist[pos] = dd; } else s_overflow = 1;
+      for (int r = 0; r < 2; ++r) {
+        const int f = 2 * tid + r;
+        if (f < nb) {
+          const u32 u = cand[b0 + f];
+          const long long e0 = __ldg(p.row_ptr + u), e1 = __ldg(p.row_ptr + u + 1);
+          const long long dl = e1 > e0 ? e1 - e0 : 0;
+          f_e0[f] = e0;
+          deg[r] = (u32)min(dl, (long long)0x7fffffff);
+          wide += (unsigned long long)dl;
         }
       }
-    }
-    __syncthreads();
-    // (b) long adjacency lists: one warp per node, lanes stride the list
-    const int nh = min(s_nhubs, EXP_MAX_HUBS);
-    for (int h = warp; h < nh; h += EXP_WARPS) {
-      const u32 u = cand[s_hubs[h]];
-      const long long e0 = __ldg(p.row_ptr + u), e1 = __ldg(p.row_ptr + u + 1);
-      for (long long base = e0; base < e1; base += 32) {
-        const long long e = base + lane;
-        const bool in = e < e1;
-        const u32 v = in ? (u32)__ldg(p.col_idx + e) : EXP_EMPTY;
-        const u32 peers = __match_any_sync(kFullMask, v);
-        const bool leader = in && (lane == __ffs(peers) - 1);
-        if (leader && !*(volatile int*)&s_overflow && hash_insert<HASH>(table, v)) {
-          const int pos = atomicAdd(&s_count, 1);
-          if (pos < MAXC) { cand[pos] = v; dist[pos] = dd; } else s_overflow = 1;
+      // (2) block exclusive scan of the degrees (and a 64-bit total to catch a batch with >= 2^31 edges)
+      u32 incl = deg[0] + deg[1];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += t;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wide += __shfl_xor_sync(kFullMask, wide, o);
+      if (lane == 31) s_wsum[warp] = incl;
+      if (lane == 0) s_wwide[warp] = wide;
+      __syncthreads();
+      u32 base = 0, total = 0;
+      unsigned long long total_wide = 0;
+#pragma unroll
+      for (int w = 0; w < EXP_WARPS; ++w) {
+        const u32 ws = s_wsum[w];
+        if (w < warp) base += ws;
+        total += ws;
+        total_wide += s_wwide[w];
+      }
+      if (total_wide > 0x7fffffffull) { if (tid == 0) s_overflow = 1; total = 0; }   // block-uniform
+      const u32 excl = base + incl - (deg[0] + deg[1]);
+      if (2 * tid < nb) f_pre[2 * tid] = excl;
+      if (2 * tid + 1 < nb) f_pre[2 * tid + 1] = excl + deg[0];
+      if (tid == 0) f_pre[nb] = total;
+      __syncthreads();
+      // (3) the batch's edges, flattened
+      for (u32 eb = 0; eb < total; eb += EXP_THREADS * EXP_EU) {
+        u32 v[EXP_EU];
+#pragma unroll
+        for (int r = 0; r < EXP_EU; ++r) {
+          const u32 e = eb + (u32)r * EXP_THREADS + (u32)tid;
+          v[r] = EXP_EMPTY;
+          if (e < total) {
+            int lo = 0, hi = nb;              // largest node with f_pre[node] <= e
+            while (hi - lo > 1) {
+              const int mid = (lo + hi) >> 1;
+              if (f_pre[mid] <= e) lo = mid; else hi = mid;
+            }
+            v[r] = (u32)__ldg(p.col_idx + f_e0[lo] + (long long)(e - f_pre[lo]));
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < EXP_EU; ++r) {
+          if (eb + (u32)r * EXP_THREADS >= total) break;        // block-uniform
+          const u32 peers = __match_any_sync(kFullMask, v[r]);
+          const bool leader = v[r] != EXP_EMPTY && (lane == __ffs(peers) - 1);
+          if (leader && !*(volatile int*)&s_overflow && hash_insert<HASH>(table, v[r])) {
+            const int pos = atomicAdd(&s_count, 1);
+            if (pos < MAXC) { cand[pos] = v[r]; dist[pos] = dd; } else s_overflow = 1;
+          }
         }
       }
+      __syncthreads();                    // the scratch is reused by the next batch
     }
-    __syncthreads();
-    if (tid == 0) s_nhubs = 0;
     level_begin = level_end;
   }
   __syncthreads();
@@ -215,6 +248,13 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
       rp[r] = Xb + (size_t)(have[r] ? row : 0) * row_bytes;
       acc[r] = 0.0f;
     }
+    // lane r fetches row r's multiplier together with the rows (not after the reduction, where its latency would be exposed)
+    float mult = 0.0f;
+    if (lane < EXP_ROWS && c0 + lane < ncand) {
+      const long long node = (long long)cand[c0 + lane];
+      const long long row = node - p.id_base;
+      if (node >= p.own_lo && node < p.own_hi && row >= 0 && row < p.N) mult = p.row_mult ? __ldg(p.row_mult + row) : 1.0f;
+    }
     for (int chunk = lane; chunk < chunks; chunk += 32) {
       uint4 xv[EXP_ROWS];
 #pragma unroll
@@ -233,10 +273,8 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
       float a = acc[r];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFullMask, a, o);
-      if (lane == 0 && c0 + r < ncand) {
-        const float m = have[r] ? (p.row_mult ? p.row_mult[(long long)cand[c0 + r] - p.id_base] : 1.0f) : 0.0f;
-        cosv[c0 + r] = (a * m) * qinv + 0.0f;
-      }
+      const float m = __shfl_sync(kFullMask, mult, r);
+      if (lane == 0 && c0 + r < ncand) cosv[c0 + r] = (a * m) * qinv + 0.0f;
     }
   }
   __syncthreads();
@@ -292,7 +330,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
     const bool own = node >= p.own_lo && node < p.own_hi;
     keys[c] = own ? make_key(p.alpha_graph * gn + p.alpha_dense * dn, cand[c]) : 0ull;   // ties on the fused score -> lower node id
   }
-  if (tid == 0) { s_prefix = 0; s_remaining = p.k; s_nout = 0; }
+  if (tid == 0) { s_prefix = 0; s_remaining = p.k; s_nout = 0; s_done = 0; }
   for (int i = tid; i < p.kp2; i += EXP_THREADS) sk[i] = 0;
   __syncthreads();
 
@@ -334,6 +372,8 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
             if (run + c[b] >= (u32)remaining) {
               s_prefix = prefix | ((u64)(u32)(lane * 8 + b) << shift);
               s_remaining = remaining - (int)run;
+              // every key of this bucket is a winner: the bucket's lowest possible key is a valid k-th key, stop refining
+              if (c[b] == (u32)remaining - run) s_done = 1;
               break;
             }
             run += c[b];
@@ -341,6 +381,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_rescore_kernel(const Expan
         }
       }
       __syncthreads();
+      if (s_done) break;      // block-uniform
     }
     kth = s_prefix;
   }

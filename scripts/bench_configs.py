@@ -109,7 +109,7 @@ def run_search_i8(name, N, D, B, k, steps=10, warmup=3):
                       "queries_per_s": B / (ms * 1e-3), "kernel_ms_per_batch": kms, "hbm_GBps": gbs, "hbm_frac_of_measured": gbs / PEAKS["hbm_gbs"]}), flush=True)
 
 
-def run_graph(name, V, E, D, B, S, k, steps=5, warmup=2):
+def run_graph(name, V, E, D, B, S, k, steps=5, warmup=2, window=2, random_seeds=False):
     X = corpus(V, D, torch.bfloat16)
     g = torch.Generator(device=dev).manual_seed(5)
     src = torch.randint(0, V, (E,), generator=g, device=dev)
@@ -125,20 +125,23 @@ def run_graph(name, V, E, D, B, S, k, steps=5, warmup=2):
     ix = DenseIndex(X, metric="cos")
     Q = queries(steps + warmup, B, D, torch.bfloat16)
     # seeds = the dense top-S of each query (the north-star pipeline)
-    seeds = [ix.search(Q[i], S)[1] for i in range(steps + warmup)]
+    if random_seeds:   # window=0 + S random seeds = the re-score gather alone (no BFS)
+        seeds = [torch.randint(0, V, (B, S), generator=g, device=dev) for i in range(steps + warmup)]
+    else:
+        seeds = [ix.search(Q[i], S)[1] for i in range(steps + warmup)]
     for i in range(warmup):
-        out = expand_rescore(ix, graph, Q[i], seeds[i], 2, 0.4, 0.2, k)
+        out = expand_rescore(ix, graph, Q[i], seeds[i], window, 0.4, 0.2, k)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        out = expand_rescore(ix, graph, Q[warmup + i], seeds[warmup + i], 2, 0.4, 0.2, k, check_status=False)
+        out = expand_rescore(ix, graph, Q[warmup + i], seeds[warmup + i], window, 0.4, 0.2, k, check_status=False)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     ncand = out["ncand"].float().mean().item()
     gather_bytes = ncand * B * D * 2
-    line = {"config": name, "nodes": V, "edges_undirected": 2 * E, "dim": D, "batch": B, "seeds": S, "k": k, "window": 2,
+    line = {"config": name, "nodes": V, "edges_undirected": 2 * E, "dim": D, "batch": B, "seeds": S, "k": k, "window": window,
             "ms_per_batch": ms, "queries_per_s": B / (ms * 1e-3), "avg_candidates": ncand,
             "gather_GBps": gather_bytes / (ms * 1e-3) / 1e9, "hbm_frac_of_measured": gather_bytes / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"],
             "overflowed_queries": int((out["status"] != 0).sum().item())}
@@ -165,6 +168,7 @@ CONFIGS = {
     "cfg3_12p5Mx384_f16_k1000_B1": lambda: run_search("cfg3_12p5Mx384_f16_k1000_B1", 12_500_000, 384, 1, 1000, torch.float16, "scan", steps=10),
     "cfg4_graph_5M_50M": lambda: run_graph("cfg4_graph_5M_50M", 5_000_000, 25_000_000, 768, 1024, 20, 10),
     "cfg4_graph_5M_50M_B4096": lambda: run_graph("cfg4_graph_5M_50M_B4096", 5_000_000, 25_000_000, 768, 4096, 20, 10),
+    "cfg4_gather_only_B4096": lambda: run_graph("cfg4_gather_only_B4096", 5_000_000, 2_500_000, 768, 4096, 2200, 10, window=0, random_seeds=True),
 }
 
 if __name__ == "__main__":

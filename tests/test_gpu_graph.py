@@ -119,7 +119,7 @@ def test_frontier_overflow_is_reported():
 
 
 def test_hub_node_and_retry_instantiation():
-    """A hub with 6000 neighbours: exercises the warp-per-node hub pass and the 8192-candidate re-run of a
+    """A hub with 6000 neighbours (its edges are spread over the whole CTA) and the 8192-candidate re-run of a
     query that overflows the 4096-candidate instantiation."""
     rng = np.random.default_rng(8)
     V, D, k = 7000, 64, 25
@@ -135,6 +135,28 @@ def test_hub_node_and_retry_instantiation():
         top, dist = O.expand_rescore(Q[b], X, row_ptr, col_idx, seeds[b], 1, 0.4, 0.2, k)
         _check_query(out, b, top, dist, k)
     assert int(out["ncand"][0]) > 4096
+
+
+def test_frontier_spanning_several_batches_and_isolated_nodes():
+    """Level 1 has 1500 nodes (> one 1024-node expansion batch), each with a private second-hop neighbour plus shared
+    ones; seeds include isolated nodes (degree 0) and a duplicate."""
+    rng = np.random.default_rng(21)
+    V, D, k = 6000, 64, 40
+    hub_s = np.zeros(1500, dtype=np.int64)
+    hub_d = np.arange(1, 1501, dtype=np.int64)
+    priv_s = np.arange(1, 1501, dtype=np.int64)
+    priv_d = np.arange(2001, 3501, dtype=np.int64)
+    shared_s = rng.integers(1, 1501, 800)
+    shared_d = rng.integers(3501, 3600, 800)
+    row_ptr, col_idx = O.csr_from_edges(V, np.concatenate([hub_s, priv_s, shared_s]), np.concatenate([hub_d, priv_d, shared_d]))
+    X = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((V, D)).astype(np.float32)))
+    Q = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((2, D)).astype(np.float32)))
+    seeds = np.array([[0, 5000, 5001, 0], [5002, 3550, -1, 5003]])     # 5000.. are isolated
+    out = _run(X, Q, row_ptr, col_idx, seeds, 2, 0.4, 0.2, k)
+    for b in range(2):
+        top, dist = O.expand_rescore(Q[b], X, row_ptr, col_idx, seeds[b], 2, 0.4, 0.2, k)
+        _check_query(out, b, top, dist, k)
+    assert int(out["ncand"][0]) > 3000
 
 
 def test_wide_embeddings_3072():
