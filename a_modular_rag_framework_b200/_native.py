@@ -78,6 +78,7 @@ def load() -> ctypes.CDLL:
     lib.b200r_graph_destroy.argtypes = [c_uint64]
     lib.b200r_expand_max_candidates.restype = c_int32
     lib.b200r_expand_rescore.argtypes = [c_uint64, c_uint64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_int32,
+                                         c_void_p, c_size_t,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.b200r_expand_workspace_bytes.argtypes = [c_int32]
     lib.b200r_expand_workspace_bytes.restype = c_size_t

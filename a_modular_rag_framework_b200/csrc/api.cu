@@ -492,14 +492,14 @@ int b200r_graph_destroy(uint64_t graph) {
 int32_t b200r_expand_max_candidates(void) { return expand_max_candidates(); }
 
 int b200r_expand_rescore(uint64_t index, uint64_t graph, const void* Q, const int64_t* seeds, int32_t B, int32_t S,
-                         int32_t window, float alpha_dense, float alpha_graph, int32_t k, float* out_scores, int64_t* out_ids,
-                         int32_t* out_hops, float* out_graph_norm, float* out_dense_norm, float* out_cos, int32_t* out_ncand,
-                         int32_t* out_status, void* stream) {
+                         int32_t window, float alpha_dense, float alpha_graph, int32_t k, void* workspace, size_t workspace_bytes,
+                         float* out_scores, int64_t* out_ids, int32_t* out_hops, float* out_graph_norm, float* out_dense_norm,
+                         float* out_cos, int32_t* out_ncand, int32_t* out_status, void* stream) {
   Index* ix = get_index(index);
   Graph* g = get_graph(graph);
   if (!ix || !g) return B200R_ESTATE;
   if (ix->device != g->device) { set_error("index and graph live on different devices"); return B200R_EINVAL; }
-  if (!Q || !seeds || !out_scores || !out_ids || !out_hops || !out_graph_norm || !out_dense_norm || !out_cos || !out_ncand || !out_status) {
+  if (!Q || !seeds || !workspace || !out_scores || !out_ids || !out_hops || !out_graph_norm || !out_dense_norm || !out_cos || !out_ncand || !out_status) {
     set_error("null pointer");
     return B200R_EINVAL;
   }
@@ -507,9 +507,13 @@ int b200r_expand_rescore(uint64_t index, uint64_t graph, const void* Q, const in
     set_error("bad B/S/k/window (%d/%d/%d/%d)", B, S, k, window);
     return B200R_EINVAL;
   }
+  if (workspace_bytes < expand_workspace_bytes(B) || (reinterpret_cast<uintptr_t>(workspace) & 255)) {
+    set_error("expand workspace too small or misaligned: need %zu bytes, 256-byte aligned", expand_workspace_bytes(B));
+    return B200R_ENOMEM;
+  }
   B200R_CUDA_CHECK(cudaSetDevice(ix->device));
   return launch_expand_rescore(ix, g, Q, seeds, B, S, window, alpha_dense, alpha_graph, k, out_scores, out_ids, out_hops,
-                               out_graph_norm, out_dense_norm, out_cos, out_ncand, out_status, 0, INT64_MIN, INT64_MAX, nullptr,
+                               out_graph_norm, out_dense_norm, out_cos, out_ncand, out_status, 0, INT64_MIN, INT64_MAX, workspace,
                                nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 

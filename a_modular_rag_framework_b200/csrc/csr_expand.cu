@@ -1,17 +1,27 @@
-// csr_expand.cu -- K3: graph-enhanced second stage.  One CTA (512 threads) per query:
-//   1. level-synchronous BFS from the seed passages over the CSR adjacency, depth <= window.  The
-//      `visited` set is a shared-memory hash set (first arrival == minimum hop distance).  A frontier
-//      level is expanded edge-parallel: adjacency ranges of the whole level are read at once, a block scan
-//      turns degrees into edge offsets, and the flattened edge list is spread over all 512 threads (coalesced
-//      col_idx reads, several in flight per thread; hubs need no special case), with a warp-level
-//      __match_any_sync pre-dedup so each distinct neighbour costs one atomic per warp.
-//   2. re-score every reached node against the query: one warp per 4 candidate rows, all 128-bit row
-//      loads of the group in flight together (this gather is the HBM-bound part).
-//   3. per-query min/max of both channels, fused = a_g*minmax(decay(hop)) + a_d*minmax(cos).
-//   4. exact top-k by (fused desc, id asc): radix select of the k-th key in smem + bitonic sort of k.
+// csr_expand.cu -- K3: graph-enhanced second stage, split so that its HBM-bound part streams on its own.
 //
-// Two instantiations share the code: 4096 candidates (71 KB smem, 3 CTAs/SM) runs for every query; the
-// 8192-candidate one re-runs only the queries that overflowed the first; beyond that B200R_EOVERFLOW.
+//   K3a bfs_kernel           one CTA (256 threads) per query: level-synchronous BFS from the seed passages over the
+//                            CSR adjacency, depth <= window.  `visited` is a shared-memory hash set (first arrival ==
+//                            minimum hop distance).  A level is expanded edge-parallel: the adjacency ranges of the
+//                            whole level are read at once, a block scan turns degrees into edge offsets and the
+//                            flattened edge list is spread over all threads (coalesced col_idx reads, several in
+//                            flight per thread; hubs need no special case), with a warp-level __match_any_sync
+//                            pre-dedup so each distinct neighbour costs one atomic per warp.  The candidate list, the
+//                            hop distances and the query's inverse norm are parked in the workspace and the query
+//                            reserves a contiguous range of 4-row groups in a flat work list (one 64-bit atomic).
+//   K3b rescore_gather_kernel persistent, grid-wide: every warp owns a contiguous slice of the flat group list (so the
+//                            load is balanced whatever the per-query candidate counts are), keeps the current query
+//                            as fp32 in its own shared-memory slice and gathers 4 candidate rows at a time with all
+//                            their 128-bit loads in flight.  This is the HBM-bound part (random 1.5 KB rows;
+//                            scripts/gather_bw.cu measures 6.9 TB/s for the bare pattern).  Per-query cosine min/max
+//                            are folded in with two order-preserving integer atomics per (warp, query).
+//   K3c fuse_select_kernel   one CTA per query: min/max normalisation of both channels (retrieval_backend.py:296-301),
+//                            fused = a_g*minmax(decay(hop)) + a_d*minmax(cos), exact top-k by (fused desc, id asc):
+//                            radix select of the k-th key in shared memory (stops as soon as a digit bucket is wholly
+//                            inside the top-k) + bitonic sort of the k winners.
+//
+// Candidate capacity: K3a/K3c run a 4096-candidate instantiation (4 CTAs/SM) for every query and a persistent
+// 8192-candidate one that only picks up the queries that overflowed the first; beyond that B200R_EOVERFLOW.
 //
 // Replaces expand_qmatch_neighbors (reference app/modules/retrieval/graph_utils.py:58-129: BFS :109-127,
 // decay :87-94), DenseReranker._cosine (retrieval_backend.py:192-197), _minmax_norm (:296-301) and the
@@ -19,17 +29,59 @@
 #include "common.cuh"
 #include "internal.h"
 #include <math_constants.h>
+#include <algorithm>
 #include <cstdlib>
 
 namespace b200r {
 
-constexpr int EXP_THREADS = 512;
-constexpr int EXP_WARPS = EXP_THREADS / 32;
-constexpr int EXP_MAXC_BIG = 8192;
-constexpr int EXP_FB = 1024;          // frontier nodes expanded per batch (2 per thread)
-constexpr int EXP_EU = 4;             // col_idx loads in flight per thread
+constexpr int EXP_MAXC_SMALL = 4096;
+constexpr int EXP_MAXC_BIG = 8192;    // row stride of the parked per-query arrays
+constexpr int BFS_THREADS = 256;
+constexpr int BFS_WARPS = BFS_THREADS / 32;
+constexpr int EXP_FB = 2 * BFS_THREADS;   // frontier nodes expanded per batch (2 per thread)
+constexpr int EXP_EU = 4;                 // col_idx loads in flight per thread
+constexpr int GATHER_ROWS = 4;            // candidate rows a warp keeps in flight (2: 0.89x, 8: 0.68x in gather_bw.cu)
+constexpr int GATHER_MAX_WARPS = 16;
+constexpr int GATHER_CTAS_PER_SM = 2;
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_WARPS = SEL_THREADS / 32;
+constexpr int EXP_PERSISTENT_CTAS = 2 * kNumSMs;
 constexpr u32 EXP_EMPTY = 0xffffffffu;
-constexpr int kStatusRetry = 1;       // internal: overflowed the small instantiation, big one will redo it
+constexpr int kStatusRetry = 1;       // internal: overflowed the small instantiation, the big one redoes it
+
+// per-call scratch, carved out of the caller's workspace (b200r_expand_workspace_bytes)
+struct ExpandWs {
+  u32* cand;            // [B][EXP_MAXC_BIG] node ids in BFS order
+  float* cos;           // [B][EXP_MAXC_BIG] cosine of the candidates this rank owns (0 elsewhere)
+  uint8_t* dist;        // [B][EXP_MAXC_BIG] hop distance
+  int* ncand;           // [B] (0 for a query that overflowed)
+  float* qinv;          // [B] 1/|q| (cosine) or 1
+  u32* mm;              // [B][2] order-preserving images of the owned candidates' (min, max) cosine
+  u32* seg_start;       // [2B] first flat group of the i-th reservation (monotonic in i)
+  u32* seg_q;           // [2B] its query
+  u64* counter;         // reservations << 32 | groups reserved
+};
+
+size_t expand_workspace_bytes(int B) {
+  const size_t b = (size_t)B;
+  return align_up(b * EXP_MAXC_BIG * 4, 256) * 2 + align_up(b * EXP_MAXC_BIG, 256) + align_up(b * 4, 256) * 2 + align_up(b * 8, 256) * 3 + 256;
+}
+
+static ExpandWs carve_ws(void* ws, int B) {
+  const size_t b = (size_t)B;
+  char* w = reinterpret_cast<char*>(ws);
+  ExpandWs s;
+  s.cand = reinterpret_cast<u32*>(w); w += align_up(b * EXP_MAXC_BIG * 4, 256);
+  s.cos = reinterpret_cast<float*>(w); w += align_up(b * EXP_MAXC_BIG * 4, 256);
+  s.dist = reinterpret_cast<uint8_t*>(w); w += align_up(b * EXP_MAXC_BIG, 256);
+  s.ncand = reinterpret_cast<int*>(w); w += align_up(b * 4, 256);
+  s.qinv = reinterpret_cast<float*>(w); w += align_up(b * 4, 256);
+  s.mm = reinterpret_cast<u32*>(w); w += align_up(b * 8, 256);
+  s.seg_start = reinterpret_cast<u32*>(w); w += align_up(b * 8, 256);
+  s.seg_q = reinterpret_cast<u32*>(w); w += align_up(b * 8, 256);
+  s.counter = reinterpret_cast<u64*>(w);
+  return s;
+}
 
 struct ExpandParams {
   const void* X;
@@ -43,11 +95,12 @@ struct ExpandParams {
   float alpha_dense, alpha_graph;
   float* out_scores; long long* out_ids; int* out_hops; float* out_gn; float* out_dn; float* out_cos;
   int* out_ncand; int* out_status;
-  // row-sharded corpora (one rank per GPU): mode 0 = everything in one launch; 1 = BFS + re-score the candidates this
-  // rank owns + local min/max, parked in the workspace; 2 = fuse with the all-reduced min/max and rank the owned ones
+  // row-sharded corpora (one rank per GPU): mode 0 = everything in one call; 1 = BFS + re-score of the candidates this
+  // rank owns + their (min, max) cosine; 2 = fuse with the all-reduced (min, max) and rank the owned candidates
   int mode;
   long long own_lo, own_hi;       // global node ids this rank scores: [own_lo, own_hi)
-  u32* ws_cand; float* ws_cos; uint8_t* ws_dist; int* ws_ncand; float* ws_minmax;   // [B][EXP_MAXC_BIG] / [B] / [B][2]
+  float* minmax;                  // [B][2] float (min, max): written by mode 1, read by mode 2
+  ExpandWs ws;
 };
 
 __device__ __forceinline__ float hop_decay(int d) {
@@ -70,396 +123,531 @@ __device__ __forceinline__ bool hash_insert(u32* table, u32 v) {
   }
 }
 
-// EXP_ROWS: candidate rows gathered together by one warp (all their 128-bit loads in flight at once)
-template <typename T, int MAXC, bool RETRY_PASS, int EXP_ROWS>
-__global__ void __launch_bounds__(EXP_THREADS, 3) expand_rescore_kernel(const ExpandParams p) {
-  typedef typename QueryType<T>::type QT;
-  constexpr int VEC = ElemTraits<T>::kVec;
+__device__ __forceinline__ void fill_no_result(const ExpandParams& p, int q) {
+  for (int i = threadIdx.x; i < p.k; i += blockDim.x) {
+    const size_t o = (size_t)q * p.k + i;
+    p.out_scores[o] = -CUDART_INF_F; p.out_ids[o] = -1; p.out_hops[o] = -1; p.out_gn[o] = 0; p.out_dn[o] = 0; p.out_cos[o] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K3a
+static size_t bfs_smem_bytes(int maxc) { return (size_t)maxc * 8 + (size_t)maxc * 4 + (size_t)EXP_FB * 8 + (size_t)(EXP_FB + 1) * 4; }
+
+template <typename QT, int MAXC>
+__global__ void __launch_bounds__(BFS_THREADS) bfs_kernel(const ExpandParams p) {
+  constexpr bool RETRY_PASS = (MAXC == EXP_MAXC_BIG);
   constexpr int HASH = 2 * MAXC;
-  const int q = blockIdx.x;
-  if (RETRY_PASS && p.out_status[q] != kStatusRetry) return;
-  if (p.mode == 2 && p.out_status[q] != 0) return;     // pass 1 already reported the overflow
-
-  extern __shared__ uint8_t smem_raw[];
-  u64* keys = reinterpret_cast<u64*>(smem_raw);                    // [MAXC]  (aliases the hash table, used after the BFS)
-  u32* table = reinterpret_cast<u32*>(smem_raw);                   // [HASH] u32
-  u32* cand = reinterpret_cast<u32*>(smem_raw + MAXC * 8);         // [MAXC] node ids
-  float* cosv = reinterpret_cast<float*>(cand + MAXC);             // [MAXC]
-  uint8_t* dist = reinterpret_cast<uint8_t*>(cosv + MAXC);         // [MAXC]
-  float* qs = reinterpret_cast<float*>(dist + MAXC);               // [D]
-  u64* sk = reinterpret_cast<u64*>(qs + ((p.D + 1) & ~1));         // [kp2]
-  __shared__ int s_count, s_overflow, s_remaining, s_nout, s_done;
-  __shared__ u32 s_wsum[EXP_WARPS];
-  __shared__ unsigned long long s_wwide[EXP_WARPS];
-  __shared__ float s_red[4][EXP_WARPS];
-  __shared__ double s_qn[EXP_WARPS];
-  __shared__ u32 hist[256];
-  __shared__ u64 s_prefix;
-
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  u32* table = reinterpret_cast<u32*>(smem_raw);                                  // [HASH]
+  u32* cand = table + HASH;                                                       // [MAXC] node ids in BFS order
+  long long* f_e0 = reinterpret_cast<long long*>(cand + MAXC);                    // [EXP_FB] first edge of a frontier node
+  u32* f_pre = reinterpret_cast<u32*>(f_e0 + EXP_FB);                             // [EXP_FB + 1] exclusive edge offsets
+  __shared__ int s_count, s_overflow;
+  __shared__ u32 s_wsum[BFS_WARPS];
+  __shared__ unsigned long long s_wwide[BFS_WARPS];
+  __shared__ double s_qn[BFS_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  int ncand = 0;
-  float qinv = 1.0f;
-  if (p.mode != 2) {
-  for (int i = tid; i < HASH; i += EXP_THREADS) table[i] = EXP_EMPTY;
-  if (tid == 0) { s_count = 0; s_overflow = 0; }
-  // query -> fp32 in smem, and its norm
-  const QT* Qp = reinterpret_cast<const QT*>(p.Q) + (size_t)q * p.D;
-  double qn = 0.0;
-  for (int d = tid; d < p.D; d += EXP_THREADS) {
-    const float v = q_to_float<QT>(Qp[d]);
-    qs[d] = v;
-    qn += (double)v * (double)v;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(kFullMask, qn, o);
-  if (lane == 0) s_qn[warp] = qn;
-  __syncthreads();
-  double qn_tot = 0.0;
-  for (int w = 0; w < EXP_WARPS; ++w) qn_tot += s_qn[w];
-  qinv = (p.metric == B200R_COS) ? (qn_tot > 0.0 ? (float)(1.0 / sqrt(qn_tot)) : 0.0f) : 1.0f;
-
-  // ---- level 0: seeds ---------------------------------------------------------------------------
-  for (int i = tid; i < p.S; i += EXP_THREADS) {
-    const long long s = p.seeds[(size_t)q * p.S + i];   // node id == global corpus row id
-    if (s >= 0 && s < p.V) {
-      if (hash_insert<HASH>(table, (u32)s)) {
-        const int pos = atomicAdd(&s_count, 1);
-        if (pos < MAXC) { cand[pos] = (u32)s; dist[pos] = 0; } else s_overflow = 1;
-      }
+  for (int q = blockIdx.x; q < p.B; q += gridDim.x) {
+    if (RETRY_PASS && p.out_status[q] != kStatusRetry) continue;      // block-uniform
+    __syncthreads();                                                  // the previous query of this CTA is done with smem
+    for (int i = tid; i < HASH; i += BFS_THREADS) table[i] = EXP_EMPTY;
+    if (tid == 0) { s_count = 0; s_overflow = 0; }
+    // the query's inverse norm (the re-score kernel multiplies by it)
+    const QT* Qp = reinterpret_cast<const QT*>(p.Q) + (size_t)q * p.D;
+    double qn = 0.0;
+    for (int d = tid; d < p.D; d += BFS_THREADS) {
+      const float v = q_to_float<QT>(Qp[d]);
+      qn += (double)v * (double)v;
     }
-  }
-  __syncthreads();
-
-  // ---- levels 1..window: edge-parallel expansion ----------------------------------------------------
-  // A level is expanded in batches of EXP_FB frontier nodes: (1) every node's adjacency range (row_ptr) is read at
-  // once, (2) a block scan turns the degrees into edge offsets, (3) the batch's edges are flattened over all 512
-  // threads (binary search of the offsets), EXP_EU col_idx loads in flight per thread, consecutive threads on
-  // consecutive edges.  A level therefore costs ~2 memory latencies whatever the degree distribution (hubs included).
-  // The scratch lives in the cosine array, which is not written before the re-score.
-  long long* f_e0 = reinterpret_cast<long long*>(cosv);               // [EXP_FB]
-  u32* f_pre = reinterpret_cast<u32*>(cosv) + 2 * EXP_FB;             // [EXP_FB + 1] exclusive edge offsets
-  int level_begin = 0;
-  for (int d = 1; d <= p.window; ++d) {
-    const int level_end = min(s_count, MAXC);
-    __syncthreads();                      // everyone has read s_count before the level appends to it
-    if (level_end == level_begin || s_overflow) break;  // block-uniform
-    const uint8_t dd = (uint8_t)min(d, 255);
-    for (int b0 = level_begin; b0 < level_end; b0 += EXP_FB) {
-      const int nb = min(EXP_FB, level_end - b0);
-      // (1) adjacency ranges, two consecutive frontier nodes per thread
-      u32 deg[2] = {0u, 0u};
-      unsigned long long wide = 0;
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int f = 2 * tid + r;
-        if (f < nb) {
-          const u32 u = cand[b0 + f];
-          const long long e0 = __ldg(p.row_ptr + u), e1 = __ldg(p.row_ptr + u + 1);
-          const long long dl = e1 > e0 ? e1 - e0 : 0;
-          f_e0[f] = e0;
-          deg[r] = (u32)min(dl, (long long)0x7fffffff);
-          wide += (unsigned long long)dl;
+    for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(kFullMask, qn, o);
+    if (lane == 0) s_qn[warp] = qn;
+    __syncthreads();
+    if (tid == 0) {
+      double qn_tot = 0.0;
+      for (int w = 0; w < BFS_WARPS; ++w) qn_tot += s_qn[w];
+      p.ws.qinv[q] = (p.metric == B200R_COS) ? (qn_tot > 0.0 ? (float)(1.0 / sqrt(qn_tot)) : 0.0f) : 1.0f;
+    }
+    uint8_t* dist_out = p.ws.dist + (size_t)q * EXP_MAXC_BIG;
+
+    // ---- level 0: seeds ---------------------------------------------------------------------------
+    for (int i = tid; i < p.S; i += BFS_THREADS) {
+      const long long s = p.seeds[(size_t)q * p.S + i];   // node id == global corpus row id
+      if (s >= 0 && s < p.V) {
+        if (hash_insert<HASH>(table, (u32)s)) {
+          const int pos = atomicAdd(&s_count, 1);
+          if (pos < MAXC) cand[pos] = (u32)s; else s_overflow = 1;
         }
       }
-      // (2) block exclusive scan of the degrees (and a 64-bit total to catch a batch with >= 2^31 edges)
-      u32 incl = deg[0] + deg[1];
+    }
+    __syncthreads();
+    for (int c = tid; c < min(s_count, MAXC); c += BFS_THREADS) dist_out[c] = 0;
+
+    // ---- levels 1..window: edge-parallel expansion, EXP_FB frontier nodes per batch ------------------
+    int level_begin = 0;
+    for (int d = 1; d <= p.window; ++d) {
+      const int level_end = min(s_count, MAXC);
+      __syncthreads();                      // everyone has read s_count before the level appends to it
+      if (level_end == level_begin || s_overflow) break;  // block-uniform
+      for (int b0 = level_begin; b0 < level_end; b0 += EXP_FB) {
+        const int nb = min(EXP_FB, level_end - b0);
+        // (1) adjacency ranges, two consecutive frontier nodes per thread
+        u32 deg[2] = {0u, 0u};
+        unsigned long long wide = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 t = __shfl_up_sync(kFullMask, incl, o);
-        if (lane >= o) incl += t;
-      }
+        for (int r = 0; r < 2; ++r) {
+          const int f = 2 * tid + r;
+          if (f < nb) {
+            const u32 u = cand[b0 + f];
+            const long long e0 = __ldg(p.row_ptr + u), e1 = __ldg(p.row_ptr + u + 1);
+            const long long dl = e1 > e0 ? e1 - e0 : 0;
+            f_e0[f] = e0;
+            deg[r] = (u32)min(dl, (long long)0x7fffffff);
+            wide += (unsigned long long)dl;
+          }
+        }
+        // (2) block exclusive scan of the degrees (and a 64-bit total to catch a batch with >= 2^31 edges)
+        u32 incl = deg[0] + deg[1];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) wide += __shfl_xor_sync(kFullMask, wide, o);
-      if (lane == 31) s_wsum[warp] = incl;
-      if (lane == 0) s_wwide[warp] = wide;
-      __syncthreads();
-      u32 base = 0, total = 0;
-      unsigned long long total_wide = 0;
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 t = __shfl_up_sync(kFullMask, incl, o);
+          if (lane >= o) incl += t;
+        }
 #pragma unroll
-      for (int w = 0; w < EXP_WARPS; ++w) {
-        const u32 ws = s_wsum[w];
-        if (w < warp) base += ws;
-        total += ws;
-        total_wide += s_wwide[w];
-      }
-      if (total_wide > 0x7fffffffull) { if (tid == 0) s_overflow = 1; total = 0; }   // block-uniform
-      const u32 excl = base + incl - (deg[0] + deg[1]);
-      if (2 * tid < nb) f_pre[2 * tid] = excl;
-      if (2 * tid + 1 < nb) f_pre[2 * tid + 1] = excl + deg[0];
-      if (tid == 0) f_pre[nb] = total;
-      __syncthreads();
-      // (3) the batch's edges, flattened
-      for (u32 eb = 0; eb < total; eb += EXP_THREADS * EXP_EU) {
-        u32 v[EXP_EU];
+        for (int o = 16; o > 0; o >>= 1) wide += __shfl_xor_sync(kFullMask, wide, o);
+        if (lane == 31) s_wsum[warp] = incl;
+        if (lane == 0) s_wwide[warp] = wide;
+        __syncthreads();
+        u32 base = 0, total = 0;
+        unsigned long long total_wide = 0;
 #pragma unroll
-        for (int r = 0; r < EXP_EU; ++r) {
-          const u32 e = eb + (u32)r * EXP_THREADS + (u32)tid;
-          v[r] = EXP_EMPTY;
-          if (e < total) {
-            int lo = 0, hi = nb;              // largest node with f_pre[node] <= e
-            while (hi - lo > 1) {
-              const int mid = (lo + hi) >> 1;
-              if (f_pre[mid] <= e) lo = mid; else hi = mid;
+        for (int w = 0; w < BFS_WARPS; ++w) {
+          const u32 ws = s_wsum[w];
+          if (w < warp) base += ws;
+          total += ws;
+          total_wide += s_wwide[w];
+        }
+        if (total_wide > 0x7fffffffull) { if (tid == 0) s_overflow = 1; total = 0; }   // block-uniform
+        const u32 excl = base + incl - (deg[0] + deg[1]);
+        if (2 * tid < nb) f_pre[2 * tid] = excl;
+        if (2 * tid + 1 < nb) f_pre[2 * tid + 1] = excl + deg[0];
+        if (tid == 0) f_pre[nb] = total;
+        __syncthreads();
+        // (3) the batch's edges, flattened over the CTA
+        for (u32 eb = 0; eb < total; eb += BFS_THREADS * EXP_EU) {
+          u32 v[EXP_EU];
+#pragma unroll
+          for (int r = 0; r < EXP_EU; ++r) {
+            const u32 e = eb + (u32)r * BFS_THREADS + (u32)tid;
+            v[r] = EXP_EMPTY;
+            if (e < total) {
+              int lo = 0, hi = nb;              // largest node with f_pre[node] <= e
+              while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (f_pre[mid] <= e) lo = mid; else hi = mid;
+              }
+              v[r] = (u32)__ldg(p.col_idx + f_e0[lo] + (long long)(e - f_pre[lo]));
             }
-            v[r] = (u32)__ldg(p.col_idx + f_e0[lo] + (long long)(e - f_pre[lo]));
           }
-        }
 #pragma unroll
-        for (int r = 0; r < EXP_EU; ++r) {
-          if (eb + (u32)r * EXP_THREADS >= total) break;        // block-uniform
-          const u32 peers = __match_any_sync(kFullMask, v[r]);
-          const bool leader = v[r] != EXP_EMPTY && (lane == __ffs(peers) - 1);
-          if (leader && !*(volatile int*)&s_overflow && hash_insert<HASH>(table, v[r])) {
-            const int pos = atomicAdd(&s_count, 1);
-            if (pos < MAXC) { cand[pos] = v[r]; dist[pos] = dd; } else s_overflow = 1;
+          for (int r = 0; r < EXP_EU; ++r) {
+            if (eb + (u32)r * BFS_THREADS >= total) break;        // block-uniform
+            const u32 peers = __match_any_sync(kFullMask, v[r]);
+            const bool leader = v[r] != EXP_EMPTY && (lane == __ffs(peers) - 1);
+            if (leader && !*(volatile int*)&s_overflow && hash_insert<HASH>(table, v[r])) {
+              const int pos = atomicAdd(&s_count, 1);
+              if (pos < MAXC) cand[pos] = v[r]; else s_overflow = 1;
+            }
           }
         }
+        __syncthreads();                    // the scratch is reused by the next batch
       }
-      __syncthreads();                    // the scratch is reused by the next batch
+      // the nodes this level appended are at hop distance d
+      const uint8_t dd = (uint8_t)min(d, 255);
+      for (int c = level_end + tid; c < min(s_count, MAXC); c += BFS_THREADS) dist_out[c] = dd;
+      level_begin = level_end;
     }
-    level_begin = level_end;
-  }
-  __syncthreads();
-  ncand = min(s_count, MAXC);
-  if (s_overflow) {  // block-uniform
-    if (tid == 0) { p.out_status[q] = (MAXC < EXP_MAXC_BIG) ? kStatusRetry : B200R_EOVERFLOW; p.out_ncand[q] = s_count; }
-    for (int i = tid; i < p.k; i += EXP_THREADS) {
-      const size_t o = (size_t)q * p.k + i;
-      p.out_scores[o] = -CUDART_INF_F; p.out_ids[o] = -1; p.out_hops[o] = -1; p.out_gn[o] = 0; p.out_dn[o] = 0; p.out_cos[o] = 0;
+    __syncthreads();
+    const int ncand = min(s_count, MAXC);
+    if (s_overflow) {  // block-uniform
+      if (tid == 0) {
+        p.out_status[q] = (MAXC < EXP_MAXC_BIG) ? kStatusRetry : B200R_EOVERFLOW;
+        p.out_ncand[q] = s_count;
+        p.ws.ncand[q] = 0;
+      }
+      fill_no_result(p, q);
+      continue;
     }
-    return;
+    u32* cand_out = p.ws.cand + (size_t)q * EXP_MAXC_BIG;
+    for (int c = tid; c < ncand; c += BFS_THREADS) cand_out[c] = cand[c];
+    if (tid == 0) {
+      p.ws.ncand[q] = ncand;
+      p.out_ncand[q] = ncand;
+      p.out_status[q] = 0;
+      p.ws.mm[2 * q] = 0xffffffffu;       // "no owned candidate yet": min image > max image
+      p.ws.mm[2 * q + 1] = 0u;
+      const u32 groups = (u32)((ncand + GATHER_ROWS - 1) / GATHER_ROWS);
+      const u64 old = atomicAdd(p.ws.counter, (1ull << 32) | (u64)groups);
+      p.ws.seg_start[old >> 32] = (u32)old;
+      p.ws.seg_q[old >> 32] = (u32)q;
+    }
   }
+}
 
-  // ---- re-score: one warp per EXP_ROWS candidate rows, their loads in flight together ---------------
+// ------------------------------------------------------------------------------------------------ K3b
+template <typename T>
+__global__ void __launch_bounds__(GATHER_MAX_WARPS * 32, GATHER_CTAS_PER_SM) rescore_gather_kernel(const ExpandParams p, const int dpad) {
+  typedef typename QueryType<T>::type QT;
+  constexpr int VEC = ElemTraits<T>::kVec;
+  constexpr int ROWS = GATHER_ROWS;
+  extern __shared__ __align__(16) float qs_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
+  float* qs = qs_all + (size_t)warp * dpad;          // this warp's current query, fp32
+
+  const u64 packed = *p.ws.counter;
+  const int nseg = (int)(packed >> 32);
+  const u32 total = (u32)packed;
+  const u64 W = (u64)gridDim.x * warps_per_cta, w = (u64)blockIdx.x * warps_per_cta + warp;
+  const u32 g_lo = (u32)((u64)total * w / W), g_hi = (u32)((u64)total * (w + 1) / W);
+  if (g_lo >= g_hi) return;
+
+  // the reservation that contains group g_lo: the last one that starts at or before it (empty ones share a start)
+  int seg = 0;
+  {
+    int lo = 0, hi = nseg;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(p.ws.seg_start + mid) <= g_lo) lo = mid; else hi = mid;
+    }
+    seg = lo;
+  }
+  u32 seg_begin = __ldg(p.ws.seg_start + seg);
+  u32 seg_end = (seg + 1 < nseg) ? __ldg(p.ws.seg_start + seg + 1) : total;
+
   const uint8_t* Xb = reinterpret_cast<const uint8_t*>(p.X);
   const int chunks = p.D / VEC;
   const size_t row_bytes = (size_t)p.D * sizeof(T);
-  for (int c0 = warp * EXP_ROWS; c0 < ncand; c0 += EXP_WARPS * EXP_ROWS) {
-    const uint8_t* rp[EXP_ROWS];
-    bool have[EXP_ROWS];
-    float acc[EXP_ROWS];
+  int q = -1, ncand = 0;
+  float qinv = 1.0f, cmin = CUDART_INF_F, cmax = -CUDART_INF_F;
+
+  auto flush_minmax = [&]() {
 #pragma unroll
-    for (int r = 0; r < EXP_ROWS; ++r) {
-      const int c = min(c0 + r, ncand - 1);
-      const long long node = (long long)cand[c];
+    for (int o = 16; o > 0; o >>= 1) {
+      cmin = fminf(cmin, __shfl_xor_sync(kFullMask, cmin, o));
+      cmax = fmaxf(cmax, __shfl_xor_sync(kFullMask, cmax, o));
+    }
+    if (lane == 0 && cmin <= cmax) {
+      atomicMin(p.ws.mm + 2 * q, f32_to_ordered(cmin));
+      atomicMax(p.ws.mm + 2 * q + 1, f32_to_ordered(cmax));
+    }
+    cmin = CUDART_INF_F; cmax = -CUDART_INF_F;
+  };
+  auto load_query = [&]() {
+    q = (int)__ldg(p.ws.seg_q + seg);
+    ncand = p.ws.ncand[q];
+    qinv = p.ws.qinv[q];
+    const QT* Qp = reinterpret_cast<const QT*>(p.Q) + (size_t)q * p.D;
+    __syncwarp();
+    for (int d = lane; d < p.D; d += 32) qs[d] = q_to_float<QT>(Qp[d]);
+    __syncwarp();
+  };
+  load_query();
+
+  for (u32 g = g_lo; g < g_hi; ++g) {
+    if (g >= seg_end) {                       // warp-uniform: next (non-empty) reservation
+      flush_minmax();
+      do {
+        ++seg;
+        seg_begin = seg_end;
+        seg_end = (seg + 1 < nseg) ? __ldg(p.ws.seg_start + seg + 1) : total;
+      } while (g >= seg_end);
+      load_query();
+    }
+    const int c0 = (int)(g - seg_begin) * ROWS;
+    // lane r < ROWS owns row r of the group: its node id, ownership and row multiplier (fetched with the rows, so its
+    // latency is hidden behind them)
+    long long my_row = 0;
+    bool my_valid = false, my_own = false, my_have = false;
+    float my_mult = 0.0f;
+    if (lane < ROWS && c0 + lane < ncand) {
+      const long long node = (long long)__ldg(p.ws.cand + (size_t)q * EXP_MAXC_BIG + c0 + lane);
       const long long row = node - p.id_base;
-      have[r] = (c0 + r < ncand) && node >= p.own_lo && node < p.own_hi && row >= 0 && row < p.N;
-      rp[r] = Xb + (size_t)(have[r] ? row : 0) * row_bytes;
+      my_valid = true;
+      my_own = node >= p.own_lo && node < p.own_hi;
+      my_have = my_own && row >= 0 && row < p.N;
+      if (my_have) { my_row = row; my_mult = p.row_mult ? __ldg(p.row_mult + row) : 1.0f; }
+    }
+    const uint8_t* rp[ROWS];
+    float acc[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      rp[r] = Xb + (size_t)__shfl_sync(kFullMask, my_row, r) * row_bytes;     // a row this rank does not hold reads row 0
       acc[r] = 0.0f;
     }
-    // lane r fetches row r's multiplier together with the rows (not after the reduction, where its latency would be exposed)
-    float mult = 0.0f;
-    if (lane < EXP_ROWS && c0 + lane < ncand) {
-      const long long node = (long long)cand[c0 + lane];
-      const long long row = node - p.id_base;
-      if (node >= p.own_lo && node < p.own_hi && row >= 0 && row < p.N) mult = p.row_mult ? __ldg(p.row_mult + row) : 1.0f;
-    }
     for (int chunk = lane; chunk < chunks; chunk += 32) {
-      uint4 xv[EXP_ROWS];
+      uint4 xv[ROWS];
 #pragma unroll
-      for (int r = 0; r < EXP_ROWS; ++r) xv[r] = ld_stream_16B(rp[r] + (size_t)chunk * 16);
+      for (int r = 0; r < ROWS; ++r) xv[r] = ld_stream_16B(rp[r] + (size_t)chunk * 16);
       const float* qc = qs + chunk * VEC;
 #pragma unroll
-      for (int r = 0; r < EXP_ROWS; ++r) {
+      for (int r = 0; r < ROWS; ++r) {
         float xf[VEC];
         ElemTraits<T>::unpack(xv[r], xf);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) acc[r] = fmaf(xf[e], qc[e], acc[r]);
       }
     }
+    float mine = 0.0f;
 #pragma unroll
-    for (int r = 0; r < EXP_ROWS; ++r) {
+    for (int r = 0; r < ROWS; ++r) {
       float a = acc[r];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFullMask, a, o);
-      const float m = __shfl_sync(kFullMask, mult, r);
-      if (lane == 0 && c0 + r < ncand) cosv[c0 + r] = (a * m) * qinv + 0.0f;
+      if (lane == r) mine = a;
+    }
+    if (my_valid) {
+      const float v = my_have ? (mine * my_mult) * qinv + 0.0f : 0.0f;
+      p.ws.cos[(size_t)q * EXP_MAXC_BIG + c0 + lane] = v;
+      if (my_own) { cmin = fminf(cmin, v); cmax = fmaxf(cmax, v); }
     }
   }
-  __syncthreads();
-  } else {
-    // pass 2: candidates, hops and cosines were parked by pass 1
-    ncand = p.ws_ncand[q];
-    for (int c = tid; c < ncand; c += EXP_THREADS) {
-      cand[c] = p.ws_cand[(size_t)q * EXP_MAXC_BIG + c];
-      cosv[c] = p.ws_cos[(size_t)q * EXP_MAXC_BIG + c];
-      dist[c] = p.ws_dist[(size_t)q * EXP_MAXC_BIG + c];
+  flush_minmax();
+}
+
+// mode 1: the host all-reduces float (min, max) pairs
+__global__ void minmax_decode_kernel(const u32* __restrict__ mm, float* __restrict__ minmax, const int* __restrict__ status, int B) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= B) return;
+  const bool any = status[q] == 0 && mm[2 * q] <= mm[2 * q + 1];
+  minmax[2 * q] = any ? ordered_to_f32(mm[2 * q]) : CUDART_INF_F;
+  minmax[2 * q + 1] = any ? ordered_to_f32(mm[2 * q + 1]) : -CUDART_INF_F;
+}
+
+// ------------------------------------------------------------------------------------------------ K3c
+static size_t select_smem_bytes(int maxc, int kp2) { return (size_t)maxc * 8 + (size_t)maxc * 4 + (size_t)kp2 * 8; }
+
+template <int MAXC>
+__global__ void __launch_bounds__(SEL_THREADS) fuse_select_kernel(const ExpandParams p) {
+  constexpr bool BIG = (MAXC == EXP_MAXC_BIG);
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  u64* keys = reinterpret_cast<u64*>(smem_raw);                    // [MAXC]
+  u64* sk = keys + MAXC;                                           // [kp2]
+  u32* cand = reinterpret_cast<u32*>(sk + p.kp2);                  // [MAXC]
+  __shared__ int s_remaining, s_nout, s_done;
+  __shared__ float s_red[2][SEL_WARPS];
+  __shared__ u32 hist[256];
+  __shared__ u64 s_prefix;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int q = blockIdx.x; q < p.B; q += gridDim.x) {
+    if (p.out_status[q] != 0) continue;                            // overflow was reported by the BFS (block-uniform)
+    const int ncand = p.ws.ncand[q];
+    if (BIG != (ncand > EXP_MAXC_SMALL)) continue;                 // the other instantiation ranks this query
+    __syncthreads();
+    const u32* cand_in = p.ws.cand + (size_t)q * EXP_MAXC_BIG;
+    const float* cos_in = p.ws.cos + (size_t)q * EXP_MAXC_BIG;
+    const uint8_t* dist_in = p.ws.dist + (size_t)q * EXP_MAXC_BIG;
+
+    // ---- min/max of both channels (retrieval_backend.py:296-301) ----------------------------------
+    float gmin = CUDART_INF_F, gmax = -CUDART_INF_F;
+    for (int c = tid; c < ncand; c += SEL_THREADS) {
+      cand[c] = cand_in[c];
+      const float gv = hop_decay(dist_in[c]);
+      gmin = fminf(gmin, gv); gmax = fmaxf(gmax, gv);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      gmin = fminf(gmin, __shfl_xor_sync(kFullMask, gmin, o)); gmax = fmaxf(gmax, __shfl_xor_sync(kFullMask, gmax, o));
+    }
+    if (lane == 0) { s_red[0][warp] = gmin; s_red[1][warp] = gmax; }
+    if (tid == 0) { s_prefix = 0; s_remaining = p.k; s_nout = 0; s_done = 0; }
+    for (int i = tid; i < p.kp2; i += SEL_THREADS) sk[i] = 0;
+    __syncthreads();
+    for (int w = 0; w < SEL_WARPS; ++w) { gmin = fminf(gmin, s_red[0][w]); gmax = fmaxf(gmax, s_red[1][w]); }
+    float cmin, cmax;
+    if (p.mode == 2) {
+      cmin = p.minmax[2 * q]; cmax = p.minmax[2 * q + 1];          // all-reduced across the ranks
+    } else {
+      const u32 lo = p.ws.mm[2 * q], hi = p.ws.mm[2 * q + 1];
+      cmin = lo <= hi ? ordered_to_f32(lo) : CUDART_INF_F;
+      cmax = lo <= hi ? ordered_to_f32(hi) : -CUDART_INF_F;
+    }
+    const bool c_flat = !(cmax > cmin), g_flat = !(gmax > gmin);   // "vmax <= vmin -> all 0.0" (:300)
+    const float c_den = c_flat ? 1.0f : (cmax - cmin), g_den = g_flat ? 1.0f : (gmax - gmin);
+
+    // ---- fused keys ---------------------------------------------------------------------------------
+    for (int c = tid; c < ncand; c += SEL_THREADS) {
+      const float dn = c_flat ? 0.0f : (cos_in[c] - cmin) / c_den;
+      const float gn = g_flat ? 0.0f : (hop_decay(dist_in[c]) - gmin) / g_den;
+      const long long node = (long long)cand[c];
+      const bool own = node >= p.own_lo && node < p.own_hi;
+      keys[c] = own ? make_key(p.alpha_graph * gn + p.alpha_dense * dn, cand[c]) : 0ull;   // ties on the fused score -> lower node id
     }
     __syncthreads();
-  }
 
-  // ---- min/max of both channels (retrieval_backend.py:296-301) ----------------------------------
-  float cmin = CUDART_INF_F, cmax = -CUDART_INF_F, gmin = CUDART_INF_F, gmax = -CUDART_INF_F;
-  for (int c = tid; c < ncand; c += EXP_THREADS) {
-    const float cv = cosv[c], gv = hop_decay(dist[c]);
-    const long long node = (long long)cand[c];
-    if (node >= p.own_lo && node < p.own_hi) { cmin = fminf(cmin, cv); cmax = fmaxf(cmax, cv); }
-    gmin = fminf(gmin, gv); gmax = fmaxf(gmax, gv);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    cmin = fminf(cmin, __shfl_xor_sync(kFullMask, cmin, o)); cmax = fmaxf(cmax, __shfl_xor_sync(kFullMask, cmax, o));
-    gmin = fminf(gmin, __shfl_xor_sync(kFullMask, gmin, o)); gmax = fmaxf(gmax, __shfl_xor_sync(kFullMask, gmax, o));
-  }
-  if (lane == 0) { s_red[0][warp] = cmin; s_red[1][warp] = cmax; s_red[2][warp] = gmin; s_red[3][warp] = gmax; }
-  __syncthreads();
-  for (int w = 0; w < EXP_WARPS; ++w) {
-    cmin = fminf(cmin, s_red[0][w]); cmax = fmaxf(cmax, s_red[1][w]);
-    gmin = fminf(gmin, s_red[2][w]); gmax = fmaxf(gmax, s_red[3][w]);
-  }
-  if (p.mode == 1) {
-    // park this rank's share; the host all-reduces ws_minmax (min, max) across ranks before pass 2
-    for (int c = tid; c < ncand; c += EXP_THREADS) {
-      p.ws_cand[(size_t)q * EXP_MAXC_BIG + c] = cand[c];
-      p.ws_cos[(size_t)q * EXP_MAXC_BIG + c] = cosv[c];
-      p.ws_dist[(size_t)q * EXP_MAXC_BIG + c] = dist[c];
-    }
-    if (tid == 0) { p.ws_ncand[q] = ncand; p.ws_minmax[2 * q] = cmin; p.ws_minmax[2 * q + 1] = cmax; p.out_ncand[q] = ncand; p.out_status[q] = 0; }
-    return;
-  }
-  if (p.mode == 2) { cmin = p.ws_minmax[2 * q]; cmax = p.ws_minmax[2 * q + 1]; }
-  const bool c_flat = !(cmax > cmin), g_flat = !(gmax > gmin);   // "vmax <= vmin -> all 0.0" (:300)
-  const float c_den = c_flat ? 1.0f : (cmax - cmin), g_den = g_flat ? 1.0f : (gmax - gmin);
-
-  // ---- fused keys (the hash table is dead now; its memory becomes the key array) ------------------
-  for (int c = tid; c < ncand; c += EXP_THREADS) {
-    const float dn = c_flat ? 0.0f : (cosv[c] - cmin) / c_den;
-    const float gn = g_flat ? 0.0f : (hop_decay(dist[c]) - gmin) / g_den;
-    const long long node = (long long)cand[c];
-    const bool own = node >= p.own_lo && node < p.own_hi;
-    keys[c] = own ? make_key(p.alpha_graph * gn + p.alpha_dense * dn, cand[c]) : 0ull;   // ties on the fused score -> lower node id
-  }
-  if (tid == 0) { s_prefix = 0; s_remaining = p.k; s_nout = 0; s_done = 0; }
-  for (int i = tid; i < p.kp2; i += EXP_THREADS) sk[i] = 0;
-  __syncthreads();
-
-  // ---- exact k-th key by radix select, then sort the winners ------------------------------------------
-  u64 kth = 0;
-  if (ncand > p.k) {
-    for (int pass = 7; pass >= 0; --pass) {
-      const int shift = pass * 8;
-      for (int i = tid; i < 256; i += EXP_THREADS) hist[i] = 0;
-      __syncthreads();
-      const u64 prefix = s_prefix;
-      const u64 hi_mask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
-      for (int base = warp * 32; base < ncand; base += EXP_THREADS) {
-        const int i = base + lane;
-        const bool active = i < ncand;
-        const u64 key = active ? keys[i] : 0ull;
-        const bool m = active && (key & hi_mask) == prefix;
-        const u32 dgt = m ? ((u32)(key >> shift) & 255u) : 0xffffffffu;
-        const u32 peers = __match_any_sync(kFullMask, dgt);
-        if (m && lane == __ffs(peers) - 1) atomicAdd(&hist[dgt], (u32)__popc(peers));
-      }
-      __syncthreads();
-      if (tid < 32) {
-        const int remaining = s_remaining;
-        u32 c[8]; u32 lane_sum = 0;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) { c[b] = hist[lane * 8 + b]; lane_sum += c[b]; }
-        u32 suffix = lane_sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const u32 t = __shfl_down_sync(kFullMask, suffix, o);
-          if (lane + o < 32) suffix += t;
+    // ---- exact k-th key by radix select, then sort the winners ------------------------------------------
+    u64 kth = 0;
+    if (ncand > p.k) {
+      for (int pass = 7; pass >= 0; --pass) {
+        const int shift = pass * 8;
+        for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
+        __syncthreads();
+        const u64 prefix = s_prefix;
+        const u64 hi_mask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
+        for (int base = warp * 32; base < ncand; base += SEL_THREADS) {
+          const int i = base + lane;
+          const bool active = i < ncand;
+          const u64 key = active ? keys[i] : 0ull;
+          const bool m = active && (key & hi_mask) == prefix;
+          const u32 dgt = m ? ((u32)(key >> shift) & 255u) : 0xffffffffu;
+          const u32 peers = __match_any_sync(kFullMask, dgt);
+          if (m && lane == __ffs(peers) - 1) atomicAdd(&hist[dgt], (u32)__popc(peers));
         }
-        const u32 above = suffix - lane_sum;
-        if (above < (u32)remaining && (u32)remaining <= suffix) {
-          u32 run = above;
+        __syncthreads();
+        if (tid < 32) {
+          const int remaining = s_remaining;
+          u32 c[8]; u32 lane_sum = 0;
 #pragma unroll
-          for (int b = 7; b >= 0; --b) {
-            if (run + c[b] >= (u32)remaining) {
-              s_prefix = prefix | ((u64)(u32)(lane * 8 + b) << shift);
-              s_remaining = remaining - (int)run;
-              // every key of this bucket is a winner: the bucket's lowest possible key is a valid k-th key, stop refining
-              if (c[b] == (u32)remaining - run) s_done = 1;
-              break;
+          for (int b = 0; b < 8; ++b) { c[b] = hist[lane * 8 + b]; lane_sum += c[b]; }
+          u32 suffix = lane_sum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_down_sync(kFullMask, suffix, o);
+            if (lane + o < 32) suffix += t;
+          }
+          const u32 above = suffix - lane_sum;
+          if (above < (u32)remaining && (u32)remaining <= suffix) {
+            u32 run = above;
+#pragma unroll
+            for (int b = 7; b >= 0; --b) {
+              if (run + c[b] >= (u32)remaining) {
+                s_prefix = prefix | ((u64)(u32)(lane * 8 + b) << shift);
+                s_remaining = remaining - (int)run;
+                // every key of this bucket is a winner: the bucket's lowest possible key is a valid k-th key, stop refining
+                if (c[b] == (u32)remaining - run) s_done = 1;
+                break;
+              }
+              run += c[b];
             }
-            run += c[b];
           }
         }
+        __syncthreads();
+        if (s_done) break;      // block-uniform
       }
-      __syncthreads();
-      if (s_done) break;      // block-uniform
+      kth = s_prefix;
     }
-    kth = s_prefix;
-  }
-  for (int i = tid; i < ncand; i += EXP_THREADS) {
-    const u64 key = keys[i];
-    if (key >= kth && key != 0) {
-      const int pos = atomicAdd(&s_nout, 1);
-      if (pos < p.kp2) sk[pos] = key;
+    for (int i = tid; i < ncand; i += SEL_THREADS) {
+      const u64 key = keys[i];
+      if (key >= kth && key != 0) {
+        const int pos = atomicAdd(&s_nout, 1);
+        if (pos < p.kp2) sk[pos] = key;
+      }
     }
-  }
-  __syncthreads();
-  block_bitonic_desc(sk, p.kp2);
+    __syncthreads();
+    block_bitonic_desc(sk, p.kp2);
 
-  // ---- emit: winner i is looked up in the candidate list by one warp (k is small) ------------------
-  const int nwin = min(min(ncand, p.k), s_nout);
-  for (int i = warp; i < p.k; i += EXP_WARPS) {
-    const size_t o = (size_t)q * p.k + i;
-    if (i < nwin) {
-      const u64 key = sk[i];
-      const u32 node = key_id(key);
-      int slot = -1;
-      for (int base = 0; base < ncand && slot < 0; base += 32) {
-        const int c = base + lane;
-        const u32 hit = __ballot_sync(kFullMask, c < ncand && cand[c] == node);
-        if (hit) slot = base + __ffs(hit) - 1;
+    // ---- emit: winner i is looked up in the candidate list by one warp (k is small) ------------------
+    const int nwin = min(min(ncand, p.k), s_nout);
+    for (int i = warp; i < p.k; i += SEL_WARPS) {
+      const size_t o = (size_t)q * p.k + i;
+      if (i < nwin) {
+        const u64 key = sk[i];
+        const u32 node = key_id(key);
+        int slot = -1;
+        for (int base = 0; base < ncand && slot < 0; base += 32) {
+          const int c = base + lane;
+          const u32 hit = __ballot_sync(kFullMask, c < ncand && cand[c] == node);
+          if (hit) slot = base + __ffs(hit) - 1;
+        }
+        if (lane == 0) {
+          const float cv = cos_in[slot];
+          const int hd = dist_in[slot];
+          p.out_scores[o] = key_score(key);
+          p.out_ids[o] = (long long)node;
+          p.out_hops[o] = hd;
+          p.out_gn[o] = g_flat ? 0.0f : (hop_decay(hd) - gmin) / g_den;
+          p.out_dn[o] = c_flat ? 0.0f : (cv - cmin) / c_den;
+          p.out_cos[o] = cv;
+        }
+      } else if (lane == 0) {
+        p.out_scores[o] = -CUDART_INF_F; p.out_ids[o] = -1; p.out_hops[o] = -1; p.out_gn[o] = 0; p.out_dn[o] = 0; p.out_cos[o] = 0;
       }
-      if (lane == 0) {
-        const float cv = cosv[slot];
-        const int hd = dist[slot];
-        p.out_scores[o] = key_score(key);
-        p.out_ids[o] = (long long)node;
-        p.out_hops[o] = hd;
-        p.out_gn[o] = g_flat ? 0.0f : (hop_decay(hd) - gmin) / g_den;
-        p.out_dn[o] = c_flat ? 0.0f : (cv - cmin) / c_den;
-        p.out_cos[o] = cv;
-      }
-    } else if (lane == 0) {
-      p.out_scores[o] = -CUDART_INF_F; p.out_ids[o] = -1; p.out_hops[o] = -1; p.out_gn[o] = 0; p.out_dn[o] = 0; p.out_cos[o] = 0;
     }
   }
-  if (tid == 0) { p.out_ncand[q] = ncand; p.out_status[q] = 0; }
 }
 
 int32_t expand_max_candidates() { return EXP_MAXC_BIG; }
 
-template <typename T, int ROWS>
-static int launch_expand_r(const ExpandParams& p, cudaStream_t st) {
-  constexpr int SMALL = 4096;
-  auto smem_of = [&](int maxc) { return (size_t)maxc * 8 + (size_t)maxc * 4 * 2 + maxc + (size_t)((p.D + 1) & ~1) * 4 + (size_t)p.kp2 * 8; };
-  if (smem_of(EXP_MAXC_BIG) > 220 * 1024) { set_error("expand_rescore: D=%d / k=%d too large for shared memory", p.D, p.k); return B200R_EINVAL; }
-  if (p.mode != 2) {
-    B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, SMALL, false, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(SMALL)));
-    expand_rescore_kernel<T, SMALL, false, ROWS><<<p.B, EXP_THREADS, smem_of(SMALL), st>>>(p);
-    count_launch();
-    B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, EXP_MAXC_BIG, true, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(EXP_MAXC_BIG)));
-    expand_rescore_kernel<T, EXP_MAXC_BIG, true, ROWS><<<p.B, EXP_THREADS, smem_of(EXP_MAXC_BIG), st>>>(p);
-    count_launch();
-  } else {
-    B200R_CUDA_CHECK(cudaFuncSetAttribute(expand_rescore_kernel<T, EXP_MAXC_BIG, false, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(EXP_MAXC_BIG)));
-    expand_rescore_kernel<T, EXP_MAXC_BIG, false, ROWS><<<p.B, EXP_THREADS, smem_of(EXP_MAXC_BIG), st>>>(p);
-    count_launch();
-  }
-  B200R_CUDA_CHECK(cudaGetLastError());
+// ------------------------------------------------------------------------------------------------ host side
+template <typename QT>
+static int launch_bfs(const ExpandParams& p, cudaStream_t st) {
+  B200R_CUDA_CHECK(cudaFuncSetAttribute(bfs_kernel<QT, EXP_MAXC_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bfs_smem_bytes(EXP_MAXC_SMALL)));
+  bfs_kernel<QT, EXP_MAXC_SMALL><<<p.B, BFS_THREADS, bfs_smem_bytes(EXP_MAXC_SMALL), st>>>(p);
+  count_launch();
+  // persistent: only the queries that overflowed the small instantiation do any work
+  B200R_CUDA_CHECK(cudaFuncSetAttribute(bfs_kernel<QT, EXP_MAXC_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bfs_smem_bytes(EXP_MAXC_BIG)));
+  bfs_kernel<QT, EXP_MAXC_BIG><<<std::min(p.B, EXP_PERSISTENT_CTAS), BFS_THREADS, bfs_smem_bytes(EXP_MAXC_BIG), st>>>(p);
+  count_launch();
   return B200R_OK;
 }
 
-// 4 rows per warp measured best (2: 0.95x, 8: 0.87x -- fewer resident CTAs)
 template <typename T>
-static int launch_expand_t(const ExpandParams& p, cudaStream_t st) { return launch_expand_r<T, 4>(p, st); }
+static int launch_gather(const ExpandParams& p, cudaStream_t st) {
+  const int dpad = (p.D + 3) & ~3;
+  // A/B knobs (measurements only): B200R_GATHER_WARPS = warps per CTA, B200R_GATHER_CTAS = CTAs per SM
+  static const int env_warps = [] { const char* e = getenv("B200R_GATHER_WARPS"); return e ? atoi(e) : 0; }();
+  static const int env_ctas = [] { const char* e = getenv("B200R_GATHER_CTAS"); return e ? atoi(e) : 0; }();
+  const int max_warps = (env_warps >= 1 && env_warps <= GATHER_MAX_WARPS) ? env_warps : GATHER_MAX_WARPS;
+  const int ctas_per_sm = (env_ctas >= 1 && env_ctas <= 8) ? env_ctas : GATHER_CTAS_PER_SM;
+  int warps = (int)std::min<size_t>(max_warps, (96 * 1024) / ((size_t)dpad * 4));
+  if (warps < 1) {
+    if ((size_t)dpad * 4 > 200 * 1024) { set_error("expand_rescore: D=%d too large for shared memory", p.D); return B200R_EINVAL; }
+    warps = 1;
+  }
+  const size_t smem = (size_t)warps * dpad * 4;
+  B200R_CUDA_CHECK(cudaFuncSetAttribute(rescore_gather_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  profile_begin(st);
+  rescore_gather_kernel<T><<<kNumSMs * ctas_per_sm, warps * 32, smem, st>>>(p, dpad);
+  profile_end(st);
+  count_launch();
+  return B200R_OK;
+}
 
-size_t expand_workspace_bytes(int B) {
-  return align_up((size_t)B * EXP_MAXC_BIG * 4, 256) * 2 + align_up((size_t)B * EXP_MAXC_BIG, 256) + align_up((size_t)B * 4, 256);
+static int launch_select(const ExpandParams& p, cudaStream_t st) {
+  if (select_smem_bytes(EXP_MAXC_BIG, p.kp2) > 220 * 1024) { set_error("expand_rescore: k=%d too large for shared memory", p.k); return B200R_EINVAL; }
+  B200R_CUDA_CHECK(cudaFuncSetAttribute(fuse_select_kernel<EXP_MAXC_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_smem_bytes(EXP_MAXC_SMALL, p.kp2)));
+  fuse_select_kernel<EXP_MAXC_SMALL><<<p.B, SEL_THREADS, select_smem_bytes(EXP_MAXC_SMALL, p.kp2), st>>>(p);
+  count_launch();
+  B200R_CUDA_CHECK(cudaFuncSetAttribute(fuse_select_kernel<EXP_MAXC_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_smem_bytes(EXP_MAXC_BIG, p.kp2)));
+  fuse_select_kernel<EXP_MAXC_BIG><<<std::min(p.B, EXP_PERSISTENT_CTAS), SEL_THREADS, select_smem_bytes(EXP_MAXC_BIG, p.kp2), st>>>(p);
+  count_launch();
+  return B200R_OK;
+}
+
+template <typename T>
+static int launch_expand_t(const ExpandParams& p, cudaStream_t st) {
+  typedef typename QueryType<T>::type QT;
+  int rc = B200R_OK;
+  if (p.mode != 2) {
+    B200R_CUDA_CHECK(cudaMemsetAsync(p.ws.counter, 0, sizeof(u64), st));
+    if ((rc = launch_bfs<QT>(p, st)) != B200R_OK) return rc;
+    if ((rc = launch_gather<T>(p, st)) != B200R_OK) return rc;
+    if (p.mode == 1) {
+      minmax_decode_kernel<<<(p.B + 255) / 256, 256, 0, st>>>(p.ws.mm, p.minmax, p.out_status, p.B);
+      count_launch();
+    }
+  }
+  if (p.mode != 1 && (rc = launch_select(p, st)) != B200R_OK) return rc;
+  B200R_CUDA_CHECK(cudaGetLastError());
+  return B200R_OK;
 }
 
 int launch_expand_rescore(const Index* ix, const Graph* g, const void* Q, const int64_t* seeds, int B, int S, int window,
                           float alpha_dense, float alpha_graph, int k, float* out_scores, int64_t* out_ids, int32_t* out_hops,
                           float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand, int32_t* out_status, int mode,
                           int64_t own_lo, int64_t own_hi, void* ws, float* minmax, cudaStream_t st) {
+  if (B > (1 << 20)) { set_error("expand_rescore: at most %d queries per call", 1 << 20); return B200R_EINVAL; }
   ExpandParams p;
   p.X = ix->X; p.Q = Q; p.row_mult = ix->row_mult;
   p.row_ptr = reinterpret_cast<const long long*>(g->row_ptr); p.col_idx = g->col_idx;
@@ -471,15 +659,8 @@ int launch_expand_rescore(const Index* ix, const Graph* g, const void* Q, const 
   p.out_scores = out_scores; p.out_ids = reinterpret_cast<long long*>(out_ids); p.out_hops = out_hops;
   p.out_gn = out_gn; p.out_dn = out_dn; p.out_cos = out_cos; p.out_ncand = out_ncand; p.out_status = out_status;
   p.mode = mode; p.own_lo = own_lo; p.own_hi = own_hi;
-  p.ws_cand = nullptr; p.ws_cos = nullptr; p.ws_dist = nullptr; p.ws_ncand = nullptr; p.ws_minmax = minmax;
-  if (mode != 0) {
-    char* w = reinterpret_cast<char*>(ws);
-    const size_t a4 = align_up((size_t)B * EXP_MAXC_BIG * 4, 256);
-    p.ws_cand = reinterpret_cast<u32*>(w);
-    p.ws_cos = reinterpret_cast<float*>(w + a4);
-    p.ws_dist = reinterpret_cast<uint8_t*>(w + 2 * a4);
-    p.ws_ncand = reinterpret_cast<int*>(w + 2 * a4 + align_up((size_t)B * EXP_MAXC_BIG, 256));
-  }
+  p.minmax = minmax;
+  p.ws = carve_ws(ws, B);
   switch (ix->dtype) {
     case B200R_BF16: return launch_expand_t<__nv_bfloat16>(p, st);
     case B200R_F16: return launch_expand_t<__half>(p, st);

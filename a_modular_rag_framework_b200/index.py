@@ -224,9 +224,13 @@ def expand_rescore(index: DenseIndex, graph: PassageGraph, Q: torch.Tensor, seed
         "ncand": torch.empty((B,), dtype=torch.int32, device=dev),
         "status": torch.empty((B,), dtype=torch.int32, device=dev),
     }
+    lib = N.load()
+    # per-call scratch (parked candidate lists) from torch's caching allocator: stream-ordered, no sync
+    ws = torch.empty(int(lib.b200r_expand_workspace_bytes(B)), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        N.check(N.load().b200r_expand_rescore(
+        N.check(lib.b200r_expand_rescore(
             index.handle, graph.handle, Q.data_ptr(), seeds.data_ptr(), B, S, int(window), float(alpha_dense), float(alpha_graph), int(k),
+            ws.data_ptr(), ws.numel(),
             out["score"].data_ptr(), out["id"].data_ptr(), out["hop"].data_ptr(), out["score_graph_norm"].data_ptr(),
             out["score_dense_norm"].data_ptr(), out["cos"].data_ptr(), out["ncand"].data_ptr(), out["status"].data_ptr(),
             _stream_ptr(dev)))

@@ -143,10 +143,15 @@ int b200r_graph_destroy(uint64_t graph);
  * score_graph_norm / score_dense_norm meta keys, retrieval_backend.py:368) and the raw cosine; tail
  * entries beyond the candidate count are (-inf, -1, -1, 0, 0, 0).  out_ncand[B] = candidates found.
  * Fails with B200R_EOVERFLOW if a query reaches more than b200r_expand_max_candidates() nodes.
+ * Three kernels run on `stream`: BFS (candidate lists parked in `workspace`), a grid-wide balanced gather of the
+ * candidate rows (the HBM-bound part), and the per-query fusion + top-k.  `workspace`: caller-owned device scratch
+ * of at least b200r_expand_workspace_bytes(B) bytes, 256-byte aligned, private to this call until it completes.
  */
 int32_t b200r_expand_max_candidates(void);
+size_t b200r_expand_workspace_bytes(int32_t B);
 int b200r_expand_rescore(uint64_t index, uint64_t graph, const void* Q, const int64_t* seeds, int32_t B,
                          int32_t S, int32_t window, float alpha_dense, float alpha_graph, int32_t k,
+                         void* workspace, size_t workspace_bytes,
                          float* out_scores, int64_t* out_ids, int32_t* out_hops, float* out_graph_norm,
                          float* out_dense_norm, float* out_cos, int32_t* out_ncand, int32_t* out_status,
                          void* stream);
@@ -157,7 +162,6 @@ int b200r_expand_rescore(uint64_t index, uint64_t graph, const void* Q, const in
  * all-reduces minmax (MIN on [:,0], MAX on [:,1]) across ranks, then pass 2 fuses with the global range and
  * returns this rank's top-k among the candidates it owns; the per-rank lists are merged with
  * b200r_merge_topk.  Seeds and reported ids are GLOBAL row ids (the index's id_base maps them to local rows). */
-size_t b200r_expand_workspace_bytes(int32_t B);
 int b200r_expand_rescore_sharded(uint64_t index, uint64_t graph, const void* Q, const int64_t* seeds, int32_t B,
                                  int32_t S, int32_t window, float alpha_dense, float alpha_graph, int32_t k,
                                  int32_t pass, int64_t own_lo, int64_t own_hi, void* workspace,

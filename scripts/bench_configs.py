@@ -109,7 +109,7 @@ def run_search_i8(name, N, D, B, k, steps=10, warmup=3):
                       "queries_per_s": B / (ms * 1e-3), "kernel_ms_per_batch": kms, "hbm_GBps": gbs, "hbm_frac_of_measured": gbs / PEAKS["hbm_gbs"]}), flush=True)
 
 
-def run_graph(name, V, E, D, B, S, k, steps=5, warmup=2, window=2, random_seeds=False):
+def run_graph(name, V, E, D, B, S, k, steps=40, warmup=8, window=2, random_seeds=False, nbatch=4):
     X = corpus(V, D, torch.bfloat16)
     g = torch.Generator(device=dev).manual_seed(5)
     src = torch.randint(0, V, (E,), generator=g, device=dev)
@@ -123,27 +123,32 @@ def run_graph(name, V, E, D, B, S, k, steps=5, warmup=2, window=2, random_seeds=
     del src, dst, a, b, order
     graph = PassageGraph(row_ptr, col)
     ix = DenseIndex(X, metric="cos")
-    Q = queries(steps + warmup, B, D, torch.bfloat16)
-    # seeds = the dense top-S of each query (the north-star pipeline)
+    Q = queries(nbatch, B, D, torch.bfloat16)
     if random_seeds:   # window=0 + S random seeds = the re-score gather alone (no BFS)
-        seeds = [torch.randint(0, V, (B, S), generator=g, device=dev) for i in range(steps + warmup)]
-    else:
-        seeds = [ix.search(Q[i], S)[1] for i in range(steps + warmup)]
+        seeds = [torch.randint(0, V, (B, S), generator=g, device=dev) for i in range(nbatch)]
+    else:              # seeds = the dense top-S of each query (the north-star pipeline)
+        seeds = [ix.search(Q[i], S)[1] for i in range(nbatch)]
     for i in range(warmup):
-        out = expand_rescore(ix, graph, Q[i], seeds[i], window, 0.4, 0.2, k)
+        out = expand_rescore(ix, graph, Q[i % nbatch], seeds[i % nbatch], window, 0.4, 0.2, k)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    _native.profile_enable(True)        # brackets the gather kernel (K3b)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
     for i in range(steps):
-        out = expand_rescore(ix, graph, Q[warmup + i], seeds[warmup + i], window, 0.4, 0.2, k, check_status=False)
-    e1.record()
+        out = expand_rescore(ix, graph, Q[i % nbatch], seeds[i % nbatch], window, 0.4, 0.2, k, check_status=False)
+        ev[i + 1].record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    gms, gn = _native.profile_read()
+    _native.profile_enable(False)
+    gms /= max(gn, 1)
+    per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
+    ms = ev[0].elapsed_time(ev[steps]) / steps
     ncand = out["ncand"].float().mean().item()
     gather_bytes = ncand * B * D * 2
     line = {"config": name, "nodes": V, "edges_undirected": 2 * E, "dim": D, "batch": B, "seeds": S, "k": k, "window": window,
-            "ms_per_batch": ms, "queries_per_s": B / (ms * 1e-3), "avg_candidates": ncand,
+            "steps": steps, "ms_per_batch": ms, "ms_median": per[len(per) // 2], "ms_min": per[0], "queries_per_s": B / (ms * 1e-3), "avg_candidates": ncand,
             "gather_GBps": gather_bytes / (ms * 1e-3) / 1e9, "hbm_frac_of_measured": gather_bytes / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"],
+            "gather_kernel_ms": gms, "gather_kernel_GBps": gather_bytes / (gms * 1e-3) / 1e9 if gms > 0 else None,
             "overflowed_queries": int((out["status"] != 0).sum().item())}
     print(json.dumps(line), flush=True)
 
