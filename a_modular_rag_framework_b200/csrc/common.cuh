@@ -135,6 +135,12 @@ template <> struct ElemTraits<__nv_bfloat16> {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
   }
+  // elements [4*part, 4*part+4) only (part is a compile-time constant at every call site)
+  __device__ static __forceinline__ void unpack4(const uint4& v, int part, float* f) {
+    const u32 w0 = part == 0 ? v.x : v.z, w1 = part == 0 ? v.y : v.w;
+    f[0] = __uint_as_float(w0 << 16); f[1] = __uint_as_float(w0 & 0xffff0000u);
+    f[2] = __uint_as_float(w1 << 16); f[3] = __uint_as_float(w1 & 0xffff0000u);
+  }
 };
 template <> struct ElemTraits<__half> {
   static constexpr int kVec = 8;
@@ -147,12 +153,19 @@ template <> struct ElemTraits<__half> {
       f[2 * i] = t.x; f[2 * i + 1] = t.y;
     }
   }
+  __device__ static __forceinline__ void unpack4(const uint4& v, int part, float* f) {
+    const u32 w0 = part == 0 ? v.x : v.z, w1 = part == 0 ? v.y : v.w;
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w0));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&w1));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  }
 };
 template <> struct ElemTraits<float> {
   static constexpr int kVec = 4;
   __device__ static __forceinline__ void unpack(const uint4& v, float* f) {
     f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
   }
+  __device__ static __forceinline__ void unpack4(const uint4& v, int, float* f) { unpack(v, f); }
 };
 template <> struct ElemTraits<int8_t> {
   static constexpr int kVec = 16;
@@ -166,6 +179,13 @@ template <> struct ElemTraits<int8_t> {
       f[4 * i + 2] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7652)) - 8388736.0f;
       f[4 * i + 3] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7653)) - 8388736.0f;
     }
+  }
+  __device__ static __forceinline__ void unpack4(const uint4& v, int part, float* f) {
+    const u32 w = (part == 0 ? v.x : part == 1 ? v.y : part == 2 ? v.z : v.w) ^ 0x80808080u;
+    f[0] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650)) - 8388736.0f;
+    f[1] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651)) - 8388736.0f;
+    f[2] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7652)) - 8388736.0f;
+    f[3] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7653)) - 8388736.0f;
   }
 };
 

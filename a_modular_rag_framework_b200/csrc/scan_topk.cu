@@ -83,25 +83,67 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_topk_kernel(const ScanPa
     const uint8_t* rowp[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) rowp[r] = Xb + (size_t)min(r0 + r, row_end - 1) * row_bytes;
+    // lane r fetches row r's multiplier now, so its latency hides behind the row loads (NaN = past the end: never passes)
+    float my_mult = __int_as_float(0x7fc00000);
+    if (lane < R && r0 + lane < row_end) my_mult = p.row_mult ? __ldg(p.row_mult + r0 + lane) : 1.0f;
 
-    for (int chunk = lane; chunk < chunks; chunk += 32) {
-      uint4 xv[R];
+    if constexpr (PARTS == 4) {
+      // int8 rows are short (D bytes): a warp-wide 128-bit load covers only 512 B of a row, so TWO chunk iterations of
+      // every row are kept in flight together, and the values are consumed one 4-element part at a time so that only 4
+      // unpacked values per row are live
+      for (int cb = 0; cb < chunks; cb += 64) {
+        uint4 xv[2][R];
+        int ch[2];
 #pragma unroll
-      for (int r = 0; r < R; ++r) xv[r] = ld_stream_16B(rowp[r] + (size_t)chunk * 16);
-      float xf[R][VEC];
+        for (int h = 0; h < 2; ++h) {
+          const int c = cb + h * 32 + lane;
+          const bool ok = c < chunks;
+          ch[h] = ok ? c : 0;
 #pragma unroll
-      for (int r = 0; r < R; ++r) ElemTraits<T>::unpack(xv[r], xf[r]);
+          for (int r = 0; r < R; ++r) xv[h][r] = ok ? ld_stream_16B(rowp[r] + (size_t)c * 16) : make_uint4(0, 0, 0, 0);   // int8 zeros add 0
+        }
 #pragma unroll
-      for (int part = 0; part < PARTS; ++part) {
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int b = 0; b < BQ; ++b) {
-          const float4 qv = q4[((size_t)part * BQ + b) * chunks + chunk];
+          for (int part = 0; part < PARTS; ++part) {
+            float4 qv[BQ];
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            acc[r][b] = fmaf(xf[r][part * 4 + 0], qv.x, acc[r][b]);
-            acc[r][b] = fmaf(xf[r][part * 4 + 1], qv.y, acc[r][b]);
-            acc[r][b] = fmaf(xf[r][part * 4 + 2], qv.z, acc[r][b]);
-            acc[r][b] = fmaf(xf[r][part * 4 + 3], qv.w, acc[r][b]);
+            for (int b = 0; b < BQ; ++b) qv[b] = q4[((size_t)part * BQ + b) * chunks + ch[h]];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              float xf[4];
+              ElemTraits<T>::unpack4(xv[h][r], part, xf);
+#pragma unroll
+              for (int b = 0; b < BQ; ++b) {
+                acc[r][b] = fmaf(xf[0], qv[b].x, acc[r][b]);
+                acc[r][b] = fmaf(xf[1], qv[b].y, acc[r][b]);
+                acc[r][b] = fmaf(xf[2], qv[b].z, acc[r][b]);
+                acc[r][b] = fmaf(xf[3], qv[b].w, acc[r][b]);
+              }
+            }
+          }
+        }
+      }
+    } else {
+      for (int chunk = lane; chunk < chunks; chunk += 32) {
+        uint4 xv[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) xv[r] = ld_stream_16B(rowp[r] + (size_t)chunk * 16);
+        float xf[R][VEC];
+#pragma unroll
+        for (int r = 0; r < R; ++r) ElemTraits<T>::unpack(xv[r], xf[r]);
+#pragma unroll
+        for (int part = 0; part < PARTS; ++part) {
+#pragma unroll
+          for (int b = 0; b < BQ; ++b) {
+            const float4 qv = q4[((size_t)part * BQ + b) * chunks + chunk];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              acc[r][b] = fmaf(xf[r][part * 4 + 0], qv.x, acc[r][b]);
+              acc[r][b] = fmaf(xf[r][part * 4 + 1], qv.y, acc[r][b]);
+              acc[r][b] = fmaf(xf[r][part * 4 + 2], qv.z, acc[r][b]);
+              acc[r][b] = fmaf(xf[r][part * 4 + 3], qv.w, acc[r][b]);
+            }
           }
         }
       }
@@ -120,8 +162,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_topk_kernel(const ScanPa
     bool pass = false;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const long long row = r0 + r;
-      const float m = (row < row_end) ? (p.row_mult ? __ldg(p.row_mult + row) : 1.0f) : __int_as_float(0x7fc00000);
+      const float m = __shfl_sync(kFullMask, my_mult, r);
 #pragma unroll
       for (int b = 0; b < BQ; ++b) {
         acc[r][b] *= m;
@@ -205,7 +246,7 @@ int launch_scan_topk(const Index* ix, const void* Q, const SearchPlan& pl, void*
     case B200R_BF16: return launch_scan_t<__nv_bfloat16, 8, 4>(ix, Q, pl, ws, st);
     case B200R_F16: return launch_scan_t<__half, 8, 4>(ix, Q, pl, ws, st);
     case B200R_F32: return launch_scan_t<float, 8, 4>(ix, Q, pl, ws, st);
-    case B200R_I8: return launch_scan_t<int8_t, 4, 2>(ix, Q, pl, ws, st);
+    case B200R_I8: return launch_scan_t<int8_t, 4, 2>(ix, Q, pl, ws, st);   // x2 chunk iterations in flight per row
   }
   set_error("bad dtype %d", ix->dtype);
   return B200R_EINVAL;

@@ -168,6 +168,7 @@ CONFIGS = {
     "f32_5Mx768_B1_scan": lambda: run_search("f32_5Mx768_B1_scan", 5_000_000, 768, 1, 100, torch.float32, "scan", steps=20),
     "f32_5Mx768_B4_scan": lambda: run_search("f32_5Mx768_B4_scan", 5_000_000, 768, 4, 100, torch.float32, "scan", steps=20),
     "i8_10Mx768_B1_scan": lambda: run_search_i8("i8_10Mx768_B1_scan", 10_000_000, 768, 1, 100, steps=20),
+    "i8_10Mx768_B4_scan": lambda: run_search_i8("i8_10Mx768_B4_scan", 10_000_000, 768, 4, 100, steps=20),
     "cfg2_10Mx768_B1_gemm": lambda: run_search("cfg2_10Mx768_B1_gemm", 10_000_000, 768, 1, 100, torch.bfloat16, "gemm", steps=20),
     "cfg3_12p5Mx384_f16_k1000_B16": lambda: run_search("cfg3_12p5Mx384_f16_k1000_B16", 12_500_000, 384, 16, 1000, torch.float16, "gemm", steps=10),
     "cfg3_12p5Mx384_f16_k1000_B1": lambda: run_search("cfg3_12p5Mx384_f16_k1000_B1", 12_500_000, 384, 1, 1000, torch.float16, "scan", steps=10),
