@@ -7,8 +7,9 @@
 //                            flattened edge list is spread over all threads (coalesced col_idx reads, several in
 //                            flight per thread; hubs need no special case), with a warp-level __match_any_sync
 //                            pre-dedup so each distinct neighbour costs one atomic per warp.  The candidate list, the
-//                            hop distances and the query's inverse norm are parked in the workspace and the query
-//                            reserves a contiguous range of 4-row groups in a flat work list (one 64-bit atomic).
+//                            hop distances and the query's inverse norm are parked in the workspace -- the candidates
+//                            this rank owns first -- and the query reserves a contiguous range of 4-row groups in a
+//                            flat work list (one 64-bit atomic).
 //   K3b rescore_gather_kernel persistent, grid-wide: every warp owns a contiguous slice of the flat group list (so the
 //                            load is balanced whatever the per-query candidate counts are), keeps the current query
 //                            as fp32 in its own shared-memory slice and gathers 4 candidate rows at a time with all
@@ -55,6 +56,7 @@ struct ExpandWs {
   float* cos;           // [B][EXP_MAXC_BIG] cosine of the candidates this rank owns (0 elsewhere)
   uint8_t* dist;        // [B][EXP_MAXC_BIG] hop distance
   int* ncand;           // [B] (0 for a query that overflowed)
+  int* nown;            // [B] candidates this rank owns: they are parked FIRST in cand/dist, so the gather reads a dense prefix
   float* qinv;          // [B] 1/|q| (cosine) or 1
   u32* mm;              // [B][2] order-preserving images of the owned candidates' (min, max) cosine
   u32* seg_start;       // [2B] first flat group of the i-th reservation (monotonic in i)
@@ -64,7 +66,7 @@ struct ExpandWs {
 
 size_t expand_workspace_bytes(int B) {
   const size_t b = (size_t)B;
-  return align_up(b * EXP_MAXC_BIG * 4, 256) * 2 + align_up(b * EXP_MAXC_BIG, 256) + align_up(b * 4, 256) * 2 + align_up(b * 8, 256) * 3 + 256;
+  return align_up(b * EXP_MAXC_BIG * 4, 256) * 2 + align_up(b * EXP_MAXC_BIG, 256) + align_up(b * 4, 256) * 3 + align_up(b * 8, 256) * 3 + 256;
 }
 
 static ExpandWs carve_ws(void* ws, int B) {
@@ -75,6 +77,7 @@ static ExpandWs carve_ws(void* ws, int B) {
   s.cos = reinterpret_cast<float*>(w); w += align_up(b * EXP_MAXC_BIG * 4, 256);
   s.dist = reinterpret_cast<uint8_t*>(w); w += align_up(b * EXP_MAXC_BIG, 256);
   s.ncand = reinterpret_cast<int*>(w); w += align_up(b * 4, 256);
+  s.nown = reinterpret_cast<int*>(w); w += align_up(b * 4, 256);
   s.qinv = reinterpret_cast<float*>(w); w += align_up(b * 4, 256);
   s.mm = reinterpret_cast<u32*>(w); w += align_up(b * 8, 256);
   s.seg_start = reinterpret_cast<u32*>(w); w += align_up(b * 8, 256);
@@ -142,7 +145,8 @@ __global__ void __launch_bounds__(BFS_THREADS) bfs_kernel(const ExpandParams p) 
   u32* cand = table + HASH;                                                       // [MAXC] node ids in BFS order
   long long* f_e0 = reinterpret_cast<long long*>(cand + MAXC);                    // [EXP_FB] first edge of a frontier node
   u32* f_pre = reinterpret_cast<u32*>(f_e0 + EXP_FB);                             // [EXP_FB + 1] exclusive edge offsets
-  __shared__ int s_count, s_overflow;
+  __shared__ int s_count, s_overflow, s_nown, s_nother, s_nlevels;
+  __shared__ int s_level_end[256];        // s_level_end[d] = candidates at hop distance <= d (window <= 255)
   __shared__ u32 s_wsum[BFS_WARPS];
   __shared__ unsigned long long s_wwide[BFS_WARPS];
   __shared__ double s_qn[BFS_WARPS];
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(BFS_THREADS) bfs_kernel(const ExpandParams p) 
     if (RETRY_PASS && p.out_status[q] != kStatusRetry) continue;      // block-uniform
     __syncthreads();                                                  // the previous query of this CTA is done with smem
     for (int i = tid; i < HASH; i += BFS_THREADS) table[i] = EXP_EMPTY;
-    if (tid == 0) { s_count = 0; s_overflow = 0; }
+    if (tid == 0) { s_count = 0; s_overflow = 0; s_nown = 0; s_nother = 0; s_nlevels = 1; }
     // the query's inverse norm (the re-score kernel multiplies by it)
     const QT* Qp = reinterpret_cast<const QT*>(p.Q) + (size_t)q * p.D;
     double qn = 0.0;
@@ -169,7 +173,6 @@ __global__ void __launch_bounds__(BFS_THREADS) bfs_kernel(const ExpandParams p) 
       for (int w = 0; w < BFS_WARPS; ++w) qn_tot += s_qn[w];
       p.ws.qinv[q] = (p.metric == B200R_COS) ? (qn_tot > 0.0 ? (float)(1.0 / sqrt(qn_tot)) : 0.0f) : 1.0f;
     }
-    uint8_t* dist_out = p.ws.dist + (size_t)q * EXP_MAXC_BIG;
 
     // ---- level 0: seeds ---------------------------------------------------------------------------
     for (int i = tid; i < p.S; i += BFS_THREADS) {
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(BFS_THREADS) bfs_kernel(const ExpandParams p) 
       }
     }
     __syncthreads();
-    for (int c = tid; c < min(s_count, MAXC); c += BFS_THREADS) dist_out[c] = 0;
+    if (tid == 0) s_level_end[0] = min(s_count, MAXC);
 
     // ---- levels 1..window: edge-parallel expansion, EXP_FB frontier nodes per batch ------------------
     int level_begin = 0;
@@ -264,8 +267,7 @@ __global__ void __launch_bounds__(BFS_THREADS) bfs_kernel(const ExpandParams p) 
         __syncthreads();                    // the scratch is reused by the next batch
       }
       // the nodes this level appended are at hop distance d
-      const uint8_t dd = (uint8_t)min(d, 255);
-      for (int c = level_end + tid; c < min(s_count, MAXC); c += BFS_THREADS) dist_out[c] = dd;
+      if (tid == 0) { s_level_end[d] = min(s_count, MAXC); s_nlevels = d + 1; }
       level_begin = level_end;
     }
     __syncthreads();
@@ -275,19 +277,34 @@ __global__ void __launch_bounds__(BFS_THREADS) bfs_kernel(const ExpandParams p) 
         p.out_status[q] = (MAXC < EXP_MAXC_BIG) ? kStatusRetry : B200R_EOVERFLOW;
         p.out_ncand[q] = s_count;
         p.ws.ncand[q] = 0;
+        p.ws.nown[q] = 0;
       }
       fill_no_result(p, q);
       continue;
     }
+    // park the list with the candidates this rank owns FIRST (the order inside a list carries no meaning: ranking breaks
+    // ties by id), so the gather kernel reads a dense prefix however the corpus is sharded
     u32* cand_out = p.ws.cand + (size_t)q * EXP_MAXC_BIG;
-    for (int c = tid; c < ncand; c += BFS_THREADS) cand_out[c] = cand[c];
+    uint8_t* dist_out = p.ws.dist + (size_t)q * EXP_MAXC_BIG;
+    const int nlevels = s_nlevels;
+    for (int c = tid; c < ncand; c += BFS_THREADS) {
+      const u32 node = cand[c];
+      int d = 0;
+      while (d + 1 < nlevels && c >= s_level_end[d]) ++d;
+      const bool own = (long long)node >= p.own_lo && (long long)node < p.own_hi;
+      const int pos = own ? atomicAdd(&s_nown, 1) : ncand - 1 - atomicAdd(&s_nother, 1);
+      cand_out[pos] = node;
+      dist_out[pos] = (uint8_t)min(d, 255);
+    }
+    __syncthreads();
     if (tid == 0) {
       p.ws.ncand[q] = ncand;
+      p.ws.nown[q] = s_nown;
       p.out_ncand[q] = ncand;
       p.out_status[q] = 0;
       p.ws.mm[2 * q] = 0xffffffffu;       // "no owned candidate yet": min image > max image
       p.ws.mm[2 * q + 1] = 0u;
-      const u32 groups = (u32)((ncand + GATHER_ROWS - 1) / GATHER_ROWS);
+      const u32 groups = (u32)((s_nown + GATHER_ROWS - 1) / GATHER_ROWS);
       const u64 old = atomicAdd(p.ws.counter, (1ull << 32) | (u64)groups);
       p.ws.seg_start[old >> 32] = (u32)old;
       p.ws.seg_q[old >> 32] = (u32)q;
@@ -345,11 +362,16 @@ __global__ void __launch_bounds__(GATHER_MAX_WARPS * 32, GATHER_CTAS_PER_SM) res
   };
   auto load_query = [&]() {
     q = (int)__ldg(p.ws.seg_q + seg);
-    ncand = p.ws.ncand[q];
+    ncand = p.ws.nown[q];          // the owned candidates are the first nown entries of the parked list
     qinv = p.ws.qinv[q];
     const QT* Qp = reinterpret_cast<const QT*>(p.Q) + (size_t)q * p.D;
     __syncwarp();
-    for (int d = lane; d < p.D; d += 32) qs[d] = q_to_float<QT>(Qp[d]);
+    // float4 "part" layout: the 4-element part `e/4` of 16-byte chunk `c` lives at q4[(e/4)*chunks + c], so a warp's 32
+    // consecutive chunks read 32 consecutive float4 (conflict-free LDS.128)
+    for (int d = lane; d < p.D; d += 32) {
+      const int c = d / VEC, e = d % VEC;
+      qs[((size_t)(e >> 2) * chunks + c) * 4 + (e & 3)] = q_to_float<QT>(Qp[d]);
+    }
     __syncwarp();
   };
   load_query();
@@ -368,34 +390,38 @@ __global__ void __launch_bounds__(GATHER_MAX_WARPS * 32, GATHER_CTAS_PER_SM) res
     // lane r < ROWS owns row r of the group: its node id, ownership and row multiplier (fetched with the rows, so its
     // latency is hidden behind them)
     long long my_row = 0;
-    bool my_valid = false, my_own = false, my_have = false;
+    bool my_valid = false, my_have = false;
     float my_mult = 0.0f;
     if (lane < ROWS && c0 + lane < ncand) {
       const long long node = (long long)__ldg(p.ws.cand + (size_t)q * EXP_MAXC_BIG + c0 + lane);
       const long long row = node - p.id_base;
       my_valid = true;
-      my_own = node >= p.own_lo && node < p.own_hi;
-      my_have = my_own && row >= 0 && row < p.N;
+      my_have = row >= 0 && row < p.N;       // a graph node that is not a corpus row scores 0.0
       if (my_have) { my_row = row; my_mult = p.row_mult ? __ldg(p.row_mult + row) : 1.0f; }
     }
     const uint8_t* rp[ROWS];
     float acc[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-      rp[r] = Xb + (size_t)__shfl_sync(kFullMask, my_row, r) * row_bytes;     // a row this rank does not hold reads row 0
+      rp[r] = Xb + (size_t)__shfl_sync(kFullMask, my_row, r) * row_bytes;     // (padding lanes of a query's last group read row 0)
       acc[r] = 0.0f;
     }
     for (int chunk = lane; chunk < chunks; chunk += 32) {
       uint4 xv[ROWS];
 #pragma unroll
       for (int r = 0; r < ROWS; ++r) xv[r] = ld_stream_16B(rp[r] + (size_t)chunk * 16);
-      const float* qc = qs + chunk * VEC;
 #pragma unroll
-      for (int r = 0; r < ROWS; ++r) {
-        float xf[VEC];
-        ElemTraits<T>::unpack(xv[r], xf);
+      for (int part = 0; part < VEC / 4; ++part) {
+        const float4 qv = reinterpret_cast<const float4*>(qs)[(size_t)part * chunks + chunk];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) acc[r] = fmaf(xf[e], qc[e], acc[r]);
+        for (int r = 0; r < ROWS; ++r) {
+          float xf[4];
+          ElemTraits<T>::unpack4(xv[r], part, xf);
+          acc[r] = fmaf(xf[0], qv.x, acc[r]);
+          acc[r] = fmaf(xf[1], qv.y, acc[r]);
+          acc[r] = fmaf(xf[2], qv.z, acc[r]);
+          acc[r] = fmaf(xf[3], qv.w, acc[r]);
+        }
       }
     }
     float mine = 0.0f;
@@ -409,7 +435,7 @@ __global__ void __launch_bounds__(GATHER_MAX_WARPS * 32, GATHER_CTAS_PER_SM) res
     if (my_valid) {
       const float v = my_have ? (mine * my_mult) * qinv + 0.0f : 0.0f;
       p.ws.cos[(size_t)q * EXP_MAXC_BIG + c0 + lane] = v;
-      if (my_own) { cmin = fminf(cmin, v); cmax = fmaxf(cmax, v); }
+      cmin = fminf(cmin, v); cmax = fmaxf(cmax, v);
     }
   }
   flush_minmax();
