@@ -23,7 +23,7 @@ EXPORTS = [
     "b200r_search_workspace_bytes", "b200r_search", "b200r_search_host", "b200r_search_scatter", "b200r_search_min_score",
     "b200r_merge_topk", "b200r_merge_topk_packed", "b200r_profile_enable", "b200r_profile_read",
     "b200r_graph_create", "b200r_graph_destroy",
-    "b200r_expand_max_candidates", "b200r_expand_rescore", "b200r_expand_workspace_bytes", "b200r_expand_rescore_sharded",
+    "b200r_merge_topk_src", "b200r_expand_max_candidates", "b200r_expand_rescore", "b200r_expand_workspace_bytes", "b200r_expand_rescore_sharded",
 ]
 
 
@@ -72,6 +72,8 @@ def load() -> ctypes.CDLL:
     lib.b200r_search_scatter.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, POINTER(c_uint64), c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.b200r_merge_topk.argtypes = [c_int, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
     lib.b200r_merge_topk_packed.argtypes = [c_int, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.b200r_merge_topk_src.argtypes = [c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_int32, c_int32, c_int32, c_int32,
+                                         c_void_p, c_void_p, c_void_p, c_void_p]
     lib.b200r_profile_enable.argtypes = [c_int]
     lib.b200r_profile_read.argtypes = [POINTER(ctypes.c_double), POINTER(c_int64)]
     lib.b200r_graph_create.argtypes = [c_int, c_void_p, c_void_p, c_int64, c_int64, POINTER(c_uint64)]

@@ -430,6 +430,17 @@ int b200r_merge_topk(int device, const float* cand_scores, const int64_t* cand_i
                            reinterpret_cast<cudaStream_t>(stream));
 }
 
+int b200r_merge_topk_src(int device, const float* cand_scores, size_t shard_stride_scores, const int64_t* cand_ids,
+                         size_t shard_stride_ids, int32_t G, int32_t B, int32_t kin, int32_t k, float* out_scores, int64_t* out_ids,
+                         int32_t* out_src, void* stream) {
+  if (!cand_scores || !cand_ids || !out_scores || !out_ids || !out_src) { set_error("null pointer"); return B200R_EINVAL; }
+  if (G <= 0 || B <= 0 || kin <= 0 || k <= 0) { set_error("G, B, kin, k must be > 0"); return B200R_EINVAL; }
+  if (shard_stride_scores < (size_t)B * kin || shard_stride_ids < (size_t)B * kin) { set_error("shard strides smaller than B*kin"); return B200R_EINVAL; }
+  B200R_CUDA_CHECK(cudaSetDevice(device));
+  return launch_merge_topk(cand_scores, cand_ids, shard_stride_scores, shard_stride_ids, G, B, kin, k, out_scores, out_ids,
+                           reinterpret_cast<cudaStream_t>(stream), out_src);
+}
+
 int b200r_merge_topk_packed(int device, const void* packed, int32_t G, int32_t B, int32_t kin, int32_t k, float* out_scores,
                             int64_t* out_ids, void* stream) {
   if (!packed || !out_scores || !out_ids) { set_error("null pointer"); return B200R_EINVAL; }

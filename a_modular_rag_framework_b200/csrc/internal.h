@@ -99,7 +99,7 @@ struct PeerScatter { int n, rank; unsigned long long base[B200R_MAX_PEERS]; };
 int launch_select_lists(const Index* ix, const SearchPlan& p, void* ws, float* out_scores, int64_t* out_ids, cudaStream_t st,
                         const PeerScatter* peers = nullptr, float min_score = -__builtin_huge_valf());
 int launch_merge_topk(const float* cs, const int64_t* ci, size_t shard_stride_s, size_t shard_stride_i, int G, int B, int kin, int k,
-                      float* os, int64_t* oi, cudaStream_t st);
+                      float* os, int64_t* oi, cudaStream_t st, int32_t* osrc = nullptr);
 void profile_begin(cudaStream_t st);
 void profile_end(cudaStream_t st);
 int launch_expand_rescore(const Index* ix, const Graph* g, const void* Q, const int64_t* seeds, int B, int S, int window,

@@ -341,6 +341,7 @@ struct MergeParams {
   int G, B, kin, k, np2;
   float* os;
   long long* oi;
+  int* osrc;                   // nullable: [B, k] position g*kin + j of every winner in the gathered lists (-1 = padding)
 };
 
 __device__ __forceinline__ bool cand_better(u32 sa, long long ia, u32 sb, long long ib) {
@@ -351,6 +352,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const MergePa
   extern __shared__ uint8_t smem_raw[];
   long long* ids = reinterpret_cast<long long*>(smem_raw);  // [np2]
   u32* sc = reinterpret_cast<u32*>(ids + p.np2);            // [np2] ordered scores
+  int* src = reinterpret_cast<int*>(sc + p.np2);            // [np2] where each candidate came from
   const int q = blockIdx.x;
   const int n = p.G * p.kin;
   for (int i = threadIdx.x; i < p.np2; i += MERGE_THREADS) {
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const MergePa
       const long long cid = p.ci[(size_t)g * p.stride_i + off];
       if (cid >= 0) { id = cid; s = f32_to_ordered(p.cs[(size_t)g * p.stride_s + off] + 0.0f); }
     }
-    sc[i] = s; ids[i] = id;
+    sc[i] = s; ids[i] = id; src[i] = i;
   }
   for (int size = 2; size <= p.np2; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -373,7 +375,10 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const MergePa
         const u32 sa = sc[lo], sb = sc[hi];
         const long long ia = ids[lo], ib = ids[hi];
         const bool lo_better = cand_better(sa, ia, sb, ib);
-        if (lo_better != desc) { sc[lo] = sb; sc[hi] = sa; ids[lo] = ib; ids[hi] = ia; }
+        if (lo_better != desc) {
+          sc[lo] = sb; sc[hi] = sa; ids[lo] = ib; ids[hi] = ia;
+          const int t2 = src[lo]; src[lo] = src[hi]; src[hi] = t2;
+        }
       }
     }
   }
@@ -382,18 +387,19 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const MergePa
     const bool ok = i < p.np2 && ids[i] != 0x7fffffffffffffffll;
     p.os[(size_t)q * p.k + i] = ok ? ordered_to_f32(sc[i]) : -CUDART_INF_F;
     p.oi[(size_t)q * p.k + i] = ok ? ids[i] : -1ll;
+    if (p.osrc) p.osrc[(size_t)q * p.k + i] = ok ? src[i] : -1;
   }
 }
 
 int launch_merge_topk(const float* cs, const int64_t* ci, size_t shard_stride_s, size_t shard_stride_i, int G, int B, int kin, int k,
-                      float* os, int64_t* oi, cudaStream_t st) {
+                      float* os, int64_t* oi, cudaStream_t st, int32_t* osrc) {
   const long long n = (long long)G * kin;
   if (n > 16384) { set_error("merge_topk: G*kin = %lld exceeds 16384", n); return B200R_EINVAL; }
   MergeParams p;
   p.cs = cs; p.ci = reinterpret_cast<const long long*>(ci); p.stride_s = shard_stride_s; p.stride_i = shard_stride_i; p.G = G; p.B = B; p.kin = kin; p.k = k;
   p.np2 = next_pow2((int)n < 2 ? 2 : (int)n);
-  p.os = os; p.oi = reinterpret_cast<long long*>(oi);
-  const size_t smem = (size_t)p.np2 * 12;
+  p.os = os; p.oi = reinterpret_cast<long long*>(oi); p.osrc = osrc;
+  const size_t smem = (size_t)p.np2 * 16;
   B200R_CUDA_CHECK(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   merge_topk_kernel<<<B, MERGE_THREADS, smem, st>>>(p);
   count_launch();

@@ -23,10 +23,10 @@ _METRICS = {"ip": N.IP, "cos": N.COS, "cosine": N.COS}
 _PATHS = {"auto": N.PATH_AUTO, "gemm": N.PATH_GEMM, "scan": N.PATH_SCAN}
 
 
-def _require_cuda(t: torch.Tensor, name: str) -> None:
+def _require_cuda(t: torch.Tensor, name: str, contiguous: bool = True) -> None:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise ValueError(f"{name} must be a CUDA tensor (there is no CPU path)")
-    if not t.is_contiguous():
+    if contiguous and not t.is_contiguous():
         raise ValueError(f"{name} must be contiguous")
 
 
@@ -167,6 +167,28 @@ def merge_topk(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int) -> Tup
     return scores, ids
 
 
+def merge_topk_src(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Like merge_topk, for [G, B, kin] views whose shard stride (dim 0) may exceed B*kin (slices of one gathered
+    buffer), and also returns src [B, k] int32 = g*kin + j, where each winner sits in its shard's list (-1 = padding)."""
+    _require_cuda(cand_scores, "cand_scores", contiguous=False)
+    _require_cuda(cand_ids, "cand_ids", contiguous=False)
+    if cand_scores.dtype != torch.float32 or cand_ids.dtype != torch.int64 or cand_scores.shape != cand_ids.shape or cand_scores.dim() != 3:
+        raise ValueError("cand_scores f32 / cand_ids i64 must both be [G, B, kin]")
+    G, B, kin = (int(x) for x in cand_scores.shape)
+    for t in (cand_scores, cand_ids):
+        if t.stride(2) != 1 or t.stride(1) != kin or (G > 1 and t.stride(0) < B * kin):
+            raise ValueError("each shard's [B, kin] block must be dense")
+    dev = cand_scores.device
+    scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((B, k), dtype=torch.int64, device=dev)
+    src = torch.empty((B, k), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.load().b200r_merge_topk_src(dev.index or 0, cand_scores.data_ptr(), max(cand_scores.stride(0), B * kin),
+                                              cand_ids.data_ptr(), max(cand_ids.stride(0), B * kin), G, B, kin, k,
+                                              scores.data_ptr(), ids.data_ptr(), src.data_ptr(), _stream_ptr(dev)))
+    return scores, ids, src
+
+
 class PassageGraph:
     """CSR of the undirected next_in_doc adjacency; node id == corpus row id."""
 
@@ -242,23 +264,35 @@ def expand_rescore(index: DenseIndex, graph: PassageGraph, Q: torch.Tensor, seed
 
 
 class ExpandShardState:
-    """Device buffers of one rank's share of a sharded expand_rescore (see sharded.ShardedGraphStage)."""
+    """Device buffers of one rank's share of a sharded expand_rescore (see sharded.ShardedGraphStage).  The six [B, k]
+    outputs are views of ONE packed record [id i64 | score f32 | hop i32 | graph_norm f32 | dense_norm f32 | cos f32]
+    so that the ranks exchange them with a single all-gather."""
+
+    FIELDS = (("id", torch.int64), ("score", torch.float32), ("hop", torch.int32), ("score_graph_norm", torch.float32),
+              ("score_dense_norm", torch.float32), ("cos", torch.float32))
 
     def __init__(self, index: DenseIndex, B: int, k: int):
         dev = index.device
         lib = N.load()
+        self.B, self.k = B, k
+        self.n = (B * k + 1) // 2 * 2          # slots per field, even so that every field offset is 8-byte aligned
         self.ws = torch.empty(int(lib.b200r_expand_workspace_bytes(B)), dtype=torch.uint8, device=dev)
         self.minmax = torch.empty((B, 2), dtype=torch.float32, device=dev)
-        self.out = {
-            "score": torch.empty((B, k), dtype=torch.float32, device=dev),
-            "id": torch.empty((B, k), dtype=torch.int64, device=dev),
-            "hop": torch.empty((B, k), dtype=torch.int32, device=dev),
-            "score_graph_norm": torch.empty((B, k), dtype=torch.float32, device=dev),
-            "score_dense_norm": torch.empty((B, k), dtype=torch.float32, device=dev),
-            "cos": torch.empty((B, k), dtype=torch.float32, device=dev),
-            "ncand": torch.empty((B,), dtype=torch.int32, device=dev),
-            "status": torch.empty((B,), dtype=torch.int32, device=dev),
-        }
+        self.record = torch.zeros(28 * self.n, dtype=torch.uint8, device=dev)
+        self.out = self.views(self.record.unsqueeze(0), squeeze=True)
+        self.out["ncand"] = torch.empty((B,), dtype=torch.int32, device=dev)
+        self.out["status"] = torch.empty((B,), dtype=torch.int32, device=dev)
+
+    def views(self, records: torch.Tensor, squeeze: bool = False) -> Dict[str, torch.Tensor]:
+        """records: uint8 [G, 28*n] -> {field: [G, B, k] view} (shard stride 28*n bytes)."""
+        G = int(records.shape[0])
+        out, off = {}, 0
+        for name, dt in self.FIELDS:
+            size = torch.empty((), dtype=dt).element_size()
+            v = records[:, off:off + size * self.n].view(dt)[:, :self.B * self.k].unflatten(1, (self.B, self.k))
+            out[name] = v[0] if squeeze else v
+            off += size * self.n
+        return out
 
 
 def expand_rescore_pass(index: DenseIndex, graph: PassageGraph, Q: torch.Tensor, seeds: torch.Tensor, window: int,

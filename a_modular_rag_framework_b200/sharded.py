@@ -12,7 +12,7 @@ on CPU ranks; the defaults are the CUDA kernels and raise without them (no CPU f
 from __future__ import annotations
 
 import ctypes
-from typing import Callable, Optional, Tuple
+from typing import Dict, Callable, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -212,41 +212,43 @@ class ShardedGraphStage:
         lo, hi = owned_range(self.N_total, self.world, self.rank)
         expand_rescore_pass(self.index, self.graph, Q, seeds, window, alpha_dense, alpha_graph, k, st, 1, lo, hi)
         if self.world > 1:
-            mn, mx = st.minmax[:, 0].contiguous(), st.minmax[:, 1].contiguous()
-            dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=self.group)
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
-            st.minmax[:, 0], st.minmax[:, 1] = mn, mx
+            # ONE all-reduce for both ends of the range: max over ranks of (-min, max)
+            st.minmax[:, 0].neg_()
+            dist.all_reduce(st.minmax, op=dist.ReduceOp.MAX, group=self.group)
+            st.minmax[:, 0].neg_()
         expand_rescore_pass(self.index, self.graph, Q, seeds, window, alpha_dense, alpha_graph, k, st, 2, lo, hi)
         if self.world == 1:
             return dict(st.out)
-        return combine_shard_outputs([self._gather(v) for v in (st.out[key] for key in _AUX_KEYS)], st.out["ncand"], st.out["status"], k)
-
-    def _gather(self, t: torch.Tensor) -> torch.Tensor:
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
-        return out
+        # ONE all-gather of the packed per-rank records, then the device merge (which also reports where each winner came from)
+        gathered = torch.empty((self.world, st.record.numel()), dtype=torch.uint8, device=st.record.device)
+        dist.all_gather_into_tensor(gathered, st.record, group=self.group)
+        return combine_shard_records(st.views(gathered), st.out["ncand"], st.out["status"], k)
 
 
-_AUX_KEYS = ("score", "id", "hop", "score_graph_norm", "score_dense_norm", "cos")
+_AUX_KEYS = ("hop", "score_graph_norm", "score_dense_norm", "cos")
+_AUX_FILL = {"hop": -1, "score_graph_norm": 0.0, "score_dense_norm": 0.0, "cos": 0.0}
+
+
+def combine_shard_records(g: Dict[str, torch.Tensor], ncand: torch.Tensor, status: torch.Tensor, k: int):
+    """g: {field: [G, B, kin]} per-rank outputs.  Merge (score, id) on the device (b200r_merge_topk_src), then pick each
+    winner's other fields from the rank list and position the merge reports (plumbing)."""
+    from .index import merge_topk_src
+    G, B, kin = (int(x) for x in g["score"].shape)
+    ms, mi, src = merge_topk_src(g["score"], g["id"], k)
+    valid = src >= 0
+    s = src.clamp_min(0).long()
+    gi, ji = s // kin, s % kin
+    qi = torch.arange(B, device=s.device).unsqueeze(1).expand_as(s)
+    out = {"score": ms, "id": mi}
+    for key in _AUX_KEYS:
+        picked = g[key][gi, qi, ji]
+        out[key] = torch.where(valid, picked, torch.full_like(picked, _AUX_FILL[key]))
+    out["ncand"], out["status"] = ncand, status
+    return out
 
 
 def combine_shard_outputs(gathered, ncand: torch.Tensor, status: torch.Tensor, k: int):
-    """gathered: the six [G, B, k] per-rank outputs (order of _AUX_KEYS).  Merge (score, id) on the device with
-    b200r_merge_topk, then pick each winner's other fields from the rank list it came from (plumbing)."""
-    from .index import merge_topk
-    g_score, g_id = gathered[0], gathered[1]
-    G, B, kk = g_score.shape
-    ms, mi = merge_topk(g_score.contiguous(), g_id.contiguous(), k)
-    flat_id = g_id.permute(1, 0, 2).reshape(B, G * kk)
-    # position of every merged id inside its query's gathered candidates (ids are unique per query; -1 pads)
-    match = (flat_id.unsqueeze(1) == mi.unsqueeze(2)) & (mi.unsqueeze(2) >= 0)
-    pos = match.float().argmax(dim=2)
-    valid = mi >= 0
-    out = {"score": ms, "id": mi}
-    fill = {"hop": -1, "score_graph_norm": 0.0, "score_dense_norm": 0.0, "cos": 0.0}
-    for key, g in zip(_AUX_KEYS[2:], gathered[2:]):
-        flat = g.permute(1, 0, 2).reshape(B, G * kk)
-        picked = torch.gather(flat, 1, pos)
-        out[key] = torch.where(valid, picked, torch.full_like(picked, fill[key]))
-    out["ncand"], out["status"] = ncand, status
-    return out
+    """gathered: the six dense [G, B, k] per-rank outputs in the order (score, id, hop, score_graph_norm,
+    score_dense_norm, cos); see combine_shard_records."""
+    keys = ("score", "id") + _AUX_KEYS
+    return combine_shard_records(dict(zip(keys, gathered)), ncand, status, k)

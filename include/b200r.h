@@ -114,6 +114,14 @@ int b200r_search_scatter(uint64_t index, const void* Q, int32_t B, int32_t k, in
 int b200r_merge_topk(int device, const float* cand_scores, const int64_t* cand_ids, int32_t G, int32_t B,
                      int32_t kin, int32_t k, float* out_scores, int64_t* out_ids, void* stream);
 
+/* Same merge with explicit shard strides (in elements) and the provenance of every winner: out_src[B, k] =
+ * g*kin + j, the winner's position in shard g's list (-1 for padding), so that a caller that gathered more
+ * per-candidate fields than (score, id) -- the graph stage's hop / normalised channel scores / cosine
+ * (retrieval_backend.py:365-369 meta keys) -- can pick them without a search. */
+int b200r_merge_topk_src(int device, const float* cand_scores, size_t shard_stride_scores, const int64_t* cand_ids,
+                         size_t shard_stride_ids, int32_t G, int32_t B, int32_t kin, int32_t k, float* out_scores,
+                         int64_t* out_ids, int32_t* out_src, void* stream);
+
 /* Same merge over the layout the all-gather of one packed buffer per rank produces:
  * packed = G records, each [ids i64 [B, kin] | scores f32 [B, kin]] (12*B*kin bytes). */
 int b200r_merge_topk_packed(int device, const void* packed, int32_t G, int32_t B, int32_t kin, int32_t k,

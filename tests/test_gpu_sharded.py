@@ -122,7 +122,7 @@ def test_graph_stage_virtual_shards_equal_single_gpu():
     all-reduce, pass 2 per shard, merge) must reproduce the single-launch result."""
     from a_modular_rag_framework_b200 import DenseIndex, PassageGraph, expand_rescore
     from a_modular_rag_framework_b200.index import ExpandShardState, expand_rescore_pass
-    from a_modular_rag_framework_b200.sharded import combine_shard_outputs, owned_range, shard_rows, _AUX_KEYS
+    from a_modular_rag_framework_b200.sharded import combine_shard_records, owned_range, shard_rows
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(21)
     V, E, D, B, S, k, G = 30000, 120000, 64, 16, 20, 10, 4
@@ -147,8 +147,9 @@ def test_graph_stage_virtual_shards_equal_single_gpu():
     for r, (ix, st) in enumerate(zip(shards, states)):
         st.minmax[:, 0], st.minmax[:, 1] = mn, mx
         expand_rescore_pass(ix, graph, Q, seeds, 2, 0.4, 0.2, k, st, 2, *owned_range(N, G, r))
-    gathered = [torch.stack([s.out[key] for s in states]) for key in _AUX_KEYS]
-    out = combine_shard_outputs(gathered, states[0].out["ncand"], states[0].out["status"], k)
+    # what the ranks' single all-gather of the packed records produces, viewed per field (shard stride = one record)
+    gathered = torch.stack([s.record for s in states])
+    out = combine_shard_records(states[0].views(gathered), states[0].out["ncand"], states[0].out["status"], k)
     assert torch.equal(out["ncand"], ref["ncand"])
     assert torch.equal(out["id"], ref["id"])
     assert torch.allclose(out["score"], ref["score"], atol=1e-6)
