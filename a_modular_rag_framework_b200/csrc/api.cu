@@ -171,14 +171,25 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
     pl->num_segments = pl->num_chunks;
   } else {
     pl->Bpad = B;
-    const int R = 4;
-    const int warps_per_block = 8;
-    long long blocks = (long long)kPlanSMs * 3;   // scan kernels are compiled for 3 CTAs/SM: one full wave
-    const long long groups = (ix->N + R - 1) / R;
-    const long long need = (groups + warps_per_block - 1) / warps_per_block;
-    if (blocks > need) blocks = need < 1 ? 1 : need;
-    pl->scan_blocks = (int)blocks;
-    pl->scan_warps = (int)blocks * warps_per_block;
+    const int bulk_warps = scan_bulk_warps(ix);
+    if (bulk_warps) {
+      // fp32 / int8: bulk-copy-fed scan, one persistent CTA per SM, every consumer warp keeps its own lists
+      pl->scan_bulk = 1;
+      const long long need = (ix->N + scan_bulk_tile_rows(ix) - 1) / scan_bulk_tile_rows(ix);
+      long long blocks = kPlanSMs;
+      if (blocks > need) blocks = need < 1 ? 1 : need;
+      pl->scan_blocks = (int)blocks;
+      pl->scan_warps = (int)blocks * bulk_warps;
+    } else {
+      const int R = 4;
+      const int warps_per_block = 8;
+      long long blocks = (long long)kPlanSMs * 3;   // scan kernels are compiled for 3 CTAs/SM: one full wave
+      const long long groups = (ix->N + R - 1) / R;
+      const long long need = (groups + warps_per_block - 1) / warps_per_block;
+      if (blocks > need) blocks = need < 1 ? 1 : need;
+      pl->scan_blocks = (int)blocks;
+      pl->scan_warps = (int)blocks * warps_per_block;
+    }
     pl->num_segments = pl->scan_warps;
   }
   size_t off = 0;
@@ -241,7 +252,7 @@ static int do_search(Index* ix, const void* Q, int B, int k, int path, float* ou
     }
   } else {
     profile_begin(st);
-    rc = launch_scan_topk(ix, Q, pl, ws, st);
+    rc = pl.scan_bulk ? launch_scan_bulk(ix, Q, pl, ws, st) : launch_scan_topk(ix, Q, pl, ws, st);
     profile_end(st);
     if (rc) return rc;
   }

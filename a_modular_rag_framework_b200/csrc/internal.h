@@ -76,6 +76,7 @@ struct SearchPlan {
   GemmPhase phases[kMaxPhases];
   // scan
   int scan_bq, scan_warps, scan_blocks;
+  int scan_bulk;         // 1: bulk-copy-fed scan (scan_bulk.cu), else the register-fed one (scan_topk.cu)
   // workspace layout (byte offsets)
   int num_groups;        // > 0: two-level final select (lists2/counts2 hold the first level's output)
   size_t off_lists, off_counts, off_gthr, off_qinv, off_lists2, off_counts2, off_qrep, off_end;
@@ -94,6 +95,9 @@ size_t query_replica_bytes(int D);
 int launch_replicate_queries(const void* Q, void* rep, int B, int D, cudaStream_t st);
 int encode_query_tmap_replicated(const Index* ix, const void* rep, CUtensorMap* tmap_q);
 int launch_scan_topk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
+int scan_bulk_warps(const Index* ix);        // consumer warps per CTA of the bulk-fed scan, 0 if it does not apply
+int scan_bulk_tile_rows(const Index* ix);
+int launch_scan_bulk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
 // out_scores == nullptr: threshold mode (publish the exact k-th best so far into gthr); else final output
 struct PeerScatter { int n, rank; unsigned long long base[B200R_MAX_PEERS]; };
 int launch_select_lists(const Index* ix, const SearchPlan& p, void* ws, float* out_scores, int64_t* out_ids, cudaStream_t st,

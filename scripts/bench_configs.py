@@ -167,6 +167,8 @@ CONFIGS = {
     "cfg2_10Mx768_B2_gemm": lambda: run_search("cfg2_10Mx768_B2_gemm", 10_000_000, 768, 2, 100, torch.bfloat16, "gemm", steps=20, check=False),
     "f32_5Mx768_B1_scan": lambda: run_search("f32_5Mx768_B1_scan", 5_000_000, 768, 1, 100, torch.float32, "scan", steps=20),
     "f32_5Mx768_B4_scan": lambda: run_search("f32_5Mx768_B4_scan", 5_000_000, 768, 4, 100, torch.float32, "scan", steps=20),
+    "f32_5Mx768_B8_scan": lambda: run_search("f32_5Mx768_B8_scan", 5_000_000, 768, 8, 100, torch.float32, "scan", steps=20),
+    "f32_5Mx768_B16_scan": lambda: run_search("f32_5Mx768_B16_scan", 5_000_000, 768, 16, 100, torch.float32, "scan", steps=10),
     "i8_10Mx768_B1_scan": lambda: run_search_i8("i8_10Mx768_B1_scan", 10_000_000, 768, 1, 100, steps=20),
     "i8_10Mx768_B4_scan": lambda: run_search_i8("i8_10Mx768_B4_scan", 10_000_000, 768, 4, 100, steps=20),
     "cfg2_10Mx768_B1_gemm": lambda: run_search("cfg2_10Mx768_B1_gemm", 10_000_000, 768, 1, 100, torch.bfloat16, "gemm", steps=20),

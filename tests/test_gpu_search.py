@@ -151,6 +151,33 @@ def test_int8_corpus_scan():
         _check_against_scores(scores, ids, O.score_matrix(Qn, deq, metric), k, 1e-5)
 
 
+@pytest.mark.parametrize("N,D,B,k,dtype", [
+    (150000, 768, 1, 100, torch.float32),      # many tiles per CTA: the stage ring wraps several times
+    (150000, 768, 16, 100, torch.float32),     # two passes of 8 queries
+    (40001, 256, 7, 33, torch.float32),        # ragged last tile, 7 queries in an 8-wide pass
+    (17, 64, 3, 5, torch.float32),             # fewer rows than one tile
+    (1, 16, 1, 1, torch.float32),
+    (300000, 768, 1, 100, torch.int8),
+    (300000, 768, 4, 100, torch.int8),
+    (65537, 384, 7, 1000, torch.int8),         # 4 + 3 queries, k = 1000
+    (63, 32, 2, 10, torch.int8),
+])
+def test_bulk_fed_scan_shapes(N, D, B, k, dtype):
+    """fp32 / int8 corpora take the bulk-copy-fed scan (scan_bulk.cu): tile / stage / pass boundaries."""
+    rng = np.random.default_rng(N + 7 * D + B)
+    Qn = rng.standard_normal((B, D)).astype(np.float32)
+    if dtype == torch.int8:
+        q8, scale = O.quantize_int8_rows(rng.standard_normal((N, D)).astype(np.float32))
+        X = torch.from_numpy(q8).to(_dev())
+        ref = q8.astype(np.float32) * scale[:, None]
+        ix = _index(X, metric="cos", row_scale=torch.from_numpy(scale).to(_dev()))
+    else:
+        ref = rng.standard_normal((N, D)).astype(np.float32)
+        ix = _index(torch.from_numpy(ref).to(_dev()), metric="cos")
+    scores, ids = ix.search(torch.from_numpy(Qn).to(_dev()), k)
+    _check_against_scores(scores, ids, O.score_matrix(Qn, ref, "cos"), k, 1e-5)
+
+
 def test_multi_chunk_large():
     """Several units per CTA and per query (chunked rows, published thresholds)."""
     g = torch.Generator(device="cuda").manual_seed(5)
