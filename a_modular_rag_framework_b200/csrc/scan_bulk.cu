@@ -6,7 +6,7 @@
 // issues one cp.async.bulk (global -> shared, mbarrier complete_tx) per tile of W*R consecutive rows (a contiguous byte
 // range, so no tensor map is needed) into a ring of stages, and W consumer warps read their R rows of the tile from
 // shared memory with conflict-free LDS.128, multiply against the queries staged as float4 "parts" (read once per R
-// rows), butterfly-reduce, and keep the same exact running top-k per (warp, query) as K2: threshold + list + radix
+// rows; int8 corpora instead run on DP4A against the query split into three signed-byte limbs), butterfly-reduce, and keep the same exact running top-k per (warp, query) as K2: threshold + list + radix
 // select (common.cuh), finished by select_lists_kernel.  Registers are free for R*BQ accumulators, so one pass over the
 // corpus serves up to 8 fp32 queries.
 //
@@ -52,6 +52,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) scan_bulk_kernel(const ScanBu
   constexpr int VEC = ElemTraits<T>::kVec;
   constexpr int PARTS = VEC / 4;
   constexpr int TR = W * R;
+  constexpr bool kInt8 = (sizeof(T) == 1);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int chunks = p.D / VEC;
   float4* q4 = reinterpret_cast<float4*>(smem_raw);                                   // [PARTS][BQ][chunks]
@@ -62,11 +63,46 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) scan_bulk_kernel(const ScanBu
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const QT* Qp = reinterpret_cast<const QT*>(p.Q);
-  for (int i = threadIdx.x; i < BQ * p.D; i += (W + 1) * 32) {
-    const int b = i / p.D, d = i % p.D;
-    const float v = (b < p.nq) ? q_to_float<QT>(Qp[(size_t)(p.q0 + b) * p.D + d]) : 0.0f;
-    const int chunk = d / VEC, e = d % VEC;
-    reinterpret_cast<float*>(&q4[((size_t)(e / 4) * BQ + b) * chunks + chunk])[e % 4] = v;
+  __shared__ u32 s_qmax[BQ];      // int8 path: bit image of max|q_b| (non-negative floats order like their bits)
+  __shared__ float s_scale[BQ];   // int8 path: q_b ~= scale_b * (l2*65536 + l1*256 + l0)
+  if constexpr (kInt8) {
+    // int8 corpus: the dot products run on DP4A.  Each query is quantised ONCE to 23-bit fixed point relative to its
+    // largest component (|q - q~| <= 2^-23 max|q|, the size of an fp32 rounding of that component) and split into three
+    // balanced signed-byte limbs, staged as 16-byte planes qL[limb][b][chunk]; the integer sums are exact.
+    if (threadIdx.x < BQ) s_qmax[threadIdx.x] = 0u;
+    __syncthreads();
+    for (int b = 0; b < BQ; ++b) {
+      float m = 0.0f;
+      if (b < p.nq)
+        for (int d = threadIdx.x; d < p.D; d += (W + 1) * 32) m = fmaxf(m, fabsf(q_to_float<QT>(Qp[(size_t)(p.q0 + b) * p.D + d])));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
+      if (lane == 0) atomicMax(&s_qmax[b], __float_as_uint(m));
+    }
+    __syncthreads();
+    int8_t* qL = reinterpret_cast<int8_t*>(smem_raw);
+    for (int i = threadIdx.x; i < BQ * p.D; i += (W + 1) * 32) {
+      const int b = i / p.D, d = i % p.D;
+      const float qmax = __uint_as_float(s_qmax[b]);
+      const float v = (b < p.nq && qmax > 0.0f) ? q_to_float<QT>(Qp[(size_t)(p.q0 + b) * p.D + d]) * (4194304.0f / qmax) : 0.0f;
+      const int qi = __float2int_rn(v);                       // |qi| <= 2^22
+      const int l0 = ((qi + 128) & 255) - 128;
+      const int q1 = (qi - l0) >> 8;
+      const int l1 = ((q1 + 128) & 255) - 128;
+      const int l2 = (q1 - l1) >> 8;                          // |l2| <= 64
+      const int chunk = d / VEC, e = d % VEC;
+      qL[(((size_t)0 * BQ + b) * chunks + chunk) * 16 + e] = (int8_t)l0;
+      qL[(((size_t)1 * BQ + b) * chunks + chunk) * 16 + e] = (int8_t)l1;
+      qL[(((size_t)2 * BQ + b) * chunks + chunk) * 16 + e] = (int8_t)l2;
+    }
+    if (threadIdx.x < BQ) s_scale[threadIdx.x] = __uint_as_float(s_qmax[threadIdx.x]) * (1.0f / 4194304.0f);
+  } else {
+    for (int i = threadIdx.x; i < BQ * p.D; i += (W + 1) * 32) {
+      const int b = i / p.D, d = i % p.D;
+      const float v = (b < p.nq) ? q_to_float<QT>(Qp[(size_t)(p.q0 + b) * p.D + d]) : 0.0f;
+      const int chunk = d / VEC, e = d % VEC;
+      reinterpret_cast<float*>(&q4[((size_t)(e / 4) * BQ + b) * chunks + chunk])[e % 4] = v;
+    }
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, W); }
@@ -122,30 +158,67 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) scan_bulk_kernel(const ScanBu
     const u32 rows = ring + (u32)s * p.tile_bytes + (u32)(warp * R) * row_bytes + (u32)lane * 16u;   // this lane's first chunk
 
     float acc[R][BQ];
+    if constexpr (kInt8) {
+      int ai[R][BQ][3];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+      for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int b = 0; b < BQ; ++b) acc[r][b] = 0.0f;
-    u32 xaddr = rows;
-    for (int chunk = lane; chunk < chunks; chunk += 32, xaddr += 512u) {
-      uint4 xv[R];
+        for (int b = 0; b < BQ; ++b) { ai[r][b][0] = 0; ai[r][b][1] = 0; ai[r][b][2] = 0; }
+      const uint4* qL = reinterpret_cast<const uint4*>(smem_raw);
+      u32 xaddr = rows;
+      for (int chunk = lane; chunk < chunks; chunk += 32, xaddr += 512u) {
+        uint4 xv[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) xv[r] = lds128(xaddr + (u32)r * row_bytes);
+        for (int r = 0; r < R; ++r) xv[r] = lds128(xaddr + (u32)r * row_bytes);
 #pragma unroll
-      for (int part = 0; part < PARTS; ++part) {
-        float4 qv[BQ];
-#pragma unroll
-        for (int b = 0; b < BQ; ++b) qv[b] = q4[((size_t)part * BQ + b) * chunks + chunk];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          float xf[4];
-          ElemTraits<T>::unpack4(xv[r], part, xf);
+        for (int limb = 0; limb < 3; ++limb) {
 #pragma unroll
           for (int b = 0; b < BQ; ++b) {
-            acc[r][b] = fmaf(xf[0], qv[b].x, acc[r][b]);
-            acc[r][b] = fmaf(xf[1], qv[b].y, acc[r][b]);
-            acc[r][b] = fmaf(xf[2], qv[b].z, acc[r][b]);
-            acc[r][b] = fmaf(xf[3], qv[b].w, acc[r][b]);
+            const uint4 qv = qL[((size_t)limb * BQ + b) * chunks + chunk];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              int a = ai[r][b][limb];
+              a = __dp4a((int)xv[r].x, (int)qv.x, a);
+              a = __dp4a((int)xv[r].y, (int)qv.y, a);
+              a = __dp4a((int)xv[r].z, (int)qv.z, a);
+              a = __dp4a((int)xv[r].w, (int)qv.w, a);
+              ai[r][b][limb] = a;
+            }
+          }
+        }
+      }
+      // per-lane partial sums are exact integers (< 2^24 each); combining the limbs rounds like any fp32 sum
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int b = 0; b < BQ; ++b)
+          acc[r][b] = fmaf((float)ai[r][b][2], 65536.0f, fmaf((float)ai[r][b][1], 256.0f, (float)ai[r][b][0]));
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int b = 0; b < BQ; ++b) acc[r][b] = 0.0f;
+      u32 xaddr = rows;
+      for (int chunk = lane; chunk < chunks; chunk += 32, xaddr += 512u) {
+        uint4 xv[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) xv[r] = lds128(xaddr + (u32)r * row_bytes);
+#pragma unroll
+        for (int part = 0; part < PARTS; ++part) {
+          float4 qv[BQ];
+#pragma unroll
+          for (int b = 0; b < BQ; ++b) qv[b] = q4[((size_t)part * BQ + b) * chunks + chunk];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            float xf[4];
+            ElemTraits<T>::unpack4(xv[r], part, xf);
+#pragma unroll
+            for (int b = 0; b < BQ; ++b) {
+              acc[r][b] = fmaf(xf[0], qv[b].x, acc[r][b]);
+              acc[r][b] = fmaf(xf[1], qv[b].y, acc[r][b]);
+              acc[r][b] = fmaf(xf[2], qv[b].z, acc[r][b]);
+              acc[r][b] = fmaf(xf[3], qv[b].w, acc[r][b]);
+            }
           }
         }
       }
@@ -170,6 +243,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) scan_bulk_kernel(const ScanBu
       const float m = __shfl_sync(kFullMask, my_mult, r);
 #pragma unroll
       for (int b = 0; b < BQ; ++b) {
+        if constexpr (kInt8) acc[r][b] *= s_scale[b];
         acc[r][b] *= m;
         pass |= acc[r][b] >= thr[b];
       }
