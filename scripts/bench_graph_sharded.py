@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--streams", type=int, default=1, help="batches in flight (round-robin over this many CUDA streams / stage objects): "
+                    "the collectives and latency-bound kernels of one batch overlap the gather of the next")
     a = ap.parse_args()
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local_rank)
@@ -70,18 +72,38 @@ def main():
         seeds = [sidx.search(Q[i], a.seeds)[1].contiguous() for i in range(nb)]
     else:
         seeds = [local.search(Q[i], a.seeds)[1].contiguous() for i in range(nb)]
-    stage = ShardedGraphStage(local, graph, V)
+    stages = [ShardedGraphStage(local, graph, V) for _ in range(a.streams)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(a.streams)] if a.streams > 1 else [torch.cuda.current_stream(dev)]
+
+    def step(i):
+        j = i % a.streams
+        if a.streams == 1:
+            return stages[0].run(Q[i % nb], seeds[i % nb], 2, 0.4, 0.2, a.k)
+        with torch.cuda.stream(streams[j]):
+            return stages[j].run(Q[i % nb], seeds[i % nb], 2, 0.4, 0.2, a.k)
+
+    def join():
+        cur = torch.cuda.current_stream(dev)
+        for s_ in streams:
+            if s_ is not cur:
+                cur.wait_stream(s_)
+
     for i in range(a.warmup):
-        out = stage.run(Q[i % nb], seeds[i % nb], 2, 0.4, 0.2, a.k)
+        out = step(i)
+    join()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     _native.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if a.streams > 1:
+        for s_ in streams:
+            s_.wait_stream(torch.cuda.current_stream(dev))
     e0.record()
     for i in range(a.steps):
-        out = stage.run(Q[i % nb], seeds[i % nb], 2, 0.4, 0.2, a.k)
+        out = step(i)
+    join()
     e1.record()
     torch.cuda.synchronize()
     gms, gn = _native.profile_read()
@@ -99,7 +121,7 @@ def main():
     if rank == 0:
         ncand = out["ncand"].float().mean().item()
         print(json.dumps({"config": "cfg4_graph_sharded", "n_gpus": world, "nodes": V, "edges_directed": 2 * a.edges, "dim": D, "batch": B,
-                          "seeds": a.seeds, "k": a.k, "window": 2, "ms_per_batch": ms, "queries_per_s": B / (ms * 1e-3),
+                          "seeds": a.seeds, "k": a.k, "window": 2, "batches_in_flight": a.streams, "ms_per_batch": ms, "queries_per_s": B / (ms * 1e-3),
                           "avg_candidates": ncand, "overflowed_queries": int((out["status"] != 0).sum().item()), "per_rank": allr}), flush=True)
     if world > 1:
         dist.barrier()
