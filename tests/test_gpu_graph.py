@@ -171,3 +171,42 @@ def test_wide_embeddings_3072():
     for b in range(B):
         top, dist = O.expand_rescore(Q[b], X, row_ptr, col_idx, seeds[b], 2, 0.4, 0.2, k)
         _check_query(out, b, top, dist, k)
+
+
+def test_flat_channels_tie_to_lower_id_and_padding():
+    """Constant embeddings (every cosine equal -> dense channel all 0.0, retrieval_backend.py:300) and window 0 (every hop
+    0 -> graph channel all 0.0): every fused score is 0.0, so the stable sort keeps id order; k beyond the candidate count
+    pads with (-inf, -1)."""
+    V, D, k = 500, 32, 12
+    X = np.ones((V, D), dtype=np.float32)
+    row_ptr, col_idx = O.csr_from_edges(V, np.arange(0, V - 1), np.arange(1, V))
+    seeds = np.array([[400, 7, 123, 7, 55, -1, 300, 8, 9]])
+    out = _run(X, np.ones((1, D), dtype=np.float32), row_ptr, col_idx, seeds, 0, 0.4, 0.2, k)
+    want = sorted({400, 7, 123, 55, 300, 8, 9})
+    ids = out["id"][0].cpu().numpy()
+    assert int(out["ncand"][0]) == len(want)
+    assert ids[:len(want)].tolist() == want
+    assert np.all(ids[len(want):] == -1)
+    assert np.all(out["score"][0].cpu().numpy()[:len(want)] == 0.0)
+    assert np.all(np.isneginf(out["score"][0].cpu().numpy()[len(want):]))
+    # window 1 on the path graph: hop-0 nodes outrank hop-1 nodes (graph channel 1.0 vs 0.0), ties still by id
+    out = _run(X, np.ones((1, D), dtype=np.float32), row_ptr, col_idx, [[10, 20]], 1, 0.4, 0.2, 6)
+    assert out["id"][0].cpu().numpy().tolist() == [10, 20, 9, 11, 19, 21]
+    assert out["hop"][0].cpu().numpy().tolist() == [0, 0, 1, 1, 1, 1]
+
+
+def test_single_query_and_many_queries_agree():
+    """The grid-wide gather splits the flat work list differently for B = 1 and B = 300; results must not depend on it."""
+    rng = np.random.default_rng(77)
+    V, E, D, S, k = 50000, 300000, 96, 20, 10
+    row_ptr, col_idx = O.csr_from_edges(V, rng.integers(0, V, E), rng.integers(0, V, E))
+    X = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((V, D)).astype(np.float32)))
+    Q = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((300, D)).astype(np.float32)))
+    seeds = rng.integers(0, V, size=(300, S))
+    big = _run(X, Q, row_ptr, col_idx, seeds, 2, 0.4, 0.2, k)
+    for b in (0, 150, 299):
+        one = _run(X, Q[b:b + 1], row_ptr, col_idx, seeds[b:b + 1], 2, 0.4, 0.2, k)
+        assert torch.equal(one["id"][0], big["id"][b])
+        assert torch.equal(one["score"][0], big["score"][b])
+        assert torch.equal(one["cos"][0], big["cos"][b])
+        assert int(one["ncand"][0]) == int(big["ncand"][b])

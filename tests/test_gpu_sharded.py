@@ -161,3 +161,40 @@ def test_graph_stage_virtual_shards_equal_single_gpu():
         top, dist_ = O.expand_rescore(Qn[b], np.concatenate([Xn, np.zeros((500, D), np.float32)]), row_ptr, col_idx,
                                       seeds[b].cpu().numpy(), 2, 0.4, 0.2, k)
         assert np.allclose(out["score"][b].cpu().numpy()[:len(top)], [t[1] for t in top], atol=2e-3)
+
+
+def test_graph_stage_ranks_that_own_no_candidates():
+    """All seeds and their neighbourhoods live in the first shard's row block: the other virtual ranks own nothing, report
+    (+inf, -inf) cosine ranges and all-padding lists, and the merge must still equal the single-launch result."""
+    from a_modular_rag_framework_b200 import DenseIndex, PassageGraph, expand_rescore
+    from a_modular_rag_framework_b200.index import ExpandShardState, expand_rescore_pass
+    from a_modular_rag_framework_b200.sharded import combine_shard_records, owned_range, shard_rows
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(5)
+    V, D, B, S, k, G = 9000, 64, 5, 6, 8, 3
+    src, dst = rng.integers(0, 2000, 8000), rng.integers(0, 2000, 8000)       # edges only among nodes < 2000 (shard 0: rows < 3000)
+    row_ptr, col_idx = O.csr_from_edges(V, src, dst)
+    X = torch.from_numpy(rng.standard_normal((V, D)).astype(np.float32)).to(dev).to(torch.bfloat16)
+    Q = torch.from_numpy(rng.standard_normal((B, D)).astype(np.float32)).to(dev).to(torch.bfloat16)
+    seeds = torch.from_numpy(rng.integers(0, 2000, size=(B, S))).to(dev)
+    graph = PassageGraph(torch.from_numpy(row_ptr).to(dev), torch.from_numpy(col_idx).to(dev))
+    ref = expand_rescore(DenseIndex(X), graph, Q, seeds, 2, 0.4, 0.2, k)
+    shards, states = [], []
+    for r in range(G):
+        lo, hi = shard_rows(V, G, r)
+        ix = DenseIndex(X[lo:hi], id_base=lo)
+        st = ExpandShardState(ix, B, k)
+        expand_rescore_pass(ix, graph, Q, seeds, 2, 0.4, 0.2, k, st, 1, *owned_range(V, G, r))
+        shards.append(ix); states.append(st)
+    assert torch.isinf(states[1].minmax).all() and torch.isinf(states[2].minmax).all()
+    mn = torch.stack([s.minmax[:, 0] for s in states]).min(0).values
+    mx = torch.stack([s.minmax[:, 1] for s in states]).max(0).values
+    for r, (ix, st) in enumerate(zip(shards, states)):
+        st.minmax[:, 0], st.minmax[:, 1] = mn, mx
+        expand_rescore_pass(ix, graph, Q, seeds, 2, 0.4, 0.2, k, st, 2, *owned_range(V, G, r))
+    assert (states[1].out["id"] == -1).all() and (states[2].out["id"] == -1).all()
+    out = combine_shard_records(states[0].views(torch.stack([s.record for s in states])), states[0].out["ncand"], states[0].out["status"], k)
+    for key in ("id", "hop", "ncand"):
+        assert torch.equal(out[key], ref[key])
+    assert torch.allclose(out["score"], ref["score"], atol=1e-6)
+    assert torch.equal(out["cos"], ref["cos"])
