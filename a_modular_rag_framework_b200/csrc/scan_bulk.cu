@@ -148,12 +148,20 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) scan_bulk_kernel(const ScanBu
     list[b] = p.lists + ((size_t)gw * p.Bpad + (size_t)(p.q0 + (valid ? b : 0))) * (size_t)p.cap;
   }
 
+  // lane r holds row r's multiplier (NaN = past the end: never passes), fetched ONE TILE AHEAD: the ring usually has the
+  // next tile resident already, so a load issued at the top of the tile would be waited for in full
+  auto load_mult = [&](int t) {
+    const long long row = cta_begin + (long long)t * TR + (long long)warp * R + lane;
+    float m = __int_as_float(0x7fc00000);
+    if (lane < R && t < ntiles && row < cta_end) m = p.row_mult ? __ldg(p.row_mult + row) : 1.0f;
+    return m;
+  };
+  float next_mult = load_mult(0);
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % p.stages;
     const long long r0 = cta_begin + (long long)t * TR + (long long)warp * R;     // this warp's first row of the tile
-    // lane r fetches row r's multiplier while the tile is still in flight (NaN = past the end: never passes)
-    float my_mult = __int_as_float(0x7fc00000);
-    if (lane < R && r0 + lane < cta_end) my_mult = p.row_mult ? __ldg(p.row_mult + r0 + lane) : 1.0f;
+    const float my_mult = next_mult;
+    next_mult = load_mult(t + 1);
     mbar_wait(full + s, (u32)((t / p.stages) & 1));
     const u32 rows = ring + (u32)s * p.tile_bytes + (u32)(warp * R) * row_bytes + (u32)lane * 16u;   // this lane's first chunk
 
