@@ -65,10 +65,12 @@ int encode_tmap_2d(CUtensorMap* tm, int dtype, const void* base, uint64_t inner,
     fn = reinterpret_cast<EncodeTiledFn>(sym);
   }
   const cuuint64_t dims[2] = {inner, outer};
-  const cuuint64_t strides[1] = {inner * 2};  // bytes; bf16/f16 only
+  if (dtype != B200R_BF16 && dtype != B200R_F16 && dtype != B200R_I8) { set_error("no tensor map for dtype %d", dtype); return B200R_EINVAL; }
+  const cuuint64_t strides[1] = {inner * (dtype == B200R_I8 ? 1 : 2)};  // bytes
   const cuuint32_t box[2] = {box_inner, box_outer};
   const cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapDataType dt = (dtype == B200R_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapDataType dt = (dtype == B200R_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : (dtype == B200R_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
   // 256-byte L2 promotion measured best for the streamed corpus tiles (5.22 vs 5.10 TB/s with 128 B / none)
   CUresult r = fn(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -98,9 +100,12 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   // measured on B200 (10M x 768 bf16): with the query tile replicated in global memory the tcgen05 tile kernel streams
   // the corpus at 6.9-7.0 TB/s (105% of the measured copy bandwidth) for every B from 1 to 128 and is tensor-bound
   // beyond; the CUDA-core scan (6.7 TB/s at B=1, 5.6 at B=2) serves fp32 / int8 / odd-D corpora
-  if (path == B200R_PATH_AUTO) path = gemm_ok ? B200R_PATH_GEMM : B200R_PATH_SCAN;
-  if (path == B200R_PATH_GEMM && !gemm_ok) {
-    set_error("gemm path needs a bf16/f16 corpus with D %% 8 == 0 (dtype=%d D=%d)", ix->dtype, ix->D);
+  // int8 corpora with up to 16 queries: tcgen05 kind::i8 with the queries split into signed-byte limbs (rows_i8.cu)
+  const bool i8_ok = ix->has_tmap_i8 && rows_i8_stages(B, ix->D) > 0;
+  if (path == B200R_PATH_AUTO) path = (gemm_ok || i8_ok) ? B200R_PATH_GEMM : B200R_PATH_SCAN;
+  if (path == B200R_PATH_GEMM && !gemm_ok && !i8_ok) {
+    set_error("tensor path needs a bf16/f16 corpus with D %% 8 == 0, or an int8 corpus with B <= %d (dtype=%d D=%d B=%d)", rows_i8_nq(),
+              ix->dtype, ix->D, B);
     return B200R_EINVAL;
   }
   if (path != B200R_PATH_GEMM && path != B200R_PATH_SCAN) { set_error("bad path %d", path); return B200R_EINVAL; }
@@ -109,10 +114,12 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   pl->cap_soft = list_cap_soft(k); pl->cap = list_cap(k);
   if (path == B200R_PATH_GEMM) {
     // more than one 128-query tile: pair the CTAs (cta_group::2) so each loads half of every corpus tile
-    pl->cta_group = (B > gemm_tile_queries() && g_cta_group_max >= 2) ? 2 : 1;
-    const int BMq = gemm_tile_queries() * pl->cta_group;
-    const int BNr = gemm_tile_rows();
-    const int list_rows_per_tile = BNr;      // rows one list can receive from one tile
+    // int8: rows-mode kernel (corpus rows on the MMA's M, 128-row tiles, one list per epilogue warp)
+    pl->rows_i8 = (ix->dtype == B200R_I8) ? 1 : 0;
+    pl->cta_group = (!pl->rows_i8 && B > gemm_tile_queries() && g_cta_group_max >= 2) ? 2 : 1;
+    const int BMq = pl->rows_i8 ? rows_i8_nq() : gemm_tile_queries() * pl->cta_group;
+    const int BNr = pl->rows_i8 ? rows_i8_tile_rows() : gemm_tile_rows();
+    const int list_rows_per_tile = pl->rows_i8 ? 32 : BNr;      // rows one list can receive from one tile
     pl->num_q_tiles = (B + BMq - 1) / BMq;
     pl->num_row_tiles = (int)((ix->N + BNr - 1) / BNr);
     pl->Bpad = pl->num_q_tiles * BMq;
@@ -168,7 +175,7 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
       seen = end; ++np;
     }
     pl->num_phases = np;
-    pl->num_segments = pl->num_chunks;
+    pl->num_segments = pl->num_chunks * (pl->rows_i8 ? 4 : 1);
   } else {
     pl->Bpad = B;
     const int bulk_warps = scan_bulk_warps(ix);
@@ -203,8 +210,9 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
     pl->off_lists2 = off; off += align_up((size_t)pl->num_groups * pl->Bpad * pl->k * 8, 256);
     pl->off_counts2 = off; off += align_up((size_t)pl->num_groups * pl->Bpad * 4, 256);
   }
-  pl->q_replicas = (path == B200R_PATH_GEMM && pl->cta_group == 1 && pl->num_q_tiles == 1 && g_q_replicas) ? 1 : 0;
+  pl->q_replicas = (path == B200R_PATH_GEMM && !pl->rows_i8 && pl->cta_group == 1 && pl->num_q_tiles == 1 && g_q_replicas) ? 1 : 0;
   if (pl->q_replicas) { pl->off_qrep = off; off += align_up(query_replica_bytes(ix->D), 256); }
+  if (pl->rows_i8) { pl->off_qrep = off; off += align_up(rows_i8_query_bytes(ix->D), 256); }   // quantised query limbs + scales
   pl->off_end = off;
   return B200R_OK;
 }
@@ -233,7 +241,19 @@ static int do_search(Index* ix, const void* Q, int B, int k, int path, float* ou
   }
   const bool floor_on = min_score > -HUGE_VALF;
   if (floor_on && (rc = launch_min_score(pl, ws, ix->metric == B200R_COS, min_score, st))) return rc;
-  if (pl.path == B200R_PATH_GEMM) {
+  if (pl.path == B200R_PATH_GEMM && pl.rows_i8) {
+    CUtensorMap tmap_q;
+    void* qws = (char*)ws + pl.off_qrep;
+    if ((rc = launch_quantize_queries_i8(Q, B, ix->D, qws, st))) return rc;
+    if ((rc = encode_query_tmap_i8(qws, ix->D, &tmap_q))) return rc;
+    for (int i = 0; i < pl.num_phases; ++i) {
+      profile_begin(st);
+      rc = launch_rows_i8(ix, &tmap_q, qws, pl, pl.phases[i], ws, st);
+      profile_end(st);
+      if (rc) return rc;
+      if (i + 1 < pl.num_phases && (rc = launch_select_lists(ix, pl, ws, nullptr, nullptr, st))) return rc;
+    }
+  } else if (pl.path == B200R_PATH_GEMM) {
     CUtensorMap tmap_q;
     if (pl.q_replicas) {
       void* rep = (char*)ws + pl.off_qrep;
@@ -308,6 +328,11 @@ int b200r_index_create(int device, const void* X, int64_t N, int32_t D, int32_t 
     if (!rc) rc = encode_tmap_2d(&ix->tmap_x_half, dtype, X, (uint64_t)D, (uint64_t)N, 64, (uint32_t)gemm_tile_rows() / 2);
     if (rc) { if (ix->row_mult) cudaFree(ix->row_mult); delete ix; return rc; }
     ix->has_tmap = true;
+  }
+  if (dtype == B200R_I8) {   // int8 tensor path (rows_i8.cu): tiles of 128 rows x 128 bytes
+    int rc = encode_tmap_2d(&ix->tmap_x_i8, dtype, X, (uint64_t)D, (uint64_t)N, 128, (uint32_t)rows_i8_tile_rows());
+    if (rc) { if (ix->row_mult) cudaFree(ix->row_mult); delete ix; return rc; }
+    ix->has_tmap_i8 = true;
   }
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {

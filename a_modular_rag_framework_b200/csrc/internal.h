@@ -35,6 +35,8 @@ struct Index {
   bool has_tmap;        // X tensor map valid (bf16/f16, D % 8 == 0)
   CUtensorMap tmap_x;        // box 64 x 256 rows (one CTA per tile)
   CUtensorMap tmap_x_half;   // box 64 x 128 rows (CTA pair, each CTA loads half of the tile's rows)
+  bool has_tmap_i8;          // int8 corpus: tensor map for the kind::i8 rows-mode kernel
+  CUtensorMap tmap_x_i8;     // box 128 bytes x 128 rows
   // staging for b200r_search_host
   void* h_q_dev; size_t q_dev_bytes;
   float* h_s_dev; int64_t* h_i_dev; size_t out_dev_elems;
@@ -70,6 +72,7 @@ struct SearchPlan {
   // gemm: row tiles are processed in phases [tile_begin, tile_end) of geometrically growing size; after each
   // phase the exact k-th best so far becomes every query's filter threshold for the next one
   int cta_group;         // 1 or 2 (CTA pair, cta_group::2)
+  int rows_i8;           // 1: int8 tensor path (rows_i8.cu): 16-query slots, 128-row tiles, 4 lists per unit
   int q_replicas;        // 1: single query tile replicated in the workspace (off_qrep) against L2 hot-spotting
   int num_q_tiles, num_row_tiles, num_chunks;   // num_q_tiles counts tiles of cta_group*128 queries
   int num_phases;
@@ -95,6 +98,13 @@ size_t query_replica_bytes(int D);
 int launch_replicate_queries(const void* Q, void* rep, int B, int D, cudaStream_t st);
 int encode_query_tmap_replicated(const Index* ix, const void* rep, CUtensorMap* tmap_q);
 int launch_scan_topk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
+int rows_i8_nq();
+int rows_i8_tile_rows();
+int rows_i8_stages(int B, int D);
+size_t rows_i8_query_bytes(int D);
+int launch_quantize_queries_i8(const void* Q, int B, int D, void* qws, cudaStream_t st);
+int encode_query_tmap_i8(const void* qws, int D, CUtensorMap* tmap_q);
+int launch_rows_i8(const Index* ix, const CUtensorMap* tmap_q, const void* qws, const SearchPlan& p, const GemmPhase& ph, void* ws, cudaStream_t st);
 int scan_bulk_warps(const Index* ix);        // consumer warps per CTA of the bulk-fed scan, 0 if it does not apply
 int scan_bulk_tile_rows(const Index* ix);
 int launch_scan_bulk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);

@@ -1,0 +1,325 @@
+// rows_i8.cu -- K1c: int8 corpora on the tensor cores (tcgen05 kind::i8), up to 16 queries per corpus pass.
+//
+// Same contract as K1/K2 (exact cosine / IP top-k; reference retrieval_backend.py:192-197, 371-372).  The CUDA-core
+// scans cannot keep up with HBM for int8 rows once there is more than one query (DP4A issues at ~16 lanes/clk/SM, the
+// PRMT/FADD/FFMA unpack is slower still), so the dot products go to the int8 tensor pipe, with the operands laid out
+// for streaming:
+//   * the 128 corpus rows of a tile are the MMA's M (TMEM lanes); tiles of [128 rows x 128 bytes] arrive by TMA
+//     (SWIZZLE_128B) in a ring of up to 12 stages that carries corpus data only;
+//   * the queries are quantised ONCE per search to 23-bit fixed point relative to their largest component
+//     (|q - q~| <= 2^-23 max|q|) and split into three balanced signed-byte limbs; the 3 x 16 limb rows are the MMA's N
+//     (48 TMEM columns) and stay RESIDENT in shared memory;
+//   * accumulation is exact int32; the epilogue thread (= TMEM lane = one corpus row) recombines the limbs of each
+//     query in fp32 (a2*65536 + a1*256 + a0), applies the query scale and the row multiplier and tests the 16 scores
+//     against the per-query thresholds.  Survivors are appended per (warp, query) with a ballot; lists, thresholds,
+//     phases and pruning exactly as in K1.
+// Roofline: HBM, N*D bytes per batch of <= 16 queries.
+#include "common.cuh"
+#include "internal.h"
+#include "tc_ptx.cuh"
+#include <math_constants.h>
+#include <cstring>
+
+namespace b200r {
+
+constexpr int RI_ROWS = 128;          // corpus rows per tile
+constexpr int RI_BK = 128;            // int8 elements per K slice = one 128-byte swizzle row
+constexpr int RI_STAGE_BYTES = RI_ROWS * RI_BK;   // 16 KB
+constexpr int RI_THREADS = 192;
+constexpr int RI_ACC = 4;             // accumulator stages in TMEM
+constexpr int RI_NQ = 16;             // queries per pass
+constexpr int RI_NCOLS = 3 * RI_NQ;   // limb rows = MMA N
+constexpr int RI_ACC_STRIDE = 64;     // TMEM columns between accumulator stages
+constexpr int RI_Q_KB_BYTES = RI_NCOLS * RI_BK;   // 6 KB per K slice of the resident limb block (6 swizzle atoms)
+
+struct RowsI8Params {
+  int B, k, D, num_kb, stages;
+  long long N;
+  int tile_begin, tile_end, tiles_per_chunk, num_units;
+  int cap, cap_soft, Bpad;
+  const float* row_mult;
+  const float* qscale;     // [RI_NQ] q_j ~= qscale[j] * (l2*65536 + l1*256 + l0)
+  u64* lists;
+  int* counts;
+  u32* gthr;
+  u32 idesc;
+};
+
+// ---- query quantisation: f32 [B, D] -> limb planes int8 [3][RI_NQ][D] + scale[RI_NQ] -------------------------
+__global__ void quantize_queries_i8_kernel(const float* __restrict__ Q, int B, int D, int8_t* __restrict__ limbs, float* __restrict__ scale) {
+  const int j = blockIdx.x;        // query slot 0..RI_NQ-1
+  __shared__ float s_max[32];
+  float m = 0.0f;
+  if (j < B)
+    for (int d = threadIdx.x; d < D; d += blockDim.x) m = fmaxf(m, fabsf(Q[(size_t)j * D + d]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+  __syncthreads();
+  float qmax = 0.0f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) qmax = fmaxf(qmax, s_max[w]);
+  const float inv = qmax > 0.0f ? 4194304.0f / qmax : 0.0f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const int qi = (j < B) ? __float2int_rn(Q[(size_t)j * D + d] * inv) : 0;      // |qi| <= 2^22
+    const int l0 = ((qi + 128) & 255) - 128;
+    const int q1 = (qi - l0) >> 8;
+    const int l1 = ((q1 + 128) & 255) - 128;
+    const int l2 = (q1 - l1) >> 8;                                               // |l2| <= 64
+    limbs[((size_t)0 * RI_NQ + j) * D + d] = (int8_t)l0;
+    limbs[((size_t)1 * RI_NQ + j) * D + d] = (int8_t)l1;
+    limbs[((size_t)2 * RI_NQ + j) * D + d] = (int8_t)l2;
+  }
+  if (threadIdx.x == 0) scale[j] = qmax * (1.0f / 4194304.0f);
+}
+
+__global__ void __launch_bounds__(RI_THREADS, 1)
+rows_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, const RowsI8Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const u32 raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  uint8_t* smem_q = smem;                                       // [num_kb][48 x 128 B]
+  uint8_t* smem_x = smem + (size_t)p.num_kb * RI_Q_KB_BYTES;    // [stages][128 x 128 B]
+  uint8_t* tail = smem_x + (size_t)p.stages * RI_STAGE_BYTES;
+  u32* smem_hist = reinterpret_cast<u32*>(tail);                // [4][256]
+  float* thr_s = reinterpret_cast<float*>(smem_hist + 4 * 256); // [4][NQ]
+  u64* kth_s = reinterpret_cast<u64*>(thr_s + 4 * RI_NQ);       // [4][NQ]
+  int* cnt_s = reinterpret_cast<int*>(kth_s + 4 * RI_NQ);       // [4][NQ]
+  float* qscale_s = reinterpret_cast<float*>(cnt_s + 4 * RI_NQ);   // [NQ]
+  u64* bars = reinterpret_cast<u64*>(qscale_s + RI_NQ);
+  u64* full_bar = bars;                      // [stages] (<= 12)
+  u64* empty_bar = bars + 12;                // [stages]
+  u64* tmem_full_bar = bars + 24;            // [RI_ACC]
+  u64* tmem_empty_bar = bars + 24 + RI_ACC;  // [RI_ACC]
+  u64* q_bar = bars + 24 + 2 * RI_ACC;
+  u32* tmem_ptr_smem = reinterpret_cast<u32*>(bars + 25 + 2 * RI_ACC);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+  constexpr u32 TMEM_COLS = RI_ACC * RI_ACC_STRIDE;   // 256
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_x);
+    for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < RI_ACC; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+    mbar_init(q_bar, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < RI_NQ) qscale_s[threadIdx.x] = p.qscale[threadIdx.x];
+  if (warp_idx == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const u32 tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      // the limb block, once: num_kb slices of [48 limb rows x 128 bytes] (columns >= D are zero-filled by TMA)
+      mbar_expect_tx(q_bar, (u32)(p.num_kb * RI_Q_KB_BYTES));
+      for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(smem_q + (size_t)kb * RI_Q_KB_BYTES, &tmap_q, q_bar, kb * RI_BK, 0, kEvictLast);
+      int stage = 0; u32 phase = 0;
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+        const int t0 = p.tile_begin + u * p.tiles_per_chunk;
+        const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], RI_STAGE_BYTES);
+            tma_load_2d(smem_x + (size_t)stage * RI_STAGE_BYTES, &tmap_x, &full_bar[stage], kb * RI_BK, t * RI_ROWS, kEvictFirst);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      mbar_wait(q_bar, 0);
+      int stage = 0; u32 phase = 0;
+      u32 tile_iter = 0;
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+        const int t0 = p.tile_begin + u * p.tiles_per_chunk;
+        const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
+        for (int t = t0; t < t1; ++t, ++tile_iter) {
+          const u32 acc = tile_iter % RI_ACC;
+          mbar_wait(&tmem_empty_bar[acc], ((tile_iter / RI_ACC) & 1) ^ 1);
+          tc_fence_after();
+          const u32 tmem_d = tmem_base + acc * RI_ACC_STRIDE;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const u64 desc_a = make_smem_desc(smem_u32(smem_x + (size_t)stage * RI_STAGE_BYTES));   // corpus rows = M
+            const u64 desc_b = make_smem_desc(smem_u32(smem_q + (size_t)kb * RI_Q_KB_BYTES));       // limb rows = N
+#pragma unroll
+            for (int kk = 0; kk < RI_BK / 32; ++kk)      // K = 32 int8 = 32 bytes per instruction
+              umma_i8(tmem_d, desc_a + (u64)(kk * 2), desc_b + (u64)(kk * 2), p.idesc, (kb | kk) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+            if (kb == p.num_kb - 1) umma_commit(&tmem_full_bar[acc]);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int quarter = warp_idx & 3;          // TMEM lane quarter this warp may access == rows 32*quarter.. of the tile
+    const int ew = warp_idx - 2;               // 0..3: index of this warp's lists / thresholds
+    u32* hist = smem_hist + ew * 256;
+    float* thr = thr_s + ew * RI_NQ;
+    u64* kth = kth_s + ew * RI_NQ;
+    int* cnt = cnt_s + ew * RI_NQ;
+    u32 tile_iter = 0;
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      const int t0 = p.tile_begin + u * p.tiles_per_chunk;
+      const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
+      if (t0 >= t1) continue;
+      const size_t seg = (size_t)u * 4 + ew;               // this warp's list segment for the unit's row chunk
+      for (int j = lane; j < RI_NQ; j += 32) {
+        const bool valid = j < p.B;
+        thr[j] = valid ? ordered_to_f32(__ldcg(p.gthr + j)) : __int_as_float(0x7f800000);
+        kth[j] = 0;
+        cnt[j] = valid ? __ldcg(p.counts + seg * p.Bpad + j) : 0;
+      }
+      __syncwarp();
+      for (int t = t0; t < t1; ++t, ++tile_iter) {
+        const u32 acc = tile_iter % RI_ACC;
+        const long long row = (long long)t * RI_ROWS + quarter * 32 + lane;
+        const float m = (row < p.N) ? (p.row_mult ? __ldg(p.row_mult + row) : 1.0f) : __int_as_float(0x7fc00000);
+        mbar_wait(&tmem_full_bar[acc], (tile_iter / RI_ACC) & 1);
+        tc_fence_after();
+        const u32 taddr = tmem_base + ((u32)(quarter * 32) << 16) + acc * RI_ACC_STRIDE;
+        u32 a0[RI_NQ], a1[RI_NQ], a2[RI_NQ];
+        tmem_ld16(taddr, a0);
+        tmem_ld16(taddr + RI_NQ, a1);
+        tmem_ld16(taddr + 2 * RI_NQ, a2);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        float s[RI_NQ];
+#pragma unroll
+        for (int j = 0; j < RI_NQ; ++j) {
+          // exact integer limb sums -> fp32 (the same recombination as the DP4A scan); NaN m for rows beyond N never passes
+          const float v = fmaf((float)(int)a2[j], 65536.0f, fmaf((float)(int)a1[j], 256.0f, (float)(int)a0[j]));
+          s[j] = (v * qscale_s[j]) * m;
+        }
+
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < RI_NQ; ++j) any |= (s[j] >= thr[j]);
+        if (__any_sync(kFullMask, any)) {
+#pragma unroll
+          for (int j = 0; j < RI_NQ; ++j) {
+            const float tj = thr[j];
+            const u32 b = __ballot_sync(kFullMask, s[j] >= tj);
+            if (b) {                                          // warp-uniform
+              const u64 key = make_key(s[j], (u32)row);
+              const u32 b2 = __ballot_sync(kFullMask, (s[j] >= tj) && key > kth[j]);
+              if (b2) {
+                const int base = cnt[j];
+                u64* lp = p.lists + (seg * p.Bpad + j) * (size_t)p.cap;
+                if ((b2 >> lane) & 1u) __stcg(lp + base + __popc(b2 & ((1u << lane) - 1u)), key);
+                const int n = base + __popc(b2);
+                __syncwarp();
+                if (n >= p.cap_soft) {
+                  const u64 kk = warp_compact(lp, n, p.k, hist);
+                  if (lane == 0) {
+                    kth[j] = kk; thr[j] = fmaxf(tj, key_score(kk)); cnt[j] = p.k;
+                    atomicMax(p.gthr + j, (u32)(kk >> 32));
+                  }
+                } else if (lane == 0) {
+                  cnt[j] = n;
+                }
+                __syncwarp();
+              }
+            }
+          }
+        }
+        // thresholds published by other CTAs / warps
+        for (int j = lane; j < RI_NQ; j += 32)
+          if (j < p.B) thr[j] = fmaxf(thr[j], ordered_to_f32(__ldcg(p.gthr + j)));
+        __syncwarp();
+      }
+      for (int j = lane; j < RI_NQ; j += 32)
+        if (j < p.B) p.counts[seg * p.Bpad + j] = cnt[j];
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+static size_t rows_i8_smem_bytes(int num_kb, int stages) {
+  return 1024 + (size_t)num_kb * RI_Q_KB_BYTES + (size_t)stages * RI_STAGE_BYTES + 4 * 256 * 4 + (size_t)4 * RI_NQ * (4 + 8 + 4) +
+         RI_NQ * 4 + (26 + 2 * RI_ACC) * 8 + 16;
+}
+
+int rows_i8_nq() { return RI_NQ; }
+int rows_i8_tile_rows() { return RI_ROWS; }
+
+// ring stages that fit next to the resident limb block; 0 = the kernel does not apply (B200R_ROWS_I8=0 switches it off)
+int rows_i8_stages(int B, int D) {
+  static const bool off = [] { const char* e = getenv("B200R_ROWS_I8"); return e && e[0] == '0'; }();
+  if (off || B > RI_NQ) return 0;
+  const int num_kb = (D + RI_BK - 1) / RI_BK;
+  int stages = 12;
+  while (stages >= 4 && rows_i8_smem_bytes(num_kb, stages) > 227 * 1024) --stages;
+  return stages >= 4 ? stages : 0;
+}
+
+// workspace for the quantised queries: limb planes [3][RI_NQ][D] int8, then RI_NQ scales
+size_t rows_i8_query_bytes(int D) { return align_up((size_t)RI_NCOLS * D, 256) + 256; }
+
+int launch_quantize_queries_i8(const void* Q, int B, int D, void* qws, cudaStream_t st) {
+  int8_t* limbs = reinterpret_cast<int8_t*>(qws);
+  float* scale = reinterpret_cast<float*>(reinterpret_cast<char*>(qws) + align_up((size_t)RI_NCOLS * D, 256));
+  quantize_queries_i8_kernel<<<RI_NQ, 256, 0, st>>>(reinterpret_cast<const float*>(Q), B, D, limbs, scale);
+  count_launch();
+  B200R_CUDA_CHECK(cudaGetLastError());
+  return B200R_OK;
+}
+
+int encode_query_tmap_i8(const void* qws, int D, CUtensorMap* tmap_q) {
+  return encode_tmap_2d(tmap_q, B200R_I8, qws, (uint64_t)D, (uint64_t)RI_NCOLS, RI_BK, RI_NCOLS);
+}
+
+int launch_rows_i8(const Index* ix, const CUtensorMap* tmap_q, const void* qws, const SearchPlan& pl, const GemmPhase& ph, void* ws,
+                   cudaStream_t st) {
+  RowsI8Params p;
+  p.B = pl.B; p.k = pl.k; p.D = ix->D; p.N = ix->N;
+  p.num_kb = (ix->D + RI_BK - 1) / RI_BK;
+  p.stages = rows_i8_stages(pl.B, ix->D);
+  if (!p.stages) { set_error("int8 tensor path: B=%d / D=%d not supported", pl.B, ix->D); return B200R_EINVAL; }
+  p.tile_begin = ph.tile_begin; p.tile_end = ph.tile_end; p.tiles_per_chunk = ph.tiles_per_chunk;
+  p.num_units = ph.num_chunks;
+  p.cap = pl.cap; p.cap_soft = pl.cap_soft; p.Bpad = pl.Bpad;
+  p.row_mult = ix->row_mult;
+  p.qscale = reinterpret_cast<const float*>(reinterpret_cast<const char*>(qws) + align_up((size_t)RI_NCOLS * ix->D, 256));
+  p.lists = reinterpret_cast<u64*>((char*)ws + pl.off_lists);
+  p.counts = reinterpret_cast<int*>((char*)ws + pl.off_counts);
+  p.gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
+  // instruction descriptor: D = s32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), K-major both, N >> 3, M >> 4
+  p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((u32)(RI_NCOLS >> 3) << 17) | ((u32)(RI_ROWS >> 4) << 24);
+  const size_t smem = rows_i8_smem_bytes(p.num_kb, p.stages);
+  B200R_CUDA_CHECK(cudaFuncSetAttribute(rows_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = p.num_units < kNumSMs ? p.num_units : kNumSMs;
+  rows_i8_kernel<<<grid, RI_THREADS, smem, st>>>(*tmap_q, ix->tmap_x_i8, p);
+  count_launch();
+  B200R_CUDA_CHECK(cudaGetLastError());
+  return B200R_OK;
+}
+
+}  // namespace b200r

@@ -81,7 +81,7 @@ def run_search(name, N, D, B, k, dtype, path, steps=10, warmup=3, check=True):
     return line
 
 
-def run_search_i8(name, N, D, B, k, steps=10, warmup=3):
+def run_search_i8(name, N, D, B, k, steps=10, warmup=3, path="auto"):
     Xf = corpus(N, D, torch.float16)
     X = torch.empty((N, D), dtype=torch.int8, device=dev)
     blk = 1 << 20
@@ -91,21 +91,23 @@ def run_search_i8(name, N, D, B, k, steps=10, warmup=3):
     Q = queries(steps + warmup, B, D, torch.float32)
     ix = DenseIndex(X, metric="cos")
     for i in range(warmup):
-        ix.search(Q[i], k)
+        ix.search(Q[i], k, path=path)
     torch.cuda.synchronize()
     _native.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        ix.search(Q[warmup + i], k)
+        ix.search(Q[warmup + i], k, path=path)
     e1.record()
     torch.cuda.synchronize()
     kms, kn = _native.profile_read()
     _native.profile_enable(False)
     ms = e0.elapsed_time(e1) / steps
     kms /= steps
-    gbs = N * D * ((B + 3) // 4) / (kms * 1e-3) / 1e9
-    print(json.dumps({"config": name, "rows": N, "dim": D, "batch": B, "k": k, "dtype": "int8", "path": "scan", "ms_per_batch": ms,
+    tensor = path != "scan" and B <= 16            # tcgen05 kind::i8: one corpus pass for up to 16 queries
+    gbs = N * D * (1 if tensor else (B + 3) // 4) / (kms * 1e-3) / 1e9
+    print(json.dumps({"config": name, "rows": N, "dim": D, "batch": B, "k": k, "dtype": "int8", "path": "tensor_i8" if tensor else "scan", "ms_per_batch": ms,
+                      "kernel_launches_per_batch": kn / steps,
                       "queries_per_s": B / (ms * 1e-3), "kernel_ms_per_batch": kms, "hbm_GBps": gbs, "hbm_frac_of_measured": gbs / PEAKS["hbm_gbs"]}), flush=True)
 
 
@@ -169,8 +171,11 @@ CONFIGS = {
     "f32_5Mx768_B4_scan": lambda: run_search("f32_5Mx768_B4_scan", 5_000_000, 768, 4, 100, torch.float32, "scan", steps=20),
     "f32_5Mx768_B8_scan": lambda: run_search("f32_5Mx768_B8_scan", 5_000_000, 768, 8, 100, torch.float32, "scan", steps=20),
     "f32_5Mx768_B16_scan": lambda: run_search("f32_5Mx768_B16_scan", 5_000_000, 768, 16, 100, torch.float32, "scan", steps=10),
-    "i8_10Mx768_B1_scan": lambda: run_search_i8("i8_10Mx768_B1_scan", 10_000_000, 768, 1, 100, steps=20),
-    "i8_10Mx768_B4_scan": lambda: run_search_i8("i8_10Mx768_B4_scan", 10_000_000, 768, 4, 100, steps=20),
+    "i8_10Mx768_B1_scan": lambda: run_search_i8("i8_10Mx768_B1_scan", 10_000_000, 768, 1, 100, steps=20, path="scan"),
+    "i8_10Mx768_B4_scan": lambda: run_search_i8("i8_10Mx768_B4_scan", 10_000_000, 768, 4, 100, steps=20, path="scan"),
+    "i8_10Mx768_B1_tensor": lambda: run_search_i8("i8_10Mx768_B1_tensor", 10_000_000, 768, 1, 100, steps=20),
+    "i8_10Mx768_B4_tensor": lambda: run_search_i8("i8_10Mx768_B4_tensor", 10_000_000, 768, 4, 100, steps=20),
+    "i8_10Mx768_B16_tensor": lambda: run_search_i8("i8_10Mx768_B16_tensor", 10_000_000, 768, 16, 100, steps=20),
     "cfg2_10Mx768_B1_gemm": lambda: run_search("cfg2_10Mx768_B1_gemm", 10_000_000, 768, 1, 100, torch.bfloat16, "gemm", steps=20),
     "cfg3_12p5Mx384_f16_k1000_B16": lambda: run_search("cfg3_12p5Mx384_f16_k1000_B16", 12_500_000, 384, 16, 1000, torch.float16, "gemm", steps=10),
     "cfg3_12p5Mx384_f16_k1000_B1": lambda: run_search("cfg3_12p5Mx384_f16_k1000_B1", 12_500_000, 384, 1, 1000, torch.float16, "scan", steps=10),

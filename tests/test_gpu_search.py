@@ -174,8 +174,46 @@ def test_bulk_fed_scan_shapes(N, D, B, k, dtype):
     else:
         ref = rng.standard_normal((N, D)).astype(np.float32)
         ix = _index(torch.from_numpy(ref).to(_dev()), metric="cos")
-    scores, ids = ix.search(torch.from_numpy(Qn).to(_dev()), k)
+    scores, ids = ix.search(torch.from_numpy(Qn).to(_dev()), k, path="scan")
     _check_against_scores(scores, ids, O.score_matrix(Qn, ref, "cos"), k, 1e-5)
+
+
+@pytest.mark.parametrize("N,D,B,k,metric", [
+    (300000, 768, 1, 100, "cos"),
+    (300000, 768, 16, 100, "cos"),          # a full 16-query pass, several phases
+    (65537, 384, 7, 1000, "ip"),            # ragged last tile, k = 1000
+    (4000, 144, 5, 20, "cos"),              # D = 128 + 16: the second K slice is mostly out of bounds (zero-filled)
+    (63, 32, 2, 10, "cos"),                 # fewer rows than one tile, D < one K slice
+    (1, 16, 1, 1, "ip"),
+    (20000, 256, 20, 50, "cos"),            # B > 16: falls back to the DP4A scan
+])
+def test_int8_tensor_path(N, D, B, k, metric):
+    """int8 corpora with B <= 16 run on tcgen05 kind::i8 (rows_i8.cu): query limbs, exact int32 accumulation."""
+    rng = np.random.default_rng(3 * N + D + B)
+    Qn = rng.standard_normal((B, D)).astype(np.float32)
+    q8, scale = O.quantize_int8_rows(rng.standard_normal((N, D)).astype(np.float32))
+    ref = q8.astype(np.float32) * scale[:, None]
+    ix = _index(torch.from_numpy(q8).to(_dev()), metric=metric, row_scale=torch.from_numpy(scale).to(_dev()), id_base=7)
+    scores, ids = ix.search(torch.from_numpy(Qn).to(_dev()), k)
+    _check_against_scores(scores, ids, O.score_matrix(Qn, ref, metric), k, 1e-5, id_base=7)
+    if B <= 16:
+        s2, i2 = ix.search(torch.from_numpy(Qn).to(_dev()), k, path="gemm")
+        assert torch.equal(i2, ids) and torch.equal(s2, scores)
+
+
+def test_int8_integer_data_bit_exact_ids():
+    """Small-integer queries and rows: limb quantisation, int32 sums and the fp32 recombination are all exact, so ids
+    must match the oracle exactly, ties (lower id first) included."""
+    rng = np.random.default_rng(99)
+    N, D, B, k = 30000, 64, 9, 40
+    X8 = rng.integers(-3, 4, size=(N, D)).astype(np.int8)
+    Qn = rng.integers(-2, 3, size=(B, D)).astype(np.float32)
+    ix = _index(torch.from_numpy(X8).to(_dev()), metric="ip")
+    scores, ids = ix.search(torch.from_numpy(Qn).to(_dev()), k)
+    S = Qn.astype(np.float64) @ X8.astype(np.float64).T
+    want_s, want_i = O.topk_from_scores(S, k)
+    assert np.array_equal(ids.cpu().numpy(), want_i)
+    assert np.array_equal(scores.cpu().numpy().astype(np.float64), want_s)
 
 
 def test_multi_chunk_large():
