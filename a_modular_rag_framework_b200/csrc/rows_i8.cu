@@ -1,4 +1,4 @@
-// rows_i8.cu -- K1c: int8 corpora on the tensor cores (tcgen05 kind::i8), up to 16 queries per corpus pass.
+// rows_i8.cu -- K1c: int8 corpora on the tensor cores (tcgen05 kind::i8), 16 queries per corpus pass.
 //
 // Same contract as K1/K2 (exact cosine / IP top-k; reference retrieval_backend.py:192-197, 371-372).  The CUDA-core
 // scans cannot keep up with HBM for int8 rows once there is more than one query (DP4A issues at ~16 lanes/clk/SM, the
@@ -34,6 +34,7 @@ constexpr int RI_Q_KB_BYTES = RI_NCOLS * RI_BK;   // 6 KB per K slice of the res
 
 struct RowsI8Params {
   int B, k, D, num_kb, stages;
+  int q0;                  // this launch serves queries [q0, min(B, q0 + RI_NQ)): list / threshold / count slots q0 + j
   long long N;
   int tile_begin, tile_end, tiles_per_chunk, num_units;
   int cap, cap_soft, Bpad;
@@ -46,12 +47,16 @@ struct RowsI8Params {
 };
 
 // ---- query quantisation: f32 [B, D] -> limb planes int8 [3][RI_NQ][D] + scale[RI_NQ] -------------------------
-__global__ void quantize_queries_i8_kernel(const float* __restrict__ Q, int B, int D, int8_t* __restrict__ limbs, float* __restrict__ scale) {
-  const int j = blockIdx.x;        // query slot 0..RI_NQ-1
+__global__ void quantize_queries_i8_kernel(const float* __restrict__ Q, int B, int D, int8_t* __restrict__ qws, size_t group_bytes,
+                                           size_t scale_off) {
+  const int g = blockIdx.x / RI_NQ, j = blockIdx.x % RI_NQ;     // group of 16 queries, slot inside it
+  const int query = g * RI_NQ + j;
+  int8_t* limbs = qws + (size_t)g * group_bytes;
+  float* scale = reinterpret_cast<float*>(qws + (size_t)g * group_bytes + scale_off);
   __shared__ float s_max[32];
   float m = 0.0f;
-  if (j < B)
-    for (int d = threadIdx.x; d < D; d += blockDim.x) m = fmaxf(m, fabsf(Q[(size_t)j * D + d]));
+  if (query < B)
+    for (int d = threadIdx.x; d < D; d += blockDim.x) m = fmaxf(m, fabsf(Q[(size_t)query * D + d]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
   if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
@@ -60,11 +65,11 @@ __global__ void quantize_queries_i8_kernel(const float* __restrict__ Q, int B, i
   for (int w = 0; w < (int)(blockDim.x >> 5); ++w) qmax = fmaxf(qmax, s_max[w]);
   const float inv = qmax > 0.0f ? 4194304.0f / qmax : 0.0f;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    const int qi = (j < B) ? __float2int_rn(Q[(size_t)j * D + d] * inv) : 0;      // |qi| <= 2^22
+    const int qi = (query < B) ? __float2int_rn(Q[(size_t)query * D + d] * inv) : 0;      // |qi| <= 2^22
     const int l0 = ((qi + 128) & 255) - 128;
     const int q1 = (qi - l0) >> 8;
     const int l1 = ((q1 + 128) & 255) - 128;
-    const int l2 = (q1 - l1) >> 8;                                               // |l2| <= 64
+    const int l2 = (q1 - l1) >> 8;                                                       // |l2| <= 64
     limbs[((size_t)0 * RI_NQ + j) * D + d] = (int8_t)l0;
     limbs[((size_t)1 * RI_NQ + j) * D + d] = (int8_t)l1;
     limbs[((size_t)2 * RI_NQ + j) * D + d] = (int8_t)l2;
@@ -181,10 +186,10 @@ rows_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       if (t0 >= t1) continue;
       const size_t seg = (size_t)u * 4 + ew;               // this warp's list segment for the unit's row chunk
       for (int j = lane; j < RI_NQ; j += 32) {
-        const bool valid = j < p.B;
-        thr[j] = valid ? ordered_to_f32(__ldcg(p.gthr + j)) : __int_as_float(0x7f800000);
+        const bool valid = p.q0 + j < p.B;
+        thr[j] = valid ? ordered_to_f32(__ldcg(p.gthr + p.q0 + j)) : __int_as_float(0x7f800000);
         kth[j] = 0;
-        cnt[j] = valid ? __ldcg(p.counts + seg * p.Bpad + j) : 0;
+        cnt[j] = valid ? __ldcg(p.counts + seg * p.Bpad + p.q0 + j) : 0;
       }
       __syncwarp();
       for (int t = t0; t < t1; ++t, ++tile_iter) {
@@ -223,7 +228,7 @@ rows_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
               const u32 b2 = __ballot_sync(kFullMask, (s[j] >= tj) && key > kth[j]);
               if (b2) {
                 const int base = cnt[j];
-                u64* lp = p.lists + (seg * p.Bpad + j) * (size_t)p.cap;
+                u64* lp = p.lists + (seg * p.Bpad + p.q0 + j) * (size_t)p.cap;
                 if ((b2 >> lane) & 1u) __stcg(lp + base + __popc(b2 & ((1u << lane) - 1u)), key);
                 const int n = base + __popc(b2);
                 __syncwarp();
@@ -231,7 +236,7 @@ rows_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                   const u64 kk = warp_compact(lp, n, p.k, hist);
                   if (lane == 0) {
                     kth[j] = kk; thr[j] = fmaxf(tj, key_score(kk)); cnt[j] = p.k;
-                    atomicMax(p.gthr + j, (u32)(kk >> 32));
+                    atomicMax(p.gthr + p.q0 + j, (u32)(kk >> 32));
                   }
                 } else if (lane == 0) {
                   cnt[j] = n;
@@ -243,11 +248,11 @@ rows_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
         // thresholds published by other CTAs / warps
         for (int j = lane; j < RI_NQ; j += 32)
-          if (j < p.B) thr[j] = fmaxf(thr[j], ordered_to_f32(__ldcg(p.gthr + j)));
+          if (p.q0 + j < p.B) thr[j] = fmaxf(thr[j], ordered_to_f32(__ldcg(p.gthr + p.q0 + j)));
         __syncwarp();
       }
       for (int j = lane; j < RI_NQ; j += 32)
-        if (j < p.B) p.counts[seg * p.Bpad + j] = cnt[j];
+        if (p.q0 + j < p.B) p.counts[seg * p.Bpad + p.q0 + j] = cnt[j];
       __syncwarp();
     }
   }
@@ -271,43 +276,48 @@ int rows_i8_nq() { return RI_NQ; }
 int rows_i8_tile_rows() { return RI_ROWS; }
 
 // ring stages that fit next to the resident limb block; 0 = the kernel does not apply (B200R_ROWS_I8=0 switches it off)
-int rows_i8_stages(int B, int D) {
+int rows_i8_stages(int D) {
   static const bool off = [] { const char* e = getenv("B200R_ROWS_I8"); return e && e[0] == '0'; }();
-  if (off || B > RI_NQ) return 0;
+  if (off) return 0;
   const int num_kb = (D + RI_BK - 1) / RI_BK;
   int stages = 12;
   while (stages >= 4 && rows_i8_smem_bytes(num_kb, stages) > 227 * 1024) --stages;
   return stages >= 4 ? stages : 0;
 }
 
-// workspace for the quantised queries: limb planes [3][RI_NQ][D] int8, then RI_NQ scales
-size_t rows_i8_query_bytes(int D) { return align_up((size_t)RI_NCOLS * D, 256) + 256; }
+// workspace for the quantised queries, per group of 16: limb planes [3][RI_NQ][D] int8, then RI_NQ scales
+static size_t rows_i8_group_bytes(int D) { return align_up((size_t)RI_NCOLS * D, 256) + 256; }
+size_t rows_i8_query_bytes(int B, int D) { return (size_t)((B + RI_NQ - 1) / RI_NQ) * rows_i8_group_bytes(D); }
 
 int launch_quantize_queries_i8(const void* Q, int B, int D, void* qws, cudaStream_t st) {
-  int8_t* limbs = reinterpret_cast<int8_t*>(qws);
-  float* scale = reinterpret_cast<float*>(reinterpret_cast<char*>(qws) + align_up((size_t)RI_NCOLS * D, 256));
-  quantize_queries_i8_kernel<<<RI_NQ, 256, 0, st>>>(reinterpret_cast<const float*>(Q), B, D, limbs, scale);
+  const int groups = (B + RI_NQ - 1) / RI_NQ;
+  quantize_queries_i8_kernel<<<groups * RI_NQ, 256, 0, st>>>(reinterpret_cast<const float*>(Q), B, D, reinterpret_cast<int8_t*>(qws),
+                                                            rows_i8_group_bytes(D), align_up((size_t)RI_NCOLS * D, 256));
   count_launch();
   B200R_CUDA_CHECK(cudaGetLastError());
   return B200R_OK;
 }
 
-int encode_query_tmap_i8(const void* qws, int D, CUtensorMap* tmap_q) {
-  return encode_tmap_2d(tmap_q, B200R_I8, qws, (uint64_t)D, (uint64_t)RI_NCOLS, RI_BK, RI_NCOLS);
+int encode_query_tmap_i8(const void* qws, int group, int D, CUtensorMap* tmap_q) {
+  const char* base = reinterpret_cast<const char*>(qws) + (size_t)group * rows_i8_group_bytes(D);
+  return encode_tmap_2d(tmap_q, B200R_I8, base, (uint64_t)D, (uint64_t)RI_NCOLS, RI_BK, RI_NCOLS);
 }
 
-int launch_rows_i8(const Index* ix, const CUtensorMap* tmap_q, const void* qws, const SearchPlan& pl, const GemmPhase& ph, void* ws,
-                   cudaStream_t st) {
+// one launch = one phase of one group of <= 16 queries
+int launch_rows_i8(const Index* ix, const CUtensorMap* tmap_q, const void* qws, int group, const SearchPlan& pl, const GemmPhase& ph,
+                   void* ws, cudaStream_t st) {
   RowsI8Params p;
   p.B = pl.B; p.k = pl.k; p.D = ix->D; p.N = ix->N;
+  p.q0 = group * RI_NQ;
   p.num_kb = (ix->D + RI_BK - 1) / RI_BK;
-  p.stages = rows_i8_stages(pl.B, ix->D);
-  if (!p.stages) { set_error("int8 tensor path: B=%d / D=%d not supported", pl.B, ix->D); return B200R_EINVAL; }
+  p.stages = rows_i8_stages(ix->D);
+  if (!p.stages) { set_error("int8 tensor path: D=%d not supported", ix->D); return B200R_EINVAL; }
   p.tile_begin = ph.tile_begin; p.tile_end = ph.tile_end; p.tiles_per_chunk = ph.tiles_per_chunk;
   p.num_units = ph.num_chunks;
   p.cap = pl.cap; p.cap_soft = pl.cap_soft; p.Bpad = pl.Bpad;
   p.row_mult = ix->row_mult;
-  p.qscale = reinterpret_cast<const float*>(reinterpret_cast<const char*>(qws) + align_up((size_t)RI_NCOLS * ix->D, 256));
+  p.qscale = reinterpret_cast<const float*>(reinterpret_cast<const char*>(qws) + (size_t)group * rows_i8_group_bytes(ix->D) +
+                                            align_up((size_t)RI_NCOLS * ix->D, 256));
   p.lists = reinterpret_cast<u64*>((char*)ws + pl.off_lists);
   p.counts = reinterpret_cast<int*>((char*)ws + pl.off_counts);
   p.gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);

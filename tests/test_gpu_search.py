@@ -185,10 +185,11 @@ def test_bulk_fed_scan_shapes(N, D, B, k, dtype):
     (4000, 144, 5, 20, "cos"),              # D = 128 + 16: the second K slice is mostly out of bounds (zero-filled)
     (63, 32, 2, 10, "cos"),                 # fewer rows than one tile, D < one K slice
     (1, 16, 1, 1, "ip"),
-    (20000, 256, 20, 50, "cos"),            # B > 16: falls back to the DP4A scan
+    (20000, 256, 20, 50, "cos"),            # two groups of 16 queries, the second one partial
+    (9000, 128, 49, 10, "ip"),              # four groups
 ])
 def test_int8_tensor_path(N, D, B, k, metric):
-    """int8 corpora with B <= 16 run on tcgen05 kind::i8 (rows_i8.cu): query limbs, exact int32 accumulation."""
+    """int8 corpora run on tcgen05 kind::i8 (rows_i8.cu), 16 queries per corpus pass: query limbs, exact int32 sums."""
     rng = np.random.default_rng(3 * N + D + B)
     Qn = rng.standard_normal((B, D)).astype(np.float32)
     q8, scale = O.quantize_int8_rows(rng.standard_normal((N, D)).astype(np.float32))
@@ -196,9 +197,8 @@ def test_int8_tensor_path(N, D, B, k, metric):
     ix = _index(torch.from_numpy(q8).to(_dev()), metric=metric, row_scale=torch.from_numpy(scale).to(_dev()), id_base=7)
     scores, ids = ix.search(torch.from_numpy(Qn).to(_dev()), k)
     _check_against_scores(scores, ids, O.score_matrix(Qn, ref, metric), k, 1e-5, id_base=7)
-    if B <= 16:
-        s2, i2 = ix.search(torch.from_numpy(Qn).to(_dev()), k, path="gemm")
-        assert torch.equal(i2, ids) and torch.equal(s2, scores)
+    s2, i2 = ix.search(torch.from_numpy(Qn).to(_dev()), k, path="gemm")
+    assert torch.equal(i2, ids) and torch.equal(s2, scores)
 
 
 def test_int8_integer_data_bit_exact_ids():
