@@ -83,6 +83,8 @@ class DenseIndex:
         return self._handle.value
 
     # -- search -----------------------------------------------------------------------------------
+    INT8_SLICE = 256
+
     def _workspace(self, B: int, k: int, path: int) -> torch.Tensor:
         need = int(self._lib.b200r_search_workspace_bytes(self._handle, B, k, path))
         if need == 0:
@@ -103,12 +105,19 @@ class DenseIndex:
             raise ValueError(f"Q must be {self.query_dtype} for a {self.X.dtype} corpus")
         B = int(Q.shape[0])
         p = _PATHS[path]
-        ws = self._workspace(B, k, p)
         if out is None:
             scores = torch.empty((B, k), dtype=torch.float32, device=self.device)
             ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
         else:
             scores, ids = out
+        if self.X.dtype == torch.int8 and B > self.INT8_SLICE:
+            # the int8 paths keep one candidate list per (epilogue warp, query): slice big batches so the workspace stays
+            # at a few hundred MB (the corpus is streamed once per 16 queries either way)
+            for b0 in range(0, B, self.INT8_SLICE):
+                b1 = min(B, b0 + self.INT8_SLICE)
+                self.search(Q[b0:b1], k, path=path, out=(scores[b0:b1], ids[b0:b1]), min_score=min_score)
+            return scores, ids
+        ws = self._workspace(B, k, p)
         with torch.cuda.device(self.device):
             if min_score is None:
                 N.check(self._lib.b200r_search(self._handle, Q.data_ptr(), B, k, p, scores.data_ptr(), ids.data_ptr(),

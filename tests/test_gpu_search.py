@@ -187,6 +187,7 @@ def test_bulk_fed_scan_shapes(N, D, B, k, dtype):
     (1, 16, 1, 1, "ip"),
     (20000, 256, 20, 50, "cos"),            # two groups of 16 queries, the second one partial
     (9000, 128, 49, 10, "ip"),              # four groups
+    (3000, 64, 300, 5, "cos"),              # more than one 256-query slice
 ])
 def test_int8_tensor_path(N, D, B, k, metric):
     """int8 corpora run on tcgen05 kind::i8 (rows_i8.cu), 16 queries per corpus pass: query limbs, exact int32 sums."""
