@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--path", default="auto", choices=["auto", "gemm", "scan"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"], help="corpus / query element type (the contract line is bf16)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -54,7 +55,7 @@ def parse_args():
 
 
 def workload_name(a):
-    return f"synthetic unit-norm {a.rows}x{a.dim} bf16 corpus, batch {a.batch}, exact cosine top-{a.k}"
+    return f"synthetic unit-norm {a.rows}x{a.dim} {a.dtype} corpus, batch {a.batch}, exact cosine top-{a.k}"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -239,14 +240,15 @@ def main():
     # ---- synthetic corpus shard, generated on the device in row blocks (seeded per block) -----------
     lo, hi = shard_rows(a.rows, world, rank)
     n_local = hi - lo
-    X = torch.empty((max(n_local, 1), a.dim), dtype=torch.bfloat16, device=dev)
+    tdt = torch.bfloat16 if a.dtype == "bf16" else torch.float16
+    X = torch.empty((max(n_local, 1), a.dim), dtype=tdt, device=dev)
     blk = 1 << 20
     for r0 in range(lo, hi, blk):
         r1 = min(hi, r0 + blk)
         g = torch.Generator(device=dev).manual_seed(1_000_003 + r0)
         t = torch.randn((r1 - r0, a.dim), generator=g, device=dev, dtype=torch.float32)
         t /= t.norm(dim=1, keepdim=True)
-        X[r0 - lo: r1 - lo] = t.to(torch.bfloat16)
+        X[r0 - lo: r1 - lo] = t.to(tdt)
         del t
     if n_local == 0:
         X.zero_()
@@ -254,7 +256,7 @@ def main():
     gq = torch.Generator(device="cpu").manual_seed(4242)
     Qh = torch.randn((n_batches, a.batch, a.dim), generator=gq, dtype=torch.float32)
     Qh /= Qh.norm(dim=2, keepdim=True)
-    Qh = Qh.to(torch.bfloat16).pin_memory()        # same queries on every rank (replicated)
+    Qh = Qh.to(tdt).pin_memory()        # same queries on every rank (replicated)
     Qd = Qh.to(dev)
     torch.cuda.synchronize()
 
@@ -428,7 +430,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": a.dtype, "data": "synthetic",
             "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "batch": a.batch, "k": a.k,
                        "path": used_path, "sharding": f"rows/{world}",
                        "exchange": "none" if world == 1 else (
