@@ -100,8 +100,9 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   // measured on B200 (10M x 768 bf16): with the query tile replicated in global memory the tcgen05 tile kernel streams
   // the corpus at 6.9-7.0 TB/s (105% of the measured copy bandwidth) for every B from 1 to 128 and is tensor-bound
   // beyond; the CUDA-core scan (6.7 TB/s at B=1, 5.6 at B=2) serves fp32 / int8 / odd-D corpora
-  // int8 corpora: tcgen05 kind::i8 with the queries split into signed-byte limbs, 16 queries per corpus pass (rows_i8.cu)
-  const bool i8_ok = ix->has_tmap_i8 && rows_i8_stages(ix->D) > 0;
+  // int8 corpora: tcgen05 kind::i8 with the queries split into signed-byte limbs, 16-64 queries per corpus pass (rows_i8.cu)
+  const int i8_nq = ix->has_tmap_i8 ? rows_i8_nq(B, ix->D) : 0;
+  const bool i8_ok = i8_nq > 0;
   if (path == B200R_PATH_AUTO) path = (gemm_ok || i8_ok) ? B200R_PATH_GEMM : B200R_PATH_SCAN;
   if (path == B200R_PATH_GEMM && !gemm_ok && !i8_ok) {
     set_error("tensor path needs a bf16/f16 corpus with D %% 8 == 0 or an int8 corpus (dtype=%d D=%d)", ix->dtype, ix->D);
@@ -114,12 +115,13 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   if (path == B200R_PATH_GEMM) {
     // more than one 128-query tile: pair the CTAs (cta_group::2) so each loads half of every corpus tile
     // int8: rows-mode kernel (corpus rows on the MMA's M, 128-row tiles, one list per epilogue warp)
-    pl->rows_i8 = (ix->dtype == B200R_I8) ? (B + rows_i8_nq() - 1) / rows_i8_nq() : 0;
+    pl->rows_i8_nq = (ix->dtype == B200R_I8) ? i8_nq : 0;
+    pl->rows_i8 = pl->rows_i8_nq ? (B + i8_nq - 1) / i8_nq : 0;
     pl->cta_group = (!pl->rows_i8 && B > gemm_tile_queries() && g_cta_group_max >= 2) ? 2 : 1;
-    const int BMq = pl->rows_i8 ? rows_i8_nq() : gemm_tile_queries() * pl->cta_group;
+    const int BMq = pl->rows_i8 ? pl->rows_i8_nq : gemm_tile_queries() * pl->cta_group;
     const int BNr = pl->rows_i8 ? rows_i8_tile_rows() : gemm_tile_rows();
     const int list_rows_per_tile = pl->rows_i8 ? 32 : BNr;      // rows one list can receive from one tile
-    pl->num_q_tiles = pl->rows_i8 ? 1 : (B + BMq - 1) / BMq;      // int8: every group of 16 queries is its own launch
+    pl->num_q_tiles = pl->rows_i8 ? 1 : (B + BMq - 1) / BMq;      // int8: every group of queries is its own launch
     pl->num_row_tiles = (int)((ix->N + BNr - 1) / BNr);
     pl->Bpad = (pl->rows_i8 ? pl->rows_i8 : pl->num_q_tiles) * BMq;
     // units = (query tile, chunk of row tiles).  More units per CTA = better balance, fewer = less list
@@ -211,7 +213,7 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   }
   pl->q_replicas = (path == B200R_PATH_GEMM && !pl->rows_i8 && pl->cta_group == 1 && pl->num_q_tiles == 1 && g_q_replicas) ? 1 : 0;
   if (pl->q_replicas) { pl->off_qrep = off; off += align_up(query_replica_bytes(ix->D), 256); }
-  if (pl->rows_i8) { pl->off_qrep = off; off += align_up(rows_i8_query_bytes(B, ix->D), 256); }   // quantised query limbs + scales
+  if (pl->rows_i8) { pl->off_qrep = off; off += align_up(rows_i8_query_bytes(B, pl->rows_i8_nq, ix->D), 256); }   // quantised query limbs + scales
   pl->off_end = off;
   return B200R_OK;
 }
@@ -242,10 +244,10 @@ static int do_search(Index* ix, const void* Q, int B, int k, int path, float* ou
   if (floor_on && (rc = launch_min_score(pl, ws, ix->metric == B200R_COS, min_score, st))) return rc;
   if (pl.path == B200R_PATH_GEMM && pl.rows_i8) {
     void* qws = (char*)ws + pl.off_qrep;
-    if ((rc = launch_quantize_queries_i8(Q, B, ix->D, qws, st))) return rc;
+    if ((rc = launch_quantize_queries_i8(Q, B, pl.rows_i8_nq, ix->D, qws, st))) return rc;
     std::vector<CUtensorMap> tmaps(pl.rows_i8);
     for (int g = 0; g < pl.rows_i8; ++g)
-      if ((rc = encode_query_tmap_i8(qws, g, ix->D, &tmaps[g]))) return rc;
+      if ((rc = encode_query_tmap_i8(qws, g, pl.rows_i8_nq, ix->D, &tmaps[g]))) return rc;
     for (int i = 0; i < pl.num_phases; ++i) {
       profile_begin(st);
       for (int g = 0; g < pl.rows_i8 && !rc; ++g) rc = launch_rows_i8(ix, &tmaps[g], qws, g, pl, pl.phases[i], ws, st);

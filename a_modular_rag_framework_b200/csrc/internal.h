@@ -72,7 +72,8 @@ struct SearchPlan {
   // gemm: row tiles are processed in phases [tile_begin, tile_end) of geometrically growing size; after each
   // phase the exact k-th best so far becomes every query's filter threshold for the next one
   int cta_group;         // 1 or 2 (CTA pair, cta_group::2)
-  int rows_i8;           // > 0: int8 tensor path (rows_i8.cu) with this many groups of 16 queries; 128-row tiles, 4 lists per unit
+  int rows_i8;           // > 0: int8 tensor path (rows_i8.cu) with this many groups of rows_i8_nq queries; 128-row tiles, 4 lists per unit
+  int rows_i8_nq;        // 16 / 32 / 64
   int q_replicas;        // 1: single query tile replicated in the workspace (off_qrep) against L2 hot-spotting
   int num_q_tiles, num_row_tiles, num_chunks;   // num_q_tiles counts tiles of cta_group*128 queries
   int num_phases;
@@ -98,12 +99,11 @@ size_t query_replica_bytes(int D);
 int launch_replicate_queries(const void* Q, void* rep, int B, int D, cudaStream_t st);
 int encode_query_tmap_replicated(const Index* ix, const void* rep, CUtensorMap* tmap_q);
 int launch_scan_topk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
-int rows_i8_nq();
+int rows_i8_nq(int B, int D);                 // queries per corpus pass (16 / 32 / 64), 0 = int8 tensor path not available
 int rows_i8_tile_rows();
-int rows_i8_stages(int D);
-size_t rows_i8_query_bytes(int B, int D);
-int launch_quantize_queries_i8(const void* Q, int B, int D, void* qws, cudaStream_t st);
-int encode_query_tmap_i8(const void* qws, int group, int D, CUtensorMap* tmap_q);
+size_t rows_i8_query_bytes(int B, int nq, int D);
+int launch_quantize_queries_i8(const void* Q, int B, int nq, int D, void* qws, cudaStream_t st);
+int encode_query_tmap_i8(const void* qws, int group, int nq, int D, CUtensorMap* tmap_q);
 int launch_rows_i8(const Index* ix, const CUtensorMap* tmap_q, const void* qws, int group, const SearchPlan& p, const GemmPhase& ph, void* ws,
                    cudaStream_t st);
 int scan_bulk_warps(const Index* ix);        // consumer warps per CTA of the bulk-fed scan, 0 if it does not apply

@@ -104,8 +104,8 @@ def run_search_i8(name, N, D, B, k, steps=10, warmup=3, path="auto"):
     _native.profile_enable(False)
     ms = e0.elapsed_time(e1) / steps
     kms /= steps
-    tensor = path != "scan"                        # tcgen05 kind::i8: one corpus pass per 16 queries
-    gbs = N * D * ((B + 15) // 16 if tensor else (B + 3) // 4) / (kms * 1e-3) / 1e9
+    tensor = path != "scan"                        # tcgen05 kind::i8: one corpus pass per group of up to 64 queries
+    gbs = N * D * ((B + 63) // 64 if tensor else (B + 3) // 4) / (kms * 1e-3) / 1e9
     print(json.dumps({"config": name, "rows": N, "dim": D, "batch": B, "k": k, "dtype": "int8", "path": "tensor_i8" if tensor else "scan", "ms_per_batch": ms,
                       "kernel_launches_per_batch": kn / steps,
                       "queries_per_s": B / (ms * 1e-3), "kernel_ms_per_batch": kms, "hbm_GBps": gbs, "hbm_frac_of_measured": gbs / PEAKS["hbm_gbs"]}), flush=True)
@@ -175,6 +175,8 @@ CONFIGS = {
     "i8_10Mx768_B4_scan": lambda: run_search_i8("i8_10Mx768_B4_scan", 10_000_000, 768, 4, 100, steps=20, path="scan"),
     "i8_10Mx768_B1_tensor": lambda: run_search_i8("i8_10Mx768_B1_tensor", 10_000_000, 768, 1, 100, steps=20),
     "i8_10Mx768_B4_tensor": lambda: run_search_i8("i8_10Mx768_B4_tensor", 10_000_000, 768, 4, 100, steps=20),
+    "i8_10Mx768_B32_tensor": lambda: run_search_i8("i8_10Mx768_B32_tensor", 10_000_000, 768, 32, 100, steps=10),
+    "i8_10Mx768_B256_tensor": lambda: run_search_i8("i8_10Mx768_B256_tensor", 10_000_000, 768, 256, 100, steps=5),
     "i8_10Mx768_B64_tensor": lambda: run_search_i8("i8_10Mx768_B64_tensor", 10_000_000, 768, 64, 100, steps=10),
     "i8_10Mx768_B16_tensor": lambda: run_search_i8("i8_10Mx768_B16_tensor", 10_000_000, 768, 16, 100, steps=20),
     "cfg2_10Mx768_B1_gemm": lambda: run_search("cfg2_10Mx768_B1_gemm", 10_000_000, 768, 1, 100, torch.bfloat16, "gemm", steps=20),

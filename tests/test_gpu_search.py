@@ -185,12 +185,14 @@ def test_bulk_fed_scan_shapes(N, D, B, k, dtype):
     (4000, 144, 5, 20, "cos"),              # D = 128 + 16: the second K slice is mostly out of bounds (zero-filled)
     (63, 32, 2, 10, "cos"),                 # fewer rows than one tile, D < one K slice
     (1, 16, 1, 1, "ip"),
-    (20000, 256, 20, 50, "cos"),            # two groups of 16 queries, the second one partial
-    (9000, 128, 49, 10, "ip"),              # four groups
+    (20000, 256, 20, 50, "cos"),            # one group of 32 queries (96 TMEM columns), partly empty
+    (9000, 128, 49, 10, "ip"),              # one group of 64 queries (192 columns, two accumulators)
+    (70000, 768, 64, 100, "cos"),           # a full 64-query group at the benchmark width
+    (5000, 1024, 40, 10, "cos"),            # 64 resident queries would not fit next to the ring: two groups of 32
     (3000, 64, 300, 5, "cos"),              # more than one 256-query slice
 ])
 def test_int8_tensor_path(N, D, B, k, metric):
-    """int8 corpora run on tcgen05 kind::i8 (rows_i8.cu), 16 queries per corpus pass: query limbs, exact int32 sums."""
+    """int8 corpora run on tcgen05 kind::i8 (rows_i8.cu), 16 / 32 / 64 queries per corpus pass: query limbs, exact int32 sums."""
     rng = np.random.default_rng(3 * N + D + B)
     Qn = rng.standard_normal((B, D)).astype(np.float32)
     q8, scale = O.quantize_int8_rows(rng.standard_normal((N, D)).astype(np.float32))
