@@ -7,7 +7,7 @@
 //   * the 128 corpus rows of a tile are the MMA's M (TMEM lanes); tiles of [128 rows x 128 bytes] arrive by TMA
 //     (SWIZZLE_128B) in a ring of up to 12 stages that carries corpus data only;
 //   * the queries are quantised ONCE per search to 23-bit fixed point relative to their largest component
-//     (|q - q~| <= 2^-23 max|q|) and split into three balanced signed-byte limbs; the 3 x NQ limb rows of a group of
+//     (|q - q~| <= 2^-22 max|q|) and split into three balanced signed-byte limbs; the 3 x NQ limb rows of a group of
 //     NQ queries are the MMA's N (48 / 96 / 192 TMEM columns) and stay RESIDENT in shared memory;
 //   * accumulation is exact int32; the epilogue thread (= TMEM lane = one corpus row) recombines the limbs of each
 //     query in fp32 (a2*65536 + a1*256 + a0), applies the query scale and the row multiplier and tests the scores, 16

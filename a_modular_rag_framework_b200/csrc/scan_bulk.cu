@@ -67,7 +67,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) scan_bulk_kernel(const ScanBu
   __shared__ float s_scale[BQ];   // int8 path: q_b ~= scale_b * (l2*65536 + l1*256 + l0)
   if constexpr (kInt8) {
     // int8 corpus: the dot products run on DP4A.  Each query is quantised ONCE to 23-bit fixed point relative to its
-    // largest component (|q - q~| <= 2^-23 max|q|, the size of an fp32 rounding of that component) and split into three
+    // largest component (|q - q~| <= 2^-22 max|q|, about an fp32 rounding of that component) and split into three
     // balanced signed-byte limbs, staged as 16-byte planes qL[limb][b][chunk]; the integer sums are exact.
     if (threadIdx.x < BQ) s_qmax[threadIdx.x] = 0u;
     __syncthreads();

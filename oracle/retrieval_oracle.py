@@ -13,6 +13,8 @@ container by ``tests/golden/make_golden.py`` and committed as ``tests/golden/*.j
 Reference lines each function follows (paths relative to the reference repo root):
 
 * ``cosine_pair``            app/modules/retrieval/retrieval_backend.py:192-197  (DenseReranker._cosine)
+* ``query_limbs_int8`` / ``int8_limb_scores``  no reference counterpart: restatement of OUR int8 arithmetic, so that its
+                             error against ``score_matrix`` can be bounded on the CPU (tests/test_int8_limbs.py)
 * ``score_matrix`` / ``topk``  same metric, vectorised; top-k = stable ``sort(reverse=True)[:k]`` of
                              retrieval_backend.py:371-372, text_index.py:96, retrieval_adapter.py:129-131
                              (stable descending sort over rows enumerated in id order == ties to lower id)
@@ -54,6 +56,41 @@ def quantize_int8_rows(x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
 
 
 # ----------------------------------------------------------------------------- a1: the metric
+
+
+def query_limbs_int8(q: np.ndarray) -> Tuple[np.ndarray, float]:
+    """The int8 paths' image of one fp32 query (csrc/rows_i8.cu quantize_queries_i8_kernel, csrc/scan_bulk.cu):
+    23-bit fixed point relative to the largest component, split into three balanced signed-byte limbs.
+    -> (limbs int8 [3, D] with q_int = l2*65536 + l1*256 + l0, scale) such that q ~= scale * q_int and
+    |q - scale*q_int| <= 2^-22 * max|q| (half a grid step from the rounding plus the fp32 rounding of the scaling).  No counterpart in the reference (it has no quantised path); the parity bar
+    for int8 corpora is still the fp64 cosine of retrieval_backend.py:192-197 on the dequantised rows."""
+    q = np.asarray(q, dtype=np.float32)
+    qmax = np.float32(np.max(np.abs(q))) if q.size else np.float32(0)
+    if not qmax > 0:
+        return np.zeros((3, q.shape[0]), dtype=np.int8), 0.0
+    inv = np.float32(4194304.0) / qmax
+    qi = np.rint(q * inv).astype(np.int64)              # round-half-even like __float2int_rn, |qi| <= 2^22
+    l0 = ((qi + 128) & 255) - 128
+    q1 = (qi - l0) >> 8
+    l1 = ((q1 + 128) & 255) - 128
+    l2 = (q1 - l1) >> 8
+    limbs = np.stack([l0, l1, l2])
+    assert limbs.min() >= -128 and limbs.max() <= 127
+    return limbs.astype(np.int8), float(qmax * np.float32(1.0 / 4194304.0))
+
+
+def int8_limb_scores(q: np.ndarray, X8: np.ndarray, row_mult: Optional[np.ndarray] = None) -> np.ndarray:
+    """Scores exactly as the int8 tensor path forms them: exact integer limb sums, fp32 recombination
+    a2*65536 + a1*256 + a0, times the query scale, times the row multiplier."""
+    limbs, scale = query_limbs_int8(q)
+    A = X8.astype(np.int64) @ limbs.astype(np.int64).T          # [N, 3] exact
+    assert np.abs(A).max(initial=0) < 2 ** 31
+    f = np.float32(65536.0) * A[:, 2].astype(np.float32)
+    f = (f + (np.float32(256.0) * A[:, 1].astype(np.float32) + A[:, 0].astype(np.float32)).astype(np.float32)).astype(np.float32)
+    s = (f * np.float32(scale)).astype(np.float32)
+    if row_mult is not None:
+        s = (s * row_mult.astype(np.float32)).astype(np.float32)
+    return s
 
 
 def cosine_pair(a: Sequence[float], b: Sequence[float]) -> float:
