@@ -204,6 +204,23 @@ def test_int8_tensor_path(N, D, B, k, metric):
     assert torch.equal(i2, ids) and torch.equal(s2, scores)
 
 
+def test_int8_tensor_scores_bit_equal_the_limb_restatement():
+    """Inner-product scores of the int8 tensor path must equal, bit for bit, the CPU restatement of its arithmetic
+    (oracle.int8_limb_scores: exact integer limb sums, fp32 recombination, query scale, row scale)."""
+    rng = np.random.default_rng(123)
+    N, D, B, k = 6000, 256, 3, 30
+    q8, scale = O.quantize_int8_rows(rng.standard_normal((N, D)).astype(np.float32))
+    Qn = rng.standard_normal((B, D)).astype(np.float32)
+    ix = _index(torch.from_numpy(q8).to(_dev()), metric="ip", row_scale=torch.from_numpy(scale).to(_dev()))
+    scores, ids = ix.search(torch.from_numpy(Qn).to(_dev()), k)
+    scores, ids = scores.cpu().numpy(), ids.cpu().numpy()
+    for b in range(B):
+        want = O.int8_limb_scores(Qn[b], q8, row_mult=scale)
+        assert np.array_equal(scores[b], want[ids[b]])
+        order = np.lexsort((np.arange(N), -want.astype(np.float64)))[:k]     # and the ranking of those exact scores
+        assert np.array_equal(ids[b], order)
+
+
 def test_int8_integer_data_bit_exact_ids():
     """Small-integer queries and rows: limb quantisation, int32 sums and the fp32 recombination are all exact, so ids
     must match the oracle exactly, ties (lower id first) included."""
