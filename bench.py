@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verify-queries", type=int, default=8,
+                    help="queries of the last timed batch checked against the CPU oracle after the timed regions (0 = skip)")
     ap.add_argument("--exchange", default=os.environ.get("B200R_EXCHANGE", "p2p"), choices=["p2p", "nccl"],
                     help="N>1: fused select->peer-memory scatter (default) or packed NCCL all-gather")
     return ap.parse_args()
@@ -154,6 +156,38 @@ def run_reference_arm(a):
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# recall leg: the oracle as the CHECKER of the results the timed regions produced (outside any timed region)
+# ------------------------------------------------------------------------------------------------
+def oracle_lists_for_shard(X, lo, Qsel_f32, k, dtype_name, block_rows=1 << 18, extra=64):
+    """Exact fp64 top-(k+extra) of the selected queries over THIS rank's corpus shard, streamed back from HBM in row
+    blocks (global ids = lo + local row)."""
+    import numpy as np
+    from oracle import retrieval_oracle as O
+
+    def blocks():
+        n = int(X.shape[0])
+        for r0 in range(0, n, block_rows):
+            xb = X[r0:min(n, r0 + block_rows)]
+            if dtype_name == "bf16":
+                import torch
+                yield lo + r0, O.bf16_bits_to_f32(xb.view(torch.int16).cpu().numpy().view(np.uint16))
+            else:
+                yield lo + r0, xb.cpu().numpy().astype(np.float32)
+    return O.topk_blocks_exact(Qsel_f32, blocks(), k, metric="cos", extra=extra)
+
+
+def judge_results(ref_s, ref_i, results, k, rel_tol=1e-3):
+    """results: {name: (scores [nq, k], ids [nq, k])} -> per-result worst case over the checked queries."""
+    from oracle import retrieval_oracle as O
+    out = {}
+    for name, (gs, gi) in results.items():
+        rs = [O.check_topk_against_list(gs[j], gi[j], ref_s[j], ref_i[j], k, rel_tol) for j in range(ref_s.shape[0])]
+        out[name] = {"recall": min(r["recall"] for r in rs), "recall_strict": min(r["recall_strict"] for r in rs),
+                     "max_rel_score_err": max(r["max_rel_score_err"] for r in rs), "ok": all(r["ok"] for r in rs)}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -373,6 +407,35 @@ def main():
                "note": "pinned host queries -> H2D -> search -> D2H results to pinned host, per step; corpus index resident"
                        + ("" if world == 1 else "; batches pipelined by one (exchange/merge/D2H of batch i-1 overlap the search of batch i)")}
 
+    # ---- recall leg (outside the timed regions): oracle top-k of a few queries of the LAST timed batch over the whole
+    # (sharded) corpus, streamed back from HBM; checks the device-resident result and the e2e host result ------------
+    verify = None
+    if a.verify_queries > 0:
+        import numpy as np
+        t0 = time.perf_counter()
+        nq = min(a.verify_queries, a.batch)
+        sel = np.unique(np.linspace(0, a.batch - 1, nq).astype(np.int64))
+        last = a.warmup + a.steps - 1
+        Qsel = Qh[last][torch.from_numpy(sel)].float().numpy()
+        loc_s, loc_i = oracle_lists_for_shard(X[:n_local], lo, Qsel, a.k, a.dtype)
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, (loc_s, loc_i))
+        else:
+            parts = [(loc_s, loc_i)]
+        if rank == 0:
+            from oracle import retrieval_oracle as O
+            ref_s, ref_i = O.merge_topk(np.stack([p_[0] for p_ in parts], axis=1), np.stack([p_[1] for p_ in parts], axis=1),
+                                        loc_s.shape[1])
+            results = {"device": (out[0][sel].cpu().numpy(), out[1][sel].cpu().numpy())}
+            if e2e is not None:
+                results["e2e"] = (hs.numpy()[sel], hi_.numpy()[sel])
+            verify = judge_results(ref_s, ref_i, results, a.k)
+            verify["queries"] = int(len(sel))
+            verify["seconds"] = time.perf_counter() - t0
+            verify["how"] = ("fp64 cosine + stable (score desc, id asc) order of the oracle over all rows of every shard (f32 BLAS "
+                             "prefilter per 262144-row block, fp64 re-score), merged over ranks; tie-aware rule, 1e-3 relative")
+
     # ---- roofline of the dominant kernel ---------------------------------------------------------------
     peaks = {}
     try:
@@ -426,6 +489,7 @@ def main():
         cpu_baseline = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                         "reference_style_python": cpu_python_style_qps(a.rows, a.dim, a.k)}
 
+    failed = False
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -441,10 +505,21 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "per_rank": per_rank,
         }
+        if verify is not None:
+            line["recall"] = min(v["recall"] for v in verify.values() if isinstance(v, dict))
+            line["max_rel_score_err"] = max(v["max_rel_score_err"] for v in verify.values() if isinstance(v, dict))
+            line["verify"] = verify
+            failed = not all(v["ok"] for v in verify.values() if isinstance(v, dict))
         print(json.dumps(line), flush=True)
     if world > 1:
+        flag = torch.tensor([1 if (rank == 0 and failed) else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        failed = bool(int(flag.item()))
         dist.barrier()
         dist.destroy_process_group()
+    if failed:
+        sys.stderr.write("[bench] recall check FAILED: the timed results differ from the oracle\n")
+        return 1
     return 0
 
 

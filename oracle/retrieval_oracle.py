@@ -332,3 +332,97 @@ def check_topk(got_scores: np.ndarray, got_ids: np.ndarray, ref_full_scores: np.
     got = set(ids.tolist())
     assert must <= got, f"missing {sorted(must - got)[:5]}"
     assert got <= may, f"spurious {sorted(got - may)[:5]}"
+
+
+# ----------------------------------------------------------------------------- large-N verification (bench.py's recall leg)
+
+
+def topk_blocks_exact(Q: np.ndarray, blocks: Iterable[Tuple[int, np.ndarray]], k: int, metric: str = "cos",
+                      extra: int = 64, margin: float = 2e-4) -> Tuple[np.ndarray, np.ndarray]:
+    """Exact (fp64) top-(k+extra) of a few queries over a corpus that arrives in row blocks ``(first_id, X_block f32)``,
+    at sizes where a full fp64 score matrix per block would take minutes (10M x 768).
+
+    Same metric and ranking rule as ``topk`` (retrieval_backend.py:192-197, 371-372).  Per block the float32 BLAS scores
+    only PRE-FILTER: every row whose f32 score is within ``margin`` (absolute; >= 4x the worst-case f32 rounding of a
+    768-term dot product of unit-scale vectors) of the block's (k+extra)-th f32 score is kept, and the kept rows are
+    re-scored in fp64 exactly like ``score_matrix``; the running result is the exact (score desc, id asc) order of those
+    fp64 scores.  A row of the true top-(k+extra) cannot be dropped: its f32 score is within margin/4 of its fp64 score.
+    Returns (scores f64 [B, k+extra], ids i64 [B, k+extra]) padded with (-inf, -1)."""
+    Q64 = np.asarray(Q, dtype=np.float64)
+    Q32 = np.asarray(Q, dtype=np.float32)
+    B = Q64.shape[0]
+    want = k + extra
+    qn = np.sqrt((Q64 * Q64).sum(axis=1))
+    best_s = [np.empty(0, dtype=np.float64) for _ in range(B)]
+    best_i = [np.empty(0, dtype=np.int64) for _ in range(B)]
+    for first_id, Xb in blocks:
+        Xb = np.asarray(Xb, dtype=np.float32)
+        n = Xb.shape[0]
+        if n == 0:
+            continue
+        S = Q32 @ Xb.T                                                  # [B, n] prefilter only
+        if metric == "cos":
+            xn32 = np.sqrt(np.einsum("nd,nd->n", Xb, Xb))
+            qn32 = np.sqrt((Q32 * Q32).sum(axis=1))
+            den = qn32[:, None] * xn32[None, :]
+            np.divide(S, den, out=S, where=den != 0)
+            S[den == 0] = 0.0
+        kk = min(want, n)
+        for b in range(B):
+            if kk < n:
+                cut = np.partition(S[b], n - kk)[n - kk] - margin
+                sel = np.nonzero(S[b] >= cut)[0]
+            else:
+                sel = np.arange(n)
+            Xs = Xb[sel].astype(np.float64)
+            s = Xs @ Q64[b]
+            if metric == "cos":
+                xn = np.sqrt((Xs * Xs).sum(axis=1))
+                den = xn * qn[b]
+                s = np.divide(s, den, out=np.zeros_like(s), where=den != 0)
+            cs = np.concatenate([best_s[b], s])
+            ci = np.concatenate([best_i[b], sel.astype(np.int64) + int(first_id)])
+            order = np.lexsort((ci, -cs))[:want]
+            best_s[b], best_i[b] = cs[order], ci[order]
+    out_s = np.full((B, want), -np.inf, dtype=np.float64)
+    out_i = np.full((B, want), -1, dtype=np.int64)
+    for b in range(B):
+        out_s[b, : len(best_s[b])] = best_s[b]
+        out_i[b, : len(best_i[b])] = best_i[b]
+    return out_s, out_i
+
+
+def check_topk_against_list(got_scores: np.ndarray, got_ids: np.ndarray, ref_scores: np.ndarray, ref_ids: np.ndarray,
+                            k: int, rel_tol: float) -> Dict[str, float]:
+    """``check_topk`` for ONE query when only the oracle's ordered top-(k+extra) list is available (large N).
+
+    Tie-aware rule of the north star: with s_k the oracle's k-th score and tol = rel_tol * max|score|, every oracle
+    entry above s_k + 2 tol must be returned, every returned id must be an oracle entry >= s_k - 2 tol, returned scores
+    must agree with the oracle's within rel_tol (relative), and bit-equal returned scores must list the lower id first
+    when the oracle ties them exactly.  Needs the list to reach below s_k - 2 tol (``deep_enough``); raises otherwise.
+    Returns {"recall", "recall_strict", "max_rel_score_err", "ok"}."""
+    valid = ref_ids >= 0
+    rs, ri = ref_scores[valid].astype(np.float64), ref_ids[valid].astype(np.int64)
+    kk = min(k, len(ri))
+    gs, gi = np.asarray(got_scores[:kk], dtype=np.float64), np.asarray(got_ids[:kk], dtype=np.int64)
+    scale = max(1e-30, float(np.max(np.abs(rs)))) if len(rs) else 1.0
+    tol = rel_tol * scale
+    s_k = rs[kk - 1]
+    if len(rs) > kk and not rs[-1] < s_k - 2 * tol:
+        raise ValueError("oracle list too shallow for the tie-aware check: raise `extra`")
+    ref_of = {int(i): float(s) for i, s in zip(ri, rs)}
+    must = {int(i) for i, s in zip(ri, rs) if s > s_k + 2 * tol}
+    may = {int(i) for i, s in zip(ri, rs) if s >= s_k - 2 * tol}
+    got = [int(i) for i in gi]
+    gset = set(got)
+    ok = len(gset) == kk and must <= gset and gset <= may
+    hit = len(gset & may)
+    errs = [abs(ref_of[i] - s) / scale for i, s in zip(got, gs) if i in ref_of]
+    max_err = max(errs) if errs else float("inf")
+    ok = ok and max_err <= rel_tol and bool(np.all(gs[:-1] >= gs[1:] - 2 * tol))
+    for j in np.nonzero(gs[1:] == gs[:-1])[0]:
+        a, c = got[j], got[j + 1]
+        if a in ref_of and c in ref_of and ref_of[a] == ref_of[c] and not a < c:
+            ok = False
+    return {"recall": hit / kk if kk else 1.0, "recall_strict": len(gset & set(ri[:kk].tolist())) / kk if kk else 1.0,
+            "max_rel_score_err": max_err, "ok": bool(ok)}

@@ -53,7 +53,10 @@ def run_search(name, N, D, B, k, dtype, path, steps=10, warmup=3, check=True):
     used = path if path != "auto" else ("gemm" if dtype in (torch.bfloat16, torch.float16) else "scan")
     line = {"config": name, "rows": N, "dim": D, "batch": B, "k": k, "dtype": str(dtype).split(".")[-1], "path": used,
             "ms_per_batch": ms, "queries_per_s": B / (ms * 1e-3), "kernel_ms_per_batch": kms, "kernel_launches_per_batch": kn / steps}
-    passes = 1 if used == "gemm" else (B + 3) // 4
+    # corpus passes per batch: the tile kernel streams the corpus once; the bulk-fed fp32 scan serves 8 queries per pass
+    # (scan_bulk.cu), the register-fed scan 4 (scan_topk.cu)
+    per_pass = 8 if dtype == torch.float32 else 4
+    passes = 1 if used == "gemm" else (B + per_pass - 1) // per_pass
     gbs = N * D * esz * passes / (kms * 1e-3) / 1e9
     tfs = 2.0 * B * N * D / (kms * 1e-3) / 1e12
     line["hbm_GBps"] = gbs

@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from oracle import retrieval_oracle as O
+from tests.helpers_graph import check_graph_query
 
 pytestmark = pytest.mark.gpu
 
@@ -24,28 +25,6 @@ def _run(X_f32, q_f32, row_ptr, col_idx, seeds, window, a_d, a_g, k, dtype=torch
     return expand_rescore(ix, g, Q, torch.from_numpy(np.asarray(seeds, dtype=np.int64)).to(_dev()), window, a_d, a_g, k)
 
 
-def _check_query(out, b, top, dist, k, tol=2e-3):
-    ids = out["id"][b].cpu().numpy()
-    sc = out["score"][b].cpu().numpy().astype(np.float64)
-    hop = out["hop"][b].cpu().numpy()
-    n = len(top)
-    assert int(out["ncand"][b]) == len(dist)
-    assert np.all(ids[n:] == -1)
-    ref_ids = [t[0] for t in top]
-    ref_sc = np.array([t[1] for t in top])
-    # hop distances are integers: exact
-    for i in range(n):
-        assert hop[i] == dist[int(ids[i])]
-    assert np.allclose(sc[:n], ref_sc, atol=tol)
-    if list(ids[:n]) != ref_ids:
-        # only near-ties (within tol) may be permuted / swapped at the boundary
-        full = {t[0]: t[1] for t in top}
-        for i, nid in enumerate(ids[:n]):
-            assert abs(sc[i] - ref_sc[i]) <= tol
-            if int(nid) in full:
-                assert abs(full[int(nid)] - sc[i]) <= tol
-
-
 def test_golden_expand_rescore(golden_dir):
     with open(os.path.join(golden_dir, "expand_rescore_cases.json")) as f:
         cases = json.load(f)
@@ -54,21 +33,22 @@ def test_golden_expand_rescore(golden_dir):
         q = O.bf16_bits_to_f32(np.array(c["q_bf16"], dtype=np.uint16))
         row_ptr, col_idx = O.csr_from_edges(c["V"], np.array(c["src"], dtype=np.int64), np.array(c["dst"], dtype=np.int64))
         out = _run(X, q[None, :], row_ptr, col_idx, [c["seeds"]], c["window"], c["alpha_dense"], c["alpha_graph"], c["k"])
+        # the fixture's ranking was recorded from the reference's own functions; the live oracle (pinned to them by
+        # tests/test_oracle_golden.py) supplies the full ranking the near-tie rule needs
+        check_graph_query(out, 0, q, X, row_ptr, col_idx, c["seeds"], c["window"], c["alpha_dense"], c["alpha_graph"], c["k"])
         ids = out["id"][0].cpu().numpy()
         n = len(c["top_ids"])
         dist = dict(zip(c["cand"], c["dist"]))
         assert int(out["ncand"][0]) == len(c["cand"])
-        assert np.allclose(out["score"][0].cpu().numpy()[:n], c["top_scores"], atol=2e-3)
-        got = list(ids[:n])
-        if got != c["top_ids"]:
-            # near-ties only
-            ref = dict(zip(c["top_ids"], c["top_scores"]))
-            for i, nid in enumerate(got):
-                assert abs(out["score"][0, i].item() - c["top_scores"][i]) <= 2e-3
+        got = [int(x) for x in ids[:n]]
+        ref = dict(zip(c["top_ids"], c["top_scores"]))
+        same = np.array(got) == np.array(c["top_ids"])
+        # recorded reference scores: positions that agree with the recorded ids agree to 1e-3 relative of the score scale
+        scale = max(1e-30, max(abs(x) for x in c["top_scores"]))
+        assert np.allclose(out["score"][0].cpu().numpy()[:n][same], np.array(c["top_scores"])[same], rtol=0, atol=1e-3 * scale)
         for i in range(n):
-            assert int(out["hop"][0, i]) == dist[int(ids[i])]
-        assert np.allclose(out["score_graph_norm"][0].cpu().numpy()[:n][np.array(got) == np.array(c["top_ids"])],
-                           np.array(c["top_g"])[np.array(got) == np.array(c["top_ids"])], atol=1e-5)
+            assert int(out["hop"][0, i]) == dist[got[i]]
+        assert np.allclose(out["score_graph_norm"][0].cpu().numpy()[:n][same], np.array(c["top_g"])[same], atol=1e-6)
 
 
 def test_bfs_golden_distances(golden_dir):
@@ -103,8 +83,7 @@ def test_random_graph_batch_vs_oracle():
     seeds[:, 1] = seeds[:, 0]   # duplicate seed
     out = _run(X, Q, row_ptr, col_idx, seeds, 2, 0.4, 0.2, k)
     for b in range(0, B, 7):
-        top, dist = O.expand_rescore(Q[b], X, row_ptr, col_idx, seeds[b], 2, 0.4, 0.2, k)
-        _check_query(out, b, top, dist, k)
+        check_graph_query(out, b, Q[b], X, row_ptr, col_idx, seeds[b], 2, 0.4, 0.2, k)
 
 
 def test_frontier_overflow_is_reported():
@@ -132,8 +111,7 @@ def test_hub_node_and_retry_instantiation():
     seeds = np.array([[0, 6500, -1], [6100, 6200, 6300]])
     out = _run(X, Q, row_ptr, col_idx, seeds, 1, 0.4, 0.2, k)
     for b in range(2):
-        top, dist = O.expand_rescore(Q[b], X, row_ptr, col_idx, seeds[b], 1, 0.4, 0.2, k)
-        _check_query(out, b, top, dist, k)
+        check_graph_query(out, b, Q[b], X, row_ptr, col_idx, seeds[b], 1, 0.4, 0.2, k)
     assert int(out["ncand"][0]) > 4096
 
 
@@ -154,8 +132,7 @@ def test_frontier_spanning_several_batches_and_isolated_nodes():
     seeds = np.array([[0, 5000, 5001, 0], [5002, 3550, -1, 5003]])     # 5000.. are isolated
     out = _run(X, Q, row_ptr, col_idx, seeds, 2, 0.4, 0.2, k)
     for b in range(2):
-        top, dist = O.expand_rescore(Q[b], X, row_ptr, col_idx, seeds[b], 2, 0.4, 0.2, k)
-        _check_query(out, b, top, dist, k)
+        check_graph_query(out, b, Q[b], X, row_ptr, col_idx, seeds[b], 2, 0.4, 0.2, k)
     assert int(out["ncand"][0]) > 3000
 
 
@@ -169,8 +146,7 @@ def test_wide_embeddings_3072():
     seeds = rng.integers(0, V, size=(B, 8))
     out = _run(X, Q, row_ptr, col_idx, seeds, 2, 0.4, 0.2, k)
     for b in range(B):
-        top, dist = O.expand_rescore(Q[b], X, row_ptr, col_idx, seeds[b], 2, 0.4, 0.2, k)
-        _check_query(out, b, top, dist, k)
+        check_graph_query(out, b, Q[b], X, row_ptr, col_idx, seeds[b], 2, 0.4, 0.2, k)
 
 
 def test_flat_channels_tie_to_lower_id_and_padding():

@@ -320,3 +320,52 @@ def test_min_score_floor_and_semantic_sim_edges():
     maybe = set(zip(*[a[S[iu] >= tau - 1e-3].tolist() for a in iu]))
     assert sure <= got <= maybe
     assert all(a < b for a, b in got) and 7 not in {a for a, _ in got} | {b for _, b in got}
+
+
+def _device_unit_rows(n, d, seed, dtype=torch.bfloat16, block=1 << 19):
+    X = torch.empty((n, d), dtype=dtype, device=_dev())
+    for r0 in range(0, n, block):
+        g = torch.Generator(device="cuda").manual_seed(seed + r0)
+        t = torch.randn((min(block, n - r0), d), generator=g, device=_dev(), dtype=torch.float32)
+        t /= t.norm(dim=1, keepdim=True)
+        X[r0:r0 + t.shape[0]] = t.to(dtype)
+    return X
+
+
+@pytest.mark.parametrize("N,D,B,k,nq", [
+    (1_000_000, 768, 1024, 100, 24),     # BASELINE.json configs[1] at full size
+    (2_100_000, 768, 640, 100, 16),      # 5 phases, 37 chunks, CTA pairs with a half-empty last pair (the 10M x 4096 schedule's shape)
+    (1_250_000, 768, 4096, 100, 16),     # one rank's shard of configs[2] at N=8, full batch
+])
+def test_benchmark_scale_configs_vs_oracle(N, D, B, k, nq):
+    """The configurations the throughput numbers are quoted on, checked like bench.py's recall leg: fp64 oracle top-k of
+    `nq` queries over ALL rows (streamed back in blocks), tie-aware rule, 1e-3 relative scores; plus exact ties planted
+    across distant tiles / phases (duplicates of row 17), which must come out adjacent, lowest id first."""
+    X = _device_unit_rows(N, D, seed=N + B)
+    dup = [17, 1000, N // 3, N - 5]
+    for r in dup[1:]:
+        X[r] = X[17]
+    g = torch.Generator(device="cuda").manual_seed(99)
+    Q = torch.randn((B, D), generator=g, device=_dev(), dtype=torch.float32)
+    Q /= Q.norm(dim=1, keepdim=True)
+    Q = Q.to(torch.bfloat16)
+    Q[5] = X[17]
+    ix = _index(X)
+    scores, ids = ix.search(Q, k)
+    sel = np.unique(np.concatenate([[5, 0, B - 1, 127, 128, 255, 256], np.linspace(0, B - 1, nq).astype(np.int64)]))
+    Qs = Q[torch.from_numpy(sel).to(_dev())].float().cpu().numpy()
+
+    def blocks(rows=1 << 18):
+        for r0 in range(0, N, rows):
+            yield r0, O.bf16_bits_to_f32(X[r0:r0 + rows].view(torch.int16).cpu().numpy().view(np.uint16))
+    ref_s, ref_i = O.topk_blocks_exact(Qs, blocks(), k, extra=64)
+    gs, gi = scores.cpu().numpy(), ids.cpu().numpy()
+    for j, b in enumerate(sel):
+        r = O.check_topk_against_list(gs[b], gi[b], ref_s[j], ref_i[j], k, 1e-3)
+        assert r["ok"] and r["recall"] == 1.0, (int(b), r)
+    assert gi[5, :4].tolist() == sorted(dup)
+    assert np.all(gs[5, :4] == gs[5, 0])
+    # whole-batch invariants at full size: ids unique per query, scores sorted
+    assert bool((scores[:, :-1] >= scores[:, 1:]).all())
+    srt = ids.sort(dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())

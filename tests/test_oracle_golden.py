@@ -108,3 +108,46 @@ def test_bf16_roundtrip_helpers():
     y = O.bf16_bits_to_f32(b)
     assert np.all(np.abs(y - x) <= np.abs(x) * 2 ** -8)
     assert np.array_equal(O.f32_to_bf16_bits(y), b)
+
+
+def test_blockwise_prefiltered_topk_equals_exact_topk():
+    """bench.py's recall leg uses topk_blocks_exact (f32 prefilter + fp64 re-score per row block): it must reproduce
+    the plain fp64 oracle, ties (duplicated rows across blocks) included."""
+    rng = np.random.default_rng(5)
+    N, D, B, k = 9000, 96, 5, 40
+    X = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((N, D)).astype(np.float32)))
+    X[7000] = X[11]
+    X[N - 1] = X[11]
+    X[123] = 0.0
+    Q = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((B, D)).astype(np.float32)))
+    Q[0] = X[11]
+    for metric in ("cos", "ip"):
+        ref_s, ref_i = O.topk(Q, X, k + 8, metric=metric)
+        blocks = ((r0, X[r0:r0 + 2048]) for r0 in range(0, N, 2048))
+        s, i = O.topk_blocks_exact(Q, blocks, k, metric=metric, extra=8)
+        assert np.array_equal(i, ref_i)
+        assert np.allclose(s, ref_s, rtol=0, atol=1e-12)
+        for b in range(B):
+            r = O.check_topk_against_list(ref_s[b, :k].astype(np.float32), ref_i[b, :k], s[b], i[b], k, 1e-3)
+            assert r["ok"] and r["recall"] == 1.0 and r["recall_strict"] == 1.0 and r["max_rel_score_err"] < 1e-6
+        # a wrong id (outside the near-tie band) and a wrong score must both be caught
+        bad_i = ref_i[1, :k].copy()
+        bad_i[3] = int(i[1, -1]) if i[1, -1] not in bad_i else N + 5
+        if s[1, -1] < s[1, k - 1] - 1e-2:
+            assert not O.check_topk_against_list(ref_s[1, :k], bad_i, s[1], i[1], k, 1e-3)["ok"]
+        bad_s = ref_s[1, :k].copy()
+        bad_s[0] *= 1.01
+        assert not O.check_topk_against_list(bad_s, ref_i[1, :k], s[1], i[1], k, 1e-3)["ok"]
+
+
+def test_blockwise_topk_shard_merge_equals_global():
+    """Per-rank lists (id_base = shard start) merged with merge_topk equal the single-process list: what bench.py's recall
+    leg does at N > 1."""
+    rng = np.random.default_rng(6)
+    N, D, B, k = 5000, 32, 3, 20
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    full_s, full_i = O.topk_blocks_exact(Q, [(0, X)], k, extra=4)
+    parts = [O.topk_blocks_exact(Q, [(lo, X[lo:lo + 1700])], k, extra=4) for lo in range(0, N, 1700)]
+    ms, mi = O.merge_topk(np.stack([p[0] for p in parts], axis=1), np.stack([p[1] for p in parts], axis=1), k + 4)
+    assert np.array_equal(mi, full_i) and np.array_equal(ms, full_s)
