@@ -43,6 +43,7 @@ void profile_end(cudaStream_t st) {
 static int g_q_replicas = [] { const char* e = getenv("B200R_Q_REPLICAS"); return (e && e[0] == '0') ? 0 : 1; }();
 static int g_cta_group_max = [] { const char* e = getenv("B200R_CTA_GROUP"); return (e && e[0] == '1') ? 1 : 2; }();
 int select_group_size();
+int select_max_flat_segments();
 int gemm_tile_rows();
 int gemm_tile_queries();
 int32_t expand_max_candidates();
@@ -202,7 +203,12 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   }
   size_t off = 0;
   pl->off_lists = off; off += align_up((size_t)pl->num_segments * pl->Bpad * pl->cap * 8, 256);
-  pl->off_counts = off; off += align_up((size_t)pl->num_segments * pl->Bpad * 4, 256);
+  // counts[num_segments][Bpad] followed by the carry lists' counts [Bpad] (zeroed together by init_search)
+  pl->off_counts = off; off += align_up((size_t)(pl->num_segments + 1) * pl->Bpad * 4, 256);
+  if (path == B200R_PATH_GEMM && pl->num_phases > 1 && pl->num_segments + 1 <= select_max_flat_segments()) {
+    pl->carry_cap = select_stage_limit(k, B);
+    pl->off_carry = off; off += align_up((size_t)pl->Bpad * pl->carry_cap * 8, 256);
+  }
   pl->off_gthr = off; off += align_up((size_t)pl->Bpad * 4, 256);
   pl->off_qinv = off; off += align_up((size_t)pl->Bpad * 4, 256);
   pl->num_groups = 0;
@@ -220,20 +226,31 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
 
 static int query_dtype(const Index* ix) { return ix->dtype == B200R_I8 ? B200R_F32 : ix->dtype; }
 
-static int do_search(Index* ix, const void* Q, int B, int k, int path, float* out_scores, int64_t* out_ids, void* ws,
-                     size_t ws_bytes, cudaStream_t st, const PeerScatter* peers = nullptr, cudaEvent_t wait_before_output = nullptr,
-                     float min_score = -HUGE_VALF) {
+// The path `auto` resolves to (make_plan applies the same rule).
+static int resolve_path(const Index* ix, int B, int path) {
+  if (path != B200R_PATH_AUTO) return path;
+  const bool i8_ok = ix->has_tmap_i8 && rows_i8_nq(B, ix->D) > 0;
+  return (ix->has_tmap || i8_ok) ? B200R_PATH_GEMM : B200R_PATH_SCAN;
+}
+
+// Queries one planned search may carry.  The scan kernels and the int8 tensor kernel keep one candidate list per
+// (consumer warp | epilogue warp, query), i.e. megabytes of workspace per query: bigger batches run as consecutive
+// slices over the same workspace (the corpus is streamed once per <= 8 / <= 64 queries either way).
+static int slice_queries(const Index* ix, int B, int k, int path) {
+  const int resolved = resolve_path(ix, B, path);
+  if (resolved == B200R_PATH_SCAN) return k <= 256 ? 32 : 16;
+  if (ix->dtype == B200R_I8) return 256;
+  return 1 << 30;
+}
+
+static int do_search_one(Index* ix, const void* Q, int B, int k, int path, float* out_scores, int64_t* out_ids, void* ws,
+                         size_t ws_bytes, cudaStream_t st, const CommDev* comm, size_t rec_stride, float min_score) {
   SearchPlan pl;
   int rc = make_plan(ix, B, k, path, &pl);
   if (rc) return rc;
-  if (!Q || (!peers && (!out_scores || !out_ids))) { set_error("null Q / output pointer"); return B200R_EINVAL; }
   if (!ws || ws_bytes < pl.off_end) {
     set_error("workspace too small: need %zu bytes, got %zu", pl.off_end, ws_bytes);
     return B200R_ENOMEM;
-  }
-  if ((reinterpret_cast<uintptr_t>(Q) & 15) || (reinterpret_cast<uintptr_t>(ws) & 255)) {
-    set_error("Q must be 16-byte aligned and the workspace 256-byte aligned");
-    return B200R_EINVAL;
   }
   if ((rc = launch_init_search(pl, ws, st))) return rc;
   if (ix->metric == B200R_COS) {
@@ -278,9 +295,88 @@ static int do_search(Index* ix, const void* Q, int B, int k, int path, float* ou
     profile_end(st);
     if (rc) return rc;
   }
-  // the peers' buffers may only be overwritten once every rank has consumed what the previous use of them held
-  if (wait_before_output) B200R_CUDA_CHECK(cudaStreamWaitEvent(st, wait_before_output, 0));
-  return launch_select_lists(ix, pl, ws, out_scores, out_ids, st, peers, min_score);
+  return launch_select_lists(ix, pl, ws, out_scores, out_ids, st, comm, rec_stride, min_score);
+}
+
+// workspace of a whole (possibly sliced) search; *temp_off = where the packed [ids | scores] record of a sliced
+// search under an exchange is staged before it is scattered to the peers
+static size_t search_workspace(const Index* ix, int B, int k, int path, size_t* temp_off) {
+  const int S = slice_queries(ix, B, k, path);
+  SearchPlan pl;
+  if (make_plan(ix, B < S ? B : S, k, resolve_path(ix, B, path), &pl)) return 0;
+  size_t need = pl.off_end;
+  if (B > S && B % S) {          // a short last slice may plan a different layout: cover both
+    SearchPlan pt;
+    if (make_plan(ix, B % S, k, resolve_path(ix, B, path), &pt)) return 0;
+    if (pt.off_end > need) need = pt.off_end;
+  }
+  if (temp_off) *temp_off = need;
+  if (B > S) need += align_up((size_t)12 * B * k, 256);
+  return need;
+}
+
+// comm != nullptr: instead of a local result, this rank's packed record goes to every rank's exchange window
+static int do_search(Index* ix, const void* Q, int B, int k, int path, float* out_scores, int64_t* out_ids, void* ws,
+                     size_t ws_bytes, cudaStream_t st, const Comm* comm = nullptr, float min_score = -HUGE_VALF) {
+  if (B <= 0) { set_error("B must be > 0 (got %d)", B); return B200R_EINVAL; }
+  if (k <= 0 || k > B200R_MAX_K) { set_error("k must be in [1, %d] (got %d)", B200R_MAX_K, k); return B200R_EINVAL; }
+  if (!Q || (!comm && (!out_scores || !out_ids))) { set_error("null Q / output pointer"); return B200R_EINVAL; }
+  if ((reinterpret_cast<uintptr_t>(Q) & 15) || (reinterpret_cast<uintptr_t>(ws) & 255)) {
+    set_error("Q must be 16-byte aligned and the workspace 256-byte aligned");
+    return B200R_EINVAL;
+  }
+  size_t temp_off = 0;
+  const size_t need = search_workspace(ix, B, k, path, &temp_off);
+  if (need == 0) return B200R_EINVAL;
+  if (!ws || ws_bytes < need) { set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes); return B200R_ENOMEM; }
+  CommDev cd;
+  const size_t stride = dense_record_stride(B, k);
+  int rc;
+  if (comm && (rc = comm_dev(comm, kChanDense, stride, &cd))) return rc;
+  const int S = slice_queries(ix, B, k, path);
+  const int resolved = resolve_path(ix, B, path);
+  if (B <= S) return do_search_one(ix, Q, B, k, resolved, out_scores, out_ids, ws, ws_bytes, st, comm ? &cd : nullptr, stride, min_score);
+  float* os = out_scores; int64_t* oi = out_ids;
+  if (comm) {
+    oi = reinterpret_cast<int64_t*>((char*)ws + temp_off);
+    os = reinterpret_cast<float*>((char*)ws + temp_off + (size_t)8 * B * k);
+  }
+  const size_t qrow = (size_t)ix->D * elem_size(query_dtype(ix));
+  for (int b0 = 0; b0 < B; b0 += S) {
+    const int nb = B - b0 < S ? B - b0 : S;
+    rc = do_search_one(ix, (const char*)Q + (size_t)b0 * qrow, nb, k, resolved, os + (size_t)b0 * k, oi + (size_t)b0 * k, ws, temp_off, st,
+                       nullptr, 0, min_score);
+    if (rc) return rc;
+  }
+  if (comm) return launch_scatter_record(cd, (char*)ws + temp_off, (size_t)12 * B * k, stride, st);
+  return B200R_OK;
+}
+
+// (re)size the library-owned device staging of the *_host calls; the stream is drained before a buffer is replaced
+static int ensure_staging(Index* ix, size_t qbytes, size_t oelems, size_t wsbytes, cudaStream_t st) {
+  if (ix->q_dev_bytes >= qbytes && ix->out_dev_elems >= oelems && ix->ws_bytes >= wsbytes) return B200R_OK;
+  B200R_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (ix->q_dev_bytes < qbytes) {
+    if (ix->h_q_dev) cudaFree(ix->h_q_dev);
+    ix->h_q_dev = nullptr; ix->q_dev_bytes = 0;
+    B200R_CUDA_CHECK(cudaMalloc(&ix->h_q_dev, qbytes));
+    ix->q_dev_bytes = qbytes;
+  }
+  if (ix->out_dev_elems < oelems) {
+    if (ix->h_s_dev) cudaFree(ix->h_s_dev);
+    if (ix->h_i_dev) cudaFree(ix->h_i_dev);
+    ix->h_s_dev = nullptr; ix->h_i_dev = nullptr; ix->out_dev_elems = 0;
+    B200R_CUDA_CHECK(cudaMalloc(&ix->h_s_dev, oelems * sizeof(float)));
+    B200R_CUDA_CHECK(cudaMalloc(&ix->h_i_dev, oelems * sizeof(int64_t)));
+    ix->out_dev_elems = oelems;
+  }
+  if (ix->ws_bytes < wsbytes) {
+    if (ix->h_ws) cudaFree(ix->h_ws);
+    ix->h_ws = nullptr; ix->ws_bytes = 0;
+    B200R_CUDA_CHECK(cudaMalloc(&ix->h_ws, wsbytes));
+    ix->ws_bytes = wsbytes;
+  }
+  return B200R_OK;
 }
 
 }  // namespace b200r
@@ -375,9 +471,9 @@ int b200r_index_info(uint64_t index, int64_t* N, int32_t* D, int32_t* dtype, int
 size_t b200r_search_workspace_bytes(uint64_t index, int32_t B, int32_t k, int32_t path) {
   Index* ix = get_index(index);
   if (!ix) return 0;
-  SearchPlan pl;
-  if (make_plan(ix, B, k, path, &pl)) return 0;
-  return pl.off_end;
+  if (B <= 0) { set_error("B must be > 0 (got %d)", B); return 0; }
+  if (k <= 0 || k > B200R_MAX_K) { set_error("k must be in [1, %d] (got %d)", B200R_MAX_K, k); return 0; }
+  return search_workspace(ix, B, k, path, nullptr);
 }
 
 int b200r_search(uint64_t index, const void* Q, int32_t B, int32_t k, int32_t path, float* out_scores, int64_t* out_ids,
@@ -395,27 +491,7 @@ int b200r_search_min_score(uint64_t index, const void* Q, int32_t B, int32_t k, 
   if (!(min_score == min_score)) { set_error("min_score is NaN"); return B200R_EINVAL; }
   B200R_CUDA_CHECK(cudaSetDevice(ix->device));
   return do_search(ix, Q, B, k, path, out_scores, out_ids, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream),
-                   nullptr, nullptr, min_score);
-}
-
-int b200r_search_scatter(uint64_t index, const void* Q, int32_t B, int32_t k, int32_t path, const uint64_t* peer_bases_host,
-                         int32_t n_peers, int32_t rank, void* wait_event, void* workspace, size_t workspace_bytes, void* stream) {
-  Index* ix = get_index(index);
-  if (!ix) return B200R_ESTATE;
-  if (!peer_bases_host || n_peers < 1 || n_peers > B200R_MAX_PEERS || rank < 0 || rank >= n_peers) {
-    set_error("bad peer arguments (n_peers=%d rank=%d)", n_peers, rank);
-    return B200R_EINVAL;
-  }
-  if (((long long)B * k) % 2) { set_error("search_scatter needs B*k even (packed record layout)"); return B200R_EINVAL; }
-  PeerScatter ps;
-  ps.n = n_peers; ps.rank = rank;
-  for (int g = 0; g < n_peers; ++g) {
-    if (!peer_bases_host[g] || (peer_bases_host[g] & 7)) { set_error("peer base %d is null or misaligned", g); return B200R_EINVAL; }
-    ps.base[g] = peer_bases_host[g];
-  }
-  B200R_CUDA_CHECK(cudaSetDevice(ix->device));
-  return do_search(ix, Q, B, k, path, nullptr, nullptr, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream), &ps,
-                   reinterpret_cast<cudaEvent_t>(wait_event));
+                   nullptr, min_score);
 }
 
 int b200r_search_host(uint64_t index, const void* Q_host, int32_t B, int32_t k, int32_t path, float* out_scores_host,
@@ -423,39 +499,90 @@ int b200r_search_host(uint64_t index, const void* Q_host, int32_t B, int32_t k, 
   Index* ix = get_index(index);
   if (!ix) return B200R_ESTATE;
   if (!Q_host || !out_scores_host || !out_ids_host) { set_error("null host pointer"); return B200R_EINVAL; }
+  if (B <= 0 || k <= 0 || k > B200R_MAX_K) { set_error("bad B / k (%d / %d)", B, k); return B200R_EINVAL; }
   B200R_CUDA_CHECK(cudaSetDevice(ix->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  SearchPlan pl;
-  int rc = make_plan(ix, B, k, path, &pl);
-  if (rc) return rc;
+  const size_t need = search_workspace(ix, B, k, path, nullptr);
+  if (!need) return B200R_EINVAL;
   const size_t qbytes = (size_t)B * ix->D * elem_size(query_dtype(ix));
   const size_t oelems = (size_t)B * k;
-  if (ix->q_dev_bytes < qbytes) {
-    if (ix->h_q_dev) cudaFree(ix->h_q_dev);
-    ix->h_q_dev = nullptr; ix->q_dev_bytes = 0;
-    B200R_CUDA_CHECK(cudaMalloc(&ix->h_q_dev, qbytes));
-    ix->q_dev_bytes = qbytes;
-  }
-  if (ix->out_dev_elems < oelems) {
-    if (ix->h_s_dev) cudaFree(ix->h_s_dev);
-    if (ix->h_i_dev) cudaFree(ix->h_i_dev);
-    ix->h_s_dev = nullptr; ix->h_i_dev = nullptr; ix->out_dev_elems = 0;
-    B200R_CUDA_CHECK(cudaMalloc(&ix->h_s_dev, oelems * sizeof(float)));
-    B200R_CUDA_CHECK(cudaMalloc(&ix->h_i_dev, oelems * sizeof(int64_t)));
-    ix->out_dev_elems = oelems;
-  }
-  if (ix->ws_bytes < pl.off_end) {
-    if (ix->h_ws) cudaFree(ix->h_ws);
-    ix->h_ws = nullptr; ix->ws_bytes = 0;
-    B200R_CUDA_CHECK(cudaMalloc(&ix->h_ws, pl.off_end));
-    ix->ws_bytes = pl.off_end;
-  }
+  int rc = ensure_staging(ix, qbytes, oelems, need, st);
+  if (rc) return rc;
   B200R_CUDA_CHECK(cudaMemcpyAsync(ix->h_q_dev, Q_host, qbytes, cudaMemcpyHostToDevice, st));
   rc = do_search(ix, ix->h_q_dev, B, k, path, ix->h_s_dev, ix->h_i_dev, ix->h_ws, ix->ws_bytes, st);
   if (rc) return rc;
   B200R_CUDA_CHECK(cudaMemcpyAsync(out_scores_host, ix->h_s_dev, oelems * sizeof(float), cudaMemcpyDeviceToHost, st));
   B200R_CUDA_CHECK(cudaMemcpyAsync(out_ids_host, ix->h_i_dev, oelems * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   B200R_CUDA_CHECK(cudaStreamSynchronize(st));
+  return B200R_OK;
+}
+
+// ---- row-sharded search over the exchange (comm.cu) ----------------------------------------------------------------
+int b200r_search_sharded_begin(uint64_t index, uint64_t comm, const void* Q, int32_t B, int32_t k, int32_t path, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  Index* ix = get_index(index);
+  Comm* c = get_comm(comm);
+  if (!ix || !c) return B200R_ESTATE;
+  if (ix->device != c->device) { set_error("index and comm live on different devices"); return B200R_EINVAL; }
+  B200R_CUDA_CHECK(cudaSetDevice(ix->device));
+  return do_search(ix, Q, B, k, path, nullptr, nullptr, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream), c);
+}
+
+int b200r_search_sharded_finish(uint64_t comm, int32_t B, int32_t k, float* out_scores, int64_t* out_ids, void* stream) {
+  Comm* c = get_comm(comm);
+  if (!c) return B200R_ESTATE;
+  if (!out_scores || !out_ids || B <= 0 || k <= 0 || k > B200R_MAX_K) { set_error("bad arguments"); return B200R_EINVAL; }
+  B200R_CUDA_CHECK(cudaSetDevice(c->device));
+  return launch_exchange_merge(c, B, k, k, out_scores, out_ids, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200r_search_sharded(uint64_t index, uint64_t comm, const void* Q, int32_t B, int32_t k, int32_t path, float* out_scores,
+                         int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = b200r_search_sharded_begin(index, comm, Q, B, k, path, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  return b200r_search_sharded_finish(comm, B, k, out_scores, out_ids, stream);
+}
+
+// One host thread driving G GPUs (the plug-in's single-process mode): host queries in, host results out.  Every device
+// gets the queries, searches its row shard and scatters its record (begin on ALL devices before any finish, so no
+// device's merge kernel waits for a kernel that has not been launched yet); the merged result is read from device 0.
+int b200r_search_sharded_host_all(const uint64_t* indexes, const uint64_t* comms, int32_t G, const void* Q_host, int32_t B, int32_t k,
+                                  int32_t path, float* out_scores_host, int64_t* out_ids_host, void* const* streams) {
+  if (!indexes || !comms || G < 1 || G > B200R_MAX_PEERS) { set_error("bad indexes / comms / G"); return B200R_EINVAL; }
+  if (!Q_host || !out_scores_host || !out_ids_host) { set_error("null host pointer"); return B200R_EINVAL; }
+  if (B <= 0 || k <= 0 || k > B200R_MAX_K) { set_error("bad B / k (%d / %d)", B, k); return B200R_EINVAL; }
+  Index* ix[B200R_MAX_PEERS]; Comm* cm[B200R_MAX_PEERS]; cudaStream_t st[B200R_MAX_PEERS];
+  for (int g = 0; g < G; ++g) {
+    ix[g] = get_index(indexes[g]); cm[g] = get_comm(comms[g]);
+    if (!ix[g] || !cm[g]) return B200R_ESTATE;
+    if (cm[g]->rank != g || cm[g]->world != G || ix[g]->device != cm[g]->device) { set_error("comm %d does not match (rank/world/device)", g); return B200R_EINVAL; }
+    st[g] = streams ? reinterpret_cast<cudaStream_t>(streams[g]) : nullptr;
+  }
+  const size_t oelems = (size_t)B * k;
+  int rc;
+  for (int g = 0; g < G; ++g) {
+    B200R_CUDA_CHECK(cudaSetDevice(ix[g]->device));
+    const size_t need = search_workspace(ix[g], B, k, path, nullptr);
+    if (!need) return B200R_EINVAL;
+    const size_t qbytes = (size_t)B * ix[g]->D * elem_size(query_dtype(ix[g]));
+    if ((rc = ensure_staging(ix[g], qbytes, g == 0 ? oelems : 1, need, st[g]))) return rc;
+    B200R_CUDA_CHECK(cudaMemcpyAsync(ix[g]->h_q_dev, Q_host, qbytes, cudaMemcpyHostToDevice, st[g]));
+    if ((rc = do_search(ix[g], ix[g]->h_q_dev, B, k, path, nullptr, nullptr, ix[g]->h_ws, ix[g]->ws_bytes, st[g], cm[g]))) return rc;
+  }
+  // only rank 0's merged copy is needed on the host; the other ranks still consume the exchange (epochs advance together)
+  for (int g = 0; g < G; ++g) {
+    B200R_CUDA_CHECK(cudaSetDevice(ix[g]->device));
+    if (g == 0) rc = launch_exchange_merge(cm[0], B, k, k, ix[0]->h_s_dev, ix[0]->h_i_dev, st[0]);
+    else rc = launch_exchange_skip(cm[g], st[g]);
+    if (rc) return rc;
+  }
+  B200R_CUDA_CHECK(cudaSetDevice(ix[0]->device));
+  B200R_CUDA_CHECK(cudaMemcpyAsync(out_scores_host, ix[0]->h_s_dev, oelems * sizeof(float), cudaMemcpyDeviceToHost, st[0]));
+  B200R_CUDA_CHECK(cudaMemcpyAsync(out_ids_host, ix[0]->h_i_dev, oelems * sizeof(int64_t), cudaMemcpyDeviceToHost, st[0]));
+  for (int g = 0; g < G; ++g) {
+    B200R_CUDA_CHECK(cudaSetDevice(ix[g]->device));
+    B200R_CUDA_CHECK(cudaStreamSynchronize(st[g]));
+  }
   return B200R_OK;
 }
 

@@ -7,6 +7,7 @@
 #include <string>
 
 #include "../../include/b200r.h"
+#include "comm.cuh"
 
 namespace b200r {
 
@@ -59,6 +60,13 @@ inline size_t elem_size(int dtype) { return dtype == B200R_F32 ? 4 : (dtype == B
 inline int list_cap_soft(int k) { return k <= 256 ? 512 : 2 * k; }
 inline int list_cap(int k) { return list_cap_soft(k) + 32; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+// keys one select CTA stages in shared memory when it reduces a query's lists (also the capacity of the carry list)
+inline int select_stage_limit(int k, int B) {
+  if (B <= 148) return 24576;             // a handful of queries: one CTA per SM can afford a 192 KB stage
+  int limit = 3 * k + 2048;
+  if (limit < 2560) limit = 2560;
+  return limit > 24576 ? 24576 : limit;
+}
 
 constexpr int kMaxPhases = 16;
 struct GemmPhase { int tile_begin, tile_end, num_chunks, tiles_per_chunk; };
@@ -83,7 +91,8 @@ struct SearchPlan {
   int scan_bulk;         // 1: bulk-copy-fed scan (scan_bulk.cu), else the register-fed one (scan_topk.cu)
   // workspace layout (byte offsets)
   int num_groups;        // > 0: two-level final select (lists2/counts2 hold the first level's output)
-  size_t off_lists, off_counts, off_gthr, off_qinv, off_lists2, off_counts2, off_qrep, off_end;
+  int carry_cap;         // > 0: phased search with one carry list per query (select_merge.cu), this many keys each
+  size_t off_lists, off_counts, off_gthr, off_qinv, off_lists2, off_counts2, off_qrep, off_carry, off_end;
 };
 
 int make_plan(const Index* ix, int B, int k, int path, SearchPlan* plan);
@@ -110,9 +119,31 @@ int scan_bulk_warps(const Index* ix);        // consumer warps per CTA of the bu
 int scan_bulk_tile_rows(const Index* ix);
 int launch_scan_bulk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
 // out_scores == nullptr: threshold mode (publish the exact k-th best so far into gthr); else final output
-struct PeerScatter { int n, rank; unsigned long long base[B200R_MAX_PEERS]; };
+// comm != nullptr: the final select stores this rank's packed record into every rank's exchange window (comm.cuh)
 int launch_select_lists(const Index* ix, const SearchPlan& p, void* ws, float* out_scores, int64_t* out_ids, cudaStream_t st,
-                        const PeerScatter* peers = nullptr, float min_score = -__builtin_huge_valf());
+                        const CommDev* comm = nullptr, size_t rec_stride = 0, float min_score = -__builtin_huge_valf());
+
+// ---- shard exchange (comm.cu) ----------------------------------------------------------------------------------
+constexpr uint32_t kCommMagic = 0xB200A003u;
+constexpr int kChanDense = 0, kChanGraphRange = 1, kChanGraphRecords = 2, kChanSpare = 3;
+struct Comm {
+  uint32_t magic;
+  int device, rank, world;
+  int max_B, max_k, max_graph_k;
+  void* window;
+  size_t window_bytes;
+  unsigned long long peer[B200R_MAX_PEERS];     // every rank's window as mapped in this process
+  bool ipc_opened[B200R_MAX_PEERS];
+  bool connected;
+  size_t data_off[kCommChannels], rec_cap[kCommChannels];
+};
+Comm* get_comm(uint64_t h);
+// device-side view of one channel; fails if rec_stride exceeds the channel's record capacity
+int comm_dev(const Comm* c, int channel, size_t rec_stride, CommDev* out);
+inline size_t dense_record_stride(int B, int k) { return align_up((size_t)12 * B * k, 16); }
+int launch_exchange_merge(const Comm* c, int B, int kin, int k, float* out_scores, int64_t* out_ids, cudaStream_t st);
+int launch_exchange_skip(const Comm* c, cudaStream_t st);
+int launch_scatter_record(const CommDev& cd, const void* src, size_t bytes, size_t rec_stride, cudaStream_t st);
 int launch_merge_topk(const float* cs, const int64_t* ci, size_t shard_stride_s, size_t shard_stride_i, int G, int B, int kin, int k,
                       float* os, int64_t* oi, cudaStream_t st, int32_t* osrc = nullptr);
 void profile_begin(cudaStream_t st);

@@ -356,7 +356,7 @@ int launch_min_score(const SearchPlan& pl, void* ws, bool cosine, float min_scor
 int launch_init_search(const SearchPlan& pl, void* ws, cudaStream_t st) {
   u32* gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
   int* counts = reinterpret_cast<int*>((char*)ws + pl.off_counts);
-  const long long n_counts = (long long)pl.num_segments * pl.Bpad;
+  const long long n_counts = (long long)(pl.num_segments + 1) * pl.Bpad;   // + the carry lists' counts
   init_search_kernel<<<kNumSMs, 256, 0, st>>>(gthr, pl.Bpad, counts, n_counts);
   count_launch();
   B200R_CUDA_CHECK(cudaGetLastError());

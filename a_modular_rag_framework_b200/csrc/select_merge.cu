@@ -7,6 +7,7 @@
 // (app/modules/retrieval/retrieval_backend.py:371-372, retrieval_adapter.py:129-131) -- over
 // candidates enumerated in id order, i.e. ties go to the lower id.
 #include "common.cuh"
+#include "comm.cuh"
 #include "internal.h"
 #include <math_constants.h>
 #include <cstring>
@@ -35,18 +36,33 @@ struct SelectParams {
   long long* out_ids;
   u64* out_lists;              // kSelPartial: out_lists[(g*Bpad + q)*k + i]
   int* out_counts;
+  // phased searches: the survivors of every per-phase prune are moved to ONE carry list per query
+  // (carry[q*carry_cap + i], i < counts[S*Bpad + q]) and the per-unit lists restart empty, so a threshold select is two
+  // dependent global loads + a few shared-memory passes instead of a serial walk over every unit list
+  u64* carry;
+  int carry_cap;
   // fused exchange (row-sharded corpora): instead of a local result, the final select writes this rank's packed
-  // record [ids i64 [B,k] | scores f32 [B,k]] straight into slot `rank` of EVERY rank's gather buffer (peer
-  // memory over NVLink), so the all-gather needs no separate collective kernel or staging copy
-  unsigned long long peer_base[B200R_MAX_PEERS];
-  int n_peers, rank;
+  // record [ids i64 [B,k] | scores f32 [B,k]] straight into its place in EVERY rank's exchange window (peer
+  // memory over NVLink, comm.cuh), so the all-gather needs no separate collective kernel or staging copy
+  CommDev comm;
+  int use_comm;
+  unsigned long long rec_stride;   // bytes between the records of consecutive ranks in a slot
+  int final_keys;              // 1: the input lists already hold keys on the FINAL score (second level of a two-level select)
   float min_score;             // results below it are reported as padding (b200r_search_min_score)
 };
+
+// Output and partial modes rank on the FINAL score (raw key score x 1/|q|), not on the score the scan kernels filtered
+// with: two different raw scores can round to the same final fp32, and the reported order must be (final score desc,
+// id asc) -- the order b200r_merge_topk and the shard exchange rely on (lists strictly sorted under that rule).
+__device__ __forceinline__ u64 final_key(u64 key, float qi) {
+  const float s = key_score(key) * qi + 0.0f;
+  return ((u64)f32_to_ordered(s) << 32) | (key & 0xffffffffull);
+}
 
 // Visit every valid key of the CTA's segments with a warp-uniform trip count: f(key, active).
 template <typename F>
 __device__ __forceinline__ void for_each_key(const SelectParams& p, int q, int s0, int s1, bool staged, const u64* stage,
-                                             int total, F f) {
+                                             int total, bool xform, float qi, F f) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int SEL_THREADS = blockDim.x, SEL_WARPS = blockDim.x >> 5;
   if (staged) {
@@ -56,14 +72,15 @@ __device__ __forceinline__ void for_each_key(const SelectParams& p, int q, int s
       f(active ? stage[i] : 0ull, active);
     }
   } else {
-    for (int s = s0 + warp; s < s1; s += SEL_WARPS) {
+    const int s_end = s1 + ((p.carry && p.mode != kSelPartial) ? 1 : 0);    // pseudo segment S = the carry list
+    for (int s = s0 + warp; s < s_end; s += SEL_WARPS) {
       const size_t slot = (size_t)s * p.Bpad + q;
       const int c = p.counts[slot];
-      const u64* lp = p.lists + slot * (size_t)p.cap;
+      const u64* lp = (s == p.S && p.carry) ? p.carry + (size_t)q * p.carry_cap : p.lists + slot * (size_t)p.cap;
       for (int base = 0; base < c; base += 32) {
         const int i = base + lane;
         const bool active = i < c;
-        f(active ? lp[i] : 0ull, active);
+        f(active ? (xform ? final_key(lp[i], qi) : lp[i]) : 0ull, active);
       }
     }
   }
@@ -88,6 +105,11 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
 
   const int q = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  u32 epoch = 0;
+  if (p.use_comm) epoch = comm_send_begin(p.comm);      // the peers have consumed what this slot held two exchanges ago
+  // final-score keys (see final_key): everywhere except the per-phase threshold selects, which stay in filter space
+  const float qi = p.qinv ? p.qinv[q] : 1.0f;
+  const bool xform = p.mode != kSelThreshold && p.qinv != nullptr && !p.final_keys;
   int s0 = 0, s1 = p.S;
   if (p.mode == kSelPartial) { s0 = blockIdx.y * p.seg_per_cta; s1 = min(p.S, s0 + p.seg_per_cta); }
 
@@ -95,7 +117,8 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
   // of the flattened candidate array by binary search over the prefix: two dependent global loads in total
   __shared__ int seg_off[SEL_MAX_SEGS + 1];
   __shared__ int warp_tot[32];
-  const int nseg = s1 - s0;
+  const bool has_carry = p.carry != nullptr && p.mode != kSelPartial;
+  const int nseg = s1 - s0 + (has_carry ? 1 : 0);       // the carry list is the last (pseudo) segment, index S
   const bool flat = nseg <= SEL_MAX_SEGS;
   if (tid == 0) { s_total = 0; s_nout = 0; s_prefix = 0; }
   __syncthreads();
@@ -136,7 +159,9 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
     for (int i = tid; i < total; i += SEL_THREADS) {
       int lo = 0, hi = nseg;                       // last segment with seg_off <= i
       while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_off[mid] <= i) lo = mid; else hi = mid; }
-      stage[i] = p.lists[((size_t)(s0 + lo) * p.Bpad + q) * (size_t)p.cap + (i - seg_off[lo])];
+      const u64 key = (has_carry && lo == nseg - 1) ? p.carry[(size_t)q * p.carry_cap + (i - seg_off[lo])]
+                                                     : p.lists[((size_t)(s0 + lo) * p.Bpad + q) * (size_t)p.cap + (i - seg_off[lo])];
+      stage[i] = xform ? final_key(key, qi) : key;
     }
     __syncthreads();
   } else if (staged) {
@@ -149,7 +174,7 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
       if (lane == 0) base = atomicAdd(&s_nout, c);
       base = __shfl_sync(kFullMask, base, 0);
       const u64* lp = p.lists + slot * (size_t)p.cap;
-      for (int i = lane; i < c; i += 32) stage[base + i] = lp[i];
+      for (int i = lane; i < c; i += 32) stage[base + i] = xform ? final_key(lp[i], qi) : lp[i];
     }
     __syncthreads();
     if (tid == 0) s_nout = 0;
@@ -166,7 +191,7 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
       __syncthreads();
       const u64 prefix = s_prefix;
       const u64 hi_mask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
-      for_each_key(p, q, s0, s1, staged, stage, total, [&](u64 key, bool active) {
+      for_each_key(p, q, s0, s1, staged, stage, total, xform, qi, [&](u64 key, bool active) {
         hist_add(hist, active && (key & hi_mask) == prefix, (u32)(key >> shift) & 255u);
       });
       __syncthreads();
@@ -202,15 +227,34 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
 
   if (p.mode == kSelThreshold) {
     if (tid == 0) atomicMax(p.gthr + q, (u32)(kth >> 32));
-    // prune: keys below the (truncated) k-th key can never reach the final top-k, so drop them from the lists.
+    // prune: keys below the (truncated) k-th key can never reach the final top-k, so drop them.
     // This keeps every later select (and the final one) at ~k + one phase's survivors per query.
     u64* wl = const_cast<u64*>(p.lists);
     int* wc = const_cast<int*>(p.counts);
-    for (int s = s0 + warp; s < s1; s += SEL_WARPS) {
+    if (has_carry && staged && flat) {
+      // survivors (already in shared memory) -> the carry list, compacted; the unit lists restart empty
+      u64* cl = p.carry + (size_t)q * p.carry_cap;
+      for (int base = warp * 32; base < total; base += SEL_THREADS) {
+        const int i = base + lane;
+        const u64 key = i < total ? stage[i] : 0ull;
+        const bool keep = i < total && key >= kth;
+        const u32 m = __ballot_sync(kFullMask, keep);
+        int pos = 0;
+        if (lane == 0 && m) pos = atomicAdd(&s_nout, __popc(m));
+        pos = __shfl_sync(kFullMask, pos, 0);
+        if (keep) cl[pos + __popc(m & ((1u << lane) - 1u))] = key;
+      }
+      for (int sgi = tid; sgi < nseg - 1; sgi += SEL_THREADS) wc[(size_t)(s0 + sgi) * p.Bpad + q] = 0;
+      __syncthreads();
+      if (tid == 0) wc[(size_t)p.S * p.Bpad + q] = s_nout;
+      return;
+    }
+    const int s_end = s1 + (has_carry ? 1 : 0);
+    for (int s = s0 + warp; s < s_end; s += SEL_WARPS) {
       const size_t slot = (size_t)s * p.Bpad + q;
       const int c = wc[slot];
       if (c == 0) continue;
-      u64* lp = wl + slot * (size_t)p.cap;
+      u64* lp = (has_carry && s == p.S) ? p.carry + (size_t)q * p.carry_cap : wl + slot * (size_t)p.cap;
       int out = 0;
       for (int base = 0; base < c; base += 32) {
         const int i = base + lane;
@@ -230,7 +274,7 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
   if (p.mode == kSelPartial) {
     const size_t oslot = (size_t)blockIdx.y * p.Bpad + q;
     u64* ol = p.out_lists + oslot * (size_t)p.k;
-    for_each_key(p, q, s0, s1, staged, stage, total, [&](u64 key, bool active) {
+    for_each_key(p, q, s0, s1, staged, stage, total, xform, qi, [&](u64 key, bool active) {
       if (active && key >= kth) {
         const int pos = atomicAdd(&s_nout, 1);
         if (pos < p.k) ol[pos] = key;
@@ -242,7 +286,7 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
 
   for (int i = tid; i < p.kp2; i += SEL_THREADS) sk[i] = 0;
   __syncthreads();
-  for_each_key(p, q, s0, s1, staged, stage, total, [&](u64 key, bool active) {
+  for_each_key(p, q, s0, s1, staged, stage, total, xform, qi, [&](u64 key, bool active) {
     if (active && key >= kth) {
       const int pos = atomicAdd(&s_nout, 1);
       if (pos < p.kp2) sk[pos] = key;
@@ -250,40 +294,35 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
   });
   __syncthreads();
   block_bitonic_desc(sk, p.kp2);
-  const float qi = p.qinv ? p.qinv[q] : 1.0f;
+  const size_t n = (size_t)p.B * p.k;
   for (int i = tid; i < p.k; i += SEL_THREADS) {
     const u64 key = sk[i];
     const bool ok = (i < want) && key != 0;
-    float sc = ok ? key_score(key) * qi : -CUDART_INF_F;
+    float sc = ok ? key_score(key) : -CUDART_INF_F;          // keys already carry the final score
     long long id = ok ? (p.id_base + (long long)key_id(key)) : -1ll;
     if (!(sc >= p.min_score)) { sc = -CUDART_INF_F; id = -1ll; }
-    if (p.n_peers == 0) {
+    if (!p.use_comm) {
       p.out_scores[(size_t)q * p.k + i] = sc;
       p.out_ids[(size_t)q * p.k + i] = id;
     } else {
-      const size_t n = (size_t)p.B * p.k;
-      const size_t rec = 12 * n;
-      for (int g = 0; g < p.n_peers; ++g) {
-        char* base = reinterpret_cast<char*>(p.peer_base[g]) + (size_t)p.rank * rec;
+      for (int g = 0; g < p.comm.world; ++g) {
+        char* base = comm_slot(p.comm, g, epoch) + (size_t)p.comm.rank * p.rec_stride;
         reinterpret_cast<long long*>(base)[(size_t)q * p.k + i] = id;
         reinterpret_cast<float*>(base + 8 * n)[(size_t)q * p.k + i] = sc;
       }
     }
   }
+  if (p.use_comm) comm_send_end(p.comm, epoch, gridDim.x * gridDim.y);
 }
 
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 static int run_select(SelectParams& p, int grid_y, cudaStream_t st) {
-  const long long all = (long long)(p.mode == kSelPartial ? p.seg_per_cta : p.S) * p.cap;
+  const long long all = (long long)(p.mode == kSelPartial ? p.seg_per_cta : p.S) * p.cap + (p.carry && p.mode != kSelPartial ? p.carry_cap : 0);
   int limit = SEL_STAGE_MAX;
-  if (p.mode != kSelPartial) {   // pruned lists hold ~k + one phase's survivors
-    limit = 3 * p.k + 2048;
-    if (limit < SEL_STAGE_LISTS) limit = SEL_STAGE_LISTS;
-    if (limit > 24576) limit = 24576;
-  }
   const long long ctas = (long long)p.B * grid_y;
-  if (ctas <= 148) limit = 24576;      // a handful of queries: one CTA per SM can afford a 192 KB stage
+  if (p.mode != kSelPartial) limit = select_stage_limit(p.k, p.B);   // pruned lists hold ~k + one phase's survivors
+  else if (ctas <= 148) limit = 24576;      // a handful of queries: one CTA per SM can afford a 192 KB stage
   p.stage_cap = (int)(all < limit ? all : limit);
   const int threads = ctas >= 2048 ? 128 : (ctas >= 512 ? 256 : (ctas >= 128 ? 512 : 1024));
   const size_t smem = (size_t)p.stage_cap * 8 + (p.mode == kSelOutput ? (size_t)p.kp2 * 8 : 0);
@@ -295,39 +334,41 @@ static int run_select(SelectParams& p, int grid_y, cudaStream_t st) {
 }
 
 int launch_select_lists(const Index* ix, const SearchPlan& pl, void* ws, float* out_scores, int64_t* out_ids, cudaStream_t st,
-                        const PeerScatter* peers, float min_score) {
+                        const CommDev* comm, size_t rec_stride, float min_score) {
   SelectParams p;
   memset(&p, 0, sizeof(p));
   p.min_score = min_score;
-  if (peers) {
-    p.n_peers = peers->n; p.rank = peers->rank;
-    for (int g = 0; g < peers->n; ++g) p.peer_base[g] = peers->base[g];
-  }
+  if (comm) { p.comm = *comm; p.use_comm = 1; p.rec_stride = rec_stride; }
   p.lists = reinterpret_cast<const u64*>((char*)ws + pl.off_lists);
   p.counts = reinterpret_cast<const int*>((char*)ws + pl.off_counts);
   p.S = pl.num_segments; p.Bpad = pl.Bpad; p.cap = pl.cap;
   p.B = pl.B; p.k = pl.k; p.kp2 = next_pow2(pl.k);
   p.qinv = (ix->metric == B200R_COS) ? reinterpret_cast<const float*>((char*)ws + pl.off_qinv) : nullptr;
   p.gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
+  if (pl.carry_cap > 0) { p.carry = reinterpret_cast<u64*>((char*)ws + pl.off_carry); p.carry_cap = pl.carry_cap; }
   p.id_base = ix->id_base;
   p.out_scores = out_scores;
   p.out_ids = reinterpret_cast<long long*>(out_ids);
-  if (!out_scores && !peers) { p.mode = kSelThreshold; return run_select(p, 1, st); }
+  if (!out_scores && !comm) { p.mode = kSelThreshold; return run_select(p, 1, st); }
   if (pl.num_groups > 0) {
     // two levels: many short per-warp lists (scan path) are first reduced group-wise to k keys each
     SelectParams p1 = p;
+    p1.use_comm = 0; p1.carry = nullptr;
+    p.carry = nullptr;
     p1.mode = kSelPartial; p1.seg_per_cta = SEL_GROUP;
     p1.out_lists = reinterpret_cast<u64*>((char*)ws + pl.off_lists2);
     p1.out_counts = reinterpret_cast<int*>((char*)ws + pl.off_counts2);
     int rc = run_select(p1, pl.num_groups, st);
     if (rc) return rc;
     p.lists = p1.out_lists; p.counts = p1.out_counts; p.S = pl.num_groups; p.cap = pl.k;
+    p.final_keys = 1;
   }
   p.mode = kSelOutput;
   return run_select(p, 1, st);
 }
 
 int select_group_size() { return SEL_GROUP; }
+int select_max_flat_segments() { return SEL_MAX_SEGS; }
 
 // ------------------------------------------------------------------------------------------------
 // public merge: candidates [G, B, kin] (f32 score, i64 id) -> [B, k]

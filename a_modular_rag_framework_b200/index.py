@@ -83,8 +83,6 @@ class DenseIndex:
         return self._handle.value
 
     # -- search -----------------------------------------------------------------------------------
-    INT8_SLICE = 256
-
     def _workspace(self, B: int, k: int, path: int) -> torch.Tensor:
         need = int(self._lib.b200r_search_workspace_bytes(self._handle, B, k, path))
         if need == 0:
@@ -110,13 +108,6 @@ class DenseIndex:
             ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
         else:
             scores, ids = out
-        if self.X.dtype == torch.int8 and B > self.INT8_SLICE:
-            # the int8 paths keep one candidate list per (epilogue warp, query): slice big batches so the workspace stays
-            # at a few hundred MB (the corpus is streamed once per 16 queries either way)
-            for b0 in range(0, B, self.INT8_SLICE):
-                b1 = min(B, b0 + self.INT8_SLICE)
-                self.search(Q[b0:b1], k, path=path, out=(scores[b0:b1], ids[b0:b1]), min_score=min_score)
-            return scores, ids
         ws = self._workspace(B, k, p)
         with torch.cuda.device(self.device):
             if min_score is None:
@@ -127,21 +118,18 @@ class DenseIndex:
                                                          ids.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
         return scores, ids
 
-    def search_scatter(self, Q: torch.Tensor, k: int, peer_bases, rank: int, path: str = "auto",
-                       wait_event: Optional[torch.cuda.Event] = None) -> None:
-        """Search and let the final select kernel store this rank's packed (ids | scores)[B, k] record into slot
-        `rank` of every rank's gather buffer (`peer_bases`: peer-mapped device addresses).  Stream-ordered, no sync."""
+    def search_sharded_begin(self, comm, Q: torch.Tensor, k: int, path: str = "auto") -> None:
+        """Local search of this rank's rows whose final select kernel stores the packed (ids | scores)[B, k] record into
+        every rank's exchange window (comm.ShardComm).  Stream-ordered, no sync; pair with comm.finish()."""
         _require_cuda(Q, "Q")
         if Q.dim() != 2 or Q.shape[1] != self.D or Q.dtype != self.query_dtype:
             raise ValueError(f"Q must be [B, {self.D}] {self.query_dtype}")
         B = int(Q.shape[0])
         p = _PATHS[path]
         ws = self._workspace(B, k, p)
-        arr = (ctypes.c_uint64 * len(peer_bases))(*[int(x) for x in peer_bases])
         with torch.cuda.device(self.device):
-            N.check(self._lib.b200r_search_scatter(self._handle, Q.data_ptr(), B, k, p, arr, len(peer_bases), int(rank),
-                                                   wait_event.cuda_event if wait_event is not None else None,
-                                                   ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+            N.check(self._lib.b200r_search_sharded_begin(self._handle, comm.handle, Q.data_ptr(), B, k, p,
+                                                         ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
 
     def search_host(self, Q_host: torch.Tensor, k: int, path: str = "auto",
                     out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:

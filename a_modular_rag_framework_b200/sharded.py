@@ -38,13 +38,23 @@ def _cuda_merge_packed(packed: torch.Tensor, G: int, B: int, k: int) -> Tuple[to
 
 
 class PendingResult:
-    """Result of ShardedDenseIndex.search(..., overlap=True): the exchange + merge run on a side stream.
-    get() makes the caller's current stream wait for them and returns (scores, ids)."""
+    """Result of ShardedDenseIndex.search(..., overlap=True).  get() returns (scores, ids) on the caller's current stream;
+    the receiving half of the exchange is issued either by the NEXT search call (after its local search has been queued,
+    so no rank ever waits for a slower peer) or by get(), whichever comes first."""
 
-    def __init__(self, scores, ids, event):
-        self._scores, self._ids, self._event = scores, ids, event
+    def __init__(self, scores=None, ids=None, event=None, finish=None):
+        self._scores, self._ids, self._event, self._finish = scores, ids, event, finish
+
+    def resolve(self):
+        if self._finish is not None:
+            fin, self._finish = self._finish, None
+            self._scores, self._ids = fin()
+            # get() may be called under another stream (e.g. a copy stream): order it behind the merge kernel
+            self._event = torch.cuda.Event()
+            self._event.record(torch.cuda.current_stream(self._scores.device))
 
     def get(self):
+        self.resolve()
         if self._event is not None:
             torch.cuda.current_stream(self._scores.device).wait_event(self._event)
             self._event = None
@@ -52,23 +62,29 @@ class PendingResult:
 
 
 class ShardedDenseIndex:
-    """`local` searches this rank's rows and reports GLOBAL ids (DenseIndex(X_shard, id_base=lo))."""
+    """`local` searches this rank's rows and reports GLOBAL ids (DenseIndex(X_shard, id_base=lo)).
+
+    exchange="abi" (default on CUDA): the C-ABI exchange (comm.ShardComm): the final select kernel of the local search stores
+    this rank's packed record into every rank's window over NVLink and one merge kernel waits for the records -- no
+    NCCL, no collective kernel, no staging copy, no side stream.  torch.distributed is used once, to swap the 128-byte
+    window descriptors.  exchange="nccl": packed all_gather_into_tensor + b200r_merge_topk_packed (also what the gloo CPU
+    tests drive, with an injected engine and merge)."""
 
     def __init__(self, local, group: Optional[dist.ProcessGroup] = None,
                  merge_packed: Optional[Callable[[torch.Tensor, int, int, int], Tuple[torch.Tensor, torch.Tensor]]] = None,
-                 exchange: str = "nccl"):
-        """exchange="nccl": packed all_gather_into_tensor.  exchange="p2p": the final select kernel of the search
-        stores each rank's packed record straight into every rank's gather buffer over NVLink (symmetric memory,
-        b200r_search_scatter), followed by a symmetric-memory barrier -- no collective kernel, no staging copy."""
-        if exchange not in ("nccl", "p2p"):
-            raise ValueError("exchange must be 'nccl' or 'p2p'")
+                 exchange: str = "nccl", comm=None):
+        if exchange == "p2p":        # round-1 name of the fused exchange
+            exchange = "abi"
+        if exchange not in ("nccl", "abi"):
+            raise ValueError("exchange must be 'abi' or 'nccl'")
         self.exchange = exchange
-        self._p2p = {}           # (B, k) -> per-slot (buffer, handle, peer pointers)
-        self._barrier_events = {}
+        self.comm = comm
+        self._comm_cap = (0, 0)
+        self._outstanding: Optional[PendingResult] = None
         self.local = local
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else (comm.world if comm is not None else 1)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else (comm.rank if comm is not None else 0)
         self._merge = merge_packed or _cuda_merge_packed
         self._bufs = {}          # (B, k, slot) -> (pack, gather)
         self._slot = 0
@@ -85,18 +101,40 @@ class ShardedDenseIndex:
                                torch.empty(rec * self.world, dtype=torch.uint8, device=device))
         return self._bufs[key]
 
+    def ensure_comm(self, B: int, k: int):
+        """(Re)create the exchange window for batches up to (B, k).  Collective: every rank calls it with the same sizes
+        (search() does, since every rank issues the same searches)."""
+        from .comm import ShardComm
+        if self.comm is not None and self._comm_cap == (0, 0):
+            return self.comm                      # supplied by the caller: its capacity is the caller's business
+        mb, mk = self._comm_cap
+        if self.comm is None or B > mb or k > mk:
+            if self._outstanding is not None:
+                self._outstanding.resolve()
+                self._outstanding = None
+            if self.comm is not None:
+                torch.cuda.synchronize()
+                if dist.is_initialized():
+                    dist.barrier(group=self.group)   # nobody is still storing into a window that is about to go away
+                self.comm.close()
+            mb, mk = max(mb, B), max(mk, k)
+            dev = self.local.device
+            self.comm = ShardComm.from_process_group(dev.index or 0, mb, mk, 0, group=self.group)
+            self._comm_cap = (mb, mk)
+        return self.comm
+
     def search(self, Q: torch.Tensor, k: int, path: str = "auto", overlap: bool = False):
         """Every rank passes the SAME Q [B, D]; every rank gets the same global (scores, ids) [B, k].
 
-        overlap=True (throughput mode, CUDA only): the all-gather and the merge of this batch are queued on a side
-        stream so the next batch's local search starts right away; returns a PendingResult."""
+        overlap=True (throughput mode): returns a PendingResult; the receiving half of this batch's exchange is issued
+        after the NEXT batch's local search has been queued."""
         if self.world == 1:
             res = self.local.search(Q, k, path=path)
             return PendingResult(res[0], res[1], None) if overlap else res
         B = int(Q.shape[0])
         n = B * k
-        if self.exchange == "p2p":
-            return self._search_p2p(Q, k, path, overlap)
+        if self.exchange == "abi":
+            return self._search_abi(Q, k, path, overlap)
         if not overlap:
             pack, gather = self._buffers(B, k, Q.device)
             ids_view = pack[: 8 * n].view(torch.int64).view(B, k)
@@ -130,53 +168,19 @@ class ShardedDenseIndex:
         self._slot_events[self._slot] = done
         return PendingResult(scores, ids, done)
 
-
-    # ---- fused exchange over peer memory ---------------------------------------------------------------
-    def _p2p_slots(self, B: int, k: int, device):
-        key = (B, k)
-        if key not in self._p2p:
-            import torch.distributed._symmetric_memory as symm_mem
-            n = B * k
-            if n % 2:
-                raise ValueError("B*k must be even for the packed exchange")
-            slots = []
-            for _ in range(2):
-                buf = symm_mem.empty(12 * n * self.world, dtype=torch.uint8, device=device)
-                hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
-                slots.append((buf, hdl, [int(p) for p in hdl.buffer_ptrs]))
-            self._p2p[key] = slots
-        return self._p2p[key]
-
-    def _search_p2p(self, Q: torch.Tensor, k: int, path: str, overlap: bool):
+    # ---- C-ABI exchange over peer memory ------------------------------------------------------------------
+    def _search_abi(self, Q: torch.Tensor, k: int, path: str, overlap: bool):
         B = int(Q.shape[0])
-        slots = self._p2p_slots(B, k, Q.device)
-        self._slot ^= 1
-        buf, hdl, ptrs = slots[self._slot]
-        cur = torch.cuda.current_stream(Q.device)
-        # the peers' copies of this slot were last read two batches ago; every rank is past that once the barrier of
-        # the PREVIOUS batch has completed here (its signal is stream-ordered after the peer's merge)
-        prev_barrier = self._barrier_events.get("last")
-        self.local.search_scatter(Q, k, ptrs, self.rank, path=path, wait_event=prev_barrier)
+        comm = self.ensure_comm(B, k)
+        self.local.search_sharded_begin(comm, Q, k, path=path)
+        prev, self._outstanding = self._outstanding, None
+        if prev is not None:
+            prev.resolve()                # finish(i-1) is queued behind begin(i): its peers arrived a batch ago
         if not overlap:
-            hdl.barrier(channel=0)
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            self._barrier_events["last"] = ev
-            return self._merge(buf, self.world, B, k)
-        if self._comm_stream is None:
-            self._comm_stream = torch.cuda.Stream(device=Q.device)
-        ready = torch.cuda.Event()
-        ready.record(cur)
-        with torch.cuda.stream(self._comm_stream):
-            self._comm_stream.wait_event(ready)
-            hdl.barrier(channel=0)
-            ev = torch.cuda.Event()
-            ev.record(self._comm_stream)
-            scores, ids = self._merge(buf, self.world, B, k)
-            done = torch.cuda.Event()
-            done.record(self._comm_stream)
-        self._barrier_events["last"] = ev
-        return PendingResult(scores, ids, done)
+            return comm.finish(B, k)
+        cur = PendingResult(finish=lambda: comm.finish(B, k))
+        self._outstanding = cur
+        return cur
 
 
 INT64_MIN, INT64_MAX = -(1 << 63), (1 << 63) - 1

@@ -51,8 +51,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--verify-queries", type=int, default=8,
                     help="queries of the last timed batch checked against the CPU oracle after the timed regions (0 = skip)")
-    ap.add_argument("--exchange", default=os.environ.get("B200R_EXCHANGE", "p2p"), choices=["p2p", "nccl"],
-                    help="N>1: fused select->peer-memory scatter (default) or packed NCCL all-gather")
+    ap.add_argument("--exchange", default=os.environ.get("B200R_EXCHANGE", "abi"), choices=["abi", "nccl"],
+                    help="N>1: the library's own exchange over peer memory (b200r_comm_*, default) or a packed NCCL all-gather")
     return ap.parse_args()
 
 
@@ -296,17 +296,12 @@ def main():
 
     local = DenseIndex(X[:max(n_local, 1)] if n_local else X, metric="cos", id_base=lo)
     index = ShardedDenseIndex(local, exchange=a.exchange) if world > 1 else local
-    if world > 1 and a.exchange == "p2p":
-        # symmetric-memory rendezvous needs CUDA IPC between the ranks; agree on a fallback if any rank cannot do it
-        ok = 1
+    if world > 1 and a.exchange == "abi":
+        # the exchange windows are mapped across the ranks with CUDA IPC; every rank learns the outcome of the bring-up
         try:
-            index._p2p_slots(a.batch, a.k, dev)
+            index.ensure_comm(a.batch, a.k)
         except Exception as e:  # noqa: BLE001
-            ok = 0
-            sys.stderr.write(f"[bench] rank {rank}: symmetric-memory exchange unavailable ({e!r}); using the NCCL all-gather\n")
-        flag = torch.tensor([ok], device=dev, dtype=torch.int32)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
+            sys.stderr.write(f"[bench] rank {rank}: C-ABI exchange unavailable ({e!r}); using the NCCL all-gather\n")
             a.exchange = "nccl"
             index = ShardedDenseIndex(local, exchange="nccl")
 
@@ -498,8 +493,8 @@ def main():
             "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "batch": a.batch, "k": a.k,
                        "path": used_path, "sharding": f"rows/{world}",
                        "exchange": "none" if world == 1 else (
-                           "final select kernel stores each rank's packed top-k into every rank's symmetric gather buffer over NVLink, symmetric-memory barrier + device merge on a side stream, overlapped with the next batch's search"
-                           if a.exchange == "p2p" else
+                           "libb200r exchange (b200r_comm_*): the final select kernel stores each rank's packed top-k into every rank's window over NVLink (CUDA IPC mapped), device-side epoch flags, one merge kernel queued behind the next batch's search; no NCCL in the data path"
+                           if a.exchange == "abi" else
                            "packed NCCL all-gather + device merge on a side stream, overlapped with the next batch's search"),
                        "l2": "corpus shard (>= 1.9 GB) is far larger than the 126 MB L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),

@@ -34,7 +34,8 @@ extern "C" {
 #define B200R_ECUDA -2    /* CUDA runtime/driver error */
 #define B200R_ENOMEM -3   /* workspace too small / allocation failed */
 #define B200R_EOVERFLOW -4 /* a bounded on-chip structure overflowed (graph frontier) */
-#define B200R_ESTATE -5   /* bad handle */
+#define B200R_ESTATE -5   /* bad handle / call out of order */
+#define B200R_ETIMEOUT -6 /* a device-side exchange wait expired (a rank never arrived) */
 
 /* element types of the corpus matrix (queries use the same type, except I8 -> F32 queries) */
 #define B200R_BF16 0
@@ -53,6 +54,7 @@ extern "C" {
 
 #define B200R_MAX_K 2048
 #define B200R_MAX_PEERS 8
+#define B200R_COMM_BLOB_BYTES 128
 
 int b200r_version(void);
 /* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
@@ -95,17 +97,49 @@ int b200r_search_min_score(uint64_t index, const void* Q, int32_t B, int32_t k, 
                            float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
                            void* stream);
 
-/* Fused exchange for row-sharded corpora: same search, but the final select kernel writes this rank's packed
- * record [ids i64 [B,k] | scores f32 [B,k]] directly into slot `rank` of every rank's gather buffer
- * (peer_bases_host[g] = device address of rank g's buffer, peer-mapped in this process, e.g. from a CUDA IPC /
- * symmetric-memory rendezvous), i.e. the all-gather is done by the kernel's own stores over NVLink.  The caller
- * then synchronises the ranks (any cross-GPU barrier ordered after this call) and runs b200r_merge_topk_packed
- * on its own gather buffer.  n_peers <= B200R_MAX_PEERS.  wait_event (cudaEvent_t as void*, may be NULL): the
- * stream waits for it right before the kernel that writes to the peers (every rank must have consumed the
- * buffers' previous contents by then); the tile kernels before it are not delayed. */
-int b200r_search_scatter(uint64_t index, const void* Q, int32_t B, int32_t k, int32_t path,
-                         const uint64_t* peer_bases_host, int32_t n_peers, int32_t rank, void* wait_event,
-                         void* workspace, size_t workspace_bytes, void* stream);
+/* ---- shard exchange (row-sharded corpus) ------------------------------------------------------
+ * The reference keeps one index in one process (BM25LiteIndex / DenseReranker, retrieval_backend.py:252-281); at
+ * 8 GPUs the corpus is row-sharded and the per-shard top-k lists must meet.  The exchange lives HERE, under the C
+ * ABI, and uses neither NCCL nor torch.distributed: every rank owns one window of device memory that all ranks map
+ * (CUDA IPC between processes, peer access inside one process) and the search kernels store into the peers' windows
+ * over NVLink themselves, ordered by device-side epoch flags (csrc/comm.cuh).
+ *
+ * Bring-up, one process per GPU:   b200r_comm_create on every rank -> b200r_comm_export (a 128-byte descriptor) ->
+ *   the host swaps the descriptors through ANY channel it has (file, socket, MPI, torch.distributed object gather) ->
+ *   b200r_comm_connect(all descriptors, rank order).
+ * Bring-up, one process, G GPUs:   b200r_comm_init_all(devices, G, ...) does all of it.
+ * max_B / max_k / max_graph_k bound the (B, k) of later exchanges (they size the window: ~24*max_B*max_k*world bytes
+ * for the dense channel, ~56*max_B*max_graph_k*world for the graph stage's; max_graph_k = 0 leaves those out).
+ * Every rank must issue the same sequence of exchange calls with the same (B, k).  Waits on the device are bounded
+ * (20 s): b200r_comm_status returns B200R_ETIMEOUT afterwards instead of the GPU hanging. */
+int b200r_comm_create(int device, int32_t rank, int32_t world, int32_t max_B, int32_t max_k, int32_t max_graph_k,
+                      uint64_t* out_comm);
+int b200r_comm_export(uint64_t comm, void* blob_host /* B200R_COMM_BLOB_BYTES */);
+int b200r_comm_connect(uint64_t comm, const void* blobs_host /* world x B200R_COMM_BLOB_BYTES, rank order */);
+int b200r_comm_init_all(const int32_t* devices, int32_t G, int32_t max_B, int32_t max_k, int32_t max_graph_k,
+                        uint64_t* out_comms /* [G] */);
+int b200r_comm_destroy(uint64_t comm);
+int b200r_comm_status(uint64_t comm, void* stream);   /* synchronises `stream`; B200R_OK or B200R_ETIMEOUT */
+int b200r_comm_info(uint64_t comm, int32_t* rank, int32_t* world, int32_t* device, size_t* window_bytes);
+
+/* Row-sharded exact top-k: `index` holds this rank's rows (id_base = first global row), every rank passes the SAME
+ * Q[B, D] and gets the same global result -- DenseReranker.score + sort/slice (retrieval_backend.py:215-247, 371-372)
+ * over the union of the shards.  _begin = local search whose final select kernel stores this rank's packed record
+ * [ids i64 [B,k] | scores f32 [B,k]] into every rank's window (the all-gather IS those stores); _finish = one kernel that
+ * waits for all ranks' records and merges the G sorted lists by (score desc, global id asc).  Splitting the two lets a
+ * throughput loop issue begin(i+1) before finish(i), so no rank ever waits for a slower peer.  Stream-ordered, no host
+ * synchronisation; safe to capture in a CUDA graph (epochs live on the device). */
+int b200r_search_sharded_begin(uint64_t index, uint64_t comm, const void* Q, int32_t B, int32_t k, int32_t path,
+                               void* workspace, size_t workspace_bytes, void* stream);
+int b200r_search_sharded_finish(uint64_t comm, int32_t B, int32_t k, float* out_scores, int64_t* out_ids, void* stream);
+int b200r_search_sharded(uint64_t index, uint64_t comm, const void* Q, int32_t B, int32_t k, int32_t path,
+                         float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream);
+/* One process driving G GPUs (comms from b200r_comm_init_all, indexes[g] on comms[g]'s device): HOST queries in, HOST
+ * results out -- H2D to every GPU, sharded search, exchange, merge on GPU 0, D2H, all streams synchronised.  This is the
+ * call behind B200RetrievalBackend(devices=[...]).  streams may be NULL (default streams). */
+int b200r_search_sharded_host_all(const uint64_t* indexes, const uint64_t* comms, int32_t G, const void* Q_host, int32_t B,
+                                  int32_t k, int32_t path, float* out_scores_host, int64_t* out_ids_host,
+                                  void* const* streams);
 
 /* ---- merge of per-shard top-k lists ----------------------------------------------------------
  * The same stable-sort rule applied to the union of G lists (one per GPU after the NCCL all-gather):

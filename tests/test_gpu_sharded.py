@@ -70,16 +70,16 @@ def _nccl_worker(rank, world, port, ret):
         for pr in pend:
             s2, i2 = pr.get()
             assert torch.equal(i2, i) and torch.equal(s2, s)
-        # fused exchange: the select kernel writes into the peers' symmetric buffers, then a symmetric-memory barrier
-        if os.environ.get("B200R_TEST_P2P", "1") == "1":
-            shp = ShardedDenseIndex(sh.local, exchange="p2p")
-            for _ in range(3):
-                s3, i3 = shp.search(Qb, k)
-                assert torch.equal(i3, i) and torch.equal(s3, s)
-            pend = [shp.search(Qb, k, overlap=True) for _ in range(5)]
-            for pr in pend:
-                s3, i3 = pr.get()
-                assert torch.equal(i3, i) and torch.equal(s3, s)
+        # C-ABI exchange (peer stores + device-side flags, csrc/comm.cu); descriptors swapped through torch.distributed
+        shp = ShardedDenseIndex(sh.local, exchange="abi")
+        for _ in range(3):
+            s3, i3 = shp.search(Qb, k)
+            assert torch.equal(i3, i) and torch.equal(s3, s)
+        pend = [shp.search(Qb, k, overlap=True) for _ in range(5)]
+        for pr in pend:
+            s3, i3 = pr.get()
+            assert torch.equal(i3, i) and torch.equal(s3, s)
+        shp.comm.check()
         # graph stage over the same row shards: CSR replicated, owner computes, min/max all-reduced
         from a_modular_rag_framework_b200 import PassageGraph
         from a_modular_rag_framework_b200.sharded import ShardedGraphStage
