@@ -26,7 +26,7 @@ EXPORTS = [
     "b200r_comm_create", "b200r_comm_export", "b200r_comm_connect", "b200r_comm_init_all", "b200r_comm_destroy", "b200r_comm_status", "b200r_comm_info",
     "b200r_search_sharded_begin", "b200r_search_sharded_finish", "b200r_search_sharded", "b200r_search_sharded_host_all",
     "b200r_merge_topk", "b200r_merge_topk_packed", "b200r_profile_enable", "b200r_profile_read",
-    "b200r_graph_create", "b200r_graph_destroy",
+    "b200r_graph_create", "b200r_graph_create_mapped", "b200r_graph_destroy",
     "b200r_merge_topk_src", "b200r_expand_max_candidates", "b200r_expand_rescore", "b200r_expand_workspace_bytes", "b200r_expand_rescore_sharded",
 ]
 
@@ -92,6 +92,7 @@ def load() -> ctypes.CDLL:
     lib.b200r_profile_enable.argtypes = [c_int]
     lib.b200r_profile_read.argtypes = [POINTER(ctypes.c_double), POINTER(c_int64)]
     lib.b200r_graph_create.argtypes = [c_int, c_void_p, c_void_p, c_int64, c_int64, POINTER(c_uint64)]
+    lib.b200r_graph_create_mapped.argtypes = [c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p, POINTER(c_uint64)]
     lib.b200r_graph_destroy.argtypes = [c_uint64]
     lib.b200r_expand_max_candidates.restype = c_int32
     lib.b200r_expand_rescore.argtypes = [c_uint64, c_uint64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_int32,

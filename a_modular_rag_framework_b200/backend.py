@@ -9,23 +9,34 @@ Boundary mirrored (reference paths):
   * retrieve(req) -> RetrievalOut                                             retrieval_backend.py:387-390
   * spans Backend/Expand|TextSearch|GraphExpand|DenseRerank                   retrieval_backend.py:308-332
   * Hit.meta keys read downstream (text, doc, sent_id, score_*_norm)         reasoning/strategies.py:108-117, 233-240
+  * per-graph_id graphs: graph_root/<graph_id>/graph.json, q_match seeds      retrieval_backend.py:151-166, graph_utils.py:13-55
 
 What changes underneath: instead of embedding <= bm25_pool_k BM25 candidates per query through the
 provider and scoring them with a pure-Python cosine, the query embedding is searched EXACTLY against the
-whole resident passage-embedding corpus on the GPU (DenseIndex), the top `seed_k` passages seed the CSR
-neighbour expansion, and candidates are re-scored and fused on the device (expand_rescore).  The optional
+whole resident passage-embedding corpus on the GPU(s), the graph named by the request's `graph_id` (loaded
+once, cached, never re-parsed per query) is expanded from its `q_match` seeds -- or from the dense top
+`seed_k` passages when it has none -- and candidates are re-scored and fused on the device.  The optional
 text channel stays on the host and is fused with the reference's formula.
 
+One code path serves one request (`run` / `retrieve`) and many (`retrieve_many`, `run_batch`): queries are
+embedded, searched, expanded and fused as arrays; Python objects are only built for the <= top_k winners.
+
 The compute engine is injectable (tests drive the host logic with an oracle engine); the default engine is
-the CUDA library and raises if it is unavailable -- there is no CPU fallback.
+the CUDA library -- one GPU, several GPUs driven by this process (`devices=[0, 1, ...]`, corpus row-sharded,
+exchange inside libb200r) or one rank of a torchrun job -- and raises if it is unavailable: no CPU fallback.
 """
 from __future__ import annotations
 
+import collections
 import contextlib
+import json
 import logging
 import os
+import re
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
 
 from . import store
 from .dto import Hit, RetrievalOut
@@ -62,49 +73,143 @@ def _span(node: str, sink: Any, trace_id: str):
         raise
 
 
-class CudaEngine:
-    """Default engine: the corpus and the graph live on one GPU; every call is a libb200r kernel."""
+GRAPH_KEYS = ("score", "id", "hop", "score_graph_norm", "score_dense_norm", "cos", "ncand", "status")
 
-    def __init__(self, emb_path: str, graph_path: str, device: str, metric: str):
-        import numpy as np
+
+class CudaEngine:
+    """Default engine: the corpus (row-sharded when several devices are given) and the graphs live in HBM; every call
+    is a libb200r kernel sequence.  Arrays in, arrays out (numpy on the host side of the boundary)."""
+
+    def __init__(self, emb_path: str, graph_path: str, device: str = "cuda:0", metric: str = "cos",
+                 devices: Optional[Sequence[int]] = None, max_batch: int = 4096, max_k: int = 256):
         import torch
         from .index import DenseIndex, PassageGraph
+        from .sharded import shard_rows
 
         if not torch.cuda.is_available():
             raise RuntimeError("B200RetrievalBackend needs a CUDA device: there is no CPU fallback")
         self.torch = torch
-        self.device = torch.device(device)
+        self.devs = [torch.device("cuda", int(d)) for d in devices] if devices else [torch.device(device)]
+        if len(self.devs) > torch.cuda.device_count():
+            raise RuntimeError(f"devices={list(devices)} but only {torch.cuda.device_count()} CUDA devices are visible")
+        self.device = self.devs[0]
         X, meta, scales = store.load_embeddings(emb_path)
-        tdtype = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32, "i8": torch.int8}[meta["dtype"]]
-        host = torch.from_numpy(np.array(X, copy=True))   # the store is a read-only memmap
-        if meta["dtype"] == "bf16":
-            host = host.view(torch.bfloat16)
-        self.X = host.to(self.device)
-        self.scales = torch.from_numpy(scales).to(self.device) if scales is not None else None
-        self.index = DenseIndex(self.X, metric=metric or meta.get("metric", "cos"), row_scale=self.scales)
-        self.dtype = tdtype
-        self.N, self.D = self.index.N, self.index.D
-        self.graph = None
-        if graph_path and os.path.exists(graph_path):
-            row_ptr, col_idx = store.load_csr(graph_path)
-            self.graph = PassageGraph(torch.from_numpy(row_ptr).to(self.device), torch.from_numpy(col_idx).to(self.device))
+        self.tdtype = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32, "i8": torch.int8}[meta["dtype"]]
+        self.N, self.D = int(meta["N"]), int(meta["D"])
+        G = len(self.devs)
+        self.shards, self._keep = [], []
+        for g, dev in enumerate(self.devs):
+            lo, hi = shard_rows(self.N, G, g)
+            host = torch.from_numpy(np.array(X[lo:hi], copy=True))      # the store is a read-only memmap
+            if meta["dtype"] == "bf16":
+                host = host.view(torch.bfloat16)
+            if hi == lo:                                                    # an empty tail shard still needs a valid pointer
+                host = torch.zeros((1, self.D), dtype=self.tdtype)
+            Xd = host.to(dev)
+            sc = torch.from_numpy(np.array(scales[lo:hi], copy=True)).to(dev) if scales is not None else None
+            self._keep.append((Xd, sc))
+            self.shards.append(DenseIndex(Xd, metric=metric or meta.get("metric", "cos"), id_base=lo, row_scale=sc))
+        self.query_dtype = self.shards[0].query_dtype
+        self.max_batch, self.max_k = int(max_batch), int(max_k)
+        self.comms = None
+        if G > 1:
+            from .comm import ShardComm
+            self.comms = ShardComm.init_all([d.index for d in self.devs], self.max_batch, self.max_k, self.max_k)
+        self._graph_cls = PassageGraph
+        self.corpus_graphs = None       # one replica per device of the corpus-level CSR (graph_path)
+        if graph_path:
+            path = store.csr_path(graph_path)
+            if not os.path.exists(path):
+                raise FileNotFoundError(f"graph_path {graph_path!r} does not exist (store.save_csr writes '<name>.npz')")
+            row_ptr, col_idx = store.load_csr(path)
+            self.corpus_graphs = self._upload_graph(row_ptr, col_idx, None)
 
-    def _q(self, qvecs: Sequence[Sequence[float]]):
-        q = self.torch.tensor(qvecs, dtype=self.torch.float32)
-        return q.to(self.index.query_dtype).to(self.device).contiguous()
+    # -- helpers ------------------------------------------------------------------------------------------
+    def _upload_graph(self, row_ptr, col_idx, node_rows):
+        t = self.torch
+        out = []
+        for dev in self.devs:
+            nr = t.from_numpy(np.ascontiguousarray(node_rows, dtype=np.int64)).to(dev) if node_rows is not None else None
+            out.append(self._graph_cls(t.from_numpy(np.ascontiguousarray(row_ptr, dtype=np.int64)).to(dev),
+                                       t.from_numpy(np.ascontiguousarray(col_idx, dtype=np.int32)).to(dev), nr))
+        return out
 
-    def dense_search(self, qvecs, k: int) -> Tuple[List[List[float]], List[List[int]]]:
-        s, i = self.index.search(self._q(qvecs), k)
-        return s.cpu().tolist(), i.cpu().tolist()
+    def _q_host(self, Q: np.ndarray):
+        q = self.torch.from_numpy(np.ascontiguousarray(Q, dtype=np.float32))
+        return q.to(self.query_dtype).contiguous()
 
     def has_graph(self) -> bool:
-        return self.graph is not None
+        return self.corpus_graphs is not None
 
-    def expand_rescore(self, qvecs, seeds: List[List[int]], window: int, alpha_dense: float, alpha_graph: float, k: int) -> Dict[str, list]:
-        from .index import expand_rescore
-        seeds_t = self.torch.tensor(seeds, dtype=self.torch.int64, device=self.device)
-        out = expand_rescore(self.index, self.graph, self._q(qvecs), seeds_t, window, alpha_dense, alpha_graph, k)
-        return {key: v.cpu().tolist() for key, v in out.items()}
+    # -- dense search ---------------------------------------------------------------------------------------
+    def dense_search(self, Q: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Q f32 [B, D] -> (scores f32 [B, k], ids i64 [B, k]); batches beyond max_batch run in slices."""
+        import ctypes
+        from . import _native as N
+        B = int(Q.shape[0])
+        scores = np.empty((B, k), dtype=np.float32)
+        ids = np.empty((B, k), dtype=np.int64)
+        if len(self.devs) > 1 and k > self.max_k:
+            raise ValueError(f"k={k} exceeds the exchange window (max_k={self.max_k}); construct the engine with a larger max_k")
+        t = self.torch
+        for b0 in range(0, B, self.max_batch):
+            b1 = min(B, b0 + self.max_batch)
+            qh = self._q_host(Q[b0:b1])
+            hs, hi = t.from_numpy(scores[b0:b1]), t.from_numpy(ids[b0:b1])
+            if len(self.devs) == 1:
+                self.shards[0].search_host(qh, k, out=(hs, hi))
+            else:
+                G = len(self.devs)
+                ih = (ctypes.c_uint64 * G)(*[s.handle for s in self.shards])
+                ch = (ctypes.c_uint64 * G)(*[c.handle for c in self.comms])
+                N.check(N.load().b200r_search_sharded_host_all(ih, ch, G, qh.data_ptr(), b1 - b0, k, N.PATH_AUTO,
+                                                               hs.data_ptr(), hi.data_ptr(), None))
+        return scores, ids
+
+    # -- graph stage ------------------------------------------------------------------------------------------
+    def expand_rescore(self, Q: np.ndarray, seeds: np.ndarray, window: int, alpha_dense: float, alpha_graph: float, k: int,
+                       graph: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+        """graph = None: the corpus-level CSR (node id == row); else (row_ptr, col_idx, node_rows) of a mapped graph
+        (local node ids, e.g. the block-diagonal union of the batch's per-graph_id graphs; seeds are local ids)."""
+        from .index import expand_rescore, expand_rescore_exchange_all
+        t = self.torch
+        graphs = self.corpus_graphs if graph is None else self._upload_graph(*graph)
+        if graphs is None:
+            raise RuntimeError("no graph loaded")
+        out: Dict[str, List[np.ndarray]] = {key: [] for key in GRAPH_KEYS}
+        B = int(Q.shape[0])
+        for b0 in range(0, B, self.max_batch):
+            b1 = min(B, b0 + self.max_batch)
+            qh = self._q_host(Q[b0:b1])
+            sh = t.from_numpy(np.ascontiguousarray(seeds[b0:b1], dtype=np.int64))
+            if len(self.devs) == 1:
+                res = expand_rescore(self.shards[0], graphs[0], qh.to(self.device), sh.to(self.device), window,
+                                     alpha_dense, alpha_graph, k, check_status=False)
+            else:
+                res = expand_rescore_exchange_all(self.shards, graphs, self.comms, self.N, qh, sh, window, alpha_dense, alpha_graph, k)
+            for key in GRAPH_KEYS:
+                out[key].append(res[key].cpu().numpy())
+        return {key: np.concatenate(v) for key, v in out.items()}
+
+
+class LocalGraph:
+    """One graph_id's graph.json reduced to what the hot path needs (build_index, graph_utils.py:25-55): local CSR of the
+    undirected next_in_doc adjacency, node -> corpus row, q_match seeds, and the sentence texts of the lexical seed fallback."""
+
+    __slots__ = ("row_ptr", "col_idx", "node_rows", "qmatch", "tokens", "row_to_node")
+
+    def __init__(self, row_ptr, col_idx, node_rows, qmatch, tokens):
+        self.row_ptr, self.col_idx, self.node_rows, self.qmatch, self.tokens = row_ptr, col_idx, node_rows, qmatch, tokens
+        self.row_to_node = {int(r): i for i, r in enumerate(node_rows)}
+
+    @property
+    def V(self) -> int:
+        return len(self.node_rows)
+
+
+def _tokenize(text: str) -> List[str]:
+    """graph_utils.py:9-10."""
+    return [t for t in re.split(r"[^a-zA-Z0-9]+", (text or "").lower()) if t]
 
 
 @dataclass
@@ -129,10 +234,13 @@ class B200RetrievalBackend:
 
     # --- new: where the resident corpus / graph come from and how they are searched ---
     emb_path: str = "data/hotpotqa/embeddings"      # store.save_embeddings directory, rows aligned with index_path
-    graph_path: str = ""                            # store.save_csr file of the corpus-level next_in_doc graph
-    seed_k: int = 20                                # dense top-S passages that seed the graph expansion
+    graph_path: str = ""                            # optional corpus-level next_in_doc CSR (store.save_csr), used for a
+                                                    # graph_id that has no graph_root/<graph_id>/graph.json
+    seed_k: int = 20                                # dense top-S passages that seed the expansion when a graph has no q_match
     device: str = "cuda:0"
+    devices: Optional[List[int]] = None             # e.g. [0,...,7]: this process drives all of them, corpus row-sharded
     metric: str = "cos"
+    graph_cache_size: int = 4096                    # per-graph_id graphs kept parsed (LRU)
     text_searcher: Any = None                       # optional object with .search(queries=, top_k=) -> raw hits (host BM25)
     expander: Any = None                            # optional object with .expand(query=, trace_id=) -> List[str]
     engine: Any = None                              # injectable compute engine (tests); default CudaEngine
@@ -143,12 +251,14 @@ class B200RetrievalBackend:
         if not self.docs:
             self.docs = store.load_docs(self.index_path)
         if self.engine is None:
-            self.engine = CudaEngine(self.emb_path, self.graph_path, self.device, self.metric)
+            self.engine = CudaEngine(self.emb_path, self.graph_path, self.device, self.metric, devices=self.devices)
         n = getattr(self.engine, "N", None)
         if self.docs and n is not None and n != len(self.docs):
             raise ValueError(f"embedding rows ({n}) and docs.jsonl lines ({len(self.docs)}) disagree")
-        logger.info("[B200RetrievalBackend] init: rows=%s seed_k=%d alpha_text=%s alpha_graph=%s alpha_dense=%s graph_window=%d",
-                    n, self.seed_k, self.alpha_text, self.alpha_graph, self.alpha_dense, self.graph_window)
+        self._graphs: "collections.OrderedDict[str, Optional[LocalGraph]]" = collections.OrderedDict()
+        self._node_rows: Optional[Dict[str, int]] = None
+        logger.info("[B200RetrievalBackend] init: rows=%s seed_k=%d alpha_text=%s alpha_graph=%s alpha_dense=%s graph_window=%d engine=%s",
+                    n, self.seed_k, self.alpha_text, self.alpha_graph, self.alpha_dense, self.graph_window, type(self.engine).__name__)
 
     # ------------------------------------------------------------------------------------------ helpers
     def _resolve_embed_model(self) -> str:
@@ -169,18 +279,25 @@ class B200RetrievalBackend:
             pass
         return "text-embedding-3-large"
 
-    def _embed_query(self, query: str, trace_id: str) -> Optional[List[float]]:
-        """router.embed exactly as DenseReranker.score calls it (retrieval_backend.py:227-231): dict or list result."""
-        cache = getattr(self, "_embed_cache", None)
-        if cache is not None and query in cache:
-            return cache[query]
-        try:
-            q_emb = self.router.embed(model_hint=self._resolve_embed_model(), texts=[query], require={"trace_id": trace_id})
-            qv = (q_emb.get("vectors") if isinstance(q_emb, dict) else q_emb)[0]
-            return [float(x) for x in qv]
-        except Exception as e:  # noqa: BLE001
-            logger.error("[B200RetrievalBackend] query embed error: %s", e, exc_info=True)
-            return None
+    def _embed_queries(self, queries: Sequence[str], trace_ids: Sequence[str]) -> List[Optional[List[float]]]:
+        """router.embed as DenseReranker.score calls it (retrieval_backend.py:227-231: dict or list result, failures
+        degrade to "no dense channel"); a batch is embedded in chunks of max(8, embed_batch) texts like :234-243."""
+        model = self._resolve_embed_model()
+        out: List[Optional[List[float]]] = [None] * len(queries)
+        if len(queries) == 1:
+            chunks = [(0, 1)]
+        else:
+            step = max(8, int(self.embed_batch))
+            chunks = [(i, min(len(queries), i + step)) for i in range(0, len(queries), step)]
+        for a, b in chunks:
+            try:
+                emb = self.router.embed(model_hint=model, texts=list(queries[a:b]), require={"trace_id": trace_ids[a]})
+                vecs = emb.get("vectors") if isinstance(emb, dict) else emb
+                for j in range(a, b):
+                    out[j] = vecs[j - a]
+            except Exception as e:  # noqa: BLE001
+                logger.error("[B200RetrievalBackend] query embed error: %s", e, exc_info=True)
+        return out
 
     def _row_meta(self, row: int) -> Dict[str, Any]:
         d = self.docs[row] if 0 <= row < len(self.docs) else {}
@@ -213,177 +330,285 @@ class B200RetrievalBackend:
             return {k: 0.0 for k in values}
         return {k: (v - vmin) / (vmax - vmin) for k, v in values.items()}
 
+    # ------------------------------------------------------------------------------------------ per-graph_id graphs
+    def _node_to_row(self, node_id: str) -> Optional[int]:
+        """Sentence node ids are '<title>::sent<j>' (NodeBuilder.build, graph_construction/node_builder.py:61-66); the corpus
+        row is the docs.jsonl line with that title and sent_id (first one when a paragraph appears under several questions)."""
+        if self._node_rows is None:
+            table: Dict[str, int] = {}
+            for row, d in enumerate(self.docs):
+                table.setdefault(f"{d.get('title')}::sent{d.get('sent_id')}", row)
+            self._node_rows = table
+        return self._node_rows.get(node_id)
+
+    def graph_for(self, graph_id: str) -> Optional[LocalGraph]:
+        """load_graph_json + build_index (graph_utils.py:13-55) ONCE per graph_id (LRU), instead of per query
+        (retrieval_backend.py:154-155).  None when graph_root/<graph_id>/graph.json does not exist."""
+        if not graph_id:
+            return None
+        if graph_id in self._graphs:
+            self._graphs.move_to_end(graph_id)
+            return self._graphs[graph_id]
+        path = os.path.join(self.graph_root or "", graph_id, "graph.json")
+        lg: Optional[LocalGraph] = None
+        if self.graph_root and os.path.exists(path):
+            with open(path, "r", encoding="utf-8") as f:
+                graph = json.load(f)
+            row_ptr, col_idx, node_rows, qmatch, texts = store.graph_json_to_local(graph, self._node_to_row)
+            lg = LocalGraph(row_ptr, col_idx, node_rows, qmatch, [set(_tokenize(t)) if t else None for t in texts])
+        self._graphs[graph_id] = lg
+        while len(self._graphs) > max(1, int(self.graph_cache_size)):
+            self._graphs.popitem(last=False)
+        return lg
+
+    def _graph_seeds(self, lg: LocalGraph, query: str, dense_rows: Sequence[int]) -> List[int]:
+        """Seeds of expand_qmatch_neighbors (graph_utils.py:73-83): the q_match targets; else every sentence node whose
+        text shares a token with the query; else (no counterpart in the reference, whose result would be empty) the dense
+        top seed_k passages that are nodes of this graph."""
+        if lg.qmatch:
+            return list(lg.qmatch)
+        q_terms = set(_tokenize(query))
+        seeds = [i for i, toks in enumerate(lg.tokens) if toks and (q_terms & toks)]
+        if seeds:
+            return seeds
+        return [lg.row_to_node[r] for r in dense_rows[: self.seed_k] if r in lg.row_to_node]
+
     # ------------------------------------------------------------------------------------------ the call
-    def run(self, req: Any) -> Dict[str, Any]:
-        trace_id = getattr(req, "trace_id", None) or "trace-demo"
-        top_k = int(getattr(req, "top_k", None) or self.default_top_k)
+    def run_batch(self, reqs: Sequence[Any]) -> "RetrievalBatch":
+        """Embeds, searches, expands and fuses every request of the batch as arrays (ONE dense search, ONE expansion per
+        distinct window); returns a columnar RetrievalBatch whose rows are materialised into hits on demand."""
+        n = len(reqs)
+        trace_ids = [getattr(r, "trace_id", None) or "trace-demo" for r in reqs]
+        top_ks = [int(getattr(r, "top_k", None) or self.default_top_k) for r in reqs]
+        t0 = trace_ids[0] if n else "trace-demo"
+        with _span("Backend/Expand", self.sink, t0):
+            queries_per_req = [[r.query] + (list(self.expander.expand(query=r.query, trace_id=t)) if self.expander is not None else [])
+                               for r, t in zip(reqs, trace_ids)]
+        with _span("Backend/TextSearch", self.sink, t0):
+            text_hits = [list(self.text_searcher.search(queries=qs, top_k=max(k, self.bm25_pool_k))) if self.text_searcher is not None else []
+                         for qs, k in zip(queries_per_req, top_ks)]
+        windows = []
+        for r in reqs:
+            gw = getattr(r, "graph_window", None)
+            windows.append(max(0, int(gw if isinstance(gw, int) else self.graph_window)))
 
-        with _span("Backend/Expand", self.sink, trace_id):
-            expanded = list(self.expander.expand(query=req.query, trace_id=trace_id)) if self.expander is not None else []
-            queries = [req.query] + expanded
+        batch = RetrievalBatch(self, reqs, trace_ids, top_ks, queries_per_req, text_hits, windows)
+        dim = getattr(self.engine, "D", None)
+        with _span("Backend/DenseRerank", self.sink, t0):
+            qvs = self._embed_queries([r.query for r in reqs], trace_ids)
+            valid = []
+            for i, qv in enumerate(qvs):
+                ok = qv is not None and (dim is None or len(qv) == dim) and any(qv)
+                if qv is not None and not ok:
+                    logger.warning("[B200RetrievalBackend] query embedding unusable (dim=%s, corpus dim=%s): dense channel empty",
+                                   len(qv), dim)
+                if ok:
+                    valid.append(i)
+            if valid:
+                Q = np.asarray([qvs[i] for i in valid], dtype=np.float32)
+                pool = max(self.seed_k, max(top_ks[i] for i in valid))
+                s, ids = self.engine.dense_search(Q, pool)
+                batch.set_dense(valid, Q, np.asarray(s, dtype=np.float32), np.asarray(ids, dtype=np.int64))
 
-        with _span("Backend/TextSearch", self.sink, trace_id):
-            t_hits_raw = list(self.text_searcher.search(queries=queries, top_k=max(top_k, self.bm25_pool_k))) if self.text_searcher is not None else []
+        with _span("Backend/GraphExpand", self.sink, t0):
+            if valid and self.alpha_graph != 0.0:
+                self._graph_stage(batch, valid, Q)
+        return batch
 
-        gw_override = getattr(req, "graph_window", None)
-        window = max(0, int(gw_override if isinstance(gw_override, int) else self.graph_window))
-        dense_rows: List[int] = []
-        dense_scores: List[float] = []
-        rows: List[int] = []
-        fused_dev: List[float] = []
-        gnorm: List[float] = []
-        dnorm: List[float] = []
-        hops: List[int] = []
-        cosv: List[float] = []
-        ncand = 0
-        qv = None
-        with _span("Backend/DenseRerank", self.sink, trace_id):
-            qv = self._embed_query(req.query, trace_id)
-            dim = getattr(self.engine, "D", None)
-            if qv is not None and (dim is None or len(qv) == dim) and any(qv):
-                pool = max(self.seed_k, top_k)
-                s, i = self.engine.dense_search([qv], pool)
-                keep = [(sc, r) for sc, r in zip(s[0], i[0]) if r >= 0]
-                dense_scores = [sc for sc, _ in keep]
-                dense_rows = [r for _, r in keep]
-            elif qv is not None:
-                logger.warning("[B200RetrievalBackend] query embedding unusable (dim=%s, corpus dim=%s): dense channel empty",
-                               len(qv), dim)
-
-        use_graph = bool(getattr(req, "graph_id", "") or "") and self.engine.has_graph() and bool(dense_rows) and self.alpha_graph != 0.0
-        with _span("Backend/GraphExpand", self.sink, trace_id):
-            if use_graph:
-                seeds = dense_rows[: self.seed_k]
-                out = self.engine.expand_rescore([qv], [seeds], window, self.alpha_dense, self.alpha_graph, max(top_k, self.bm25_pool_k))
-                ncand = int(out["ncand"][0])
-                for j, r in enumerate(out["id"][0]):
-                    if r < 0:
-                        break
-                    rows.append(int(r)); fused_dev.append(float(out["score"][0][j])); gnorm.append(float(out["score_graph_norm"][0][j]))
-                    dnorm.append(float(out["score_dense_norm"][0][j])); hops.append(int(out["hop"][0][j])); cosv.append(float(out["cos"][0][j]))
+    def _graph_stage(self, batch: "RetrievalBatch", valid: List[int], Q: np.ndarray) -> None:
+        """Group the requests that take the graph channel by (kind of graph, window) and expand each group in one call.
+        Requests whose graph_id has its own graph.json are expanded together over the block-diagonal union of their
+        graphs (local node ids, shared blocks for repeated graph_ids); the others use the corpus-level CSR, if any."""
+        reqs = batch.reqs
+        kk = max(max(batch.top_ks[i] for i in valid), self.bm25_pool_k)
+        groups: Dict[Tuple[str, int], List[int]] = {}
+        local: Dict[int, LocalGraph] = {}
+        for pos, i in enumerate(valid):
+            gid = getattr(reqs[i], "graph_id", "") or ""
+            if not gid or not len(batch.dense_rows(i)):
+                continue
+            lg = self.graph_for(gid)
+            if lg is not None:
+                if lg.V == 0:
+                    continue                                  # an empty graph.json: no graph channel, like the reference
+                local[i] = lg
+                groups.setdefault(("local", batch.windows[i]), []).append(pos)
+            elif self.engine.has_graph():
+                groups.setdefault(("corpus", batch.windows[i]), []).append(pos)
+        for (kind, window), members in groups.items():
+            idx = [valid[p] for p in members]
+            Qg = Q[members]
+            if kind == "corpus":
+                S = self.seed_k
+                seeds = np.full((len(idx), S), -1, dtype=np.int64)
+                for j, i in enumerate(idx):
+                    rows = batch.dense_rows(i)[:S]
+                    seeds[j, : len(rows)] = rows
+                out = self.engine.expand_rescore(Qg, seeds, window, self.alpha_dense, self.alpha_graph, kk)
             else:
-                # dense-only: the candidate set is the exact dense top-k; min-max over it like the reference does over its pool
-                nd = self._minmax_norm({str(r): sc for r, sc in zip(dense_rows, dense_scores)})
-                for r, sc in zip(dense_rows, dense_scores):
-                    rows.append(r); dnorm.append(nd[str(r)]); gnorm.append(0.0); hops.append(-1); cosv.append(sc)
-                    fused_dev.append(self.alpha_dense * nd[str(r)])
+                blocks: Dict[int, int] = {}                     # id(LocalGraph) -> node offset of its block
+                rp, ci, nr = [np.zeros(1, dtype=np.int64)], [], []
+                node_off = edge_off = 0
+                seed_lists = []
+                for i in idx:
+                    lg = local[i]
+                    if id(lg) not in blocks:
+                        blocks[id(lg)] = node_off
+                        rp.append(lg.row_ptr[1:] + edge_off)
+                        ci.append(lg.col_idx.astype(np.int64) + node_off)
+                        nr.append(lg.node_rows)
+                        node_off += lg.V
+                        edge_off += int(lg.row_ptr[-1])
+                    base = blocks[id(lg)]
+                    seed_lists.append([base + s for s in self._graph_seeds(lg, reqs[i].query, batch.dense_rows(i).tolist())])
+                S = max(1, max(len(sl) for sl in seed_lists))
+                seeds = np.full((len(idx), S), -1, dtype=np.int64)
+                for j, sl in enumerate(seed_lists):
+                    seeds[j, : len(sl)] = sl
+                graph = (np.concatenate(rp), np.concatenate(ci).astype(np.int32) if ci else np.zeros(0, np.int32), np.concatenate(nr))
+                out = self.engine.expand_rescore(Qg, seeds, window, self.alpha_dense, self.alpha_graph, kk, graph=graph)
+            batch.set_graph(idx, {key: np.asarray(out[key]) for key in GRAPH_KEYS})
 
-        # ---- fusion with the (optional) host text channel: retrieval_backend.py:336-372 on row-joined ids ----
+    def run(self, req: Any) -> Dict[str, Any]:
+        return self.run_batch([req]).result(0)
+
+    def retrieve(self, req: Any) -> RetrievalOut:
+        return self.run_batch([req]).output(0)
+
+    def retrieve_many(self, reqs: Sequence[Any]) -> List[RetrievalOut]:
+        """Batching shim (SURVEY.md section 8 f-4): the orchestrator issues one query at a time
+        (app/orchestrator/nodes.py:110-115, my_code/run_system.py:35-39); a batch runner hands all requests over at once
+        so the dense stage is ONE search launch and the graph stage ONE expand launch.  Identical results to retrieve()
+        per request (it is the same code path with a batch of one)."""
+        if not reqs:
+            return []
+        batch = self.run_batch(reqs)
+        return [batch.output(i) for i in range(len(reqs))]
+
+
+class RetrievalBatch:
+    """Columnar result of B200RetrievalBackend.run_batch: per request the candidate rows, fused scores and channel
+    scores as arrays.  `result(i)` / `output(i)` materialise request i in the reference's shapes
+    (retrieval_backend.py:365-385); batch runners that only need rows and scores read `rows(i)` / `scores(i)` and never
+    pay for Python objects."""
+
+    def __init__(self, be: B200RetrievalBackend, reqs, trace_ids, top_ks, queries, text_hits, windows):
+        self.be, self.reqs, self.trace_ids, self.top_ks = be, list(reqs), trace_ids, top_ks
+        self.queries, self.text_hits, self.windows = queries, text_hits, windows
+        self._pos: Dict[int, int] = {}              # request -> row of the dense arrays
+        self._dense_s: Optional[np.ndarray] = None
+        self._dense_i: Optional[np.ndarray] = None
+        self._graph: Dict[int, Tuple[Dict[str, np.ndarray], int]] = {}   # request -> (group arrays, row in them)
+
+    # -- filled by the backend ------------------------------------------------------------------------------
+    def set_dense(self, valid: List[int], Q: np.ndarray, scores: np.ndarray, ids: np.ndarray) -> None:
+        self._pos = {i: p for p, i in enumerate(valid)}
+        self._dense_s, self._dense_i = scores, ids
+
+    def set_graph(self, idx: List[int], out: Dict[str, np.ndarray]) -> None:
+        for j, i in enumerate(idx):
+            self._graph[i] = (out, j)
+
+    def dense_rows(self, i: int) -> np.ndarray:
+        p = self._pos.get(i)
+        if p is None:
+            return np.zeros(0, dtype=np.int64)
+        ids = self._dense_i[p]
+        return ids[ids >= 0]
+
+    # -- columnar accessors ---------------------------------------------------------------------------------
+    def columns(self, i: int) -> Dict[str, np.ndarray]:
+        """Candidates of request i BEFORE the text channel / top_k cut, best first: rows, fused, gnorm, dnorm, hop, cos."""
+        if i in self._graph:
+            out, j = self._graph[i]
+            keep = out["id"][j] >= 0
+            return {"rows": out["id"][j][keep], "fused": out["score"][j][keep].astype(np.float64),
+                    "gnorm": out["score_graph_norm"][j][keep], "dnorm": out["score_dense_norm"][j][keep],
+                    "hop": out["hop"][j][keep], "cos": out["cos"][j][keep], "ncand": int(out["ncand"][j]),
+                    "status": int(out["status"][j]), "graph": True}
+        p = self._pos.get(i)
+        if p is None:
+            z = np.zeros(0)
+            return {"rows": np.zeros(0, np.int64), "fused": z, "gnorm": z, "dnorm": z, "hop": np.zeros(0, np.int32), "cos": z,
+                    "ncand": 0, "status": 0, "graph": False}
+        keep = self._dense_i[p] >= 0
+        rows, sc = self._dense_i[p][keep], self._dense_s[p][keep].astype(np.float64)
+        # dense-only: the candidate set is the exact dense top-k; min-max over it like the reference does over its pool (:296-301)
+        if len(sc) and sc.max() > sc.min():
+            dn = (sc - sc.min()) / (sc.max() - sc.min())
+        else:
+            dn = np.zeros_like(sc)
+        return {"rows": rows, "fused": self.be.alpha_dense * dn, "gnorm": np.zeros_like(sc), "dnorm": dn,
+                "hop": np.full(len(sc), -1, np.int32), "cos": sc, "ncand": 0, "status": 0, "graph": False}
+
+    def rows(self, i: int) -> np.ndarray:
+        return self.columns(i)["rows"][: self.top_ks[i]]
+
+    def scores(self, i: int) -> np.ndarray:
+        return self.columns(i)["fused"][: self.top_ks[i]]
+
+    # -- the reference's shapes -----------------------------------------------------------------------------
+    def result(self, i: int) -> Dict[str, Any]:
+        be, top_k = self.be, self.top_ks[i]
+        c = self.columns(i)
+        if c["status"] != 0:
+            raise RuntimeError(f"graph expansion of request {i} reached more nodes than the expansion kernels hold "
+                               f"({c['ncand']}); lower graph_window")
+        t_hits_raw = self.text_hits[i]
+        use_text = bool(t_hits_raw) and be.alpha_text != 0.0
+        n_take = len(c["rows"]) if use_text else min(len(c["rows"]), top_k + 8)   # a few spare rows for id collisions
         fused: Dict[str, Dict[str, Any]] = {}
-        for j, r in enumerate(rows):
-            meta = self._row_meta(r)
-            meta["source"] = "graph" if (use_graph and hops[j] > 0) else "dense"
-            if hops[j] >= 0:
-                meta["distance"] = hops[j]
-            meta["score_dense"] = cosv[j]
-            nid, _ = self._normalize_id({"id": f"sent::row{r}", "meta": meta})
-            meta["score_text_norm"], meta["score_graph_norm"], meta["score_dense_norm"] = 0.0, gnorm[j], dnorm[j]
-            if nid not in fused or fused_dev[j] > fused[nid]["score"]:
-                fused[nid] = {"id": nid, "score": float(fused_dev[j]), "meta": meta, "_row": r}
-        if t_hits_raw and self.alpha_text != 0.0:
+        for j in range(n_take):
+            r = int(c["rows"][j])
+            meta = be._row_meta(r)
+            hop = int(c["hop"][j])
+            meta["source"] = "graph" if (c["graph"] and hop > 0) else "dense"
+            if hop >= 0:
+                meta["distance"] = hop
+            meta["score_dense"] = float(c["cos"][j])
+            nid, _ = be._normalize_id({"id": f"sent::row{r}", "meta": meta})
+            meta["score_text_norm"], meta["score_graph_norm"], meta["score_dense_norm"] = 0.0, float(c["gnorm"][j]), float(c["dnorm"][j])
+            sc = float(c["fused"][j])
+            if nid not in fused or sc > fused[nid]["score"]:          # duplicate ids keep the max (retrieval_backend.py:336-348)
+                fused[nid] = {"id": nid, "score": sc, "meta": meta, "_row": r}
+            if not use_text and len(fused) >= top_k:
+                break
+        if use_text:
+            # fusion with the host text channel: retrieval_backend.py:336-372 on row-joined ids
             tmap: Dict[str, Dict[str, Any]] = {}
             for h in t_hits_raw:
-                nid, meta = self._normalize_id(h)
+                nid, meta = be._normalize_id(h)
                 sc = float(h.get("score") or 0.0)
                 if nid not in tmap or sc > tmap[nid]["score"]:
                     tmap[nid] = {"score": sc, "meta": dict(meta or {})}
-            norm_text = self._minmax_norm({k: v["score"] for k, v in tmap.items()})
+            norm_text = be._minmax_norm({k: v["score"] for k, v in tmap.items()})
             for nid, ts in norm_text.items():
                 if nid in fused:
-                    fused[nid]["score"] += self.alpha_text * ts
+                    fused[nid]["score"] += be.alpha_text * ts
                     fused[nid]["meta"]["score_text_norm"] = ts
                 else:
                     meta = dict(tmap[nid]["meta"])
                     meta["score_text_norm"], meta["score_graph_norm"], meta["score_dense_norm"] = ts, 0.0, 0.0
-                    fused[nid] = {"id": nid, "score": float(self.alpha_text * ts), "meta": meta, "_row": 1 << 62}
+                    fused[nid] = {"id": nid, "score": float(be.alpha_text * ts), "meta": meta, "_row": 1 << 62}
         ordered = sorted(fused.values(), key=lambda h: h["_row"])          # enumerate in id order ...
         ordered.sort(key=lambda h: h["score"], reverse=True)               # ... so the stable sort breaks ties by lower id
         hits = [{"id": h["id"], "score": h["score"], "meta": h["meta"]} for h in ordered[:top_k]]
-
+        has_dense = i in self._pos and len(self.dense_rows(i)) > 0
         diagnostics = {
-            "queries": queries,
+            "queries": self.queries[i],
             "bm25_candidates": len(t_hits_raw),
-            "graph_candidates": ncand,
-            "dense_scored": getattr(self.engine, "N", len(dense_rows)) if dense_rows else 0,
-            "weights": {"alpha_text": self.alpha_text, "alpha_graph": self.alpha_graph, "alpha_dense": self.alpha_dense},
-            "pool": {"bm25_pool_k": self.bm25_pool_k, "final_top_k": top_k, "seed_k": self.seed_k},
-            "graph_window_used": window,
-            "embed_batch": int(self.embed_batch),
-            "resolved_embed_model": self._resolve_embed_model(),
-            "engine": type(self.engine).__name__,
+            "graph_candidates": c["ncand"],
+            "dense_scored": getattr(be.engine, "N", len(c["rows"])) if has_dense else 0,
+            "weights": {"alpha_text": be.alpha_text, "alpha_graph": be.alpha_graph, "alpha_dense": be.alpha_dense},
+            "pool": {"bm25_pool_k": be.bm25_pool_k, "final_top_k": top_k, "seed_k": be.seed_k},
+            "graph_window_used": self.windows[i],
+            "embed_batch": int(be.embed_batch),
+            "resolved_embed_model": be._resolve_embed_model(),
+            "engine": type(be.engine).__name__,
         }
         return {"hits": hits, "diagnostics": diagnostics}
 
-    def retrieve_many(self, reqs: Sequence[Any]) -> List[RetrievalOut]:
-        """Batching shim (SURVEY.md section 8 f-4): the orchestrator issues one query at a time
-        (app/orchestrator/nodes.py:110-115, my_code/run_system.py:35-39); a batch runner can hand all
-        requests over at once so the dense stage is ONE search launch and the graph stage ONE expand launch.
-        Results are identical to calling retrieve() per request (same engine calls, batched)."""
-        if not reqs:
-            return []
-        self._embed_cache = {}
-        batch = _BatchedEngine(self, reqs)
-        saved = self.engine
-        self.engine = batch
-        try:
-            return [self.retrieve(r) for r in reqs]
-        finally:
-            self.engine = saved
-            self._embed_cache = None
-
-    def retrieve(self, req: Any) -> RetrievalOut:
-        result = self.run(req)
-        hits = [Hit(id=h["id"], score=h["score"], meta=h.get("meta")) for h in result["hits"]]
-        return RetrievalOut(hits=hits, diagnostics=result.get("diagnostics", {}))
-
-
-class _BatchedEngine:
-    """Engine proxy used by retrieve_many: pre-computes the dense search (and, when every request takes the
-    graph path with the same window, the expansion) for the whole batch, then serves the per-request calls."""
-
-    def __init__(self, be: "B200RetrievalBackend", reqs: Sequence[Any]):
-        self.inner = be.engine
-        self.N = getattr(self.inner, "N", None)
-        self.D = getattr(self.inner, "D", None)
-        self._dense: Dict[Tuple[float, ...], Tuple[List[float], List[int]]] = {}
-        self._graph: Dict[Tuple[Tuple[float, ...], Tuple[int, ...], int], Dict[str, list]] = {}
-        qvs = []
-        for r in reqs:
-            qv = be._embed_query(r.query, getattr(r, "trace_id", None) or "trace-demo")
-            be._embed_cache[r.query] = qv
-            if qv is not None and (self.D is None or len(qv) == self.D) and any(qv):
-                qvs.append(qv)
-        if not qvs:
-            return
-        pools = {max(be.seed_k, int(getattr(r, "top_k", None) or be.default_top_k)) for r in reqs}
-        pool = max(pools)
-        s, i = self.inner.dense_search(qvs, pool)
-        for qv, ss, ii in zip(qvs, s, i):
-            self._dense[tuple(qv)] = (ss, ii)
-        self._pool = pool
-        windows = {max(0, int(getattr(r, "graph_window", None) if isinstance(getattr(r, "graph_window", None), int) else be.graph_window)) for r in reqs}
-        all_graph = all(bool(getattr(r, "graph_id", "") or "") for r in reqs) and self.inner.has_graph() and be.alpha_graph != 0.0
-        if all_graph and len(windows) == 1 and len(pools) == 1:
-            w = windows.pop()
-            kk = max(pool, be.bm25_pool_k)
-            seeds = [[r for r in self._dense[tuple(qv)][1] if r >= 0][: be.seed_k] for qv in qvs]
-            S = max(len(sd) for sd in seeds)
-            padded = [sd + [-1] * (S - len(sd)) for sd in seeds]
-            out = self.inner.expand_rescore(qvs, padded, w, be.alpha_dense, be.alpha_graph, kk)
-            for j, (qv, sd) in enumerate(zip(qvs, seeds)):
-                self._graph[(tuple(qv), tuple(sd), w)] = {key: [v[j]] for key, v in out.items()}
-
-    def has_graph(self) -> bool:
-        return self.inner.has_graph()
-
-    def dense_search(self, qvecs, k: int):
-        hit = self._dense.get(tuple(qvecs[0])) if len(qvecs) == 1 else None
-        if hit is not None and k <= self._pool:
-            return [hit[0][:k]], [hit[1][:k]]
-        return self.inner.dense_search(qvecs, k)
-
-    def expand_rescore(self, qvecs, seeds, window, alpha_dense, alpha_graph, k):
-        hit = self._graph.get((tuple(qvecs[0]), tuple(seeds[0]), window)) if len(qvecs) == 1 else None
-        if hit is not None and k <= len(hit["id"][0]):
-            return {key: ([v[0][:k]] if isinstance(v[0], list) else v) for key, v in hit.items()}
-        return self.inner.expand_rescore(qvecs, seeds, window, alpha_dense, alpha_graph, k)
+    def output(self, i: int) -> RetrievalOut:
+        res = self.result(i)
+        return RetrievalOut(hits=[Hit(id=h["id"], score=h["score"], meta=h.get("meta")) for h in res["hits"]],
+                            diagnostics=res.get("diagnostics", {}))

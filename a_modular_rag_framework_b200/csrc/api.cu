@@ -645,16 +645,30 @@ int b200r_profile_read(double* kernel_ms, int64_t* launches) {
   return B200R_OK;
 }
 
-int b200r_graph_create(int device, const int64_t* row_ptr, const int32_t* col_idx, int64_t V, int64_t E, uint64_t* out_graph) {
+static int graph_create(int device, const int64_t* row_ptr, const int32_t* col_idx, int64_t V, int64_t E, const int64_t* node_rows,
+                        uint64_t* out_graph) {
   if (!out_graph) { set_error("out_graph is null"); return B200R_EINVAL; }
   *out_graph = 0;
   if (!row_ptr || V <= 0 || E < 0 || (E > 0 && !col_idx)) { set_error("bad graph arguments"); return B200R_EINVAL; }
   if (V > 0xfffffffell) { set_error("V too large"); return B200R_EINVAL; }
+  B200R_CUDA_CHECK(cudaSetDevice(device));
+  int rc = validate_csr(reinterpret_cast<const long long*>(row_ptr), col_idx, V, E);
+  if (rc) return rc;
   Graph* g = new (std::nothrow) Graph();
   if (!g) { set_error("out of host memory"); return B200R_ENOMEM; }
-  g->magic = kGraphMagic; g->device = device; g->row_ptr = row_ptr; g->col_idx = col_idx; g->V = V; g->E = E;
+  g->magic = kGraphMagic; g->device = device; g->row_ptr = row_ptr; g->col_idx = col_idx; g->node_rows = node_rows; g->V = V; g->E = E;
   *out_graph = reinterpret_cast<uint64_t>(g);
   return B200R_OK;
+}
+
+int b200r_graph_create(int device, const int64_t* row_ptr, const int32_t* col_idx, int64_t V, int64_t E, uint64_t* out_graph) {
+  return graph_create(device, row_ptr, col_idx, V, E, nullptr, out_graph);
+}
+
+int b200r_graph_create_mapped(int device, const int64_t* row_ptr, const int32_t* col_idx, int64_t V, int64_t E,
+                              const int64_t* node_rows, uint64_t* out_graph) {
+  if (!node_rows) { set_error("node_rows is null"); return B200R_EINVAL; }
+  return graph_create(device, row_ptr, col_idx, V, E, node_rows, out_graph);
 }
 
 int b200r_graph_destroy(uint64_t graph) {

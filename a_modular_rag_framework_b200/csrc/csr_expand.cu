@@ -92,6 +92,7 @@ struct ExpandParams {
   const float* row_mult;
   const long long* row_ptr;
   const int* col_idx;
+  const long long* node_rows;     // nullable: graph node -> global corpus row (per-graph_id graphs keep LOCAL node ids)
   const long long* seeds;
   long long N, V, id_base;
   int D, B, S, window, k, kp2, metric;
@@ -250,7 +251,8 @@ __global__ void __launch_bounds__(BFS_THREADS) bfs_kernel(const ExpandParams p) 
                 const int mid = (lo + hi) >> 1;
                 if (f_pre[mid] <= e) lo = mid; else hi = mid;
               }
-              v[r] = (u32)__ldg(p.col_idx + f_e0[lo] + (long long)(e - f_pre[lo]));
+              const int nb_id = __ldg(p.col_idx + f_e0[lo] + (long long)(e - f_pre[lo]));
+              v[r] = (nb_id >= 0 && (long long)nb_id < p.V) ? (u32)nb_id : EXP_EMPTY;     // malformed CSR entries are dropped
             }
           }
 #pragma unroll
@@ -288,9 +290,13 @@ __global__ void __launch_bounds__(BFS_THREADS) bfs_kernel(const ExpandParams p) 
     uint8_t* dist_out = p.ws.dist + (size_t)q * EXP_MAXC_BIG;
     const int nlevels = s_nlevels;
     for (int c = tid; c < ncand; c += BFS_THREADS) {
-      const u32 node = cand[c];
+      u32 node = cand[c];
       int d = 0;
       while (d + 1 < nlevels && c >= s_level_end[d]) ++d;
+      if (p.node_rows) {            // mapped graph: report (and score) the corpus row behind the node; < 0 = no row
+        const long long r = __ldg(p.node_rows + node);
+        node = (r >= 0 && r < 0xffffffffll) ? (u32)r : 0xfffffffeu;
+      }
       const bool own = (long long)node >= p.own_lo && (long long)node < p.own_hi;
       const int pos = own ? atomicAdd(&s_nown, 1) : ncand - 1 - atomicAdd(&s_nother, 1);
       cand_out[pos] = node;
@@ -605,6 +611,38 @@ __global__ void __launch_bounds__(SEL_THREADS) fuse_select_kernel(const ExpandPa
 
 int32_t expand_max_candidates() { return EXP_MAXC_BIG; }
 
+// CSR sanity check at graph creation: row_ptr[0] == 0, non-decreasing, row_ptr[V] == E, 0 <= col_idx < V
+__global__ void validate_csr_kernel(const long long* __restrict__ row_ptr, const int* __restrict__ col_idx, long long V, long long E,
+                                    int* __restrict__ bad) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, step = (long long)gridDim.x * blockDim.x;
+  for (long long i = i0; i <= V; i += step) {
+    const long long a = row_ptr[i];
+    if ((i == 0 && a != 0) || (i == V && a != E) || a < 0 || a > E || (i < V && row_ptr[i + 1] < a)) atomicOr(bad, 1);
+  }
+  for (long long e = i0; e < E; e += step) {
+    const int c = col_idx[e];
+    if (c < 0 || (long long)c >= V) atomicOr(bad, 2);
+  }
+}
+
+int validate_csr(const long long* row_ptr, const int* col_idx, long long V, long long E) {
+  int* d_bad = nullptr;
+  B200R_CUDA_CHECK(cudaMalloc(&d_bad, sizeof(int)));
+  B200R_CUDA_CHECK(cudaMemset(d_bad, 0, sizeof(int)));
+  validate_csr_kernel<<<2 * kNumSMs, 256>>>(row_ptr, col_idx, V, E, d_bad);
+  count_launch();
+  int bad = 0;
+  cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(d_bad);
+  if (e != cudaSuccess) { set_error("CSR validation failed to run: %s", cudaGetErrorString(e)); return B200R_ECUDA; }
+  if (bad) {
+    set_error("malformed CSR:%s%s", (bad & 1) ? " row_ptr must start at 0, be non-decreasing and end at E;" : "",
+              (bad & 2) ? " col_idx entries must lie in [0, V)" : "");
+    return B200R_EINVAL;
+  }
+  return B200R_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 template <typename QT>
 static int launch_bfs(const ExpandParams& p, cudaStream_t st) {
@@ -677,6 +715,7 @@ int launch_expand_rescore(const Index* ix, const Graph* g, const void* Q, const 
   ExpandParams p;
   p.X = ix->X; p.Q = Q; p.row_mult = ix->row_mult;
   p.row_ptr = reinterpret_cast<const long long*>(g->row_ptr); p.col_idx = g->col_idx;
+  p.node_rows = reinterpret_cast<const long long*>(g->node_rows);
   p.seeds = reinterpret_cast<const long long*>(seeds);
   p.N = ix->N; p.V = g->V; p.id_base = ix->id_base;
   p.D = ix->D; p.B = B; p.S = S; p.window = window; p.k = k; p.metric = ix->metric;

@@ -49,8 +49,10 @@ struct Graph {
   int device;
   const int64_t* row_ptr;
   const int32_t* col_idx;
+  const int64_t* node_rows;   // nullable: node -> global corpus row (b200r_graph_create_mapped)
   int64_t V, E;
 };
+int validate_csr(const long long* row_ptr, const int* col_idx, long long V, long long E);
 
 constexpr int kPlanSMs = 148;  // B200
 constexpr uint32_t kIndexMagic = 0xB200A001u;

@@ -62,7 +62,7 @@ __device__ __forceinline__ u64 final_key(u64 key, float qi) {
 // Visit every valid key of the CTA's segments with a warp-uniform trip count: f(key, active).
 template <typename F>
 __device__ __forceinline__ void for_each_key(const SelectParams& p, int q, int s0, int s1, bool staged, const u64* stage,
-                                             int total, bool xform, float qi, F f) {
+                                             int total, bool xform, float qi, bool has_carry, F f) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int SEL_THREADS = blockDim.x, SEL_WARPS = blockDim.x >> 5;
   if (staged) {
@@ -72,11 +72,12 @@ __device__ __forceinline__ void for_each_key(const SelectParams& p, int q, int s
       f(active ? stage[i] : 0ull, active);
     }
   } else {
-    const int s_end = s1 + ((p.carry && p.mode != kSelPartial) ? 1 : 0);    // pseudo segment S = the carry list
+    const int s_end = s1 + (has_carry ? 1 : 0);    // pseudo segment s1 = the carry list (its count lives at index S)
     for (int s = s0 + warp; s < s_end; s += SEL_WARPS) {
-      const size_t slot = (size_t)s * p.Bpad + q;
+      const bool is_carry = has_carry && s == s1;
+      const size_t slot = (size_t)(is_carry ? p.S : s) * p.Bpad + q;
       const int c = p.counts[slot];
-      const u64* lp = (s == p.S && p.carry) ? p.carry + (size_t)q * p.carry_cap : p.lists + slot * (size_t)p.cap;
+      const u64* lp = is_carry ? p.carry + (size_t)q * p.carry_cap : p.lists + slot * (size_t)p.cap;
       for (int base = 0; base < c; base += 32) {
         const int i = base + lane;
         const bool active = i < c;
@@ -117,8 +118,10 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
   // of the flattened candidate array by binary search over the prefix: two dependent global loads in total
   __shared__ int seg_off[SEL_MAX_SEGS + 1];
   __shared__ int warp_tot[32];
-  const bool has_carry = p.carry != nullptr && p.mode != kSelPartial;
-  const int nseg = s1 - s0 + (has_carry ? 1 : 0);       // the carry list is the last (pseudo) segment, index S
+  // the carry list rides along as one more (pseudo) segment after the real ones; a two-level select hands it to group 0
+  const bool has_carry = p.carry != nullptr && (p.mode != kSelPartial || blockIdx.y == 0);
+  const int nreal = s1 - s0;
+  const int nseg = nreal + (has_carry ? 1 : 0);
   const bool flat = nseg <= SEL_MAX_SEGS;
   if (tid == 0) { s_total = 0; s_nout = 0; s_prefix = 0; }
   __syncthreads();
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
     int mine = 0;
     for (int j = 0; j < per; ++j) {
       const int sgi = tid * per + j;
-      const int c = sgi < nseg ? p.counts[(size_t)(s0 + sgi) * p.Bpad + q] : 0;
+      const int c = sgi < nseg ? p.counts[(size_t)(sgi < nreal ? s0 + sgi : p.S) * p.Bpad + q] : 0;
       if (sgi < nseg) seg_off[sgi] = c;
       mine += c;
     }
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
     if (tid == SEL_THREADS - 1) { seg_off[nseg] = run; s_total = run; }
     __syncthreads();
   } else {
-    int local = 0;
+    int local = (has_carry && tid == 0) ? p.counts[(size_t)p.S * p.Bpad + q] : 0;
     for (int s = s0 + tid; s < s1; s += SEL_THREADS) local += p.counts[(size_t)s * p.Bpad + q];
     if (local) atomicAdd(&s_total, local);
     __syncthreads();
@@ -159,21 +162,22 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
     for (int i = tid; i < total; i += SEL_THREADS) {
       int lo = 0, hi = nseg;                       // last segment with seg_off <= i
       while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_off[mid] <= i) lo = mid; else hi = mid; }
-      const u64 key = (has_carry && lo == nseg - 1) ? p.carry[(size_t)q * p.carry_cap + (i - seg_off[lo])]
+      const u64 key = (lo >= nreal) ? p.carry[(size_t)q * p.carry_cap + (i - seg_off[lo])]
                                                      : p.lists[((size_t)(s0 + lo) * p.Bpad + q) * (size_t)p.cap + (i - seg_off[lo])];
       stage[i] = xform ? final_key(key, qi) : key;
     }
     __syncthreads();
   } else if (staged) {
     // gather the valid keys: one warp per segment, coalesced
-    for (int s = s0 + warp; s < s1; s += SEL_WARPS) {
-      const size_t slot = (size_t)s * p.Bpad + q;
+    for (int s = s0 + warp; s < s1 + (has_carry ? 1 : 0); s += SEL_WARPS) {
+      const bool is_carry = has_carry && s == s1;
+      const size_t slot = (size_t)(is_carry ? p.S : s) * p.Bpad + q;
       const int c = p.counts[slot];
       if (c == 0) continue;
       int base = 0;
       if (lane == 0) base = atomicAdd(&s_nout, c);
       base = __shfl_sync(kFullMask, base, 0);
-      const u64* lp = p.lists + slot * (size_t)p.cap;
+      const u64* lp = is_carry ? p.carry + (size_t)q * p.carry_cap : p.lists + slot * (size_t)p.cap;
       for (int i = lane; i < c; i += 32) stage[base + i] = xform ? final_key(lp[i], qi) : lp[i];
     }
     __syncthreads();
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
       __syncthreads();
       const u64 prefix = s_prefix;
       const u64 hi_mask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
-      for_each_key(p, q, s0, s1, staged, stage, total, xform, qi, [&](u64 key, bool active) {
+      for_each_key(p, q, s0, s1, staged, stage, total, xform, qi, has_carry, [&](u64 key, bool active) {
         hist_add(hist, active && (key & hi_mask) == prefix, (u32)(key >> shift) & 255u);
       });
       __syncthreads();
@@ -244,17 +248,18 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
         pos = __shfl_sync(kFullMask, pos, 0);
         if (keep) cl[pos + __popc(m & ((1u << lane) - 1u))] = key;
       }
-      for (int sgi = tid; sgi < nseg - 1; sgi += SEL_THREADS) wc[(size_t)(s0 + sgi) * p.Bpad + q] = 0;
+      for (int sgi = tid; sgi < nreal; sgi += SEL_THREADS) wc[(size_t)(s0 + sgi) * p.Bpad + q] = 0;
       __syncthreads();
       if (tid == 0) wc[(size_t)p.S * p.Bpad + q] = s_nout;
       return;
     }
     const int s_end = s1 + (has_carry ? 1 : 0);
     for (int s = s0 + warp; s < s_end; s += SEL_WARPS) {
-      const size_t slot = (size_t)s * p.Bpad + q;
+      const bool is_carry = has_carry && s == s1;
+      const size_t slot = (size_t)(is_carry ? p.S : s) * p.Bpad + q;
       const int c = wc[slot];
       if (c == 0) continue;
-      u64* lp = (has_carry && s == p.S) ? p.carry + (size_t)q * p.carry_cap : wl + slot * (size_t)p.cap;
+      u64* lp = is_carry ? p.carry + (size_t)q * p.carry_cap : wl + slot * (size_t)p.cap;
       int out = 0;
       for (int base = 0; base < c; base += 32) {
         const int i = base + lane;
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
   if (p.mode == kSelPartial) {
     const size_t oslot = (size_t)blockIdx.y * p.Bpad + q;
     u64* ol = p.out_lists + oslot * (size_t)p.k;
-    for_each_key(p, q, s0, s1, staged, stage, total, xform, qi, [&](u64 key, bool active) {
+    for_each_key(p, q, s0, s1, staged, stage, total, xform, qi, has_carry, [&](u64 key, bool active) {
       if (active && key >= kth) {
         const int pos = atomicAdd(&s_nout, 1);
         if (pos < p.k) ol[pos] = key;
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
 
   for (int i = tid; i < p.kp2; i += SEL_THREADS) sk[i] = 0;
   __syncthreads();
-  for_each_key(p, q, s0, s1, staged, stage, total, xform, qi, [&](u64 key, bool active) {
+  for_each_key(p, q, s0, s1, staged, stage, total, xform, qi, has_carry, [&](u64 key, bool active) {
     if (active && key >= kth) {
       const int pos = atomicAdd(&s_nout, 1);
       if (pos < p.kp2) sk[pos] = key;
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 static int run_select(SelectParams& p, int grid_y, cudaStream_t st) {
-  const long long all = (long long)(p.mode == kSelPartial ? p.seg_per_cta : p.S) * p.cap + (p.carry && p.mode != kSelPartial ? p.carry_cap : 0);
+  const long long all = (long long)(p.mode == kSelPartial ? p.seg_per_cta : p.S) * p.cap + (p.carry ? p.carry_cap : 0);
   int limit = SEL_STAGE_MAX;
   const long long ctas = (long long)p.B * grid_y;
   if (p.mode != kSelPartial) limit = select_stage_limit(p.k, p.B);   // pruned lists hold ~k + one phase's survivors
@@ -353,7 +358,7 @@ int launch_select_lists(const Index* ix, const SearchPlan& pl, void* ws, float* 
   if (pl.num_groups > 0) {
     // two levels: many short per-warp lists (scan path) are first reduced group-wise to k keys each
     SelectParams p1 = p;
-    p1.use_comm = 0; p1.carry = nullptr;
+    p1.use_comm = 0;           // the partial level's group 0 also reduces the carry list
     p.carry = nullptr;
     p1.mode = kSelPartial; p1.seg_per_cta = SEL_GROUP;
     p1.out_lists = reinterpret_cast<u64*>((char*)ws + pl.off_lists2);

@@ -187,21 +187,31 @@ def merge_topk_src(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int) ->
 
 
 class PassageGraph:
-    """CSR of the undirected next_in_doc adjacency; node id == corpus row id."""
+    """CSR of the undirected next_in_doc adjacency.  Without `node_rows` node id == corpus row id; with it the node ids are
+    local and node_rows[v] (int64, < 0 = none) is node v's corpus row (per-graph_id graphs, block-diagonal batches)."""
 
-    def __init__(self, row_ptr: torch.Tensor, col_idx: torch.Tensor):
+    def __init__(self, row_ptr: torch.Tensor, col_idx: torch.Tensor, node_rows: Optional[torch.Tensor] = None):
         _require_cuda(row_ptr, "row_ptr")
         _require_cuda(col_idx, "col_idx")
         if row_ptr.dtype != torch.int64 or col_idx.dtype != torch.int32:
             raise ValueError("row_ptr must be int64 and col_idx int32")
         self._lib = N.load()
-        self.row_ptr, self.col_idx = row_ptr, col_idx
+        self.row_ptr, self.col_idx, self.node_rows = row_ptr, col_idx, node_rows
         self.device = row_ptr.device
         self.V = int(row_ptr.numel()) - 1
         self.E = int(col_idx.numel())
         self._handle = ctypes.c_uint64(0)
-        N.check(self._lib.b200r_graph_create(self.device.index or 0, row_ptr.data_ptr(),
-                                             col_idx.data_ptr() if self.E else None, self.V, self.E, ctypes.byref(self._handle)))
+        with torch.cuda.device(self.device):
+            if node_rows is None:
+                N.check(self._lib.b200r_graph_create(self.device.index or 0, row_ptr.data_ptr(),
+                                                     col_idx.data_ptr() if self.E else None, self.V, self.E, ctypes.byref(self._handle)))
+            else:
+                _require_cuda(node_rows, "node_rows")
+                if node_rows.dtype != torch.int64 or node_rows.numel() != self.V:
+                    raise ValueError("node_rows must be int64 [V]")
+                N.check(self._lib.b200r_graph_create_mapped(self.device.index or 0, row_ptr.data_ptr(),
+                                                            col_idx.data_ptr() if self.E else None, self.V, self.E,
+                                                            node_rows.data_ptr(), ctypes.byref(self._handle)))
 
     def close(self) -> None:
         if getattr(self, "_handle", None) is not None and self._handle.value:

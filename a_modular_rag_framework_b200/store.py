@@ -114,10 +114,67 @@ def next_in_doc_edges(docs: Iterable[Dict[str, Any]]) -> Tuple[np.ndarray, np.nd
     return np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64)
 
 
-def save_csr(path: str, row_ptr: np.ndarray, col_idx: np.ndarray) -> None:
-    np.savez(path, row_ptr=np.asarray(row_ptr, dtype=np.int64), col_idx=np.asarray(col_idx, dtype=np.int32))
+def csr_path(path: str) -> str:
+    """The file save_csr writes for `path`: numpy appends '.npz' to a name that lacks it."""
+    return path if path.endswith(".npz") else path + ".npz"
+
+
+def save_csr(path: str, row_ptr: np.ndarray, col_idx: np.ndarray) -> str:
+    out = csr_path(path)
+    np.savez(out, row_ptr=np.asarray(row_ptr, dtype=np.int64), col_idx=np.asarray(col_idx, dtype=np.int32))
+    return out
 
 
 def load_csr(path: str) -> Tuple[np.ndarray, np.ndarray]:
-    z = np.load(path)
+    z = np.load(path if os.path.exists(path) else csr_path(path))
     return z["row_ptr"].astype(np.int64), z["col_idx"].astype(np.int32)
+
+
+def graph_json_to_local(graph: Dict[str, Any], node_to_row: Callable[[str], Optional[int]]
+                        ) -> Tuple[np.ndarray, np.ndarray, np.ndarray, List[int], List[str]]:
+    """graph.json dict (one graph_id) -> LOCAL CSR + node -> corpus row map + q_match seeds + sentence texts.
+
+    Follows build_index (graph_utils.py:25-55): ``next_in_doc`` edges feed the undirected adjacency, ``q_match`` edges
+    whose source is "q1" give the seeds, sentence nodes contribute ``props.text`` (the lexical seed fallback of
+    expand_qmatch_neighbors, :76-83); every other edge / node type is ignored.  Nodes that do not map to a corpus row
+    cannot be scored or materialised and are dropped.  Local node ids follow first appearance (nodes, then edges).
+    -> (row_ptr int64 [V+1], col_idx int32, node_rows int64 [V], qmatch local ids, texts [V])"""
+    local: Dict[str, int] = {}
+    rows: List[int] = []
+    texts: List[str] = []
+
+    def node(nid: Any) -> Optional[int]:
+        if nid in local:
+            return local[nid]
+        r = node_to_row(nid) if isinstance(nid, str) else None
+        if r is None:
+            return None
+        local[nid] = len(rows)
+        rows.append(int(r))
+        texts.append("")
+        return local[nid]
+
+    for n in graph.get("nodes", []):
+        if n.get("type") == "sentence":
+            v = node(n.get("id"))
+            if v is not None:
+                texts[v] = ((n.get("props") or {}).get("text") or "")
+    src: List[int] = []
+    dst: List[int] = []
+    qmatch: List[int] = []
+    for e in graph.get("edges", []):
+        et = e.get("type")
+        s, t = e.get("source"), e.get("target")
+        if et == "next_in_doc":
+            a, b = node(s), node(t)
+            if a is not None and b is not None:
+                src.append(a)
+                dst.append(b)
+        elif et == "q_match" and s == "q1":
+            v = node(t)
+            if v is not None and v not in qmatch:
+                qmatch.append(v)
+    V = len(rows)
+    row_ptr, col_idx = csr_from_edges(V, np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64)) if V else (
+        np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int32))
+    return row_ptr, col_idx, np.asarray(rows, dtype=np.int64), qmatch, texts

@@ -175,6 +175,14 @@ int b200r_profile_read(double* kernel_ms, int64_t* launches);
  */
 int b200r_graph_create(int device, const int64_t* row_ptr, const int32_t* col_idx, int64_t V, int64_t E,
                        uint64_t* out_graph);
+/* Graph whose node ids are LOCAL (0..V-1) with node_rows[V] i64 mapping every node to its global corpus row (< 0 = the
+ * node has no embedding row and scores 0.0): the shape of the reference's per-question graphs
+ * (data/graph/<graph_id>/graph.json, load_graph_json graph_utils.py:13-22), and of a block-diagonal union of many of
+ * them so that a batch of requests with DIFFERENT graph_ids expands in one launch.  Seeds passed to expand_rescore are
+ * local node ids; reported ids are corpus rows.  Both creators validate the CSR on the device (row_ptr monotone from
+ * 0 to E, 0 <= col_idx < V) and fail with B200R_EINVAL on a malformed one. */
+int b200r_graph_create_mapped(int device, const int64_t* row_ptr, const int32_t* col_idx, int64_t V, int64_t E,
+                              const int64_t* node_rows, uint64_t* out_graph);
 int b200r_graph_destroy(uint64_t graph);
 
 /* Replaces expand_qmatch_neighbors (graph_utils.py:58-129) + _cosine re-score + _minmax_norm and the

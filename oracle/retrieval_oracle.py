@@ -289,13 +289,24 @@ def fuse_and_rank(dense: Dict[int, float], graph: Dict[int, float], alpha_dense:
 
 def expand_rescore(q: np.ndarray, X: np.ndarray, row_ptr: np.ndarray, col_idx: np.ndarray,
                    seeds: Iterable[int], window: int, alpha_dense: float, alpha_graph: float, k: int,
-                   metric: str = "cos") -> Tuple[List[Tuple[int, float, float, float, float]], Dict[int, int]]:
-    """Graph-enhanced second stage for ONE query: BFS candidates, cosine re-score, fuse, top-k."""
+                   metric: str = "cos", node_rows: Optional[np.ndarray] = None
+                   ) -> Tuple[List[Tuple[int, float, float, float, float]], Dict[int, int]]:
+    """Graph-enhanced second stage for ONE query: BFS candidates, cosine re-score, fuse, top-k.
+
+    node_rows (optional): the graph's node ids are local and node_rows[v] is node v's corpus row (the shape of the
+    reference's per-graph_id graphs, graph_utils.py:13-55, whose node ids are strings); seeds are then local ids and the
+    returned ids / distance keys are corpus rows.  A node without a corpus row (or beyond X) scores 0.0."""
     dist = bfs_expand(row_ptr, col_idx, seeds, window)
+    if node_rows is not None:
+        dist = {int(node_rows[v]): d for v, d in dist.items()}
     cand = np.array(sorted(dist), dtype=np.int64)
     if len(cand) == 0:
         return [], dist
-    S = score_matrix(np.asarray(q)[None, :], np.asarray(X)[cand], metric)[0]
+    X = np.asarray(X)
+    Xc = np.zeros((len(cand), X.shape[1]), dtype=np.float64)
+    inside = (cand >= 0) & (cand < X.shape[0])
+    Xc[inside] = X[cand[inside]]
+    S = score_matrix(np.asarray(q)[None, :], Xc, metric)[0]
     dense = {int(c): float(s) for c, s in zip(cand, S)}
     graph = {int(c): decay(dist[int(c)]) for c in cand}
     return fuse_and_rank(dense, graph, alpha_dense, alpha_graph, k), dist

@@ -177,3 +177,92 @@ def test_retrieve_many_equals_retrieve(corpus):
     assert type(be.engine).__name__ == "OracleEngine"   # proxy removed afterwards
     mixed = be.retrieve_many([_req(corpus.docs[5]["text"], graph_id=""), _req(corpus.docs[6]["text"], top_k=3)])
     assert mixed[0].hits[0].meta["row"] == 5 and len(mixed[1].hits) == 3
+
+
+# ------------------------------------------------------------------------------------------------ a5: graph_id -> graph.json
+
+
+def _bfs_cases(golden_dir):
+    import json
+    with open(os.path.join(golden_dir, "bfs_cases.json")) as f:
+        return json.load(f)
+
+
+def check_bfs_case_through_backend(be, case, gid):
+    """The recorded output of the reference's expand_qmatch_neighbors (tests/golden/bfs_cases.json) must come back through
+    the plug-in call: candidate set, hop distances (meta.distance) and the candidate count in the diagnostics."""
+    out = be.run(_req("the question", graph_id=gid, top_k=max(1, len(case["nodes"])), graph_window=case["window"]))
+    rows = sorted(h["meta"]["row"] for h in out["hits"])
+    assert rows == case["nodes"]
+    dist = dict(zip(case["nodes"], case["dist"]))
+    assert all(h["meta"]["distance"] == dist[h["meta"]["row"]] for h in out["hits"])
+    assert out["diagnostics"]["graph_candidates"] == len(case["nodes"])
+    assert out["diagnostics"]["graph_window_used"] == case["window"]
+    return out
+
+
+def test_graph_id_graphs_replay_reference_bfs_cases(tmp_path, golden_dir):
+    from tests.helpers_backend import make_graph_id_fixture
+    for n, case in enumerate(_bfs_cases(golden_dir)):
+        fx = make_graph_id_fixture(str(tmp_path / f"c{n}"), case, "g")
+        eng = OracleEngine(fx.X)
+        be = B200RetrievalBackend(router=FakeRouter(fx.dim), index_path=fx.index_path, emb_path=fx.emb_path, graph_root=fx.graph_root,
+                                  engine=eng)
+        check_bfs_case_through_backend(be, case, "g")
+        check_bfs_case_through_backend(be, case, "g")
+        assert len(be._graphs) == 1                       # parsed once, not per query (retrieval_backend.py:154-155 does)
+        # a graph_id without a graph.json and no corpus-level CSR: dense channel only, like the reference's empty graph
+        out = be.run(_req("the question", graph_id="missing", top_k=5))
+        assert out["diagnostics"]["graph_candidates"] == 0 and len(out["hits"]) == min(5, case["V"])
+
+
+def test_graph_id_seed_fallbacks(tmp_path, golden_dir):
+    """No q_match edges: the lexical-overlap seeds of graph_utils.py:76-83; no overlap either: the dense top-seed_k passages."""
+    from tests.helpers_backend import make_graph_id_fixture
+    case = _bfs_cases(golden_dir)[7]                      # V=60, window 2
+    fx = make_graph_id_fixture(str(tmp_path), case, "g", qmatch=False)
+    be = B200RetrievalBackend(router=FakeRouter(fx.dim), index_path=fx.index_path, emb_path=fx.emb_path, graph_root=fx.graph_root,
+                              engine=OracleEngine(fx.X), seed_k=3)
+    lg = be.graph_for("g")
+    assert lg.qmatch == [] and lg.V == 60
+    # "alpha17" occurs in exactly one sentence -> that node is the only seed
+    assert be._graph_seeds(lg, "tell me about alpha17", []) == [lg.row_to_node[17]]
+    rp, ci = store.csr_from_edges(60, np.array(case["src"]), np.array(case["dst"]))
+    want = O.bfs_expand(rp, ci, [17], 2)
+    out = be.run(_req("tell me about alpha17", graph_id="g", top_k=60))
+    assert sorted(h["meta"]["row"] for h in out["hits"]) == sorted(want)
+    assert all(h["meta"]["distance"] == want[h["meta"]["row"]] for h in out["hits"])
+    # no token in common with any sentence: seeds = dense top-3 rows
+    out = be.run(_req("zzz qqq", graph_id="g", top_k=60))
+    qv = O.bf16_bits_to_f32(O.f32_to_bf16_bits(text_vec("zzz qqq", fx.dim)))
+    _, top = O.topk(qv[None], O.bf16_bits_to_f32(O.f32_to_bf16_bits(fx.X)), 3)
+    want = O.bfs_expand(rp, ci, top[0].tolist(), 2)
+    assert sorted(h["meta"]["row"] for h in out["hits"]) == sorted(want)
+
+
+def test_batch_with_different_graph_ids_is_one_expansion(tmp_path, golden_dir):
+    """retrieve_many over requests that name DIFFERENT graph_ids: one dense search and one expansion (block-diagonal union
+    of the graphs), results equal to the one-request-at-a-time path."""
+    from tests.helpers_backend import make_graph_id_fixture
+    cases = _bfs_cases(golden_dir)
+    case_a, case_b = cases[6], cases[7]                   # same V = 60 corpus, windows 1 and 2 -> same docs, two graphs
+    fx = make_graph_id_fixture(str(tmp_path), case_a, "ga")
+    # second graph over the same corpus: reversed chain edges and other seeds
+    import json
+    g2 = {"nodes": [], "edges": [{"source": f"Doc::sent{v}", "target": f"Doc::sent{v + 1}", "type": "next_in_doc"} for v in range(0, 59, 2)]
+          + [{"source": "q1", "target": "Doc::sent10", "type": "q_match"}, {"source": "q1", "target": "Doc::sent41", "type": "q_match"}]}
+    os.makedirs(os.path.join(fx.graph_root, "gb"))
+    with open(os.path.join(fx.graph_root, "gb", "graph.json"), "w") as f:
+        json.dump(g2, f)
+    eng = OracleEngine(fx.X)
+    be = B200RetrievalBackend(router=FakeRouter(fx.dim), index_path=fx.index_path, emb_path=fx.emb_path, graph_root=fx.graph_root, engine=eng)
+    reqs = [_req("the question", graph_id="ga", top_k=20), _req("alpha3 sentence", graph_id="gb", top_k=20),
+            _req("the question", graph_id="ga", top_k=7), _req("other", graph_id="", top_k=5), _req("x", graph_id="nope", top_k=5)]
+    single = [be.retrieve(r) for r in reqs]
+    eng.calls = {"dense": 0, "expand": 0}
+    many = be.retrieve_many(reqs)
+    assert eng.calls == {"dense": 1, "expand": 1}
+    for a, b in zip(single, many):
+        assert [h.id for h in a.hits] == [h.id for h in b.hits]
+        assert np.allclose([h.score for h in a.hits], [h.score for h in b.hits])
+    assert {h.meta["row"] for h in many[1].hits} == {10, 11, 40, 41}     # gb's edges are disjoint pairs (2v, 2v+1)
