@@ -27,7 +27,7 @@ EXPORTS = [
     "b200r_search_sharded_begin", "b200r_search_sharded_finish", "b200r_search_sharded", "b200r_search_sharded_host_all",
     "b200r_merge_topk", "b200r_merge_topk_packed", "b200r_profile_enable", "b200r_profile_read",
     "b200r_graph_create", "b200r_graph_create_mapped", "b200r_graph_destroy",
-    "b200r_merge_topk_src", "b200r_expand_max_candidates", "b200r_expand_rescore", "b200r_expand_workspace_bytes", "b200r_expand_rescore_sharded",
+    "b200r_merge_topk_src", "b200r_expand_max_candidates", "b200r_expand_rescore", "b200r_expand_workspace_bytes", "b200r_expand_rescore_sharded", "b200r_expand_rescore_exchange",
 ]
 
 
@@ -103,6 +103,9 @@ def load() -> ctypes.CDLL:
     lib.b200r_expand_rescore_sharded.argtypes = [c_uint64, c_uint64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_int32,
                                                  c_int32, c_int64, c_int64, c_void_p, c_size_t, c_void_p,
                                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.b200r_expand_rescore_exchange.argtypes = [c_uint64, c_uint64, c_uint64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float,
+                                                  c_int32, c_int64, c_int32, c_void_p, c_size_t,
+                                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is c_int and name not in ("b200r_version", "b200r_last_error"):

@@ -90,8 +90,8 @@ class CudaEngine:
             raise RuntimeError("B200RetrievalBackend needs a CUDA device: there is no CPU fallback")
         self.torch = torch
         self.devs = [torch.device("cuda", int(d)) for d in devices] if devices else [torch.device(device)]
-        if len(self.devs) > torch.cuda.device_count():
-            raise RuntimeError(f"devices={list(devices)} but only {torch.cuda.device_count()} CUDA devices are visible")
+        if max((d.index or 0) for d in self.devs) >= torch.cuda.device_count():
+            raise RuntimeError(f"devices={list(devices or [device])} but only {torch.cuda.device_count()} CUDA devices are visible")
         self.device = self.devs[0]
         X, meta, scales = store.load_embeddings(emb_path)
         self.tdtype = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32, "i8": torch.int8}[meta["dtype"]]

@@ -709,6 +709,36 @@ int b200r_expand_rescore(uint64_t index, uint64_t graph, const void* Q, const in
 
 size_t b200r_expand_workspace_bytes(int32_t B) { return B > 0 ? expand_workspace_bytes(B) : 0; }
 
+int b200r_expand_rescore_exchange(uint64_t index, uint64_t graph, uint64_t comm, const void* Q, const int64_t* seeds, int32_t B,
+                                  int32_t S, int32_t window, float alpha_dense, float alpha_graph, int32_t k, int64_t n_total_rows,
+                                  int32_t phase, void* workspace, size_t workspace_bytes, float* out_scores, int64_t* out_ids,
+                                  int32_t* out_hops, float* out_graph_norm, float* out_dense_norm, float* out_cos, int32_t* out_ncand,
+                                  int32_t* out_status, void* stream) {
+  Index* ix = get_index(index);
+  Graph* g = get_graph(graph);
+  Comm* c = get_comm(comm);
+  if (!ix || !g || !c) return B200R_ESTATE;
+  if (ix->device != g->device || ix->device != c->device) { set_error("index, graph and comm must live on the same device"); return B200R_EINVAL; }
+  if (!Q || !seeds || !workspace || !out_scores || !out_ids || !out_hops || !out_graph_norm || !out_dense_norm || !out_cos || !out_ncand ||
+      !out_status) { set_error("null pointer"); return B200R_EINVAL; }
+  if (B <= 0 || S <= 0 || k <= 0 || k > B200R_MAX_K || window < 0 || window > 255 || phase < 0 || phase > 4) {
+    set_error("bad B/S/k/window/phase (%d/%d/%d/%d/%d)", B, S, k, window, phase);
+    return B200R_EINVAL;
+  }
+  if (workspace_bytes < expand_workspace_bytes(B) || (reinterpret_cast<uintptr_t>(workspace) & 255)) {
+    set_error("expand workspace too small or misaligned: need %zu bytes, 256-byte aligned", expand_workspace_bytes(B));
+    return B200R_ENOMEM;
+  }
+  B200R_CUDA_CHECK(cudaSetDevice(ix->device));
+  for (int ph = (phase ? phase : 1); ph <= (phase ? phase : 4); ++ph) {
+    int rc = launch_expand_rescore_exchange(ix, g, c, Q, seeds, B, S, window, alpha_dense, alpha_graph, k, n_total_rows, out_scores, out_ids,
+                                            out_hops, out_graph_norm, out_dense_norm, out_cos, out_ncand, out_status, workspace, ph,
+                                            reinterpret_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+  }
+  return B200R_OK;
+}
+
 int b200r_expand_rescore_sharded(uint64_t index, uint64_t graph, const void* Q, const int64_t* seeds, int32_t B, int32_t S,
                                  int32_t window, float alpha_dense, float alpha_graph, int32_t k, int32_t pass, int64_t own_lo,
                                  int64_t own_hi, void* workspace, size_t workspace_bytes, float* minmax, float* out_scores,

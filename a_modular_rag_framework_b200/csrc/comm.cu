@@ -195,8 +195,12 @@ static int comm_alloc(int device, int rank, int world, int max_B, int max_k, int
   c->max_B = max_B; c->max_k = max_k; c->max_graph_k = max_graph_k;
   c->rec_cap[kChanDense] = dense_record_stride(max_B, max_k);
   if (max_graph_k > 0) {
-    c->rec_cap[kChanGraphRange] = align_up((size_t)8 * max_B, 16);
-    c->rec_cap[kChanGraphRecords] = align_up((size_t)28 * (((size_t)max_B * max_graph_k + 1) / 2 * 2), 16);
+    // graph stage (csr_expand.cu, mode 3): requests home -> owner (one record per sending rank), cosines owner -> home
+    // and results home -> everybody (one shared region each, expressed as world equal parts)
+    const int per = (max_B + world - 1) / world;
+    c->rec_cap[kChanGraphReq] = expand_xchg_req_bytes(per);
+    c->rec_cap[kChanGraphCos] = align_up((expand_xchg_cos_bytes(per) + world - 1) / world, 16);
+    c->rec_cap[kChanGraphOut] = align_up((expand_xchg_out_bytes(max_B, max_graph_k) + world - 1) / world, 16);
   }
   size_t off = kCommCtrlBytes;
   for (int ch = 0; ch < kCommChannels; ++ch) {

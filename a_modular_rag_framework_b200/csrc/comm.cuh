@@ -104,6 +104,10 @@ __device__ __forceinline__ u32 comm_recv_begin(const CommDev& c) {
   __syncthreads();
   return E;
 }
+// epoch of the exchange a receiver is about to read, without waiting (a kernel that runs after one that already waited)
+__device__ __forceinline__ u32 comm_recv_peek(const CommDev& c) {
+  return *reinterpret_cast<volatile u32*>(&comm_ctrl(c, c.rank)->recv_epoch[c.channel]) + 1u;
+}
 __device__ __forceinline__ void comm_recv_end(const CommDev& c, u32 E, u32 nctas) {
   __syncthreads();                  // every thread's reads of the window have returned
   __shared__ u32 r_last;

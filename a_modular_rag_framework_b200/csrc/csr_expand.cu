@@ -28,10 +28,12 @@
 // decay :87-94), DenseReranker._cosine (retrieval_backend.py:192-197), _minmax_norm (:296-301) and the
 // fusion / sort / slice of HybridRetrievalBackend.run (:353-372).
 #include "common.cuh"
+#include "comm.cuh"
 #include "internal.h"
 #include <math_constants.h>
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 namespace b200r {
 
@@ -105,7 +107,46 @@ struct ExpandParams {
   long long own_lo, own_hi;       // global node ids this rank scores: [own_lo, own_hi)
   float* minmax;                  // [B][2] float (min, max): written by mode 1, read by mode 2
   ExpandWs ws;
+  // mode 3 (b200r_expand_rescore_exchange): queries are sharded over the ranks as well.  The HOME rank of a query runs its
+  // BFS and its fusion / top-k; the candidates travel to the ranks that OWN their rows (c_req), the cosines travel back
+  // (c_cos), and every home rank stores its queries' results into all ranks' output slots (c_out) -- all by peer stores
+  // from inside the kernels (comm.cuh), no collective.
+  CommDev c_req, c_cos, c_out;
+  int per;                        // queries per home rank: home(q) = q / per
+  int q_lo, q_hi;                 // this rank's home queries
+  long long rows_per;             // corpus rows per owner rank: owner(row) = min(row / rows_per, world - 1)
 };
+
+// ---- layout of the exchange slots (mode 3) ----------------------------------------------------------------------
+// c_req slot (in the OWNER's window): one record per sending (home) rank: hdr[per][2] u32 (count, offset of this owner's
+// sublist inside the home's candidate list) followed by ids[per][EXP_MAXC_BIG] u32 (corpus rows).
+__host__ __device__ inline size_t xreq_record_bytes(int per) { return (size_t)per * 8 + (size_t)per * EXP_MAXC_BIG * 4; }
+__device__ __forceinline__ u32* xreq_hdr(const CommDev& c, int owner, u32 E, int sender, int lq, int per) {
+  return reinterpret_cast<u32*>(comm_slot(c, owner, E) + (size_t)sender * xreq_record_bytes(per)) + 2 * lq;
+}
+__device__ __forceinline__ u32* xreq_ids(const CommDev& c, int owner, u32 E, int sender, int lq, int per) {
+  return reinterpret_cast<u32*>(comm_slot(c, owner, E) + (size_t)sender * xreq_record_bytes(per) + (size_t)per * 8) + (size_t)lq * EXP_MAXC_BIG;
+}
+// c_cos slot (in the HOME's window): cos[per][EXP_MAXC_BIG] f32, same positions as the home's parked candidate list
+__device__ __forceinline__ float* xcos(const CommDev& c, int home, u32 E, int lq) {
+  return reinterpret_cast<float*>(comm_slot(c, home, E)) + (size_t)lq * EXP_MAXC_BIG;
+}
+// c_out slot (in EVERY window): ids i64 [B][k] | score f32 | hop i32 | graph_norm f32 | dense_norm f32 | cos f32 | ncand i32 [B] | status i32 [B]
+__host__ __device__ inline size_t xout_bytes(int B, int k) { return (size_t)28 * B * k + (size_t)8 * B; }
+struct XOut { long long* ids; float* score; int* hop; float* gn; float* dn; float* cos; int* ncand; int* status; };
+__device__ __forceinline__ XOut xout(char* base, int B, int k) {
+  const size_t n = (size_t)B * k;
+  XOut o;
+  o.ids = reinterpret_cast<long long*>(base); o.score = reinterpret_cast<float*>(base + 8 * n);
+  o.hop = reinterpret_cast<int*>(base + 12 * n); o.gn = reinterpret_cast<float*>(base + 16 * n);
+  o.dn = reinterpret_cast<float*>(base + 20 * n); o.cos = reinterpret_cast<float*>(base + 24 * n);
+  o.ncand = reinterpret_cast<int*>(base + 28 * n); o.status = o.ncand + B;
+  return o;
+}
+__device__ __forceinline__ int row_owner(const ExpandParams& p, u32 row) {
+  const long long o = (long long)row / p.rows_per;
+  return (int)(o < p.c_req.world ? o : p.c_req.world - 1);
+}
 
 __device__ __forceinline__ float hop_decay(int d) {
   // graph_utils.py:87-94
@@ -151,9 +192,14 @@ __global__ void __launch_bounds__(BFS_THREADS) bfs_kernel(const ExpandParams p) 
   __shared__ u32 s_wsum[BFS_WARPS];
   __shared__ unsigned long long s_wwide[BFS_WARPS];
   __shared__ double s_qn[BFS_WARPS];
+  __shared__ int s_ocnt[B200R_MAX_PEERS], s_ooff[B200R_MAX_PEERS + 1], s_ofill[B200R_MAX_PEERS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool xchg = p.mode == 3;
+  u32 epoch = 0;
+  if (xchg) epoch = comm_send_begin(p.c_req);         // the owners have consumed the requests this slot held two exchanges ago
+  const int q_first = xchg ? p.q_lo : 0, q_last = xchg ? p.q_hi : p.B;
 
-  for (int q = blockIdx.x; q < p.B; q += gridDim.x) {
+  for (int q = q_first + blockIdx.x; q < q_last; q += gridDim.x) {
     if (RETRY_PASS && p.out_status[q] != kStatusRetry) continue;      // block-uniform
     __syncthreads();                                                  // the previous query of this CTA is done with smem
     for (int i = tid; i < HASH; i += BFS_THREADS) table[i] = EXP_EMPTY;
@@ -281,7 +327,11 @@ __global__ void __launch_bounds__(BFS_THREADS) bfs_kernel(const ExpandParams p) 
         p.ws.ncand[q] = 0;
         p.ws.nown[q] = 0;
       }
-      fill_no_result(p, q);
+      if (!xchg) fill_no_result(p, q);
+      else if (MAXC == EXP_MAXC_BIG && tid < p.c_req.world) {       // final overflow: every owner learns "no candidates"
+        u32* h = xreq_hdr(p.c_req, tid, epoch, p.c_req.rank, q - p.q_lo, p.per);
+        h[0] = 0u; h[1] = 0u;
+      }
       continue;
     }
     // park the list with the candidates this rank owns FIRST (the order inside a list carries no meaning: ranking breaks
@@ -289,6 +339,45 @@ __global__ void __launch_bounds__(BFS_THREADS) bfs_kernel(const ExpandParams p) 
     u32* cand_out = p.ws.cand + (size_t)q * EXP_MAXC_BIG;
     uint8_t* dist_out = p.ws.dist + (size_t)q * EXP_MAXC_BIG;
     const int nlevels = s_nlevels;
+    if (xchg) {
+      // exchange mode: the list is parked grouped by the rank that owns each candidate's row; every owner receives its
+      // sublist (corpus rows) and where it sits in this list, so that its cosines come back to the same positions
+      const int G = p.c_req.world, lq = q - p.q_lo;
+      if (tid < G) { s_ocnt[tid] = 0; s_ofill[tid] = 0; }
+      __syncthreads();
+      for (int c = tid; c < ncand; c += BFS_THREADS) {
+        u32 node = cand[c];
+        if (p.node_rows) {
+          const long long r = __ldg(p.node_rows + node);
+          node = (r >= 0 && r < 0xffffffffll) ? (u32)r : 0xfffffffeu;
+          cand[c] = node;                                           // from here on the list holds corpus rows
+        }
+        atomicAdd(&s_ocnt[row_owner(p, node)], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int run = 0;
+        for (int o = 0; o < G; ++o) { s_ooff[o] = run; run += s_ocnt[o]; }
+        s_ooff[G] = run;
+      }
+      __syncthreads();
+      for (int c = tid; c < ncand; c += BFS_THREADS) {
+        const u32 row = cand[c];
+        int d = 0;
+        while (d + 1 < nlevels && c >= s_level_end[d]) ++d;
+        const int o = row_owner(p, row);
+        const int j = atomicAdd(&s_ofill[o], 1);
+        cand_out[s_ooff[o] + j] = row;
+        dist_out[s_ooff[o] + j] = (uint8_t)min(d, 255);
+        xreq_ids(p.c_req, o, epoch, p.c_req.rank, lq, p.per)[j] = row;
+      }
+      if (tid < G) {
+        u32* h = xreq_hdr(p.c_req, tid, epoch, p.c_req.rank, lq, p.per);
+        h[0] = (u32)s_ocnt[tid]; h[1] = (u32)s_ooff[tid];
+      }
+      if (tid == 0) { p.ws.ncand[q] = ncand; p.ws.nown[q] = ncand; p.out_ncand[q] = ncand; p.out_status[q] = 0; }
+      continue;
+    }
     for (int c = tid; c < ncand; c += BFS_THREADS) {
       u32 node = cand[c];
       int d = 0;
@@ -316,6 +405,11 @@ __global__ void __launch_bounds__(BFS_THREADS) bfs_kernel(const ExpandParams p) 
       p.ws.seg_q[old >> 32] = (u32)q;
     }
   }
+  if (xchg) {
+    // the small instantiation only makes its stores visible; the persistent big one (always launched after it) signals
+    if (RETRY_PASS) comm_send_end(p.c_req, epoch, gridDim.x);
+    else __threadfence_system();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ K3b
@@ -328,12 +422,16 @@ __global__ void __launch_bounds__(GATHER_MAX_WARPS * 32, GATHER_CTAS_PER_SM) res
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
   float* qs = qs_all + (size_t)warp * dpad;          // this warp's current query, fp32
 
+  const bool xchg = p.mode == 3;
+  u32 e_req = 0, e_cos = 0;
+  if (xchg) { e_cos = comm_send_begin(p.c_cos); e_req = comm_recv_peek(p.c_req); }   // the plan kernel already waited for the requests
   const u64 packed = *p.ws.counter;
   const int nseg = (int)(packed >> 32);
   const u32 total = (u32)packed;
   const u64 W = (u64)gridDim.x * warps_per_cta, w = (u64)blockIdx.x * warps_per_cta + warp;
   const u32 g_lo = (u32)((u64)total * w / W), g_hi = (u32)((u64)total * (w + 1) / W);
-  if (g_lo >= g_hi) return;
+  do {
+  if (g_lo >= g_hi) break;
 
   // the reservation that contains group g_lo: the last one that starts at or before it (empty ones share a start)
   int seg = 0;
@@ -353,8 +451,11 @@ __global__ void __launch_bounds__(GATHER_MAX_WARPS * 32, GATHER_CTAS_PER_SM) res
   const size_t row_bytes = (size_t)p.D * sizeof(T);
   int q = -1, ncand = 0;
   float qinv = 1.0f, cmin = CUDART_INF_F, cmax = -CUDART_INF_F;
+  const u32* cand_src = nullptr;      // this query's candidate rows (parked list, or the request received from its home rank)
+  float* cos_dst = nullptr;           // where their cosines go (workspace, or the home rank's window)
 
   auto flush_minmax = [&]() {
+    if (xchg) return;                 // the home rank sees every cosine and takes the range itself
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       cmin = fminf(cmin, __shfl_xor_sync(kFullMask, cmin, o));
@@ -370,6 +471,14 @@ __global__ void __launch_bounds__(GATHER_MAX_WARPS * 32, GATHER_CTAS_PER_SM) res
     q = (int)__ldg(p.ws.seg_q + seg);
     ncand = p.ws.nown[q];          // the owned candidates are the first nown entries of the parked list
     qinv = p.ws.qinv[q];
+    if (xchg) {
+      const int home = q / p.per, lq = q - home * p.per;
+      cand_src = xreq_ids(p.c_req, p.c_req.rank, e_req, home, lq, p.per);
+      cos_dst = xcos(p.c_cos, home, e_cos, lq) + xreq_hdr(p.c_req, p.c_req.rank, e_req, home, lq, p.per)[1];
+    } else {
+      cand_src = p.ws.cand + (size_t)q * EXP_MAXC_BIG;
+      cos_dst = p.ws.cos + (size_t)q * EXP_MAXC_BIG;
+    }
     const QT* Qp = reinterpret_cast<const QT*>(p.Q) + (size_t)q * p.D;
     __syncwarp();
     // float4 "part" layout: the 4-element part `e/4` of 16-byte chunk `c` lives at q4[(e/4)*chunks + c], so a warp's 32
@@ -399,7 +508,7 @@ __global__ void __launch_bounds__(GATHER_MAX_WARPS * 32, GATHER_CTAS_PER_SM) res
     bool my_valid = false, my_have = false;
     float my_mult = 0.0f;
     if (lane < ROWS && c0 + lane < ncand) {
-      const long long node = (long long)__ldg(p.ws.cand + (size_t)q * EXP_MAXC_BIG + c0 + lane);
+      const long long node = (long long)cand_src[c0 + lane];
       const long long row = node - p.id_base;
       my_valid = true;
       my_have = row >= 0 && row < p.N;       // a graph node that is not a corpus row scores 0.0
@@ -440,11 +549,65 @@ __global__ void __launch_bounds__(GATHER_MAX_WARPS * 32, GATHER_CTAS_PER_SM) res
     }
     if (my_valid) {
       const float v = my_have ? (mine * my_mult) * qinv + 0.0f : 0.0f;
-      p.ws.cos[(size_t)q * EXP_MAXC_BIG + c0 + lane] = v;
+      cos_dst[c0 + lane] = v;
       cmin = fminf(cmin, v); cmax = fmaxf(cmax, v);
     }
   }
   flush_minmax();
+  } while (0);
+  if (xchg) {
+    comm_recv_end(p.c_req, e_req, gridDim.x);       // the requests have been read: their slot may be reused
+    comm_send_end(p.c_cos, e_cos, gridDim.x);       // every cosine of this rank is in its home's window
+  }
+}
+
+// exchange mode, owner side: wait for every home rank's requests, then lay the flat work list of the gather out over ALL
+// queries (query q's groups follow query q-1's) and note how many candidates of each query this rank owns.  One CTA.
+__global__ void __launch_bounds__(1024) gather_plan_kernel(const ExpandParams p) {
+  __shared__ u32 s_warp[32];
+  __shared__ u32 s_base;
+  const u32 E = comm_recv_begin(p.c_req);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int q0 = 0; q0 < p.B; q0 += 1024) {
+    const int q = q0 + tid;
+    u32 cnt = 0;
+    if (q < p.B) {
+      const int home = q / p.per, lq = q - home * p.per;
+      cnt = xreq_hdr(p.c_req, p.c_req.rank, E, home, lq, p.per)[0];
+      if (cnt > (u32)EXP_MAXC_BIG) cnt = 0;          // cannot happen; never index beyond a record
+      p.ws.nown[q] = (int)cnt;
+      if (p.metric != B200R_COS) p.ws.qinv[q] = 1.0f;
+    }
+    const u32 groups = (cnt + GATHER_ROWS - 1) / GATHER_ROWS;
+    u32 incl = groups;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(kFullMask, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    u32 wbase = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) { if (w < warp) wbase += s_warp[w]; tot += s_warp[w]; }
+    const u32 base = s_base;
+    if (q < p.B) { p.ws.seg_start[q] = base + wbase + incl - groups; p.ws.seg_q[q] = (u32)q; }
+    __syncthreads();
+    if (tid == 0) s_base = base + tot;
+    __syncthreads();
+  }
+  if (tid == 0) *p.ws.counter = ((u64)(u32)p.B << 32) | (u64)s_base;
+}
+
+// exchange mode, every rank: wait for all home ranks' results and hand them to the caller's arrays
+__global__ void __launch_bounds__(256) collect_outputs_kernel(const ExpandParams p) {
+  const u32 E = comm_recv_begin(p.c_out);
+  const XOut o = xout(comm_slot(p.c_out, p.c_out.rank, E), p.B, p.k);
+  const size_t n = (size_t)p.B * p.k, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = i0; i < n; i += step) {
+    p.out_ids[i] = o.ids[i]; p.out_scores[i] = o.score[i]; p.out_hops[i] = o.hop[i];
+    p.out_gn[i] = o.gn[i]; p.out_dn[i] = o.dn[i]; p.out_cos[i] = o.cos[i];
+  }
+  for (size_t q = i0; q < (size_t)p.B; q += step) { p.out_ncand[q] = o.ncand[q]; p.out_status[q] = o.status[q]; }
+  comm_recv_end(p.c_out, E, gridDim.x);
 }
 
 // mode 1: the host all-reduces float (min, max) pairs
@@ -467,38 +630,62 @@ __global__ void __launch_bounds__(SEL_THREADS) fuse_select_kernel(const ExpandPa
   u64* sk = keys + MAXC;                                           // [kp2]
   u32* cand = reinterpret_cast<u32*>(sk + p.kp2);                  // [MAXC]
   __shared__ int s_remaining, s_nout, s_done;
-  __shared__ float s_red[2][SEL_WARPS];
+  __shared__ float s_red[4][SEL_WARPS];
   __shared__ u32 hist[256];
   __shared__ u64 s_prefix;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool xchg = p.mode == 3;
+  u32 e_cos = 0, e_out = 0;
+  if (xchg) { e_cos = comm_recv_begin(p.c_cos); e_out = comm_send_begin(p.c_out); }   // every owner's cosines have arrived
+  const int q_first = xchg ? p.q_lo : 0, q_last = xchg ? p.q_hi : p.B;
 
-  for (int q = blockIdx.x; q < p.B; q += gridDim.x) {
-    if (p.out_status[q] != 0) continue;                            // overflow was reported by the BFS (block-uniform)
+  for (int q = q_first + blockIdx.x; q < q_last; q += gridDim.x) {
+    if (p.out_status[q] != 0) {                                    // overflow was reported by the BFS (block-uniform)
+      if (xchg && !BIG) {                                          // ... and every rank must learn it
+        const int st = p.out_status[q], nc = p.out_ncand[q];
+        for (int g = 0; g < p.c_out.world; ++g) {
+          const XOut o = xout(comm_slot(p.c_out, g, e_out), p.B, p.k);
+          for (int i = tid; i < p.k; i += SEL_THREADS) {
+            const size_t oi = (size_t)q * p.k + i;
+            o.score[oi] = -CUDART_INF_F; o.ids[oi] = -1; o.hop[oi] = -1; o.gn[oi] = 0; o.dn[oi] = 0; o.cos[oi] = 0;
+          }
+          if (tid == 0) { o.ncand[q] = nc; o.status[q] = st; }
+        }
+      }
+      continue;
+    }
     const int ncand = p.ws.ncand[q];
     if (BIG != (ncand > EXP_MAXC_SMALL)) continue;                 // the other instantiation ranks this query
     __syncthreads();
     const u32* cand_in = p.ws.cand + (size_t)q * EXP_MAXC_BIG;
-    const float* cos_in = p.ws.cos + (size_t)q * EXP_MAXC_BIG;
+    const float* cos_in = xchg ? xcos(p.c_cos, p.c_cos.rank, e_cos, q - p.q_lo) : p.ws.cos + (size_t)q * EXP_MAXC_BIG;
     const uint8_t* dist_in = p.ws.dist + (size_t)q * EXP_MAXC_BIG;
 
     // ---- min/max of both channels (retrieval_backend.py:296-301) ----------------------------------
-    float gmin = CUDART_INF_F, gmax = -CUDART_INF_F;
+    float gmin = CUDART_INF_F, gmax = -CUDART_INF_F, xmin = CUDART_INF_F, xmax = -CUDART_INF_F;
     for (int c = tid; c < ncand; c += SEL_THREADS) {
       cand[c] = cand_in[c];
       const float gv = hop_decay(dist_in[c]);
       gmin = fminf(gmin, gv); gmax = fmaxf(gmax, gv);
+      if (xchg) { const float cv = cos_in[c]; xmin = fminf(xmin, cv); xmax = fmaxf(xmax, cv); }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       gmin = fminf(gmin, __shfl_xor_sync(kFullMask, gmin, o)); gmax = fmaxf(gmax, __shfl_xor_sync(kFullMask, gmax, o));
+      xmin = fminf(xmin, __shfl_xor_sync(kFullMask, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(kFullMask, xmax, o));
     }
-    if (lane == 0) { s_red[0][warp] = gmin; s_red[1][warp] = gmax; }
+    if (lane == 0) { s_red[0][warp] = gmin; s_red[1][warp] = gmax; s_red[2][warp] = xmin; s_red[3][warp] = xmax; }
     if (tid == 0) { s_prefix = 0; s_remaining = p.k; s_nout = 0; s_done = 0; }
     for (int i = tid; i < p.kp2; i += SEL_THREADS) sk[i] = 0;
     __syncthreads();
-    for (int w = 0; w < SEL_WARPS; ++w) { gmin = fminf(gmin, s_red[0][w]); gmax = fmaxf(gmax, s_red[1][w]); }
+    for (int w = 0; w < SEL_WARPS; ++w) {
+      gmin = fminf(gmin, s_red[0][w]); gmax = fmaxf(gmax, s_red[1][w]);
+      xmin = fminf(xmin, s_red[2][w]); xmax = fmaxf(xmax, s_red[3][w]);
+    }
     float cmin, cmax;
-    if (p.mode == 2) {
+    if (xchg) {
+      cmin = xmin; cmax = xmax;                                    // this rank holds every candidate's cosine
+    } else if (p.mode == 2) {
       cmin = p.minmax[2 * q]; cmax = p.minmax[2 * q + 1];          // all-reduced across the ranks
     } else {
       const u32 lo = p.ws.mm[2 * q], hi = p.ws.mm[2 * q + 1];
@@ -583,6 +770,9 @@ __global__ void __launch_bounds__(SEL_THREADS) fuse_select_kernel(const ExpandPa
     const int nwin = min(min(ncand, p.k), s_nout);
     for (int i = warp; i < p.k; i += SEL_WARPS) {
       const size_t o = (size_t)q * p.k + i;
+      float v_score = -CUDART_INF_F, v_gn = 0.0f, v_dn = 0.0f, v_cos = 0.0f;
+      long long v_id = -1;
+      int v_hop = -1;
       if (i < nwin) {
         const u64 key = sk[i];
         const u32 node = key_id(key);
@@ -592,20 +782,30 @@ __global__ void __launch_bounds__(SEL_THREADS) fuse_select_kernel(const ExpandPa
           const u32 hit = __ballot_sync(kFullMask, c < ncand && cand[c] == node);
           if (hit) slot = base + __ffs(hit) - 1;
         }
+        const float cv = cos_in[slot];             // warp-uniform address
+        const int hd = dist_in[slot];
+        v_score = key_score(key); v_id = (long long)node; v_hop = hd;
+        v_gn = g_flat ? 0.0f : (hop_decay(hd) - gmin) / g_den;
+        v_dn = c_flat ? 0.0f : (cv - cmin) / c_den;
+        v_cos = cv;
+      }
+      if (!xchg) {
         if (lane == 0) {
-          const float cv = cos_in[slot];
-          const int hd = dist_in[slot];
-          p.out_scores[o] = key_score(key);
-          p.out_ids[o] = (long long)node;
-          p.out_hops[o] = hd;
-          p.out_gn[o] = g_flat ? 0.0f : (hop_decay(hd) - gmin) / g_den;
-          p.out_dn[o] = c_flat ? 0.0f : (cv - cmin) / c_den;
-          p.out_cos[o] = cv;
+          p.out_scores[o] = v_score; p.out_ids[o] = v_id; p.out_hops[o] = v_hop; p.out_gn[o] = v_gn; p.out_dn[o] = v_dn; p.out_cos[o] = v_cos;
         }
-      } else if (lane == 0) {
-        p.out_scores[o] = -CUDART_INF_F; p.out_ids[o] = -1; p.out_hops[o] = -1; p.out_gn[o] = 0; p.out_dn[o] = 0; p.out_cos[o] = 0;
+      } else if (lane < p.c_out.world) {           // lane g stores the winner into rank g's output slot
+        const XOut x = xout(comm_slot(p.c_out, lane, e_out), p.B, p.k);
+        x.score[o] = v_score; x.ids[o] = v_id; x.hop[o] = v_hop; x.gn[o] = v_gn; x.dn[o] = v_dn; x.cos[o] = v_cos;
       }
     }
+    if (xchg && tid < p.c_out.world) {
+      const XOut x = xout(comm_slot(p.c_out, tid, e_out), p.B, p.k);
+      x.ncand[q] = ncand; x.status[q] = 0;
+    }
+  }
+  if (xchg) {
+    if (BIG) { comm_recv_end(p.c_cos, e_cos, gridDim.x); comm_send_end(p.c_out, e_out, gridDim.x); }
+    else __threadfence_system();
   }
 }
 
@@ -644,14 +844,18 @@ int validate_csr(const long long* row_ptr, const int* col_idx, long long V, long
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+// queries this rank's per-query kernels (BFS, fusion) work on: all of them, or its home queries in exchange mode
+static int work_queries(const ExpandParams& p) { return p.mode == 3 ? std::max(p.q_hi - p.q_lo, 0) : p.B; }
+
 template <typename QT>
 static int launch_bfs(const ExpandParams& p, cudaStream_t st) {
+  const int nq = std::max(work_queries(p), 1);       // exchange mode: a rank without home queries still signals its peers
   B200R_CUDA_CHECK(cudaFuncSetAttribute(bfs_kernel<QT, EXP_MAXC_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bfs_smem_bytes(EXP_MAXC_SMALL)));
-  bfs_kernel<QT, EXP_MAXC_SMALL><<<p.B, BFS_THREADS, bfs_smem_bytes(EXP_MAXC_SMALL), st>>>(p);
+  bfs_kernel<QT, EXP_MAXC_SMALL><<<nq, BFS_THREADS, bfs_smem_bytes(EXP_MAXC_SMALL), st>>>(p);
   count_launch();
   // persistent: only the queries that overflowed the small instantiation do any work
   B200R_CUDA_CHECK(cudaFuncSetAttribute(bfs_kernel<QT, EXP_MAXC_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bfs_smem_bytes(EXP_MAXC_BIG)));
-  bfs_kernel<QT, EXP_MAXC_BIG><<<std::min(p.B, EXP_PERSISTENT_CTAS), BFS_THREADS, bfs_smem_bytes(EXP_MAXC_BIG), st>>>(p);
+  bfs_kernel<QT, EXP_MAXC_BIG><<<std::min(nq, EXP_PERSISTENT_CTAS), BFS_THREADS, bfs_smem_bytes(EXP_MAXC_BIG), st>>>(p);
   count_launch();
   return B200R_OK;
 }
@@ -680,12 +884,40 @@ static int launch_gather(const ExpandParams& p, cudaStream_t st) {
 
 static int launch_select(const ExpandParams& p, cudaStream_t st) {
   if (select_smem_bytes(EXP_MAXC_BIG, p.kp2) > 220 * 1024) { set_error("expand_rescore: k=%d too large for shared memory", p.k); return B200R_EINVAL; }
+  const int nq = std::max(work_queries(p), 1);
   B200R_CUDA_CHECK(cudaFuncSetAttribute(fuse_select_kernel<EXP_MAXC_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_smem_bytes(EXP_MAXC_SMALL, p.kp2)));
-  fuse_select_kernel<EXP_MAXC_SMALL><<<p.B, SEL_THREADS, select_smem_bytes(EXP_MAXC_SMALL, p.kp2), st>>>(p);
+  fuse_select_kernel<EXP_MAXC_SMALL><<<nq, SEL_THREADS, select_smem_bytes(EXP_MAXC_SMALL, p.kp2), st>>>(p);
   count_launch();
   B200R_CUDA_CHECK(cudaFuncSetAttribute(fuse_select_kernel<EXP_MAXC_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_smem_bytes(EXP_MAXC_BIG, p.kp2)));
-  fuse_select_kernel<EXP_MAXC_BIG><<<std::min(p.B, EXP_PERSISTENT_CTAS), SEL_THREADS, select_smem_bytes(EXP_MAXC_BIG, p.kp2), st>>>(p);
+  fuse_select_kernel<EXP_MAXC_BIG><<<std::min(nq, EXP_PERSISTENT_CTAS), SEL_THREADS, select_smem_bytes(EXP_MAXC_BIG, p.kp2), st>>>(p);
   count_launch();
+  return B200R_OK;
+}
+
+// exchange mode runs in four phases so that a host driving several ranks from one thread can issue phase i on every rank
+// before phase i+1 on any (a kernel never waits for a kernel that has not been launched):
+//   1  BFS of the home queries, candidates stored into their owners' windows
+//   2  owners: plan + gather / re-score, cosines stored into the home ranks' windows
+//   3  home: fusion + top-k, results stored into every rank's window
+//   4  every rank: results -> the caller's arrays
+template <typename T>
+static int launch_expand_phase_t(const ExpandParams& p, int phase, int qdtype, cudaStream_t st) {
+  typedef typename QueryType<T>::type QT;
+  int rc = B200R_OK;
+  if (phase == 1) {
+    if ((rc = launch_bfs<QT>(p, st)) != B200R_OK) return rc;
+  } else if (phase == 2) {
+    if (p.metric == B200R_COS && (rc = launch_query_inv_norm(p.Q, p.B, p.D, qdtype, p.ws.qinv, st)) != B200R_OK) return rc;
+    gather_plan_kernel<<<1, 1024, 0, st>>>(p);
+    count_launch();
+    if ((rc = launch_gather<T>(p, st)) != B200R_OK) return rc;
+  } else if (phase == 3) {
+    if ((rc = launch_select(p, st)) != B200R_OK) return rc;
+  } else {
+    collect_outputs_kernel<<<2 * kNumSMs, 256, 0, st>>>(p);
+    count_launch();
+  }
+  B200R_CUDA_CHECK(cudaGetLastError());
   return B200R_OK;
 }
 
@@ -707,12 +939,71 @@ static int launch_expand_t(const ExpandParams& p, cudaStream_t st) {
   return B200R_OK;
 }
 
+size_t expand_xchg_req_bytes(int per) { return align_up(xreq_record_bytes(per), 16); }
+size_t expand_xchg_cos_bytes(int per) { return (size_t)per * EXP_MAXC_BIG * 4; }
+size_t expand_xchg_out_bytes(int B, int k) { return xout_bytes(B, k); }
+
+static void fill_params(ExpandParams& p, const Index* ix, const Graph* g, const void* Q, const int64_t* seeds, int B, int S, int window,
+                        float alpha_dense, float alpha_graph, int k, float* out_scores, int64_t* out_ids, int32_t* out_hops,
+                        float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand, int32_t* out_status, void* ws) {
+  memset(&p, 0, sizeof(p));
+  p.X = ix->X; p.Q = Q; p.row_mult = ix->row_mult;
+  p.row_ptr = reinterpret_cast<const long long*>(g->row_ptr); p.col_idx = g->col_idx;
+  p.node_rows = reinterpret_cast<const long long*>(g->node_rows);
+  p.seeds = reinterpret_cast<const long long*>(seeds);
+  p.N = ix->N; p.V = g->V; p.id_base = ix->id_base;
+  p.D = ix->D; p.B = B; p.S = S; p.window = window; p.k = k; p.metric = ix->metric;
+  p.kp2 = 2; while (p.kp2 < k) p.kp2 <<= 1;
+  p.alpha_dense = alpha_dense; p.alpha_graph = alpha_graph;
+  p.out_scores = out_scores; p.out_ids = reinterpret_cast<long long*>(out_ids); p.out_hops = out_hops;
+  p.out_gn = out_gn; p.out_dn = out_dn; p.out_cos = out_cos; p.out_ncand = out_ncand; p.out_status = out_status;
+  p.ws = carve_ws(ws, B);
+}
+
+int launch_expand_rescore_exchange(const Index* ix, const Graph* g, const Comm* comm, const void* Q, const int64_t* seeds, int B, int S,
+                                   int window, float alpha_dense, float alpha_graph, int k, int64_t n_total_rows, float* out_scores,
+                                   int64_t* out_ids, int32_t* out_hops, float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand,
+                                   int32_t* out_status, void* ws, int phase, cudaStream_t st) {
+  if (B > (1 << 20)) { set_error("expand_rescore: at most %d queries per call", 1 << 20); return B200R_EINVAL; }
+  if (phase < 1 || phase > 4) { set_error("phase must be 1..4"); return B200R_EINVAL; }
+  if (n_total_rows <= 0) { set_error("n_total_rows must be > 0"); return B200R_EINVAL; }
+  ExpandParams p;
+  fill_params(p, ix, g, Q, seeds, B, S, window, alpha_dense, alpha_graph, k, out_scores, out_ids, out_hops, out_gn, out_dn, out_cos,
+              out_ncand, out_status, ws);
+  p.mode = 3;
+  p.own_lo = INT64_MIN; p.own_hi = INT64_MAX;          // the home rank ranks every candidate of its queries
+  const int G = comm->world;
+  p.per = (B + G - 1) / G;
+  p.q_lo = std::min(B, comm->rank * p.per);
+  p.q_hi = std::min(B, p.q_lo + p.per);
+  p.rows_per = (n_total_rows + G - 1) / G;
+  int rc;
+  if ((rc = comm_dev(comm, kChanGraphReq, expand_xchg_req_bytes(p.per), &p.c_req))) return rc;
+  if ((rc = comm_dev(comm, kChanGraphCos, 0, &p.c_cos))) return rc;
+  if ((rc = comm_dev(comm, kChanGraphOut, 0, &p.c_out))) return rc;
+  if (expand_xchg_cos_bytes(p.per) > p.c_cos.slot_bytes || expand_xchg_out_bytes(B, k) > p.c_out.slot_bytes) {
+    set_error("graph exchange of (B=%d, k=%d) exceeds the comm's windows (created for max_B=%d, max_graph_k=%d)", B, k, comm->max_B, comm->max_graph_k);
+    return B200R_EINVAL;
+  }
+  if (phase == 1) B200R_CUDA_CHECK(cudaMemsetAsync(p.ws.counter, 0, sizeof(u64), st));
+  const int qdtype = ix->dtype == B200R_I8 ? B200R_F32 : ix->dtype;
+  switch (ix->dtype) {
+    case B200R_BF16: return launch_expand_phase_t<__nv_bfloat16>(p, phase, qdtype, st);
+    case B200R_F16: return launch_expand_phase_t<__half>(p, phase, qdtype, st);
+    case B200R_F32: return launch_expand_phase_t<float>(p, phase, qdtype, st);
+    case B200R_I8: return launch_expand_phase_t<int8_t>(p, phase, qdtype, st);
+  }
+  set_error("bad dtype");
+  return B200R_EINVAL;
+}
+
 int launch_expand_rescore(const Index* ix, const Graph* g, const void* Q, const int64_t* seeds, int B, int S, int window,
                           float alpha_dense, float alpha_graph, int k, float* out_scores, int64_t* out_ids, int32_t* out_hops,
                           float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand, int32_t* out_status, int mode,
                           int64_t own_lo, int64_t own_hi, void* ws, float* minmax, cudaStream_t st) {
   if (B > (1 << 20)) { set_error("expand_rescore: at most %d queries per call", 1 << 20); return B200R_EINVAL; }
   ExpandParams p;
+  memset(&p, 0, sizeof(p));
   p.X = ix->X; p.Q = Q; p.row_mult = ix->row_mult;
   p.row_ptr = reinterpret_cast<const long long*>(g->row_ptr); p.col_idx = g->col_idx;
   p.node_rows = reinterpret_cast<const long long*>(g->node_rows);

@@ -127,7 +127,7 @@ int launch_select_lists(const Index* ix, const SearchPlan& p, void* ws, float* o
 
 // ---- shard exchange (comm.cu) ----------------------------------------------------------------------------------
 constexpr uint32_t kCommMagic = 0xB200A003u;
-constexpr int kChanDense = 0, kChanGraphRange = 1, kChanGraphRecords = 2, kChanSpare = 3;
+constexpr int kChanDense = 0, kChanGraphReq = 1, kChanGraphCos = 2, kChanGraphOut = 3;
 struct Comm {
   uint32_t magic;
   int device, rank, world;
@@ -155,6 +155,15 @@ int launch_expand_rescore(const Index* ix, const Graph* g, const void* Q, const 
                           float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand, int32_t* out_status, int mode,
                           int64_t own_lo, int64_t own_hi, void* ws, float* minmax, cudaStream_t st);
 size_t expand_workspace_bytes(int B);
+// graph stage over the exchange (csr_expand.cu, mode 3): slot sizes of its three channels and the phased launcher
+size_t expand_xchg_req_bytes(int per);          // one home rank's request record for `per` queries
+size_t expand_xchg_cos_bytes(int per);          // a home rank's cosine slot
+size_t expand_xchg_out_bytes(int B, int k);     // the result slot
+struct Comm;
+int launch_expand_rescore_exchange(const Index* ix, const Graph* g, const Comm* comm, const void* Q, const int64_t* seeds, int B, int S,
+                                   int window, float alpha_dense, float alpha_graph, int k, int64_t n_total_rows, float* out_scores,
+                                   int64_t* out_ids, int32_t* out_hops, float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand,
+                                   int32_t* out_status, void* ws, int phase, cudaStream_t st);
 int encode_tmap_2d(CUtensorMap* tm, int dtype, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer);
 
 }  // namespace b200r

@@ -270,6 +270,62 @@ def expand_rescore(index: DenseIndex, graph: PassageGraph, Q: torch.Tensor, seed
     return out
 
 
+def _expand_outputs(dev, B: int, k: int) -> Dict[str, torch.Tensor]:
+    return {
+        "score": torch.empty((B, k), dtype=torch.float32, device=dev),
+        "id": torch.empty((B, k), dtype=torch.int64, device=dev),
+        "hop": torch.empty((B, k), dtype=torch.int32, device=dev),
+        "score_graph_norm": torch.empty((B, k), dtype=torch.float32, device=dev),
+        "score_dense_norm": torch.empty((B, k), dtype=torch.float32, device=dev),
+        "cos": torch.empty((B, k), dtype=torch.float32, device=dev),
+        "ncand": torch.empty((B,), dtype=torch.int32, device=dev),
+        "status": torch.empty((B,), dtype=torch.int32, device=dev),
+    }
+
+
+def _exchange_phase(index: DenseIndex, graph: "PassageGraph", comm, Q, seeds, window, alpha_dense, alpha_graph, k, n_total, phase, ws, out):
+    B, S = int(seeds.shape[0]), int(seeds.shape[1])
+    with torch.cuda.device(index.device):
+        N.check(N.load().b200r_expand_rescore_exchange(
+            index.handle, graph.handle, comm.handle, Q.data_ptr(), seeds.data_ptr(), B, S, int(window), float(alpha_dense),
+            float(alpha_graph), int(k), int(n_total), int(phase), ws.data_ptr(), ws.numel(),
+            out["score"].data_ptr(), out["id"].data_ptr(), out["hop"].data_ptr(), out["score_graph_norm"].data_ptr(),
+            out["score_dense_norm"].data_ptr(), out["cos"].data_ptr(), out["ncand"].data_ptr(), out["status"].data_ptr(),
+            _stream_ptr(index.device)))
+
+
+def expand_rescore_exchange(index: DenseIndex, graph: "PassageGraph", comm, Q: torch.Tensor, seeds: torch.Tensor, window: int,
+                            alpha_dense: float, alpha_graph: float, k: int, n_total_rows: int) -> Dict[str, torch.Tensor]:
+    """Graph stage of ONE rank of a row-sharded corpus over the C-ABI exchange (one process per GPU): queries sharded by
+    home rank, candidates by owner rank, every transfer a peer store from inside the kernels (b200r_expand_rescore_exchange).
+    Every rank passes the same Q / seeds (global row or local node ids) and gets the same [B, k] results."""
+    _require_cuda(Q, "Q")
+    _require_cuda(seeds, "seeds")
+    B = int(seeds.shape[0])
+    out = _expand_outputs(index.device, B, k)
+    ws = torch.empty(int(N.load().b200r_expand_workspace_bytes(B)), dtype=torch.uint8, device=index.device)
+    _exchange_phase(index, graph, comm, Q, seeds, window, alpha_dense, alpha_graph, k, n_total_rows, 0, ws, out)
+    return out
+
+
+def expand_rescore_exchange_all(shards, graphs, comms, n_total_rows: int, Q_host: torch.Tensor, seeds_host: torch.Tensor, window: int,
+                                alpha_dense: float, alpha_graph: float, k: int) -> Dict[str, torch.Tensor]:
+    """The same stage with ONE host thread driving every rank (B200RetrievalBackend(devices=[...])): host Q / seeds are
+    handed to every device, then phase p is issued on every rank before phase p+1 on any; rank 0's results are returned."""
+    B = int(seeds_host.shape[0])
+    Qd = [Q_host.to(s.device, non_blocking=True) for s in shards]
+    Sd = [seeds_host.to(s.device, non_blocking=True) for s in shards]
+    outs = [_expand_outputs(s.device, B, k) for s in shards]
+    nbytes = int(N.load().b200r_expand_workspace_bytes(B))
+    wss = [torch.empty(nbytes, dtype=torch.uint8, device=s.device) for s in shards]
+    for phase in (1, 2, 3, 4):
+        for g, s in enumerate(shards):
+            _exchange_phase(s, graphs[g], comms[g], Qd[g], Sd[g], window, alpha_dense, alpha_graph, k, n_total_rows, phase, wss[g], outs[g])
+    for s in shards:
+        torch.cuda.synchronize(s.device)       # the windows / workspaces of all ranks stay alive until every rank is done
+    return outs[0]
+
+
 class ExpandShardState:
     """Device buffers of one rank's share of a sharded expand_rescore (see sharded.ShardedGraphStage).  The six [B, k]
     outputs are views of ONE packed record [id i64 | score f32 | hop i32 | graph_norm f32 | dense_norm f32 | cos f32]

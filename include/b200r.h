@@ -219,6 +219,25 @@ int b200r_expand_rescore_sharded(uint64_t index, uint64_t graph, const void* Q, 
                                  int32_t* out_hops, float* out_graph_norm, float* out_dense_norm, float* out_cos,
                                  int32_t* out_ncand, int32_t* out_status, void* stream);
 
+/* The same stage with the QUERIES sharded over the ranks as well, entirely over the exchange (no NCCL collective, no
+ * host reduction): every rank passes the same Q / seeds and receives the same [B, k] results.
+ *   phase 1  the HOME rank of a query (q / ceil(B/world)) runs its BFS and stores, for every rank, the candidates whose
+ *            corpus rows that rank OWNS (row / ceil(n_total_rows/world)) into that rank's window;
+ *   phase 2  every rank gathers + re-scores the candidates it received (the HBM-bound part, now 1/world of the work per
+ *            rank) and stores each cosine into the home rank's window, at the candidate's position in the home's list;
+ *   phase 3  the home rank min-max-normalises, fuses and ranks its queries (it now holds every cosine, so the
+ *            reference's per-query min/max, retrieval_backend.py:296-301, needs no reduction) and stores the results
+ *            into every rank's window;
+ *   phase 4  every rank copies the results into the caller's arrays.
+ * phase = 0 runs all four (one process per GPU); a host thread that drives several ranks issues phase p on every rank
+ * before phase p+1 on any.  The comm must have been created with max_graph_k >= k and max_B >= B.  Node ids reported
+ * are corpus rows; `workspace` as for b200r_expand_rescore. */
+int b200r_expand_rescore_exchange(uint64_t index, uint64_t graph, uint64_t comm, const void* Q, const int64_t* seeds, int32_t B,
+                                  int32_t S, int32_t window, float alpha_dense, float alpha_graph, int32_t k, int64_t n_total_rows,
+                                  int32_t phase, void* workspace, size_t workspace_bytes, float* out_scores, int64_t* out_ids,
+                                  int32_t* out_hops, float* out_graph_norm, float* out_dense_norm, float* out_cos, int32_t* out_ncand,
+                                  int32_t* out_status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

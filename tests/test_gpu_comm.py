@@ -150,6 +150,19 @@ def _ipc_worker(rank, world, port, tmpdir, ret):
         s4, i4 = ShardedDenseIndex(local, exchange="nccl").search(Q, k)
         assert torch.equal(i4, i) and torch.equal(s4, s)
         sh.comm.check()
+        # graph stage over the exchange, one rank per process: home / owner sharding, all phases in one call
+        from a_modular_rag_framework_b200 import PassageGraph
+        from a_modular_rag_framework_b200.index import expand_rescore_exchange
+        from tests.helpers_graph import check_graph_query
+        row_ptr, col_idx = O.csr_from_edges(N, rng.integers(0, N, 4 * N), rng.integers(0, N, 4 * N))
+        graph = PassageGraph(torch.from_numpy(row_ptr).to(dev), torch.from_numpy(col_idx).to(dev))
+        gcomm = ShardComm.from_process_group(rank, B, k, max_graph_k=10)
+        seeds = i[:, :8].contiguous()
+        for _ in range(3):
+            out = expand_rescore_exchange(local, graph, gcomm, Q, seeds, 2, 0.4, 0.2, 10, N)
+        for b in range(0, B, 3):
+            check_graph_query(out, b, Qn[b], Xn, row_ptr, col_idx, seeds[b].cpu().numpy(), 2, 0.4, 0.2, 10)
+        gcomm.check()
         ret[rank] = True
     finally:
         dist.destroy_process_group()
@@ -170,3 +183,76 @@ def test_two_processes_over_cuda_ipc(tmp_path):
         p.join(300)
         assert p.exitcode == 0
     assert ret.get(0) and ret.get(1)
+
+
+@pytest.mark.parametrize("G,B,V,E,D,S,k,window", [
+    (4, 16, 30000, 120000, 64, 20, 10, 2),
+    (3, 50, 20000, 60000, 96, 8, 25, 2),
+    (8, 5, 9000, 30000, 64, 6, 8, 3),          # fewer queries than ranks: some ranks have no home query
+    (2, 33, 5000, 0, 32, 4, 6, 2),             # no edges at all: candidates == seeds
+])
+def test_graph_stage_over_the_exchange_equals_single_gpu(G, B, V, E, D, S, k, window):
+    """b200r_expand_rescore_exchange: queries sharded by home rank, candidates by owner rank, cosines returned to the home
+    rank, results stored into every rank's window -- must reproduce the single-launch stage and the oracle."""
+    from a_modular_rag_framework_b200 import DenseIndex, PassageGraph, expand_rescore
+    from a_modular_rag_framework_b200.comm import ShardComm
+    from a_modular_rag_framework_b200.index import expand_rescore_exchange_all
+    from tests.helpers_graph import check_graph_query
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(G * 100 + B)
+    row_ptr, col_idx = O.csr_from_edges(V, rng.integers(0, V, E), rng.integers(0, V, E))
+    N = V - 300                                               # the last 300 nodes have no corpus row (score 0.0)
+    Xn = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((N, D)).astype(np.float32)))
+    Qn = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((B, D)).astype(np.float32)))
+    seeds = rng.integers(0, V, size=(B, S))
+    seeds[:, -1] = -1
+    X = torch.from_numpy(Xn).to(dev).to(torch.bfloat16)
+    Q = torch.from_numpy(Qn).to(dev).to(torch.bfloat16)
+    graph = PassageGraph(torch.from_numpy(row_ptr).to(dev), torch.from_numpy(col_idx).to(dev))
+    ref = expand_rescore(DenseIndex(X), graph, Q, torch.from_numpy(seeds).to(dev), window, 0.4, 0.2, k)
+    shards = _shards(X, G)
+    comms = ShardComm.init_all([0] * G, max_B=B, max_k=k, max_graph_k=k)
+    for rep in range(3):
+        out = expand_rescore_exchange_all(shards, [graph] * G, comms, N, Q.cpu(), torch.from_numpy(seeds), window, 0.4, 0.2, k)
+        for key in ("id", "hop", "ncand", "status"):
+            assert torch.equal(out[key], ref[key]), key
+        assert torch.equal(out["cos"], ref["cos"])
+        assert torch.allclose(out["score"], ref["score"], rtol=0, atol=1e-6)
+        assert torch.allclose(out["score_dense_norm"], ref["score_dense_norm"], rtol=0, atol=1e-6)
+    for c in comms:
+        c.check()
+    Xfull = np.concatenate([Xn, np.zeros((300, D), np.float32)])
+    for b in range(0, B, 7):
+        check_graph_query(out, b, Qn[b], Xfull, row_ptr, col_idx, seeds[b], window, 0.4, 0.2, k)
+
+
+def test_graph_exchange_overflow_and_mapped_graphs():
+    """A query whose frontier overflows is reported per query (status) to every rank while the others still get results;
+    mapped graphs (local node ids -> corpus rows) work through the exchange."""
+    from a_modular_rag_framework_b200 import DenseIndex, PassageGraph, expand_rescore
+    from a_modular_rag_framework_b200.comm import ShardComm
+    from a_modular_rag_framework_b200.index import expand_rescore_exchange_all
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(3)
+    V, D, G, k = 20000, 32, 3, 10
+    star_s, star_d = np.zeros(V - 1, dtype=np.int64), np.arange(1, V, dtype=np.int64)          # node 0 reaches everything
+    row_ptr, col_idx = O.csr_from_edges(V, star_s, star_d)
+    X = torch.from_numpy(rng.standard_normal((V, D)).astype(np.float32)).to(dev).to(torch.bfloat16)
+    Q = torch.from_numpy(rng.standard_normal((4, D)).astype(np.float32)).to(dev).to(torch.bfloat16)
+    seeds = np.array([[5], [0], [7], [9]])                                                    # query 1 overflows at window 1
+    graph = PassageGraph(torch.from_numpy(row_ptr).to(dev), torch.from_numpy(col_idx).to(dev))
+    comms = ShardComm.init_all([0] * G, max_B=8, max_k=k, max_graph_k=k)
+    shards = _shards(X, G)
+    out = expand_rescore_exchange_all(shards, [graph] * G, comms, V, Q.cpu(), torch.from_numpy(seeds), 1, 0.4, 0.2, k)
+    ref = expand_rescore(DenseIndex(X), graph, Q, torch.from_numpy(seeds).to(dev), 1, 0.4, 0.2, k, check_status=False)
+    assert out["status"].tolist() == ref["status"].tolist() and out["status"][1] != 0 and out["status"][0] == 0
+    assert torch.equal(out["id"], ref["id"]) and (out["id"][1] == -1).all()
+    # mapped graph: 3 local nodes in a chain whose corpus rows are far apart (different owner ranks)
+    rp, ci = O.csr_from_edges(3, np.array([0, 1]), np.array([1, 2]))
+    node_rows = np.array([19000, 40, 9000], dtype=np.int64)
+    mg = PassageGraph(torch.from_numpy(rp).to(dev), torch.from_numpy(ci).to(dev), torch.from_numpy(node_rows).to(dev))
+    sd = np.array([[0], [2], [1], [-1]])
+    out = expand_rescore_exchange_all(shards, [mg] * G, comms, V, Q.cpu(), torch.from_numpy(sd), 1, 0.4, 0.2, k)
+    ref = expand_rescore(DenseIndex(X), mg, Q, torch.from_numpy(sd).to(dev), 1, 0.4, 0.2, k)
+    assert torch.equal(out["id"], ref["id"]) and torch.equal(out["hop"], ref["hop"]) and torch.equal(out["cos"], ref["cos"])
+    assert sorted(out["id"][0][:2].tolist()) == [40, 19000] and out["ncand"].tolist() == [2, 2, 3, 0]
