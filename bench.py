@@ -9,6 +9,11 @@ configs[2], the configuration the metric is quoted on; it fits one GPU).  With N
 torchrun, one rank per GPU) the corpus is row-sharded, every rank searches its rows, the packed local
 top-k lists are all-gathered over NCCL and merged on the device: strong scaling.
 
+After the timed regions a RECALL leg checks the results those regions produced (device-resident and e2e) against the
+fp64 oracle over the whole (sharded) corpus, and the run exits non-zero if recall < 1 under the tie-aware rule; short
+secondary legs ("legs": batch-1 / batch-16 latency on the same shards, the graph stage of configs[4]) put the other
+north-star targets into the same line.
+
 Printed JSON line (rank 0): value = whole-job queries/s with the queries already in HBM;
 e2e = the same metric through the host-buffer C-ABI call (pinned host queries in, host results out,
 copies inside the timed region); roofline = the dominant kernel (tcgen05 GEMM + fused top-k) against
@@ -49,6 +54,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the secondary legs (batch 1 / batch 16 latency, graph stage)")
+    ap.add_argument("--graph-nodes", type=int, default=5_000_000, help="graph leg: nodes (= rows of its corpus, taken from the shards)")
+    ap.add_argument("--graph-edges", type=int, default=25_000_000, help="graph leg: directed edges before symmetrisation")
     ap.add_argument("--verify-queries", type=int, default=8,
                     help="queries of the last timed batch checked against the CPU oracle after the timed regions (0 = skip)")
     ap.add_argument("--exchange", default=os.environ.get("B200R_EXCHANGE", "abi"), choices=["abi", "nccl"],
@@ -188,6 +196,172 @@ def judge_results(ref_s, ref_i, results, k, rel_tol=1e-3):
         out[name] = {"recall": min(r["recall"] for r in rs), "recall_strict": min(r["recall_strict"] for r in rs),
                      "max_rel_score_err": max(r["max_rel_score_err"] for r in rs), "ok": all(r["ok"] for r in rs)}
     return out
+
+
+
+# ------------------------------------------------------------------------------------------------
+# secondary legs (after the contract timing, reported under "legs"): the other north-star targets on the SAME run
+# ------------------------------------------------------------------------------------------------
+def leg_small_batch(torch, index, world, Q, k, steps, n_local, dim, peaks, _native):
+    """Latency of ONE small batch end to end on the device (search + exchange + merge at N > 1), and the HBM roofline of
+    its tile kernel (one query tile: the corpus shard is streamed once)."""
+    B = int(Q.shape[1])
+    for i in range(3):
+        index.search(Q[i % Q.shape[0]], k)
+    torch.cuda.synchronize()
+    _native.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        index.search(Q[i % Q.shape[0]], k)
+    e1.record()
+    torch.cuda.synchronize()
+    kms, kn = _native.profile_read()
+    _native.profile_enable(False)
+    ms = e0.elapsed_time(e1) / steps
+    kms /= steps
+    gbs = n_local * dim * 2 / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+    peak = peaks.get("hbm_gbs", 6650.0)
+    return {"batch": B, "k": k, "ms_per_batch": ms, "queries_per_s": B / (ms * 1e-3), "tile_kernel_ms": kms, "launches_per_batch": kn / steps,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "algorithmic": "N_local*D*2 bytes per batch per GPU (corpus shard streamed once), tile kernel time only"}}
+
+
+def build_graph(torch, V, E, dev, seed=5):
+    """Synthetic passage graph, identical on every rank: E random directed edges, symmetrised, neighbours sorted."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    src = torch.randint(0, V, (E,), generator=g, device=dev)
+    dst = torch.randint(0, V, (E,), generator=g, device=dev)
+    a, b = torch.cat([src, dst]), torch.cat([dst, src])
+    del src, dst
+    order = torch.argsort(a * V + b)
+    a, b = a[order], b[order]
+    del order
+    row_ptr = torch.zeros(V + 1, dtype=torch.int64, device=dev)
+    row_ptr[1:] = torch.cumsum(torch.bincount(a, minlength=V), 0)
+    return row_ptr, b.to(torch.int32).contiguous()
+
+
+def leg_graph(torch, dist, a, X, rank, world, dev, Qd, peaks, _native, steps=20, warmup=5):
+    """BASELINE.json configs[4]: dense top-20 seeds -> 2-hop CSR expansion over a 5M-node / 50M-edge graph -> re-score ->
+    fused top-10.  The graph corpus is the first rows of every rank's shard (row-sharded like the dense corpus); at
+    N > 1 the stage runs over the library's exchange (queries sharded by home rank, candidates by owner rank)."""
+    from a_modular_rag_framework_b200 import DenseIndex, PassageGraph, expand_rescore
+    from a_modular_rag_framework_b200.comm import ShardComm
+    from a_modular_rag_framework_b200.index import expand_rescore_exchange
+    from a_modular_rag_framework_b200.sharded import ShardedDenseIndex, shard_rows
+    V = min(a.graph_nodes, a.rows // 2)
+    E = int(a.graph_edges * (V / a.graph_nodes))
+    B, S, k, window = a.batch, 20, 10, 2
+    glo, ghi = shard_rows(V, world, rank)
+    Xg = X[: max(ghi - glo, 1)]
+    local = DenseIndex(Xg, metric="cos", id_base=glo)
+    row_ptr, col = build_graph(torch, V, E, dev)
+    graph = PassageGraph(row_ptr, col)
+    nb = min(4, Qd.shape[0])
+    if world > 1:
+        comm = ShardComm.from_process_group(dev.index, B, S, max_graph_k=k)
+        sidx = ShardedDenseIndex(local, exchange="abi", comm=comm)
+        seeds = [sidx.search(Qd[i], S)[1].contiguous() for i in range(nb)]
+        run = lambda i: expand_rescore_exchange(local, graph, comm, Qd[i % nb], seeds[i % nb], window, 0.4, 0.2, k, V)   # noqa: E731
+    else:
+        seeds = [local.search(Qd[i], S)[1].contiguous() for i in range(nb)]
+        run = lambda i: expand_rescore(local, graph, Qd[i % nb], seeds[i % nb], window, 0.4, 0.2, k, check_status=False)   # noqa: E731
+    for i in range(warmup):
+        out = run(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    _native.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        out = run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    gms, gn = _native.profile_read()
+    _native.profile_enable(False)
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ncand = float(out["ncand"].float().mean().item())
+    gather_bytes = ncand * B * a.dim * 2 / world               # per GPU
+    peak = peaks.get("hbm_gbs", 6650.0)
+    gms = gms / max(gn, 1)
+    leg = {"workload": f"{V} nodes / {2 * E} adjacency entries, {a.dim}-d {a.dtype} rows, batch {B}, {S} dense seeds, window {window}, top-{k}",
+           "ms_per_batch": ms, "queries_per_s": B / (ms * 1e-3), "avg_candidates": ncand,
+           "overflowed_queries": int((out["status"] != 0).sum().item()),
+           "roofline": {"bound": "hbm", "achieved": gather_bytes / (gms * 1e-3) / 1e9 if gms > 0 else 0.0, "peak": peak, "unit": "GB/s",
+                        "frac": (gather_bytes / (gms * 1e-3) / 1e9 / peak) if gms > 0 else 0.0, "kernel": "rescore_gather_kernel",
+                        "kernel_ms_per_batch": gms,
+                        "algorithmic": "candidates*D*2 bytes per batch per GPU (random 1.5 KB rows), gather kernel time only"},
+           "stage_hbm_frac": gather_bytes / (ms * 1e-3) / 1e9 / peak}
+    # ---- parity of the last batch against the oracle (2 queries): BFS on the host CSR, rows fetched from their owners ----
+    try:
+        leg["verify"] = verify_graph_leg(torch, dist, out, Qd[(steps - 1) % nb], seeds[(steps - 1) % nb], row_ptr, col, Xg, glo, ghi,
+                                         V, rank, world, window, k)
+    except Exception as e:  # noqa: BLE001
+        leg["verify"] = {"ok": False, "error": repr(e)}
+    return leg
+
+
+def verify_graph_leg(torch, dist, out, Q, seeds, row_ptr, col, Xg, glo, ghi, V, rank, world, window, k, sel=(0, 1)):
+    import numpy as np
+    from oracle import retrieval_oracle as O
+    sel = [q for q in sel if q < Q.shape[0]]
+    rp = row_ptr.cpu().numpy() if rank == 0 else None
+    ci = col.cpu().numpy() if rank == 0 else None
+    dists = [O.bfs_expand(rp, ci, seeds[q].cpu().numpy(), window) for q in sel] if rank == 0 else None
+    if world > 1:
+        box = [dists]
+        dist.broadcast_object_list(box, src=0)
+        dists = box[0]
+    # every rank contributes the (dequantised) rows it owns
+    mine = {}
+    for d in dists:
+        for node in d:
+            if glo <= node < ghi and node not in mine:
+                mine[node] = Xg[node - glo].float().cpu().numpy()
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+    else:
+        parts = [mine]
+    if rank != 0:
+        return None
+    rows = {}
+    for p_ in parts:
+        rows.update(p_)
+    res = {"queries": len(sel), "ok": True, "max_rel_cos_err": 0.0, "ids_equal": True}
+    for j, q in enumerate(sel):
+        d = dists[j]
+        cand = sorted(d)
+        Xc = np.stack([rows[c] for c in cand]).astype(np.float64)
+        cos = O.score_matrix(Q[q].float().cpu().numpy()[None].astype(np.float64), Xc)[0]
+        dense = dict(zip(cand, cos.tolist()))
+        full = O.fuse_and_rank(dense, {c: O.decay(d[c]) for c in cand}, 0.4, 0.2, len(cand))
+        ref_of = {t[0]: t[1] for t in full}
+        scale = max(1e-30, float(np.max(np.abs(cos))))
+        rng_ = float(cos.max() - cos.min())
+        tol_f = (0.4 * 2 * 1e-3 * scale / rng_ if rng_ > 0 else 0.0) + 1e-6
+        ids = out["id"][q].cpu().numpy()[:k]
+        sc = out["score"][q].cpu().numpy()[:k]
+        cv = out["cos"][q].cpu().numpy()[:k]
+        hop = out["hop"][q].cpu().numpy()[:k]
+        if int(out["ncand"][q]) != len(cand):
+            res["ok"] = False
+        for i, nid in enumerate(ids.tolist()):
+            if nid not in d or hop[i] != d[nid] or abs(cv[i] - dense[nid]) > 1e-3 * scale or abs(sc[i] - ref_of[nid]) > tol_f:
+                res["ok"] = False
+                continue
+            res["max_rel_cos_err"] = float(max(res["max_rel_cos_err"], abs(float(cv[i]) - dense[nid]) / scale))
+            if nid != full[i][0]:
+                res["ids_equal"] = False
+                if abs(ref_of[nid] - full[i][1]) > tol_f:       # not a near-tie
+                    res["ok"] = False
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -476,6 +650,25 @@ def main():
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
                     "algorithmic": "N_local*D*2 bytes per corpus pass (one pass per <=4 queries), summed over the step"}
 
+    # ---- secondary legs: batch-1 / batch-16 latency on the same shards, graph stage (configs[4]) --------------------------
+    legs = None
+    if not a.no_legs:
+        legs = {}
+        if world > 1 and a.exchange == "abi" and getattr(index, "_outstanding", None) is not None:
+            index._outstanding.resolve()
+            index._outstanding = None
+        gs = torch.Generator(device="cpu").manual_seed(777)
+        for Bs in (1, 16):
+            Qs = torch.randn((8, Bs, a.dim), generator=gs, dtype=torch.float32)
+            Qs /= Qs.norm(dim=2, keepdim=True)
+            legs[f"batch{Bs}"] = leg_small_batch(torch, index, world, Qs.to(tdt).to(dev), a.k, 50, n_local, a.dim, peaks, _native)
+        try:
+            legs["graph"] = leg_graph(torch, dist, a, X, rank, world, dev, Qd, peaks, _native)
+        except Exception as e:  # noqa: BLE001
+            legs["graph"] = {"error": repr(e)}
+        if world > 1:
+            dist.barrier()
+
     # ---- CPU baseline on rank 0, N=1 only ---------------------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -498,14 +691,17 @@ def main():
                            "packed NCCL all-gather + device merge on a side stream, overlapped with the next batch's search"),
                        "l2": "corpus shard (>= 1.9 GB) is far larger than the 126 MB L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "per_rank": per_rank,
+            "clocks": clocks, "per_rank": per_rank, "legs": legs,
         }
         if verify is not None:
             line["recall"] = min(v["recall"] for v in verify.values() if isinstance(v, dict))
             line["max_rel_score_err"] = max(v["max_rel_score_err"] for v in verify.values() if isinstance(v, dict))
             line["verify"] = verify
             failed = not all(v["ok"] for v in verify.values() if isinstance(v, dict))
-        print(json.dumps(line), flush=True)
+        gv = ((legs or {}).get("graph") or {}).get("verify")
+        if isinstance(gv, dict) and not gv.get("ok", False):
+            failed = True
+        print(json.dumps(line, default=float), flush=True)
     if world > 1:
         flag = torch.tensor([1 if (rank == 0 and failed) else 0], device=dev, dtype=torch.int32)
         dist.all_reduce(flag, op=dist.ReduceOp.MAX)
