@@ -10,6 +10,7 @@
 #include <new>
 #include <cstdint>
 #include <vector>
+#include <string>
 
 namespace b200r {
 
@@ -39,6 +40,23 @@ void profile_end(cudaStream_t st) {
   else { cudaEventDestroy(g_prof_events.back()); g_prof_events.pop_back(); }
 }
 
+// ---- per-launch-site timeline (b200r_profile_enable(2) / b200r_profile_dump) ----
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof_recs;
+static bool g_prof_all = false;
+ProfScope::ProfScope(cudaStream_t stream, const char* name) : st(stream), slot(-1) {
+  if (!g_prof_all) return;
+  ProfRec r; r.name = name;
+  if (cudaEventCreate(&r.a) != cudaSuccess) return;
+  if (cudaEventCreate(&r.b) != cudaSuccess) { cudaEventDestroy(r.a); return; }
+  cudaEventRecord(r.a, st);
+  g_prof_recs.push_back(r);
+  slot = (int)g_prof_recs.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0 && slot < (int)g_prof_recs.size()) cudaEventRecord(g_prof_recs[slot].b, st);
+}
+
 // B200R_CTA_GROUP=1 forces the single-CTA tile kernel, B200R_Q_REPLICAS=0 disables the query-tile replication (A/B measurements)
 static int g_q_replicas = [] { const char* e = getenv("B200R_Q_REPLICAS"); return (e && e[0] == '0') ? 0 : 1; }();
 static int g_cta_group_max = [] { const char* e = getenv("B200R_CTA_GROUP"); return (e && e[0] == '1') ? 1 : 2; }();
@@ -66,12 +84,13 @@ int encode_tmap_2d(CUtensorMap* tm, int dtype, const void* base, uint64_t inner,
     fn = reinterpret_cast<EncodeTiledFn>(sym);
   }
   const cuuint64_t dims[2] = {inner, outer};
-  if (dtype != B200R_BF16 && dtype != B200R_F16 && dtype != B200R_I8) { set_error("no tensor map for dtype %d", dtype); return B200R_EINVAL; }
-  const cuuint64_t strides[1] = {inner * (dtype == B200R_I8 ? 1 : 2)};  // bytes
+  if (dtype < B200R_BF16 || dtype > B200R_I8) { set_error("no tensor map for dtype %d", dtype); return B200R_EINVAL; }
+  const cuuint64_t strides[1] = {inner * (dtype == B200R_I8 ? 1 : (dtype == B200R_F32 ? 4 : 2))};  // bytes
   const cuuint32_t box[2] = {box_inner, box_outer};
   const cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = (dtype == B200R_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                                 : (dtype == B200R_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+                                 : (dtype == B200R_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                    : (dtype == B200R_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8));
   // 256-byte L2 promotion measured best for the streamed corpus tiles (5.22 vs 5.10 TB/s with 128 B / none)
   CUresult r = fn(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -102,11 +121,13 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   // the corpus at 6.9-7.0 TB/s (105% of the measured copy bandwidth) for every B from 1 to 128 and is tensor-bound
   // beyond; the CUDA-core scan (6.7 TB/s at B=1, 5.6 at B=2) serves fp32 / int8 / odd-D corpora
   // int8 corpora: tcgen05 kind::i8 with the queries split into signed-byte limbs, 16-64 queries per corpus pass (rows_i8.cu)
-  const int i8_nq = ix->has_tmap_i8 ? rows_i8_nq(B, ix->D) : 0;
+  // fp32 corpora: tcgen05 kind::tf32 with both operands split into two exact tf32 pieces, 16 queries per corpus pass (rows_f32.cu)
+  const int f32_nq = ix->has_tmap_f32 ? rows_f32_nq(ix->D) : 0;
+  const int i8_nq = ix->has_tmap_i8 ? rows_i8_nq(B, ix->D) : f32_nq;
   const bool i8_ok = i8_nq > 0;
   if (path == B200R_PATH_AUTO) path = (gemm_ok || i8_ok) ? B200R_PATH_GEMM : B200R_PATH_SCAN;
   if (path == B200R_PATH_GEMM && !gemm_ok && !i8_ok) {
-    set_error("tensor path needs a bf16/f16 corpus with D %% 8 == 0 or an int8 corpus (dtype=%d D=%d)", ix->dtype, ix->D);
+    set_error("tensor path needs a bf16/f16 corpus with D %% 8 == 0, an int8 corpus or an fp32 corpus with D <= ~1400 (dtype=%d D=%d)", ix->dtype, ix->D);
     return B200R_EINVAL;
   }
   if (path != B200R_PATH_GEMM && path != B200R_PATH_SCAN) { set_error("bad path %d", path); return B200R_EINVAL; }
@@ -116,7 +137,8 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   if (path == B200R_PATH_GEMM) {
     // more than one 128-query tile: pair the CTAs (cta_group::2) so each loads half of every corpus tile
     // int8: rows-mode kernel (corpus rows on the MMA's M, 128-row tiles, one list per epilogue warp)
-    pl->rows_i8_nq = (ix->dtype == B200R_I8) ? i8_nq : 0;
+    pl->rows_i8_nq = (ix->dtype == B200R_I8 || ix->dtype == B200R_F32) ? i8_nq : 0;
+    pl->rows_f32 = (ix->dtype == B200R_F32) ? 1 : 0;
     pl->rows_i8 = pl->rows_i8_nq ? (B + i8_nq - 1) / i8_nq : 0;
     pl->cta_group = (!pl->rows_i8 && B > gemm_tile_queries() && g_cta_group_max >= 2) ? 2 : 1;
     const int BMq = pl->rows_i8 ? pl->rows_i8_nq : gemm_tile_queries() * pl->cta_group;
@@ -153,9 +175,13 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
     int seen = 0, np = 0;
     // The slow-path work of a phase is ~ B * k * ratio appends, so small batches afford a much coarser schedule
     // (fewer launches and threshold selects, which is what matters for batch-1 latency on small shards).
-    const int ratio = B <= 16 ? 64 : (B <= 128 ? 16 : 8);
+    static const int env_ratio = [] { const char* e = getenv("B200R_PHASE_RATIO"); return e ? atoi(e) : 0; }();   // A/B knob
+    const int ratio = env_ratio >= 2 ? env_ratio : (B <= 16 ? 64 : (B <= 128 ? 16 : 8));
     int want0 = (10 * k + BNr - 1) / BNr;
     if (want0 < 4) want0 = 4;
+    // a handful of queries: make the unfiltered first phase 1/64 of the corpus (one tile per chunk, all chunks busy) so
+    // that ONE more phase finishes the scan -- two launches and one select per search instead of three or four
+    if (B <= 16 && want0 < pl->num_row_tiles / 64) want0 = pl->num_row_tiles / 64;
     int tpc0 = (pl->cap_soft - 32) / list_rows_per_tile;
     if (tpc0 < 1) tpc0 = 1;
     if (want0 > C * tpc0) want0 = C * tpc0;
@@ -219,7 +245,8 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   }
   pl->q_replicas = (path == B200R_PATH_GEMM && !pl->rows_i8 && pl->cta_group == 1 && pl->num_q_tiles == 1 && g_q_replicas) ? 1 : 0;
   if (pl->q_replicas) { pl->off_qrep = off; off += align_up(query_replica_bytes(ix->D), 256); }
-  if (pl->rows_i8) { pl->off_qrep = off; off += align_up(rows_i8_query_bytes(B, pl->rows_i8_nq, ix->D), 256); }   // quantised query limbs + scales
+  if (pl->rows_i8 && pl->rows_f32) { pl->off_qrep = off; off += rows_f32_query_bytes(B, ix->D); }                   // hi / mid query planes
+  else if (pl->rows_i8) { pl->off_qrep = off; off += align_up(rows_i8_query_bytes(B, pl->rows_i8_nq, ix->D), 256); }   // quantised query limbs + scales
   pl->off_end = off;
   return B200R_OK;
 }
@@ -230,7 +257,8 @@ static int query_dtype(const Index* ix) { return ix->dtype == B200R_I8 ? B200R_F
 static int resolve_path(const Index* ix, int B, int path) {
   if (path != B200R_PATH_AUTO) return path;
   const bool i8_ok = ix->has_tmap_i8 && rows_i8_nq(B, ix->D) > 0;
-  return (ix->has_tmap || i8_ok) ? B200R_PATH_GEMM : B200R_PATH_SCAN;
+  const bool f32_ok = ix->has_tmap_f32 && rows_f32_nq(ix->D) > 0;
+  return (ix->has_tmap || i8_ok || f32_ok) ? B200R_PATH_GEMM : B200R_PATH_SCAN;
 }
 
 // Queries one planned search may carry.  The scan kernels and the int8 tensor kernel keep one candidate list per
@@ -239,7 +267,7 @@ static int resolve_path(const Index* ix, int B, int path) {
 static int slice_queries(const Index* ix, int B, int k, int path) {
   const int resolved = resolve_path(ix, B, path);
   if (resolved == B200R_PATH_SCAN) return k <= 256 ? 32 : 16;
-  if (ix->dtype == B200R_I8) return 256;
+  if (ix->dtype == B200R_I8 || ix->dtype == B200R_F32) return 256;
   return 1 << 30;
 }
 
@@ -259,7 +287,20 @@ static int do_search_one(Index* ix, const void* Q, int B, int k, int path, float
   }
   const bool floor_on = min_score > -HUGE_VALF;
   if (floor_on && (rc = launch_min_score(pl, ws, ix->metric == B200R_COS, min_score, st))) return rc;
-  if (pl.path == B200R_PATH_GEMM && pl.rows_i8) {
+  if (pl.path == B200R_PATH_GEMM && pl.rows_i8 && pl.rows_f32) {
+    void* qws = (char*)ws + pl.off_qrep;
+    if ((rc = launch_split_queries_tf32(Q, B, ix->D, qws, st))) return rc;
+    std::vector<CUtensorMap> tmaps(pl.rows_i8);
+    for (int g = 0; g < pl.rows_i8; ++g)
+      if ((rc = encode_query_tmap_f32(qws, g, ix->D, &tmaps[g]))) return rc;
+    for (int i = 0; i < pl.num_phases; ++i) {
+      profile_begin(st);
+      for (int g = 0; g < pl.rows_i8 && !rc; ++g) rc = launch_rows_f32(ix, &tmaps[g], g, pl, pl.phases[i], ws, st);
+      profile_end(st);
+      if (rc) return rc;
+      if (i + 1 < pl.num_phases && (rc = launch_select_lists(ix, pl, ws, nullptr, nullptr, st))) return rc;
+    }
+  } else if (pl.path == B200R_PATH_GEMM && pl.rows_i8) {
     void* qws = (char*)ws + pl.off_qrep;
     if ((rc = launch_quantize_queries_i8(Q, B, pl.rows_i8_nq, ix->D, qws, st))) return rc;
     std::vector<CUtensorMap> tmaps(pl.rows_i8);
@@ -427,6 +468,11 @@ int b200r_index_create(int device, const void* X, int64_t N, int32_t D, int32_t 
     if (rc) { if (ix->row_mult) cudaFree(ix->row_mult); delete ix; return rc; }
     ix->has_tmap = true;
   }
+  if (dtype == B200R_F32 && rows_f32_nq(D) > 0) {   // fp32 tensor path (rows_f32.cu): tiles of 128 rows x 32 floats
+    int rc = encode_tmap_2d(&ix->tmap_x_f32, dtype, X, (uint64_t)D, (uint64_t)N, 32, (uint32_t)rows_f32_tile_rows());
+    if (rc) { if (ix->row_mult) cudaFree(ix->row_mult); delete ix; return rc; }
+    ix->has_tmap_f32 = true;
+  }
   if (dtype == B200R_I8) {   // int8 tensor path (rows_i8.cu): tiles of 128 rows x 128 bytes
     int rc = encode_tmap_2d(&ix->tmap_x_i8, dtype, X, (uint64_t)D, (uint64_t)N, 128, (uint32_t)rows_i8_tile_rows());
     if (rc) { if (ix->row_mult) cudaFree(ix->row_mult); delete ix; return rc; }
@@ -517,6 +563,51 @@ int b200r_search_host(uint64_t index, const void* Q_host, int32_t B, int32_t k, 
   return B200R_OK;
 }
 
+// ---- range search: every row with score >= min_score (gemm_topk.cu range mode) ----------------------------------------
+// One pass over the corpus per call, single phase.  Workspace: counts, per-(chunk, query) offsets, query norms, the
+// (unused) threshold words and, for one query tile, the replicated queries.
+static int range_plan(const Index* ix, int B, SearchPlan* pl, size_t* off_slot) {
+  if (!ix->has_tmap) { set_error("range search runs on the tensor path: bf16/f16 corpus with D %% 8 == 0 (dtype=%d D=%d)", ix->dtype, ix->D); return B200R_EINVAL; }
+  int rc = make_plan(ix, B, 1, B200R_PATH_GEMM, pl);
+  if (rc) return rc;
+  pl->num_phases = 1;
+  pl->phases[0].tile_begin = 0; pl->phases[0].tile_end = pl->num_row_tiles;
+  pl->phases[0].tiles_per_chunk = (pl->num_row_tiles + pl->num_chunks - 1) / pl->num_chunks;
+  pl->phases[0].num_chunks = (pl->num_row_tiles + pl->phases[0].tiles_per_chunk - 1) / pl->phases[0].tiles_per_chunk;
+  size_t off = 0;
+  pl->off_lists = 0;
+  pl->off_counts = off; off += align_up((size_t)(pl->num_chunks + 1) * pl->Bpad * 4, 256);
+  *off_slot = off; off += align_up((size_t)pl->num_chunks * pl->Bpad * 8, 256);
+  pl->off_gthr = off; off += align_up((size_t)pl->Bpad * 4, 256);
+  pl->off_qinv = off; off += align_up((size_t)pl->Bpad * 4, 256);
+  pl->carry_cap = 0; pl->num_groups = 0;
+  if (pl->q_replicas) { pl->off_qrep = off; off += align_up(query_replica_bytes(ix->D), 256); }
+  pl->off_end = off;
+  return B200R_OK;
+}
+
+static int range_pass(Index* ix, const void* Q, int B, float min_score, const int64_t* id_gt, int mode, const int64_t* slot_off, void* out,
+                      const SearchPlan& pl, void* ws, cudaStream_t st) {
+  int rc;
+  float* qinv = nullptr;
+  if (ix->metric == B200R_COS) {
+    qinv = reinterpret_cast<float*>((char*)ws + pl.off_qinv);
+    if ((rc = launch_query_inv_norm(Q, B, ix->D, query_dtype(ix), qinv, st))) return rc;
+  }
+  CUtensorMap tmap_q;
+  if (pl.q_replicas) {
+    void* rep = (char*)ws + pl.off_qrep;
+    if ((rc = launch_replicate_queries(Q, rep, B, ix->D, st))) return rc;
+    rc = encode_query_tmap_replicated(ix, rep, &tmap_q);
+  } else {
+    rc = encode_query_tmap(ix, Q, B, &tmap_q);
+  }
+  if (rc) return rc;
+  RangeArgs rg;
+  rg.mode = mode; rg.tau = min_score; rg.qinv = qinv; rg.id_gt = id_gt; rg.offsets = slot_off; rg.out = out;
+  return launch_gemm_topk(ix, &tmap_q, pl, pl.phases[0], ws, st, &rg);
+}
+
 // ---- row-sharded search over the exchange (comm.cu) ----------------------------------------------------------------
 int b200r_search_sharded_begin(uint64_t index, uint64_t comm, const void* Q, int32_t B, int32_t k, int32_t path, void* workspace,
                                size_t workspace_bytes, void* stream) {
@@ -586,6 +677,54 @@ int b200r_search_sharded_host_all(const uint64_t* indexes, const uint64_t* comms
   return B200R_OK;
 }
 
+size_t b200r_range_workspace_bytes(uint64_t index, int32_t B) {
+  Index* ix = get_index(index);
+  if (!ix || B <= 0) return 0;
+  SearchPlan pl; size_t off_slot;
+  if (range_plan(ix, B, &pl, &off_slot)) return 0;
+  return pl.off_end;
+}
+
+int b200r_range_count(uint64_t index, const void* Q, int32_t B, float min_score, const int64_t* id_gt, int64_t* out_offsets,
+                      int64_t* total_host, void* workspace, size_t workspace_bytes, void* stream) {
+  Index* ix = get_index(index);
+  if (!ix) return B200R_ESTATE;
+  if (!Q || !out_offsets || !total_host || B <= 0) { set_error("null pointer / bad B"); return B200R_EINVAL; }
+  if (!(min_score == min_score)) { set_error("min_score is NaN"); return B200R_EINVAL; }
+  B200R_CUDA_CHECK(cudaSetDevice(ix->device));
+  SearchPlan pl; size_t off_slot;
+  int rc = range_plan(ix, B, &pl, &off_slot);
+  if (rc) return rc;
+  if (!workspace || workspace_bytes < pl.off_end || (reinterpret_cast<uintptr_t>(workspace) & 255)) {
+    set_error("range workspace too small or misaligned: need %zu bytes, 256-byte aligned", pl.off_end);
+    return B200R_ENOMEM;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if ((rc = range_pass(ix, Q, B, min_score, id_gt, 1, nullptr, nullptr, pl, workspace, st))) return rc;
+  int64_t* slot_off = reinterpret_cast<int64_t*>((char*)workspace + off_slot);
+  if ((rc = launch_range_offsets(pl, workspace, out_offsets, slot_off, st))) return rc;
+  B200R_CUDA_CHECK(cudaMemcpyAsync(total_host, out_offsets + B, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  B200R_CUDA_CHECK(cudaStreamSynchronize(st));
+  return B200R_OK;
+}
+
+int b200r_range_fill(uint64_t index, const void* Q, int32_t B, float min_score, const int64_t* id_gt, int64_t total,
+                     int64_t* out_ids, float* out_scores, void* workspace, size_t workspace_bytes, void* stream) {
+  Index* ix = get_index(index);
+  if (!ix) return B200R_ESTATE;
+  if (!Q || B <= 0 || total < 0 || (total > 0 && (!out_ids || !out_scores))) { set_error("null pointer / bad B / total"); return B200R_EINVAL; }
+  B200R_CUDA_CHECK(cudaSetDevice(ix->device));
+  SearchPlan pl; size_t off_slot;
+  int rc = range_plan(ix, B, &pl, &off_slot);
+  if (rc) return rc;
+  if (!workspace || workspace_bytes < pl.off_end) { set_error("range workspace too small: need %zu bytes", pl.off_end); return B200R_ENOMEM; }
+  if (total == 0) return B200R_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t* slot_off = reinterpret_cast<const int64_t*>((char*)workspace + off_slot);      // left there by b200r_range_count
+  if ((rc = range_pass(ix, Q, B, min_score, id_gt, 2, slot_off, out_ids, pl, workspace, st))) return rc;
+  return launch_range_unpack(nullptr, total, nullptr, B, 0.f, ix->id_base, out_ids, out_scores, st);
+}
+
 int b200r_merge_topk(int device, const float* cand_scores, const int64_t* cand_ids, int32_t G, int32_t B, int32_t kin,
                      int32_t k, float* out_scores, int64_t* out_ids, void* stream) {
   if (!cand_scores || !cand_ids || !out_scores || !out_ids) { set_error("null pointer"); return B200R_EINVAL; }
@@ -619,8 +758,37 @@ int b200r_merge_topk_packed(int device, const void* packed, int32_t G, int32_t B
   return launch_merge_topk(scores, ids, 3 * n, n + n / 2, G, B, kin, k, out_scores, out_ids, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int b200r_profile_dump(char* buf, size_t n) {
+  // {"name": [total_ms, launches], ...} in first-seen order; clears the records
+  std::vector<const char*> names; std::vector<double> ms; std::vector<int> cnt;
+  for (const ProfRec& r : g_prof_recs) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess) cudaEventElapsedTime(&t, r.a, r.b);
+    size_t i = 0;
+    for (; i < names.size(); ++i) if (strcmp(names[i], r.name) == 0) break;
+    if (i == names.size()) { names.push_back(r.name); ms.push_back(0.0); cnt.push_back(0); }
+    ms[i] += t; cnt[i] += 1;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof_recs.clear();
+  std::string out = "{";
+  for (size_t i = 0; i < names.size(); ++i) {
+    char tmp[160];
+    snprintf(tmp, sizeof(tmp), "%s\"%s\": [%.6f, %d]", i ? ", " : "", names[i], ms[i], cnt[i]);
+    out += tmp;
+  }
+  out += "}";
+  if (buf && n) { strncpy(buf, out.c_str(), n - 1); buf[n - 1] = 0; }
+  return (int)out.size();
+}
+
 int b200r_profile_enable(int on) {
-  g_prof_on = on != 0;
+  g_prof_all = on == 2;
+  if (!g_prof_all) {
+    for (const ProfRec& r : g_prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof_recs.clear();
+  }
+  g_prof_on = on == 1;
   if (!g_prof_on) {
     for (cudaEvent_t e : g_prof_events) cudaEventDestroy(e);
     g_prof_events.clear();

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(XM_THREADS) exchange_merge_kernel(const ExchMe
 }
 
 int launch_exchange_merge(const Comm* c, int B, int kin, int k, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+  ProfScope _ps(st, "exchange_merge");
   ExchMergeParams p;
   int rc = comm_dev(c, kChanDense, dense_record_stride(B, kin), &p.comm);
   if (rc) return rc;
@@ -139,6 +140,7 @@ __global__ void exchange_skip_kernel(const CommDev comm) {
 }
 
 int launch_exchange_skip(const Comm* c, cudaStream_t st) {
+  ProfScope _ps(st, "exchange_skip");
   CommDev cd;
   int rc = comm_dev(c, kChanDense, 0, &cd);
   if (rc) return rc;
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(256) scatter_record_kernel(const CommDev comm,
 }
 
 int launch_scatter_record(const CommDev& cd, const void* src, size_t bytes, size_t rec_stride, cudaStream_t st) {
+  ProfScope _ps(st, "scatter_record");
   if (bytes % 4 || bytes > rec_stride) { set_error("scatter_record: bad record size %zu (stride %zu)", bytes, rec_stride); return B200R_EINVAL; }
   const size_t words = bytes / 4;
   int blocks = (int)((words / 4 + 255) / 256);

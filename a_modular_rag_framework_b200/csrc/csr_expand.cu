@@ -849,6 +849,7 @@ static int work_queries(const ExpandParams& p) { return p.mode == 3 ? std::max(p
 
 template <typename QT>
 static int launch_bfs(const ExpandParams& p, cudaStream_t st) {
+  ProfScope _ps(st, "graph_bfs");
   const int nq = std::max(work_queries(p), 1);       // exchange mode: a rank without home queries still signals its peers
   B200R_CUDA_CHECK(cudaFuncSetAttribute(bfs_kernel<QT, EXP_MAXC_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bfs_smem_bytes(EXP_MAXC_SMALL)));
   bfs_kernel<QT, EXP_MAXC_SMALL><<<nq, BFS_THREADS, bfs_smem_bytes(EXP_MAXC_SMALL), st>>>(p);
@@ -862,6 +863,7 @@ static int launch_bfs(const ExpandParams& p, cudaStream_t st) {
 
 template <typename T>
 static int launch_gather(const ExpandParams& p, cudaStream_t st) {
+  ProfScope _ps(st, "graph_gather");
   const int dpad = (p.D + 3) & ~3;
   // A/B knobs (measurements only): B200R_GATHER_WARPS = warps per CTA, B200R_GATHER_CTAS = CTAs per SM
   static const int env_warps = [] { const char* e = getenv("B200R_GATHER_WARPS"); return e ? atoi(e) : 0; }();
@@ -883,6 +885,7 @@ static int launch_gather(const ExpandParams& p, cudaStream_t st) {
 }
 
 static int launch_select(const ExpandParams& p, cudaStream_t st) {
+  ProfScope _ps(st, "graph_fuse_select");
   if (select_smem_bytes(EXP_MAXC_BIG, p.kp2) > 220 * 1024) { set_error("expand_rescore: k=%d too large for shared memory", p.k); return B200R_EINVAL; }
   const int nq = std::max(work_queries(p), 1);
   B200R_CUDA_CHECK(cudaFuncSetAttribute(fuse_select_kernel<EXP_MAXC_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_smem_bytes(EXP_MAXC_SMALL, p.kp2)));
@@ -908,13 +911,13 @@ static int launch_expand_phase_t(const ExpandParams& p, int phase, int qdtype, c
     if ((rc = launch_bfs<QT>(p, st)) != B200R_OK) return rc;
   } else if (phase == 2) {
     if (p.metric == B200R_COS && (rc = launch_query_inv_norm(p.Q, p.B, p.D, qdtype, p.ws.qinv, st)) != B200R_OK) return rc;
-    gather_plan_kernel<<<1, 1024, 0, st>>>(p);
+    { ProfScope _ps(st, "graph_plan"); gather_plan_kernel<<<1, 1024, 0, st>>>(p); }
     count_launch();
     if ((rc = launch_gather<T>(p, st)) != B200R_OK) return rc;
   } else if (phase == 3) {
     if ((rc = launch_select(p, st)) != B200R_OK) return rc;
   } else {
-    collect_outputs_kernel<<<2 * kNumSMs, 256, 0, st>>>(p);
+    { ProfScope _ps(st, "graph_collect"); collect_outputs_kernel<<<2 * kNumSMs, 256, 0, st>>>(p); }
     count_launch();
   }
   B200R_CUDA_CHECK(cudaGetLastError());

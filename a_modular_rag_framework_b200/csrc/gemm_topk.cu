@@ -61,6 +61,15 @@ struct GemmTopkParams {
   u32 idesc;
   unsigned long long x_hint;   // L2 eviction policy of the corpus tiles
   int q_replicas;              // > 1: the (single) query tile exists in this many copies, CTA b reads copy b % q_replicas
+  // range mode (b200r_range_count / b200r_range_fill): every row with FINAL score >= tau (and id > id_gt[q]) instead of a
+  // top-k.  1 = count per (chunk, query) into `counts`; 2 = write the keys at range_off[slot] + i into range_out.
+  int range_mode;
+  float tau;
+  const float* qinv;           // nullable (inner product)
+  const long long* id_gt;      // nullable: only rows whose GLOBAL id exceeds id_gt[q]
+  long long id_base;
+  const long long* range_off;  // [num_chunks][Bpad]
+  u64* range_out;
 };
 
 // s[j] for a runtime j without spilling s[] to local memory: a balanced tree of 31 selects
@@ -220,6 +229,20 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       int cnt = valid ? __ldcg(p.counts + slot) : 0;   // lists persist across phases (ids keep increasing)
       u64 kth_key = 0;
       float thr = valid ? ordered_to_f32(__ldcg(p.gthr + q)) : __int_as_float(0x7f800000);
+      // range mode: the test is on the final score acc*mult*qi >= tau, identical in the count and the fill pass
+      const bool range = p.range_mode != 0;
+      float qi = 1.0f;
+      long long row_gt = -1;                    // local rows <= row_gt are excluded
+      u64* range_dst = nullptr;
+      if (range) {
+        cnt = 0;
+        thr = valid ? p.tau : __int_as_float(0x7f800000);
+        if (valid) {
+          qi = p.qinv ? p.qinv[q] : 1.0f;
+          if (p.id_gt) row_gt = p.id_gt[q] - p.id_base;
+          if (p.range_mode == 2) range_dst = p.range_out + p.range_off[slot];
+        }
+      }
 
       for (int t = t0; t < t1; ++t, ++tile_iter) {
         const u32 acc = tile_iter & 1;
@@ -263,8 +286,35 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
           for (int j = 2; j < 32; j += 2) rmax = fmaxf(rmax, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
           // conservative test on the raw accumulators (see mmax above); a non-positive threshold always enters
-          const bool maybe = !(rmax * mmax[c] < thr) || !(thr > 0.0f);
-          if (__any_sync(kFullMask, maybe)) {
+          const bool maybe = !((rmax * mmax[c]) * qi < thr) || !(thr > 0.0f);     // qi == 1 outside range mode
+          if (range) {
+            if (__any_sync(kFullMask, maybe)) {
+              float s[32];
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 m4 = *reinterpret_cast<const float4*>(mult + c * 32 + j);
+                s[j] = (__uint_as_float(v[j]) * m4.x) * qi;
+                s[j + 1] = (__uint_as_float(v[j + 1]) * m4.y) * qi;
+                s[j + 2] = (__uint_as_float(v[j + 2]) * m4.z) * qi;
+                s[j + 3] = (__uint_as_float(v[j + 3]) * m4.w) * qi;
+              }
+              u32 mask = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) mask |= (s[j] >= thr) ? (1u << j) : 0u;     // NaN multipliers (rows beyond N) never pass
+              // rows at or below the query's own id bound
+              const long long first = (long long)row0 + c * 32;
+              if (row_gt >= first) mask &= (row_gt - first >= 31) ? 0u : (0xffffffffu << (int)(row_gt - first + 1));
+              if (p.range_mode == 1) {
+                cnt += __popc(mask);
+              } else {
+                while (mask) {
+                  const int j = __ffs(mask) - 1;
+                  mask &= mask - 1;
+                  range_dst[cnt++] = make_key(mux32(s, j), row0 + c * 32 + j);
+                }
+              }
+            }
+          } else if (__any_sync(kFullMask, maybe)) {
             // rare path: exact scores, survivor bitmask per lane (straight-line), then each lane walks its own bits
             // and picks the value with a 5-level select tree -- no dependent vote/branch chain
             float s[32];
@@ -302,9 +352,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
         }
         // pick up thresholds published by other CTAs working on the same queries
-        if (valid) thr = fmaxf(thr, ordered_to_f32(__ldcg(p.gthr + q)));
+        if (valid && !range) thr = fmaxf(thr, ordered_to_f32(__ldcg(p.gthr + q)));
       }
-      p.counts[slot] = valid ? cnt : 0;
+      if (p.range_mode != 2) p.counts[slot] = valid ? cnt : 0;
     }
   }
 
@@ -338,6 +388,7 @@ __global__ void replicate_queries_kernel(const T* __restrict__ Q, T* __restrict_
 size_t query_replica_bytes(int D) { return (size_t)kQReplicas * BM * D * 2; }
 
 int launch_replicate_queries(const void* Q, void* rep, int B, int D, cudaStream_t st) {
+  ProfScope _ps(st, "replicate_queries");
   replicate_queries_kernel<unsigned short><<<kNumSMs, 256, 0, st>>>(reinterpret_cast<const unsigned short*>(Q),
                                                                     reinterpret_cast<unsigned short*>(rep), B, D);
   count_launch();
@@ -355,7 +406,8 @@ int encode_query_tmap(const Index* ix, const void* Q, int B, CUtensorMap* tmap_q
 }
 
 template <int CG>
-static int launch_gemm_cg(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& pl, const GemmPhase& ph, void* ws, cudaStream_t st) {
+static int launch_gemm_cg(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& pl, const GemmPhase& ph, void* ws, cudaStream_t st,
+                          const RangeArgs* rg) {
   GemmTopkParams p;
   p.B = pl.B; p.k = pl.k; p.D = ix->D; p.N = ix->N;
   p.num_q_tiles = pl.num_q_tiles; p.num_row_tiles = pl.num_row_tiles;     // num_q_tiles counts tiles of CG*128 queries
@@ -373,6 +425,11 @@ static int launch_gemm_cg(const Index* ix, const CUtensorMap* tmap_q, const Sear
   // one query tile: every corpus tile is read exactly once -> do not let it displace Q / the lists in L2
   p.x_hint = (pl.num_q_tiles == 1) ? kEvictFirst : kEvictNormal;
   p.q_replicas = pl.q_replicas ? kQReplicas : 1;
+  p.range_mode = 0; p.tau = 0.0f; p.qinv = nullptr; p.id_gt = nullptr; p.id_base = ix->id_base; p.range_off = nullptr; p.range_out = nullptr;
+  if (rg) {
+    p.range_mode = rg->mode; p.tau = rg->tau; p.qinv = rg->qinv; p.id_gt = reinterpret_cast<const long long*>(rg->id_gt);
+    p.range_off = reinterpret_cast<const long long*>(rg->offsets); p.range_out = reinterpret_cast<u64*>(rg->out);
+  }
   B200R_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<CG>::kSmemBytes));
   const int groups = p.num_units < kNumSMs / CG ? p.num_units : kNumSMs / CG;
   cudaLaunchConfig_t cfg;
@@ -391,8 +448,10 @@ static int launch_gemm_cg(const Index* ix, const CUtensorMap* tmap_q, const Sear
   return B200R_OK;
 }
 
-int launch_gemm_topk(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& pl, const GemmPhase& ph, void* ws, cudaStream_t st) {
-  return pl.cta_group == 2 ? launch_gemm_cg<2>(ix, tmap_q, pl, ph, ws, st) : launch_gemm_cg<1>(ix, tmap_q, pl, ph, ws, st);
+int launch_gemm_topk(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& pl, const GemmPhase& ph, void* ws, cudaStream_t st,
+                     const RangeArgs* rg) {
+  ProfScope _ps(st, rg ? "gemm_range" : "gemm_topk");
+  return pl.cta_group == 2 ? launch_gemm_cg<2>(ix, tmap_q, pl, ph, ws, st, rg) : launch_gemm_cg<1>(ix, tmap_q, pl, ph, ws, st, rg);
 }
 
 int gemm_tile_rows() { return BN; }

@@ -38,6 +38,8 @@ struct Index {
   CUtensorMap tmap_x_half;   // box 64 x 128 rows (CTA pair, each CTA loads half of the tile's rows)
   bool has_tmap_i8;          // int8 corpus: tensor map for the kind::i8 rows-mode kernel
   CUtensorMap tmap_x_i8;     // box 128 bytes x 128 rows
+  bool has_tmap_f32;         // fp32 corpus: tensor map for the kind::tf32 split-precision rows-mode kernel (rows_f32.cu)
+  CUtensorMap tmap_x_f32;    // box 32 floats x 128 rows
   // staging for b200r_search_host
   void* h_q_dev; size_t q_dev_bytes;
   float* h_s_dev; int64_t* h_i_dev; size_t out_dev_elems;
@@ -84,6 +86,7 @@ struct SearchPlan {
   int cta_group;         // 1 or 2 (CTA pair, cta_group::2)
   int rows_i8;           // > 0: int8 tensor path (rows_i8.cu) with this many groups of rows_i8_nq queries; 128-row tiles, 4 lists per unit
   int rows_i8_nq;        // 16 / 32 / 64
+  int rows_f32;          // 1: the groups above are served by the fp32 split-precision kernel (rows_f32.cu, 16 queries each)
   int q_replicas;        // 1: single query tile replicated in the workspace (off_qrep) against L2 hot-spotting
   int num_q_tiles, num_row_tiles, num_chunks;   // num_q_tiles counts tiles of cta_group*128 queries
   int num_phases;
@@ -105,7 +108,13 @@ int launch_query_inv_norm(const void* Q, int B, int D, int qdtype, float* qinv, 
 int launch_init_search(const SearchPlan& p, void* ws, cudaStream_t st);
 int launch_min_score(const SearchPlan& p, void* ws, bool cosine, float min_score, cudaStream_t st);
 int encode_query_tmap(const Index* ix, const void* Q, int B, CUtensorMap* tmap_q);
-int launch_gemm_topk(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& p, const GemmPhase& ph, void* ws, cudaStream_t st);
+// range mode of the tile kernel (gemm_topk.cu): mode 1 = count per (chunk, query) into the plan's counts, 2 = fill
+struct RangeArgs { int mode; float tau; const float* qinv; const int64_t* id_gt; const int64_t* offsets; void* out; };
+int launch_gemm_topk(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& p, const GemmPhase& ph, void* ws, cudaStream_t st,
+                     const RangeArgs* rg = nullptr);
+int launch_range_offsets(const SearchPlan& pl, void* ws, int64_t* offsets, int64_t* slot_off, cudaStream_t st);
+int launch_range_unpack(const void* keys, int64_t total, const int64_t* offsets, int B, float unused, int64_t id_base, int64_t* out_ids,
+                        float* out_scores, cudaStream_t st);
 size_t query_replica_bytes(int D);
 int launch_replicate_queries(const void* Q, void* rep, int B, int D, cudaStream_t st);
 int encode_query_tmap_replicated(const Index* ix, const void* rep, CUtensorMap* tmap_q);
@@ -117,6 +126,12 @@ int launch_quantize_queries_i8(const void* Q, int B, int nq, int D, void* qws, c
 int encode_query_tmap_i8(const void* qws, int group, int nq, int D, CUtensorMap* tmap_q);
 int launch_rows_i8(const Index* ix, const CUtensorMap* tmap_q, const void* qws, int group, const SearchPlan& p, const GemmPhase& ph, void* ws,
                    cudaStream_t st);
+int rows_f32_nq(int D);                       // queries per corpus pass of the fp32 tensor path (16), 0 = not available
+int rows_f32_tile_rows();
+size_t rows_f32_query_bytes(int B, int D);
+int launch_split_queries_tf32(const void* Q, int B, int D, void* qws, cudaStream_t st);
+int encode_query_tmap_f32(const void* qws, int group, int D, CUtensorMap* tmap_q);
+int launch_rows_f32(const Index* ix, const CUtensorMap* tmap_q, int group, const SearchPlan& p, const GemmPhase& ph, void* ws, cudaStream_t st);
 int scan_bulk_warps(const Index* ix);        // consumer warps per CTA of the bulk-fed scan, 0 if it does not apply
 int scan_bulk_tile_rows(const Index* ix);
 int launch_scan_bulk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
@@ -150,6 +165,12 @@ int launch_merge_topk(const float* cs, const int64_t* ci, size_t shard_stride_s,
                       float* os, int64_t* oi, cudaStream_t st, int32_t* osrc = nullptr);
 void profile_begin(cudaStream_t st);
 void profile_end(cudaStream_t st);
+// b200r_profile_enable(2): every launch site is bracketed by CUDA events under its name (b200r_profile_dump)
+struct ProfScope {
+  cudaStream_t st; int slot;
+  ProfScope(cudaStream_t stream, const char* name);
+  ~ProfScope();
+};
 int launch_expand_rescore(const Index* ix, const Graph* g, const void* Q, const int64_t* seeds, int B, int S, int window,
                           float alpha_dense, float alpha_graph, int k, float* out_scores, int64_t* out_ids, int32_t* out_hops,
                           float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand, int32_t* out_status, int mode,

@@ -314,6 +314,7 @@ static size_t rows_i8_group_bytes(int nq, int D) { return align_up((size_t)3 * n
 size_t rows_i8_query_bytes(int B, int nq, int D) { return (size_t)((B + nq - 1) / nq) * rows_i8_group_bytes(nq, D); }
 
 int launch_quantize_queries_i8(const void* Q, int B, int nq, int D, void* qws, cudaStream_t st) {
+  ProfScope _ps(st, "quantize_queries_i8");
   const int groups = (B + nq - 1) / nq;
   quantize_queries_i8_kernel<<<groups * nq, 256, 0, st>>>(reinterpret_cast<const float*>(Q), B, D, nq, reinterpret_cast<int8_t*>(qws),
                                                         rows_i8_group_bytes(nq, D), align_up((size_t)3 * nq * D, 256));
@@ -359,6 +360,7 @@ static int launch_rows_i8_nq(const Index* ix, const CUtensorMap* tmap_q, const v
 // one launch = one phase of one group of <= pl.rows_i8_nq queries
 int launch_rows_i8(const Index* ix, const CUtensorMap* tmap_q, const void* qws, int group, const SearchPlan& pl, const GemmPhase& ph,
                    void* ws, cudaStream_t st) {
+  ProfScope _ps(st, "rows_i8");
   switch (pl.rows_i8_nq) {
     case 16: return launch_rows_i8_nq<16>(ix, tmap_q, qws, group, pl, ph, ws, st);
     case 32: return launch_rows_i8_nq<32>(ix, tmap_q, qws, group, pl, ph, ws, st);

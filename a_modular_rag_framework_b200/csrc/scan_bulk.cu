@@ -366,6 +366,7 @@ static int launch_bulk_t(const Index* ix, const void* Q, const SearchPlan& pl, v
 }
 
 int launch_scan_bulk(const Index* ix, const void* Q, const SearchPlan& pl, void* ws, cudaStream_t st) {
+  ProfScope _ps(st, "scan_bulk");
   if (ix->dtype == B200R_I8) return launch_bulk_t<int8_t>(ix, Q, pl, ws, st);
   if (ix->dtype == B200R_F32) return launch_bulk_t<float>(ix, Q, pl, ws, st);
   set_error("bulk scan: unsupported dtype %d", ix->dtype);

@@ -242,6 +242,7 @@ static int launch_scan_t(const Index* ix, const void* Q, const SearchPlan& pl, v
 }
 
 int launch_scan_topk(const Index* ix, const void* Q, const SearchPlan& pl, void* ws, cudaStream_t st) {
+  ProfScope _ps(st, "scan_topk");
   switch (ix->dtype) {
     case B200R_BF16: return launch_scan_t<__nv_bfloat16, 8, 4>(ix, Q, pl, ws, st);
     case B200R_F16: return launch_scan_t<__half, 8, 4>(ix, Q, pl, ws, st);
@@ -314,6 +315,7 @@ __global__ void query_inv_norm_kernel(const QT* Q, int B, int D, float* qinv) {
 }
 
 int launch_query_inv_norm(const void* Q, int B, int D, int qdtype, float* qinv, cudaStream_t st) {
+  ProfScope _ps(st, "query_inv_norm");
   const int wpb = 4;
   const unsigned blocks = (unsigned)((B + wpb - 1) / wpb);
   switch (qdtype) {
@@ -345,6 +347,7 @@ __global__ void min_score_gthr_kernel(u32* gthr, const float* qinv, int B, float
 }
 
 int launch_min_score(const SearchPlan& pl, void* ws, bool cosine, float min_score, cudaStream_t st) {
+  ProfScope _ps(st, "min_score");
   u32* gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
   const float* qinv = cosine ? reinterpret_cast<const float*>((char*)ws + pl.off_qinv) : nullptr;
   min_score_gthr_kernel<<<(pl.B + 255) / 256, 256, 0, st>>>(gthr, qinv, pl.B, min_score);
@@ -354,6 +357,7 @@ int launch_min_score(const SearchPlan& pl, void* ws, bool cosine, float min_scor
 }
 
 int launch_init_search(const SearchPlan& pl, void* ws, cudaStream_t st) {
+  ProfScope _ps(st, "init_search");
   u32* gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
   int* counts = reinterpret_cast<int*>((char*)ws + pl.off_counts);
   const long long n_counts = (long long)(pl.num_segments + 1) * pl.Bpad;   // + the carry lists' counts

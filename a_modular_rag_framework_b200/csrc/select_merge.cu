@@ -11,6 +11,7 @@
 #include "internal.h"
 #include <math_constants.h>
 #include <cstring>
+#include <cstdlib>
 
 namespace b200r {
 
@@ -90,9 +91,14 @@ __device__ __forceinline__ void for_each_key(const SelectParams& p, int q, int s
 // histogram increment with one shared-memory atomic per distinct digit per warp (candidate keys share
 // their leading bytes, so un-aggregated atomics would serialise on one bin)
 __device__ __forceinline__ void hist_add(u32* hist, bool active, u32 digit) {
-  const u32 d = active ? digit : 0xffffffffu;
-  const u32 peers = __match_any_sync(kFullMask, d);
-  if (active && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[d], (u32)__popc(peers));
+  const u32 act = __ballot_sync(kFullMask, active);
+  if (!act) return;
+  const u32 d0 = __shfl_sync(kFullMask, digit, __ffs(act) - 1);
+  if (__all_sync(kFullMask, !active || digit == d0)) {        // the leading bytes of candidate keys: everybody agrees
+    if ((threadIdx.x & 31) == __ffs(act) - 1) atomicAdd(&hist[d0], (u32)__popc(act));
+  } else if (active) {
+    atomicAdd(&hist[digit], 1u);
+  }
 }
 
 __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const SelectParams p) {
@@ -320,9 +326,157 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
   if (p.use_comm) comm_send_end(p.comm, epoch, gridDim.x * gridDim.y);
 }
 
+// ------------------------------------------------------------------------------------------------
+// threshold_warp_kernel: the per-phase select (threshold mode) with ONE WARP per query -- no block barriers, a third of
+// the instructions of the CTA-per-query kernel.  Used when a carry list exists and the per-query candidate count
+// (~k + one phase's survivors) fits the warp's stage; a query that does not fit is handled from global memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int TW_WARPS = 4;            // queries per CTA
+constexpr int TW_STAGE = 1536;         // keys staged per warp (12 KB)
+
+__device__ __forceinline__ int tw_find_segment(const int* seg_off, int nseg, int i) {
+  int lo = 0, hi = nseg;                       // last segment with seg_off <= i
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_off[mid] <= i) lo = mid; else hi = mid; }
+  return lo;
+}
+
+__global__ void __launch_bounds__(TW_WARPS * 32) threshold_warp_kernel(const SelectParams p, const int seg_stride) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * TW_WARPS + warp;
+  if (q >= p.B) return;                                               // whole warp
+  u64* stage = reinterpret_cast<u64*>(smem_raw) + (size_t)warp * TW_STAGE;
+  u32* hist = reinterpret_cast<u32*>(reinterpret_cast<u64*>(smem_raw) + (size_t)TW_WARPS * TW_STAGE) + warp * 256;
+  int* seg_off = reinterpret_cast<int*>(reinterpret_cast<u32*>(reinterpret_cast<u64*>(smem_raw) + (size_t)TW_WARPS * TW_STAGE) + TW_WARPS * 256) +
+                 (size_t)warp * seg_stride;
+  const int nreal = p.S, nseg = p.S + 1;                               // + the carry list (count at index S)
+  // ---- counts -> exclusive offsets ----
+  int run = 0;
+  for (int base = 0; base < nseg; base += 32) {
+    const int sgi = base + lane;
+    const int c = sgi < nseg ? p.counts[(size_t)sgi * p.Bpad + q] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFullMask, incl, o); if (lane >= o) incl += t; }
+    if (sgi < nseg) seg_off[sgi] = run + incl - c;
+    run += __shfl_sync(kFullMask, incl, 31);
+  }
+  if (lane == 0) seg_off[nseg] = run;
+  __syncwarp();
+  const int total = run;
+  if (total < p.k) return;                                             // not enough candidates yet for a threshold
+  const u64* carry = p.carry + (size_t)q * p.carry_cap;
+  auto load_key = [&](int i) -> u64 {
+    const int sg = tw_find_segment(seg_off, nseg, i);
+    const int j = i - seg_off[sg];
+    return sg >= nreal ? carry[j] : p.lists[((size_t)sg * p.Bpad + q) * (size_t)p.cap + j];
+  };
+  const bool staged = total <= TW_STAGE;
+  if (staged) {
+    // four independent loads in flight per lane
+    for (int base = 0; base < total; base += 128) {
+      u64 v[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { const int i = base + r * 32 + lane; v[r] = i < total ? load_key(i) : 0ull; }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { const int i = base + r * 32 + lane; if (i < total) stage[i] = v[r]; }
+    }
+    __syncwarp();
+  }
+  // ---- radix select of the k-th key, top 24 bits (a truncated key is a valid, slightly low threshold) ----
+  u64 prefix = 0;
+  int remaining = p.k;
+#pragma unroll 1
+  for (int pass = 7; pass >= 5; --pass) {
+    const int shift = pass * 8;
+    for (int i = lane; i < 256; i += 32) hist[i] = 0;
+    __syncwarp();
+    const u64 hi_mask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
+    for (int base = 0; base < total; base += 32) {
+      const int i = base + lane;
+      const bool active = i < total;
+      const u64 key = active ? (staged ? stage[i] : load_key(i)) : 0ull;
+      const bool m = active && (key & hi_mask) == prefix;
+      hist_add(hist, m, (u32)(key >> shift) & 255u);
+    }
+    __syncwarp();
+    u32 c[8]; u32 lane_sum = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) { c[b] = hist[lane * 8 + b]; lane_sum += c[b]; }
+    u32 suffix = lane_sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_down_sync(kFullMask, suffix, o); if (lane + o < 32) suffix += t; }
+    const u32 above = suffix - lane_sum;
+    const bool mine = (above < (u32)remaining) && ((u32)remaining <= suffix);
+    int digit = 0, new_remaining = 0;
+    if (mine) {
+      u32 r2 = above;
+#pragma unroll
+      for (int b = 7; b >= 0; --b) {
+        if (r2 + c[b] >= (u32)remaining) { digit = lane * 8 + b; new_remaining = remaining - (int)r2; break; }
+        r2 += c[b];
+      }
+    }
+    const int src = __ffs(__ballot_sync(kFullMask, mine)) - 1;
+    digit = __shfl_sync(kFullMask, digit, src);
+    remaining = __shfl_sync(kFullMask, new_remaining, src);
+    prefix |= (u64)(u32)digit << shift;
+    __syncwarp();
+  }
+  const u64 kth = prefix;
+  if (lane == 0) atomicMax(p.gthr + q, (u32)(kth >> 32));
+  // ---- prune ----
+  int* wc = const_cast<int*>(p.counts);
+  if (staged) {
+    u64* cl = p.carry + (size_t)q * p.carry_cap;      // every read of the old carry is in the stage by now
+    int out = 0;
+    for (int base = 0; base < total; base += 32) {
+      const int i = base + lane;
+      const u64 key = i < total ? stage[i] : 0ull;
+      const bool keep = i < total && key >= kth;
+      const u32 m = __ballot_sync(kFullMask, keep);
+      if (keep) cl[out + __popc(m & ((1u << lane) - 1u))] = key;
+      out += __popc(m);
+    }
+    for (int sgi = lane; sgi < nreal; sgi += 32) wc[(size_t)sgi * p.Bpad + q] = 0;
+    if (lane == 0) wc[(size_t)p.S * p.Bpad + q] = out;
+    return;
+  }
+  u64* wl = const_cast<u64*>(p.lists);
+  for (int sg = 0; sg < nseg; ++sg) {                 // in place, segment by segment (the carry may not hold everything)
+    const size_t slot = (size_t)sg * p.Bpad + q;
+    const int c = seg_off[sg + 1] - seg_off[sg];
+    if (c == 0) continue;
+    u64* lp = sg >= nreal ? p.carry + (size_t)q * p.carry_cap : wl + slot * (size_t)p.cap;
+    int out = 0;
+    for (int base = 0; base < c; base += 32) {
+      const int i = base + lane;
+      const u64 key = (i < c) ? lp[i] : 0ull;
+      const bool keep = (i < c) && key >= kth;
+      const u32 m = __ballot_sync(kFullMask, keep);
+      __syncwarp();
+      if (keep) lp[out + __popc(m & ((1u << lane) - 1u))] = key;
+      out += __popc(m);
+    }
+    if (lane == 0) wc[slot] = out;
+  }
+}
+
+static int run_threshold_warp(const SelectParams& p, cudaStream_t st) {
+  ProfScope _ps(st, "select_threshold_warp");
+  const int seg_stride = (p.S + 2 + 3) & ~3;
+  const size_t smem = (size_t)TW_WARPS * TW_STAGE * 8 + (size_t)TW_WARPS * 256 * 4 + (size_t)TW_WARPS * seg_stride * 4;
+  B200R_CUDA_CHECK(cudaFuncSetAttribute(threshold_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  threshold_warp_kernel<<<(p.B + TW_WARPS - 1) / TW_WARPS, TW_WARPS * 32, smem, st>>>(p, seg_stride);
+  count_launch();
+  B200R_CUDA_CHECK(cudaGetLastError());
+  return B200R_OK;
+}
+
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 static int run_select(SelectParams& p, int grid_y, cudaStream_t st) {
+  ProfScope _ps(st, p.mode == kSelThreshold ? "select_threshold" : (p.mode == kSelPartial ? "select_partial" : (p.use_comm ? "select_final_scatter" : "select_final")));
   const long long all = (long long)(p.mode == kSelPartial ? p.seg_per_cta : p.S) * p.cap + (p.carry ? p.carry_cap : 0);
   int limit = SEL_STAGE_MAX;
   const long long ctas = (long long)p.B * grid_y;
@@ -354,7 +508,13 @@ int launch_select_lists(const Index* ix, const SearchPlan& pl, void* ws, float* 
   p.id_base = ix->id_base;
   p.out_scores = out_scores;
   p.out_ids = reinterpret_cast<long long*>(out_ids);
-  if (!out_scores && !comm) { p.mode = kSelThreshold; return run_select(p, 1, st); }
+  if (!out_scores && !comm) {
+    p.mode = kSelThreshold;
+    // one warp per query when there are enough queries to fill the GPU that way and a phase's survivors fit its stage
+    static const int env_warp = [] { const char* e = getenv("B200R_SELECT_WARP"); return e ? atoi(e) : 1; }();
+    if (env_warp && p.carry && p.B >= 512 && 9 * p.k + 256 <= TW_STAGE && p.S + 1 <= SEL_MAX_SEGS) return run_threshold_warp(p, st);
+    return run_select(p, 1, st);
+  }
   if (pl.num_groups > 0) {
     // two levels: many short per-warp lists (scan path) are first reduced group-wise to k keys each
     SelectParams p1 = p;
@@ -370,6 +530,71 @@ int launch_select_lists(const Index* ix, const SearchPlan& pl, void* ws, float* 
   }
   p.mode = kSelOutput;
   return run_select(p, 1, st);
+}
+
+// ---- range search bookkeeping (b200r_range_count / b200r_range_fill) ---------------------------------------------------
+// counts[c][q] (hits of query q in row chunk c) -> offsets[q] (exclusive over queries, offsets[B] = total) and
+// slot_off[c][q] = offsets[q] + hits of q in the chunks before c: per query the hits land in ascending row order.  One CTA.
+__global__ void __launch_bounds__(1024) range_offsets_kernel(const int* __restrict__ counts, int num_chunks, int Bpad, int B,
+                                                             long long* __restrict__ offsets, long long* __restrict__ slot_off) {
+  __shared__ long long s_warp[32];
+  __shared__ long long s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int q0 = 0; q0 < B; q0 += 1024) {
+    const int q = q0 + tid;
+    long long tot = 0;
+    if (q < B)
+      for (int c = 0; c < num_chunks; ++c) { slot_off[(size_t)c * Bpad + q] = tot; tot += counts[(size_t)c * Bpad + q]; }
+    long long incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(kFullMask, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    long long wbase = 0, all = 0;
+    for (int w = 0; w < 32; ++w) { if (w < warp) wbase += s_warp[w]; all += s_warp[w]; }
+    const long long mine = s_base + wbase + incl - tot;
+    if (q < B) {
+      offsets[q] = mine;
+      for (int c = 0; c < num_chunks; ++c) slot_off[(size_t)c * Bpad + q] += mine;
+    }
+    __syncthreads();
+    if (tid == 0) s_base += all;
+    __syncthreads();
+  }
+  if (tid == 0) offsets[B] = s_base;
+}
+
+int launch_range_offsets(const SearchPlan& pl, void* ws, int64_t* offsets, int64_t* slot_off, cudaStream_t st) {
+  ProfScope _ps(st, "range_offsets");
+  range_offsets_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const int*>((char*)ws + pl.off_counts), pl.num_chunks, pl.Bpad, pl.B,
+                                           reinterpret_cast<long long*>(offsets), reinterpret_cast<long long*>(slot_off));
+  count_launch();
+  B200R_CUDA_CHECK(cudaGetLastError());
+  return B200R_OK;
+}
+
+// keys (left in the id array by the fill pass) -> global ids + scores, in place
+__global__ void range_unpack_kernel(long long* __restrict__ ids, float* __restrict__ scores, long long total, long long id_base) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, step = (long long)gridDim.x * blockDim.x;
+  for (long long i = i0; i < total; i += step) {
+    const u64 key = (u64)ids[i];
+    scores[i] = key_score(key);
+    ids[i] = id_base + (long long)key_id(key);
+  }
+}
+
+int launch_range_unpack(const void*, int64_t total, const int64_t*, int, float, int64_t id_base, int64_t* out_ids, float* out_scores,
+                        cudaStream_t st) {
+  if (total <= 0) return B200R_OK;
+  ProfScope _ps(st, "range_unpack");
+  long long blocks = (total + 255) / 256;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  range_unpack_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<long long*>(out_ids), out_scores, total, id_base);
+  count_launch();
+  B200R_CUDA_CHECK(cudaGetLastError());
+  return B200R_OK;
 }
 
 int select_group_size() { return SEL_GROUP; }
@@ -439,6 +664,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const MergePa
 
 int launch_merge_topk(const float* cs, const int64_t* ci, size_t shard_stride_s, size_t shard_stride_i, int G, int B, int kin, int k,
                       float* os, int64_t* oi, cudaStream_t st, int32_t* osrc) {
+  ProfScope _ps(st, "merge_topk");
   const long long n = (long long)G * kin;
   if (n > 16384) { set_error("merge_topk: G*kin = %lld exceeds 16384", n); return B200R_EINVAL; }
   MergeParams p;

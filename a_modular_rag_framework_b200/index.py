@@ -148,6 +148,29 @@ class DenseIndex:
         return scores, ids
 
 
+class CapturedSearch:
+    """One search step (local or row-sharded: search + exchange + merge) captured into a CUDA graph and replayed: a
+    batch-1 step is a dozen short kernels, so its latency is the host's launch rate unless they go down as ONE graph
+    launch.  libb200r's calls are capture-safe (no allocation, no synchronisation; the exchange keeps its epochs on the
+    device).  `index` is a DenseIndex or a ShardedDenseIndex; the query buffer and the outputs are static tensors:
+    copy a new batch into `.Q` (or pass it to __call__) and replay.  Every rank of a sharded index must replay in step."""
+
+    def __init__(self, index, Q: torch.Tensor, k: int, path: str = "auto"):
+        self.index, self.k, self.path = index, int(k), path
+        self.Q = Q.clone()
+        index.search(self.Q, self.k, path=path)                   # warm-up outside the capture: workspaces, windows, attributes
+        torch.cuda.synchronize(self.Q.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.scores, self.ids = index.search(self.Q, self.k, path=path)
+
+    def __call__(self, Q: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        if Q is not None:
+            self.Q.copy_(Q, non_blocking=True)
+        self.graph.replay()
+        return self.scores, self.ids
+
+
 def merge_topk(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """[G, B, kin] per-shard lists -> [B, k] by (score desc, id asc); ids < 0 are padding."""
     _require_cuda(cand_scores, "cand_scores")
@@ -375,15 +398,50 @@ def expand_rescore_pass(index: DenseIndex, graph: PassageGraph, Q: torch.Tensor,
             _stream_ptr(index.device)))
 
 
-def semantic_sim_edges(index: DenseIndex, threshold: float, max_per_row: int = 64, batch: int = 4096) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Corpus-scale version of EdgeBuilder.build step 4 (edge_builder.py:146-169): every unordered pair (a, b), a < b,
-    with cosine >= threshold (the reference enumerates itertools.combinations, i.e. each pair once, a before b).
-    Each row keeps at most `max_per_row` best partners.  Returns (src i64, dst i64, sim f32) on the device."""
-    src, dst, sim = [], [], []
-    for r0 in range(0, index.N, batch):
-        Q = index.X[r0:r0 + batch].to(index.query_dtype).contiguous()
-        s, i = index.search(Q, max_per_row + 1, min_score=threshold)
-        rows = torch.arange(r0, r0 + Q.shape[0], device=index.device, dtype=torch.int64).unsqueeze(1).expand_as(i) + index.id_base
-        keep = (i >= 0) & (i > rows)          # drops padding, self matches and the mirrored half
-        src.append(rows[keep]); dst.append(i[keep]); sim.append(s[keep])
-    return torch.cat(src), torch.cat(dst), torch.cat(sim)
+def range_search(index: DenseIndex, Q: torch.Tensor, min_score: float, id_gt: Optional[torch.Tensor] = None
+                 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """EVERY row with score >= min_score for each query (no cap): -> (offsets i64 [B+1], ids i64 [total], scores f32 [total]);
+    query q's hits are ids[offsets[q]:offsets[q+1]] in ascending id.  id_gt (i64 [B]): only ids > id_gt[q].  Two passes of the
+    tile kernel (count, then fill into exactly-sized arrays, b200r_range_count / b200r_range_fill)."""
+    _require_cuda(Q, "Q")
+    if Q.dim() != 2 or Q.shape[1] != index.D or Q.dtype != index.query_dtype:
+        raise ValueError(f"Q must be [B, {index.D}] {index.query_dtype}")
+    if id_gt is not None:
+        _require_cuda(id_gt, "id_gt")
+        if id_gt.dtype != torch.int64 or id_gt.numel() != Q.shape[0]:
+            raise ValueError("id_gt must be int64 [B]")
+    lib = N.load()
+    B, dev = int(Q.shape[0]), index.device
+    nbytes = int(lib.b200r_range_workspace_bytes(index.handle, B))
+    if nbytes == 0:
+        raise N.B200RError(-1, N.last_error())
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    offsets = torch.empty(B + 1, dtype=torch.int64, device=dev)
+    total = ctypes.c_int64(0)
+    gt = id_gt.data_ptr() if id_gt is not None else None
+    with torch.cuda.device(dev):
+        N.check(lib.b200r_range_count(index.handle, Q.data_ptr(), B, float(min_score), gt, offsets.data_ptr(), ctypes.byref(total),
+                                      ws.data_ptr(), ws.numel(), _stream_ptr(dev)))
+        n = int(total.value)
+        ids = torch.empty(n, dtype=torch.int64, device=dev)
+        scores = torch.empty(n, dtype=torch.float32, device=dev)
+        N.check(lib.b200r_range_fill(index.handle, Q.data_ptr(), B, float(min_score), gt, n, ids.data_ptr(), scores.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), _stream_ptr(dev)))
+    return offsets, ids, scores
+
+
+def semantic_sim_edges(index: DenseIndex, threshold: float, batch: int = 4096, row_range: Optional[Tuple[int, int]] = None):
+    """Corpus-scale version of EdgeBuilder.build step 4 (edge_builder.py:146-169): EVERY unordered pair (a, b), a < b, with
+    cosine >= threshold (the reference enumerates itertools.combinations, i.e. each pair once, a before b) -- no per-row
+    cap.  Rows [row_range) of the corpus are the `a` side (default: all), processed `batch` rows at a time through
+    range_search with id_gt = the row's own id.  Yields (a_first, offsets i64 [n+1], dst i64 [m], sim f32 [m]) per block:
+    row a_first + j pairs with dst[offsets[j]:offsets[j+1]] (ascending), all on the device."""
+    lo, hi = row_range if row_range is not None else (0, index.N)
+    for r0 in range(lo, hi, batch):
+        r1 = min(hi, r0 + batch)
+        Q = index.X[r0:r1]
+        if Q.dtype != index.query_dtype or not Q.is_contiguous():
+            Q = Q.to(index.query_dtype).contiguous()
+        own = torch.arange(r0, r1, device=index.device, dtype=torch.int64) + index.id_base
+        offsets, dst, sim = range_search(index, Q, threshold, id_gt=own)
+        yield r0 + index.id_base, offsets, dst, sim

@@ -222,7 +222,25 @@ def leg_small_batch(torch, index, world, Q, k, steps, n_local, dim, peaks, _nati
     kms /= steps
     gbs = n_local * dim * 2 / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
     peak = peaks.get("hbm_gbs", 6650.0)
+    # the same step replayed as ONE CUDA graph launch (search + exchange + merge): what a latency-bound caller would use
+    graph_ms, graph_err = None, None
+    try:
+        from a_modular_rag_framework_b200.index import CapturedSearch
+        cap = CapturedSearch(index, Q[0], k)
+        for i in range(3):
+            cap(Q[i % Q.shape[0]])
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(steps):
+            cap(Q[i % Q.shape[0]])
+        e1.record()
+        torch.cuda.synchronize()
+        graph_ms = e0.elapsed_time(e1) / steps
+    except Exception as e:  # noqa: BLE001
+        graph_err = repr(e)
     return {"batch": B, "k": k, "ms_per_batch": ms, "queries_per_s": B / (ms * 1e-3), "tile_kernel_ms": kms, "launches_per_batch": kn / steps,
+            "cuda_graph_ms_per_batch": graph_ms, "cuda_graph_queries_per_s": (B / (graph_ms * 1e-3)) if graph_ms else None,
+            "cuda_graph_error": graph_err,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                          "algorithmic": "N_local*D*2 bytes per batch per GPU (corpus shard streamed once), tile kernel time only"}}
 
@@ -650,6 +668,25 @@ def main():
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
                     "algorithmic": "N_local*D*2 bytes per corpus pass (one pass per <=4 queries), summed over the step"}
 
+    # ---- per-launch-site timeline of the dense step (events around every launch; 5 extra steps, outside the timed region) ----
+    timeline = None
+    try:
+        _native.profile_timeline(True)
+        for i in range(5):
+            if world > 1:
+                index.search(Qd[a.warmup + i % a.steps], a.k, path=a.path, overlap=True)
+            else:
+                index.search(Qd[a.warmup + i % a.steps], a.k, path=a.path)
+        if world > 1 and getattr(index, "_outstanding", None) is not None:
+            index._outstanding.resolve()
+            index._outstanding = None
+        torch.cuda.synchronize()
+        timeline = {site: {"ms_per_step": v[0] / 5, "launches_per_step": v[1] / 5} for site, v in _native.profile_dump().items()}
+    except Exception as e:  # noqa: BLE001
+        timeline = {"error": repr(e)}
+    finally:
+        _native.profile_timeline(False)
+
     # ---- secondary legs: batch-1 / batch-16 latency on the same shards, graph stage (configs[4]) --------------------------
     legs = None
     if not a.no_legs:
@@ -691,7 +728,7 @@ def main():
                            "packed NCCL all-gather + device merge on a side stream, overlapped with the next batch's search"),
                        "l2": "corpus shard (>= 1.9 GB) is far larger than the 126 MB L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "per_rank": per_rank, "legs": legs,
+            "clocks": clocks, "per_rank": per_rank, "legs": legs, "timeline": timeline,
         }
         if verify is not None:
             line["recall"] = min(v["recall"] for v in verify.values() if isinstance(v, dict))

@@ -97,6 +97,23 @@ int b200r_search_min_score(uint64_t index, const void* Q, int32_t B, int32_t k, 
                            float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
                            void* stream);
 
+/* ---- range search: EVERY row at or above a similarity threshold --------------------------------------------------
+ * The all-pairs `sim >= semantic_threshold` test of EdgeBuilder.build step 4 (app/modules/graph_construction/
+ * edge_builder.py:146-169) at corpus scale, without any per-row cap: the tile kernel's epilogue tests the FINAL score
+ * (dot * row multiplier * 1/|q|, 0.0 for zero norms like _cosine) against min_score instead of keeping a top-k.
+ * Two passes over the corpus: b200r_range_count counts the hits of every (row chunk, query), turns them into offsets
+ * (out_offsets[B+1] on the device, exclusive; *total_host = out_offsets[B]; synchronises `stream`) and leaves the
+ * per-chunk offsets in `workspace`; the caller allocates exactly `total` ids / scores and b200r_range_fill (same Q,
+ * min_score, id_gt and workspace) writes query q's hits to [out_offsets[q], out_offsets[q+1]) in ASCENDING row id.
+ * id_gt (nullable, i64 [B]): only rows whose global id is > id_gt[q] -- with Q = rows of the corpus and id_gt[q] = q's own
+ * id every unordered pair is reported once (itertools.combinations order, edge_builder.py:153) and never a self match.
+ * bf16 / f16 corpora with D % 8 == 0 (the tensor path). */
+size_t b200r_range_workspace_bytes(uint64_t index, int32_t B);
+int b200r_range_count(uint64_t index, const void* Q, int32_t B, float min_score, const int64_t* id_gt, int64_t* out_offsets,
+                      int64_t* total_host, void* workspace, size_t workspace_bytes, void* stream);
+int b200r_range_fill(uint64_t index, const void* Q, int32_t B, float min_score, const int64_t* id_gt, int64_t total,
+                     int64_t* out_ids, float* out_scores, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- shard exchange (row-sharded corpus) ------------------------------------------------------
  * The reference keeps one index in one process (BM25LiteIndex / DenseReranker, retrieval_backend.py:252-281); at
  * 8 GPUs the corpus is row-sharded and the per-shard top-k lists must meet.  The exchange lives HERE, under the C
@@ -167,6 +184,10 @@ int b200r_merge_topk_packed(int device, const void* packed, int32_t G, int32_t B
  * returns the summed device time in ms and the number of bracketed launches (and clears them). */
 int b200r_profile_enable(int on);
 int b200r_profile_read(double* kernel_ms, int64_t* launches);
+/* b200r_profile_enable(2): EVERY launch site of the library is bracketed by CUDA events under its name; b200r_profile_dump
+ * synchronises them, writes {"site": [total_ms, launches], ...} (JSON, NUL terminated, truncated to n) into buf, clears the
+ * records and returns the untruncated length.  The timeline behind profiles/*_timeline.json. */
+int b200r_profile_dump(char* buf, size_t n);
 
 /* ---- passage/entity graph --------------------------------------------------------------------
  * Replaces load_graph_json + build_index (graph_utils.py:13-55), done once instead of per query:

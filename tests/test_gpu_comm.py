@@ -52,6 +52,23 @@ def test_virtual_ranks_exchange_equals_unsharded(G, N, D, B, k, dtype):
             assert torch.equal(s, full_s)
     for c in comms:
         c.check()
+    if G == 4:
+        # the whole sharded step (every rank's begin, then every rank's finish) captured into ONE CUDA graph: the exchange
+        # keeps its epochs on the device, so replays stay in step
+        graph = torch.cuda.CUDAGraph()
+        Qs = Q.clone()
+        with torch.cuda.graph(graph):
+            for r in range(G):
+                shards[r].search_sharded_begin(comms[r], Qs, k)
+            outs_g = [comms[r].finish(B, k) for r in range(G)]
+        for rep in range(4):
+            Qs.copy_(Q if rep % 2 == 0 else Q.flip(0))
+            graph.replay()
+            want_i = full_i if rep % 2 == 0 else full_i.flip(0)
+            for s, i in outs_g:
+                assert torch.equal(i, want_i)
+        for c in comms:
+            c.check()
     pos7, posl = (full_i[0] == 7).nonzero().item(), (full_i[0] == N - 1).nonzero().item()
     assert posl == pos7 + 1
     S = O.score_matrix(Q[:2].float().cpu().numpy(), X.float().cpu().numpy())

@@ -313,13 +313,61 @@ def test_min_score_floor_and_semantic_sim_edges():
             if len(ref) <= 50:
                 assert sure <= set(got.tolist()) <= maybe, (path, b)
             assert np.all(s[b][: len(got)] >= tau - 1e-3) and np.all(np.isneginf(s[b][len(got):]))
-    src, dst, sim = semantic_sim_edges(ix, tau, max_per_row=64, batch=1024)
-    got = set(zip(src.cpu().tolist(), dst.cpu().tolist()))
+    # every pair a < b with cos >= tau, no per-row cap (the cluster rows have ~40 partners each)
+    got = set()
+    for a0, offs, dst, sim in semantic_sim_edges(ix, tau, batch=1024):
+        offs, dst, sim = offs.cpu().numpy(), dst.cpu().numpy(), sim.cpu().numpy()
+        for j in range(len(offs) - 1):
+            seg = dst[offs[j]:offs[j + 1]]
+            assert np.all(np.diff(seg) > 0) and (len(seg) == 0 or seg[0] > a0 + j)          # ascending, strictly above the row itself
+            assert np.allclose(sim[offs[j]:offs[j + 1]], S[a0 + j, seg], atol=1e-3)
+            got.update((a0 + j, int(b)) for b in seg)
     iu = np.triu_indices(N, 1)
     sure = set(zip(*[a[S[iu] >= tau + 1e-3].tolist() for a in iu]))
     maybe = set(zip(*[a[S[iu] >= tau - 1e-3].tolist() for a in iu]))
     assert sure <= got <= maybe
     assert all(a < b for a, b in got) and 7 not in {a for a, _ in got} | {b for _, b in got}
+
+
+@pytest.mark.parametrize("N,D,B,dtype", [(3000, 64, 3000, torch.bfloat16), (70000, 128, 5, torch.float16), (999, 40, 130, torch.bfloat16)])
+def test_range_search_returns_every_hit(N, D, B, dtype):
+    """b200r_range_count / b200r_range_fill: exact-size output, every row at or above the threshold, ascending ids, no cap --
+    including the reference's own degenerate case (edge_builder.py:47-48: a 1-D fake embedding makes EVERY pair qualify)."""
+    from a_modular_rag_framework_b200.index import range_search
+    rng = np.random.default_rng(N + B)
+    if N == 3000:
+        Xn = np.ones((N, D), dtype=np.float32) * rng.uniform(0.5, 2.0, size=(N, 1)).astype(np.float32)   # all cosines == 1
+        Xn[17] = 0.0                                                                                  # zero norm -> 0.0, never an edge
+    else:
+        Xn = rng.standard_normal((N, D)).astype(np.float32)
+        Xn[: N // 3] = Xn[0] + 0.5 * rng.standard_normal((N // 3, D)).astype(np.float32)               # a big near-duplicate cluster
+    X = _to_dev(Xn, dtype)
+    Xf = _as_f32(X)
+    ix = _index(X, id_base=5)
+    Q = X[:B].contiguous()
+    S = O.score_matrix(Xf[:B], Xf)
+    tau = 0.8
+    offs, ids, sc = range_search(ix, Q, tau)
+    offs, ids, sc = offs.cpu().numpy(), ids.cpu().numpy() - 5, sc.cpu().numpy()
+    assert offs[0] == 0 and offs[-1] == len(ids) == len(sc)
+    total_sure = 0
+    for b in range(B):
+        seg = ids[offs[b]:offs[b + 1]]
+        assert np.all(np.diff(seg) > 0)
+        sure = np.nonzero(S[b] >= tau + 1e-3)[0]
+        maybe = S[b] >= tau - 1e-3
+        assert np.all(maybe[seg]) and np.isin(sure, seg).all()
+        assert np.allclose(sc[offs[b]:offs[b + 1]], S[b, seg], atol=1e-3)
+        total_sure += len(sure)
+    if N == 3000:
+        assert len(ids) == (N - 1) * (N - 1)                      # every non-zero row pairs with every non-zero row (itself included)
+        own = torch.arange(B, device=_dev(), dtype=torch.int64) + 5
+        offs2, ids2, _ = range_search(ix, Q, tau, id_gt=own)
+        assert int(offs2[-1]) == (N - 1) * (N - 2) // 2            # each unordered pair once, no self pairs
+        assert bool((ids2 > own.repeat_interleave(offs2[1:] - offs2[:-1])).all())
+    # nothing qualifies
+    o3, i3, s3 = range_search(ix, Q[:2].contiguous(), 1.5)
+    assert o3.tolist() == [0, 0, 0] and i3.numel() == 0
 
 
 def _device_unit_rows(n, d, seed, dtype=torch.bfloat16, block=1 << 19):
@@ -369,3 +417,68 @@ def test_benchmark_scale_configs_vs_oracle(N, D, B, k, nq):
     assert bool((scores[:, :-1] >= scores[:, 1:]).all())
     srt = ids.sort(dim=1).values
     assert bool((srt[:, 1:] != srt[:, :-1]).all())
+
+
+def test_search_captured_in_a_cuda_graph_replays():
+    """A whole search step (init, tile phases, selects) captured once and replayed with new queries in the static buffer."""
+    from a_modular_rag_framework_b200.index import CapturedSearch
+    g = torch.Generator(device="cuda").manual_seed(3)
+    X = torch.randn((200000, 64), generator=g, device=_dev()).to(torch.bfloat16)
+    ix = _index(X)
+    for B in (1, 16, 300):
+        Qs = [torch.randn((B, 64), generator=g, device=_dev()).to(torch.bfloat16) for _ in range(3)]
+        cap = CapturedSearch(ix, Qs[0], 50)
+        for q in Qs:
+            s, i = cap(q)
+            rs, ri = ix.search(q, 50)
+            assert torch.equal(i, ri) and torch.equal(s, rs)
+
+
+@pytest.mark.parametrize("N,D,B,k,metric", [
+    (150000, 768, 1, 100, "cos"),
+    (150000, 768, 16, 100, "cos"),          # a full 16-query pass: the corpus is streamed once
+    (300000, 384, 9, 100, "ip"),            # several phases
+    (40001, 256, 7, 33, "cos"),             # ragged last tile
+    (5000, 100, 5, 50, "cos"),              # D % 32 != 0: the last K slice is partly out of bounds (zero-filled)
+    (17, 64, 3, 5, "cos"),                  # fewer rows than one tile
+    (1, 16, 1, 1, "ip"),
+    (60000, 768, 40, 10, "cos"),            # three groups of 16 queries
+    (30000, 1024, 4, 20, "cos"),
+])
+def test_fp32_tensor_path(N, D, B, k, metric):
+    """fp32 corpora on tcgen05 kind::tf32 with both operands split into two exact tf32 pieces (rows_f32.cu): the fp32 bar,
+    1e-5 relative against the fp64 oracle, on data whose components span many binades (so the low mantissa bits matter)."""
+    rng = np.random.default_rng(5 * N + D + B)
+    Xn = (rng.standard_normal((N, D)) * np.exp2(rng.integers(-6, 7, size=(N, D)))).astype(np.float32)
+    Qn = (rng.standard_normal((B, D)) * np.exp2(rng.integers(-6, 7, size=(B, D)))).astype(np.float32)
+    if N > 100:
+        Xn[N // 2] = Xn[3]                  # exact duplicate: ties -> lower id first
+        Qn[0] = Xn[3]
+    X, Q = torch.from_numpy(Xn).to(_dev()), torch.from_numpy(Qn).to(_dev())
+    ix = _index(X, metric=metric, id_base=11)
+    S = O.score_matrix(Qn, Xn, metric)
+    scores, ids = ix.search(Q, k, path="gemm")
+    _check_against_scores(scores, ids, S, k, 1e-5, id_base=11)
+    s_auto, i_auto = ix.search(Q, k)                       # auto == the tensor path for fp32 corpora it fits
+    assert torch.equal(i_auto, ids) and torch.equal(s_auto, scores)
+    if N > 100:
+        assert ids[0, :2].tolist() == [3 + 11, N // 2 + 11]
+    # the CUDA-core scan agrees to the same bar
+    s2, i2 = ix.search(Q, k, path="scan")
+    _check_against_scores(s2, i2, S, k, 1e-5, id_base=11)
+
+
+def test_fp32_split_is_tight_on_nearly_parallel_vectors():
+    """Cosines packed within 1e-6 of each other near 1.0: a plain tf32 product (2^-11 per operand) would scramble them; the
+    split-precision path must rank them like the fp64 oracle wherever they differ by more than the fp32 bar."""
+    rng = np.random.default_rng(1)
+    N, D, k = 20000, 768, 50
+    base = rng.standard_normal(D).astype(np.float32)
+    Xn = base[None, :] * (1.0 + 1e-3 * rng.standard_normal((N, D)).astype(np.float32))
+    Qn = base[None, :].copy()
+    ix = _index(torch.from_numpy(Xn).to(_dev()), metric="cos")
+    scores, ids = ix.search(torch.from_numpy(Qn).to(_dev()), k, path="gemm")
+    S = O.score_matrix(Qn, Xn)
+    got = scores.cpu().numpy()[0].astype(np.float64)
+    assert np.max(np.abs(got - S[0, ids.cpu().numpy()[0]])) < 3e-7        # far inside 1e-5: the split loses < 2^-22 per operand
+    _check_against_scores(scores, ids, S, k, 1e-5)
