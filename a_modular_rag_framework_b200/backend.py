@@ -166,6 +166,17 @@ class CudaEngine:
                                                                hs.data_ptr(), hi.data_ptr(), None))
         return scores, ids
 
+    # -- MMR post-filter ---------------------------------------------------------------------------------------
+    def mmr(self, ids: np.ndarray, scores: np.ndarray, top_k: int, lam: float) -> np.ndarray:
+        """[B, P] candidate rows / scores -> positions [B, top_k] of the MMR picks (app/utils/similarity.py:33-62)."""
+        from .index import mmr_diversify
+        if len(self.devs) > 1:
+            raise NotImplementedError("MMR needs the candidates' rows on one device; it is not available with devices=[...]")
+        t = self.torch
+        _, _, pos = mmr_diversify(self.shards[0], t.from_numpy(np.ascontiguousarray(ids, dtype=np.int64)).to(self.device),
+                                  t.from_numpy(np.ascontiguousarray(scores, dtype=np.float32)).to(self.device), top_k, lam)
+        return pos.cpu().numpy()
+
     # -- graph stage ------------------------------------------------------------------------------------------
     def expand_rescore(self, Q: np.ndarray, seeds: np.ndarray, window: int, alpha_dense: float, alpha_graph: float, k: int,
                        graph: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]] = None) -> Dict[str, np.ndarray]:
@@ -241,6 +252,8 @@ class B200RetrievalBackend:
     devices: Optional[List[int]] = None             # e.g. [0,...,7]: this process drives all of them, corpus row-sharded
     metric: str = "cos"
     graph_cache_size: int = 4096                    # per-graph_id graphs kept parsed (LRU)
+    mmr_lambda: Optional[float] = None              # not None: the final top_k are picked from the best `mmr_pool` fused candidates by
+    mmr_pool: int = 100                             # MMR on the device (mmr_diversify, app/utils/similarity.py:33-62; item vectors = corpus rows)
     text_searcher: Any = None                       # optional object with .search(queries=, top_k=) -> raw hits (host BM25)
     expander: Any = None                            # optional object with .expand(query=, trace_id=) -> List[str]
     engine: Any = None                              # injectable compute engine (tests); default CudaEngine
@@ -413,6 +426,8 @@ class B200RetrievalBackend:
         with _span("Backend/GraphExpand", self.sink, t0):
             if valid and self.alpha_graph != 0.0:
                 self._graph_stage(batch, valid, Q)
+        if self.mmr_lambda is not None and valid:
+            batch.apply_mmr(float(self.mmr_lambda), int(self.mmr_pool))
         return batch
 
     def _graph_stage(self, batch: "RetrievalBatch", valid: List[int], Q: np.ndarray) -> None:
@@ -499,6 +514,7 @@ class RetrievalBatch:
         self._dense_s: Optional[np.ndarray] = None
         self._dense_i: Optional[np.ndarray] = None
         self._graph: Dict[int, Tuple[Dict[str, np.ndarray], int]] = {}   # request -> (group arrays, row in them)
+        self._order: Dict[int, np.ndarray] = {}     # request -> MMR order of its candidates
 
     # -- filled by the backend ------------------------------------------------------------------------------
     def set_dense(self, valid: List[int], Q: np.ndarray, scores: np.ndarray, ids: np.ndarray) -> None:
@@ -509,6 +525,24 @@ class RetrievalBatch:
         for j, i in enumerate(idx):
             self._graph[i] = (out, j)
 
+    def apply_mmr(self, lam: float, pool: int) -> None:
+        """Re-order every request's best `pool` candidates by MMR (ONE device call for the batch); the rest keep their order."""
+        idx = [i for i in range(len(self.reqs)) if len(self.columns(i)["rows"])]
+        if not idx:
+            return
+        P = max(1, min(pool, max(len(self.columns(i)["rows"]) for i in idx)))
+        ids = np.full((len(idx), P), -1, dtype=np.int64)
+        sc = np.full((len(idx), P), -np.inf, dtype=np.float32)
+        for j, i in enumerate(idx):
+            c = self.columns(i)
+            n = min(P, len(c["rows"]))
+            ids[j, :n], sc[j, :n] = c["rows"][:n], c["fused"][:n]
+        pos = np.asarray(self.be.engine.mmr(ids, sc, P, lam))
+        for j, i in enumerate(idx):
+            n = len(self.columns(i)["rows"])
+            head = [int(x) for x in pos[j] if x >= 0]
+            self._order[i] = np.asarray(head + list(range(min(P, n), n)), dtype=np.int64)
+
     def dense_rows(self, i: int) -> np.ndarray:
         p = self._pos.get(i)
         if p is None:
@@ -518,7 +552,16 @@ class RetrievalBatch:
 
     # -- columnar accessors ---------------------------------------------------------------------------------
     def columns(self, i: int) -> Dict[str, np.ndarray]:
-        """Candidates of request i BEFORE the text channel / top_k cut, best first: rows, fused, gnorm, dnorm, hop, cos."""
+        """Candidates of request i BEFORE the text channel / top_k cut, best first (MMR order if enabled): rows, fused, gnorm,
+        dnorm, hop, cos."""
+        c = self._columns(i)
+        order = self._order.get(i)
+        if order is not None:
+            c = {k: (v[order] if isinstance(v, np.ndarray) else v) for k, v in c.items()}
+            c["mmr"] = True
+        return c
+
+    def _columns(self, i: int) -> Dict[str, np.ndarray]:
         if i in self._graph:
             out, j = self._graph[i]
             keep = out["id"][j] >= 0
@@ -590,8 +633,11 @@ class RetrievalBatch:
                     meta = dict(tmap[nid]["meta"])
                     meta["score_text_norm"], meta["score_graph_norm"], meta["score_dense_norm"] = ts, 0.0, 0.0
                     fused[nid] = {"id": nid, "score": float(be.alpha_text * ts), "meta": meta, "_row": 1 << 62}
-        ordered = sorted(fused.values(), key=lambda h: h["_row"])          # enumerate in id order ...
-        ordered.sort(key=lambda h: h["score"], reverse=True)               # ... so the stable sort breaks ties by lower id
+        if c.get("mmr") and not use_text:
+            ordered = list(fused.values())                                     # MMR pick order (dicts keep insertion order)
+        else:
+            ordered = sorted(fused.values(), key=lambda h: h["_row"])          # enumerate in id order ...
+            ordered.sort(key=lambda h: h["score"], reverse=True)               # ... so the stable sort breaks ties by lower id
         hits = [{"id": h["id"], "score": h["score"], "meta": h["meta"]} for h in ordered[:top_k]]
         has_dense = i in self._pos and len(self.dense_rows(i)) > 0
         diagnostics = {

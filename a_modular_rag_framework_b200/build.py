@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libb200r.so")
-SOURCES = ["api.cu", "gemm_topk.cu", "scan_topk.cu", "scan_bulk.cu", "rows_i8.cu", "rows_f32.cu", "select_merge.cu", "csr_expand.cu", "comm.cu"]
+SOURCES = ["api.cu", "gemm_topk.cu", "scan_topk.cu", "scan_bulk.cu", "rows_i8.cu", "rows_f32.cu", "select_merge.cu", "csr_expand.cu", "comm.cu", "mmr.cu"]
 HEADERS = ["common.cuh", "comm.cuh", "internal.h", "tc_ptx.cuh", os.path.join("..", "..", "include", "b200r.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

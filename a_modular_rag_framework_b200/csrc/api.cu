@@ -725,6 +725,16 @@ int b200r_range_fill(uint64_t index, const void* Q, int32_t B, float min_score, 
   return launch_range_unpack(nullptr, total, nullptr, B, 0.f, ix->id_base, out_ids, out_scores, st);
 }
 
+int b200r_mmr_diversify(uint64_t index, const int64_t* cand_ids, const float* cand_scores, int32_t B, int32_t P, int32_t top_k,
+                        float lambda_weight, int64_t* out_ids, float* out_scores, int32_t* out_pos, void* stream) {
+  Index* ix = get_index(index);
+  if (!ix) return B200R_ESTATE;
+  if (!cand_ids || !cand_scores || !out_ids || !out_scores || !out_pos) { set_error("null pointer"); return B200R_EINVAL; }
+  if (B <= 0 || P <= 0 || top_k <= 0 || P > 16384) { set_error("bad B / P / top_k (%d / %d / %d)", B, P, top_k); return B200R_EINVAL; }
+  B200R_CUDA_CHECK(cudaSetDevice(ix->device));
+  return launch_mmr(ix, cand_ids, cand_scores, B, P, top_k, lambda_weight, out_ids, out_scores, out_pos, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int b200r_merge_topk(int device, const float* cand_scores, const int64_t* cand_ids, int32_t G, int32_t B, int32_t kin,
                      int32_t k, float* out_scores, int64_t* out_ids, void* stream) {
   if (!cand_scores || !cand_ids || !out_scores || !out_ids) { set_error("null pointer"); return B200R_EINVAL; }

@@ -148,6 +148,25 @@ class DenseIndex:
         return scores, ids
 
 
+def mmr_diversify(index: DenseIndex, cand_ids: torch.Tensor, cand_scores: torch.Tensor, top_k: int, lambda_weight: float = 0.7
+                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """mmr_diversify (app/utils/similarity.py:33-62) for B candidate lists [B, P] at once; the item vectors are the corpus rows
+    behind the ids.  -> (ids i64 [B, top_k], scores f32 [B, top_k], pos i32 [B, top_k]) in pick order."""
+    _require_cuda(cand_ids, "cand_ids")
+    _require_cuda(cand_scores, "cand_scores")
+    if cand_ids.dtype != torch.int64 or cand_scores.dtype != torch.float32 or cand_ids.shape != cand_scores.shape or cand_ids.dim() != 2:
+        raise ValueError("cand_ids i64 / cand_scores f32 must both be [B, P]")
+    B, P = (int(x) for x in cand_ids.shape)
+    dev = index.device
+    ids = torch.empty((B, top_k), dtype=torch.int64, device=dev)
+    sc = torch.empty((B, top_k), dtype=torch.float32, device=dev)
+    pos = torch.empty((B, top_k), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.load().b200r_mmr_diversify(index.handle, cand_ids.data_ptr(), cand_scores.data_ptr(), B, P, int(top_k), float(lambda_weight),
+                                             ids.data_ptr(), sc.data_ptr(), pos.data_ptr(), _stream_ptr(dev)))
+    return ids, sc, pos
+
+
 class CapturedSearch:
     """One search step (local or row-sharded: search + exchange + merge) captured into a CUDA graph and replayed: a
     batch-1 step is a dozen short kernels, so its latency is the host's launch rate unless they go down as ONE graph

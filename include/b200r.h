@@ -158,6 +158,16 @@ int b200r_search_sharded_host_all(const uint64_t* indexes, const uint64_t* comms
                                   int32_t k, int32_t path, float* out_scores_host, int64_t* out_ids_host,
                                   void* const* streams);
 
+/* ---- MMR diversification (optional post-filter) ----------------------------------------------------------------
+ * Replaces mmr_diversify (app/utils/similarity.py:33-62) for B candidate lists at once: cand_ids / cand_scores [B, P]
+ * (global ids, < 0 = padding; list order matters: ties go to the earlier item), the item vectors are the corpus rows
+ * behind the ids (an id whose row is not in this index has no vector: similarity 0, like a None vector).  Greedy:
+ * first pick = best score, then argmax of lambda*score - (1-lambda)*max(0, max cos to the picked ones).
+ * out_ids / out_scores / out_pos [B, top_k]: the picks in order, their original scores and positions ((-1, -inf, -1)
+ * once a list is exhausted). */
+int b200r_mmr_diversify(uint64_t index, const int64_t* cand_ids, const float* cand_scores, int32_t B, int32_t P, int32_t top_k,
+                        float lambda_weight, int64_t* out_ids, float* out_scores, int32_t* out_pos, void* stream);
+
 /* ---- merge of per-shard top-k lists ----------------------------------------------------------
  * The same stable-sort rule applied to the union of G lists (one per GPU after the NCCL all-gather):
  * cand_scores/cand_ids [G, B, kin] -> out [B, k], (score desc, id asc); ids < 0 are padding.

@@ -23,6 +23,7 @@ Reference lines each function follows (paths relative to the reference repo root
 * ``minmax_norm``            retrieval_backend.py:296-301
 * ``fuse_and_rank``          retrieval_backend.py:357-372 (weighted sum, stable sort, slice)
 * ``expand_rescore``         composition a4+a1+a6+a3 of SURVEY.md section 8(a)
+* ``mmr_diversify``          app/utils/similarity.py:33-62 (+ cosine :11-16)
 """
 from __future__ import annotations
 
@@ -310,6 +311,38 @@ def expand_rescore(q: np.ndarray, X: np.ndarray, row_ptr: np.ndarray, col_idx: n
     dense = {int(c): float(s) for c, s in zip(cand, S)}
     graph = {int(c): decay(dist[int(c)]) for c in cand}
     return fuse_and_rank(dense, graph, alpha_dense, alpha_graph, k), dist
+
+
+def mmr_diversify(items: Sequence[Tuple[int, float, Optional[Sequence[float]]]], top_k: int = 20, lambda_weight: float = 0.7
+                  ) -> List[Tuple[int, float, Optional[Sequence[float]]]]:
+    """Restatement of mmr_diversify (app/utils/similarity.py:33-62): greedy MMR; the first pick maximises the raw score, later
+    picks lambda*score - (1-lambda)*sim_max with sim_max starting at 0.0 (negative cosines never count) and cosine as in
+    similarity.py:11-16 (0.0 for empty / zero vectors); `val > best_val` is strict, so ties go to the earlier item."""
+    def cos(u, v):
+        if u is None or v is None or len(u) == 0 or len(v) == 0:
+            return 0.0
+        du = math.sqrt(sum(x * x for x in u))
+        dv = math.sqrt(sum(x * x for x in v))
+        if du == 0 or dv == 0:
+            return 0.0
+        return sum(x * y for x, y in zip(u, v)) / (du * dv)
+    selected: List[Tuple[int, float, Optional[Sequence[float]]]] = []
+    candidates = list(items)
+    while candidates and len(selected) < top_k:
+        best, best_val = None, -1e9
+        for cid, cscore, cvec in candidates:
+            if not selected:
+                val = cscore
+            else:
+                sim_max = 0.0
+                for _, _, svec in selected:
+                    sim_max = max(sim_max, cos(cvec, svec) if (cvec is not None and svec is not None) else 0.0)
+                val = lambda_weight * cscore - (1 - lambda_weight) * sim_max
+            if val > best_val:
+                best_val, best = val, (cid, cscore, cvec)
+        selected.append(best)
+        candidates = [x for x in candidates if x[0] != best[0]]
+    return selected
 
 
 # ----------------------------------------------------------------------------- comparison helper

@@ -12,6 +12,8 @@ produced by code imported from /root/reference:
 * DenseReranker._cosine                 app/modules/retrieval/retrieval_backend.py:192-197
 * HybridRetrievalBackend._minmax_norm   app/modules/retrieval/retrieval_backend.py:296-301
 * build_index / expand_qmatch_neighbors app/modules/retrieval/graph_utils.py:25-55, 58-129
+* mmr_diversify                         app/utils/similarity.py:33-62 (own seeded stream, appended last so that the
+  earlier fixtures stay byte-identical)
 * the stable ``sort(key=score, reverse=True)[:k]`` rule of retrieval_backend.py:371-372 is applied
   here with the same Python ``list.sort`` the reference uses, on candidates enumerated in id order.
 
@@ -189,6 +191,28 @@ def gen_expand_rescore(rng):
     return cases
 
 
+def gen_mmr(rng):
+    """mmr_diversify (similarity.py:33-62) on bf16-representable vectors: clustered items (so diversity matters), exact
+    score ties, a None vector, a zero vector, top_k beyond the list, lambda 0 / 0.3 / 0.7 / 1."""
+    from app.utils.similarity import mmr_diversify
+    cases = []
+    for n, D, top_k, lam in ((12, 16, 5, 0.7), (40, 32, 10, 0.3), (25, 24, 40, 0.7), (30, 16, 8, 0.0), (30, 16, 8, 1.0), (1, 8, 3, 0.5)):
+        centers = rng.standard_normal((max(2, n // 6), D)).astype(np.float32)
+        X = centers[rng.integers(0, len(centers), n)] + 0.15 * rng.standard_normal((n, D)).astype(np.float32)
+        X = bf16_bits_to_f32(f32_to_bf16_bits(X))
+        scores = np.round(rng.uniform(0.0, 1.0, n), 2).astype(np.float32)       # two decimals -> exact ties occur
+        vec_none = int(rng.integers(0, n)) if n > 3 else -1
+        vec_zero = int(rng.integers(0, n)) if n > 5 else -1
+        if vec_zero >= 0:
+            X[vec_zero] = 0.0
+        ids = (rng.permutation(1000)[:n] + 7).tolist()
+        items = [(ids[i], float(scores[i]), None if i == vec_none else X[i].astype(float).tolist()) for i in range(n)]
+        picked = mmr_diversify(items, top_k=top_k, lambda_weight=lam)
+        cases.append({"ids": ids, "scores": [float(s) for s in scores], "X_bf16": f32_to_bf16_bits(X).tolist(), "none": vec_none,
+                      "top_k": top_k, "lambda": lam, "picked": [p[0] for p in picked]})
+    return cases
+
+
 def main():
     rng = np.random.default_rng(20261018)
     with open(os.path.join(HERE, "cosine_kat.json"), "w") as f:
@@ -202,6 +226,8 @@ def main():
         json.dump(gen_minmax(rng), f)
     with open(os.path.join(HERE, "expand_rescore_cases.json"), "w") as f:
         json.dump(gen_expand_rescore(rng), f)
+    with open(os.path.join(HERE, "mmr_cases.json"), "w") as f:
+        json.dump(gen_mmr(np.random.default_rng(20261019)), f)
     print("golden fixtures written to", HERE)
 
 

@@ -59,6 +59,15 @@ class OracleEngine:
     def has_graph(self):
         return self.row_ptr is not None
 
+    def mmr(self, ids, scores, top_k, lam):
+        out = np.full((len(ids), top_k), -1, dtype=np.int32)
+        for b in range(len(ids)):
+            items = [(j, float(scores[b][j]), self.X[int(r)].astype(float).tolist() if 0 <= int(r) < self.N else None)
+                     for j, r in enumerate(ids[b]) if r >= 0]
+            picks = O.mmr_diversify(items, top_k=top_k, lambda_weight=lam)
+            out[b, :len(picks)] = [p[0] for p in picks]
+        return out
+
     def expand_rescore(self, Q, seeds, window, alpha_dense, alpha_graph, k, graph=None):
         self.calls["expand"] += 1
         row_ptr, col_idx, node_rows = (self.row_ptr, self.col_idx, None) if graph is None else graph

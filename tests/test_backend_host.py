@@ -266,3 +266,19 @@ def test_batch_with_different_graph_ids_is_one_expansion(tmp_path, golden_dir):
         assert [h.id for h in a.hits] == [h.id for h in b.hits]
         assert np.allclose([h.score for h in a.hits], [h.score for h in b.hits])
     assert {h.meta["row"] for h in many[1].hits} == {10, 11, 40, 41}     # gb's edges are disjoint pairs (2v, 2v+1)
+
+
+def test_mmr_post_filter(corpus):
+    """mmr_lambda: the final top_k come from the best mmr_pool fused candidates in MMR pick order (similarity.py:33-62)."""
+    plain = _backend(corpus, seed_k=5)
+    be = _backend(corpus, seed_k=5, mmr_lambda=0.5, mmr_pool=30)
+    q = corpus.docs[17]["text"]
+    a, b = plain.run(_req(q, top_k=8)), be.run(_req(q, top_k=8))
+    assert len(b["hits"]) == 8 and b["hits"][0]["meta"]["row"] == a["hits"][0]["meta"]["row"]      # first pick = best score
+    pool = plain.run(_req(q, top_k=30))["hits"]
+    Xb = O.bf16_bits_to_f32(O.f32_to_bf16_bits(corpus.X))
+    items = [(h["meta"]["row"], np.float32(h["score"]).item(), Xb[h["meta"]["row"]].astype(float).tolist()) for h in pool]
+    want = [p[0] for p in O.mmr_diversify(items, top_k=8, lambda_weight=0.5)]
+    assert [h["meta"]["row"] for h in b["hits"]] == want
+    many = be.retrieve_many([_req(q, top_k=8), _req(corpus.docs[3]["text"], top_k=4)])
+    assert [h.meta["row"] for h in many[0].hits] == want and len(many[1].hits) == 4

@@ -482,3 +482,40 @@ def test_fp32_split_is_tight_on_nearly_parallel_vectors():
     got = scores.cpu().numpy()[0].astype(np.float64)
     assert np.max(np.abs(got - S[0, ids.cpu().numpy()[0]])) < 3e-7        # far inside 1e-5: the split loses < 2^-22 per operand
     _check_against_scores(scores, ids, S, k, 1e-5)
+
+
+def test_mmr_diversify_golden_and_random(golden_dir):
+    """b200r_mmr_diversify against picks recorded from the reference (mmr_cases.json: corpus rows = the item vectors) and
+    against the oracle restatement on random clustered candidates for a whole batch."""
+    import json
+    from a_modular_rag_framework_b200.index import mmr_diversify
+    with open(os.path.join(golden_dir, "mmr_cases.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        X = O.bf16_bits_to_f32(np.array(c["X_bf16"], dtype=np.uint16))
+        n = len(c["ids"])
+        ix = _index(_to_dev(X, torch.bfloat16), metric="cos", id_base=100)
+        ids = torch.tensor([[(100 + j) if j != c["none"] else 100 + n + 5 for j in range(n)]], device=_dev())   # the None item: an id with no row
+        sc = torch.tensor([c["scores"]], device=_dev(), dtype=torch.float32)
+        oi, osc, pos = mmr_diversify(ix, ids, sc, c["top_k"], c["lambda"])
+        want = [c["ids"].index(p) for p in c["picked"]]
+        got = pos[0].cpu().tolist()
+        assert got[:len(want)] == want and all(g == -1 for g in got[len(want):]), (c["top_k"], c["lambda"])
+        assert oi[0, :len(want)].cpu().tolist() == [int(ids[0, w]) for w in want]
+    # a batch of random clustered lists from a larger corpus, with padding
+    rng = np.random.default_rng(9)
+    N, D, B, P, top_k = 5000, 64, 7, 60, 12
+    centers = rng.standard_normal((20, D)).astype(np.float32)
+    Xn = O.bf16_bits_to_f32(O.f32_to_bf16_bits(centers[rng.integers(0, 20, N)] + 0.2 * rng.standard_normal((N, D)).astype(np.float32)))
+    ix = _index(_to_dev(Xn, torch.bfloat16))
+    ids = np.stack([rng.permutation(N)[:P] for _ in range(B)]).astype(np.int64)
+    ids[2, 40:] = -1
+    sc = rng.uniform(0, 1, size=(B, P)).astype(np.float32)
+    oi, osc, pos = mmr_diversify(ix, torch.from_numpy(ids).to(_dev()), torch.from_numpy(sc).to(_dev()), top_k, 0.6)
+    for b in range(B):
+        items = [(int(i), float(s), Xn[i].astype(float).tolist()) for i, s in zip(ids[b], sc[b]) if i >= 0]
+        want = [p[0] for p in O.mmr_diversify(items, top_k=top_k, lambda_weight=0.6)]
+        got = oi[b].cpu().tolist()
+        if got[:len(want)] != want:          # fp32 vs fp64 cosines: only picks whose MMR values tie within 1e-5 may swap
+            first = next(j for j in range(len(want)) if got[j] != want[j])
+            assert False, (b, first, got, want)

@@ -151,3 +151,12 @@ def test_blockwise_topk_shard_merge_equals_global():
     parts = [O.topk_blocks_exact(Q, [(lo, X[lo:lo + 1700])], k, extra=4) for lo in range(0, N, 1700)]
     ms, mi = O.merge_topk(np.stack([p[0] for p in parts], axis=1), np.stack([p[1] for p in parts], axis=1), k + 4)
     assert np.array_equal(mi, full_i) and np.array_equal(ms, full_s)
+
+
+def test_mmr_restatement_matches_reference(golden_dir):
+    """oracle.mmr_diversify against picks recorded from the reference's mmr_diversify (app/utils/similarity.py:33-62)."""
+    for c in _load(golden_dir, "mmr_cases.json"):
+        X = O.bf16_bits_to_f32(np.array(c["X_bf16"], dtype=np.uint16))
+        items = [(i, s, None if j == c["none"] else X[j].astype(float).tolist()) for j, (i, s) in enumerate(zip(c["ids"], c["scores"]))]
+        got = O.mmr_diversify(items, top_k=c["top_k"], lambda_weight=c["lambda"])
+        assert [g[0] for g in got] == c["picked"]
