@@ -29,6 +29,7 @@ EXPORTS = [
     "b200r_merge_topk", "b200r_merge_topk_packed", "b200r_mmr_diversify", "b200r_profile_enable", "b200r_profile_read", "b200r_profile_dump",
     "b200r_graph_create", "b200r_graph_create_mapped", "b200r_graph_destroy",
     "b200r_merge_topk_src", "b200r_expand_max_candidates", "b200r_expand_rescore", "b200r_expand_workspace_bytes", "b200r_expand_rescore_sharded", "b200r_expand_rescore_exchange",
+    "b200r_expand_big_workspace_bytes", "b200r_expand_rescore_big",
 ]
 
 
@@ -109,6 +110,10 @@ def load() -> ctypes.CDLL:
     lib.b200r_expand_rescore_sharded.argtypes = [c_uint64, c_uint64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_int32,
                                                  c_int32, c_int64, c_int64, c_void_p, c_size_t, c_void_p,
                                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.b200r_expand_big_workspace_bytes.argtypes = [c_uint64]
+    lib.b200r_expand_big_workspace_bytes.restype = c_size_t
+    lib.b200r_expand_rescore_big.argtypes = [c_uint64, c_uint64, c_void_p, c_void_p, c_int32, c_int32, c_float, c_float, c_int32, c_void_p, c_size_t,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.b200r_expand_rescore_exchange.argtypes = [c_uint64, c_uint64, c_uint64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float,
                                                   c_int32, c_int64, c_int32, c_void_p, c_size_t,
                                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]

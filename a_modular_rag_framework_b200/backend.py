@@ -195,7 +195,7 @@ class CudaEngine:
             sh = t.from_numpy(np.ascontiguousarray(seeds[b0:b1], dtype=np.int64))
             if len(self.devs) == 1:
                 res = expand_rescore(self.shards[0], graphs[0], qh.to(self.device), sh.to(self.device), window,
-                                     alpha_dense, alpha_graph, k, check_status=False)
+                                     alpha_dense, alpha_graph, k, check_status=False, unbounded=True)
             else:
                 res = expand_rescore_exchange_all(self.shards, graphs, self.comms, self.N, qh, sh, window, alpha_dense, alpha_graph, k)
             for key in GRAPH_KEYS:

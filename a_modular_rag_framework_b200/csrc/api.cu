@@ -887,6 +887,34 @@ int b200r_expand_rescore(uint64_t index, uint64_t graph, const void* Q, const in
 
 size_t b200r_expand_workspace_bytes(int32_t B) { return B > 0 ? expand_workspace_bytes(B) : 0; }
 
+size_t b200r_expand_big_workspace_bytes(uint64_t graph) {
+  Graph* g = get_graph(graph);
+  return g ? expand_big_workspace_bytes(g->V) : 0;
+}
+
+int b200r_expand_rescore_big(uint64_t index, uint64_t graph, const void* Q, const int64_t* seeds, int32_t S, int32_t window,
+                             float alpha_dense, float alpha_graph, int32_t k, void* workspace, size_t workspace_bytes, float* out_scores,
+                             int64_t* out_ids, int32_t* out_hops, float* out_graph_norm, float* out_dense_norm, float* out_cos,
+                             int32_t* out_ncand, void* stream) {
+  Index* ix = get_index(index);
+  Graph* g = get_graph(graph);
+  if (!ix || !g) return B200R_ESTATE;
+  if (ix->device != g->device) { set_error("index and graph live on different devices"); return B200R_EINVAL; }
+  if (!Q || !seeds || !workspace || !out_scores || !out_ids || !out_hops || !out_graph_norm || !out_dense_norm || !out_cos || !out_ncand) {
+    set_error("null pointer");
+    return B200R_EINVAL;
+  }
+  if (S <= 0 || k <= 0 || k > B200R_MAX_K || window < 0 || window > 255) { set_error("bad S/k/window (%d/%d/%d)", S, k, window); return B200R_EINVAL; }
+  if (g->V > 0x7fffffffll) { set_error("unbounded frontier path: V must be < 2^31"); return B200R_EINVAL; }
+  if (workspace_bytes < expand_big_workspace_bytes(g->V) || (reinterpret_cast<uintptr_t>(workspace) & 255)) {
+    set_error("workspace too small or misaligned: need %zu bytes, 256-byte aligned", expand_big_workspace_bytes(g->V));
+    return B200R_ENOMEM;
+  }
+  B200R_CUDA_CHECK(cudaSetDevice(ix->device));
+  return launch_expand_rescore_big(ix, g, Q, seeds, S, window, alpha_dense, alpha_graph, k, out_scores, out_ids, out_hops, out_graph_norm,
+                                   out_dense_norm, out_cos, out_ncand, workspace, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int b200r_expand_rescore_exchange(uint64_t index, uint64_t graph, uint64_t comm, const void* Q, const int64_t* seeds, int32_t B,
                                   int32_t S, int32_t window, float alpha_dense, float alpha_graph, int32_t k, int64_t n_total_rows,
                                   int32_t phase, void* workspace, size_t workspace_bytes, float* out_scores, int64_t* out_ids,

@@ -1000,6 +1000,195 @@ int launch_expand_rescore_exchange(const Index* ix, const Graph* g, const Comm* 
   return B200R_EINVAL;
 }
 
+
+// ------------------------------------------------------------------------------------------------ unbounded frontier
+// The reference's BFS has no candidate limit (graph_utils.py:109-127).  A query that overflows the 8192-candidate
+// shared-memory instantiation is redone here with everything in global memory: a visited BITMAP over the graph's nodes,
+// a candidate array that can hold every node, one grid-wide kernel per BFS level, the same gather kernel for the
+// re-score, an element-wise fusion into 64-bit keys and the list-select kernel for the top-k.  One query per call.
+struct BigWs {
+  u32* visited;      // [V/32 + 1]
+  u32* cand;         // [V] nodes in BFS order, then corpus rows
+  uint8_t* dist;     // [V]
+  float* cos;        // [V]
+  u64* keys;         // [V]
+  int* ncand;        // [1]
+  int* level_end;    // [257]
+  int* nown; float* qinv; u32* mm; u32* seg_start; u32* seg_q; u64* counter;   // what the gather kernel reads (B = 1)
+};
+
+size_t expand_big_workspace_bytes(long long V) {
+  const size_t v = (size_t)V;
+  return align_up((v / 32 + 1) * 4, 256) + align_up(v * 4, 256) * 2 + align_up(v, 256) + align_up(v * 8, 256) + 8 * 256 + align_up(257 * 4, 256);
+}
+
+static BigWs carve_big(void* ws, long long V) {
+  const size_t v = (size_t)V;
+  char* w = reinterpret_cast<char*>(ws);
+  BigWs b;
+  b.visited = reinterpret_cast<u32*>(w); w += align_up((v / 32 + 1) * 4, 256);
+  b.cand = reinterpret_cast<u32*>(w); w += align_up(v * 4, 256);
+  b.cos = reinterpret_cast<float*>(w); w += align_up(v * 4, 256);
+  b.dist = reinterpret_cast<uint8_t*>(w); w += align_up(v, 256);
+  b.keys = reinterpret_cast<u64*>(w); w += align_up(v * 8, 256);
+  b.ncand = reinterpret_cast<int*>(w); w += 256;
+  b.level_end = reinterpret_cast<int*>(w); w += align_up(257 * 4, 256);
+  b.nown = reinterpret_cast<int*>(w); w += 256;
+  b.qinv = reinterpret_cast<float*>(w); w += 256;
+  b.mm = reinterpret_cast<u32*>(w); w += 256;
+  b.seg_start = reinterpret_cast<u32*>(w); w += 256;
+  b.seg_q = reinterpret_cast<u32*>(w); w += 256;
+  b.counter = reinterpret_cast<u64*>(w); w += 256;
+  return b;
+}
+
+__device__ __forceinline__ bool big_visit(u32* visited, u32 v) {
+  const u32 bit = 1u << (v & 31u);
+  return (atomicOr(&visited[v >> 5], bit) & bit) == 0u;
+}
+
+__global__ void bfs_big_seed_kernel(const long long* __restrict__ seeds, int S, long long V, BigWs b) {
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    const long long s = seeds[i];
+    if (s >= 0 && s < V && big_visit(b.visited, (u32)s)) {
+      const int pos = atomicAdd(b.ncand, 1);
+      b.cand[pos] = (u32)s; b.dist[pos] = 0;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) b.level_end[0] = *b.ncand;
+}
+
+// one warp per frontier node, lanes over its adjacency
+__global__ void bfs_big_level_kernel(const long long* __restrict__ row_ptr, const int* __restrict__ col_idx, long long V, int d, BigWs b) {
+  const int lo = d >= 2 ? b.level_end[d - 2] : 0, hi = b.level_end[d - 1];
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int f = lo + warp; f < hi; f += nwarps) {
+    const u32 u = b.cand[f];
+    const long long e0 = __ldg(row_ptr + u), e1 = __ldg(row_ptr + u + 1);
+    for (long long e = e0 + lane; e < e1; e += 32) {
+      const int v = __ldg(col_idx + e);
+      if (v >= 0 && (long long)v < V && big_visit(b.visited, (u32)v)) {
+        const int pos = atomicAdd(b.ncand, 1);
+        b.cand[pos] = (u32)v; b.dist[pos] = (uint8_t)min(d, 255);
+      }
+    }
+  }
+}
+__global__ void bfs_big_close_level_kernel(int d, BigWs b) { b.level_end[d] = *b.ncand; }
+
+// nodes -> corpus rows, and the gather kernel's bookkeeping for a single query
+__global__ void bfs_big_finish_kernel(const long long* __restrict__ node_rows, BigWs b, int* out_ncand) {
+  const int n = *b.ncand;
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, step = gridDim.x * blockDim.x;
+  if (node_rows)
+    for (int i = i0; i < n; i += step) {
+      const long long r = node_rows[b.cand[i]];
+      b.cand[i] = (r >= 0 && r < 0xffffffffll) ? (u32)r : 0xfffffffeu;
+    }
+  if (i0 == 0) {
+    b.nown[0] = n; b.seg_start[0] = 0; b.seg_q[0] = 0;
+    b.counter[0] = (1ull << 32) | (u64)((n + GATHER_ROWS - 1) / GATHER_ROWS);
+    b.mm[0] = 0xffffffffu; b.mm[1] = 0u;
+    *out_ncand = n;
+  }
+}
+
+__global__ void fuse_big_kernel(BigWs b, int window, float alpha_dense, float alpha_graph) {
+  const int n = *b.ncand;
+  int dmax = 0;
+  for (int d = 1; d <= window; ++d) if (b.level_end[d] > b.level_end[d - 1]) dmax = d;
+  const float gmax = hop_decay(0), gmin = hop_decay(dmax);
+  const bool g_flat = !(gmax > gmin);
+  const u32 lo = b.mm[0], hi = b.mm[1];
+  const float cmin = lo <= hi ? ordered_to_f32(lo) : CUDART_INF_F, cmax = lo <= hi ? ordered_to_f32(hi) : -CUDART_INF_F;
+  const bool c_flat = !(cmax > cmin);
+  const float c_den = c_flat ? 1.0f : (cmax - cmin), g_den = g_flat ? 1.0f : (gmax - gmin);
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, step = gridDim.x * blockDim.x;
+  for (int i = i0; i < n; i += step) {
+    const float dn = c_flat ? 0.0f : (b.cos[i] - cmin) / c_den;
+    const float gn = g_flat ? 0.0f : (hop_decay(b.dist[i]) - gmin) / g_den;
+    b.keys[i] = make_key(alpha_graph * gn + alpha_dense * dn, b.cand[i]);
+  }
+}
+
+// winner j (one CTA): find its slot in the candidate array, emit the per-hit fields
+__global__ void __launch_bounds__(256) lookup_big_kernel(BigWs b, int window, int k, const long long* __restrict__ ids, float* out_scores,
+                                                          int* out_hops, float* out_gn, float* out_dn, float* out_cos) {
+  __shared__ int s_slot;
+  const int j = blockIdx.x, n = *b.ncand;
+  if (threadIdx.x == 0) s_slot = -1;
+  __syncthreads();
+  const long long id = ids[j];
+  if (id >= 0)
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      if ((long long)b.cand[i] == id) s_slot = i;          // rows are unique within a candidate list
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const int slot = s_slot;
+  if (slot < 0) { out_scores[j] = -CUDART_INF_F; out_hops[j] = -1; out_gn[j] = 0; out_dn[j] = 0; out_cos[j] = 0; return; }
+  int dmax = 0;
+  for (int d = 1; d <= window; ++d) if (b.level_end[d] > b.level_end[d - 1]) dmax = d;
+  const float gmax = hop_decay(0), gmin = hop_decay(dmax);
+  const bool g_flat = !(gmax > gmin);
+  const u32 lo = b.mm[0], hi = b.mm[1];
+  const float cmin = lo <= hi ? ordered_to_f32(lo) : CUDART_INF_F, cmax = lo <= hi ? ordered_to_f32(hi) : -CUDART_INF_F;
+  const bool c_flat = !(cmax > cmin);
+  const int hd = b.dist[slot];
+  const float cv = b.cos[slot];
+  out_hops[j] = hd; out_cos[j] = cv;
+  out_gn[j] = g_flat ? 0.0f : (hop_decay(hd) - gmin) / (gmax - gmin);
+  out_dn[j] = c_flat ? 0.0f : (cv - cmin) / (cmax - cmin);
+}
+
+int launch_select_flat_keys(const void* keys, const int* count_dev, long long cap, int k, float* out_scores, int64_t* out_ids, cudaStream_t st);
+
+template <typename T>
+static int launch_gather_big(const ExpandParams& p, cudaStream_t st) { return launch_gather<T>(p, st); }
+
+int launch_expand_rescore_big(const Index* ix, const Graph* g, const void* Q, const int64_t* seeds, int S, int window, float alpha_dense,
+                              float alpha_graph, int k, float* out_scores, int64_t* out_ids, int32_t* out_hops, float* out_gn, float* out_dn,
+                              float* out_cos, int32_t* out_ncand, void* ws, cudaStream_t st) {
+  ProfScope _ps(st, "graph_big_frontier");
+  BigWs b = carve_big(ws, g->V);
+  const long long V = g->V;
+  B200R_CUDA_CHECK(cudaMemsetAsync(b.visited, 0, ((size_t)V / 32 + 1) * 4, st));
+  B200R_CUDA_CHECK(cudaMemsetAsync(b.ncand, 0, 256 + align_up(257 * 4, 256), st));
+  bfs_big_seed_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const long long*>(seeds), S, V, b);
+  for (int d = 1; d <= window; ++d) {
+    bfs_big_level_kernel<<<2 * kNumSMs, 256, 0, st>>>(reinterpret_cast<const long long*>(g->row_ptr), g->col_idx, V, d, b);
+    bfs_big_close_level_kernel<<<1, 1, 0, st>>>(d, b);
+  }
+  bfs_big_finish_kernel<<<2 * kNumSMs, 256, 0, st>>>(reinterpret_cast<const long long*>(g->node_rows), b, out_ncand);
+  count_launch(3 + 2 * window);
+  int rc;
+  const int qdtype = ix->dtype == B200R_I8 ? B200R_F32 : ix->dtype;
+  if (ix->metric == B200R_COS) { if ((rc = launch_query_inv_norm(Q, 1, ix->D, qdtype, b.qinv, st))) return rc; }
+  else { const float one = 1.0f; B200R_CUDA_CHECK(cudaMemcpyAsync(b.qinv, &one, 4, cudaMemcpyHostToDevice, st)); }
+  // the re-score gather, unchanged: one reservation covering the whole list of the single query
+  ExpandParams p;
+  memset(&p, 0, sizeof(p));
+  p.X = ix->X; p.Q = Q; p.row_mult = ix->row_mult; p.N = ix->N; p.V = V; p.id_base = ix->id_base; p.D = ix->D; p.B = 1; p.metric = ix->metric;
+  p.own_lo = INT64_MIN; p.own_hi = INT64_MAX;
+  p.ws.cand = b.cand; p.ws.cos = b.cos; p.ws.dist = b.dist; p.ws.ncand = b.ncand; p.ws.nown = b.nown; p.ws.qinv = b.qinv; p.ws.mm = b.mm;
+  p.ws.seg_start = b.seg_start; p.ws.seg_q = b.seg_q; p.ws.counter = b.counter;
+  switch (ix->dtype) {
+    case B200R_BF16: rc = launch_gather_big<__nv_bfloat16>(p, st); break;
+    case B200R_F16: rc = launch_gather_big<__half>(p, st); break;
+    case B200R_F32: rc = launch_gather_big<float>(p, st); break;
+    default: rc = launch_gather_big<int8_t>(p, st); break;
+  }
+  if (rc) return rc;
+  fuse_big_kernel<<<2 * kNumSMs, 256, 0, st>>>(b, window, alpha_dense, alpha_graph);
+  count_launch();
+  if ((rc = launch_select_flat_keys(b.keys, b.ncand, V, k, out_scores, out_ids, st))) return rc;
+  lookup_big_kernel<<<k, 256, 0, st>>>(b, window, k, reinterpret_cast<const long long*>(out_ids), out_scores, out_hops, out_gn, out_dn, out_cos);
+  count_launch();
+  B200R_CUDA_CHECK(cudaGetLastError());
+  return B200R_OK;
+}
+
 int launch_expand_rescore(const Index* ix, const Graph* g, const void* Q, const int64_t* seeds, int B, int S, int window,
                           float alpha_dense, float alpha_graph, int k, float* out_scores, int64_t* out_ids, int32_t* out_hops,
                           float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand, int32_t* out_status, int mode,

@@ -178,6 +178,10 @@ int launch_expand_rescore(const Index* ix, const Graph* g, const void* Q, const 
                           float* out_gn, float* out_dn, float* out_cos, int32_t* out_ncand, int32_t* out_status, int mode,
                           int64_t own_lo, int64_t own_hi, void* ws, float* minmax, cudaStream_t st);
 size_t expand_workspace_bytes(int B);
+size_t expand_big_workspace_bytes(long long V);
+int launch_expand_rescore_big(const Index* ix, const Graph* g, const void* Q, const int64_t* seeds, int S, int window, float alpha_dense,
+                              float alpha_graph, int k, float* out_scores, int64_t* out_ids, int32_t* out_hops, float* out_gn, float* out_dn,
+                              float* out_cos, int32_t* out_ncand, void* ws, cudaStream_t st);
 // graph stage over the exchange (csr_expand.cu, mode 3): slot sizes of its three channels and the phased launcher
 size_t expand_xchg_req_bytes(int per);          // one home rank's request record for `per` queries
 size_t expand_xchg_cos_bytes(int per);          // a home rank's cosine slot

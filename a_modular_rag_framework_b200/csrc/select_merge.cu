@@ -597,6 +597,19 @@ int launch_range_unpack(const void*, int64_t total, const int64_t*, int, float, 
   return B200R_OK;
 }
 
+// exact top-k of ONE flat list of keys in global memory (the unbounded-frontier path of the graph stage): *count_dev keys
+int launch_select_flat_keys(const void* keys, const int* count_dev, long long cap, int k, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+  SelectParams p;
+  memset(&p, 0, sizeof(p));
+  p.min_score = -__builtin_huge_valf();
+  p.lists = reinterpret_cast<const u64*>(keys); p.counts = count_dev;
+  p.S = 1; p.Bpad = 1; p.cap = (int)(cap > 0x7fffffffll ? 0x7fffffffll : cap);
+  p.B = 1; p.k = k; p.kp2 = next_pow2(k);
+  p.out_scores = out_scores; p.out_ids = reinterpret_cast<long long*>(out_ids);
+  p.mode = kSelOutput;
+  return run_select(p, 1, st);
+}
+
 int select_group_size() { return SEL_GROUP; }
 int select_max_flat_segments() { return SEL_MAX_SEGS; }
 

@@ -274,9 +274,11 @@ class PassageGraph:
 
 
 def expand_rescore(index: DenseIndex, graph: PassageGraph, Q: torch.Tensor, seeds: torch.Tensor, window: int,
-                   alpha_dense: float, alpha_graph: float, k: int, check_status: bool = True) -> Dict[str, torch.Tensor]:
+                   alpha_dense: float, alpha_graph: float, k: int, check_status: bool = True, unbounded: bool = False) -> Dict[str, torch.Tensor]:
     """Graph second stage for B queries: BFS (<= window hops) from ``seeds`` [B, S] (i64, <0 = padding),
-    cosine re-score, min-max fusion, top-k.  Returns device tensors keyed like the reference's meta keys."""
+    cosine re-score, min-max fusion, top-k.  Returns device tensors keyed like the reference's meta keys.
+    unbounded=True: queries whose neighbourhood exceeds the on-chip capacity are redone in global memory
+    (b200r_expand_rescore_big) instead of being reported through out["status"]."""
     _require_cuda(Q, "Q")
     _require_cuda(seeds, "seeds")
     if Q.dtype != index.query_dtype or Q.dim() != 2 or Q.shape[1] != index.D:
@@ -305,10 +307,21 @@ def expand_rescore(index: DenseIndex, graph: PassageGraph, Q: torch.Tensor, seed
             out["score"].data_ptr(), out["id"].data_ptr(), out["hop"].data_ptr(), out["score_graph_norm"].data_ptr(),
             out["score_dense_norm"].data_ptr(), out["cos"].data_ptr(), out["ncand"].data_ptr(), out["status"].data_ptr(),
             _stream_ptr(dev)))
-    if check_status:
-        bad = int((out["status"] != 0).sum().item())
-        if bad:
-            raise N.B200RError(N.EOVERFLOW, f"{bad} queries reached more than {N.load().b200r_expand_max_candidates()} graph nodes")
+    if unbounded or check_status:
+        over = (out["status"] != 0).nonzero().flatten().tolist()        # synchronises; almost always empty
+        if over and unbounded:
+            # the reference's BFS is unbounded (graph_utils.py:109-127): redo the few oversized queries in global memory
+            big = torch.empty(int(lib.b200r_expand_big_workspace_bytes(graph.handle)), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                for q in over:
+                    N.check(lib.b200r_expand_rescore_big(
+                        index.handle, graph.handle, Q[q].data_ptr(), seeds[q].data_ptr(), S, int(window), float(alpha_dense),
+                        float(alpha_graph), int(k), big.data_ptr(), big.numel(),
+                        out["score"][q].data_ptr(), out["id"][q].data_ptr(), out["hop"][q].data_ptr(), out["score_graph_norm"][q].data_ptr(),
+                        out["score_dense_norm"][q].data_ptr(), out["cos"][q].data_ptr(), out["ncand"][q:q + 1].data_ptr(), _stream_ptr(dev)))
+                    out["status"][q] = 0
+        elif over and check_status:
+            raise N.B200RError(N.EOVERFLOW, f"{len(over)} queries reached more than {N.load().b200r_expand_max_candidates()} graph nodes")
     return out
 
 

@@ -237,6 +237,17 @@ int b200r_expand_rescore(uint64_t index, uint64_t graph, const void* Q, const in
                          float* out_dense_norm, float* out_cos, int32_t* out_ncand, int32_t* out_status,
                          void* stream);
 
+/* Unbounded frontier: ONE query whose expansion exceeds b200r_expand_max_candidates() (out_status == B200R_EOVERFLOW
+ * above) redone with everything in global memory -- a visited bitmap over the graph's nodes, one grid-wide kernel per
+ * BFS level, the same gather / fusion / top-k -- so that, like the reference's BFS (graph_utils.py:109-127), no
+ * neighbourhood is too large.  Q: that query's vector, seeds [S]; outputs [k] (+ out_ncand [1]), same meaning as above.
+ * workspace: b200r_expand_big_workspace_bytes(graph) bytes (about 21 bytes per graph node), 256-byte aligned. */
+size_t b200r_expand_big_workspace_bytes(uint64_t graph);
+int b200r_expand_rescore_big(uint64_t index, uint64_t graph, const void* Q, const int64_t* seeds, int32_t S, int32_t window,
+                             float alpha_dense, float alpha_graph, int32_t k, void* workspace, size_t workspace_bytes, float* out_scores,
+                             int64_t* out_ids, int32_t* out_hops, float* out_graph_norm, float* out_dense_norm, float* out_cos,
+                             int32_t* out_ncand, void* stream);
+
 /* Row-sharded corpora (one rank per GPU, CSR replicated, embeddings sharded by rows; SURVEY 8e "owner
  * computes").  pass 1: BFS + re-score of the candidates whose global id lies in [own_lo, own_hi), parked in
  * `workspace` (b200r_expand_workspace_bytes(B)), and minmax[B][2] = this rank's (min, max) cosine.  The caller

@@ -186,3 +186,42 @@ def test_single_query_and_many_queries_agree():
         assert torch.equal(one["score"][0], big["score"][b])
         assert torch.equal(one["cos"][0], big["cos"][b])
         assert int(one["ncand"][0]) == int(big["ncand"][b])
+
+
+def test_unbounded_frontier_like_the_reference():
+    """The reference's BFS has no candidate limit (graph_utils.py:109-127).  Queries beyond the 8192-candidate on-chip
+    capacity are redone in global memory (b200r_expand_rescore_big): a star (one hop reaches 20000 nodes), a power-law-tail
+    graph with hub seeds, next to ordinary queries of the same batch."""
+    from a_modular_rag_framework_b200 import DenseIndex, PassageGraph, expand_rescore
+    rng = np.random.default_rng(12)
+    V, D, k = 30000, 64, 15
+    # power-law tail: a few hubs with thousands of neighbours + a sparse random background
+    hubs = np.arange(5)
+    hub_src = np.repeat(hubs, [9000, 6000, 3000, 1500, 800])
+    hub_dst = rng.integers(5, V, size=len(hub_src))
+    bg_s, bg_d = rng.integers(0, V, 40000), rng.integers(0, V, 40000)
+    row_ptr, col_idx = O.csr_from_edges(V, np.concatenate([hub_src, bg_s]), np.concatenate([hub_dst, bg_d]))
+    Xn = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((V, D)).astype(np.float32)))
+    Qn = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((4, D)).astype(np.float32)))
+    seeds = np.array([[0, 1, -1], [100, 200, 300], [2, 7000, 3], [4, -1, -1]])
+    dev = _dev()
+    ix = DenseIndex(torch.from_numpy(Xn).to(dev).to(torch.bfloat16))
+    g = PassageGraph(torch.from_numpy(row_ptr).to(dev), torch.from_numpy(col_idx).to(dev))
+    Q = torch.from_numpy(Qn).to(dev).to(torch.bfloat16)
+    sd = torch.from_numpy(seeds).to(dev)
+    bounded = expand_rescore(ix, g, Q, sd, 2, 0.4, 0.2, k, check_status=False)
+    assert (bounded["status"] != 0).sum().item() >= 2                 # hub queries overflow the on-chip path ...
+    out = expand_rescore(ix, g, Q, sd, 2, 0.4, 0.2, k, unbounded=True)
+    assert (out["status"] == 0).all()                                  # ... and are completed by the global-memory path
+    for b in range(4):
+        check_graph_query(out, b, Qn[b], Xn, row_ptr, col_idx, seeds[b], 2, 0.4, 0.2, k)
+    assert int(out["ncand"][0]) > 8192
+    for key in ("id", "score", "hop", "cos"):                           # queries that fit are untouched
+        assert torch.equal(out[key][1], bounded[key][1])
+    # window 1 on a star: every node is a candidate
+    Vs = 20000
+    rp, ci = O.csr_from_edges(Vs, np.zeros(Vs - 1, dtype=np.int64), np.arange(1, Vs, dtype=np.int64))
+    gs = PassageGraph(torch.from_numpy(rp).to(dev), torch.from_numpy(ci).to(dev))
+    one = expand_rescore(ix, gs, Q[:1].contiguous(), torch.tensor([[0]], device=dev), 1, 0.4, 0.2, k, unbounded=True)
+    assert int(one["ncand"][0]) == Vs
+    check_graph_query(one, 0, Qn[0], Xn, rp, ci, [0], 1, 0.4, 0.2, k)
