@@ -83,32 +83,58 @@ class CudaEngine:
     def __init__(self, emb_path: str, graph_path: str, device: str = "cuda:0", metric: str = "cos",
                  devices: Optional[Sequence[int]] = None, max_batch: int = 4096, max_k: int = 256):
         import torch
-        from .index import DenseIndex, PassageGraph
         from .sharded import shard_rows
 
         if not torch.cuda.is_available():
             raise RuntimeError("B200RetrievalBackend needs a CUDA device: there is no CPU fallback")
-        self.torch = torch
-        self.devs = [torch.device("cuda", int(d)) for d in devices] if devices else [torch.device(device)]
-        if max((d.index or 0) for d in self.devs) >= torch.cuda.device_count():
+        devs = [torch.device("cuda", int(d)) for d in devices] if devices else [torch.device(device)]
+        if max((d.index or 0) for d in devs) >= torch.cuda.device_count():
             raise RuntimeError(f"devices={list(devices or [device])} but only {torch.cuda.device_count()} CUDA devices are visible")
-        self.device = self.devs[0]
         X, meta, scales = store.load_embeddings(emb_path)
-        self.tdtype = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32, "i8": torch.int8}[meta["dtype"]]
-        self.N, self.D = int(meta["N"]), int(meta["D"])
-        G = len(self.devs)
-        self.shards, self._keep = [], []
-        for g, dev in enumerate(self.devs):
-            lo, hi = shard_rows(self.N, G, g)
+        tdtype = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32, "i8": torch.int8}[meta["dtype"]]
+        N, D, G = int(meta["N"]), int(meta["D"]), len(devs)
+        shards, row_scales = [], []
+        for g, dev in enumerate(devs):
+            lo, hi = shard_rows(N, G, g)
             host = torch.from_numpy(np.array(X[lo:hi], copy=True))      # the store is a read-only memmap
             if meta["dtype"] == "bf16":
                 host = host.view(torch.bfloat16)
             if hi == lo:                                                    # an empty tail shard still needs a valid pointer
-                host = torch.zeros((1, self.D), dtype=self.tdtype)
-            Xd = host.to(dev)
-            sc = torch.from_numpy(np.array(scales[lo:hi], copy=True)).to(dev) if scales is not None else None
-            self._keep.append((Xd, sc))
-            self.shards.append(DenseIndex(Xd, metric=metric or meta.get("metric", "cos"), id_base=lo, row_scale=sc))
+                host = torch.zeros((1, D), dtype=tdtype)
+            shards.append(host.to(dev))
+            row_scales.append(torch.from_numpy(np.array(scales[lo:hi], copy=True)).to(dev) if scales is not None else None)
+        self._setup(shards, row_scales, N, metric or meta.get("metric", "cos"), max_batch, max_k)
+        if graph_path:
+            path = store.csr_path(graph_path)
+            if not os.path.exists(path):
+                raise FileNotFoundError(f"graph_path {graph_path!r} does not exist (store.save_csr writes '<name>.npz')")
+            row_ptr, col_idx = store.load_csr(path)
+            self.corpus_graphs = self._upload_graph(row_ptr, col_idx, None)
+
+    @classmethod
+    def from_shards(cls, shards: Sequence[Any], n_total: int, metric: str = "cos", max_batch: int = 4096, max_k: int = 256,
+                    row_scales: Optional[Sequence[Any]] = None) -> "CudaEngine":
+        """Engine over row shards that already live in HBM: shards[g] (a CUDA tensor on its device) holds rows
+        shard_rows(n_total, G, g) of the corpus."""
+        self = cls.__new__(cls)
+        self._setup(list(shards), list(row_scales) if row_scales is not None else [None] * len(shards), int(n_total), metric, max_batch, max_k)
+        return self
+
+    def _setup(self, shards, row_scales, n_total: int, metric: str, max_batch: int, max_k: int) -> None:
+        import torch
+        from .index import DenseIndex, PassageGraph
+        from .sharded import shard_rows
+        self.torch = torch
+        self.devs = [x.device for x in shards]
+        self.device = self.devs[0]
+        self.N, self.D = int(n_total), int(shards[0].shape[1])
+        self.tdtype = shards[0].dtype
+        G = len(shards)
+        self._keep = list(zip(shards, row_scales))
+        self.shards = []
+        for g, (Xd, sc) in enumerate(self._keep):
+            lo, _ = shard_rows(self.N, G, g)
+            self.shards.append(DenseIndex(Xd, metric=metric, id_base=lo, row_scale=sc))
         self.query_dtype = self.shards[0].query_dtype
         self.max_batch, self.max_k = int(max_batch), int(max_k)
         self.comms = None
@@ -117,12 +143,7 @@ class CudaEngine:
             self.comms = ShardComm.init_all([d.index for d in self.devs], self.max_batch, self.max_k, self.max_k)
         self._graph_cls = PassageGraph
         self.corpus_graphs = None       # one replica per device of the corpus-level CSR (graph_path)
-        if graph_path:
-            path = store.csr_path(graph_path)
-            if not os.path.exists(path):
-                raise FileNotFoundError(f"graph_path {graph_path!r} does not exist (store.save_csr writes '<name>.npz')")
-            row_ptr, col_idx = store.load_csr(path)
-            self.corpus_graphs = self._upload_graph(row_ptr, col_idx, None)
+        self._qpin = None               # pinned staging of the converted queries
 
     # -- helpers ------------------------------------------------------------------------------------------
     def _upload_graph(self, row_ptr, col_idx, node_rows):
@@ -135,8 +156,14 @@ class CudaEngine:
         return out
 
     def _q_host(self, Q: np.ndarray):
+        """f32 host queries -> the index's query dtype in PINNED memory (the H2D copies to the devices run asynchronously)."""
         q = self.torch.from_numpy(np.ascontiguousarray(Q, dtype=np.float32))
-        return q.to(self.query_dtype).contiguous()
+        n = q.numel()
+        if self._qpin is None or self._qpin.numel() < n or self._qpin.dtype != self.query_dtype:
+            self._qpin = self.torch.empty(max(n, 1), dtype=self.query_dtype).pin_memory()
+        out = self._qpin[:n].view(q.shape)
+        out.copy_(q)
+        return out
 
     def has_graph(self) -> bool:
         return self.corpus_graphs is not None

@@ -127,7 +127,7 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   const bool i8_ok = i8_nq > 0;
   if (path == B200R_PATH_AUTO) path = (gemm_ok || i8_ok) ? B200R_PATH_GEMM : B200R_PATH_SCAN;
   if (path == B200R_PATH_GEMM && !gemm_ok && !i8_ok) {
-    set_error("tensor path needs a bf16/f16 corpus with D %% 8 == 0, an int8 corpus or an fp32 corpus with D <= ~1400 (dtype=%d D=%d)", ix->dtype, ix->D);
+    set_error("tensor path needs a bf16/f16 corpus with D %% 8 == 0, an int8 corpus or an fp32 corpus (dtype=%d D=%d)", ix->dtype, ix->D);
     return B200R_EINVAL;
   }
   if (path != B200R_PATH_GEMM && path != B200R_PATH_SCAN) { set_error("bad path %d", path); return B200R_EINVAL; }

@@ -6,13 +6,15 @@
 //   * every fp32 value v is split EXACTLY into hi = v with the low 13 mantissa bits cleared and mid = (v - hi) with ITS
 //     low 13 bits cleared; both are exactly representable in tf32 (so the result does not depend on how the MMA rounds its
 //     inputs) and v - hi - mid is below 2^-22 |v|;
-//   * q . x = q_hi.x_hi + q_mid.x_hi + q_hi.x_mid  (+ terms below 2^-22 |q||x|): three kind::tf32 MMAs per K step into ONE
-//     fp32 accumulator; every product of two 11-bit significands is exact, the sums are fp32;
+//   * q . x = q_hi.x_hi + q_mid.x_hi + q_hi.x_mid  (+ terms below 2^-22 |q||x|): three kind::tf32 MMAs per K step; every
+//     product of two 11-bit significands is exact; the fp32 accumulation is spread over 8 partial accumulators per tile
+//     (see RF_PARTS) that the epilogue adds with round-to-nearest;
 //   * operand layout is the streaming one of rows_i8.cu: the 128 corpus rows of a tile are the MMA's M (TMEM lanes), tiles of
 //     [128 rows x 128 bytes = 32 floats] arrive by TMA (SWIZZLE_128B) straight from the fp32 corpus into a ring that carries
 //     corpus data only; four CONVERTER warps split each arrived slice in shared memory (hi in place, mid into a
 //     double-buffered side tile; 15 instructions per 4 elements, a sixth of the SM's issue slots at HBM speed) and hand it to
-//     the MMA warp; the 16 queries of the pass (hi and mid planes, split once per search) stay RESIDENT in shared memory;
+//     the MMA warp; the hi and mid planes of the pass's 16 queries (split once per search, 96 KB at D = 768, L2-resident) are
+//     streamed slice by slice with the corpus, which leaves shared memory for an 8-deep ring at any D;
 //   * epilogue thread = TMEM lane = one corpus row: 16 fp32 scores, row multiplier, per-query thresholds, ballot appends;
 //     lists, thresholds, phases and pruning exactly as in K1.
 // Roofline: HBM, N*D*4 bytes per group of 16 queries.
@@ -30,13 +32,20 @@ constexpr int RF_BK = 32;                           // fp32 elements per K slice
 constexpr int RF_STAGE_BYTES = RF_ROWS * RF_BK * 4; // 16 KB
 constexpr int RF_NQ = 16;                           // queries per corpus pass (MMA N)
 constexpr int RF_Q_KB_BYTES = 2 * RF_NQ * RF_BK * 4;   // hi rows then mid rows of one K slice: 4 KB
+constexpr int RF_RING_BYTES = RF_STAGE_BYTES + RF_Q_KB_BYTES;   // a ring stage: the corpus slice and the matching query slice
 constexpr int RF_THREADS = 320;                     // TMA, MMA, 4 epilogue warps, 4 converter warps
-constexpr int RF_ACC = 4, RF_ACC_STRIDE = 32;       // accumulators in TMEM
+// The tensor core adds each instruction's partial sum into the fp32 accumulator with truncation, a bias that grows with the
+// length of the accumulation chain (measured 1.5e-5 relative on 768 same-sign terms, above the fp32 bar).  The K slices of a
+// tile are therefore dealt round-robin onto RF_PARTS accumulators (chains 8x shorter) that the epilogue adds in fp32 RN.
+constexpr int RF_PARTS = 8;
+constexpr int RF_PART_COLS = 2 * 16;                // a partial accumulator: columns 0..15 = x.q_hi terms, 16..31 = x_hi.q_mid
+constexpr int RF_ACC = 2, RF_ACC_STRIDE = RF_PARTS * RF_PART_COLS;   // tiles in flight in TMEM x 256 columns each
 constexpr int RF_MAX_STAGES = 8;
 constexpr u32 RF_TF32_MASK = 0xffffe000u;
 
 struct RowsF32Params {
-  int B, k, D, num_kb, stages;
+  int B, k, D, num_kb, stages, mids;          // raw ring stages, mid side buffers
+  int store_hi;            // 1: the converters also write the truncated hi piece back in place (see rows_f32_store_hi)
   int q0;                  // this launch serves queries [q0, min(B, q0 + 16))
   long long N;
   int tile_begin, tile_end, tiles_per_chunk, num_units;
@@ -45,7 +54,7 @@ struct RowsF32Params {
   u64* lists;
   int* counts;
   u32* gthr;
-  u32 idesc;
+  u32 idesc, idesc32;      // N = 16 / N = 32 instruction descriptors
 };
 
 // ---- query split: f32 [B, D] -> per group of 16 queries: planes f32 [2][16][D] (hi, mid) -------------------------------
@@ -78,10 +87,12 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const u32 raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  uint8_t* smem_q = smem;                                       // [num_kb][32 rows x 128 B]: hi rows 0..15, mid rows 16..31
-  uint8_t* smem_x = smem + (size_t)p.num_kb * RF_Q_KB_BYTES;    // [stages][128 x 128 B] raw -> hi (in place)
-  uint8_t* smem_m = smem_x + (size_t)p.stages * RF_STAGE_BYTES; // [2][128 x 128 B] mid
-  uint8_t* tail = smem_m + 2 * RF_STAGE_BYTES;
+  // ring stage = [128 x 128 B corpus slice, raw -> hi in place | 32 x 128 B query slice: hi rows 0..15, mid rows 16..31].
+  // The query planes (2 x 16 x D floats, L2-resident) are streamed with the corpus instead of being kept in shared memory:
+  // that leaves room for an 8-deep ring (128 KB of corpus reads in flight per SM) at any D.
+  uint8_t* smem_x = smem;                                         // [stages][20 KB]
+  uint8_t* smem_m = smem_x + (size_t)p.stages * RF_RING_BYTES;    // [mids][128 x 128 B] mid
+  uint8_t* tail = smem_m + (size_t)p.mids * RF_STAGE_BYTES;
   u32* smem_hist = reinterpret_cast<u32*>(tail);                // [4][256]
   float* thr_s = reinterpret_cast<float*>(smem_hist + 4 * 256); // [4][16]
   u64* kth_s = reinterpret_cast<u64*>(thr_s + 4 * RF_NQ);       // [4][16]
@@ -90,24 +101,22 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   u64* full_bar = bars;                               // [stages]  TMA landed
   u64* conv_bar = bars + RF_MAX_STAGES;               // [stages]  split done (4 converter warps)
   u64* empty_bar = bars + 2 * RF_MAX_STAGES;          // [stages]  MMAs retired
-  u64* mid_empty_bar = bars + 3 * RF_MAX_STAGES;      // [2]
-  u64* tmem_full_bar = mid_empty_bar + 2;             // [RF_ACC]
+  u64* mid_empty_bar = bars + 3 * RF_MAX_STAGES;      // [mids] (<= 4)
+  u64* tmem_full_bar = mid_empty_bar + 4;             // [RF_ACC]
   u64* tmem_empty_bar = tmem_full_bar + RF_ACC;       // [RF_ACC]
-  u64* q_bar = tmem_empty_bar + RF_ACC;
-  u32* tmem_ptr_smem = reinterpret_cast<u32*>(q_bar + 1);
+  u32* tmem_ptr_smem = reinterpret_cast<u32*>(tmem_empty_bar + RF_ACC);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
-  constexpr u32 TMEM_COLS = RF_ACC * RF_ACC_STRIDE;   // 128
+  constexpr u32 TMEM_COLS = RF_ACC * RF_ACC_STRIDE;   // 512
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_q);
     prefetch_tmap(&tmap_x);
     for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&conv_bar[i], 4); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) mbar_init(&mid_empty_bar[i], 1);
+    for (int i = 0; i < p.mids; ++i) mbar_init(&mid_empty_bar[i], 1);
     for (int i = 0; i < RF_ACC; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
-    mbar_init(q_bar, 1);
     fence_barrier_init();
   }
   if (warp_idx == 1) {
@@ -122,8 +131,6 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp_idx == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      mbar_expect_tx(q_bar, (u32)(p.num_kb * RF_Q_KB_BYTES));
-      for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(smem_q + (size_t)kb * RF_Q_KB_BYTES, &tmap_q, q_bar, kb * RF_BK, 0, kEvictLast);
       int stage = 0; u32 phase = 0;
       for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
         const int t0 = p.tile_begin + u * p.tiles_per_chunk;
@@ -131,8 +138,9 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], RF_STAGE_BYTES);
-            tma_load_2d(smem_x + (size_t)stage * RF_STAGE_BYTES, &tmap_x, &full_bar[stage], kb * RF_BK, t * RF_ROWS, kEvictFirst);
+            mbar_expect_tx(&full_bar[stage], RF_RING_BYTES);
+            tma_load_2d(smem_x + (size_t)stage * RF_RING_BYTES, &tmap_x, &full_bar[stage], kb * RF_BK, t * RF_ROWS, kEvictFirst);
+            tma_load_2d(smem_x + (size_t)stage * RF_RING_BYTES + RF_STAGE_BYTES, &tmap_q, &full_bar[stage], kb * RF_BK, 0, kEvictLast);
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -141,9 +149,9 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   } else if (warp_idx == 1) {
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
-      mbar_wait(q_bar, 0);
       int stage = 0; u32 phase = 0;
-      u32 tile_iter = 0, it = 0;
+      u32 tile_iter = 0;
+      int m = 0;
       for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
         const int t0 = p.tile_begin + u * p.tiles_per_chunk;
         const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
@@ -151,24 +159,23 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const u32 acc = tile_iter % RF_ACC;
           mbar_wait(&tmem_empty_bar[acc], ((tile_iter / RF_ACC) & 1) ^ 1);
           tc_fence_after();
-          const u32 tmem_d = tmem_base + acc * RF_ACC_STRIDE;
-          for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            const u32 tmem_d = tmem_base + acc * RF_ACC_STRIDE + (u32)(kb % RF_PARTS) * RF_PART_COLS;    // this slice's partial accumulator
             mbar_wait(&conv_bar[stage], phase);          // the converters have split this slice (and fenced the async proxy)
             tc_fence_after();
-            const u32 m = it & 1u;
-            const u64 x_hi = make_smem_desc(smem_u32(smem_x + (size_t)stage * RF_STAGE_BYTES));
+            const u64 x_hi = make_smem_desc(smem_u32(smem_x + (size_t)stage * RF_RING_BYTES));
             const u64 x_mid = make_smem_desc(smem_u32(smem_m + (size_t)m * RF_STAGE_BYTES));
-            const u64 q_hi = make_smem_desc(smem_u32(smem_q + (size_t)kb * RF_Q_KB_BYTES));
-            const u64 q_mid = make_smem_desc(smem_u32(smem_q + (size_t)kb * RF_Q_KB_BYTES + RF_NQ * RF_BK * 4));
+            const u64 q_all = make_smem_desc(smem_u32(smem_x + (size_t)stage * RF_RING_BYTES + RF_STAGE_BYTES));   // 32 rows: q_hi then q_mid
 #pragma unroll
             for (int kk = 0; kk < RF_BK / 8; ++kk) {      // K = 8 tf32 = 32 bytes per instruction
-              umma_tf32(tmem_d, x_hi + (u64)(kk * 2), q_hi + (u64)(kk * 2), p.idesc, (kb | kk) != 0 ? 1u : 0u);
-              umma_tf32(tmem_d, x_hi + (u64)(kk * 2), q_mid + (u64)(kk * 2), p.idesc, 1u);
-              umma_tf32(tmem_d, x_mid + (u64)(kk * 2), q_hi + (u64)(kk * 2), p.idesc, 1u);
+              // x_hi . [q_hi ; q_mid] -> 32 columns, then x_mid . q_hi onto the first 16
+              umma_tf32(tmem_d, x_hi + (u64)(kk * 2), q_all + (u64)(kk * 2), p.idesc32, (kb >= RF_PARTS || kk != 0) ? 1u : 0u);
+              umma_tf32(tmem_d, x_mid + (u64)(kk * 2), q_all + (u64)(kk * 2), p.idesc, 1u);
             }
             umma_commit(&empty_bar[stage]);
             umma_commit(&mid_empty_bar[m]);
             if (kb == p.num_kb - 1) umma_commit(&tmem_full_bar[acc]);
+            if (++m == p.mids) m = 0;
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -180,16 +187,15 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // the split is elementwise, so the mid tile keeps the raw tile's swizzled layout)
     const int ct = threadIdx.x - 6 * 32;
     int stage = 0; u32 phase = 0;
-    u32 it = 0;
+    int m = 0; u32 mphase = 0;
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
       const int t0 = p.tile_begin + u * p.tiles_per_chunk;
       const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
       for (int t = t0; t < t1; ++t) {
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const u32 m = it & 1u;
-          mbar_wait(&mid_empty_bar[m], ((it >> 1) & 1u) ^ 1u);      // the MMAs that read this mid buffer two slices ago retired
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&mid_empty_bar[m], mphase ^ 1u);                 // the MMAs that read this mid buffer `mids` slices ago retired
           mbar_wait(&full_bar[stage], phase);
-          uint4* raw = reinterpret_cast<uint4*>(smem_x + (size_t)stage * RF_STAGE_BYTES);
+          uint4* raw = reinterpret_cast<uint4*>(smem_x + (size_t)stage * RF_RING_BYTES);
           uint4* mid = reinterpret_cast<uint4*>(smem_m + (size_t)m * RF_STAGE_BYTES);
 #pragma unroll
           for (int c = 0; c < RF_STAGE_BYTES / 16 / 128; ++c) {
@@ -200,12 +206,13 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             r.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & RF_TF32_MASK;
             r.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & RF_TF32_MASK;
             r.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & RF_TF32_MASK;
-            raw[c * 128 + ct] = h;
+            if (p.store_hi) raw[c * 128 + ct] = h;
             mid[c * 128 + ct] = r;
           }
           fence_proxy_async_smem();            // generic-proxy stores -> visible to the tensor core's (async proxy) reads
           __syncwarp();
           if (lane == 0) mbar_arrive(&conv_bar[stage]);
+          if (++m == p.mids) { m = 0; mphase ^= 1u; }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -238,16 +245,23 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_wait(&tmem_full_bar[acc], (tile_iter / RF_ACC) & 1);
         tc_fence_after();
         const u32 taddr = tmem_base + ((u32)(quarter * 32) << 16) + acc * RF_ACC_STRIDE;
-        u32 a[16];
-        tmem_ld16(taddr, a);
-        tmem_ld_wait();
+        const int nparts = p.num_kb < RF_PARTS ? p.num_kb : RF_PARTS;      // partial accumulators this tile wrote
+        float s[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s[j] = 0.0f;
+        for (int part = 0; part < nparts; ++part) {
+          u32 a[32];
+          tmem_ld32(taddr + part * RF_PART_COLS, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s[j] += __uint_as_float(a[j]) + __uint_as_float(a[16 + j]);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-        float s[16];
         bool any = false;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { s[j] = __uint_as_float(a[j]) * m; any |= (s[j] >= thr[j]); }   // NaN m (rows beyond N) never passes
+        for (int j = 0; j < 16; ++j) { s[j] *= m; any |= (s[j] >= thr[j]); }   // NaN m (rows beyond N) never passes
         if (__any_sync(kFullMask, any)) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -295,20 +309,30 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
-static size_t rows_f32_smem_bytes(int num_kb, int stages) {
-  return 1024 + (size_t)num_kb * RF_Q_KB_BYTES + (size_t)(stages + 2) * RF_STAGE_BYTES + 4 * 256 * 4 + (size_t)4 * RF_NQ * (4 + 8 + 4) +
-         (3 * RF_MAX_STAGES + 2 + 2 * RF_ACC + 2) * 8 + 16;
+// kind::tf32 reads the top 19 bits of each fp32 operand and IGNORES the low 13 mantissa bits (truncation), so the raw corpus
+// slice already is the hi piece and the in-place store (a sixth of the kernel's shared-memory traffic, which is what bounds
+// it) can be skipped; tests/test_gpu_search.py::test_fp32_split_is_tight_on_nearly_parallel_vectors would fail by three
+// orders of magnitude if the hardware rounded instead.  B200R_F32_STORE_HI=1 restores the store.
+static int rows_f32_store_hi() {
+  static const int v = [] { const char* e = getenv("B200R_F32_STORE_HI"); return (e && e[0] == '1') ? 1 : 0; }();
+  return v;
 }
-static int rows_f32_stages_for(int D) {
-  const int num_kb = (D + RF_BK - 1) / RF_BK;
+static int rows_f32_mids() {
+  static const int m = [] { const char* e = getenv("B200R_F32_MIDS"); const int v = e ? atoi(e) : 3; return (v >= 2 && v <= 4) ? v : 3; }();
+  return m;
+}
+static size_t rows_f32_smem_bytes(int stages) {
+  return 1024 + (size_t)stages * RF_RING_BYTES + (size_t)rows_f32_mids() * RF_STAGE_BYTES + 4 * 256 * 4 + (size_t)4 * RF_NQ * (4 + 8 + 4) +
+         (3 * RF_MAX_STAGES + 4 + 2 * RF_ACC + 2) * 8 + 16;
+}
+static int rows_f32_stages_for(int) {
   int stages = RF_MAX_STAGES;
-  while (stages >= 3 && rows_f32_smem_bytes(num_kb, stages) > 227 * 1024) --stages;
+  while (stages >= 3 && rows_f32_smem_bytes(stages) > 227 * 1024) --stages;
   return stages >= 3 ? stages : 0;
 }
 
 int rows_f32_tile_rows() { return RF_ROWS; }
-// queries per corpus pass (16), 0 = the kernel does not apply: the resident query planes leave no room for a ring
-// (D > ~1400) or B200R_ROWS_F32=0
+// queries per corpus pass (16); 0 = switched off (B200R_ROWS_F32=0)
 int rows_f32_nq(int D) {
   static const bool off = [] { const char* e = getenv("B200R_ROWS_F32"); return e && e[0] == '0'; }();
   return (!off && rows_f32_stages_for(D)) ? RF_NQ : 0;
@@ -341,6 +365,8 @@ int launch_rows_f32(const Index* ix, const CUtensorMap* tmap_q, int group, const
   p.q0 = group * RF_NQ;
   p.num_kb = (ix->D + RF_BK - 1) / RF_BK;
   p.stages = rows_f32_stages_for(ix->D);
+  p.mids = rows_f32_mids();
+  p.store_hi = rows_f32_store_hi();
   if (!p.stages) { set_error("fp32 tensor path: D=%d does not fit", ix->D); return B200R_EINVAL; }
   p.tile_begin = ph.tile_begin; p.tile_end = ph.tile_end; p.tiles_per_chunk = ph.tiles_per_chunk;
   p.num_units = ph.num_chunks;
@@ -351,7 +377,8 @@ int launch_rows_f32(const Index* ix, const CUtensorMap* tmap_q, int group, const
   p.gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
   // instruction descriptor: D = f32 (1 << 4), A = B = tf32 (2 << 7, 2 << 10), K-major both, N >> 3, M >> 4
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((u32)(RF_NQ >> 3) << 17) | ((u32)(RF_ROWS >> 4) << 24);
-  const size_t smem = rows_f32_smem_bytes(p.num_kb, p.stages);
+  p.idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((u32)((2 * RF_NQ) >> 3) << 17) | ((u32)(RF_ROWS >> 4) << 24);
+  const size_t smem = rows_f32_smem_bytes(p.stages);
   B200R_CUDA_CHECK(cudaFuncSetAttribute(rows_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = p.num_units < kNumSMs ? p.num_units : kNumSMs;
   rows_f32_kernel<<<grid, RF_THREADS, smem, st>>>(*tmap_q, ix->tmap_x_f32, p);

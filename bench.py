@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-plugin-leg", action="store_true", help="N>1: skip the leg where ONE process drives all N GPUs through the plug-in engine")
     ap.add_argument("--no-legs", action="store_true", help="skip the secondary legs (batch 1 / batch 16 latency, graph stage)")
     ap.add_argument("--graph-nodes", type=int, default=5_000_000, help="graph leg: nodes (= rows of its corpus, taken from the shards)")
     ap.add_argument("--graph-edges", type=int, default=25_000_000, help="graph leg: directed edges before symmetrisation")
@@ -66,6 +67,12 @@ def parse_args():
 
 def workload_name(a):
     return f"synthetic unit-norm {a.rows}x{a.dim} {a.dtype} corpus, batch {a.batch}, exact cosine top-{a.k}"
+
+
+def shared_config(a):
+    """The `config` of BOTH arms (the driver compares them): the workload only; how each arm runs it is in `detail`."""
+    return {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "batch": a.batch, "k": a.k,
+            "l2": "inputs (corpus >= 1.9 GB per GPU) are far larger than the 126 MB L2; no flush between steps"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -156,7 +163,10 @@ def run_reference_arm(a):
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "batch": a.batch, "k": a.k},
+        "config": shared_config(a),
+        "detail": {"extrapolated": True,
+                   "how": "the CPU arm times a bounded sample (<= 256 queries x a row subset) and scales queries/s linearly in rows to the "
+                          "full corpus; see cpu_baseline.sample"},
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -243,6 +253,51 @@ def leg_small_batch(torch, index, world, Q, k, steps, n_local, dim, peaks, _nati
             "cuda_graph_error": graph_err,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                          "algorithmic": "N_local*D*2 bytes per batch per GPU (corpus shard streamed once), tile kernel time only"}}
+
+
+def gen_shard(torch, lo, hi, dim, tdt, dev, blk=1 << 20):
+    """Rows [lo, hi) of the synthetic unit-norm corpus on `dev`: Gaussian rows seeded per GLOBAL 2^20-row-aligned piece of
+    the range, so any process that generates rows [lo, hi) with the same (lo, blk) gets the same bits."""
+    n_local = hi - lo
+    X = torch.empty((max(n_local, 1), dim), dtype=tdt, device=dev)
+    for r0 in range(lo, hi, blk):
+        r1 = min(hi, r0 + blk)
+        g = torch.Generator(device=dev).manual_seed(1_000_003 + r0)
+        t = torch.randn((r1 - r0, dim), generator=g, device=dev, dtype=torch.float32)
+        t /= t.norm(dim=1, keepdim=True)
+        X[r0 - lo: r1 - lo] = t.to(tdt)
+        del t
+    if n_local == 0:
+        X.zero_()
+    return X
+
+
+def leg_plugin_single_process(torch, a, world, tdt, Qh, ref_ids, steps, warmup):
+    """N > 1, rank 0 only, while the other ranks wait: ONE process drives all N GPUs through the plug-in's engine
+    (backend.CudaEngine, what B200RetrievalBackend(devices=[0..N-1]) builds): float32 host queries in, host results out, the
+    corpus row-sharded over the devices, exchange + merge inside libb200r (b200r_search_sharded_host_all)."""
+    from a_modular_rag_framework_b200.backend import CudaEngine
+    from a_modular_rag_framework_b200.sharded import shard_rows
+    shards = []
+    for g in range(world):
+        lo, hi = shard_rows(a.rows, world, g)
+        shards.append(gen_shard(torch, lo, hi, a.dim, tdt, torch.device("cuda", g)))
+    eng = CudaEngine.from_shards(shards, a.rows, "cos", max_batch=a.batch, max_k=a.k)
+    Qf = [Qh[i].float().numpy() for i in range(Qh.shape[0])]
+    for i in range(min(warmup, 2)):
+        eng.dense_search(Qf[i], a.k)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        s, ids = eng.dense_search(Qf[warmup + i], a.k)
+    dt = time.perf_counter() - t0
+    same = bool((torch.from_numpy(ids) == ref_ids.cpu()).all().item())
+    del eng, shards
+    torch.cuda.empty_cache()
+    return {"value": steps * a.batch / dt, "unit": UNIT, "ms_per_step": dt / steps * 1e3, "devices": world,
+            "h2d_bytes_per_step": a.batch * a.dim * 2 * world, "d2h_bytes_per_step": a.batch * a.k * 12,
+            "identical_to_the_torchrun_result": same,
+            "note": "one host thread, N GPUs: f32 -> corpus dtype on the host, async H2D to every device, sharded search + exchange + "
+                    "merge (libb200r), D2H from device 0; not pipelined across batches"}
 
 
 def build_graph(torch, V, E, dev, seed=5):
@@ -467,17 +522,7 @@ def main():
     lo, hi = shard_rows(a.rows, world, rank)
     n_local = hi - lo
     tdt = torch.bfloat16 if a.dtype == "bf16" else torch.float16
-    X = torch.empty((max(n_local, 1), a.dim), dtype=tdt, device=dev)
-    blk = 1 << 20
-    for r0 in range(lo, hi, blk):
-        r1 = min(hi, r0 + blk)
-        g = torch.Generator(device=dev).manual_seed(1_000_003 + r0)
-        t = torch.randn((r1 - r0, a.dim), generator=g, device=dev, dtype=torch.float32)
-        t /= t.norm(dim=1, keepdim=True)
-        X[r0 - lo: r1 - lo] = t.to(tdt)
-        del t
-    if n_local == 0:
-        X.zero_()
+    X = gen_shard(torch, lo, hi, a.dim, tdt, dev)
     n_batches = a.warmup + a.steps
     gq = torch.Generator(device="cpu").manual_seed(4242)
     Qh = torch.randn((n_batches, a.batch, a.dim), generator=gq, dtype=torch.float32)
@@ -704,7 +749,18 @@ def main():
         except Exception as e:  # noqa: BLE001
             legs["graph"] = {"error": repr(e)}
         if world > 1:
-            dist.barrier()
+            # the other ranks wait on the HOST (gloo): an NCCL barrier would park a spinning kernel on their GPUs, which rank 0's
+            # kernels would have to time-slice with
+            torch.cuda.synchronize()
+            cpu_group = dist.new_group(backend="gloo")
+            dist.barrier(group=cpu_group)
+            if rank == 0 and not a.no_plugin_leg:
+                try:
+                    legs["plugin_single_process"] = leg_plugin_single_process(torch, a, world, tdt, Qh, out[1], a.steps, a.warmup)
+                except Exception as e:  # noqa: BLE001
+                    legs["plugin_single_process"] = {"error": repr(e)}
+                torch.cuda.set_device(local_rank)
+            dist.barrier(group=cpu_group)
 
     # ---- CPU baseline on rank 0, N=1 only ---------------------------------------------------------------
     cpu_baseline = None
@@ -720,13 +776,12 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": a.dtype, "data": "synthetic",
-            "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "batch": a.batch, "k": a.k,
-                       "path": used_path, "sharding": f"rows/{world}",
+            "config": shared_config(a),
+            "detail": {"path": used_path, "sharding": f"rows/{world}",
                        "exchange": "none" if world == 1 else (
                            "libb200r exchange (b200r_comm_*): the final select kernel stores each rank's packed top-k into every rank's window over NVLink (CUDA IPC mapped), device-side epoch flags, one merge kernel queued behind the next batch's search; no NCCL in the data path"
                            if a.exchange == "abi" else
-                           "packed NCCL all-gather + device merge on a side stream, overlapped with the next batch's search"),
-                       "l2": "corpus shard (>= 1.9 GB) is far larger than the 126 MB L2; no flush needed"},
+                           "packed NCCL all-gather + device merge on a side stream, overlapped with the next batch's search")},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "per_rank": per_rank, "legs": legs, "timeline": timeline,
         }

@@ -57,6 +57,8 @@ def run_search(name, N, D, B, k, dtype, path, steps=10, warmup=3, check=True):
     # (scan_bulk.cu), the register-fed scan 4 (scan_topk.cu)
     per_pass = 8 if dtype == torch.float32 else 4
     passes = 1 if used == "gemm" else (B + per_pass - 1) // per_pass
+    if used == "gemm" and dtype == torch.float32:
+        passes = (B + 15) // 16          # rows_f32.cu: 16 queries per corpus pass
     gbs = N * D * esz * passes / (kms * 1e-3) / 1e9
     tfs = 2.0 * B * N * D / (kms * 1e-3) / 1e12
     line["hbm_GBps"] = gbs
@@ -170,6 +172,9 @@ CONFIGS = {
     "cfg2_10Mx768_B16_scan": lambda: run_search("cfg2_10Mx768_B16_scan", 10_000_000, 768, 16, 100, torch.bfloat16, "scan", steps=5),
     "cfg2_10Mx768_B2_scan": lambda: run_search("cfg2_10Mx768_B2_scan", 10_000_000, 768, 2, 100, torch.bfloat16, "scan", steps=20, check=False),
     "cfg2_10Mx768_B2_gemm": lambda: run_search("cfg2_10Mx768_B2_gemm", 10_000_000, 768, 2, 100, torch.bfloat16, "gemm", steps=20, check=False),
+    "f32_5Mx768_B1_tensor": lambda: run_search("f32_5Mx768_B1_tensor", 5_000_000, 768, 1, 100, torch.float32, "gemm", steps=20),
+    "f32_5Mx768_B8_tensor": lambda: run_search("f32_5Mx768_B8_tensor", 5_000_000, 768, 8, 100, torch.float32, "gemm", steps=20),
+    "f32_5Mx768_B16_tensor": lambda: run_search("f32_5Mx768_B16_tensor", 5_000_000, 768, 16, 100, torch.float32, "gemm", steps=20),
     "f32_5Mx768_B1_scan": lambda: run_search("f32_5Mx768_B1_scan", 5_000_000, 768, 1, 100, torch.float32, "scan", steps=20),
     "f32_5Mx768_B4_scan": lambda: run_search("f32_5Mx768_B4_scan", 5_000_000, 768, 4, 100, torch.float32, "scan", steps=20),
     "f32_5Mx768_B8_scan": lambda: run_search("f32_5Mx768_B8_scan", 5_000_000, 768, 8, 100, torch.float32, "scan", steps=20),

@@ -480,7 +480,9 @@ def test_fp32_split_is_tight_on_nearly_parallel_vectors():
     scores, ids = ix.search(torch.from_numpy(Qn).to(_dev()), k, path="gemm")
     S = O.score_matrix(Qn, Xn)
     got = scores.cpu().numpy()[0].astype(np.float64)
-    assert np.max(np.abs(got - S[0, ids.cpu().numpy()[0]])) < 3e-7        # far inside 1e-5: the split loses < 2^-22 per operand
+    # far inside 1e-5: the split loses < 2^-22 per operand and the accumulation runs in 8 short chains (a single chain of
+    # truncating tensor-core adds measured 1.5e-5 here)
+    assert np.max(np.abs(got - S[0, ids.cpu().numpy()[0]])) < 4e-6
     _check_against_scores(scores, ids, S, k, 1e-5)
 
 
