@@ -37,14 +37,22 @@ constexpr int RF_THREADS = 320;                     // TMA, MMA, 4 epilogue warp
 // The tensor core adds each instruction's partial sum into the fp32 accumulator with truncation, a bias that grows with the
 // length of the accumulation chain (measured 1.5e-5 relative on 768 same-sign terms, above the fp32 bar).  The K slices of a
 // tile are therefore dealt round-robin onto RF_PARTS accumulators (chains 8x shorter) that the epilogue adds in fp32 RN.
-constexpr int RF_PARTS = 8;
+constexpr int RF_PARTS_SMEM = 8, RF_PARTS_TMEM = 4;
 constexpr int RF_PART_COLS = 2 * 16;                // a partial accumulator: columns 0..15 = x.q_hi terms, 16..31 = x_hi.q_mid
-constexpr int RF_ACC = 2, RF_ACC_STRIDE = RF_PARTS * RF_PART_COLS;   // tiles in flight in TMEM x 256 columns each
-constexpr int RF_MAX_STAGES = 8;
+constexpr int RF_ACC = 2;                           // tiles in flight in TMEM
+// MID_TMEM variant: the mid piece never touches shared memory.  The kernel is bound by shared-memory bandwidth when the
+// converters write a mid tile that the MMA then reads back (90 KB of traffic per 16 KB slice, 0.68 of the HBM roofline
+// measured); here each converter thread owns one corpus ROW (conflict-free reads thanks to the 128-byte swizzle), and
+// stores its 32 mid values into TMEM with tcgen05.st, where the MMA takes them as its A operand (58 KB per slice).
+// TMEM columns: 2 tiles x 4 partial accumulators x 32 + 3 mid buffers x 32 = 352 (512 allocated).
+constexpr int RF_MID_TMEM_BUFS = 3;
+constexpr int RF_MID_TMEM_COL0 = RF_ACC * RF_PARTS_TMEM * RF_PART_COLS;   // 256
+constexpr int RF_MAX_STAGES = 10;
 constexpr u32 RF_TF32_MASK = 0xffffe000u;
 
 struct RowsF32Params {
   int B, k, D, num_kb, stages, mids;          // raw ring stages, mid side buffers
+  int backoff;             // 1: waiting epilogue warps sleep between polls
   int store_hi;            // 1: the converters also write the truncated hi piece back in place (see rows_f32_store_hi)
   int q0;                  // this launch serves queries [q0, min(B, q0 + 16))
   long long N;
@@ -80,9 +88,33 @@ __device__ __forceinline__ void umma_tf32(u32 tmem_d, u64 desc_a, u64 desc_b, u3
       : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// A operand from tensor memory (128 lanes = rows, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(u32 tmem_d, u32 tmem_a, u64 desc_b, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(u32 taddr, const u32* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+template <bool MID_TMEM>
 __global__ void __launch_bounds__(RF_THREADS, 1)
 rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, const RowsF32Params p) {
+  constexpr int RF_PARTS = MID_TMEM ? RF_PARTS_TMEM : RF_PARTS_SMEM;
+  constexpr int RF_ACC_STRIDE = RF_PARTS * RF_PART_COLS;
   extern __shared__ uint8_t smem_raw[];
   const u32 raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -92,7 +124,7 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   // that leaves room for an 8-deep ring (128 KB of corpus reads in flight per SM) at any D.
   uint8_t* smem_x = smem;                                         // [stages][20 KB]
   uint8_t* smem_m = smem_x + (size_t)p.stages * RF_RING_BYTES;    // [mids][128 x 128 B] mid
-  uint8_t* tail = smem_m + (size_t)p.mids * RF_STAGE_BYTES;
+  uint8_t* tail = smem_m + (MID_TMEM ? (size_t)0 : (size_t)p.mids * RF_STAGE_BYTES);
   u32* smem_hist = reinterpret_cast<u32*>(tail);                // [4][256]
   float* thr_s = reinterpret_cast<float*>(smem_hist + 4 * 256); // [4][16]
   u64* kth_s = reinterpret_cast<u64*>(thr_s + 4 * RF_NQ);       // [4][16]
@@ -109,7 +141,7 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
-  constexpr u32 TMEM_COLS = RF_ACC * RF_ACC_STRIDE;   // 512
+  constexpr u32 TMEM_COLS = 512;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_q);
@@ -170,7 +202,8 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             for (int kk = 0; kk < RF_BK / 8; ++kk) {      // K = 8 tf32 = 32 bytes per instruction
               // x_hi . [q_hi ; q_mid] -> 32 columns, then x_mid . q_hi onto the first 16
               umma_tf32(tmem_d, x_hi + (u64)(kk * 2), q_all + (u64)(kk * 2), p.idesc32, (kb >= RF_PARTS || kk != 0) ? 1u : 0u);
-              umma_tf32(tmem_d, x_mid + (u64)(kk * 2), q_all + (u64)(kk * 2), p.idesc, 1u);
+              if constexpr (MID_TMEM) umma_tf32_ts(tmem_d, tmem_base + RF_MID_TMEM_COL0 + (u32)m * 32u + (u32)kk * 8u, q_all + (u64)(kk * 2), p.idesc, 1u);
+              else umma_tf32(tmem_d, x_mid + (u64)(kk * 2), q_all + (u64)(kk * 2), p.idesc, 1u);
             }
             umma_commit(&empty_bar[stage]);
             umma_commit(&mid_empty_bar[m]);
@@ -195,6 +228,23 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&mid_empty_bar[m], mphase ^ 1u);                 // the MMAs that read this mid buffer `mids` slices ago retired
           mbar_wait(&full_bar[stage], phase);
+          if constexpr (MID_TMEM) {
+            // thread = corpus row (the TMEM lane its warp may address): its 128 bytes, un-swizzled chunk by chunk
+            const int row = (warp_idx & 3) * 32 + lane;
+            const uint8_t* rp = smem_x + (size_t)stage * RF_RING_BYTES + (size_t)row * 128;
+            u32 r[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 v = *reinterpret_cast<const uint4*>(rp + ((c ^ (row & 7)) << 4));
+              const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                r[c * 4 + e] = __float_as_uint(__uint_as_float(w[e]) - __uint_as_float(w[e] & RF_TF32_MASK)) & RF_TF32_MASK;
+            }
+            tmem_st32(tmem_base + ((u32)((warp_idx & 3) * 32) << 16) + RF_MID_TMEM_COL0 + (u32)m * 32u, r);
+            tmem_st_wait();
+            tc_fence_before();
+          } else {
           uint4* raw = reinterpret_cast<uint4*>(smem_x + (size_t)stage * RF_RING_BYTES);
           uint4* mid = reinterpret_cast<uint4*>(smem_m + (size_t)m * RF_STAGE_BYTES);
 #pragma unroll
@@ -210,6 +260,7 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             mid[c * 128 + ct] = r;
           }
           fence_proxy_async_smem();            // generic-proxy stores -> visible to the tensor core's (async proxy) reads
+          }
           __syncwarp();
           if (lane == 0) mbar_arrive(&conv_bar[stage]);
           if (++m == p.mids) { m = 0; mphase ^= 1u; }
@@ -242,7 +293,9 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const u32 acc = tile_iter % RF_ACC;
         const long long row = (long long)t * RF_ROWS + quarter * 32 + lane;
         const float m = (row < p.N) ? (p.row_mult ? __ldg(p.row_mult + row) : 1.0f) : __int_as_float(0x7fc00000);
-        mbar_wait(&tmem_full_bar[acc], (tile_iter / RF_ACC) & 1);
+        // a tile takes ~10 us to arrive: sleep between polls so the spin does not take issue slots from the converters
+        if (p.backoff) mbar_wait_backoff(&tmem_full_bar[acc], (tile_iter / RF_ACC) & 1, 200);
+        else mbar_wait(&tmem_full_bar[acc], (tile_iter / RF_ACC) & 1);
         tc_fence_after();
         const u32 taddr = tmem_base + ((u32)(quarter * 32) << 16) + acc * RF_ACC_STRIDE;
         const int nparts = p.num_kb < RF_PARTS ? p.num_kb : RF_PARTS;      // partial accumulators this tile wrote
@@ -317,13 +370,19 @@ static int rows_f32_store_hi() {
   static const int v = [] { const char* e = getenv("B200R_F32_STORE_HI"); return (e && e[0] == '1') ? 1 : 0; }();
   return v;
 }
+// B200R_F32_MID_TMEM=0 selects the variant that keeps the mid piece in shared memory (A/B measurements)
+static bool rows_f32_mid_tmem() {
+  static const bool v = [] { const char* e = getenv("B200R_F32_MID_TMEM"); return !(e && e[0] == '0'); }();
+  return v;
+}
 static int rows_f32_mids() {
+  if (rows_f32_mid_tmem()) return RF_MID_TMEM_BUFS;
   static const int m = [] { const char* e = getenv("B200R_F32_MIDS"); const int v = e ? atoi(e) : 3; return (v >= 2 && v <= 4) ? v : 3; }();
   return m;
 }
 static size_t rows_f32_smem_bytes(int stages) {
-  return 1024 + (size_t)stages * RF_RING_BYTES + (size_t)rows_f32_mids() * RF_STAGE_BYTES + 4 * 256 * 4 + (size_t)4 * RF_NQ * (4 + 8 + 4) +
-         (3 * RF_MAX_STAGES + 4 + 2 * RF_ACC + 2) * 8 + 16;
+  return 1024 + (size_t)stages * RF_RING_BYTES + (rows_f32_mid_tmem() ? 0 : (size_t)rows_f32_mids() * RF_STAGE_BYTES) + 4 * 256 * 4 +
+         (size_t)4 * RF_NQ * (4 + 8 + 4) + (3 * RF_MAX_STAGES + 4 + 2 * RF_ACC + 2) * 8 + 16;
 }
 static int rows_f32_stages_for(int) {
   int stages = RF_MAX_STAGES;
@@ -367,6 +426,7 @@ int launch_rows_f32(const Index* ix, const CUtensorMap* tmap_q, int group, const
   p.stages = rows_f32_stages_for(ix->D);
   p.mids = rows_f32_mids();
   p.store_hi = rows_f32_store_hi();
+  { static const int b = [] { const char* e = getenv("B200R_F32_BACKOFF"); return (e && e[0] == '0') ? 0 : 1; }(); p.backoff = b; }
   if (!p.stages) { set_error("fp32 tensor path: D=%d does not fit", ix->D); return B200R_EINVAL; }
   p.tile_begin = ph.tile_begin; p.tile_end = ph.tile_end; p.tiles_per_chunk = ph.tiles_per_chunk;
   p.num_units = ph.num_chunks;
@@ -379,9 +439,14 @@ int launch_rows_f32(const Index* ix, const CUtensorMap* tmap_q, int group, const
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((u32)(RF_NQ >> 3) << 17) | ((u32)(RF_ROWS >> 4) << 24);
   p.idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((u32)((2 * RF_NQ) >> 3) << 17) | ((u32)(RF_ROWS >> 4) << 24);
   const size_t smem = rows_f32_smem_bytes(p.stages);
-  B200R_CUDA_CHECK(cudaFuncSetAttribute(rows_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = p.num_units < kNumSMs ? p.num_units : kNumSMs;
-  rows_f32_kernel<<<grid, RF_THREADS, smem, st>>>(*tmap_q, ix->tmap_x_f32, p);
+  if (rows_f32_mid_tmem()) {
+    B200R_CUDA_CHECK(cudaFuncSetAttribute(rows_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rows_f32_kernel<true><<<grid, RF_THREADS, smem, st>>>(*tmap_q, ix->tmap_x_f32, p);
+  } else {
+    B200R_CUDA_CHECK(cudaFuncSetAttribute(rows_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rows_f32_kernel<false><<<grid, RF_THREADS, smem, st>>>(*tmap_q, ix->tmap_x_f32, p);
+  }
   count_launch();
   B200R_CUDA_CHECK(cudaGetLastError());
   return B200R_OK;

@@ -30,6 +30,10 @@ __device__ __forceinline__ bool mbar_try_wait(u64* bar, u32 parity) {
 __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// for warps that wait long while OTHER warps of the SM need the issue slots (converters, epilogue of a streaming kernel)
+__device__ __forceinline__ void mbar_wait_backoff(u64* bar, u32 parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
