@@ -359,6 +359,18 @@ def leg_graph(torch, dist, a, X, rank, world, dev, Qd, peaks, _native, steps=20,
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # per-launch-site timeline of the stage (events around every launch, 5 extra batches)
+    timeline = None
+    try:
+        _native.profile_timeline(True)
+        for i in range(5):
+            run(i)
+        torch.cuda.synchronize()
+        timeline = {site: {"ms_per_batch": v[0] / 5, "launches_per_batch": v[1] / 5} for site, v in _native.profile_dump().items()}
+    except Exception as e:  # noqa: BLE001
+        timeline = {"error": repr(e)}
+    finally:
+        _native.profile_timeline(False)
     ncand = float(out["ncand"].float().mean().item())
     gather_bytes = ncand * B * a.dim * 2 / world               # per GPU
     peak = peaks.get("hbm_gbs", 6650.0)
@@ -370,7 +382,7 @@ def leg_graph(torch, dist, a, X, rank, world, dev, Qd, peaks, _native, steps=20,
                         "frac": (gather_bytes / (gms * 1e-3) / 1e9 / peak) if gms > 0 else 0.0, "kernel": "rescore_gather_kernel",
                         "kernel_ms_per_batch": gms,
                         "algorithmic": "candidates*D*2 bytes per batch per GPU (random 1.5 KB rows), gather kernel time only"},
-           "stage_hbm_frac": gather_bytes / (ms * 1e-3) / 1e9 / peak}
+           "stage_hbm_frac": gather_bytes / (ms * 1e-3) / 1e9 / peak, "timeline": timeline}
     # ---- parity of the last batch against the oracle (2 queries): BFS on the host CSR, rows fetched from their owners ----
     try:
         leg["verify"] = verify_graph_leg(torch, dist, out, Qd[(steps - 1) % nb], seeds[(steps - 1) % nb], row_ptr, col, Xg, glo, ghi,
