@@ -25,6 +25,17 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int num_sms() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
+    cache[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+  }
+  return cache[dev];
+}
+
 // ---- optional event bracketing of the dominant kernel (b200r_profile_*) ----
 static bool g_prof_on = false;
 static std::vector<cudaEvent_t> g_prof_events;  // start0, stop0, start1, stop1, ...
@@ -149,7 +160,7 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
     pl->Bpad = (pl->rows_i8 ? pl->rows_i8 : pl->num_q_tiles) * BMq;
     // units = (query tile, chunk of row tiles).  More units per CTA = better balance, fewer = less list
     // traffic; pick the chunk count (near a target) that wastes the fewest CTA slots in the last wave.
-    const int grid_max = kPlanSMs / pl->cta_group;
+    const int grid_max = num_sms() / pl->cta_group;
     const int m = pl->num_q_tiles >= 16 ? 8 : (pl->num_q_tiles >= 4 ? 4 : (pl->num_q_tiles >= 2 ? 2 : 1));
     long long target = ((long long)grid_max * m + pl->num_q_tiles - 1) / pl->num_q_tiles;
     if (target < 1) target = 1;
@@ -211,14 +222,14 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
       // fp32 / int8: bulk-copy-fed scan, one persistent CTA per SM, every consumer warp keeps its own lists
       pl->scan_bulk = 1;
       const long long need = (ix->N + scan_bulk_tile_rows(ix) - 1) / scan_bulk_tile_rows(ix);
-      long long blocks = kPlanSMs;
+      long long blocks = num_sms();
       if (blocks > need) blocks = need < 1 ? 1 : need;
       pl->scan_blocks = (int)blocks;
       pl->scan_warps = (int)blocks * bulk_warps;
     } else {
       const int R = 4;
       const int warps_per_block = 8;
-      long long blocks = (long long)kPlanSMs * 3;   // scan kernels are compiled for 3 CTAs/SM: one full wave
+      long long blocks = (long long)num_sms() * 3;   // scan kernels are compiled for 3 CTAs/SM: one full wave
       const long long groups = (ix->N + R - 1) / R;
       const long long need = (groups + warps_per_block - 1) / warps_per_block;
       if (blocks > need) blocks = need < 1 ? 1 : need;

@@ -180,7 +180,7 @@ int launch_scatter_record(const CommDev& cd, const void* src, size_t bytes, size
   const size_t words = bytes / 4;
   int blocks = (int)((words / 4 + 255) / 256);
   if (blocks < 1) blocks = 1;
-  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+  if (blocks > 2 * num_sms()) blocks = 2 * num_sms();
   scatter_record_kernel<<<blocks, 256, 0, st>>>(cd, reinterpret_cast<const u32*>(src), words, rec_stride);
   count_launch();
   B200R_CUDA_CHECK(cudaGetLastError());

@@ -11,7 +11,6 @@ namespace b200r {
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
-constexpr int kNumSMs = 148;           // B200
 constexpr u32 kFullMask = 0xffffffffu;
 
 // ---------------------------------------------------------------------------------------------

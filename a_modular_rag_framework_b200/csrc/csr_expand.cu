@@ -48,7 +48,7 @@ constexpr int GATHER_MAX_WARPS = 16;
 constexpr int GATHER_CTAS_PER_SM = 2;
 constexpr int SEL_THREADS = 256;
 constexpr int SEL_WARPS = SEL_THREADS / 32;
-constexpr int EXP_PERSISTENT_CTAS = 2 * kNumSMs;
+static int exp_persistent_ctas() { return 2 * num_sms(); }
 constexpr u32 EXP_EMPTY = 0xffffffffu;
 constexpr int kStatusRetry = 1;       // internal: overflowed the small instantiation, the big one redoes it
 
@@ -829,7 +829,7 @@ int validate_csr(const long long* row_ptr, const int* col_idx, long long V, long
   int* d_bad = nullptr;
   B200R_CUDA_CHECK(cudaMalloc(&d_bad, sizeof(int)));
   B200R_CUDA_CHECK(cudaMemset(d_bad, 0, sizeof(int)));
-  validate_csr_kernel<<<2 * kNumSMs, 256>>>(row_ptr, col_idx, V, E, d_bad);
+  validate_csr_kernel<<<2 * num_sms(), 256>>>(row_ptr, col_idx, V, E, d_bad);
   count_launch();
   int bad = 0;
   cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
@@ -856,7 +856,7 @@ static int launch_bfs(const ExpandParams& p, cudaStream_t st) {
   count_launch();
   // persistent: only the queries that overflowed the small instantiation do any work
   B200R_CUDA_CHECK(cudaFuncSetAttribute(bfs_kernel<QT, EXP_MAXC_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bfs_smem_bytes(EXP_MAXC_BIG)));
-  bfs_kernel<QT, EXP_MAXC_BIG><<<std::min(nq, EXP_PERSISTENT_CTAS), BFS_THREADS, bfs_smem_bytes(EXP_MAXC_BIG), st>>>(p);
+  bfs_kernel<QT, EXP_MAXC_BIG><<<std::min(nq, exp_persistent_ctas()), BFS_THREADS, bfs_smem_bytes(EXP_MAXC_BIG), st>>>(p);
   count_launch();
   return B200R_OK;
 }
@@ -878,7 +878,7 @@ static int launch_gather(const ExpandParams& p, cudaStream_t st) {
   const size_t smem = (size_t)warps * dpad * 4;
   B200R_CUDA_CHECK(cudaFuncSetAttribute(rescore_gather_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   profile_begin(st);
-  rescore_gather_kernel<T><<<kNumSMs * ctas_per_sm, warps * 32, smem, st>>>(p, dpad);
+  rescore_gather_kernel<T><<<num_sms() * ctas_per_sm, warps * 32, smem, st>>>(p, dpad);
   profile_end(st);
   count_launch();
   return B200R_OK;
@@ -892,7 +892,7 @@ static int launch_select(const ExpandParams& p, cudaStream_t st) {
   fuse_select_kernel<EXP_MAXC_SMALL><<<nq, SEL_THREADS, select_smem_bytes(EXP_MAXC_SMALL, p.kp2), st>>>(p);
   count_launch();
   B200R_CUDA_CHECK(cudaFuncSetAttribute(fuse_select_kernel<EXP_MAXC_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_smem_bytes(EXP_MAXC_BIG, p.kp2)));
-  fuse_select_kernel<EXP_MAXC_BIG><<<std::min(nq, EXP_PERSISTENT_CTAS), SEL_THREADS, select_smem_bytes(EXP_MAXC_BIG, p.kp2), st>>>(p);
+  fuse_select_kernel<EXP_MAXC_BIG><<<std::min(nq, exp_persistent_ctas()), SEL_THREADS, select_smem_bytes(EXP_MAXC_BIG, p.kp2), st>>>(p);
   count_launch();
   return B200R_OK;
 }
@@ -917,7 +917,7 @@ static int launch_expand_phase_t(const ExpandParams& p, int phase, int qdtype, c
   } else if (phase == 3) {
     if ((rc = launch_select(p, st)) != B200R_OK) return rc;
   } else {
-    { ProfScope _ps(st, "graph_collect"); collect_outputs_kernel<<<2 * kNumSMs, 256, 0, st>>>(p); }
+    { ProfScope _ps(st, "graph_collect"); collect_outputs_kernel<<<2 * num_sms(), 256, 0, st>>>(p); }
     count_launch();
   }
   B200R_CUDA_CHECK(cudaGetLastError());
@@ -1157,10 +1157,10 @@ int launch_expand_rescore_big(const Index* ix, const Graph* g, const void* Q, co
   B200R_CUDA_CHECK(cudaMemsetAsync(b.ncand, 0, 256 + align_up(257 * 4, 256), st));
   bfs_big_seed_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const long long*>(seeds), S, V, b);
   for (int d = 1; d <= window; ++d) {
-    bfs_big_level_kernel<<<2 * kNumSMs, 256, 0, st>>>(reinterpret_cast<const long long*>(g->row_ptr), g->col_idx, V, d, b);
+    bfs_big_level_kernel<<<2 * num_sms(), 256, 0, st>>>(reinterpret_cast<const long long*>(g->row_ptr), g->col_idx, V, d, b);
     bfs_big_close_level_kernel<<<1, 1, 0, st>>>(d, b);
   }
-  bfs_big_finish_kernel<<<2 * kNumSMs, 256, 0, st>>>(reinterpret_cast<const long long*>(g->node_rows), b, out_ncand);
+  bfs_big_finish_kernel<<<2 * num_sms(), 256, 0, st>>>(reinterpret_cast<const long long*>(g->node_rows), b, out_ncand);
   count_launch(3 + 2 * window);
   int rc;
   const int qdtype = ix->dtype == B200R_I8 ? B200R_F32 : ix->dtype;
@@ -1180,7 +1180,7 @@ int launch_expand_rescore_big(const Index* ix, const Graph* g, const void* Q, co
     default: rc = launch_gather_big<int8_t>(p, st); break;
   }
   if (rc) return rc;
-  fuse_big_kernel<<<2 * kNumSMs, 256, 0, st>>>(b, window, alpha_dense, alpha_graph);
+  fuse_big_kernel<<<2 * num_sms(), 256, 0, st>>>(b, window, alpha_dense, alpha_graph);
   count_launch();
   if ((rc = launch_select_flat_keys(b.keys, b.ncand, V, k, out_scores, out_ids, st))) return rc;
   lookup_big_kernel<<<k, 256, 0, st>>>(b, window, k, reinterpret_cast<const long long*>(out_ids), out_scores, out_hops, out_gn, out_dn, out_cos);

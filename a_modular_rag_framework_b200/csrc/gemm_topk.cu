@@ -389,7 +389,7 @@ size_t query_replica_bytes(int D) { return (size_t)kQReplicas * BM * D * 2; }
 
 int launch_replicate_queries(const void* Q, void* rep, int B, int D, cudaStream_t st) {
   ProfScope _ps(st, "replicate_queries");
-  replicate_queries_kernel<unsigned short><<<kNumSMs, 256, 0, st>>>(reinterpret_cast<const unsigned short*>(Q),
+  replicate_queries_kernel<unsigned short><<<num_sms(), 256, 0, st>>>(reinterpret_cast<const unsigned short*>(Q),
                                                                     reinterpret_cast<unsigned short*>(rep), B, D);
   count_launch();
   B200R_CUDA_CHECK(cudaGetLastError());
@@ -431,7 +431,7 @@ static int launch_gemm_cg(const Index* ix, const CUtensorMap* tmap_q, const Sear
     p.range_off = reinterpret_cast<const long long*>(rg->offsets); p.range_out = reinterpret_cast<u64*>(rg->out);
   }
   B200R_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<CG>::kSmemBytes));
-  const int groups = p.num_units < kNumSMs / CG ? p.num_units : kNumSMs / CG;
+  const int groups = p.num_units < num_sms() / CG ? p.num_units : num_sms() / CG;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(groups * CG);

@@ -56,7 +56,8 @@ struct Graph {
 };
 int validate_csr(const long long* row_ptr, const int* col_idx, long long V, long long E);
 
-constexpr int kPlanSMs = 148;  // B200
+// SMs of the CURRENT device (148 on B200), queried once per device: grids and the plan are sized from it
+int num_sms();
 constexpr uint32_t kIndexMagic = 0xB200A001u;
 constexpr uint32_t kGraphMagic = 0xB200A002u;
 

@@ -439,7 +439,7 @@ int launch_rows_f32(const Index* ix, const CUtensorMap* tmap_q, int group, const
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((u32)(RF_NQ >> 3) << 17) | ((u32)(RF_ROWS >> 4) << 24);
   p.idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((u32)((2 * RF_NQ) >> 3) << 17) | ((u32)(RF_ROWS >> 4) << 24);
   const size_t smem = rows_f32_smem_bytes(p.stages);
-  const int grid = p.num_units < kNumSMs ? p.num_units : kNumSMs;
+  const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
   if (rows_f32_mid_tmem()) {
     B200R_CUDA_CHECK(cudaFuncSetAttribute(rows_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rows_f32_kernel<true><<<grid, RF_THREADS, smem, st>>>(*tmap_q, ix->tmap_x_f32, p);

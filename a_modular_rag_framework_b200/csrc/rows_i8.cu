@@ -350,7 +350,7 @@ static int launch_rows_i8_nq(const Index* ix, const CUtensorMap* tmap_q, const v
   p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((u32)(RiGeo<NQ>::NCOLS >> 3) << 17) | ((u32)(RI_ROWS >> 4) << 24);
   const size_t smem = rows_i8_smem_bytes(NQ, p.num_kb, p.stages);
   B200R_CUDA_CHECK(cudaFuncSetAttribute(rows_i8_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = p.num_units < kNumSMs ? p.num_units : kNumSMs;
+  const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
   rows_i8_kernel<NQ><<<grid, RI_THREADS, smem, st>>>(*tmap_q, ix->tmap_x_i8, p);
   count_launch();
   B200R_CUDA_CHECK(cudaGetLastError());

@@ -361,7 +361,7 @@ int launch_init_search(const SearchPlan& pl, void* ws, cudaStream_t st) {
   u32* gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
   int* counts = reinterpret_cast<int*>((char*)ws + pl.off_counts);
   const long long n_counts = (long long)(pl.num_segments + 1) * pl.Bpad;   // + the carry lists' counts
-  init_search_kernel<<<kNumSMs, 256, 0, st>>>(gthr, pl.Bpad, counts, n_counts);
+  init_search_kernel<<<num_sms(), 256, 0, st>>>(gthr, pl.Bpad, counts, n_counts);
   count_launch();
   B200R_CUDA_CHECK(cudaGetLastError());
   return B200R_OK;

@@ -590,7 +590,7 @@ int launch_range_unpack(const void*, int64_t total, const int64_t*, int, float, 
   if (total <= 0) return B200R_OK;
   ProfScope _ps(st, "range_unpack");
   long long blocks = (total + 255) / 256;
-  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   range_unpack_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<long long*>(out_ids), out_scores, total, id_base);
   count_launch();
   B200R_CUDA_CHECK(cudaGetLastError());

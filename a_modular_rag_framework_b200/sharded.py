@@ -187,72 +187,33 @@ INT64_MIN, INT64_MAX = -(1 << 63), (1 << 63) - 1
 
 
 def owned_range(N: int, world: int, rank: int) -> Tuple[int, int]:
-    """Global node ids whose candidates `rank` scores: its row block; the first rank also takes ids < 0 (none)
-    and the last rank everything >= its block start (graph nodes that are not corpus rows score 0.0, exactly as
-    on one GPU)."""
+    """Global node ids whose candidates `rank` scores in the two-pass owner-computes graph stage
+    (b200r_expand_rescore_sharded): its row block; the first rank also takes ids < 0 (none) and the last rank everything
+    >= its block start (graph nodes that are not corpus rows score 0.0, exactly as on one GPU)."""
     lo, hi = shard_rows(N, world, rank)
     return (INT64_MIN if rank == 0 else lo), (INT64_MAX if rank == world - 1 else hi)
 
 
 class ShardedGraphStage:
-    """Graph 2-hop expansion + re-score over a ROW-SHARDED corpus: the CSR is replicated,
-    every rank runs the same (cheap, integer-only) frontier expansion, re-scores only the candidates whose rows it
-    owns, the per-query cosine range is all-reduced (min/max; the reference's per-channel min-max normalisation is a
-    global reduction, retrieval_backend.py:296-301), each rank ranks its own candidates with the global range and the
-    per-rank top-k lists are all-gathered and merged by (fused score desc, id asc)."""
+    """Graph 2-hop expansion + re-score over a ROW-SHARDED corpus, one rank per process, entirely over
+    the library's exchange (b200r_expand_rescore_exchange): the CSR is replicated, queries are sharded by HOME rank (BFS,
+    fusion, top-k), candidates by the rank that OWNS their rows (gather + re-score), and every transfer is a peer store from
+    inside the kernels -- no NCCL collective and no host-side reduction; torch.distributed only swaps the window descriptors."""
 
-    def __init__(self, local_index, graph, N_total: int, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, local_index, graph, N_total: int, group: Optional[dist.ProcessGroup] = None, comm=None,
+                 max_B: int = 4096, max_k: int = 256):
         self.index, self.graph, self.N_total, self.group = local_index, graph, int(N_total), group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self._state = None
+        self.comm, self._cap = comm, (int(max_B), int(max_k))
 
     def run(self, Q: torch.Tensor, seeds: torch.Tensor, window: int, alpha_dense: float, alpha_graph: float, k: int):
-        from .index import ExpandShardState, expand_rescore_pass, merge_topk
-        B = int(Q.shape[0])
-        if self._state is None or self._state.out["score"].shape != (B, k):
-            self._state = ExpandShardState(self.index, B, k)
-        st = self._state
-        lo, hi = owned_range(self.N_total, self.world, self.rank)
-        expand_rescore_pass(self.index, self.graph, Q, seeds, window, alpha_dense, alpha_graph, k, st, 1, lo, hi)
-        if self.world > 1:
-            # ONE all-reduce for both ends of the range: max over ranks of (-min, max)
-            st.minmax[:, 0].neg_()
-            dist.all_reduce(st.minmax, op=dist.ReduceOp.MAX, group=self.group)
-            st.minmax[:, 0].neg_()
-        expand_rescore_pass(self.index, self.graph, Q, seeds, window, alpha_dense, alpha_graph, k, st, 2, lo, hi)
+        from .comm import ShardComm
+        from .index import expand_rescore, expand_rescore_exchange
         if self.world == 1:
-            return dict(st.out)
-        # ONE all-gather of the packed per-rank records, then the device merge (which also reports where each winner came from)
-        gathered = torch.empty((self.world, st.record.numel()), dtype=torch.uint8, device=st.record.device)
-        dist.all_gather_into_tensor(gathered, st.record, group=self.group)
-        return combine_shard_records(st.views(gathered), st.out["ncand"], st.out["status"], k)
-
-
-_AUX_KEYS = ("hop", "score_graph_norm", "score_dense_norm", "cos")
-_AUX_FILL = {"hop": -1, "score_graph_norm": 0.0, "score_dense_norm": 0.0, "cos": 0.0}
-
-
-def combine_shard_records(g: Dict[str, torch.Tensor], ncand: torch.Tensor, status: torch.Tensor, k: int):
-    """g: {field: [G, B, kin]} per-rank outputs.  Merge (score, id) on the device (b200r_merge_topk_src), then pick each
-    winner's other fields from the rank list and position the merge reports (plumbing)."""
-    from .index import merge_topk_src
-    G, B, kin = (int(x) for x in g["score"].shape)
-    ms, mi, src = merge_topk_src(g["score"], g["id"], k)
-    valid = src >= 0
-    s = src.clamp_min(0).long()
-    gi, ji = s // kin, s % kin
-    qi = torch.arange(B, device=s.device).unsqueeze(1).expand_as(s)
-    out = {"score": ms, "id": mi}
-    for key in _AUX_KEYS:
-        picked = g[key][gi, qi, ji]
-        out[key] = torch.where(valid, picked, torch.full_like(picked, _AUX_FILL[key]))
-    out["ncand"], out["status"] = ncand, status
-    return out
-
-
-def combine_shard_outputs(gathered, ncand: torch.Tensor, status: torch.Tensor, k: int):
-    """gathered: the six dense [G, B, k] per-rank outputs in the order (score, id, hop, score_graph_norm,
-    score_dense_norm, cos); see combine_shard_records."""
-    keys = ("score", "id") + _AUX_KEYS
-    return combine_shard_records(dict(zip(keys, gathered)), ncand, status, k)
+            return expand_rescore(self.index, self.graph, Q, seeds, window, alpha_dense, alpha_graph, k, check_status=False)
+        B = int(Q.shape[0])
+        if self.comm is None:
+            mb, mk = max(self._cap[0], B), max(self._cap[1], k)
+            self.comm = ShardComm.from_process_group(self.index.device.index or 0, mb, mk, max_graph_k=mk, group=self.group)
+        return expand_rescore_exchange(self.index, self.graph, self.comm, Q, seeds, window, alpha_dense, alpha_graph, k, self.N_total)

@@ -117,7 +117,8 @@ def test_graph_stage_virtual_shards_equal_single_gpu():
     all-reduce, pass 2 per shard, merge) must reproduce the single-launch result."""
     from a_modular_rag_framework_b200 import DenseIndex, PassageGraph, expand_rescore
     from a_modular_rag_framework_b200.index import ExpandShardState, expand_rescore_pass
-    from a_modular_rag_framework_b200.sharded import combine_shard_records, owned_range, shard_rows
+    from a_modular_rag_framework_b200.sharded import owned_range, shard_rows
+    from tests.helpers_sharded import combine_shard_records
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(21)
     V, E, D, B, S, k, G = 30000, 120000, 64, 16, 20, 10, 4
@@ -161,7 +162,8 @@ def test_graph_stage_ranks_that_own_no_candidates():
     (+inf, -inf) cosine ranges and all-padding lists, and the merge must still equal the single-launch result."""
     from a_modular_rag_framework_b200 import DenseIndex, PassageGraph, expand_rescore
     from a_modular_rag_framework_b200.index import ExpandShardState, expand_rescore_pass
-    from a_modular_rag_framework_b200.sharded import combine_shard_records, owned_range, shard_rows
+    from a_modular_rag_framework_b200.sharded import owned_range, shard_rows
+    from tests.helpers_sharded import combine_shard_records
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(5)
     V, D, B, S, k, G = 9000, 64, 5, 6, 8, 3
