@@ -465,9 +465,10 @@ class B200RetrievalBackend:
         kk = max(max(batch.top_ks[i] for i in valid), self.bm25_pool_k)
         groups: Dict[Tuple[str, int], List[int]] = {}
         local: Dict[int, LocalGraph] = {}
+        has_dense = (batch._dense_i[:, 0] >= 0)
         for pos, i in enumerate(valid):
             gid = getattr(reqs[i], "graph_id", "") or ""
-            if not gid or not len(batch.dense_rows(i)):
+            if not gid or not has_dense[pos]:
                 continue
             lg = self.graph_for(gid)
             if lg is not None:
@@ -481,11 +482,8 @@ class B200RetrievalBackend:
             idx = [valid[p] for p in members]
             Qg = Q[members]
             if kind == "corpus":
-                S = self.seed_k
-                seeds = np.full((len(idx), S), -1, dtype=np.int64)
-                for j, i in enumerate(idx):
-                    rows = batch.dense_rows(i)[:S]
-                    seeds[j, : len(rows)] = rows
+                # seeds = the dense top-seed_k rows (ids are already padded with -1 where the corpus has fewer rows)
+                seeds = np.ascontiguousarray(batch._dense_i[members, : self.seed_k])
                 out = self.engine.expand_rescore(Qg, seeds, window, self.alpha_dense, self.alpha_graph, kk)
             else:
                 blocks: Dict[int, int] = {}                     # id(LocalGraph) -> node offset of its block
