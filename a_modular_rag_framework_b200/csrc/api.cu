@@ -160,7 +160,9 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
     pl->Bpad = (pl->rows_i8 ? pl->rows_i8 : pl->num_q_tiles) * BMq;
     // units = (query tile, chunk of row tiles).  More units per CTA = better balance, fewer = less list
     // traffic; pick the chunk count (near a target) that wastes the fewest CTA slots in the last wave.
-    const int grid_max = num_sms() / pl->cta_group;
+    // int8: the query groups of a slice share one launch, num_sms / groups CTAs each (rows_i8.cu), so the chunks are
+    // sized for that many CTAs per group
+    const int grid_max = (pl->rows_i8 && !pl->rows_f32) ? rows_i8_ctas_per_group(pl->rows_i8) : num_sms() / pl->cta_group;
     const int m = pl->num_q_tiles >= 16 ? 8 : (pl->num_q_tiles >= 4 ? 4 : (pl->num_q_tiles >= 2 ? 2 : 1));
     long long target = ((long long)grid_max * m + pl->num_q_tiles - 1) / pl->num_q_tiles;
     if (target < 1) target = 1;
@@ -314,12 +316,11 @@ static int do_search_one(Index* ix, const void* Q, int B, int k, int path, float
   } else if (pl.path == B200R_PATH_GEMM && pl.rows_i8) {
     void* qws = (char*)ws + pl.off_qrep;
     if ((rc = launch_quantize_queries_i8(Q, B, pl.rows_i8_nq, ix->D, qws, st))) return rc;
-    std::vector<CUtensorMap> tmaps(pl.rows_i8);
-    for (int g = 0; g < pl.rows_i8; ++g)
-      if ((rc = encode_query_tmap_i8(qws, g, pl.rows_i8_nq, ix->D, &tmaps[g]))) return rc;
+    CUtensorMap tmap_q;
+    if ((rc = encode_query_tmap_i8(qws, pl.rows_i8, pl.rows_i8_nq, ix->D, &tmap_q))) return rc;
     for (int i = 0; i < pl.num_phases; ++i) {
       profile_begin(st);
-      for (int g = 0; g < pl.rows_i8 && !rc; ++g) rc = launch_rows_i8(ix, &tmaps[g], qws, g, pl, pl.phases[i], ws, st);
+      rc = launch_rows_i8(ix, &tmap_q, qws, pl, pl.phases[i], ws, st);
       profile_end(st);
       if (rc) return rc;
       if (i + 1 < pl.num_phases && (rc = launch_select_lists(ix, pl, ws, nullptr, nullptr, st))) return rc;

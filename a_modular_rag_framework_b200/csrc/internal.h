@@ -85,7 +85,7 @@ struct SearchPlan {
   // gemm: row tiles are processed in phases [tile_begin, tile_end) of geometrically growing size; after each
   // phase the exact k-th best so far becomes every query's filter threshold for the next one
   int cta_group;         // 1 or 2 (CTA pair, cta_group::2)
-  int rows_i8;           // > 0: int8 tensor path (rows_i8.cu) with this many groups of rows_i8_nq queries; 128-row tiles, 4 lists per unit
+  int rows_i8;           // > 0: int8 tensor path (rows_i8.cu) with this many groups of rows_i8_nq queries (ganged in one launch); 128-row tiles, 4 lists per unit
   int rows_i8_nq;        // 16 / 32 / 64
   int rows_f32;          // 1: the groups above are served by the fp32 split-precision kernel (rows_f32.cu, 16 queries each)
   int q_replicas;        // 1: single query tile replicated in the workspace (off_qrep) against L2 hot-spotting
@@ -124,9 +124,10 @@ int rows_i8_nq(int B, int D);                 // queries per corpus pass (16 / 3
 int rows_i8_tile_rows();
 size_t rows_i8_query_bytes(int B, int nq, int D);
 int launch_quantize_queries_i8(const void* Q, int B, int nq, int D, void* qws, cudaStream_t st);
-int encode_query_tmap_i8(const void* qws, int group, int nq, int D, CUtensorMap* tmap_q);
-int launch_rows_i8(const Index* ix, const CUtensorMap* tmap_q, const void* qws, int group, const SearchPlan& p, const GemmPhase& ph, void* ws,
-                   cudaStream_t st);
+int encode_query_tmap_i8(const void* qws, int groups, int nq, int D, CUtensorMap* tmap_q);   // one map over every group's limb rows
+int rows_i8_ctas_per_group(int groups);      // CTAs per query group when `groups` groups are ganged in one launch
+int launch_rows_i8(const Index* ix, const CUtensorMap* tmap_q, const void* qws, const SearchPlan& p, const GemmPhase& ph, void* ws,
+                   cudaStream_t st);        // one phase of ALL the plan's query groups
 int rows_f32_nq(int D);                       // queries per corpus pass of the fp32 tensor path (16), 0 = not available
 int rows_f32_tile_rows();
 size_t rows_f32_query_bytes(int B, int D);

@@ -37,25 +37,28 @@ template <int NQ> struct RiGeo {
 
 struct RowsI8Params {
   int B, k, D, num_kb, stages;
-  int q0;                  // this launch serves queries [q0, min(B, q0 + NQ)): list / threshold / count slots q0 + j
+  int groups;              // query groups ganged in this launch: CTA b serves group b % groups (queries [g*NQ, g*NQ + NQ)) and is
+                           // CTA b / groups of the gridDim.x / groups that share that group's units.  The CTAs of one gang index
+                           // stream the same corpus tiles at the same time, so HBM sees each tile once and the rest hit in L2
   long long N;
   int tile_begin, tile_end, tiles_per_chunk, num_units;
   int cap, cap_soft, Bpad;
   const float* row_mult;
-  const float* qscale;     // [NQ] q_j ~= qscale[j] * (l2*65536 + l1*256 + l0)
+  const float* qscale;     // [groups * NQ] q_j ~= qscale[j] * (l2*65536 + l1*256 + l0)
   u64* lists;
   int* counts;
   u32* gthr;
   u32 idesc;
 };
 
-// ---- query quantisation: f32 [B, D] -> per group of nq queries: limb planes int8 [3][nq][D] + scale[nq] -----------
+// ---- query quantisation: f32 [B, D] -> limb planes int8 [groups][3][nq][D] (one 2-D tensor map over all of them), then
+// the scales f32 [groups][nq] -------------------------------------------------------------------------------------------
 __global__ void quantize_queries_i8_kernel(const float* __restrict__ Q, int B, int D, int nq, int8_t* __restrict__ qws,
-                                           size_t group_bytes, size_t scale_off) {
+                                           size_t scale_off) {
   const int g = blockIdx.x / nq, j = blockIdx.x % nq;           // group of nq queries, slot inside it
   const int query = g * nq + j;
-  int8_t* limbs = qws + (size_t)g * group_bytes;
-  float* scale = reinterpret_cast<float*>(qws + (size_t)g * group_bytes + scale_off);
+  int8_t* limbs = qws + (size_t)g * 3 * nq * D;
+  float* scale = reinterpret_cast<float*>(qws + scale_off) + (size_t)g * nq;
   __shared__ float s_max[32];
   float m = 0.0f;
   if (query < B)
@@ -110,6 +113,10 @@ rows_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
+  const int group = blockIdx.x % p.groups;          // which NQ queries
+  const int u_first = blockIdx.x / p.groups;        // first unit of this CTA, then every u_step-th
+  const int u_step = gridDim.x / p.groups;
+  const int q0 = group * RI_NQ;                     // list / threshold / count slots q0 + j
   constexpr u32 TMEM_COLS = RI_ACC * RI_ACC_STRIDE;   // 256 (NQ = 16) or 512
 
   if (threadIdx.x == 0) {
@@ -120,7 +127,7 @@ rows_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     mbar_init(q_bar, 1);
     fence_barrier_init();
   }
-  if (threadIdx.x < RI_NQ) qscale_s[threadIdx.x] = p.qscale[threadIdx.x];   // RI_NQ <= 64 < RI_THREADS
+  if (threadIdx.x < RI_NQ) qscale_s[threadIdx.x] = p.qscale[q0 + threadIdx.x];   // RI_NQ <= 64 < RI_THREADS
   if (warp_idx == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -135,9 +142,9 @@ rows_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     if (lane == 0) {
       // the limb block, once: num_kb slices of [3*NQ limb rows x 128 bytes] (columns >= D are zero-filled by TMA)
       mbar_expect_tx(q_bar, (u32)(p.num_kb * RI_Q_KB_BYTES));
-      for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(smem_q + (size_t)kb * RI_Q_KB_BYTES, &tmap_q, q_bar, kb * RI_BK, 0, kEvictLast);
+      for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(smem_q + (size_t)kb * RI_Q_KB_BYTES, &tmap_q, q_bar, kb * RI_BK, group * RiGeo<NQ>::NCOLS, kEvictLast);
       int stage = 0; u32 phase = 0;
-      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      for (int u = u_first; u < p.num_units; u += u_step) {
         const int t0 = p.tile_begin + u * p.tiles_per_chunk;
         const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
         for (int t = t0; t < t1; ++t) {
@@ -156,7 +163,7 @@ rows_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_wait(q_bar, 0);
       int stage = 0; u32 phase = 0;
       u32 tile_iter = 0;
-      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      for (int u = u_first; u < p.num_units; u += u_step) {
         const int t0 = p.tile_begin + u * p.tiles_per_chunk;
         const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
         for (int t = t0; t < t1; ++t, ++tile_iter) {
@@ -188,16 +195,16 @@ rows_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     u64* kth = kth_s + ew * RI_NQ;
     int* cnt = cnt_s + ew * RI_NQ;
     u32 tile_iter = 0;
-    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+    for (int u = u_first; u < p.num_units; u += u_step) {
       const int t0 = p.tile_begin + u * p.tiles_per_chunk;
       const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
       if (t0 >= t1) continue;
       const size_t seg = (size_t)u * 4 + ew;               // this warp's list segment for the unit's row chunk
       for (int j = lane; j < RI_NQ; j += 32) {
-        const bool valid = p.q0 + j < p.B;
-        thr[j] = valid ? ordered_to_f32(__ldcg(p.gthr + p.q0 + j)) : __int_as_float(0x7f800000);
+        const bool valid = q0 + j < p.B;
+        thr[j] = valid ? ordered_to_f32(__ldcg(p.gthr + q0 + j)) : __int_as_float(0x7f800000);
         kth[j] = 0;
-        cnt[j] = valid ? __ldcg(p.counts + seg * p.Bpad + p.q0 + j) : 0;
+        cnt[j] = valid ? __ldcg(p.counts + seg * p.Bpad + q0 + j) : 0;
       }
       __syncwarp();
       for (int t = t0; t < t1; ++t, ++tile_iter) {
@@ -241,7 +248,7 @@ rows_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 const u32 b2 = __ballot_sync(kFullMask, (s[j] >= tj) && key > kth[jj]);
                 if (b2) {
                   const int base = cnt[jj];
-                  u64* lp = p.lists + (seg * p.Bpad + p.q0 + jj) * (size_t)p.cap;
+                  u64* lp = p.lists + (seg * p.Bpad + q0 + jj) * (size_t)p.cap;
                   if ((b2 >> lane) & 1u) __stcg(lp + base + __popc(b2 & ((1u << lane) - 1u)), key);
                   const int n = base + __popc(b2);
                   __syncwarp();
@@ -249,7 +256,7 @@ rows_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     const u64 kk = warp_compact(lp, n, p.k, hist);
                     if (lane == 0) {
                       kth[jj] = kk; thr[jj] = fmaxf(tj, key_score(kk)); cnt[jj] = p.k;
-                      atomicMax(p.gthr + p.q0 + jj, (u32)(kk >> 32));
+                      atomicMax(p.gthr + q0 + jj, (u32)(kk >> 32));
                     }
                   } else if (lane == 0) {
                     cnt[jj] = n;
@@ -262,11 +269,11 @@ rows_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
         // thresholds published by other CTAs / warps
         for (int j = lane; j < RI_NQ; j += 32)
-          if (p.q0 + j < p.B) thr[j] = fmaxf(thr[j], ordered_to_f32(__ldcg(p.gthr + p.q0 + j)));
+          if (q0 + j < p.B) thr[j] = fmaxf(thr[j], ordered_to_f32(__ldcg(p.gthr + q0 + j)));
         __syncwarp();
       }
       for (int j = lane; j < RI_NQ; j += 32)
-        if (p.q0 + j < p.B) p.counts[seg * p.Bpad + p.q0 + j] = cnt[j];
+        if (q0 + j < p.B) p.counts[seg * p.Bpad + q0 + j] = cnt[j];
       __syncwarp();
     }
   }
@@ -309,31 +316,35 @@ int rows_i8_nq(int B, int D) {
   return best;
 }
 
-// workspace for the quantised queries, per group of nq: limb planes [3][nq][D] int8, then nq scales
-static size_t rows_i8_group_bytes(int nq, int D) { return align_up((size_t)3 * nq * D, 256) + 256; }
-size_t rows_i8_query_bytes(int B, int nq, int D) { return (size_t)((B + nq - 1) / nq) * rows_i8_group_bytes(nq, D); }
+// workspace for the quantised queries: limb planes [groups][3][nq][D] int8 (contiguous: ONE tensor map covers every group),
+// then groups * nq scales
+static size_t rows_i8_limb_bytes(int groups, int nq, int D) { return align_up((size_t)groups * 3 * nq * D, 256); }
+size_t rows_i8_query_bytes(int B, int nq, int D) {
+  const int groups = (B + nq - 1) / nq;
+  return rows_i8_limb_bytes(groups, nq, D) + align_up((size_t)groups * nq * 4, 256);
+}
 
 int launch_quantize_queries_i8(const void* Q, int B, int nq, int D, void* qws, cudaStream_t st) {
   ProfScope _ps(st, "quantize_queries_i8");
   const int groups = (B + nq - 1) / nq;
   quantize_queries_i8_kernel<<<groups * nq, 256, 0, st>>>(reinterpret_cast<const float*>(Q), B, D, nq, reinterpret_cast<int8_t*>(qws),
-                                                        rows_i8_group_bytes(nq, D), align_up((size_t)3 * nq * D, 256));
+                                                        rows_i8_limb_bytes(groups, nq, D));
   count_launch();
   B200R_CUDA_CHECK(cudaGetLastError());
   return B200R_OK;
 }
 
-int encode_query_tmap_i8(const void* qws, int group, int nq, int D, CUtensorMap* tmap_q) {
-  const char* base = reinterpret_cast<const char*>(qws) + (size_t)group * rows_i8_group_bytes(nq, D);
-  return encode_tmap_2d(tmap_q, B200R_I8, base, (uint64_t)D, (uint64_t)(3 * nq), RI_BK, (uint32_t)(3 * nq));
+// one map over the limb rows of every group: box = the 3*nq limb rows of one group x one 128-byte K slice
+int encode_query_tmap_i8(const void* qws, int groups, int nq, int D, CUtensorMap* tmap_q) {
+  return encode_tmap_2d(tmap_q, B200R_I8, qws, (uint64_t)D, (uint64_t)groups * 3 * nq, RI_BK, (uint32_t)(3 * nq));
 }
 
 template <int NQ>
-static int launch_rows_i8_nq(const Index* ix, const CUtensorMap* tmap_q, const void* qws, int group, const SearchPlan& pl,
+static int launch_rows_i8_nq(const Index* ix, const CUtensorMap* tmap_q, const void* qws, const SearchPlan& pl,
                              const GemmPhase& ph, void* ws, cudaStream_t st) {
   RowsI8Params p;
   p.B = pl.B; p.k = pl.k; p.D = ix->D; p.N = ix->N;
-  p.q0 = group * NQ;
+  p.groups = pl.rows_i8;
   p.num_kb = (ix->D + RI_BK - 1) / RI_BK;
   p.stages = rows_i8_stages_for(NQ, ix->D);
   if (!p.stages) { set_error("int8 tensor path: D=%d not supported with %d queries per pass", ix->D, NQ); return B200R_EINVAL; }
@@ -341,8 +352,7 @@ static int launch_rows_i8_nq(const Index* ix, const CUtensorMap* tmap_q, const v
   p.num_units = ph.num_chunks;
   p.cap = pl.cap; p.cap_soft = pl.cap_soft; p.Bpad = pl.Bpad;
   p.row_mult = ix->row_mult;
-  p.qscale = reinterpret_cast<const float*>(reinterpret_cast<const char*>(qws) + (size_t)group * rows_i8_group_bytes(NQ, ix->D) +
-                                            align_up((size_t)3 * NQ * ix->D, 256));
+  p.qscale = reinterpret_cast<const float*>(reinterpret_cast<const char*>(qws) + rows_i8_limb_bytes(pl.rows_i8, NQ, ix->D));
   p.lists = reinterpret_cast<u64*>((char*)ws + pl.off_lists);
   p.counts = reinterpret_cast<int*>((char*)ws + pl.off_counts);
   p.gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
@@ -350,21 +360,29 @@ static int launch_rows_i8_nq(const Index* ix, const CUtensorMap* tmap_q, const v
   p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((u32)(RiGeo<NQ>::NCOLS >> 3) << 17) | ((u32)(RI_ROWS >> 4) << 24);
   const size_t smem = rows_i8_smem_bytes(NQ, p.num_kb, p.stages);
   B200R_CUDA_CHECK(cudaFuncSetAttribute(rows_i8_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
-  rows_i8_kernel<NQ><<<grid, RI_THREADS, smem, st>>>(*tmap_q, ix->tmap_x_i8, p);
+  // a gang of `groups` CTAs per unit slot; the plan sized the chunks for num_sms / groups CTAs per group
+  int per_group = rows_i8_ctas_per_group(pl.rows_i8);
+  if (per_group > p.num_units) per_group = p.num_units;
+  rows_i8_kernel<NQ><<<per_group * p.groups, RI_THREADS, smem, st>>>(*tmap_q, ix->tmap_x_i8, p);
   count_launch();
   B200R_CUDA_CHECK(cudaGetLastError());
   return B200R_OK;
 }
 
-// one launch = one phase of one group of <= pl.rows_i8_nq queries
-int launch_rows_i8(const Index* ix, const CUtensorMap* tmap_q, const void* qws, int group, const SearchPlan& pl, const GemmPhase& ph,
+// CTAs each query group gets when `groups` groups share one launch (one CTA per SM in total)
+int rows_i8_ctas_per_group(int groups) {
+  const int n = num_sms() / (groups > 0 ? groups : 1);
+  return n > 0 ? n : 1;
+}
+
+// one launch = one phase of every group of <= pl.rows_i8_nq queries of the (<= 256-query) slice
+int launch_rows_i8(const Index* ix, const CUtensorMap* tmap_q, const void* qws, const SearchPlan& pl, const GemmPhase& ph,
                    void* ws, cudaStream_t st) {
   ProfScope _ps(st, "rows_i8");
   switch (pl.rows_i8_nq) {
-    case 16: return launch_rows_i8_nq<16>(ix, tmap_q, qws, group, pl, ph, ws, st);
-    case 32: return launch_rows_i8_nq<32>(ix, tmap_q, qws, group, pl, ph, ws, st);
-    case 64: return launch_rows_i8_nq<64>(ix, tmap_q, qws, group, pl, ph, ws, st);
+    case 16: return launch_rows_i8_nq<16>(ix, tmap_q, qws, pl, ph, ws, st);
+    case 32: return launch_rows_i8_nq<32>(ix, tmap_q, qws, pl, ph, ws, st);
+    case 64: return launch_rows_i8_nq<64>(ix, tmap_q, qws, pl, ph, ws, st);
   }
   set_error("int8 tensor path: bad group size %d", pl.rows_i8_nq);
   return B200R_EINVAL;

@@ -86,7 +86,7 @@ def run_search(name, N, D, B, k, dtype, path, steps=10, warmup=3, check=True):
     return line
 
 
-def run_search_i8(name, N, D, B, k, steps=10, warmup=3, path="auto"):
+def run_search_i8(name, N, D, B, k, steps=10, warmup=3, path="auto", check=True):
     Xf = corpus(N, D, torch.float16)
     X = torch.empty((N, D), dtype=torch.int8, device=dev)
     blk = 1 << 20
@@ -109,11 +109,37 @@ def run_search_i8(name, N, D, B, k, steps=10, warmup=3, path="auto"):
     _native.profile_enable(False)
     ms = e0.elapsed_time(e1) / steps
     kms /= steps
-    tensor = path != "scan"                        # tcgen05 kind::i8: one corpus pass per group of up to 64 queries
-    gbs = N * D * ((B + 63) // 64 if tensor else (B + 3) // 4) / (kms * 1e-3) / 1e9
-    print(json.dumps({"config": name, "rows": N, "dim": D, "batch": B, "k": k, "dtype": "int8", "path": "tensor_i8" if tensor else "scan", "ms_per_batch": ms,
-                      "kernel_launches_per_batch": kn / steps,
-                      "queries_per_s": B / (ms * 1e-3), "kernel_ms_per_batch": kms, "hbm_GBps": gbs, "hbm_frac_of_measured": gbs / PEAKS["hbm_gbs"]}), flush=True)
+    tensor = path != "scan"
+    # tcgen05 kind::i8: the (up to 4) 64-query groups of a 256-query slice share one launch and the corpus tiles through L2,
+    # so HBM sees the corpus once per slice; the MMA work is three signed-byte limbs per query
+    passes = (B + 255) // 256 if tensor else (B + 3) // 4
+    gbs = N * D * passes / (kms * 1e-3) / 1e9
+    tops = 3 * 2.0 * B * N * D / (kms * 1e-3) / 1e12
+    line = {"config": name, "rows": N, "dim": D, "batch": B, "k": k, "dtype": "int8", "path": "tensor_i8" if tensor else "scan", "ms_per_batch": ms,
+            "kernel_launches_per_batch": kn / steps, "queries_per_s": B / (ms * 1e-3), "kernel_ms_per_batch": kms, "hbm_GBps": gbs,
+            "hbm_frac_of_measured": gbs / PEAKS["hbm_gbs"]}
+    if tensor:
+        line["int8_limb_TOPs"] = tops
+        line["frac_of_2x_bf16_sustained"] = tops / (2.0 * PEAKS["bf16_tflops_sustained"])
+    if check:
+        # last batch, a few queries spread over the groups: fp32 scores of the dequantised rows on the device (torch, test
+        # infrastructure), ranked by the oracle's rule
+        from oracle import retrieval_oracle as O
+        s, ids = ix.search(Q[warmup + steps - 1], k, path=path)
+        sel = sorted(set(int(x) for x in np.linspace(0, B - 1, num=min(B, 4))))
+        Qs = Q[warmup + steps - 1][sel].float()
+        Qs = Qs / Qs.norm(dim=1, keepdim=True)
+        sc = torch.empty((len(sel), N), dtype=torch.float32, device=dev)
+        for r0 in range(0, N, blk):
+            Xb = X[r0:r0 + blk].float()
+            sc[:, r0:r0 + blk] = (Qs @ Xb.T) / Xb.norm(dim=1)[None, :]
+        ws_, wi_ = O.topk_from_scores(sc.cpu().numpy().astype(np.float64), k)
+        got_i, got_s = ids[sel].cpu().numpy(), s[sel].cpu().numpy()
+        line["recall_vs_f32"] = float(np.mean([len(set(got_i[b]) & set(wi_[b])) / k for b in range(len(sel))]))
+        line["max_abs_score_err"] = float(np.max(np.abs(np.sort(got_s, 1) - np.sort(ws_, 1))))
+    print(json.dumps(line), flush=True)
+    del ix, X, Q
+    torch.cuda.empty_cache()
 
 
 def run_graph(name, V, E, D, B, S, k, steps=40, warmup=8, window=2, random_seeds=False, nbatch=4):
@@ -185,6 +211,8 @@ CONFIGS = {
     "i8_10Mx768_B4_tensor": lambda: run_search_i8("i8_10Mx768_B4_tensor", 10_000_000, 768, 4, 100, steps=20),
     "i8_10Mx768_B32_tensor": lambda: run_search_i8("i8_10Mx768_B32_tensor", 10_000_000, 768, 32, 100, steps=10),
     "i8_10Mx768_B256_tensor": lambda: run_search_i8("i8_10Mx768_B256_tensor", 10_000_000, 768, 256, 100, steps=5),
+    "i8_10Mx768_B1024_tensor": lambda: run_search_i8("i8_10Mx768_B1024_tensor", 10_000_000, 768, 1024, 100, steps=3, warmup=2),
+    "i8_10Mx768_B4096_tensor": lambda: run_search_i8("i8_10Mx768_B4096_tensor", 10_000_000, 768, 4096, 100, steps=3, warmup=2),
     "i8_10Mx768_B64_tensor": lambda: run_search_i8("i8_10Mx768_B64_tensor", 10_000_000, 768, 64, 100, steps=10),
     "i8_10Mx768_B16_tensor": lambda: run_search_i8("i8_10Mx768_B16_tensor", 10_000_000, 768, 16, 100, steps=20),
     "cfg2_10Mx768_B1_gemm": lambda: run_search("cfg2_10Mx768_B1_gemm", 10_000_000, 768, 1, 100, torch.bfloat16, "gemm", steps=20),

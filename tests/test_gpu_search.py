@@ -190,6 +190,9 @@ def test_bulk_fed_scan_shapes(N, D, B, k, dtype):
     (70000, 768, 64, 100, "cos"),           # a full 64-query group at the benchmark width
     (5000, 1024, 40, 10, "cos"),            # 64 resident queries would not fit next to the ring: two groups of 32
     (3000, 64, 300, 5, "cos"),              # more than one 256-query slice
+    (120000, 768, 256, 50, "cos"),          # four 64-query groups ganged in one launch (37 CTAs each), several phases
+    (50000, 256, 130, 20, "ip"),            # three ganged groups, the last one mostly empty
+    (40000, 1024, 200, 10, "cos"),          # seven ganged groups of 32 (21 CTAs each, one SM idle)
 ])
 def test_int8_tensor_path(N, D, B, k, metric):
     """int8 corpora run on tcgen05 kind::i8 (rows_i8.cu), 16 / 32 / 64 queries per corpus pass: query limbs, exact int32 sums."""
