@@ -179,6 +179,37 @@ def test_retrieve_many_equals_retrieve(corpus):
     assert mixed[0].hits[0].meta["row"] == 5 and len(mixed[1].hits) == 3
 
 
+def test_batch_converted_materialisation_equals_the_general_path(corpus, monkeypatch):
+    """RetrievalBatch.result has two routes to the same hits: lists converted once per batch (no text channel, no MMR)
+    and per-request arrays.  Graph and dense-only requests, top_k beyond the corpus, id collisions on sent_id 0
+    (every document's first sentence normalises to 'sent::<doc>::', retrieval_backend.py:283-294)."""
+    from a_modular_rag_framework_b200.backend import RetrievalBatch
+    be = _backend(corpus, seed_k=6)
+    reqs = [_req(corpus.docs[r]["text"], top_k=k, graph_id=g, trace_id=f"t{r}")
+            for r, k, g in ((0, 10, "g1"), (5, 3, "g1"), (10, 10, ""), (17, 100, ""), (20, 100, "g1"), (31, 1, "g1"), (45, 25, ""))]
+    batch = be.run_batch(reqs)
+    fast = [batch.result(i) for i in range(len(reqs))]
+    assert batch._heads, "the batch-converted route did not run"
+    monkeypatch.setattr(RetrievalBatch, "_fast_hits", lambda self, i, top_k: None)
+    slow_batch = be.run_batch(reqs)
+    slow = [slow_batch.result(i) for i in range(len(reqs))]
+    assert not slow_batch._heads
+    for a, b in zip(fast, slow):
+        assert a == b
+    assert any(h["id"].endswith("::") for h in fast[0]["hits"])     # a sent_id-0 collision id is in play
+    assert len(fast[3]["hits"]) <= len(corpus.docs)
+
+
+def test_query_matrix_accepts_lists_and_arrays():
+    qm = B200RetrievalBackend._query_matrix
+    v = [[1.0, 2.0, 3.0], None, [0.0, 0.0, 0.0], [4.0, 5.0], [6.0, 7.0, 8.0]]
+    valid, Q = qm(v, 3)
+    assert valid == [0, 4] and Q.dtype == np.float32 and np.array_equal(Q, np.asarray([[1, 2, 3], [6, 7, 8]], dtype=np.float32))
+    valid, Q = qm([np.asarray([1.0, 0.0]), np.asarray([0.0, 2.0])], None)
+    assert valid == [0, 1] and Q.shape == (2, 2)
+    assert qm([None, []], 3) == ([], None)
+
+
 # ------------------------------------------------------------------------------------------------ a5: graph_id -> graph.json
 
 
