@@ -2,6 +2,7 @@
 #include "internal.h"
 
 #include <atomic>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -37,35 +38,44 @@ int num_sms() {
 }
 
 // ---- optional event bracketing of the dominant kernel (b200r_profile_*) ----
-static bool g_prof_on = false;
-static std::vector<cudaEvent_t> g_prof_events;  // start0, stop0, start1, stop1, ...
+// Host threads may search concurrently (one per device in a multi-GPU host): the switches are atomics, every thread
+// keeps its own open bracket, and finished (start, stop) pairs are appended under one mutex.
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
+struct ProfPair { cudaEvent_t a, b; };
+static std::vector<ProfPair> g_prof_events;
+static thread_local cudaEvent_t t_prof_open = nullptr;
 void profile_begin(cudaStream_t st) {
-  if (!g_prof_on) return;
+  if (!g_prof_on.load(std::memory_order_relaxed) || t_prof_open) return;
   cudaEvent_t e;
-  if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); g_prof_events.push_back(e); }
+  if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); t_prof_open = e; }
 }
 void profile_end(cudaStream_t st) {
-  if (!g_prof_on || (g_prof_events.size() & 1) == 0) return;
-  cudaEvent_t e;
-  if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); g_prof_events.push_back(e); }
-  else { cudaEventDestroy(g_prof_events.back()); g_prof_events.pop_back(); }
+  if (!t_prof_open) return;
+  cudaEvent_t a = t_prof_open, e;
+  t_prof_open = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) { cudaEventDestroy(a); return; }
+  cudaEventRecord(e, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_events.push_back({a, e});
 }
 
 // ---- per-launch-site timeline (b200r_profile_enable(2) / b200r_profile_dump) ----
 struct ProfRec { const char* name; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof_recs;
-static bool g_prof_all = false;
-ProfScope::ProfScope(cudaStream_t stream, const char* name) : st(stream), slot(-1) {
-  if (!g_prof_all) return;
-  ProfRec r; r.name = name;
-  if (cudaEventCreate(&r.a) != cudaSuccess) return;
-  if (cudaEventCreate(&r.b) != cudaSuccess) { cudaEventDestroy(r.a); return; }
-  cudaEventRecord(r.a, st);
-  g_prof_recs.push_back(r);
-  slot = (int)g_prof_recs.size() - 1;
+static std::atomic<bool> g_prof_all{false};
+ProfScope::ProfScope(cudaStream_t stream, const char* nm) : st(stream), name(nm), a(nullptr), b(nullptr), on(false) {
+  if (!g_prof_all.load(std::memory_order_relaxed)) return;
+  if (cudaEventCreate(&a) != cudaSuccess) return;
+  if (cudaEventCreate(&b) != cudaSuccess) { cudaEventDestroy(a); return; }
+  cudaEventRecord(a, st);
+  on = true;
 }
 ProfScope::~ProfScope() {
-  if (slot >= 0 && slot < (int)g_prof_recs.size()) cudaEventRecord(g_prof_recs[slot].b, st);
+  if (!on) return;
+  cudaEventRecord(b, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_recs.push_back({name, a, b});
 }
 
 // B200R_CTA_GROUP=1 forces the single-CTA tile kernel, B200R_Q_REPLICAS=0 disables the query-tile replication (A/B measurements)
@@ -782,8 +792,10 @@ int b200r_merge_topk_packed(int device, const void* packed, int32_t G, int32_t B
 
 int b200r_profile_dump(char* buf, size_t n) {
   // {"name": [total_ms, launches], ...} in first-seen order; clears the records
+  std::vector<ProfRec> recs;
+  { std::lock_guard<std::mutex> lk(g_prof_mu); recs.swap(g_prof_recs); }
   std::vector<const char*> names; std::vector<double> ms; std::vector<int> cnt;
-  for (const ProfRec& r : g_prof_recs) {
+  for (const ProfRec& r : recs) {
     float t = 0.f;
     if (cudaEventSynchronize(r.b) == cudaSuccess) cudaEventElapsedTime(&t, r.a, r.b);
     size_t i = 0;
@@ -792,7 +804,6 @@ int b200r_profile_dump(char* buf, size_t n) {
     ms[i] += t; cnt[i] += 1;
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }
-  g_prof_recs.clear();
   std::string out = "{";
   for (size_t i = 0; i < names.size(); ++i) {
     char tmp[160];
@@ -805,34 +816,39 @@ int b200r_profile_dump(char* buf, size_t n) {
 }
 
 int b200r_profile_enable(int on) {
-  g_prof_all = on == 2;
-  if (!g_prof_all) {
-    for (const ProfRec& r : g_prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
-    g_prof_recs.clear();
+  g_prof_all.store(on == 2);
+  g_prof_on.store(on == 1);
+  std::vector<ProfRec> recs;
+  std::vector<ProfPair> pairs;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (on != 2) recs.swap(g_prof_recs);
+    if (on != 1) pairs.swap(g_prof_events);
   }
-  g_prof_on = on == 1;
-  if (!g_prof_on) {
-    for (cudaEvent_t e : g_prof_events) cudaEventDestroy(e);
-    g_prof_events.clear();
-  }
+  for (const ProfRec& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (const ProfPair& e : pairs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   return B200R_OK;
 }
 
 int b200r_profile_read(double* kernel_ms, int64_t* launches) {
+  std::vector<ProfPair> pairs;
+  { std::lock_guard<std::mutex> lk(g_prof_mu); pairs.swap(g_prof_events); }
   double total = 0.0;
   int64_t n = 0;
-  for (size_t i = 0; i + 1 < g_prof_events.size(); i += 2) {
+  int rc = B200R_OK;
+  for (const ProfPair& e : pairs) {
     float ms = 0.f;
-    B200R_CUDA_CHECK(cudaEventSynchronize(g_prof_events[i + 1]));
-    B200R_CUDA_CHECK(cudaEventElapsedTime(&ms, g_prof_events[i], g_prof_events[i + 1]));
+    if (rc == B200R_OK && (cudaEventSynchronize(e.b) != cudaSuccess || cudaEventElapsedTime(&ms, e.a, e.b) != cudaSuccess)) {
+      set_error("profile_read: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = B200R_ECUDA;
+    }
     total += ms;
     ++n;
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
   }
-  for (cudaEvent_t e : g_prof_events) cudaEventDestroy(e);
-  g_prof_events.clear();
   if (kernel_ms) *kernel_ms = total;
   if (launches) *launches = n;
-  return B200R_OK;
+  return rc;
 }
 
 static int graph_create(int device, const int64_t* row_ptr, const int32_t* col_idx, int64_t V, int64_t E, const int64_t* node_rows,

@@ -171,7 +171,7 @@ void profile_begin(cudaStream_t st);
 void profile_end(cudaStream_t st);
 // b200r_profile_enable(2): every launch site is bracketed by CUDA events under its name (b200r_profile_dump)
 struct ProfScope {
-  cudaStream_t st; int slot;
+  cudaStream_t st; const char* name; cudaEvent_t a, b; bool on;
   ProfScope(cudaStream_t stream, const char* name);
   ~ProfScope();
 };

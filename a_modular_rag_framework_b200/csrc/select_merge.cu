@@ -327,12 +327,20 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
 }
 
 // ------------------------------------------------------------------------------------------------
-// threshold_warp_kernel: the per-phase select (threshold mode) with ONE WARP per query -- no block barriers, a third of
-// the instructions of the CTA-per-query kernel.  Used when a carry list exists and the per-query candidate count
-// (~k + one phase's survivors) fits the warp's stage; a query that does not fit is handled from global memory.
+// threshold_warp_kernel: the per-phase select (threshold mode) with ONE WARP per query -- no block barriers.
+// Used when a carry list exists and the per-query candidate count (~k + one phase's survivors) fits the warp's stage;
+// a query that does not fit is handled from global memory with the radix select.
+//
+// The threshold only has to be a VALID lower bound of the final k-th score that is as tight as the candidates allow, so
+// the staged path does not run an exact radix select: the candidates are gathered segment by segment (coalesced, four
+// segments in flight), binned ONCE into 1024 bins that are linear in the score between the smallest and the largest
+// candidate, the bin b* that holds the k-th best is found with one suffix scan, and the threshold is the smallest
+// candidate score whose bin is >= b* -- an actual candidate's score, so exactly suffix(b*) >= k candidates reach it.
+// About a third of the instructions of three 8-bit radix passes with warp-aggregated atomics.
 // ------------------------------------------------------------------------------------------------
-constexpr int TW_WARPS = 4;            // queries per CTA
+constexpr int TW_WARPS = 1;            // queries per CTA (the kernel is latency-bound: small CTAs pack the SMs to the smem limit)
 constexpr int TW_STAGE = 1536;         // keys staged per warp (12 KB)
+constexpr int TW_BINS = 1024;          // score bins, two 16-bit counters per word (a bin holds <= TW_STAGE keys)
 
 __device__ __forceinline__ int tw_find_segment(const int* seg_off, int nseg, int i) {
   int lo = 0, hi = nseg;                       // last segment with seg_off <= i
@@ -340,50 +348,23 @@ __device__ __forceinline__ int tw_find_segment(const int* seg_off, int nseg, int
   return lo;
 }
 
-__global__ void __launch_bounds__(TW_WARPS * 32) threshold_warp_kernel(const SelectParams p, const int seg_stride) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x * TW_WARPS + warp;
-  if (q >= p.B) return;                                               // whole warp
-  u64* stage = reinterpret_cast<u64*>(smem_raw) + (size_t)warp * TW_STAGE;
-  u32* hist = reinterpret_cast<u32*>(reinterpret_cast<u64*>(smem_raw) + (size_t)TW_WARPS * TW_STAGE) + warp * 256;
-  int* seg_off = reinterpret_cast<int*>(reinterpret_cast<u32*>(reinterpret_cast<u64*>(smem_raw) + (size_t)TW_WARPS * TW_STAGE) + TW_WARPS * 256) +
-                 (size_t)warp * seg_stride;
-  const int nreal = p.S, nseg = p.S + 1;                               // + the carry list (count at index S)
-  // ---- counts -> exclusive offsets ----
-  int run = 0;
-  for (int base = 0; base < nseg; base += 32) {
-    const int sgi = base + lane;
-    const int c = sgi < nseg ? p.counts[(size_t)sgi * p.Bpad + q] : 0;
-    int incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFullMask, incl, o); if (lane >= o) incl += t; }
-    if (sgi < nseg) seg_off[sgi] = run + incl - c;
-    run += __shfl_sync(kFullMask, incl, 31);
-  }
-  if (lane == 0) seg_off[nseg] = run;
-  __syncwarp();
-  const int total = run;
-  if (total < p.k) return;                                             // not enough candidates yet for a threshold
+__device__ __forceinline__ int tw_bin(u64 key, float flo, float scale) {
+  const int b = (int)((key_score(key) - flo) * scale);      // monotone in the score; flo is the smallest candidate score
+  return b < TW_BINS - 1 ? b : TW_BINS - 1;
+}
+
+// the radix path for a query whose candidates do not fit the stage: keys are re-read from global memory in every pass
+struct TwArgs { const u64* lists; int* counts; u64* carry; u32* gthr; int S, Bpad, cap, k, carry_cap; };
+__device__ __noinline__ void tw_select_unstaged(const TwArgs p, int q, const int* seg_off, u32* hist, int total) {
+  const int lane = threadIdx.x & 31;
+  const int nreal = p.S, nseg = p.S + 1;
   const u64* carry = p.carry + (size_t)q * p.carry_cap;
   auto load_key = [&](int i) -> u64 {
     const int sg = tw_find_segment(seg_off, nseg, i);
     const int j = i - seg_off[sg];
     return sg >= nreal ? carry[j] : p.lists[((size_t)sg * p.Bpad + q) * (size_t)p.cap + j];
   };
-  const bool staged = total <= TW_STAGE;
-  if (staged) {
-    // four independent loads in flight per lane
-    for (int base = 0; base < total; base += 128) {
-      u64 v[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) { const int i = base + r * 32 + lane; v[r] = i < total ? load_key(i) : 0ull; }
-#pragma unroll
-      for (int r = 0; r < 4; ++r) { const int i = base + r * 32 + lane; if (i < total) stage[i] = v[r]; }
-    }
-    __syncwarp();
-  }
-  // ---- radix select of the k-th key, top 24 bits (a truncated key is a valid, slightly low threshold) ----
+  // radix select of the k-th key, top 24 bits (a truncated key is a valid, slightly low threshold)
   u64 prefix = 0;
   int remaining = p.k;
 #pragma unroll 1
@@ -395,7 +376,7 @@ __global__ void __launch_bounds__(TW_WARPS * 32) threshold_warp_kernel(const Sel
     for (int base = 0; base < total; base += 32) {
       const int i = base + lane;
       const bool active = i < total;
-      const u64 key = active ? (staged ? stage[i] : load_key(i)) : 0ull;
+      const u64 key = active ? load_key(i) : 0ull;
       const bool m = active && (key & hi_mask) == prefix;
       hist_add(hist, m, (u32)(key >> shift) & 255u);
     }
@@ -425,25 +406,10 @@ __global__ void __launch_bounds__(TW_WARPS * 32) threshold_warp_kernel(const Sel
   }
   const u64 kth = prefix;
   if (lane == 0) atomicMax(p.gthr + q, (u32)(kth >> 32));
-  // ---- prune ----
-  int* wc = const_cast<int*>(p.counts);
-  if (staged) {
-    u64* cl = p.carry + (size_t)q * p.carry_cap;      // every read of the old carry is in the stage by now
-    int out = 0;
-    for (int base = 0; base < total; base += 32) {
-      const int i = base + lane;
-      const u64 key = i < total ? stage[i] : 0ull;
-      const bool keep = i < total && key >= kth;
-      const u32 m = __ballot_sync(kFullMask, keep);
-      if (keep) cl[out + __popc(m & ((1u << lane) - 1u))] = key;
-      out += __popc(m);
-    }
-    for (int sgi = lane; sgi < nreal; sgi += 32) wc[(size_t)sgi * p.Bpad + q] = 0;
-    if (lane == 0) wc[(size_t)p.S * p.Bpad + q] = out;
-    return;
-  }
+  // prune in place, segment by segment (the carry may not hold everything)
+  int* wc = p.counts;
   u64* wl = const_cast<u64*>(p.lists);
-  for (int sg = 0; sg < nseg; ++sg) {                 // in place, segment by segment (the carry may not hold everything)
+  for (int sg = 0; sg < nseg; ++sg) {
     const size_t slot = (size_t)sg * p.Bpad + q;
     const int c = seg_off[sg + 1] - seg_off[sg];
     if (c == 0) continue;
@@ -462,10 +428,127 @@ __global__ void __launch_bounds__(TW_WARPS * 32) threshold_warp_kernel(const Sel
   }
 }
 
+__global__ void __launch_bounds__(TW_WARPS * 32) threshold_warp_kernel(const SelectParams p, const int seg_stride) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * TW_WARPS + warp;
+  if (q >= p.B) return;                                               // whole warp
+  u64* stage = reinterpret_cast<u64*>(smem_raw) + (size_t)warp * TW_STAGE;
+  u32* hist = reinterpret_cast<u32*>(reinterpret_cast<u64*>(smem_raw) + (size_t)TW_WARPS * TW_STAGE) + warp * (TW_BINS / 2);
+  int* seg_off = reinterpret_cast<int*>(reinterpret_cast<u32*>(reinterpret_cast<u64*>(smem_raw) + (size_t)TW_WARPS * TW_STAGE) + TW_WARPS * (TW_BINS / 2)) +
+                 (size_t)warp * seg_stride;
+  const int nreal = p.S, nseg = p.S + 1;                               // + the carry list (count at index S)
+  // ---- counts -> exclusive offsets ----
+  int run = 0;
+  for (int base = 0; base < nseg; base += 32) {
+    const int sgi = base + lane;
+    const int c = sgi < nseg ? p.counts[(size_t)sgi * p.Bpad + q] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFullMask, incl, o); if (lane >= o) incl += t; }
+    if (sgi < nseg) seg_off[sgi] = run + incl - c;
+    run += __shfl_sync(kFullMask, incl, 31);
+  }
+  if (lane == 0) seg_off[nseg] = run;
+  __syncwarp();
+  const int total = run;
+  if (total < p.k) return;                                             // not enough candidates yet for a threshold
+  if (total > TW_STAGE) {
+    const TwArgs a = {p.lists, const_cast<int*>(p.counts), p.carry, p.gthr, p.S, p.Bpad, p.cap, p.k, p.carry_cap};
+    tw_select_unstaged(a, q, seg_off, hist, total);
+    return;
+  }
+
+  // ---- gather: segment by segment, four segments' loads in flight; track the score range ----
+  u64* carry = p.carry + (size_t)q * p.carry_cap;
+  u32 lo32 = 0xffffffffu, hi32 = 0u;
+  for (int sg0 = 0; sg0 < nseg; sg0 += 4) {
+    u64 v[4]; int o[4], c[4]; const u64* lp[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int sg = sg0 + r;
+      o[r] = sg < nseg ? seg_off[sg] : 0;
+      c[r] = sg < nseg ? seg_off[sg + 1] - o[r] : 0;
+      lp[r] = sg >= nreal ? carry : p.lists + ((size_t)sg * p.Bpad + q) * (size_t)p.cap;
+      v[r] = lane < c[r] ? lp[r][lane] : 0ull;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (lane < c[r]) { stage[o[r] + lane] = v[r]; lo32 = min(lo32, (u32)(v[r] >> 32)); hi32 = max(hi32, (u32)(v[r] >> 32)); }
+      for (int i = lane + 32; i < c[r]; i += 32) {
+        const u64 key = lp[r][i];
+        stage[o[r] + i] = key;
+        lo32 = min(lo32, (u32)(key >> 32)); hi32 = max(hi32, (u32)(key >> 32));
+      }
+    }
+  }
+  lo32 = __reduce_min_sync(kFullMask, lo32);
+  hi32 = __reduce_max_sync(kFullMask, hi32);
+  for (int i = lane; i < TW_BINS / 2; i += 32) hist[i] = 0;
+  __syncwarp();
+
+  // ---- one histogram over bins linear in the score, then the bin of the k-th best ----
+  const float flo = ordered_to_f32(lo32), fhi = ordered_to_f32(hi32);
+  const float range = fhi - flo;
+  const float scale = (range > 0.0f && range < CUDART_INF_F) ? (float)(TW_BINS - 1) / range : 0.0f;    // 0: every key in bin 0
+  for (int i = lane; i < total; i += 32) {
+    const int b = tw_bin(stage[i], flo, scale);
+    atomicAdd(&hist[b >> 1], 1u << ((b & 1) * 16));
+  }
+  __syncwarp();
+  // lane L owns bins [32 L, 32 L + 32) = 16 words
+  u32 w[16]; u32 lane_sum = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 t = reinterpret_cast<const uint4*>(hist + lane * 16)[j];
+    w[4 * j] = t.x; w[4 * j + 1] = t.y; w[4 * j + 2] = t.z; w[4 * j + 3] = t.w;
+    lane_sum += (t.x & 0xffffu) + (t.x >> 16) + (t.y & 0xffffu) + (t.y >> 16) + (t.z & 0xffffu) + (t.z >> 16) + (t.w & 0xffffu) + (t.w >> 16);
+  }
+  u32 suffix = lane_sum;                                             // keys in this lane's bins and all higher ones
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_down_sync(kFullMask, suffix, o); if (lane + o < 32) suffix += t; }
+  const u32 above = suffix - lane_sum;
+  const bool mine = above < (u32)p.k && (u32)p.k <= suffix;          // exactly one lane (total >= k)
+  int bstar = 0;
+  if (mine) {
+    u32 acc = above;
+#pragma unroll
+    for (int j = 15; j >= 0; --j) {
+      acc += w[j] >> 16;
+      if (acc >= (u32)p.k) { bstar = lane * 32 + 2 * j + 1; break; }
+      acc += w[j] & 0xffffu;
+      if (acc >= (u32)p.k) { bstar = lane * 32 + 2 * j; break; }
+    }
+  }
+  bstar = __shfl_sync(kFullMask, bstar, __ffs(__ballot_sync(kFullMask, mine)) - 1);
+  // ---- threshold = the smallest candidate score in bins >= b*: at least k candidates reach it ----
+  u32 t32 = 0xffffffffu;
+  for (int i = lane; i < total; i += 32) {
+    const u64 key = stage[i];
+    if (tw_bin(key, flo, scale) >= bstar) t32 = min(t32, (u32)(key >> 32));
+  }
+  t32 = __reduce_min_sync(kFullMask, t32);
+  const u64 kth = (u64)t32 << 32;
+  if (lane == 0) atomicMax(p.gthr + q, t32);
+  // ---- prune: survivors -> the carry list (every read of the old carry is in the stage by now); unit lists restart empty ----
+  int* wc = const_cast<int*>(p.counts);
+  int out = 0;
+  for (int base = 0; base < total; base += 32) {
+    const int i = base + lane;
+    const u64 key = i < total ? stage[i] : 0ull;
+    const bool keep = i < total && key >= kth;
+    const u32 m = __ballot_sync(kFullMask, keep);
+    if (keep) carry[out + __popc(m & ((1u << lane) - 1u))] = key;
+    out += __popc(m);
+  }
+  for (int sgi = lane; sgi < nreal; sgi += 32) wc[(size_t)sgi * p.Bpad + q] = 0;
+  if (lane == 0) wc[(size_t)p.S * p.Bpad + q] = out;
+}
+
 static int run_threshold_warp(const SelectParams& p, cudaStream_t st) {
   ProfScope _ps(st, "select_threshold_warp");
   const int seg_stride = (p.S + 2 + 3) & ~3;
-  const size_t smem = (size_t)TW_WARPS * TW_STAGE * 8 + (size_t)TW_WARPS * 256 * 4 + (size_t)TW_WARPS * seg_stride * 4;
+  const size_t smem = (size_t)TW_WARPS * TW_STAGE * 8 + (size_t)TW_WARPS * (TW_BINS / 2) * 4 + (size_t)TW_WARPS * seg_stride * 4;
   B200R_CUDA_CHECK(cudaFuncSetAttribute(threshold_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   threshold_warp_kernel<<<(p.B + TW_WARPS - 1) / TW_WARPS, TW_WARPS * 32, smem, st>>>(p, seg_stride);
   count_launch();

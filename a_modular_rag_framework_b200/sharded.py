@@ -1,13 +1,15 @@
-"""Row-sharded exact search across the GPUs of one box: one process per GPU (torch.distributed).
+"""Row-sharded exact search across the GPUs of one box: one process per GPU.
 
 Rows of the corpus are independent, and the top-k of a union is the top-k of the per-shard top-k's
 (SURVEY.md section 8e), so the path has ONE exchange step: every rank searches its contiguous row
-block, the packed (ids, scores)[B, k] results are all-gathered (NCCL over NVLink on the GPU box,
-gloo in the CPU tests) and every rank runs the same on-device merge (b200r_merge_topk_packed), ties
-resolved by (score desc, GLOBAL id asc) exactly like the single-GPU path.
+block, every rank's packed (ids, scores)[B, k] record reaches every rank, and every rank runs the same
+on-device merge, ties resolved by (score desc, GLOBAL id asc) exactly like the single-GPU path.
 
-The local search engine and the merge are injectable so the sharding / exchange logic can be tested
-on CPU ranks; the defaults are the CUDA kernels and raise without them (no CPU fallback).
+On the GPU box the exchange is the library's own (exchange="abi": b200r_comm_*, peer stores over NVLink from
+inside the final select kernel, device-side epoch flags; torch.distributed only swaps the 128-byte window
+descriptors at bring-up).  exchange="nccl" keeps the packed all-gather + b200r_merge_topk_packed; it is also
+what the gloo CPU tests drive, with an injected local engine and merge.  There is no CPU fallback: the
+defaults are the CUDA kernels and raise without them.
 """
 from __future__ import annotations
 
