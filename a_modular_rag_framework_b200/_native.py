@@ -22,10 +22,10 @@ COMM_BLOB_BYTES = 128
 EXPORTS = [
     "b200r_version", "b200r_last_error", "b200r_launch_count",
     "b200r_index_create", "b200r_index_destroy", "b200r_index_info",
-    "b200r_search_workspace_bytes", "b200r_search", "b200r_search_host", "b200r_search_min_score",
+    "b200r_search_workspace_bytes", "b200r_search", "b200r_search_host", "b200r_search_host_f32", "b200r_convert_f32", "b200r_search_min_score",
     "b200r_range_workspace_bytes", "b200r_range_count", "b200r_range_fill",
     "b200r_comm_create", "b200r_comm_export", "b200r_comm_connect", "b200r_comm_init_all", "b200r_comm_destroy", "b200r_comm_status", "b200r_comm_info",
-    "b200r_search_sharded_begin", "b200r_search_sharded_finish", "b200r_search_sharded", "b200r_search_sharded_host_all",
+    "b200r_search_sharded_begin", "b200r_search_sharded_finish", "b200r_search_sharded", "b200r_search_sharded_host_all", "b200r_search_sharded_host_all_f32",
     "b200r_merge_topk", "b200r_merge_topk_packed", "b200r_mmr_diversify", "b200r_profile_enable", "b200r_profile_read", "b200r_profile_dump",
     "b200r_graph_create", "b200r_graph_create_mapped", "b200r_graph_destroy",
     "b200r_merge_topk_src", "b200r_expand_max_candidates", "b200r_expand_rescore", "b200r_expand_workspace_bytes", "b200r_expand_rescore_sharded", "b200r_expand_rescore_exchange",
@@ -74,6 +74,8 @@ def load() -> ctypes.CDLL:
     lib.b200r_search_workspace_bytes.restype = c_size_t
     lib.b200r_search.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.b200r_search_host.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.b200r_search_host_f32.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.b200r_convert_f32.argtypes = [c_int, c_void_p, c_void_p, c_int64, c_int32, c_void_p]
     lib.b200r_search_min_score.argtypes = [c_uint64, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.b200r_range_workspace_bytes.argtypes = [c_uint64, c_int32]
     lib.b200r_range_workspace_bytes.restype = c_size_t
@@ -91,6 +93,7 @@ def load() -> ctypes.CDLL:
     lib.b200r_search_sharded.argtypes = [c_uint64, c_uint64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.b200r_search_sharded_host_all.argtypes = [POINTER(c_uint64), POINTER(c_uint64), c_int32, c_void_p, c_int32, c_int32, c_int32,
                                                   c_void_p, c_void_p, POINTER(c_void_p)]
+    lib.b200r_search_sharded_host_all_f32.argtypes = lib.b200r_search_sharded_host_all.argtypes
     lib.b200r_mmr_diversify.argtypes = [c_uint64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.b200r_merge_topk.argtypes = [c_int, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
     lib.b200r_merge_topk_packed.argtypes = [c_int, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]

@@ -145,7 +145,8 @@ class CudaEngine:
             self.comms = ShardComm.init_all([d.index for d in self.devs], self.max_batch, self.max_k, self.max_k)
         self._graph_cls = PassageGraph
         self.corpus_graphs = None       # one replica per device of the corpus-level CSR (graph_path)
-        self._qpin = None               # pinned staging of the converted queries
+        self._qpin = None               # pinned fp32 staging of the queries
+        self._opin = None               # pinned staging of the results
 
     # -- helpers ------------------------------------------------------------------------------------------
     def _upload_graph(self, row_ptr, col_idx, node_rows):
@@ -158,14 +159,23 @@ class CudaEngine:
         return out
 
     def _q_host(self, Q: np.ndarray):
-        """f32 host queries -> the index's query dtype in PINNED memory (the H2D copies to the devices run asynchronously)."""
+        """f32 host queries -> PINNED fp32 staging (the H2D copies to the devices run asynchronously; the library rounds
+        them to the index's query dtype on the device -- no 2-byte conversion on the host)."""
         q = self.torch.from_numpy(np.ascontiguousarray(Q, dtype=np.float32))
         n = q.numel()
-        if self._qpin is None or self._qpin.numel() < n or self._qpin.dtype != self.query_dtype:
-            self._qpin = self.torch.empty(max(n, 1), dtype=self.query_dtype).pin_memory()
+        if self._qpin is None or self._qpin.numel() < n:
+            self._qpin = self.torch.empty(max(n, 1), dtype=self.torch.float32).pin_memory()
         out = self._qpin[:n].view(q.shape)
         out.copy_(q)
         return out
+
+    def _out_host(self, B: int, k: int):
+        """Pinned result staging [B, k] (scores f32, ids i64): the D2H copies land here, then one memcpy into the caller's arrays."""
+        n = B * k
+        if self._opin is None or self._opin[0].numel() < n:
+            self._opin = (self.torch.empty(max(n, 1), dtype=self.torch.float32).pin_memory(),
+                          self.torch.empty(max(n, 1), dtype=self.torch.int64).pin_memory())
+        return self._opin[0][:n].view(B, k), self._opin[1][:n].view(B, k)
 
     def has_graph(self) -> bool:
         return self.corpus_graphs is not None
@@ -180,19 +190,19 @@ class CudaEngine:
         ids = np.empty((B, k), dtype=np.int64)
         if len(self.devs) > 1 and k > self.max_k:
             raise ValueError(f"k={k} exceeds the exchange window (max_k={self.max_k}); construct the engine with a larger max_k")
-        t = self.torch
         for b0 in range(0, B, self.max_batch):
             b1 = min(B, b0 + self.max_batch)
             qh = self._q_host(Q[b0:b1])
-            hs, hi = t.from_numpy(scores[b0:b1]), t.from_numpy(ids[b0:b1])
+            hs, hi = self._out_host(b1 - b0, k)
             if len(self.devs) == 1:
                 self.shards[0].search_host(qh, k, out=(hs, hi))
             else:
                 G = len(self.devs)
                 ih = (ctypes.c_uint64 * G)(*[s.handle for s in self.shards])
                 ch = (ctypes.c_uint64 * G)(*[c.handle for c in self.comms])
-                N.check(N.load().b200r_search_sharded_host_all(ih, ch, G, qh.data_ptr(), b1 - b0, k, N.PATH_AUTO,
-                                                               hs.data_ptr(), hi.data_ptr(), None))
+                N.check(N.load().b200r_search_sharded_host_all_f32(ih, ch, G, qh.data_ptr(), b1 - b0, k, N.PATH_AUTO,
+                                                                   hs.data_ptr(), hi.data_ptr(), None))
+            scores[b0:b1], ids[b0:b1] = hs.numpy(), hi.numpy()
         return scores, ids
 
     # -- MMR post-filter ---------------------------------------------------------------------------------------
@@ -223,7 +233,8 @@ class CudaEngine:
             qh = self._q_host(Q[b0:b1])
             sh = t.from_numpy(np.ascontiguousarray(seeds[b0:b1], dtype=np.int64))
             if len(self.devs) == 1:
-                res = expand_rescore(self.shards[0], graphs[0], qh.to(self.device), sh.to(self.device), window,
+                qd = self.shards[0].to_query_dtype(qh.to(self.device, non_blocking=True))
+                res = expand_rescore(self.shards[0], graphs[0], qd, sh.to(self.device), window,
                                      alpha_dense, alpha_graph, k, check_status=False, unbounded=True)
             else:
                 res = expand_rescore_exchange_all(self.shards, graphs, self.comms, self.N, qh, sh, window, alpha_dense, alpha_graph, k)

@@ -170,9 +170,9 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
     pl->Bpad = (pl->rows_i8 ? pl->rows_i8 : pl->num_q_tiles) * BMq;
     // units = (query tile, chunk of row tiles).  More units per CTA = better balance, fewer = less list
     // traffic; pick the chunk count (near a target) that wastes the fewest CTA slots in the last wave.
-    // int8: the query groups of a slice share one launch, num_sms / groups CTAs each (rows_i8.cu), so the chunks are
-    // sized for that many CTAs per group
-    const int grid_max = (pl->rows_i8 && !pl->rows_f32) ? rows_i8_ctas_per_group(pl->rows_i8) : num_sms() / pl->cta_group;
+    // int8 / fp32: the query groups of a slice share one launch, num_sms / groups CTAs each (rows_i8.cu, rows_f32.cu), so the
+    // chunks are sized for that many CTAs per group
+    const int grid_max = pl->rows_i8 ? rows_i8_ctas_per_group(pl->rows_i8) : num_sms() / pl->cta_group;
     const int m = pl->num_q_tiles >= 16 ? 8 : (pl->num_q_tiles >= 4 ? 4 : (pl->num_q_tiles >= 2 ? 2 : 1));
     long long target = ((long long)grid_max * m + pl->num_q_tiles - 1) / pl->num_q_tiles;
     if (target < 1) target = 1;
@@ -303,22 +303,26 @@ static int do_search_one(Index* ix, const void* Q, int B, int k, int path, float
     set_error("workspace too small: need %zu bytes, got %zu", pl.off_end, ws_bytes);
     return B200R_ENOMEM;
   }
-  if ((rc = launch_init_search(pl, ws, st))) return rc;
-  if (ix->metric == B200R_COS) {
-    float* qinv = reinterpret_cast<float*>((char*)ws + pl.off_qinv);
-    if ((rc = launch_query_inv_norm(Q, B, ix->D, query_dtype(ix), qinv, st))) return rc;
+  const bool k1 = pl.path == B200R_PATH_GEMM && !pl.rows_i8;      // bf16 / fp16 tile kernel: one fused prologue launch
+  if (k1) {
+    if ((rc = launch_search_prologue(pl, ws, Q, ix->D, query_dtype(ix), ix->metric == B200R_COS, st))) return rc;
+  } else {
+    if ((rc = launch_init_search(pl, ws, st))) return rc;
+    if (ix->metric == B200R_COS) {
+      float* qinv = reinterpret_cast<float*>((char*)ws + pl.off_qinv);
+      if ((rc = launch_query_inv_norm(Q, B, ix->D, query_dtype(ix), qinv, st))) return rc;
+    }
   }
   const bool floor_on = min_score > -HUGE_VALF;
   if (floor_on && (rc = launch_min_score(pl, ws, ix->metric == B200R_COS, min_score, st))) return rc;
   if (pl.path == B200R_PATH_GEMM && pl.rows_i8 && pl.rows_f32) {
     void* qws = (char*)ws + pl.off_qrep;
     if ((rc = launch_split_queries_tf32(Q, B, ix->D, qws, st))) return rc;
-    std::vector<CUtensorMap> tmaps(pl.rows_i8);
-    for (int g = 0; g < pl.rows_i8; ++g)
-      if ((rc = encode_query_tmap_f32(qws, g, ix->D, &tmaps[g]))) return rc;
+    CUtensorMap tmap_q;
+    if ((rc = encode_query_tmap_f32(qws, pl.rows_i8, ix->D, &tmap_q))) return rc;
     for (int i = 0; i < pl.num_phases; ++i) {
       profile_begin(st);
-      for (int g = 0; g < pl.rows_i8 && !rc; ++g) rc = launch_rows_f32(ix, &tmaps[g], g, pl, pl.phases[i], ws, st);
+      rc = launch_rows_f32(ix, &tmap_q, pl, pl.phases[i], ws, st);
       profile_end(st);
       if (rc) return rc;
       if (i + 1 < pl.num_phases && (rc = launch_select_lists(ix, pl, ws, nullptr, nullptr, st))) return rc;
@@ -337,13 +341,8 @@ static int do_search_one(Index* ix, const void* Q, int B, int k, int path, float
     }
   } else if (pl.path == B200R_PATH_GEMM) {
     CUtensorMap tmap_q;
-    if (pl.q_replicas) {
-      void* rep = (char*)ws + pl.off_qrep;
-      if ((rc = launch_replicate_queries(Q, rep, B, ix->D, st))) return rc;
-      rc = encode_query_tmap_replicated(ix, rep, &tmap_q);
-    } else {
-      rc = encode_query_tmap(ix, Q, B, &tmap_q);
-    }
+    if (pl.q_replicas) rc = encode_query_tmap_replicated(ix, (char*)ws + pl.off_qrep, &tmap_q);   // written by the prologue
+    else rc = encode_query_tmap(ix, Q, B, &tmap_q);
     if (rc) return rc;
     for (int i = 0; i < pl.num_phases; ++i) {
       profile_begin(st);
@@ -416,9 +415,15 @@ static int do_search(Index* ix, const void* Q, int B, int k, int path, float* ou
 }
 
 // (re)size the library-owned device staging of the *_host calls; the stream is drained before a buffer is replaced
-static int ensure_staging(Index* ix, size_t qbytes, size_t oelems, size_t wsbytes, cudaStream_t st) {
-  if (ix->q_dev_bytes >= qbytes && ix->out_dev_elems >= oelems && ix->ws_bytes >= wsbytes) return B200R_OK;
+static int ensure_staging(Index* ix, size_t qbytes, size_t oelems, size_t wsbytes, cudaStream_t st, size_t q32bytes = 0) {
+  if (ix->q_dev_bytes >= qbytes && ix->out_dev_elems >= oelems && ix->ws_bytes >= wsbytes && ix->q32_dev_bytes >= q32bytes) return B200R_OK;
   B200R_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (ix->q32_dev_bytes < q32bytes) {
+    if (ix->h_q32_dev) cudaFree(ix->h_q32_dev);
+    ix->h_q32_dev = nullptr; ix->q32_dev_bytes = 0;
+    B200R_CUDA_CHECK(cudaMalloc(&ix->h_q32_dev, q32bytes));
+    ix->q32_dev_bytes = q32bytes;
+  }
   if (ix->q_dev_bytes < qbytes) {
     if (ix->h_q_dev) cudaFree(ix->h_q_dev);
     ix->h_q_dev = nullptr; ix->q_dev_bytes = 0;
@@ -440,6 +445,22 @@ static int ensure_staging(Index* ix, size_t qbytes, size_t oelems, size_t wsbyte
     ix->ws_bytes = wsbytes;
   }
   return B200R_OK;
+}
+
+// Host queries -> ix->h_q_dev on `st`.  from_f32: the host rows are fp32 whatever the index's query dtype; a 2-byte query
+// dtype is produced on the device (RNE), so the host never converts.  The staging must have been sized by ensure_staging.
+static int stage_queries(Index* ix, const void* Q_host, int B, bool from_f32, cudaStream_t st) {
+  const size_t n = (size_t)B * ix->D;
+  const int qd = query_dtype(ix);
+  if (!from_f32 || qd == B200R_F32) {
+    B200R_CUDA_CHECK(cudaMemcpyAsync(ix->h_q_dev, Q_host, n * elem_size(qd), cudaMemcpyHostToDevice, st));
+    return B200R_OK;
+  }
+  B200R_CUDA_CHECK(cudaMemcpyAsync(ix->h_q32_dev, Q_host, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  return launch_convert_queries(reinterpret_cast<const float*>(ix->h_q32_dev), ix->h_q_dev, n, qd, st);
+}
+static size_t q32_staging_bytes(const Index* ix, int B, bool from_f32) {
+  return (from_f32 && query_dtype(ix) != B200R_F32) ? (size_t)B * ix->D * sizeof(float) : 0;
 }
 
 }  // namespace b200r
@@ -517,6 +538,7 @@ int b200r_index_destroy(uint64_t index) {
   cudaSetDevice(ix->device);
   if (ix->row_mult) cudaFree(ix->row_mult);
   if (ix->h_q_dev) cudaFree(ix->h_q_dev);
+  if (ix->h_q32_dev) cudaFree(ix->h_q32_dev);
   if (ix->h_s_dev) cudaFree(ix->h_s_dev);
   if (ix->h_i_dev) cudaFree(ix->h_i_dev);
   if (ix->h_ws) cudaFree(ix->h_ws);
@@ -562,8 +584,14 @@ int b200r_search_min_score(uint64_t index, const void* Q, int32_t B, int32_t k, 
                    nullptr, min_score);
 }
 
-int b200r_search_host(uint64_t index, const void* Q_host, int32_t B, int32_t k, int32_t path, float* out_scores_host,
-                      int64_t* out_ids_host, void* stream) {
+int b200r_convert_f32(int device, const float* src, void* dst, int64_t n, int32_t dtype, void* stream) {
+  if (!src || !dst || n < 0) { set_error("null pointer / negative n"); return B200R_EINVAL; }
+  B200R_CUDA_CHECK(cudaSetDevice(device));
+  return launch_convert_queries(src, dst, (size_t)n, dtype, reinterpret_cast<cudaStream_t>(stream));
+}
+
+static int search_host_impl(uint64_t index, const void* Q_host, bool from_f32, int32_t B, int32_t k, int32_t path, float* out_scores_host,
+                            int64_t* out_ids_host, void* stream) {
   Index* ix = get_index(index);
   if (!ix) return B200R_ESTATE;
   if (!Q_host || !out_scores_host || !out_ids_host) { set_error("null host pointer"); return B200R_EINVAL; }
@@ -574,15 +602,25 @@ int b200r_search_host(uint64_t index, const void* Q_host, int32_t B, int32_t k, 
   if (!need) return B200R_EINVAL;
   const size_t qbytes = (size_t)B * ix->D * elem_size(query_dtype(ix));
   const size_t oelems = (size_t)B * k;
-  int rc = ensure_staging(ix, qbytes, oelems, need, st);
+  int rc = ensure_staging(ix, qbytes, oelems, need, st, q32_staging_bytes(ix, B, from_f32));
   if (rc) return rc;
-  B200R_CUDA_CHECK(cudaMemcpyAsync(ix->h_q_dev, Q_host, qbytes, cudaMemcpyHostToDevice, st));
+  if ((rc = stage_queries(ix, Q_host, B, from_f32, st))) return rc;
   rc = do_search(ix, ix->h_q_dev, B, k, path, ix->h_s_dev, ix->h_i_dev, ix->h_ws, ix->ws_bytes, st);
   if (rc) return rc;
   B200R_CUDA_CHECK(cudaMemcpyAsync(out_scores_host, ix->h_s_dev, oelems * sizeof(float), cudaMemcpyDeviceToHost, st));
   B200R_CUDA_CHECK(cudaMemcpyAsync(out_ids_host, ix->h_i_dev, oelems * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   B200R_CUDA_CHECK(cudaStreamSynchronize(st));
   return B200R_OK;
+}
+
+int b200r_search_host(uint64_t index, const void* Q_host, int32_t B, int32_t k, int32_t path, float* out_scores_host,
+                      int64_t* out_ids_host, void* stream) {
+  return search_host_impl(index, Q_host, false, B, k, path, out_scores_host, out_ids_host, stream);
+}
+
+int b200r_search_host_f32(uint64_t index, const float* Q_host_f32, int32_t B, int32_t k, int32_t path, float* out_scores_host,
+                          int64_t* out_ids_host, void* stream) {
+  return search_host_impl(index, Q_host_f32, true, B, k, path, out_scores_host, out_ids_host, stream);
 }
 
 // ---- range search: every row with score >= min_score (gemm_topk.cu range mode) ----------------------------------------
@@ -659,8 +697,9 @@ int b200r_search_sharded(uint64_t index, uint64_t comm, const void* Q, int32_t B
 // One host thread driving G GPUs (the plug-in's single-process mode): host queries in, host results out.  Every device
 // gets the queries, searches its row shard and scatters its record (begin on ALL devices before any finish, so no
 // device's merge kernel waits for a kernel that has not been launched yet); the merged result is read from device 0.
-int b200r_search_sharded_host_all(const uint64_t* indexes, const uint64_t* comms, int32_t G, const void* Q_host, int32_t B, int32_t k,
-                                  int32_t path, float* out_scores_host, int64_t* out_ids_host, void* const* streams) {
+static int search_sharded_host_all_impl(const uint64_t* indexes, const uint64_t* comms, int32_t G, const void* Q_host, bool from_f32,
+                                        int32_t B, int32_t k, int32_t path, float* out_scores_host, int64_t* out_ids_host,
+                                        void* const* streams) {
   if (!indexes || !comms || G < 1 || G > B200R_MAX_PEERS) { set_error("bad indexes / comms / G"); return B200R_EINVAL; }
   if (!Q_host || !out_scores_host || !out_ids_host) { set_error("null host pointer"); return B200R_EINVAL; }
   if (B <= 0 || k <= 0 || k > B200R_MAX_K) { set_error("bad B / k (%d / %d)", B, k); return B200R_EINVAL; }
@@ -678,8 +717,8 @@ int b200r_search_sharded_host_all(const uint64_t* indexes, const uint64_t* comms
     const size_t need = search_workspace(ix[g], B, k, path, nullptr);
     if (!need) return B200R_EINVAL;
     const size_t qbytes = (size_t)B * ix[g]->D * elem_size(query_dtype(ix[g]));
-    if ((rc = ensure_staging(ix[g], qbytes, g == 0 ? oelems : 1, need, st[g]))) return rc;
-    B200R_CUDA_CHECK(cudaMemcpyAsync(ix[g]->h_q_dev, Q_host, qbytes, cudaMemcpyHostToDevice, st[g]));
+    if ((rc = ensure_staging(ix[g], qbytes, g == 0 ? oelems : 1, need, st[g], q32_staging_bytes(ix[g], B, from_f32)))) return rc;
+    if ((rc = stage_queries(ix[g], Q_host, B, from_f32, st[g]))) return rc;
     if ((rc = do_search(ix[g], ix[g]->h_q_dev, B, k, path, nullptr, nullptr, ix[g]->h_ws, ix[g]->ws_bytes, st[g], cm[g]))) return rc;
   }
   // only rank 0's merged copy is needed on the host; the other ranks still consume the exchange (epochs advance together)
@@ -697,6 +736,16 @@ int b200r_search_sharded_host_all(const uint64_t* indexes, const uint64_t* comms
     B200R_CUDA_CHECK(cudaStreamSynchronize(st[g]));
   }
   return B200R_OK;
+}
+
+int b200r_search_sharded_host_all(const uint64_t* indexes, const uint64_t* comms, int32_t G, const void* Q_host, int32_t B, int32_t k,
+                                  int32_t path, float* out_scores_host, int64_t* out_ids_host, void* const* streams) {
+  return search_sharded_host_all_impl(indexes, comms, G, Q_host, false, B, k, path, out_scores_host, out_ids_host, streams);
+}
+
+int b200r_search_sharded_host_all_f32(const uint64_t* indexes, const uint64_t* comms, int32_t G, const float* Q_host_f32, int32_t B,
+                                      int32_t k, int32_t path, float* out_scores_host, int64_t* out_ids_host, void* const* streams) {
+  return search_sharded_host_all_impl(indexes, comms, G, Q_host_f32, true, B, k, path, out_scores_host, out_ids_host, streams);
 }
 
 size_t b200r_range_workspace_bytes(uint64_t index, int32_t B) {

@@ -25,6 +25,7 @@
 #include "tc_ptx.cuh"
 #include <math_constants.h>
 #include <cstring>
+#include <type_traits>
 #include <cstdlib>
 
 namespace b200r {
@@ -386,6 +387,84 @@ __global__ void replicate_queries_kernel(const T* __restrict__ Q, T* __restrict_
 }
 
 size_t query_replica_bytes(int D) { return (size_t)kQReplicas * BM * D * 2; }
+
+// Everything a K1 search needs before its first tile kernel, in ONE launch (three launches cost ~20 us of a 0.4 ms batch-1
+// search on a 1.25 M-row shard): thresholds to -inf and list counts to zero, 1/|q| per query (cosine), and -- one query
+// tile only -- the 16 replicas of the zero-padded query tile, written as 16-byte chunks.
+template <typename QT>
+__global__ void __launch_bounds__(256) search_prologue_kernel(u32* __restrict__ gthr, int n_gthr, int* __restrict__ counts, long long n_counts,
+                                                              const QT* __restrict__ Q, int B, int D, float* __restrict__ qinv,
+                                                              uint4* __restrict__ rep) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  for (long long j = tid; j < n_gthr; j += nthreads) gthr[j] = kOrderedNegInf;
+  for (long long j = tid; j < n_counts; j += nthreads) counts[j] = 0;
+  if (qinv) {                                      // one warp per query, same arithmetic as query_inv_norm_kernel
+    const int lane = threadIdx.x & 31;
+    for (long long b = tid >> 5; b < B; b += nthreads >> 5) {
+      double acc = 0.0;
+      for (int d = lane; d < D; d += 32) {
+        const double v = (double)q_to_float<QT>(Q[(size_t)b * D + d]);
+        acc += v * v;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
+      if (lane == 0) qinv[b] = acc > 0.0 ? (float)(1.0 / sqrt(acc)) : 0.0f;
+    }
+  }
+  if (rep) {                                       // D % 8 == 0 and Q 16-byte aligned on this path
+    const int cpr = D / 8;                         // 16-byte chunks per row
+    const long long per = (long long)BM * cpr;
+    const uint4* Qv = reinterpret_cast<const uint4*>(Q);
+    for (long long j = tid; j < per; j += nthreads) {
+      const int row = (int)(j / cpr);
+      const uint4 v = row < B ? Qv[j] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int r = 0; r < kQReplicas; ++r) rep[(long long)r * per + j] = v;
+    }
+  }
+}
+
+int launch_search_prologue(const SearchPlan& pl, void* ws, const void* Q, int D, int qdtype, bool cosine, cudaStream_t st) {
+  ProfScope _ps(st, "search_prologue");
+  u32* gthr = reinterpret_cast<u32*>((char*)ws + pl.off_gthr);
+  int* counts = reinterpret_cast<int*>((char*)ws + pl.off_counts);
+  const long long n_counts = (long long)(pl.num_segments + 1) * pl.Bpad;   // + the carry lists' counts
+  float* qinv = cosine ? reinterpret_cast<float*>((char*)ws + pl.off_qinv) : nullptr;
+  uint4* rep = pl.q_replicas ? reinterpret_cast<uint4*>((char*)ws + pl.off_qrep) : nullptr;
+  const int grid = num_sms() * 2;
+  if (qdtype == B200R_BF16)
+    search_prologue_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(gthr, pl.Bpad, counts, n_counts, reinterpret_cast<const __nv_bfloat16*>(Q), pl.B, D, qinv, rep);
+  else if (qdtype == B200R_F16)
+    search_prologue_kernel<__half><<<grid, 256, 0, st>>>(gthr, pl.Bpad, counts, n_counts, reinterpret_cast<const __half*>(Q), pl.B, D, qinv, rep);
+  else { set_error("search_prologue: query dtype %d", qdtype); return B200R_EINVAL; }
+  count_launch();
+  B200R_CUDA_CHECK(cudaGetLastError());
+  return B200R_OK;
+}
+
+// f32 host queries -> the index's 2-byte query dtype, round to nearest even (b200r_search_host_f32)
+template <typename T>
+__global__ void convert_queries_kernel(const float* __restrict__ src, T* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if constexpr (sizeof(T) == sizeof(__nv_bfloat16) && std::is_same<T, __nv_bfloat16>::value) dst[i] = __float2bfloat16_rn(src[i]);
+    else dst[i] = __float2half_rn(src[i]);
+  }
+}
+
+int launch_convert_queries(const float* src, void* dst, size_t n, int dtype, cudaStream_t st) {
+  ProfScope _ps(st, "convert_queries");
+  if (n == 0) return B200R_OK;
+  const int threads = 256;
+  size_t blocks = (n + threads - 1) / threads;
+  if (blocks > (size_t)num_sms() * 8) blocks = (size_t)num_sms() * 8;
+  if (dtype == B200R_BF16) convert_queries_kernel<__nv_bfloat16><<<(unsigned)blocks, threads, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  else if (dtype == B200R_F16) convert_queries_kernel<__half><<<(unsigned)blocks, threads, 0, st>>>(src, reinterpret_cast<__half*>(dst), n);
+  else { set_error("convert_queries: dtype %d is not a 2-byte float type", dtype); return B200R_EINVAL; }
+  count_launch();
+  B200R_CUDA_CHECK(cudaGetLastError());
+  return B200R_OK;
+}
 
 int launch_replicate_queries(const void* Q, void* rep, int B, int D, cudaStream_t st) {
   ProfScope _ps(st, "replicate_queries");

@@ -42,6 +42,7 @@ struct Index {
   CUtensorMap tmap_x_f32;    // box 32 floats x 128 rows
   // staging for b200r_search_host
   void* h_q_dev; size_t q_dev_bytes;
+  void* h_q32_dev; size_t q32_dev_bytes;   // fp32 host queries before their on-device conversion (b200r_search_host_f32)
   float* h_s_dev; int64_t* h_i_dev; size_t out_dev_elems;
   void* h_ws; size_t ws_bytes;
 };
@@ -118,6 +119,8 @@ int launch_range_unpack(const void* keys, int64_t total, const int64_t* offsets,
                         float* out_scores, cudaStream_t st);
 size_t query_replica_bytes(int D);
 int launch_replicate_queries(const void* Q, void* rep, int B, int D, cudaStream_t st);
+int launch_search_prologue(const SearchPlan& p, void* ws, const void* Q, int D, int qdtype, bool cosine, cudaStream_t st);   // K1: init + 1/|q| + query replicas in one launch
+int launch_convert_queries(const float* src, void* dst, size_t n, int dtype, cudaStream_t st);   // f32 -> bf16 / f16, RNE
 int encode_query_tmap_replicated(const Index* ix, const void* rep, CUtensorMap* tmap_q);
 int launch_scan_topk(const Index* ix, const void* Q, const SearchPlan& p, void* ws, cudaStream_t st);
 int rows_i8_nq(int B, int D);                 // queries per corpus pass (16 / 32 / 64), 0 = int8 tensor path not available
@@ -132,8 +135,8 @@ int rows_f32_nq(int D);                       // queries per corpus pass of the 
 int rows_f32_tile_rows();
 size_t rows_f32_query_bytes(int B, int D);
 int launch_split_queries_tf32(const void* Q, int B, int D, void* qws, cudaStream_t st);
-int encode_query_tmap_f32(const void* qws, int group, int D, CUtensorMap* tmap_q);
-int launch_rows_f32(const Index* ix, const CUtensorMap* tmap_q, int group, const SearchPlan& p, const GemmPhase& ph, void* ws, cudaStream_t st);
+int encode_query_tmap_f32(const void* qws, int groups, int D, CUtensorMap* tmap_q);        // one map over every group's hi / mid planes
+int launch_rows_f32(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& p, const GemmPhase& ph, void* ws, cudaStream_t st);   // one phase of ALL groups
 int launch_mmr(const Index* ix, const int64_t* ids, const float* scores, int B, int P, int top_k, float lambda, int64_t* out_ids,
                float* out_scores, int32_t* out_pos, cudaStream_t st);
 int scan_bulk_warps(const Index* ix);        // consumer warps per CTA of the bulk-fed scan, 0 if it does not apply

@@ -566,7 +566,11 @@ static int run_select(SelectParams& p, int grid_y, cudaStream_t st) {
   if (p.mode != kSelPartial) limit = select_stage_limit(p.k, p.B);   // pruned lists hold ~k + one phase's survivors
   else if (ctas <= 148) limit = 24576;      // a handful of queries: one CTA per SM can afford a 192 KB stage
   p.stage_cap = (int)(all < limit ? all : limit);
-  const int threads = ctas >= 2048 ? 128 : (ctas >= 512 ? 256 : (ctas >= 128 ? 512 : 1024));
+  int threads = ctas >= 2048 ? 128 : (ctas >= 512 ? 256 : (ctas >= 128 ? 512 : 1024));
+  // few keys per CTA (e.g. the second level of a two-level select: groups x k keys): the ~70 block barriers of the radix
+  // passes and the sort dominate, and they are several times cheaper with 4 warps than with 32
+  if (all <= 1024) threads = 128;
+  else if (all <= 4096 && threads > 256) threads = 256;
   const size_t smem = (size_t)p.stage_cap * 8 + (p.mode == kSelOutput ? (size_t)p.kp2 * 8 : 0);
   B200R_CUDA_CHECK(cudaFuncSetAttribute(select_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   select_lists_kernel<<<dim3(p.B, grid_y), threads, smem, st>>>(p);

@@ -131,11 +131,26 @@ class DenseIndex:
             N.check(self._lib.b200r_search_sharded_begin(self._handle, comm.handle, Q.data_ptr(), B, k, p,
                                                          ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
 
+    def to_query_dtype(self, Q32: torch.Tensor) -> torch.Tensor:
+        """fp32 queries on this index's device -> its query dtype, converted by the library (b200r_convert_f32, RNE)."""
+        _require_cuda(Q32, "Q32")
+        if Q32.dtype != torch.float32 or not Q32.is_contiguous():
+            raise ValueError("Q32 must be a contiguous float32 CUDA tensor")
+        if self.query_dtype == torch.float32:
+            return Q32
+        out = torch.empty(Q32.shape, dtype=self.query_dtype, device=Q32.device)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.b200r_convert_f32(self.device.index or 0, Q32.data_ptr(), out.data_ptr(), Q32.numel(),
+                                                _DTYPES[self.query_dtype], _stream_ptr(self.device)))
+        return out
+
     def search_host(self, Q_host: torch.Tensor, k: int, path: str = "auto",
                     out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Host buffers in, host buffers out (H2D + search + D2H + stream sync inside the C call)."""
-        if Q_host.is_cuda or not Q_host.is_contiguous() or Q_host.dtype != self.query_dtype or Q_host.shape[1] != self.D:
-            raise ValueError("Q_host must be a contiguous CPU tensor [B, D] in the index's query dtype")
+        """Host buffers in, host buffers out (H2D + search + D2H + stream sync inside the C call).  Q_host is in the index's
+        query dtype, or float32 (what an embedding provider returns): the library then rounds it to the query dtype on the device."""
+        if Q_host.is_cuda or not Q_host.is_contiguous() or Q_host.dtype not in (self.query_dtype, torch.float32) or Q_host.shape[1] != self.D:
+            raise ValueError("Q_host must be a contiguous CPU tensor [B, D] in the index's query dtype or float32")
+        call = self._lib.b200r_search_host if Q_host.dtype == self.query_dtype else self._lib.b200r_search_host_f32
         B = int(Q_host.shape[0])
         if out is None:
             scores = torch.empty((B, k), dtype=torch.float32).pin_memory()
@@ -143,8 +158,7 @@ class DenseIndex:
         else:
             scores, ids = out
         with torch.cuda.device(self.device):
-            N.check(self._lib.b200r_search_host(self._handle, Q_host.data_ptr(), B, k, _PATHS[path], scores.data_ptr(),
-                                                ids.data_ptr(), _stream_ptr(self.device)))
+            N.check(call(self._handle, Q_host.data_ptr(), B, k, _PATHS[path], scores.data_ptr(), ids.data_ptr(), _stream_ptr(self.device)))
         return scores, ids
 
 
@@ -369,6 +383,8 @@ def expand_rescore_exchange_all(shards, graphs, comms, n_total_rows: int, Q_host
     handed to every device, then phase p is issued on every rank before phase p+1 on any; rank 0's results are returned."""
     B = int(seeds_host.shape[0])
     Qd = [Q_host.to(s.device, non_blocking=True) for s in shards]
+    if Q_host.dtype == torch.float32:            # provider embeddings: rounded to the query dtype on every device
+        Qd = [s.to_query_dtype(q) for s, q in zip(shards, Qd)]
     Sd = [seeds_host.to(s.device, non_blocking=True) for s in shards]
     outs = [_expand_outputs(s.device, B, k) for s in shards]
     nbytes = int(N.load().b200r_expand_workspace_bytes(B))

@@ -275,7 +275,7 @@ def gen_shard(torch, lo, hi, dim, tdt, dev, blk=1 << 20):
 def leg_plugin_single_process(torch, a, world, tdt, Qh, ref_ids, steps, warmup):
     """N > 1, rank 0 only, while the other ranks wait: ONE process drives all N GPUs through the plug-in's engine
     (backend.CudaEngine, what B200RetrievalBackend(devices=[0..N-1]) builds): float32 host queries in, host results out, the
-    corpus row-sharded over the devices, exchange + merge inside libb200r (b200r_search_sharded_host_all)."""
+    corpus row-sharded over the devices, exchange + merge inside libb200r (b200r_search_sharded_host_all_f32)."""
     from a_modular_rag_framework_b200.backend import CudaEngine
     from a_modular_rag_framework_b200.sharded import shard_rows
     shards = []
@@ -294,10 +294,10 @@ def leg_plugin_single_process(torch, a, world, tdt, Qh, ref_ids, steps, warmup):
     del eng, shards
     torch.cuda.empty_cache()
     return {"value": steps * a.batch / dt, "unit": UNIT, "ms_per_step": dt / steps * 1e3, "devices": world,
-            "h2d_bytes_per_step": a.batch * a.dim * 2 * world, "d2h_bytes_per_step": a.batch * a.k * 12,
+            "h2d_bytes_per_step": a.batch * a.dim * 4 * world, "d2h_bytes_per_step": a.batch * a.k * 12,
             "identical_to_the_torchrun_result": same,
-            "note": "one host thread, N GPUs: f32 -> corpus dtype on the host, async H2D to every device, sharded search + exchange + "
-                    "merge (libb200r), D2H from device 0; not pipelined across batches"}
+            "note": "one host thread, N GPUs: float32 host queries, async H2D to every device, rounded to the corpus dtype on the device, "
+                    "sharded search + exchange + merge (libb200r), D2H from device 0; not pipelined across batches"}
 
 
 def build_graph(torch, V, E, dev, seed=5):

@@ -88,6 +88,16 @@ int b200r_search(uint64_t index, const void* Q, int32_t B, int32_t k, int32_t pa
  * buffers that grow on demand. */
 int b200r_search_host(uint64_t index, const void* Q_host, int32_t B, int32_t k, int32_t path,
                       float* out_scores_host, int64_t* out_ids_host, void* stream);
+/* The same with the queries as FP32, whatever the corpus dtype -- what an embedding provider returns
+ * (router.embed yields Python floats, retrieval_backend.py:227-231).  The fp32 rows are copied to the device and
+ * rounded there to the index's query dtype (round to nearest even, the conversion torch / numpy apply), so the host
+ * never touches the 2-byte types. */
+int b200r_search_host_f32(uint64_t index, const float* Q_host_f32, int32_t B, int32_t k, int32_t path,
+                          float* out_scores_host, int64_t* out_ids_host, void* stream);
+
+/* fp32 -> bf16 / f16 on the device (round to nearest even): how fp32 query embeddings become the query dtype of a
+ * bf16 / f16 index without a host-side conversion.  src / dst are device pointers on `device`; dtype = B200R_BF16 / B200R_F16. */
+int b200r_convert_f32(int device, const float* src, void* dst, int64_t n, int32_t dtype, void* stream);
 
 /* Similarity floor: only results with score >= min_score are reported (at most the k best per query, the rest
  * of the row is (-inf, -1)).  With Q = rows of the corpus itself this is the all-pairs `sim >= semantic_threshold`
@@ -157,6 +167,10 @@ int b200r_search_sharded(uint64_t index, uint64_t comm, const void* Q, int32_t B
 int b200r_search_sharded_host_all(const uint64_t* indexes, const uint64_t* comms, int32_t G, const void* Q_host, int32_t B,
                                   int32_t k, int32_t path, float* out_scores_host, int64_t* out_ids_host,
                                   void* const* streams);
+/* ... with FP32 host queries, converted to the indexes' query dtype on every device (see b200r_search_host_f32). */
+int b200r_search_sharded_host_all_f32(const uint64_t* indexes, const uint64_t* comms, int32_t G, const float* Q_host_f32,
+                                      int32_t B, int32_t k, int32_t path, float* out_scores_host, int64_t* out_ids_host,
+                                      void* const* streams);
 
 /* ---- MMR diversification (optional post-filter) ----------------------------------------------------------------
  * Replaces mmr_diversify (app/utils/similarity.py:33-62) for B candidate lists at once: cand_ids / cand_scores [B, P]

@@ -58,7 +58,7 @@ def run_search(name, N, D, B, k, dtype, path, steps=10, warmup=3, check=True):
     per_pass = 8 if dtype == torch.float32 else 4
     passes = 1 if used == "gemm" else (B + per_pass - 1) // per_pass
     if used == "gemm" and dtype == torch.float32:
-        passes = (B + 15) // 16          # rows_f32.cu: 16 queries per corpus pass
+        passes = (B + 255) // 256        # rows_f32.cu: 16 queries per group, the groups of a 256-query slice ganged over L2
     gbs = N * D * esz * passes / (kms * 1e-3) / 1e9
     tfs = 2.0 * B * N * D / (kms * 1e-3) / 1e12
     line["hbm_GBps"] = gbs
@@ -201,6 +201,8 @@ CONFIGS = {
     "f32_5Mx768_B1_tensor": lambda: run_search("f32_5Mx768_B1_tensor", 5_000_000, 768, 1, 100, torch.float32, "gemm", steps=20),
     "f32_5Mx768_B8_tensor": lambda: run_search("f32_5Mx768_B8_tensor", 5_000_000, 768, 8, 100, torch.float32, "gemm", steps=20),
     "f32_5Mx768_B16_tensor": lambda: run_search("f32_5Mx768_B16_tensor", 5_000_000, 768, 16, 100, torch.float32, "gemm", steps=20),
+    "f32_5Mx768_B64_tensor": lambda: run_search("f32_5Mx768_B64_tensor", 5_000_000, 768, 64, 100, torch.float32, "gemm", steps=10),
+    "f32_5Mx768_B256_tensor": lambda: run_search("f32_5Mx768_B256_tensor", 5_000_000, 768, 256, 100, torch.float32, "gemm", steps=5),
     "f32_5Mx768_B1_scan": lambda: run_search("f32_5Mx768_B1_scan", 5_000_000, 768, 1, 100, torch.float32, "scan", steps=20),
     "f32_5Mx768_B4_scan": lambda: run_search("f32_5Mx768_B4_scan", 5_000_000, 768, 4, 100, torch.float32, "scan", steps=20),
     "f32_5Mx768_B8_scan": lambda: run_search("f32_5Mx768_B8_scan", 5_000_000, 768, 8, 100, torch.float32, "scan", steps=20),

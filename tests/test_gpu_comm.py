@@ -127,6 +127,13 @@ def test_single_process_host_all_call():
     for _ in range(3):
         N_.check(lib.b200r_search_sharded_host_all(ih, ch, G, Qh.data_ptr(), B, k, 0, hs.data_ptr(), hi.data_ptr(), None))
         assert torch.equal(hi, ri.cpu()) and torch.equal(hs, rs.cpu())
+    # fp32 host queries (provider embeddings), rounded to bf16 on every device: same result as the host-rounded ones
+    Q32 = torch.randn((B, D), generator=g, device=dev)
+    rs, ri = DenseIndex(X).search(Q32.to(torch.bfloat16), k)
+    Q32h = Q32.cpu().pin_memory()
+    hs.fill_(0); hi.fill_(0)
+    N_.check(lib.b200r_search_sharded_host_all_f32(ih, ch, G, Q32h.data_ptr(), B, k, 0, hs.data_ptr(), hi.data_ptr(), None))
+    assert torch.equal(hi, ri.cpu()) and torch.equal(hs, rs.cpu())
 
 
 def _ipc_worker(rank, world, port, tmpdir, ret):

@@ -264,6 +264,23 @@ def test_search_host_matches_device():
     assert torch.equal(i_dev.cpu(), i_h) and torch.equal(s_dev.cpu(), s_h)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_search_host_f32_queries_are_rounded_on_the_device(dtype):
+    """b200r_search_host_f32 / b200r_convert_f32: fp32 provider embeddings are rounded to the index's query dtype by the
+    library (RNE, bit-identical to torch's conversion, halfway cases and subnormals included), so the result equals the
+    search with host-converted queries."""
+    g = torch.Generator(device="cuda").manual_seed(10)
+    X = torch.randn((20000, 96), generator=g, device=_dev()).to(dtype)
+    Q32 = torch.randn((37, 96), generator=g, device=_dev())
+    Q32[0, :8] = torch.tensor([1.00390625, 1.01171875, -1.00390625, 3.0e-39, 65504.0, 1e-8, -0.0, 0.333251953125], device=_dev())
+    ix = _index(X)
+    if dtype != torch.float32:
+        assert torch.equal(ix.to_query_dtype(Q32.contiguous()).view(torch.int16), Q32.to(dtype).view(torch.int16))
+    s_ref, i_ref = ix.search(Q32.to(dtype), 10)
+    s_h, i_h = ix.search_host(Q32.cpu().pin_memory(), 10)
+    assert torch.equal(i_ref.cpu(), i_h) and torch.equal(s_ref.cpu(), s_h)
+
+
 def test_merge_topk_vs_oracle():
     from a_modular_rag_framework_b200 import merge_topk
     rng = np.random.default_rng(2)
@@ -445,8 +462,10 @@ def test_search_captured_in_a_cuda_graph_replays():
     (5000, 100, 5, 50, "cos"),              # D % 32 != 0: the last K slice is partly out of bounds (zero-filled)
     (17, 64, 3, 5, "cos"),                  # fewer rows than one tile
     (1, 16, 1, 1, "ip"),
-    (60000, 768, 40, 10, "cos"),            # three groups of 16 queries
+    (60000, 768, 40, 10, "cos"),            # three groups of 16 queries ganged in one launch (49 CTAs each)
     (30000, 1024, 4, 20, "cos"),
+    (100000, 768, 256, 20, "cos"),          # a full 256-query slice: 16 ganged groups, 9 CTAs each
+    (20000, 128, 300, 10, "ip"),            # two slices, the second one with 3 groups
 ])
 def test_fp32_tensor_path(N, D, B, k, metric):
     """fp32 corpora on tcgen05 kind::tf32 with both operands split into two exact tf32 pieces (rows_f32.cu): the fp32 bar,
