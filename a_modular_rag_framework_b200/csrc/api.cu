@@ -170,9 +170,9 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
     pl->Bpad = (pl->rows_i8 ? pl->rows_i8 : pl->num_q_tiles) * BMq;
     // units = (query tile, chunk of row tiles).  More units per CTA = better balance, fewer = less list
     // traffic; pick the chunk count (near a target) that wastes the fewest CTA slots in the last wave.
-    // int8 / fp32: the query groups of a slice share one launch, num_sms / groups CTAs each (rows_i8.cu, rows_f32.cu), so the
-    // chunks are sized for that many CTAs per group
-    const int grid_max = pl->rows_i8 ? rows_i8_ctas_per_group(pl->rows_i8) : num_sms() / pl->cta_group;
+    // int8: the query groups of a slice share one launch, num_sms / groups CTAs each (rows_i8.cu), so the chunks are
+    // sized for that many CTAs per group
+    const int grid_max = (pl->rows_i8 && !pl->rows_f32) ? rows_i8_ctas_per_group(pl->rows_i8) : num_sms() / pl->cta_group;
     const int m = pl->num_q_tiles >= 16 ? 8 : (pl->num_q_tiles >= 4 ? 4 : (pl->num_q_tiles >= 2 ? 2 : 1));
     long long target = ((long long)grid_max * m + pl->num_q_tiles - 1) / pl->num_q_tiles;
     if (target < 1) target = 1;
@@ -261,7 +261,11 @@ int make_plan(const Index* ix, int B, int k, int path, SearchPlan* pl) {
   pl->off_gthr = off; off += align_up((size_t)pl->Bpad * 4, 256);
   pl->off_qinv = off; off += align_up((size_t)pl->Bpad * 4, 256);
   pl->num_groups = 0;
-  if (pl->num_segments > 2 * select_group_size()) {
+  // Two-level final select for the thousands of short lists of the scan paths.  A handful of queries on the tile kernel
+  // (<= 148 pruned lists each) take ONE wide CTA per query instead: their candidates (~k + the last phase's survivors) fit
+  // its 192 KB stage, and the second launch costs more than it saves (batch 1: 21 + 19 us against ~22 us).
+  const bool one_level = path == B200R_PATH_GEMM && !pl->rows_i8 && B <= 16 && k <= 256 && pl->num_phases > 1 && pl->num_segments + 1 <= select_max_flat_segments();
+  if (pl->num_segments > 2 * select_group_size() && !one_level) {
     pl->num_groups = (pl->num_segments + select_group_size() - 1) / select_group_size();
     pl->off_lists2 = off; off += align_up((size_t)pl->num_groups * pl->Bpad * pl->k * 8, 256);
     pl->off_counts2 = off; off += align_up((size_t)pl->num_groups * pl->Bpad * 4, 256);
@@ -318,11 +322,15 @@ static int do_search_one(Index* ix, const void* Q, int B, int k, int path, float
   if (pl.path == B200R_PATH_GEMM && pl.rows_i8 && pl.rows_f32) {
     void* qws = (char*)ws + pl.off_qrep;
     if ((rc = launch_split_queries_tf32(Q, B, ix->D, qws, st))) return rc;
-    CUtensorMap tmap_q;
-    if ((rc = encode_query_tmap_f32(qws, pl.rows_i8, ix->D, &tmap_q))) return rc;
+    // one launch per group of 16 queries per phase: ganging the groups like the int8 kernel was measured and dropped -- this
+    // kernel is bound by its per-SM converter / MMA pipeline, not by HBM, so sharing tiles through L2 gains nothing and the
+    // extra index arithmetic cost 11 % (profiles/r2_f32_mid_buffers_and_gang_ab.jsonl)
+    std::vector<CUtensorMap> tmaps(pl.rows_i8);
+    for (int g = 0; g < pl.rows_i8; ++g)
+      if ((rc = encode_query_tmap_f32(qws, g, ix->D, &tmaps[g]))) return rc;
     for (int i = 0; i < pl.num_phases; ++i) {
       profile_begin(st);
-      rc = launch_rows_f32(ix, &tmap_q, pl, pl.phases[i], ws, st);
+      for (int g = 0; g < pl.rows_i8 && !rc; ++g) rc = launch_rows_f32(ix, &tmaps[g], g, pl, pl.phases[i], ws, st);
       profile_end(st);
       if (rc) return rc;
       if (i + 1 < pl.num_phases && (rc = launch_select_lists(ix, pl, ws, nullptr, nullptr, st))) return rc;

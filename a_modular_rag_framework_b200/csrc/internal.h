@@ -135,8 +135,8 @@ int rows_f32_nq(int D);                       // queries per corpus pass of the 
 int rows_f32_tile_rows();
 size_t rows_f32_query_bytes(int B, int D);
 int launch_split_queries_tf32(const void* Q, int B, int D, void* qws, cudaStream_t st);
-int encode_query_tmap_f32(const void* qws, int groups, int D, CUtensorMap* tmap_q);        // one map over every group's hi / mid planes
-int launch_rows_f32(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& p, const GemmPhase& ph, void* ws, cudaStream_t st);   // one phase of ALL groups
+int encode_query_tmap_f32(const void* qws, int group, int D, CUtensorMap* tmap_q);
+int launch_rows_f32(const Index* ix, const CUtensorMap* tmap_q, int group, const SearchPlan& p, const GemmPhase& ph, void* ws, cudaStream_t st);
 int launch_mmr(const Index* ix, const int64_t* ids, const float* scores, int B, int P, int top_k, float lambda, int64_t* out_ids,
                float* out_scores, int32_t* out_pos, cudaStream_t st);
 int scan_bulk_warps(const Index* ix);        // consumer warps per CTA of the bulk-fed scan, 0 if it does not apply

@@ -44,12 +44,8 @@ constexpr int RF_ACC = 2;                           // tiles in flight in TMEM
 // converters write a mid tile that the MMA then reads back (90 KB of traffic per 16 KB slice, 0.68 of the HBM roofline
 // measured); here each converter thread owns one corpus ROW (conflict-free reads thanks to the 128-byte swizzle), and
 // stores its 32 mid values into TMEM with tcgen05.st, where the MMA takes them as its A operand (58 KB per slice).
-// TMEM columns: 2 tiles x 4 partial accumulators x 32 = 256, the other 256 hold up to 8 mid buffers x 32.  The converters
-// may run `mids` slices ahead of the MMAs' retirement.  ncu shows them waiting for a free buffer 61 % of their time with 3
-// buffers (24.5 % of all samples), but 3 / 5 / 8 buffers measure the same (B200R_F32_MID_BUFS A/B,
-// profiles/r2_f32_mid_buffers_and_gang_ab.jsonl): the wait is back-pressure from the MMA stage, not a shortage of buffers.
-constexpr int RF_MID_TMEM_BUFS = 8;
-constexpr int RF_MID_MAX = 8;
+// TMEM columns: 2 tiles x 4 partial accumulators x 32 + 3 mid buffers x 32 = 352 (512 allocated).
+constexpr int RF_MID_TMEM_BUFS = 3;
 constexpr int RF_MID_TMEM_COL0 = RF_ACC * RF_PARTS_TMEM * RF_PART_COLS;   // 256
 constexpr int RF_MAX_STAGES = 10;
 constexpr u32 RF_TF32_MASK = 0xffffe000u;
@@ -58,8 +54,7 @@ struct RowsF32Params {
   int B, k, D, num_kb, stages, mids;          // raw ring stages, mid side buffers
   int backoff;             // 1: waiting epilogue warps sleep between polls
   int store_hi;            // 1: the converters also write the truncated hi piece back in place (see rows_f32_store_hi)
-  int groups;              // 16-query groups ganged in this launch: CTA b serves group b % groups and is CTA b / groups of the
-                           // gridDim.x / groups that walk that group's units (the gang streams the same corpus tiles: L2 hits)
+  int q0;                  // this launch serves queries [q0, min(B, q0 + 16))
   long long N;
   int tile_begin, tile_end, tiles_per_chunk, num_units;
   int cap, cap_soft, Bpad;
@@ -138,8 +133,8 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   u64* full_bar = bars;                               // [stages]  TMA landed
   u64* conv_bar = bars + RF_MAX_STAGES;               // [stages]  split done (4 converter warps)
   u64* empty_bar = bars + 2 * RF_MAX_STAGES;          // [stages]  MMAs retired
-  u64* mid_empty_bar = bars + 3 * RF_MAX_STAGES;      // [mids] (<= RF_MID_MAX)
-  u64* tmem_full_bar = mid_empty_bar + RF_MID_MAX;    // [RF_ACC]
+  u64* mid_empty_bar = bars + 3 * RF_MAX_STAGES;      // [mids] (<= 4)
+  u64* tmem_full_bar = mid_empty_bar + 4;             // [RF_ACC]
   u64* tmem_empty_bar = tmem_full_bar + RF_ACC;       // [RF_ACC]
   u32* tmem_ptr_smem = reinterpret_cast<u32*>(tmem_empty_bar + RF_ACC);
 
@@ -164,15 +159,12 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const u32 tmem_base = *tmem_ptr_smem;
-  const int group = blockIdx.x % p.groups;          // which 16 queries
-  const int u_first = blockIdx.x / p.groups, u_step = gridDim.x / p.groups;
-  const int q0 = group * RF_NQ;                     // list / threshold / count slots q0 + j
 
   if (warp_idx == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int stage = 0; u32 phase = 0;
-      for (int u = u_first; u < p.num_units; u += u_step) {
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
         const int t0 = p.tile_begin + u * p.tiles_per_chunk;
         const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
         for (int t = t0; t < t1; ++t) {
@@ -180,7 +172,7 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_expect_tx(&full_bar[stage], RF_RING_BYTES);
             tma_load_2d(smem_x + (size_t)stage * RF_RING_BYTES, &tmap_x, &full_bar[stage], kb * RF_BK, t * RF_ROWS, kEvictFirst);
-            tma_load_2d(smem_x + (size_t)stage * RF_RING_BYTES + RF_STAGE_BYTES, &tmap_q, &full_bar[stage], kb * RF_BK, group * 2 * RF_NQ, kEvictLast);
+            tma_load_2d(smem_x + (size_t)stage * RF_RING_BYTES + RF_STAGE_BYTES, &tmap_q, &full_bar[stage], kb * RF_BK, 0, kEvictLast);
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -192,7 +184,7 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       int stage = 0; u32 phase = 0;
       u32 tile_iter = 0;
       int m = 0;
-      for (int u = u_first; u < p.num_units; u += u_step) {
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
         const int t0 = p.tile_begin + u * p.tiles_per_chunk;
         const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
         for (int t = t0; t < t1; ++t, ++tile_iter) {
@@ -229,7 +221,7 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int ct = threadIdx.x - 6 * 32;
     int stage = 0; u32 phase = 0;
     int m = 0; u32 mphase = 0;
-    for (int u = u_first; u < p.num_units; u += u_step) {
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
       const int t0 = p.tile_begin + u * p.tiles_per_chunk;
       const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
       for (int t = t0; t < t1; ++t) {
@@ -285,16 +277,16 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     u64* kth = kth_s + ew * RF_NQ;
     int* cnt = cnt_s + ew * RF_NQ;
     u32 tile_iter = 0;
-    for (int u = u_first; u < p.num_units; u += u_step) {
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
       const int t0 = p.tile_begin + u * p.tiles_per_chunk;
       const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
       if (t0 >= t1) continue;
       const size_t seg = (size_t)u * 4 + ew;               // this warp's list segment for the unit's row chunk
       if (lane < RF_NQ) {
-        const bool valid = q0 + lane < p.B;
-        thr[lane] = valid ? ordered_to_f32(__ldcg(p.gthr + q0 + lane)) : __int_as_float(0x7f800000);
+        const bool valid = p.q0 + lane < p.B;
+        thr[lane] = valid ? ordered_to_f32(__ldcg(p.gthr + p.q0 + lane)) : __int_as_float(0x7f800000);
         kth[lane] = 0;
-        cnt[lane] = valid ? __ldcg(p.counts + seg * p.Bpad + q0 + lane) : 0;
+        cnt[lane] = valid ? __ldcg(p.counts + seg * p.Bpad + p.q0 + lane) : 0;
       }
       __syncwarp();
       for (int t = t0; t < t1; ++t, ++tile_iter) {
@@ -333,7 +325,7 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               const u32 b2 = __ballot_sync(kFullMask, (s[j] >= tj) && key > kth[j]);
               if (b2) {
                 const int base = cnt[j];
-                u64* lp = p.lists + (seg * p.Bpad + q0 + j) * (size_t)p.cap;
+                u64* lp = p.lists + (seg * p.Bpad + p.q0 + j) * (size_t)p.cap;
                 if ((b2 >> lane) & 1u) __stcg(lp + base + __popc(b2 & ((1u << lane) - 1u)), key);
                 const int n = base + __popc(b2);
                 __syncwarp();
@@ -341,7 +333,7 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                   const u64 kk = warp_compact(lp, n, p.k, hist);
                   if (lane == 0) {
                     kth[j] = kk; thr[j] = fmaxf(tj, key_score(kk)); cnt[j] = p.k;
-                    atomicMax(p.gthr + q0 + j, (u32)(kk >> 32));
+                    atomicMax(p.gthr + p.q0 + j, (u32)(kk >> 32));
                   }
                 } else if (lane == 0) {
                   cnt[j] = n;
@@ -352,10 +344,10 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         }
         // thresholds published by other CTAs / warps
-        if (lane < RF_NQ && q0 + lane < p.B) thr[lane] = fmaxf(thr[lane], ordered_to_f32(__ldcg(p.gthr + q0 + lane)));
+        if (lane < RF_NQ && p.q0 + lane < p.B) thr[lane] = fmaxf(thr[lane], ordered_to_f32(__ldcg(p.gthr + p.q0 + lane)));
         __syncwarp();
       }
-      if (lane < RF_NQ && q0 + lane < p.B) p.counts[seg * p.Bpad + q0 + lane] = cnt[lane];
+      if (lane < RF_NQ && p.q0 + lane < p.B) p.counts[seg * p.Bpad + p.q0 + lane] = cnt[lane];
       __syncwarp();
     }
   }
@@ -384,16 +376,13 @@ static bool rows_f32_mid_tmem() {
   return v;
 }
 static int rows_f32_mids() {
-  if (rows_f32_mid_tmem()) {
-    static const int t = [] { const char* e = getenv("B200R_F32_MID_BUFS"); const int v = e ? atoi(e) : RF_MID_TMEM_BUFS; return (v >= 2 && v <= RF_MID_MAX) ? v : RF_MID_TMEM_BUFS; }();
-    return t;
-  }
+  if (rows_f32_mid_tmem()) return RF_MID_TMEM_BUFS;
   static const int m = [] { const char* e = getenv("B200R_F32_MIDS"); const int v = e ? atoi(e) : 3; return (v >= 2 && v <= 4) ? v : 3; }();
   return m;
 }
 static size_t rows_f32_smem_bytes(int stages) {
   return 1024 + (size_t)stages * RF_RING_BYTES + (rows_f32_mid_tmem() ? 0 : (size_t)rows_f32_mids() * RF_STAGE_BYTES) + 4 * 256 * 4 +
-         (size_t)4 * RF_NQ * (4 + 8 + 4) + (3 * RF_MAX_STAGES + RF_MID_MAX + 2 * RF_ACC + 2) * 8 + 16;
+         (size_t)4 * RF_NQ * (4 + 8 + 4) + (3 * RF_MAX_STAGES + 4 + 2 * RF_ACC + 2) * 8 + 16;
 }
 static int rows_f32_stages_for(int) {
   int stages = RF_MAX_STAGES;
@@ -421,18 +410,18 @@ int launch_split_queries_tf32(const void* Q, int B, int D, void* qws, cudaStream
   return B200R_OK;
 }
 
-// one map over the hi / mid planes of every group: box = the 32 plane rows of one group x one 128-byte K slice
-int encode_query_tmap_f32(const void* qws, int groups, int D, CUtensorMap* tmap_q) {
-  return encode_tmap_2d(tmap_q, B200R_F32, qws, (uint64_t)D, (uint64_t)groups * 2 * RF_NQ, RF_BK, (uint32_t)(2 * RF_NQ));
+int encode_query_tmap_f32(const void* qws, int group, int D, CUtensorMap* tmap_q) {
+  const float* base = reinterpret_cast<const float*>(qws) + (size_t)group * rows_f32_group_floats(D);
+  return encode_tmap_2d(tmap_q, B200R_F32, base, (uint64_t)D, (uint64_t)(2 * RF_NQ), RF_BK, (uint32_t)(2 * RF_NQ));
 }
 
-// one launch = one phase of ALL the plan's groups of <= 16 queries (ganged like rows_i8.cu)
-int launch_rows_f32(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan& pl, const GemmPhase& ph, void* ws,
+// one launch = one phase of one group of <= 16 queries
+int launch_rows_f32(const Index* ix, const CUtensorMap* tmap_q, int group, const SearchPlan& pl, const GemmPhase& ph, void* ws,
                     cudaStream_t st) {
   ProfScope _ps(st, "rows_f32");
   RowsF32Params p;
   p.B = pl.B; p.k = pl.k; p.D = ix->D; p.N = ix->N;
-  p.groups = pl.rows_i8;
+  p.q0 = group * RF_NQ;
   p.num_kb = (ix->D + RF_BK - 1) / RF_BK;
   p.stages = rows_f32_stages_for(ix->D);
   p.mids = rows_f32_mids();
@@ -450,9 +439,7 @@ int launch_rows_f32(const Index* ix, const CUtensorMap* tmap_q, const SearchPlan
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((u32)(RF_NQ >> 3) << 17) | ((u32)(RF_ROWS >> 4) << 24);
   p.idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((u32)((2 * RF_NQ) >> 3) << 17) | ((u32)(RF_ROWS >> 4) << 24);
   const size_t smem = rows_f32_smem_bytes(p.stages);
-  int per_group = rows_i8_ctas_per_group(pl.rows_i8);       // the plan sized the chunks for num_sms / groups CTAs per group
-  if (per_group > p.num_units) per_group = p.num_units;
-  const int grid = per_group * p.groups;
+  const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
   if (rows_f32_mid_tmem()) {
     B200R_CUDA_CHECK(cudaFuncSetAttribute(rows_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rows_f32_kernel<true><<<grid, RF_THREADS, smem, st>>>(*tmap_q, ix->tmap_x_f32, p);

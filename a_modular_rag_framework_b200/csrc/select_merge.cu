@@ -21,6 +21,7 @@ constexpr int SEL_STAGE_MAX = 6144;   // keys staged in shared memory for the gr
 constexpr int SEL_STAGE_LISTS = 2560; // ... and for the per-phase / final select over pruned lists (20 KB -> 11 CTAs/SM)
 constexpr int SEL_MAX_SEGS = 1024;     // segments whose counts fit the in-smem prefix (flattened gather)
 constexpr int SEL_GROUP = 64;         // segments per CTA in the first level of a two-level select
+constexpr int SEL_BINS = 1024;        // linear score bins of the histogram path (see select_lists_kernel)
 
 enum SelectMode { kSelOutput = 0, kSelThreshold = 1, kSelPartial = 2 };
 
@@ -106,9 +107,11 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
   extern __shared__ uint8_t smem_raw[];
   u64* stage = reinterpret_cast<u64*>(smem_raw);            // [stage_cap]
   u64* sk = stage + p.stage_cap;                            // [kp2] (output mode)
-  __shared__ u32 hist[256];
+  __shared__ __align__(16) u32 hist[SEL_BINS];              // radix passes use the first 256 words
   __shared__ u64 s_prefix;
   __shared__ int s_remaining, s_total, s_nout;
+  __shared__ u32 s_lo32, s_hi32, s_t32;                     // histogram path: score range of the staged keys, threshold
+  __shared__ int s_bstar, s_reach;                          // ... bin of the k-th best, keys in bins >= it
 
   const int q = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
   const int nreal = s1 - s0;
   const int nseg = nreal + (has_carry ? 1 : 0);
   const bool flat = nseg <= SEL_MAX_SEGS;
-  if (tid == 0) { s_total = 0; s_nout = 0; s_prefix = 0; }
+  if (tid == 0) { s_total = 0; s_nout = 0; s_prefix = 0; s_lo32 = 0xffffffffu; s_hi32 = 0u; s_t32 = 0xffffffffu; }
   __syncthreads();
   if (flat) {
     // blocked scan: thread t owns segments [t*per, t*per+per)
@@ -165,13 +168,51 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
   if (p.mode == kSelThreshold && total < p.k) return;   // not enough candidates yet for a threshold
   const bool staged = total <= p.stage_cap;
   if (staged && flat) {
-    for (int i = tid; i < total; i += SEL_THREADS) {
-      int lo = 0, hi = nseg;                       // last segment with seg_off <= i
-      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_off[mid] <= i) lo = mid; else hi = mid; }
-      const u64 key = (lo >= nreal) ? p.carry[(size_t)q * p.carry_cap + (i - seg_off[lo])]
-                                                     : p.lists[((size_t)(s0 + lo) * p.Bpad + q) * (size_t)p.cap + (i - seg_off[lo])];
-      stage[i] = xform ? final_key(key, qi) : key;
+    // one warp per segment (the prefix gives every segment its place in the stage: deterministic, coalesced, ~6
+    // instructions per 32 keys -- a per-key binary search over the prefix cost 60), four segments' first loads in flight;
+    // the score range of what is staged feeds the histogram path below
+    u32 lo32 = 0xffffffffu, hi32 = 0u;
+    if (nseg < SEL_WARPS) {
+      // fewer segments than warps (one long flat list, the second level of a two-level select): spread the KEYS over the
+      // threads instead, each locating its segment by binary search over the prefix
+      for (int i = tid; i < total; i += SEL_THREADS) {
+        int lo = 0, hi = nseg;                       // last segment with seg_off <= i
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_off[mid] <= i) lo = mid; else hi = mid; }
+        const u64 raw = (lo >= nreal) ? p.carry[(size_t)q * p.carry_cap + (i - seg_off[lo])]
+                                      : p.lists[((size_t)(s0 + lo) * p.Bpad + q) * (size_t)p.cap + (i - seg_off[lo])];
+        const u64 key = xform ? final_key(raw, qi) : raw;
+        stage[i] = key;
+        lo32 = min(lo32, (u32)(key >> 32)); hi32 = max(hi32, (u32)(key >> 32));
+      }
+    } else
+    for (int sg0 = warp; sg0 < nseg; sg0 += 4 * SEL_WARPS) {
+      u64 v[4]; int o[4], c[4]; const u64* lp[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int sg = sg0 + r * SEL_WARPS;
+        o[r] = sg < nseg ? seg_off[sg] : 0;
+        c[r] = sg < nseg ? seg_off[sg + 1] - o[r] : 0;
+        lp[r] = (sg >= nreal) ? p.carry + (size_t)q * p.carry_cap : p.lists + ((size_t)(s0 + sg) * p.Bpad + q) * (size_t)p.cap;
+        v[r] = lane < c[r] ? lp[r][lane] : 0ull;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (lane < c[r]) {
+          const u64 key = xform ? final_key(v[r], qi) : v[r];
+          stage[o[r] + lane] = key;
+          lo32 = min(lo32, (u32)(key >> 32)); hi32 = max(hi32, (u32)(key >> 32));
+        }
+        for (int i = lane + 32; i < c[r]; i += 32) {
+          const u64 raw = lp[r][i];
+          const u64 key = xform ? final_key(raw, qi) : raw;
+          stage[o[r] + i] = key;
+          lo32 = min(lo32, (u32)(key >> 32)); hi32 = max(hi32, (u32)(key >> 32));
+        }
+      }
     }
+    lo32 = __reduce_min_sync(kFullMask, lo32);
+    hi32 = __reduce_max_sync(kFullMask, hi32);
+    if (lane == 0 && lo32 <= hi32) { atomicMin(&s_lo32, lo32); atomicMax(&s_hi32, hi32); }
     __syncthreads();
   } else if (staged) {
     // gather the valid keys: one warp per segment, coalesced
@@ -191,7 +232,62 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) select_lists_kernel(const Sel
   }
 
   u64 kth = 0;
-  if (total > p.k || p.mode == kSelThreshold) {
+  // Histogram path (staged + flat; not the partial level, which must hand on exactly k keys): bin the staged keys ONCE
+  // into SEL_BINS bins linear in the score between the smallest and the largest of them, find the bin b* of the k-th best
+  // with one suffix scan, and take T = the smallest score found in bins >= b*.  Every key with score >= T is kept:
+  // `reach` >= k of them, usually k plus a handful.  A threshold select needs nothing more (T is a valid, tight lower bound
+  // of the k-th best); the final select sorts those `reach` keys and emits the best k -- unless they do not fit the sort
+  // buffer (mass ties), in which case the exact radix select below runs.  One pass + two short ones instead of 3 / 8 radix
+  // passes with warp-aggregated atomics: the per-phase select of a batch-1 search went from 179 k to ~35 k warp
+  // instructions on its one SM.
+  bool have_kth = false;
+  if (staged && flat && p.mode != kSelPartial && (total > p.k || p.mode == kSelThreshold)) {
+    for (int i = tid; i < SEL_BINS; i += SEL_THREADS) hist[i] = 0;
+    __syncthreads();
+    const float flo = ordered_to_f32(s_lo32), fhi = ordered_to_f32(s_hi32);
+    const float range = fhi - flo;
+    const float scale = (range > 0.0f && range < CUDART_INF_F) ? (float)(SEL_BINS - 1) / range : 0.0f;    // 0: every key in bin 0
+    auto bin_of = [&](u64 key) -> int {
+      const int b = (int)((key_score(key) - flo) * scale);      // monotone in the score
+      return b < SEL_BINS - 1 ? b : SEL_BINS - 1;
+    };
+    for (int i = tid; i < total; i += SEL_THREADS) atomicAdd(&hist[bin_of(stage[i])], 1u);
+    __syncthreads();
+    if (tid < 32) {                                    // lane L owns bins [32 L, 32 L + 32)
+      u32 w[32]; u32 lane_sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 t = reinterpret_cast<const uint4*>(hist + lane * 32)[j];
+        w[4 * j] = t.x; w[4 * j + 1] = t.y; w[4 * j + 2] = t.z; w[4 * j + 3] = t.w;
+        lane_sum += t.x + t.y + t.z + t.w;
+      }
+      u32 suffix = lane_sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_down_sync(kFullMask, suffix, o); if (lane + o < 32) suffix += t; }
+      const u32 above = suffix - lane_sum;
+      if (above < (u32)p.k && (u32)p.k <= suffix) {    // exactly one lane (total >= k)
+        u32 acc = above;
+#pragma unroll
+        for (int j = 31; j >= 0; --j) {
+          acc += w[j];
+          if (acc >= (u32)p.k) { s_bstar = lane * 32 + j; s_reach = (int)acc; break; }
+        }
+      }
+    }
+    __syncthreads();
+    const int bstar = s_bstar;
+    u32 t32 = 0xffffffffu;
+    for (int i = tid; i < total; i += SEL_THREADS) {
+      const u64 key = stage[i];
+      if (bin_of(key) >= bstar) t32 = min(t32, (u32)(key >> 32));
+    }
+    t32 = __reduce_min_sync(kFullMask, t32);
+    if (lane == 0 && t32 != 0xffffffffu) atomicMin(&s_t32, t32);
+    __syncthreads();
+    // reach = keys in bins >= b* = keys with score >= T (the bin is a function of the score)
+    if (p.mode == kSelThreshold || s_reach <= p.kp2) { kth = (u64)s_t32 << 32; have_kth = true; }
+  }
+  if (!have_kth && (total > p.k || p.mode == kSelThreshold)) {
     // threshold mode stops after the top 24 bits: the truncated key is a valid (slightly low) threshold
     const int last_pass = (p.mode == kSelThreshold) ? 5 : 0;
     if (tid == 0) s_remaining = p.k;

@@ -12,6 +12,18 @@ dev = torch.device("cuda:0")
 PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
 
 
+def sm_clock_mhz():
+    """SM clock right now (called while the timed kernels are still queued): several kernels here are bound by an SM-side
+    pipeline, so a power-capped box measures slower -- the line says which clock it ran at."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
+        return int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def corpus(N, D, dtype, seed=1):
     X = torch.empty((N, D), dtype=dtype, device=dev)
     blk = 1 << 20
@@ -44,6 +56,7 @@ def run_search(name, N, D, B, k, dtype, path, steps=10, warmup=3, check=True):
     for i in range(steps):
         out = ix.search(Q[warmup + i], k, path=path)
     e1.record()
+    mhz = sm_clock_mhz()
     torch.cuda.synchronize()
     kms, kn = _native.profile_read()
     _native.profile_enable(False)
@@ -52,7 +65,7 @@ def run_search(name, N, D, B, k, dtype, path, steps=10, warmup=3, check=True):
     esz = X.element_size()
     used = path if path != "auto" else ("gemm" if dtype in (torch.bfloat16, torch.float16) else "scan")
     line = {"config": name, "rows": N, "dim": D, "batch": B, "k": k, "dtype": str(dtype).split(".")[-1], "path": used,
-            "ms_per_batch": ms, "queries_per_s": B / (ms * 1e-3), "kernel_ms_per_batch": kms, "kernel_launches_per_batch": kn / steps}
+            "ms_per_batch": ms, "queries_per_s": B / (ms * 1e-3), "kernel_ms_per_batch": kms, "kernel_launches_per_batch": kn / steps, "sm_mhz": mhz}
     # corpus passes per batch: the tile kernel streams the corpus once; the bulk-fed fp32 scan serves 8 queries per pass
     # (scan_bulk.cu), the register-fed scan 4 (scan_topk.cu)
     per_pass = 8 if dtype == torch.float32 else 4
