@@ -620,7 +620,8 @@ __global__ void minmax_decode_kernel(const u32* __restrict__ mm, float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ K3c
-static size_t select_smem_bytes(int maxc, int kp2) { return (size_t)maxc * 8 + (size_t)maxc * 4 + (size_t)kp2 * 8; }
+constexpr int FUSE_BINS = 1024;        // linear bins of the histogram select in fuse_select_kernel
+static size_t select_smem_bytes(int maxc, int kp2) { return (size_t)maxc * 8 + (size_t)maxc * 4 + (size_t)kp2 * 8 + (size_t)kp2 * 4; }
 
 template <int MAXC>
 __global__ void __launch_bounds__(SEL_THREADS) fuse_select_kernel(const ExpandParams p) {
@@ -629,10 +630,13 @@ __global__ void __launch_bounds__(SEL_THREADS) fuse_select_kernel(const ExpandPa
   u64* keys = reinterpret_cast<u64*>(smem_raw);                    // [MAXC]
   u64* sk = keys + MAXC;                                           // [kp2]
   u32* cand = reinterpret_cast<u32*>(sk + p.kp2);                  // [MAXC]
+  int* wslot = reinterpret_cast<int*>(cand + MAXC);                // [kp2] position of every winner in the candidate list
   __shared__ int s_remaining, s_nout, s_done;
   __shared__ float s_red[4][SEL_WARPS];
-  __shared__ u32 hist[256];
+  __shared__ __align__(16) u32 hist[FUSE_BINS];          // the radix passes use the first 256 words
   __shared__ u64 s_prefix;
+  __shared__ u32 s_lo32, s_hi32, s_t32;                  // histogram select: range of the fused scores, threshold
+  __shared__ int s_valid, s_bstar, s_reach;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool xchg = p.mode == 3;
   u32 e_cos = 0, e_out = 0;
@@ -675,7 +679,7 @@ __global__ void __launch_bounds__(SEL_THREADS) fuse_select_kernel(const ExpandPa
       xmin = fminf(xmin, __shfl_xor_sync(kFullMask, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(kFullMask, xmax, o));
     }
     if (lane == 0) { s_red[0][warp] = gmin; s_red[1][warp] = gmax; s_red[2][warp] = xmin; s_red[3][warp] = xmax; }
-    if (tid == 0) { s_prefix = 0; s_remaining = p.k; s_nout = 0; s_done = 0; }
+    if (tid == 0) { s_prefix = 0; s_remaining = p.k; s_nout = 0; s_done = 0; s_lo32 = 0xffffffffu; s_hi32 = 0u; s_t32 = 0xffffffffu; s_valid = 0; }
     for (int i = tid; i < p.kp2; i += SEL_THREADS) sk[i] = 0;
     __syncthreads();
     for (int w = 0; w < SEL_WARPS; ++w) {
@@ -695,19 +699,75 @@ __global__ void __launch_bounds__(SEL_THREADS) fuse_select_kernel(const ExpandPa
     const bool c_flat = !(cmax > cmin), g_flat = !(gmax > gmin);   // "vmax <= vmin -> all 0.0" (:300)
     const float c_den = c_flat ? 1.0f : (cmax - cmin), g_den = g_flat ? 1.0f : (gmax - gmin);
 
-    // ---- fused keys ---------------------------------------------------------------------------------
-    for (int c = tid; c < ncand; c += SEL_THREADS) {
-      const float dn = c_flat ? 0.0f : (cos_in[c] - cmin) / c_den;
-      const float gn = g_flat ? 0.0f : (hop_decay(dist_in[c]) - gmin) / g_den;
-      const long long node = (long long)cand[c];
-      const bool own = node >= p.own_lo && node < p.own_hi;
-      keys[c] = own ? make_key(p.alpha_graph * gn + p.alpha_dense * dn, cand[c]) : 0ull;   // ties on the fused score -> lower node id
+    // ---- fused keys (and their score range / count, for the histogram select) ------------------------------
+    {
+      u32 lo32 = 0xffffffffu, hi32 = 0u; int nv = 0;
+      for (int c = tid; c < ncand; c += SEL_THREADS) {
+        const float dn = c_flat ? 0.0f : (cos_in[c] - cmin) / c_den;
+        const float gn = g_flat ? 0.0f : (hop_decay(dist_in[c]) - gmin) / g_den;
+        const long long node = (long long)cand[c];
+        const bool own = node >= p.own_lo && node < p.own_hi;
+        const u64 key = own ? make_key(p.alpha_graph * gn + p.alpha_dense * dn, cand[c]) : 0ull;   // ties on the fused score -> lower node id
+        keys[c] = key;
+        if (key != 0) { lo32 = min(lo32, (u32)(key >> 32)); hi32 = max(hi32, (u32)(key >> 32)); ++nv; }
+      }
+      lo32 = __reduce_min_sync(kFullMask, lo32); hi32 = __reduce_max_sync(kFullMask, hi32); nv = __reduce_add_sync(kFullMask, nv);
+      if (lane == 0 && nv) { atomicMin(&s_lo32, lo32); atomicMax(&s_hi32, hi32); atomicAdd(&s_valid, nv); }
     }
     __syncthreads();
 
-    // ---- exact k-th key by radix select, then sort the winners ------------------------------------------
+    // ---- k-th key.  Histogram select (as select_merge.cu): ONE pass into 1 024 bins linear in the fused score, the bin b*
+    // of the k-th best from a suffix scan, T = the smallest score in bins >= b*; the `reach` >= k keys with score >= T are
+    // sorted below and the best k emitted.  Mass ties (reach > kp2) take the exact radix select. ----
     u64 kth = 0;
-    if (ncand > p.k) {
+    bool have_kth = s_valid <= p.k;                 // every valid key wins (kth = 0)
+    if (!have_kth) {
+      for (int i = tid; i < FUSE_BINS; i += SEL_THREADS) hist[i] = 0;
+      __syncthreads();
+      const float flo = ordered_to_f32(s_lo32), fhi = ordered_to_f32(s_hi32);
+      const float range = fhi - flo;
+      const float scale = (range > 0.0f && range < CUDART_INF_F) ? (float)(FUSE_BINS - 1) / range : 0.0f;
+      auto bin_of = [&](u64 key) -> int {
+        const int b = (int)((key_score(key) - flo) * scale);
+        return b < FUSE_BINS - 1 ? b : FUSE_BINS - 1;
+      };
+      for (int c = tid; c < ncand; c += SEL_THREADS) { const u64 key = keys[c]; if (key != 0) atomicAdd(&hist[bin_of(key)], 1u); }
+      __syncthreads();
+      if (tid < 32) {                               // lane L owns bins [32 L, 32 L + 32)
+        u32 w[32]; u32 lane_sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 t = reinterpret_cast<const uint4*>(hist + lane * 32)[j];
+          w[4 * j] = t.x; w[4 * j + 1] = t.y; w[4 * j + 2] = t.z; w[4 * j + 3] = t.w;
+          lane_sum += t.x + t.y + t.z + t.w;
+        }
+        u32 suffix = lane_sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_down_sync(kFullMask, suffix, o); if (lane + o < 32) suffix += t; }
+        const u32 above = suffix - lane_sum;
+        if (above < (u32)p.k && (u32)p.k <= suffix) {
+          u32 acc = above;
+#pragma unroll
+          for (int j = 31; j >= 0; --j) {
+            acc += w[j];
+            if (acc >= (u32)p.k) { s_bstar = lane * 32 + j; s_reach = (int)acc; break; }
+          }
+        }
+      }
+      __syncthreads();
+      const int bstar = s_bstar;
+      u32 t32 = 0xffffffffu;
+      for (int c = tid; c < ncand; c += SEL_THREADS) {
+        const u64 key = keys[c];
+        if (key != 0 && bin_of(key) >= bstar) t32 = min(t32, (u32)(key >> 32));
+      }
+      t32 = __reduce_min_sync(kFullMask, t32);
+      if (lane == 0 && t32 != 0xffffffffu) atomicMin(&s_t32, t32);
+      __syncthreads();
+      if (s_reach <= p.kp2) { kth = (u64)s_t32 << 32; have_kth = true; }
+    }
+    // ---- exact k-th key by radix select (mass ties only), then sort the winners ------------------------------------------
+    if (!have_kth) {
       for (int pass = 7; pass >= 0; --pass) {
         const int shift = pass * 8;
         for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
@@ -766,36 +826,41 @@ __global__ void __launch_bounds__(SEL_THREADS) fuse_select_kernel(const ExpandPa
     __syncthreads();
     block_bitonic_desc(sk, p.kp2);
 
-    // ---- emit: winner i is looked up in the candidate list by one warp (k is small) ------------------
+    // ---- emit: every winning candidate finds its rank by binary search of its key in the sorted winners and leaves its
+    // position there; then one thread per winner writes the record.  (A warp-wide scan of the candidate list per winner
+    // was 45 % of this kernel's instructions at ~2 200 candidates.)
     const int nwin = min(min(ncand, p.k), s_nout);
-    for (int i = warp; i < p.k; i += SEL_WARPS) {
+    for (int c = tid; c < ncand; c += SEL_THREADS) {
+      const u64 key = keys[c];
+      if (key >= kth && key != 0) {
+        int lo = 0, hi = nwin;                     // sk[0, nwin) is strictly descending (keys are unique)
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sk[mid] > key) lo = mid + 1; else hi = mid; }
+        if (lo < nwin && sk[lo] == key) wslot[lo] = c;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < p.k; i += SEL_THREADS) {
       const size_t o = (size_t)q * p.k + i;
       float v_score = -CUDART_INF_F, v_gn = 0.0f, v_dn = 0.0f, v_cos = 0.0f;
       long long v_id = -1;
       int v_hop = -1;
       if (i < nwin) {
         const u64 key = sk[i];
-        const u32 node = key_id(key);
-        int slot = -1;
-        for (int base = 0; base < ncand && slot < 0; base += 32) {
-          const int c = base + lane;
-          const u32 hit = __ballot_sync(kFullMask, c < ncand && cand[c] == node);
-          if (hit) slot = base + __ffs(hit) - 1;
-        }
-        const float cv = cos_in[slot];             // warp-uniform address
+        const int slot = wslot[i];
+        const float cv = cos_in[slot];
         const int hd = dist_in[slot];
-        v_score = key_score(key); v_id = (long long)node; v_hop = hd;
+        v_score = key_score(key); v_id = (long long)key_id(key); v_hop = hd;
         v_gn = g_flat ? 0.0f : (hop_decay(hd) - gmin) / g_den;
         v_dn = c_flat ? 0.0f : (cv - cmin) / c_den;
         v_cos = cv;
       }
       if (!xchg) {
-        if (lane == 0) {
-          p.out_scores[o] = v_score; p.out_ids[o] = v_id; p.out_hops[o] = v_hop; p.out_gn[o] = v_gn; p.out_dn[o] = v_dn; p.out_cos[o] = v_cos;
+        p.out_scores[o] = v_score; p.out_ids[o] = v_id; p.out_hops[o] = v_hop; p.out_gn[o] = v_gn; p.out_dn[o] = v_dn; p.out_cos[o] = v_cos;
+      } else {
+        for (int g = 0; g < p.c_out.world; ++g) {    // the winner goes into every rank's output slot
+          const XOut x = xout(comm_slot(p.c_out, g, e_out), p.B, p.k);
+          x.score[o] = v_score; x.ids[o] = v_id; x.hop[o] = v_hop; x.gn[o] = v_gn; x.dn[o] = v_dn; x.cos[o] = v_cos;
         }
-      } else if (lane < p.c_out.world) {           // lane g stores the winner into rank g's output slot
-        const XOut x = xout(comm_slot(p.c_out, lane, e_out), p.B, p.k);
-        x.score[o] = v_score; x.ids[o] = v_id; x.hop[o] = v_hop; x.gn[o] = v_gn; x.dn[o] = v_dn; x.cos[o] = v_cos;
       }
     }
     if (xchg && tid < p.c_out.world) {

@@ -187,6 +187,13 @@ def run_graph(name, V, E, D, B, S, k, steps=40, warmup=8, window=2, random_seeds
     gms, gn = _native.profile_read()
     _native.profile_enable(False)
     gms /= max(gn, 1)
+    # per-launch-site timeline of a few more batches (events around every launch: not part of the timed loop above)
+    _native.profile_timeline(True)
+    for i in range(4):
+        expand_rescore(ix, graph, Q[i % nbatch], seeds[i % nbatch], window, 0.4, 0.2, k, check_status=False)
+    torch.cuda.synchronize()
+    timeline = {name: round(v[0] / 4 * 1000, 1) for name, v in _native.profile_dump().items()}
+    _native.profile_timeline(False)
     per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
     ms = ev[0].elapsed_time(ev[steps]) / steps
     ncand = out["ncand"].float().mean().item()
@@ -195,7 +202,7 @@ def run_graph(name, V, E, D, B, S, k, steps=40, warmup=8, window=2, random_seeds
             "steps": steps, "ms_per_batch": ms, "ms_median": per[len(per) // 2], "ms_min": per[0], "queries_per_s": B / (ms * 1e-3), "avg_candidates": ncand,
             "gather_GBps": gather_bytes / (ms * 1e-3) / 1e9, "hbm_frac_of_measured": gather_bytes / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"],
             "gather_kernel_ms": gms, "gather_kernel_GBps": gather_bytes / (gms * 1e-3) / 1e9 if gms > 0 else None,
-            "overflowed_queries": int((out["status"] != 0).sum().item())}
+            "overflowed_queries": int((out["status"] != 0).sum().item()), "timeline_us_per_batch": timeline}
     print(json.dumps(line), flush=True)
 
 
