@@ -720,6 +720,10 @@ static int search_sharded_host_all_impl(const uint64_t* indexes, const uint64_t*
   }
   const size_t oelems = (size_t)B * k;
   int rc;
+  // H2D + local search (+ peer stores) of every device, issued from the calling thread.  One launch thread per device was
+  // measured on 8 GPUs (profiles/r2_plugin_devices_host_threads_ab.jsonl): batch 1 0.645 -> 0.607 ms, but batch 4096 7.05 ->
+  // 9.74 ms (the eight H2D copies of the queries then start together and contend, instead of each hiding behind the
+  // previous devices' searches) -- not kept.
   for (int g = 0; g < G; ++g) {
     B200R_CUDA_CHECK(cudaSetDevice(ix[g]->device));
     const size_t need = search_workspace(ix[g], B, k, path, nullptr);

@@ -276,6 +276,7 @@ def leg_plugin_single_process(torch, a, world, tdt, Qh, ref_ids, steps, warmup):
     """N > 1, rank 0 only, while the other ranks wait: ONE process drives all N GPUs through the plug-in's engine
     (backend.CudaEngine, what B200RetrievalBackend(devices=[0..N-1]) builds): float32 host queries in, host results out, the
     corpus row-sharded over the devices, exchange + merge inside libb200r (b200r_search_sharded_host_all_f32)."""
+    import numpy as np
     from a_modular_rag_framework_b200.backend import CudaEngine
     from a_modular_rag_framework_b200.sharded import shard_rows
     shards = []
@@ -291,11 +292,20 @@ def leg_plugin_single_process(torch, a, world, tdt, Qh, ref_ids, steps, warmup):
         s, ids = eng.dense_search(Qf[warmup + i], a.k)
     dt = time.perf_counter() - t0
     same = bool((torch.from_numpy(ids) == ref_ids.cpu()).all().item())
+    # one query at a time, the way the reference's orchestrator calls its retriever (app/orchestrator/nodes.py:110-115)
+    q1 = [np.ascontiguousarray(Qf[i % len(Qf)][:1]) for i in range(8)]
+    for i in range(5):
+        eng.dense_search(q1[i % 8], a.k)
+    t1 = time.perf_counter()
+    n1 = 100
+    for i in range(n1):
+        eng.dense_search(q1[i % 8], a.k)
+    b1_ms = (time.perf_counter() - t1) / n1 * 1e3
     del eng, shards
     torch.cuda.empty_cache()
     return {"value": steps * a.batch / dt, "unit": UNIT, "ms_per_step": dt / steps * 1e3, "devices": world,
             "h2d_bytes_per_step": a.batch * a.dim * 4 * world, "d2h_bytes_per_step": a.batch * a.k * 12,
-            "identical_to_the_torchrun_result": same,
+            "identical_to_the_torchrun_result": same, "batch1_ms_per_query_host_to_host": b1_ms,
             "note": "one host thread, N GPUs: float32 host queries, async H2D to every device, rounded to the corpus dtype on the device, "
                     "sharded search + exchange + merge (libb200r), D2H from device 0; not pipelined across batches"}
 
