@@ -2,7 +2,8 @@
 //
 //  * select_lists_kernel: final reduction of the per-unit candidate lists K1/K2 leave in the
 //    workspace -> out_scores/out_ids [B, k].
-//  * merge_topk_kernel: public merge of G per-shard top-k lists (after the NCCL all-gather).
+//  * merge_topk_kernel: public merge of G per-shard top-k lists (b200r_merge_topk*; the shard exchange of comm.cu has its
+//    own merge kernel that first waits for the peers' records).
 // Both implement the reference's ranking rule -- python stable sort, descending, slice
 // (app/modules/retrieval/retrieval_backend.py:371-372, retrieval_adapter.py:129-131) -- over
 // candidates enumerated in id order, i.e. ties go to the lower id.

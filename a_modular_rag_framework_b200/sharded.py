@@ -66,7 +66,7 @@ class PendingResult:
 class ShardedDenseIndex:
     """`local` searches this rank's rows and reports GLOBAL ids (DenseIndex(X_shard, id_base=lo)).
 
-    exchange="abi" (default on CUDA): the C-ABI exchange (comm.ShardComm): the final select kernel of the local search stores
+    exchange="abi" (what "auto" picks for a CUDA DenseIndex): the C-ABI exchange (comm.ShardComm): the final select kernel of the local search stores
     this rank's packed record into every rank's window over NVLink and one merge kernel waits for the records -- no
     NCCL, no collective kernel, no staging copy, no side stream.  torch.distributed is used once, to swap the 128-byte
     window descriptors.  exchange="nccl": packed all_gather_into_tensor + b200r_merge_topk_packed (also what the gloo CPU
@@ -74,11 +74,14 @@ class ShardedDenseIndex:
 
     def __init__(self, local, group: Optional[dist.ProcessGroup] = None,
                  merge_packed: Optional[Callable[[torch.Tensor, int, int, int], Tuple[torch.Tensor, torch.Tensor]]] = None,
-                 exchange: str = "nccl", comm=None):
+                 exchange: str = "auto", comm=None):
         if exchange == "p2p":        # round-1 name of the fused exchange
             exchange = "abi"
+        if exchange == "auto":       # the library's exchange whenever the local engine is a CUDA index; collectives otherwise
+            dev = getattr(local, "device", None)
+            exchange = "abi" if (hasattr(local, "search_sharded_begin") and getattr(dev, "type", None) == "cuda") else "nccl"
         if exchange not in ("nccl", "abi"):
-            raise ValueError("exchange must be 'abi' or 'nccl'")
+            raise ValueError("exchange must be 'auto', 'abi' or 'nccl'")
         self.exchange = exchange
         self.comm = comm
         self._comm_cap = (0, 0)

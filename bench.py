@@ -408,7 +408,9 @@ def verify_graph_leg(torch, dist, out, Q, seeds, row_ptr, col, Xg, glo, ghi, V, 
     sel = [q for q in sel if q < Q.shape[0]]
     rp = row_ptr.cpu().numpy() if rank == 0 else None
     ci = col.cpu().numpy() if rank == 0 else None
+    t_cpu = time.perf_counter()
     dists = [O.bfs_expand(rp, ci, seeds[q].cpu().numpy(), window) for q in sel] if rank == 0 else None
+    t_cpu = time.perf_counter() - t_cpu            # the oracle's BFS (expand_qmatch_neighbors restated), one host core
     if world > 1:
         box = [dists]
         dist.broadcast_object_list(box, src=0)
@@ -434,9 +436,11 @@ def verify_graph_leg(torch, dist, out, Q, seeds, row_ptr, col, Xg, glo, ghi, V, 
         d = dists[j]
         cand = sorted(d)
         Xc = np.stack([rows[c] for c in cand]).astype(np.float64)
+        t1 = time.perf_counter()
         cos = O.score_matrix(Q[q].float().cpu().numpy()[None].astype(np.float64), Xc)[0]
         dense = dict(zip(cand, cos.tolist()))
         full = O.fuse_and_rank(dense, {c: O.decay(d[c]) for c in cand}, 0.4, 0.2, len(cand))
+        t_cpu += time.perf_counter() - t1          # + re-score of the candidates (numpy) + min-max fusion + ranking
         ref_of = {t[0]: t[1] for t in full}
         scale = max(1e-30, float(np.max(np.abs(cos))))
         rng_ = float(cos.max() - cos.min())
@@ -456,6 +460,11 @@ def verify_graph_leg(torch, dist, out, Q, seeds, row_ptr, col, Xg, glo, ghi, V, 
                 res["ids_equal"] = False
                 if abs(ref_of[nid] - full[i][1]) > tol_f:       # not a near-tie
                     res["ok"] = False
+    if sel and t_cpu > 0:
+        res["cpu_reference"] = {"value": len(sel) / t_cpu, "unit": "queries/s", "cores": 1, "kind": "port",
+                                "sample": f"{len(sel)} queries of the batch: BFS + decay in Python over the host CSR, numpy fp64 re-score of "
+                                          f"the candidates, min-max fusion, ranking (oracle port of graph_utils.py:58-129 + "
+                                          f"retrieval_backend.py:296-372; rows already gathered)"}
     return res
 
 

@@ -183,7 +183,8 @@ int b200r_mmr_diversify(uint64_t index, const int64_t* cand_ids, const float* ca
                         float lambda_weight, int64_t* out_ids, float* out_scores, int32_t* out_pos, void* stream);
 
 /* ---- merge of per-shard top-k lists ----------------------------------------------------------
- * The same stable-sort rule applied to the union of G lists (one per GPU after the NCCL all-gather):
+ * The same stable-sort rule applied to the union of G lists (one per GPU, however the host gathered them -- the
+ * library's own exchange, b200r_search_sharded*, merges without this call):
  * cand_scores/cand_ids [G, B, kin] -> out [B, k], (score desc, id asc); ids < 0 are padding.
  */
 int b200r_merge_topk(int device, const float* cand_scores, const int64_t* cand_ids, int32_t G, int32_t B,

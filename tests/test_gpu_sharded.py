@@ -59,7 +59,8 @@ def _nccl_worker(rank, world, port, ret):
         Qn = O.bf16_bits_to_f32(O.f32_to_bf16_bits(rng.standard_normal((B, D)).astype(np.float32)))
         lo, hi = shard_rows(N, world, rank)
         X = torch.from_numpy(Xn[lo:hi]).to(dev).to(torch.bfloat16)
-        sh = ShardedDenseIndex(DenseIndex(X, id_base=lo))
+        sh = ShardedDenseIndex(DenseIndex(X, id_base=lo), exchange="nccl")      # the collective fallback first
+        assert ShardedDenseIndex(sh.local).exchange == "abi"                    # what "auto" picks for a CUDA index
         s, i = sh.search(torch.from_numpy(Qn).to(dev).to(torch.bfloat16), k)
         S = O.score_matrix(Qn, Xn)
         for b in range(B):
