@@ -1,7 +1,7 @@
 """The plug-in engine on ALL visible GPUs from ONE process (what B200RetrievalBackend(devices=[...]) builds): float32 host
 queries in, host results out, corpus row-sharded over the devices (b200r_search_sharded_host_all_f32).  Reports the
 host-to-host latency of one call at batch 1 / 16 / 4096 -- batch 1 is how the reference's orchestrator calls its retriever
-(app/orchestrator/nodes.py:110-115).  B200R_HOST_THREADS=0 makes the calling thread launch every device's kernels (A/B).
+(app/orchestrator/nodes.py:110-115).
 
     python scripts/bench_plugin_devices.py [--rows 10000000] [--dim 768] [--k 100]
 """
@@ -34,7 +34,7 @@ def main():
         shards.append(X)
     eng = CudaEngine.from_shards(shards, a.rows, "cos", max_batch=4096, max_k=a.k)
     rng = np.random.default_rng(0)
-    out = {"devices": G, "rows": a.rows, "dim": a.dim, "k": a.k, "host_threads": os.environ.get("B200R_HOST_THREADS", "1")}
+    out = {"devices": G, "rows": a.rows, "dim": a.dim, "k": a.k}
     for B, reps in ((1, 300), (16, 300), (4096, 10)):
         Qs = [rng.standard_normal((B, a.dim)).astype(np.float32) for _ in range(4)]
         for i in range(3):
