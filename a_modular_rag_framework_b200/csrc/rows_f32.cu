@@ -10,8 +10,9 @@
 //     product of two 11-bit significands is exact; the fp32 accumulation is spread over 8 partial accumulators per tile
 //     (see RF_PARTS) that the epilogue adds with round-to-nearest;
 //   * operand layout is the streaming one of rows_i8.cu: the 128 corpus rows of a tile are the MMA's M (TMEM lanes), tiles of
-//     [128 rows x 128 bytes = 32 floats] arrive by TMA (SWIZZLE_128B) straight from the fp32 corpus into a ring that carries
-//     corpus data only; four CONVERTER warps split each arrived slice in shared memory (hi in place, mid into a
+//     [128 rows x 128 bytes = 32 floats] arrive by TMA (SWIZZLE_128B) straight from the fp32 corpus; a ring STAGE carries up
+//     to three such K blocks (48 KB of corpus) plus the matching query slices under ONE barrier, because what bounds this
+//     kernel is the number of barrier hand-offs per byte (see rows_f32_kps); four CONVERTER warps split each arrived slice in shared memory (hi in place, mid into a
 //     double-buffered side tile; 15 instructions per 4 elements, a sixth of the SM's issue slots at HBM speed) and hand it to
 //     the MMA warp; the hi and mid planes of the pass's 16 queries (split once per search, 96 KB at D = 768, L2-resident) are
 //     streamed slice by slice with the corpus, which leaves shared memory for an 8-deep ring at any D;
@@ -53,6 +54,7 @@ constexpr u32 RF_TF32_MASK = 0xffffe000u;
 struct RowsF32Params {
   int B, k, D, num_kb, stages, mids;          // raw ring stages, mid side buffers
   int backoff;             // 1: waiting epilogue warps sleep between polls
+  int kps;                 // K blocks (32-float slices) per ring stage / barrier hand-off, 1..4 (see rows_f32_kps; selects the instantiation)
   int store_hi;            // 1: the converters also write the truncated hi piece back in place (see rows_f32_store_hi)
   int q0;                  // this launch serves queries [q0, min(B, q0 + 16))
   long long N;
@@ -110,7 +112,7 @@ __device__ __forceinline__ void tmem_st32(u32 taddr, const u32* v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <bool MID_TMEM>
+template <bool MID_TMEM, int KPS>
 __global__ void __launch_bounds__(RF_THREADS, 1)
 rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, const RowsF32Params p) {
   constexpr int RF_PARTS = MID_TMEM ? RF_PARTS_TMEM : RF_PARTS_SMEM;
@@ -119,11 +121,11 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const u32 raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  // ring stage = [128 x 128 B corpus slice, raw -> hi in place | 32 x 128 B query slice: hi rows 0..15, mid rows 16..31].
+  // ring stage = KPS x [128 x 128 B corpus slice] followed by KPS x [32 x 128 B query slice: hi rows 0..15, mid rows 16..31].
   // The query planes (2 x 16 x D floats, L2-resident) are streamed with the corpus instead of being kept in shared memory:
-  // that leaves room for an 8-deep ring (128 KB of corpus reads in flight per SM) at any D.
+  // that leaves 144-200 KB of corpus reads in flight per SM at any D.
   uint8_t* smem_x = smem;                                         // [stages][20 KB]
-  uint8_t* smem_m = smem_x + (size_t)p.stages * RF_RING_BYTES;    // [mids][128 x 128 B] mid
+  uint8_t* smem_m = smem_x + (size_t)p.stages * KPS * RF_RING_BYTES;    // [mids][128 x 128 B] mid
   uint8_t* tail = smem_m + (MID_TMEM ? (size_t)0 : (size_t)p.mids * RF_STAGE_BYTES);
   u32* smem_hist = reinterpret_cast<u32*>(tail);                // [4][256]
   float* thr_s = reinterpret_cast<float*>(smem_hist + 4 * 256); // [4][16]
@@ -141,6 +143,10 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
+  constexpr int kps = KPS;                                     // K blocks (32-float slices) per ring stage = per barrier hand-off
+  const int num_kp = (p.num_kb + kps - 1) / kps;               // stages (hand-offs) per tile
+  constexpr size_t stage_bytes = (size_t)kps * RF_RING_BYTES;  // [kps corpus slices | kps query slices]
+  constexpr size_t q_off = (size_t)kps * RF_STAGE_BYTES;       // query slices start behind the corpus slices of the stage
   constexpr u32 TMEM_COLS = 512;
 
   if (threadIdx.x == 0) {
@@ -168,11 +174,16 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int t0 = p.tile_begin + u * p.tiles_per_chunk;
         const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
         for (int t = t0; t < t1; ++t) {
-          for (int kb = 0; kb < p.num_kb; ++kb) {
+          for (int kp = 0; kp < num_kp; ++kp) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], RF_RING_BYTES);
-            tma_load_2d(smem_x + (size_t)stage * RF_RING_BYTES, &tmap_x, &full_bar[stage], kb * RF_BK, t * RF_ROWS, kEvictFirst);
-            tma_load_2d(smem_x + (size_t)stage * RF_RING_BYTES + RF_STAGE_BYTES, &tmap_q, &full_bar[stage], kb * RF_BK, 0, kEvictLast);
+            mbar_expect_tx(&full_bar[stage], (u32)stage_bytes);
+            uint8_t* sb = smem_x + (size_t)stage * stage_bytes;
+#pragma unroll
+            for (int h = 0; h < kps; ++h) {          // a K block past D is wholly out of bounds: TMA zero-fills it
+              const int kb = kp * kps + h;
+              tma_load_2d(sb + (size_t)h * RF_STAGE_BYTES, &tmap_x, &full_bar[stage], kb * RF_BK, t * RF_ROWS, kEvictFirst);
+              tma_load_2d(sb + q_off + (size_t)h * RF_Q_KB_BYTES, &tmap_q, &full_bar[stage], kb * RF_BK, 0, kEvictLast);
+            }
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -191,23 +202,29 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const u32 acc = tile_iter % RF_ACC;
           mbar_wait(&tmem_empty_bar[acc], ((tile_iter / RF_ACC) & 1) ^ 1);
           tc_fence_after();
-          for (int kb = 0; kb < p.num_kb; ++kb) {
-            const u32 tmem_d = tmem_base + acc * RF_ACC_STRIDE + (u32)(kb % RF_PARTS) * RF_PART_COLS;    // this slice's partial accumulator
-            mbar_wait(&conv_bar[stage], phase);          // the converters have split this slice (and fenced the async proxy)
+          for (int kp = 0; kp < num_kp; ++kp) {
+            mbar_wait(&conv_bar[stage], phase);          // the converters have split this stage (and fenced the async proxy)
             tc_fence_after();
-            const u64 x_hi = make_smem_desc(smem_u32(smem_x + (size_t)stage * RF_RING_BYTES));
-            const u64 x_mid = make_smem_desc(smem_u32(smem_m + (size_t)m * RF_STAGE_BYTES));
-            const u64 q_all = make_smem_desc(smem_u32(smem_x + (size_t)stage * RF_RING_BYTES + RF_STAGE_BYTES));   // 32 rows: q_hi then q_mid
+            const uint8_t* sb = smem_x + (size_t)stage * stage_bytes;
 #pragma unroll
-            for (int kk = 0; kk < RF_BK / 8; ++kk) {      // K = 8 tf32 = 32 bytes per instruction
-              // x_hi . [q_hi ; q_mid] -> 32 columns, then x_mid . q_hi onto the first 16
-              umma_tf32(tmem_d, x_hi + (u64)(kk * 2), q_all + (u64)(kk * 2), p.idesc32, (kb >= RF_PARTS || kk != 0) ? 1u : 0u);
-              if constexpr (MID_TMEM) umma_tf32_ts(tmem_d, tmem_base + RF_MID_TMEM_COL0 + (u32)m * 32u + (u32)kk * 8u, q_all + (u64)(kk * 2), p.idesc, 1u);
-              else umma_tf32(tmem_d, x_mid + (u64)(kk * 2), q_all + (u64)(kk * 2), p.idesc, 1u);
+            for (int h = 0; h < kps; ++h) {
+              const int kb = kp * kps + h;
+              if (kb >= p.num_kb) break;                   // zero-filled tail block of an odd D/32: nothing to add
+              const u32 tmem_d = tmem_base + acc * RF_ACC_STRIDE + (u32)(kb % RF_PARTS) * RF_PART_COLS;    // this slice's partial accumulator
+              const u64 x_hi = make_smem_desc(smem_u32(sb + (size_t)h * RF_STAGE_BYTES));
+              const u64 x_mid = make_smem_desc(smem_u32(smem_m + (size_t)m * RF_STAGE_BYTES));
+              const u64 q_all = make_smem_desc(smem_u32(sb + q_off + (size_t)h * RF_Q_KB_BYTES));   // 32 rows: q_hi then q_mid
+#pragma unroll
+              for (int kk = 0; kk < RF_BK / 8; ++kk) {      // K = 8 tf32 = 32 bytes per instruction
+                // x_hi . [q_hi ; q_mid] -> 32 columns, then x_mid . q_hi onto the first 16
+                umma_tf32(tmem_d, x_hi + (u64)(kk * 2), q_all + (u64)(kk * 2), p.idesc32, (kb >= RF_PARTS || kk != 0) ? 1u : 0u);
+                if constexpr (MID_TMEM) umma_tf32_ts(tmem_d, tmem_base + RF_MID_TMEM_COL0 + (u32)(m * kps + h) * 32u + (u32)kk * 8u, q_all + (u64)(kk * 2), p.idesc, 1u);
+                else umma_tf32(tmem_d, x_mid + (u64)(kk * 2), q_all + (u64)(kk * 2), p.idesc, 1u);
+              }
             }
             umma_commit(&empty_bar[stage]);
             umma_commit(&mid_empty_bar[m]);
-            if (kb == p.num_kb - 1) umma_commit(&tmem_full_bar[acc]);
+            if (kp == num_kp - 1) umma_commit(&tmem_full_bar[acc]);
             if (++m == p.mids) m = 0;
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
@@ -225,23 +242,26 @@ rows_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int t0 = p.tile_begin + u * p.tiles_per_chunk;
       const int t1 = min(p.tile_end, t0 + p.tiles_per_chunk);
       for (int t = t0; t < t1; ++t) {
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&mid_empty_bar[m], mphase ^ 1u);                 // the MMAs that read this mid buffer `mids` slices ago retired
+        for (int kp = 0; kp < num_kp; ++kp) {
+          mbar_wait(&mid_empty_bar[m], mphase ^ 1u);                 // the MMAs that read this mid buffer `mids` stages ago retired
           mbar_wait(&full_bar[stage], phase);
           if constexpr (MID_TMEM) {
-            // thread = corpus row (the TMEM lane its warp may address): its 128 bytes, un-swizzled chunk by chunk
+            // thread = corpus row (the TMEM lane its warp may address): its 128 bytes per K block, un-swizzled chunk by chunk
             const int row = (warp_idx & 3) * 32 + lane;
-            const uint8_t* rp = smem_x + (size_t)stage * RF_RING_BYTES + (size_t)row * 128;
-            u32 r[32];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint4 v = *reinterpret_cast<const uint4*>(rp + ((c ^ (row & 7)) << 4));
-              const u32 w[4] = {v.x, v.y, v.z, v.w};
+            for (int h = 0; h < kps; ++h) {
+              const uint8_t* rp = smem_x + (size_t)stage * stage_bytes + (size_t)h * RF_STAGE_BYTES + (size_t)row * 128;
+              u32 r[32];
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                r[c * 4 + e] = __float_as_uint(__uint_as_float(w[e]) - __uint_as_float(w[e] & RF_TF32_MASK)) & RF_TF32_MASK;
+              for (int c = 0; c < 8; ++c) {
+                const uint4 v = *reinterpret_cast<const uint4*>(rp + ((c ^ (row & 7)) << 4));
+                const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  r[c * 4 + e] = __float_as_uint(__uint_as_float(w[e]) - __uint_as_float(w[e] & RF_TF32_MASK)) & RF_TF32_MASK;
+              }
+              tmem_st32(tmem_base + ((u32)((warp_idx & 3) * 32) << 16) + RF_MID_TMEM_COL0 + (u32)(m * kps + h) * 32u, r);
             }
-            tmem_st32(tmem_base + ((u32)((warp_idx & 3) * 32) << 16) + RF_MID_TMEM_COL0 + (u32)m * 32u, r);
             tmem_st_wait();
             tc_fence_before();
           } else {
@@ -375,19 +395,35 @@ static bool rows_f32_mid_tmem() {
   static const bool v = [] { const char* e = getenv("B200R_F32_MID_TMEM"); return !(e && e[0] == '0'); }();
   return v;
 }
-static int rows_f32_mids() {
-  if (rows_f32_mid_tmem()) return RF_MID_TMEM_BUFS;
+// K blocks (32-float slices) per ring stage = per barrier hand-off (TMEM variant).  The kernel is bound by the serial chain
+// of hand-offs per slice (TMA -> converters -> MMA thread -> commit -> release), not by HBM, shared memory or the tensor
+// pipe: with 16 KB per hand-off it streams 5 M x 768 fp32 in 2.98 ms (0.79 of the measured copy bandwidth), with 32 KB in
+// 2.49 ms (0.94), with 48 KB in 2.43 ms (0.97), with 64 KB (only two stages fit) in 2.58 ms (0.91) -- same box, back to
+// back (profiles/r2_f32_kblocks_per_stage.jsonl).  Default: 3, or 2 when D/32 is even but not a multiple of 3 (a stage whose
+// tail K blocks lie past D still moves zero-filled boxes into shared memory).  B200R_F32_KPS = 1..4 overrides.
+static int rows_f32_kps(int D) {
+  static const int env = [] { const char* e = getenv("B200R_F32_KPS"); const int k = e ? atoi(e) : 0; return (k >= 1 && k <= 4) ? k : 0; }();
+  if (!rows_f32_mid_tmem()) return 1;
+  if (env) return env;
+  const int num_kb = (D + RF_BK - 1) / RF_BK;
+  if (num_kb <= 2) return num_kb;
+  if (num_kb % 3 == 0) return 3;
+  return (num_kb % 2 == 0) ? 2 : 3;
+}
+static int rows_f32_mids(int D) {
+  // TMEM variant: buffers of 32 x kps columns behind the 256 accumulator columns (<= 256 more)
+  if (rows_f32_mid_tmem()) { const int fit = 8 / rows_f32_kps(D); return fit < RF_MID_TMEM_BUFS ? fit : RF_MID_TMEM_BUFS; }
   static const int m = [] { const char* e = getenv("B200R_F32_MIDS"); const int v = e ? atoi(e) : 3; return (v >= 2 && v <= 4) ? v : 3; }();
   return m;
 }
-static size_t rows_f32_smem_bytes(int stages) {
-  return 1024 + (size_t)stages * RF_RING_BYTES + (rows_f32_mid_tmem() ? 0 : (size_t)rows_f32_mids() * RF_STAGE_BYTES) + 4 * 256 * 4 +
+static size_t rows_f32_smem_bytes(int stages, int D) {
+  return 1024 + (size_t)stages * rows_f32_kps(D) * RF_RING_BYTES + (rows_f32_mid_tmem() ? 0 : (size_t)rows_f32_mids(D) * RF_STAGE_BYTES) + 4 * 256 * 4 +
          (size_t)4 * RF_NQ * (4 + 8 + 4) + (3 * RF_MAX_STAGES + 4 + 2 * RF_ACC + 2) * 8 + 16;
 }
-static int rows_f32_stages_for(int) {
+static int rows_f32_stages_for(int D) {
   int stages = RF_MAX_STAGES;
-  while (stages >= 3 && rows_f32_smem_bytes(stages) > 227 * 1024) --stages;
-  return stages >= 3 ? stages : 0;
+  while (stages >= 2 && rows_f32_smem_bytes(stages, D) > 227 * 1024) --stages;
+  return stages >= 2 ? stages : 0;
 }
 
 int rows_f32_tile_rows() { return RF_ROWS; }
@@ -424,7 +460,8 @@ int launch_rows_f32(const Index* ix, const CUtensorMap* tmap_q, int group, const
   p.q0 = group * RF_NQ;
   p.num_kb = (ix->D + RF_BK - 1) / RF_BK;
   p.stages = rows_f32_stages_for(ix->D);
-  p.mids = rows_f32_mids();
+  p.mids = rows_f32_mids(ix->D);
+  p.kps = rows_f32_kps(ix->D);
   p.store_hi = rows_f32_store_hi();
   { static const int b = [] { const char* e = getenv("B200R_F32_BACKOFF"); return (e && e[0] == '0') ? 0 : 1; }(); p.backoff = b; }
   if (!p.stages) { set_error("fp32 tensor path: D=%d does not fit", ix->D); return B200R_EINVAL; }
@@ -438,15 +475,19 @@ int launch_rows_f32(const Index* ix, const CUtensorMap* tmap_q, int group, const
   // instruction descriptor: D = f32 (1 << 4), A = B = tf32 (2 << 7, 2 << 10), K-major both, N >> 3, M >> 4
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((u32)(RF_NQ >> 3) << 17) | ((u32)(RF_ROWS >> 4) << 24);
   p.idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((u32)((2 * RF_NQ) >> 3) << 17) | ((u32)(RF_ROWS >> 4) << 24);
-  const size_t smem = rows_f32_smem_bytes(p.stages);
+  const size_t smem = rows_f32_smem_bytes(p.stages, ix->D);
   const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
-  if (rows_f32_mid_tmem()) {
-    B200R_CUDA_CHECK(cudaFuncSetAttribute(rows_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rows_f32_kernel<true><<<grid, RF_THREADS, smem, st>>>(*tmap_q, ix->tmap_x_f32, p);
-  } else {
-    B200R_CUDA_CHECK(cudaFuncSetAttribute(rows_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rows_f32_kernel<false><<<grid, RF_THREADS, smem, st>>>(*tmap_q, ix->tmap_x_f32, p);
-  }
+#define B200R_F32_LAUNCH(TMEM, KPS)                                                                                              \
+  do {                                                                                                                         \
+    B200R_CUDA_CHECK(cudaFuncSetAttribute(rows_f32_kernel<TMEM, KPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    rows_f32_kernel<TMEM, KPS><<<grid, RF_THREADS, smem, st>>>(*tmap_q, ix->tmap_x_f32, p);                                     \
+  } while (0)
+  if (!rows_f32_mid_tmem()) B200R_F32_LAUNCH(false, 1);
+  else if (p.kps == 4) B200R_F32_LAUNCH(true, 4);
+  else if (p.kps == 3) B200R_F32_LAUNCH(true, 3);
+  else if (p.kps == 2) B200R_F32_LAUNCH(true, 2);
+  else B200R_F32_LAUNCH(true, 1);
+#undef B200R_F32_LAUNCH
   count_launch();
   B200R_CUDA_CHECK(cudaGetLastError());
   return B200R_OK;
