@@ -24,6 +24,18 @@ def test_shard_rows_cover_exactly():
             assert all(lo <= hi for lo, hi in spans)
 
 
+def test_exchange_auto_picks_collectives_without_a_cuda_index():
+    """exchange="auto": the library's peer-memory exchange needs a CUDA DenseIndex; any other local engine (these CPU
+    stand-ins) gets the collective path, and an unknown name is rejected."""
+    local = type("L", (), {"search": lambda *a, **k: None})()
+    assert ShardedDenseIndex(local, merge_packed=lambda *a: None).exchange == "nccl"
+    cuda_like = type("C", (), {"search_sharded_begin": lambda *a, **k: None, "device": torch.device("cuda", 0)})()
+    assert ShardedDenseIndex(cuda_like).exchange == "abi"
+    assert ShardedDenseIndex(cuda_like, exchange="p2p").exchange == "abi"          # round-1 name
+    with pytest.raises(ValueError):
+        ShardedDenseIndex(local, exchange="smoke-signals")
+
+
 class _OracleLocal:
     def __init__(self, X, id_base):
         self.X, self.id_base = X, id_base
